@@ -1,0 +1,101 @@
+"""oracle/refrun.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/_ref/libulref_{k1,k31,kMD}.so (the unmodified reference UL path, see
+oracle/ref_wrap.cpp and oracle/Makefile).  Only tests/, tests/golden/make_golden.py and bench.py's
+`--impl reference` / cpu_baseline leg may import this.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIELDS = {"x": 0, "V": 1, "A": 2, "ea": 3, "cA": 4, "cB": 5, "cC": 6, "fa_u": 7, "X_prev": 8, "V_hlf": 9}
+WIDTH = {"x": 3, "V": 3, "A": 3, "ea": 6, "cA": 1, "cB": 1, "cC": 1, "fa_u": 3, "X_prev": 3, "V_hlf": 3}
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def ref_available(variant="k1"):
+    return os.path.exists(os.path.join(HERE, "_ref", "libulref_%s.so" % variant))
+
+
+def _load(variant):
+    lib = C.CDLL(os.path.join(HERE, "_ref", "libulref_%s.so" % variant))
+    lib.ulref_create.restype = C.c_void_p
+    lib.ulref_create.argtypes = [C.c_int, _dp, C.c_int, _ip, C.c_int, _dp, C.c_int, _ip]
+    lib.ulref_destroy.argtypes = [C.c_void_p]
+    lib.ulref_srand.argtypes = [C.c_uint]
+    lib.ulref_rand.restype = C.c_int
+    lib.ulref_default_kint.restype = C.c_double
+    lib.ulref_get.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+    lib.ulref_set.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+    lib.ulref_onering.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, C.c_int]
+    lib.ulref_boundary_flags.argtypes = [C.c_void_p, C.c_int, _ip]
+    lib.ulref_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.ulref_eval_element.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, C.c_double, _dp, _dp, _dp]
+    lib.ulref_force_field.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp, _dp]
+    return lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+class RefSim:
+    """The reference UL step (El Topo off) on one cell + one substrate mesh."""
+
+    def __init__(self, variant, xyz_c, tri_c, xyz_s, tri_s):
+        self.variant = variant
+        self.lib = _load(variant)
+        xyz_c = np.ascontiguousarray(xyz_c, dtype=np.float64); xyz_s = np.ascontiguousarray(xyz_s, dtype=np.float64)
+        tri_c = np.ascontiguousarray(tri_c, dtype=np.int32); tri_s = np.ascontiguousarray(tri_s, dtype=np.int32)
+        self.nn = (len(xyz_c), len(xyz_s)); self.ne = (len(tri_c), len(tri_s))
+        self.h = self.lib.ulref_create(len(xyz_c), _d(xyz_c), len(tri_c), tri_c.ctypes.data_as(_ip),
+                                       len(xyz_s), _d(xyz_s), len(tri_s), tri_s.ctypes.data_as(_ip))
+        self.kint = self.lib.ulref_default_kint()          # what main.cpp passes to updateFA
+        self.kint_force = 1000.0 if variant == "k1" else 31000.0   # hard-coded in updateForces_Explicit
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ulref_destroy(self.h); self.h = None
+
+    def srand(self, seed):
+        self.lib.ulref_srand(seed)
+
+    def get(self, surface, field):
+        n = self.nn[surface]; w = WIDTH[field]
+        out = np.empty((n, w) if w > 1 else (n,), dtype=np.float64)
+        rc = self.lib.ulref_get(self.h, surface, FIELDS[field], _d(out)); assert rc == 0
+        return out
+
+    def set(self, surface, field, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64); assert arr.size == self.nn[surface] * WIDTH[field]
+        rc = self.lib.ulref_set(self.h, surface, FIELDS[field], _d(arr)); assert rc == 0
+
+    def step(self, dt, t_curr, subs_scale=0.0):
+        self.lib.ulref_step(self.h, dt, t_curr, self.kint, subs_scale)
+
+    def boundary_flags(self, surface):
+        out = np.empty(self.nn[surface], dtype=np.int32)
+        self.lib.ulref_boundary_flags(self.h, surface, out.ctypes.data_as(_ip)); return out
+
+    def onering(self, surface, v):
+        out = np.empty(64, dtype=np.int32)
+        n = self.lib.ulref_onering(self.h, surface, v, out.ctypes.data_as(_ip), 64); return out[:n].copy()
+
+    def force_field(self, which, dt, t_curr):
+        names = {"Res_cell": 0, "F_FA": 1, "F_AP": 2, "F_bend": 3, "F_area": 4, "Res_subs": 5, "F_FA_subs": 6}
+        w = names[which]; surf = 1 if w >= 5 else 0; n = self.nn[surf]
+        out = np.zeros((n, 3)); mm = np.zeros(n); rea = np.zeros((n, 6)); aux = np.zeros(4)
+        rc = self.lib.ulref_force_field(self.h, w, dt, t_curr, self.kint_force, _d(out), _d(mm), _d(rea), _d(aux)); assert rc == 0
+        return {"F": out, "MM": mm, "Res_ea": rea, "area": aux}
+
+
+def ref_eval_element(variant, mat, X, x, ea, cA, cC, dt, centroid, time):
+    lib = _load(variant)
+    X = np.ascontiguousarray(X, dtype=np.float64); x = np.ascontiguousarray(x, dtype=np.float64)
+    ea = np.ascontiguousarray(ea, dtype=np.float64); cA = np.ascontiguousarray(cA, dtype=np.float64)
+    cC = np.ascontiguousarray(cC, dtype=np.float64); cen = np.ascontiguousarray(centroid, dtype=np.float64)
+    Re = np.zeros(9); Rea = np.zeros(18); MMe = np.zeros(3)
+    lib.ulref_eval_element(mat, _d(X), _d(x), _d(ea), _d(cA), _d(cC), dt, _d(cen), time, _d(Re), _d(Rea), _d(MMe))
+    return Re, Rea, MMe
