@@ -1,0 +1,150 @@
+/* wcfe.h -- C ABI of libwcfe.so: the explicit updated-Lagrangian (UL) step of wholeCellFE's cellBP on B200.
+ *
+ * Drop-in boundary.  The reference has no plugin loader: the boundary is the
+ * link-time free-function interface between cellBP/main.cpp and cellBP/UL_growth_explicit.cpp, whose
+ * prototypes main.cpp re-declares by hand (wholeCellFE_k1/cellBP/main.cpp:69-87) and calls from
+ * advance_sim() (main.cpp:168-418).  This header is the flat C surface a binding would target (same
+ * style as El Topo's own C API, eltopo3d/eltopo.h:150-268: flattened `const double* xyz[3N]`,
+ * `const int* tri[3M]`, caller-owned buffers, int status codes, no exceptions).  The C++ adapter
+ * wholecellfe_b200/csrc/ul_adapter.cpp defines the reference's five C++ symbols on top of it so that
+ * the unmodified reference main.cpp links against libwcfe instead of UL_growth_explicit.o
+ * (INTEGRATION.md).
+ *
+ * Conventions: all host arrays are array-of-structs exactly as the reference stores them
+ * (std::vector<Vec3d> == 3 contiguous doubles per node, common/vec.h:22-25; strains 6 per node in the
+ * order xx,yy,zz,xy,xz,yz, UL_growth_explicit.cpp:784-786,886).  Device state is struct-of-arrays FP64
+ * and never leaves the GPU unless asked for.  Every entry point returns WCFE_OK (0) or a negative
+ * error code; wcfe_last_error() gives the text.  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with WCFE_ERR_CUDA.
+ */
+#ifndef WCFE_H
+#define WCFE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WCFE_OK 0
+#define WCFE_ERR_ARG (-1)          /* bad argument / state (e.g. no mesh uploaded) */
+#define WCFE_ERR_CUDA (-2)         /* CUDA runtime error, or no device */
+#define WCFE_ERR_UNSUPPORTED (-3)  /* a parameter combination the GPU path does not implement */
+#define WCFE_ERR_CAPACITY (-4)     /* a device-side table overflowed (see wcfe_last_error) */
+#define WCFE_ERR_NUMERIC (-5)      /* NaN/Inf sentinel tripped */
+
+#define WCFE_CELL 0
+#define WCFE_SUBS 1
+
+/* variants == which reference source tree: wholeCellFE_k1 / _k31 / _kMD */
+#define WCFE_K1 0
+#define WCFE_K31 1
+#define WCFE_KMD 2
+
+/* state fields (widths in doubles per node) */
+#define WCFE_F_X 0      /* 3  positions                DynamicSurface::pm_positions  */
+#define WCFE_F_V 1      /* 3  velocity                 m_Vt   (dynamicsurface.h:234-264) */
+#define WCFE_F_A 2      /* 3  acceleration             m_At   */
+#define WCFE_F_EA 3     /* 6  Euler-Almansi strain     m_eat  */
+#define WCFE_F_CA 4     /* 1  free integrin conc.      m_cA   (cell only) */
+#define WCFE_F_CB 5     /* 1                           m_cB   (cell only; never read by the UL path) */
+#define WCFE_F_CC 6     /* 1  bound integrin fraction  m_cC   (cell only) */
+#define WCFE_F_FAU 7    /* 3  integrin anchor vector   m_fau  (cell only) */
+#define WCFE_F_XPREV 8  /* 3  positions at the start of the last step (read-only) */
+
+/* discrete state of the last step, one int per cell node (parity gates of SURVEY.md 8d) */
+#define WCFE_D_LOC_BOND 0         /* containing substrate triangle in updateFA (last match), -1 none; debug mode only */
+#define WCFE_D_LOC_FORCE_CNT 1    /* number of containing triangles in calculateForce_FA_subs */
+#define WCFE_D_LOC_FORCE_FIRST 2  /* lowest-index containing triangle, -1 none */
+#define WCFE_D_AP_FIRE 3          /* actin-polymerisation Poisson event fired (boundary vertices) */
+#define WCFE_D_FA_RESET 4         /* anchor reset branch of UL_growth_explicit.cpp:2107-2111 */
+#define WCFE_D_CC_CLAMP 5         /* c_C < 0 clamp (UL:2095) */
+
+/* RNG modes for the actin-polymerisation draw (UL_growth_explicit.cpp:1525) */
+#define WCFE_RNG_GLIBC_REPLAY 0   /* replays glibc rand() after srand(seed): bit-identical to the (patched) reference */
+#define WCFE_RNG_PHILOX 1         /* counter-based Philox4x32-10 keyed by (seed, step, boundary ordinal) */
+
+/* Everything the reference hard-codes in source, with its literal values as defaults
+ * (wcfe_default_params).  File:line are in wholeCellFE_k1/cellBP/UL_growth_explicit.cpp. */
+typedef struct wcfe_params {
+    int law;             /* 0 linear integrin spring, 1 piecewise-linear MD table (kMD :1204-1214) */
+    double kint_force;   /* kint inside updateForces_Explicit (:458,:559): 1000 / 31000 */
+    double kint_bond;    /* kint main.cpp hands to updateFA (main.cpp:350-354): 1000 / 31000 / -1 */
+    double subs_scale;   /* the literal `0*` of main.cpp:299; only 0 is implemented on the GPU */
+    double mu_cell, mu_subs;                  /* :724,:727 */
+    double t_act_rate, t_act_max, t_act_t1;   /* :744-756  t<2 ? 200 t : 400 */
+    double thick, kappa;                      /* :767,:871  (kappa must be 0.5 on the GPU: the a0 term vanishes) */
+    double thetag_dot;                        /* :714 growth rate; theta_g = 1 + thetag_dot*dt */
+    double damp, rho, drag;                   /* :596,:597,:569 */
+    double rho_i_max;                         /* :1231 */
+    double k_bend;                            /* :1632 */
+    double k_area, area_0;                    /* :1755-1756 */
+    double ap_rate, ap_quantum, ap_density;   /* :1528,:1539,:1530 */
+    double k_on, ka, kb, Fa, Fb;              /* :2079-2083 */
+    double pin_limit, t_i, t_f;               /* :298-301 */
+    double md_px[6], md_py[6], md_k[6];       /* kMD :1208,:1211,:1214 */
+    double c_A_init;                          /* main.cpp:672 */
+} wcfe_params;
+
+typedef struct wcfe_ctx wcfe_ctx;
+
+int wcfe_default_params(wcfe_params *p, int variant);
+
+/* lifetime; `device` is the CUDA ordinal (one context per process per GPU) */
+int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p);
+int wcfe_destroy(wcfe_ctx *c);
+int wcfe_set_params(wcfe_ctx *c, const wcfe_params *p);
+/* run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own */
+int wcfe_set_stream(wcfe_ctx *c, void *cuda_stream);
+const char *wcfe_last_error(wcfe_ctx *c);
+
+/* Mesh + state.  upload_mesh replaces connectivity, rebuilds the vertex->triangle CSR, the boundary
+ * tables and (substrate) the point-location grid, and resets the surface's state the way
+ * scriptinit.cpp:552-580 + main.cpp:671-674 do (V = A = ea = fa_u = 0, c_A = c_A_init, c_C = 0).
+ * Replaces: ScriptInit/SurfTrack construction (main.cpp:597-609) and, after remeshing, the re-upload. */
+int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne, const int *tri);
+int wcfe_upload_state(wcfe_ctx *c, int surface, int field, const double *host);
+int wcfe_download_state(wcfe_ctx *c, int surface, int field, double *host);
+int wcfe_mesh_sizes(wcfe_ctx *c, int surface, int *nn, int *ne);
+
+int wcfe_set_rng(wcfe_ctx *c, int mode, unsigned int seed);
+int wcfe_set_debug(wcfe_ctx *c, int on);   /* also record WCFE_D_LOC_BOND (extra point location per step) */
+
+/* ---- the reference's call sequence, one entry point per call site of advance_sim() --------------- */
+
+/* driverVelocities_Explicit / driverVelocities_Biaxial + the inline predictor (main.cpp:224-231,
+ * :293-302): V_hlf = V + dt/2 A (z = 0, substrate pins), x_new = x + dt V_hlf (substrate: + 0*).
+ * This is the "mesh-driver interface": positions in, predicted positions out.  xyz_new_out may be NULL
+ * (keep the prediction on the device). */
+int wcfe_predict(wcfe_ctx *c, int surface, double dt, double t_curr, double *xyz_new_out);
+/* positions the host integrator actually accepted (El Topo integrate(), main.cpp:248,:316);
+ * NULL = accept the prediction as is (collision_safety 0) */
+int wcfe_commit(wcfe_ctx *c, int surface, const double *xyz_final);
+/* updateFA + updateForces_Explicit(cell) + updateForces_Explicit(substrate) (main.cpp:354,:360,:361) */
+int wcfe_update(wcfe_ctx *c, double dt_req, double dt_real, double t_curr);
+
+/* El-Topo-free fast path: n x (predict, commit(NULL), update) without leaving the device; time advances
+ * as sim->m_curr_t += accum_dt does (main.cpp:405).  *t_io: in = time at the start, out = time after. */
+int wcfe_step_n(wcfe_ctx *c, int n, double dt, double *t_io);
+
+/* host round trip per step, as the adapter drives it with El Topo in the loop: predict -> D2H predicted
+ * positions of both surfaces into pinned buffers -> H2D of the same buffers as "accepted" positions ->
+ * update -> D2H diagnostics.  Used for the end-to-end measurement; returns bytes moved per step. */
+int wcfe_step_n_roundtrip(wcfe_ctx *c, int n, double dt, double *t_io, long long *h2d_bytes_per_step, long long *d2h_bytes_per_step);
+
+/* out8: total area, centroid x,y,z (UL:531-535), |Res_cell|, |Res_subs| (UL:593,:472), step counter, time */
+int wcfe_get_diagnostics(wcfe_ctx *c, double *out8);
+int wcfe_get_discrete(wcfe_ctx *c, int which, int *out);
+/* mesh incidence as built for the device: out arrays may be NULL */
+int wcfe_get_boundary_flags(wcfe_ctx *c, int surface, int *out);
+/* number of kernels launched since creation, and wall-free device time of the last step_n in ms */
+long long wcfe_kernel_launches(wcfe_ctx *c);
+double wcfe_last_step_ms(wcfe_ctx *c);
+/* individual nodal force fields on the current device state, same ids as the oracle's force_field:
+ * 0 Res(cell) 1 F_FA 2 F_AP 3 F_bending 4 F_area 5 Res(subs) 6 F_FA_subs; out[3*nn]; mm[nn] / res_ea[6*nn]
+ * may be NULL.  Diagnostic entry point for the force-level parity gate (1e-10). */
+int wcfe_force_field(wcfe_ctx *c, int which, double dt, double t_curr, double *out, double *mm, double *res_ea);
+int wcfe_sync(wcfe_ctx *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

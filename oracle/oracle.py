@@ -52,12 +52,14 @@ def lib():
         L.ulo_params_of.restype = C.POINTER(Params); L.ulo_params_of.argtypes = [C.c_void_p]
         L.ulo_set_use_grid.argtypes = [C.c_void_p, C.c_int]
         L.ulo_seed.argtypes = [C.c_void_p, C.c_uint]
+        L.ulo_rng_discard.argtypes = [C.c_void_p, C.c_long]
         L.ulo_get.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
         L.ulo_set.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
         L.ulo_get_discrete.argtypes = [C.c_void_p, C.c_int, _ip]
         L.ulo_get_diag.argtypes = [C.c_void_p, _dp]
         L.ulo_step.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.ulo_force_field.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp]
+        L.ulo_step_force_field.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
         L.ulo_eval_element.argtypes = [C.POINTER(Params), C.c_int, _dp, _dp, _dp, C.c_double, _dp, C.c_double, _dp, _dp, _dp]
         L.ulo_default_params.argtypes = [C.POINTER(Params), C.c_int]
         L.ulo_srand.argtypes = [C.c_void_p, C.c_uint]
@@ -97,6 +99,9 @@ class OracleSim:
     def srand(self, seed):
         self.L.ulo_seed(self.h, seed)
 
+    def rng_discard(self, n):
+        self.L.ulo_rng_discard(self.h, int(n))
+
     def get(self, surface, field):
         n = self.nn[surface]; w = WIDTH[field]
         out = np.empty((n, w) if w > 1 else (n,), dtype=np.float64)
@@ -124,6 +129,15 @@ class OracleSim:
         out = np.zeros((n, 3)); mm = np.zeros(n); rea = np.zeros((n, 6)); aux = np.zeros(4)
         assert self.L.ulo_force_field(self.h, w, dt, t_curr, _d(out), _d(mm), _d(rea), _d(aux)) == 0
         return {"F": out, "MM": mm, "Res_ea": rea, "area": aux}
+
+
+    def step_force_field(self, which):
+        """Force field as it was inside the last step() (same names as force_field)."""
+        names = {"Res_cell": 0, "F_FA": 1, "F_AP": 2, "F_bend": 3, "F_area": 4, "Res_subs": 5, "F_FA_subs": 6}
+        w = names[which]; surf = 1 if w >= 5 else 0; n = self.nn[surf]
+        out = np.zeros((n, 3)); mm = np.zeros(n); rea = np.zeros((n, 6))
+        assert self.L.ulo_step_force_field(self.h, w, _d(out), _d(mm), _d(rea)) == 0
+        return {"F": out, "MM": mm, "Res_ea": rea}
 
 
 def eval_element(variant, mat, X, x, ea, dt, centroid, time):

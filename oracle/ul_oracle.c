@@ -659,6 +659,9 @@ static void update_forces_cell(ulo_sim *s, double dt, double dt_real, double t_t
     for (i = 0; i < 3 * nn; i++) f[i] = F_vd[i] + F_b[i] + F_AP[i] + F_FA[i] + F_a[i] - Res[i];   /* UL:592 */
     for (i = 0; i < 4; i++) s->diag[i] = area[i];
     s->diag[4] = norm_n(Res, 3 * nn);
+    memcpy(s->sf[0], Res, sizeof(double) * 3 * nn); memcpy(s->sf[1], F_FA, sizeof(double) * 3 * nn); memcpy(s->sf[2], F_AP, sizeof(double) * 3 * nn);
+    memcpy(s->sf[3], F_b, sizeof(double) * 3 * nn); memcpy(s->sf[4], F_a, sizeof(double) * 3 * nn);
+    memcpy(s->s_mm[0], MM, sizeof(double) * nn); memcpy(s->s_rea[0], Rea, sizeof(double) * 6 * nn);
     nodal_update(p, nn, f, MM, Rea, c->A, c->V, c->Vh, c->ea, dt, dt_real);
     free(Res); free(Rea); free(MM); free(F_FA); free(F_AP); free(F_vd); free(F_b); free(F_a); free(f);
 }
@@ -674,6 +677,8 @@ static void update_forces_subs(ulo_sim *s, double dt, double dt_real, double t_t
     ulo_force_FA_subs(s, F_FA);                                                         /* UL:467 */
     for (i = 0; i < 3 * nn; i++) f[i] = F_FA[i] - Res[i];                               /* UL:471 */
     s->diag[5] = norm_n(Res, 3 * nn);
+    memcpy(s->sf[5], Res, sizeof(double) * 3 * nn); memcpy(s->sf[6], F_FA, sizeof(double) * 3 * nn);
+    memcpy(s->s_mm[1], MM, sizeof(double) * nn); memcpy(s->s_rea[1], Rea, sizeof(double) * 6 * nn);
     nodal_update(p, nn, f, MM, Rea, b->A, b->V, b->Vh, b->ea, dt, dt_real);
     free(Res); free(Rea); free(MM); free(F_FA); free(f);
 }
@@ -706,17 +711,23 @@ ulo_sim *ulo_create(int variant, int nn_c, const double *xyz_c, int ne_c, const 
     ulo_srand(&s->rng, 1);                                                      /* main.cpp:709 */
     s->loc_bond = (int *)calloc(n, sizeof(int)); s->loc_force_cnt = (int *)calloc(n, sizeof(int)); s->loc_force_first = (int *)calloc(n, sizeof(int));
     s->ap_fire = (unsigned char *)calloc(n, 1); s->fa_reset = (unsigned char *)calloc(n, 1); s->cc_clamp = (unsigned char *)calloc(n, 1);
+    for (i = 0; i < 7; i++) s->sf[i] = (double *)calloc(3 * (size_t)((i < 5 ? nn_c : nn_s) > 0 ? (i < 5 ? nn_c : nn_s) : 1), sizeof(double));
+    s->s_mm[0] = (double *)calloc(n, sizeof(double)); s->s_rea[0] = (double *)calloc(6 * n, sizeof(double));
+    s->s_mm[1] = (double *)calloc((size_t)(nn_s > 0 ? nn_s : 1), sizeof(double)); s->s_rea[1] = (double *)calloc(6 * (size_t)(nn_s > 0 ? nn_s : 1), sizeof(double));
     return s;
 }
 void ulo_destroy(ulo_sim *s) {
     if (!s) return;
     surf_free(&s->cell); surf_free(&s->subs);
     free(s->loc_bond); free(s->loc_force_cnt); free(s->loc_force_first); free(s->ap_fire); free(s->fa_reset); free(s->cc_clamp);
+    { int i; for (i = 0; i < 7; i++) free(s->sf[i]); }
+    free(s->s_mm[0]); free(s->s_mm[1]); free(s->s_rea[0]); free(s->s_rea[1]);
     free(s);
 }
 ulo_params *ulo_params_of(ulo_sim *s) { return &s->p; }
 void ulo_set_use_grid(ulo_sim *s, int on) { s->use_grid = on; }
 void ulo_seed(ulo_sim *s, unsigned int seed) { ulo_srand(&s->rng, seed); }
+void ulo_rng_discard(ulo_sim *s, long n) { long i; for (i = 0; i < n; i++) (void)ulo_rand(&s->rng); }
 
 static double *field_ptr(ulo_surface *s, int field, int *w) {
     switch (field) {
@@ -803,4 +814,14 @@ int ulo_force_field(ulo_sim *s, int which, double dt, double t_curr, double *out
     case 6: ulo_force_FA_subs(s, out); return 0;
     }
     return -1;
+}
+
+int ulo_step_force_field(ulo_sim *s, int which, double *out, double *mm, double *res_ea) {
+    int surf, nn;
+    if (which < 0 || which > 6) return -1;
+    surf = which >= 5; nn = surf ? s->subs.m.nn : s->cell.m.nn;
+    memcpy(out, s->sf[which], sizeof(double) * 3 * (size_t)nn);
+    if (mm) memcpy(mm, s->s_mm[surf], sizeof(double) * (size_t)nn);
+    if (res_ea) memcpy(res_ea, s->s_rea[surf], sizeof(double) * 6 * (size_t)nn);
+    return 0;
 }

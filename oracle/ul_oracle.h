@@ -55,7 +55,9 @@ typedef struct ulo_sim {
     unsigned char *fa_reset;  /* [nn_cell] else-branch of UL:2107 taken */
     unsigned char *cc_clamp;  /* [nn_cell] c_C<0 clamp taken */
     double diag[8];        /* area, cx, cy, cz, |Res_cell|, |Res_subs| */
-    /* grid over substrate triangles (built lazily) */
+    /* force fields of the last step as they were inside updateForces_Explicit (for the 1e-10 force gate):
+       0 Res(cell) 1 F_FA 2 F_AP 3 F_bending 4 F_area 5 Res(subs) 6 F_FA_subs; mm / res_ea per surface */
+    double *sf[7], *s_mm[2], *s_rea[2];
     void *grid;
 } ulo_sim;
 
@@ -73,6 +75,7 @@ void ulo_destroy(ulo_sim *s);
 ulo_params *ulo_params_of(ulo_sim *s);
 void ulo_set_use_grid(ulo_sim *s, int on);
 void ulo_seed(ulo_sim *s, unsigned int seed);
+void ulo_rng_discard(ulo_sim *s, long n);   /* skip n draws (resume a replay mid-run) */
 /* field ids as oracle/ref_wrap.cpp: 0 x 1 V 2 A 3 ea 4 cA 5 cB 6 cC 7 fa_u 8 X_prev 9 V_hlf */
 int  ulo_get(ulo_sim *s, int surface, int field, double *out);
 int  ulo_set(ulo_sim *s, int surface, int field, const double *in);
@@ -97,6 +100,8 @@ void ulo_driver_explicit(int nn, const double *V, const double *A, double dt, do
 void ulo_driver_biaxial(const ulo_params *p, int nn, const double *X, const double *V, const double *A, double dt, double t, double *Vh);
 /* force field by id on the current state, same ids as ulref_force_field */
 int  ulo_force_field(ulo_sim *s, int which, double dt, double t_curr, double *out, double *mm, double *res_ea, double *aux4);
+/* the same fields as they were inside the last ulo_step() */
+int  ulo_step_force_field(ulo_sim *s, int which, double *out, double *mm, double *res_ea);
 
 #ifdef __cplusplus
 }

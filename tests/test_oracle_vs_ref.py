@@ -1,0 +1,43 @@
+"""The C restatement against the UNMODIFIED reference translation units (oracle/_ref, built by `make -C oracle ref`
+where /root/reference exists).  Skipped on boxes without oracle/_ref."""
+import numpy as np
+import pytest
+from conftest import rel_err
+from oracle.oracle import OracleSim, eval_element
+from oracle.refrun import RefSim, ref_available, ref_eval_element
+
+pytestmark = pytest.mark.skipif(not ref_available("k1"), reason="oracle/_ref not built here")
+
+
+@pytest.mark.parametrize("variant,nsteps", [("k1", 40), ("k31", 12), ("kMD", 12)])
+def test_first_steps_all_fields(meshes, variant, nsteps):
+    """k31 / kMD: only the first dozen steps -- after that bond-rupture avalanches amplify rounding differences
+    by ~10x every 4 steps (measured between this restatement and the reference itself), see DESIGN.md."""
+    xc, tc, xs, ts = meshes
+    r = RefSim(variant, xc, tc, xs, ts); r.srand(1)
+    o = OracleSim(variant, xc, tc, xs, ts); o.srand(1)
+    t = 0.0
+    for k in range(nsteps):
+        r.step(0.005, t); o.step(0.005, t); t += 0.005
+        for f in ["x", "V", "A", "ea", "cC", "fa_u"]:
+            assert rel_err(o.get(0, f), r.get(0, f)) < 1e-10, (variant, k, f)
+    # the in-step force fields of the restatement agree with the reference's functions on the same state
+    for name in ["F_FA", "F_bend", "F_area", "Res_cell", "Res_subs", "F_FA_subs"]:
+        a = o.force_field(name, 0.005, t); b = r.force_field(name, 0.005, t)
+        scale = max(np.abs(b["F"]).max(), 1.0)
+        assert rel_err(a["F"], b["F"], scale) < 1e-10, name
+
+
+def test_random_elements_3d_and_planar():
+    rng = np.random.default_rng(7)
+    base = np.array([[0, 0, 0], [1.0, 0, 0], [0.4, 0.9, 0]])
+    for trial in range(200):
+        X = base + 0.15 * rng.normal(size=(3, 3)); x = X + 0.02 * rng.normal(size=(3, 3)); ea = 0.04 * rng.normal(size=(3, 6))
+        if trial % 2 == 0:
+            X[:, 2] = 0; x[:, 2] = 0; ea[:, [2, 4, 5]] = 0
+        mat = 1 + trial % 2
+        cen = rng.normal(size=3)
+        a = eval_element("k1", mat, X.ravel(), x.ravel(), ea.ravel(), 0.005, cen, 1.3)
+        b = ref_eval_element("k1", mat, X.ravel(), x.ravel(), ea.ravel(), np.full(3, 100.0), np.zeros(3), 0.005, cen, 1.3)
+        for u, v in zip(a, b):
+            assert rel_err(u, v) < 1e-12

@@ -1,0 +1,78 @@
+"""ctypes binding of libwcfe.so (include/wcfe.h).  Fails loudly when the CUDA library is missing."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwcfe.so")
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_NUMERIC = 0, -1, -2, -3, -4, -5
+CELL, SUBS = 0, 1
+VARIANTS = {"k1": 0, "k31": 1, "kMD": 2}
+FIELDS = {"x": 0, "V": 1, "A": 2, "ea": 3, "cA": 4, "cB": 5, "cC": 6, "fa_u": 7, "X_prev": 8}
+WIDTH = {"x": 3, "V": 3, "A": 3, "ea": 6, "cA": 1, "cB": 1, "cC": 1, "fa_u": 3, "X_prev": 3}
+DISCRETE = {"loc_bond": 0, "loc_force_cnt": 1, "loc_force_first": 2, "ap_fire": 3, "fa_reset": 4, "cc_clamp": 5}
+FORCE_FIELDS = {"Res_cell": 0, "F_FA": 1, "F_AP": 2, "F_bend": 3, "F_area": 4, "Res_subs": 5, "F_FA_subs": 6}
+RNG_GLIBC_REPLAY, RNG_PHILOX = 0, 1
+
+# every symbol include/wcfe.h declares
+SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_params", "wcfe_set_stream", "wcfe_last_error",
+           "wcfe_upload_mesh", "wcfe_upload_state", "wcfe_download_state", "wcfe_mesh_sizes", "wcfe_set_rng", "wcfe_set_debug",
+           "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_step_n", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
+           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_sync"]
+
+
+class Params(C.Structure):
+    _fields_ = [("law", C.c_int), ("kint_force", C.c_double), ("kint_bond", C.c_double), ("subs_scale", C.c_double),
+                ("mu_cell", C.c_double), ("mu_subs", C.c_double),
+                ("t_act_rate", C.c_double), ("t_act_max", C.c_double), ("t_act_t1", C.c_double),
+                ("thick", C.c_double), ("kappa", C.c_double), ("thetag_dot", C.c_double),
+                ("damp", C.c_double), ("rho", C.c_double), ("drag", C.c_double),
+                ("rho_i_max", C.c_double), ("k_bend", C.c_double), ("k_area", C.c_double), ("area_0", C.c_double),
+                ("ap_rate", C.c_double), ("ap_quantum", C.c_double), ("ap_density", C.c_double),
+                ("k_on", C.c_double), ("ka", C.c_double), ("kb", C.c_double), ("Fa", C.c_double), ("Fb", C.c_double),
+                ("pin_limit", C.c_double), ("t_i", C.c_double), ("t_f", C.c_double),
+                ("md_px", C.c_double * 6), ("md_py", C.c_double * 6), ("md_k", C.c_double * 6),
+                ("c_A_init", C.c_double)]
+
+
+_lib = None
+
+
+def load():
+    """Load libwcfe.so.  There is no fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libwcfe.so is not built (%s missing): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "or `python -m wholecellfe_b200.build`; there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.wcfe_default_params.argtypes = [C.POINTER(Params), C.c_int]
+    L.wcfe_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Params)]
+    L.wcfe_destroy.argtypes = [vp]
+    L.wcfe_set_params.argtypes = [vp, C.POINTER(Params)]
+    L.wcfe_set_stream.argtypes = [vp, vp]
+    L.wcfe_last_error.argtypes = [vp]; L.wcfe_last_error.restype = C.c_char_p
+    L.wcfe_upload_mesh.argtypes = [vp, C.c_int, C.c_int, _dp, C.c_int, _ip]
+    L.wcfe_upload_state.argtypes = [vp, C.c_int, C.c_int, _dp]
+    L.wcfe_download_state.argtypes = [vp, C.c_int, C.c_int, _dp]
+    L.wcfe_mesh_sizes.argtypes = [vp, C.c_int, _ip, _ip]
+    L.wcfe_set_rng.argtypes = [vp, C.c_int, C.c_uint]
+    L.wcfe_set_debug.argtypes = [vp, C.c_int]
+    L.wcfe_predict.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp]
+    L.wcfe_commit.argtypes = [vp, C.c_int, _dp]
+    L.wcfe_update.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    L.wcfe_step_n.argtypes = [vp, C.c_int, C.c_double, _dp]
+    L.wcfe_step_n_roundtrip.argtypes = [vp, C.c_int, C.c_double, _dp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.wcfe_get_diagnostics.argtypes = [vp, _dp]
+    L.wcfe_get_discrete.argtypes = [vp, C.c_int, _ip]
+    L.wcfe_get_boundary_flags.argtypes = [vp, C.c_int, _ip]
+    L.wcfe_kernel_launches.argtypes = [vp]; L.wcfe_kernel_launches.restype = C.c_longlong
+    L.wcfe_last_step_ms.argtypes = [vp]; L.wcfe_last_step_ms.restype = C.c_double
+    L.wcfe_force_field.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp]
+    L.wcfe_sync.argtypes = [vp]
+    _lib = L
+    return L

@@ -1,0 +1,786 @@
+// wcfe_api.cu -- the C ABI of include/wcfe.h: context, host-side mesh preprocessing, device state, launches.
+//
+// Host side mirrors what the reference keeps in NonDestructiveTriMesh / DynamicSurface:
+//   vertex->triangle map in triangle order (eltopo3d/nondestructivetrimesh.cpp:138-194),
+//   boundary-vertex flags from odd-incidence edges (:527-543),
+//   per-node state vectors (eltopo3d/dynamicsurface.h:234-264),
+// but lays it out as SoA FP64 on the device and never runs the physics on the CPU.
+#include "../../include/wcfe.h"
+#include "wcfe_kernels.cuh"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace wcfe;
+
+namespace {
+
+struct HostRng {   // glibc rand(): TYPE_3 additive feedback x^31+x^3+1 (the stream the reference consumes at UL:1525)
+    unsigned int r[31]; int f, b;
+    void seed(unsigned int s) {
+        if (s == 0) s = 1;
+        r[0] = s;
+        for (int i = 1; i < 31; i++) {
+            long hi = (int)r[i - 1] / 127773, lo = (int)r[i - 1] % 127773;
+            long w = 16807 * lo - 2836 * hi;
+            if (w < 0) w += 2147483647;
+            r[i] = (unsigned int)w;
+        }
+        f = 3; b = 0;
+        for (int i = 0; i < 310; i++) next();
+    }
+    unsigned int next() {
+        r[f] += r[b];
+        const unsigned int v = r[f] >> 1;
+        f = (f + 1) % 31; b = (b + 1) % 31;
+        return v;
+    }
+};
+
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (!count) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; n = 0; }
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct Surface {
+    int nn = 0, np = 0, ne = 0, nep = 0;
+    std::vector<int> tri;                 // host copy, [3*ne] AoS as uploaded
+    std::vector<unsigned char> is_bnd;
+    std::vector<int> ring_ptr, ring;      // host CSR
+    DevBuf<int> d_tri, d_ring_ptr, d_ring;
+    DevBuf<double> x, X, V, A, ea[2], cA, cB, cC, fa, asum;
+    int ea_cur = 0;
+    // boundary (cell)
+    int nb = 0;
+    std::vector<int> bnd_node;
+    DevBuf<int> d_bnd_node, d_bnd_index, d_cand_ptr, d_cand;
+    DevBuf<double> d_bnd_buf;
+    // debug capture
+    DevBuf<double> g_res, g_ffa, g_fap, g_fbend, g_farea, g_mm, g_rea;
+    double max_edge = 0, max_tri_area = 0, area = 0;
+};
+
+}   // namespace
+
+struct wcfe_ctx {
+    int device = 0;
+    wcfe_params prm;
+    Consts k;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Surface s[2];
+    // point location grid over the substrate + triangle buckets
+    GridView grid{};
+    DevBuf<int> g_ptr, g_items;
+    DevBuf<unsigned long long> b_head;
+    DevBuf<int> b_items;
+    int b_cap = 0;
+    unsigned int epoch = 0;
+    double box[4] = {0, 0, 0, 0};         // padded anchor region, substrate nodes outside cannot receive force
+    double ibox[4] = {0, 0, 0, 0};        // region the anchors themselves must stay in (box shrunk by the longest substrate edge)
+    // discrete state + flags
+    DevBuf<int> d_flags, d_loc_bond, d_loc_cnt, d_loc_first, d_ap_fire, d_err;
+    DevBuf<double> d_partials, d_diag;
+    DevBuf<unsigned int> d_tape;
+    size_t tape_cap = 0;
+    unsigned int *h_tape = nullptr;       // pinned
+    double *h_stage = nullptr; size_t stage_bytes = 0;   // pinned staging for up/downloads
+    int rng_mode = WCFE_RNG_GLIBC_REPLAY; unsigned int seed = 1; HostRng rng;
+    unsigned int step = 0;
+    int debug = 0;
+    long long launches = 0;
+    double last_ms = 0, t_last = 0;
+    bool have_predict[2] = {false, false};
+    std::string err;
+};
+
+namespace {
+
+int fail(wcfe_ctx *c, int code, const std::string &msg) { if (c) c->err = msg; return code; }
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) return fail(c, WCFE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+int width_of(int field) {
+    switch (field) {
+    case WCFE_F_X: case WCFE_F_V: case WCFE_F_A: case WCFE_F_FAU: case WCFE_F_XPREV: return 3;
+    case WCFE_F_EA: return 6;
+    case WCFE_F_CA: case WCFE_F_CB: case WCFE_F_CC: return 1;
+    }
+    return 0;
+}
+double *field_dev(wcfe_ctx *c, int surface, int field) {
+    Surface &s = c->s[surface];
+    switch (field) {
+    case WCFE_F_X: return s.x.p;
+    case WCFE_F_XPREV: return surface == WCFE_SUBS ? s.x.p : s.X.p;
+    case WCFE_F_V: return s.V.p;
+    case WCFE_F_A: return s.A.p;
+    case WCFE_F_EA: return s.ea[s.ea_cur].p;
+    case WCFE_F_CA: return surface == WCFE_CELL ? s.cA.p : nullptr;
+    case WCFE_F_CB: return surface == WCFE_CELL ? s.cB.p : nullptr;
+    case WCFE_F_CC: return surface == WCFE_CELL ? s.cC.p : nullptr;
+    case WCFE_F_FAU: return surface == WCFE_CELL ? s.fa.p : nullptr;
+    }
+    return nullptr;
+}
+
+int ensure_stage(wcfe_ctx *c, size_t bytes) {
+    if (bytes <= c->stage_bytes) return WCFE_OK;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->stage_bytes = 0;
+    CK(cudaMallocHost((void **)&c->h_stage, bytes));
+    c->stage_bytes = bytes;
+    return WCFE_OK;
+}
+
+// AoS host [n*w] -> SoA device [w*np] through the pinned staging buffer
+int put_field(wcfe_ctx *c, double *dev, const double *host, int nn, int np, int w) {
+    int rc = ensure_stage(c, sizeof(double) * (size_t)w * np);
+    if (rc) return rc;
+    double *st = c->h_stage;
+    for (int q = 0; q < w; q++) {
+        for (int i = 0; i < nn; i++) st[(size_t)q * np + i] = host[(size_t)i * w + q];
+        for (int i = nn; i < np; i++) st[(size_t)q * np + i] = 0.0;
+    }
+    CK(cudaMemcpyAsync(dev, st, sizeof(double) * (size_t)w * np, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return WCFE_OK;
+}
+int get_field(wcfe_ctx *c, const double *dev, double *host, int nn, int np, int w) {
+    int rc = ensure_stage(c, sizeof(double) * (size_t)w * np);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->h_stage, dev, sizeof(double) * (size_t)w * np, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const double *st = c->h_stage;
+    for (int q = 0; q < w; q++) for (int i = 0; i < nn; i++) host[(size_t)i * w + q] = st[(size_t)q * np + i];
+    return WCFE_OK;
+}
+int fill_field(wcfe_ctx *c, double *dev, int nn, int np, int w, double value) {
+    std::vector<double> h((size_t)nn * w, value);
+    return put_field(c, dev, h.data(), nn, np, w);
+}
+
+void make_consts(wcfe_ctx *c) {
+    const wcfe_params &p = c->prm; Consts &k = c->k;
+    k.law = p.law; k.kint_force = p.kint_force; k.kint_bond = p.kint_bond;
+    k.mu_cell = p.mu_cell; k.mu_subs = p.mu_subs; k.t_act_rate = p.t_act_rate; k.t_act_max = p.t_act_max; k.t_act_t1 = p.t_act_t1;
+    k.thick = p.thick; k.kappa = p.kappa; k.thetag_dot = p.thetag_dot;
+    k.damp = p.damp; k.rho = p.rho; k.drag = p.drag; k.rho_i_max = p.rho_i_max; k.k_bend = p.k_bend; k.k_area = p.k_area; k.area_0 = p.area_0;
+    k.ap_quantum = p.ap_quantum; k.ap_density = p.ap_density;
+    k.k_on = p.k_on; k.ka = p.ka; k.kb = p.kb; k.Fa = p.Fa; k.Fb = p.Fb;
+    k.pin_limit = p.pin_limit; k.t_i = p.t_i; k.t_f = p.t_f;
+    for (int i = 0; i < 6; i++) { k.md_px[i] = p.md_px[i]; k.md_py[i] = p.md_py[i]; k.md_k[i] = p.md_k[i]; }
+}
+int check_params(wcfe_ctx *c, const wcfe_params *p) {
+    if (p->subs_scale != 0.0) return fail(c, WCFE_ERR_UNSUPPORTED, "subs_scale != 0: a moving substrate (main.cpp:299 without the 0*) is not implemented on the GPU path");
+    if (p->kappa != 0.5) return fail(c, WCFE_ERR_UNSUPPORTED, "kappa != 0.5: the anisotropic active-stress term (UL:877) needs the centroid of the same step and is not implemented");
+    if (p->law != 0 && p->law != 1) return fail(c, WCFE_ERR_ARG, "law must be 0 (linear) or 1 (MD table)");
+    return WCFE_OK;
+}
+
+SurfView view(Surface &s) {
+    SurfView v{};
+    v.nn = s.nn; v.np = s.np; v.ne = s.ne; v.nep = s.nep;
+    v.tri = s.d_tri.p; v.ring_ptr = s.d_ring_ptr.p; v.ring = s.d_ring.p;
+    v.x = s.x.p; v.X = s.X.p ? s.X.p : s.x.p; v.V = s.V.p; v.A = s.A.p;
+    v.ea_in = s.ea[s.ea_cur].p; v.ea_out = s.ea[s.ea_cur ^ 1].p;
+    v.cC = s.cC.p; v.fa = s.fa.p; v.asum = s.asum.p;
+    return v;
+}
+BoundaryView bview(Surface &s) {
+    BoundaryView b{};
+    b.nb = s.nb; b.node = s.d_bnd_node.p; b.index = s.d_bnd_index.p; b.cand_ptr = s.d_cand_ptr.p; b.cand = s.d_cand.p; b.buf = s.d_bnd_buf.p;
+    return b;
+}
+DebugView dview(Surface &s) {
+    DebugView d{};
+    d.res = s.g_res.p; d.f_fa = s.g_ffa.p; d.f_ap = s.g_fap.p; d.f_bend = s.g_fbend.p; d.f_area = s.g_farea.p; d.mm = s.g_mm.p; d.res_ea = s.g_rea.p;
+    return d;
+}
+
+int alloc_debug(wcfe_ctx *c, int surface) {
+    Surface &s = c->s[surface];
+    if (!s.nn || s.g_res.p) return WCFE_OK;
+    const size_t np = s.np;
+    CK(s.g_res.alloc(3 * np)); CK(s.g_ffa.alloc(3 * np)); CK(s.g_mm.alloc(np)); CK(s.g_rea.alloc(6 * np));
+    if (surface == WCFE_CELL) { CK(s.g_fap.alloc(3 * np)); CK(s.g_fbend.alloc(3 * np)); CK(s.g_farea.alloc(3 * np)); }
+    return WCFE_OK;
+}
+
+// bounding box of the cell, padded: substrate nodes outside it are never asked for bucket contents
+void update_box(wcfe_ctx *c, const double *xyz, int nn) {
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int i = 0; i < nn; i++) {
+        x0 = std::min(x0, xyz[3 * i]); x1 = std::max(x1, xyz[3 * i]);
+        y0 = std::min(y0, xyz[3 * i + 1]); y1 = std::max(y1, xyz[3 * i + 1]);
+    }
+    const double pad_in = std::max(2.0, 0.25 * std::max(x1 - x0, y1 - y0)), pad = pad_in + c->s[WCFE_SUBS].max_edge;
+    c->box[0] = x0 - pad; c->box[1] = x1 + pad; c->box[2] = y0 - pad; c->box[3] = y1 + pad;
+    c->ibox[0] = x0 - pad_in; c->ibox[1] = x1 + pad_in; c->ibox[2] = y0 - pad_in; c->ibox[3] = y1 + pad_in;
+}
+
+int build_grid(wcfe_ctx *c, const double *xyz) {
+    Surface &s = c->s[WCFE_SUBS];
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int i = 0; i < s.nn; i++) {
+        xmin = std::min(xmin, xyz[3 * i]); xmax = std::max(xmax, xyz[3 * i]);
+        ymin = std::min(ymin, xyz[3 * i + 1]); ymax = std::max(ymax, xyz[3 * i + 1]);
+    }
+    double h = std::sqrt(((xmax - xmin) * (ymax - ymin)) / std::max(1, s.ne)) * 1.5;
+    if (!(h > 0)) h = 1;
+    const double eps = 1e-9 * ((xmax - xmin) + (ymax - ymin) + 1.0);
+    GridView &g = c->grid;
+    g.x0 = xmin - 2 * eps; g.y0 = ymin - 2 * eps; g.inv_h = 1.0 / h;
+    g.nx = (int)((xmax - g.x0 + 2 * eps) * g.inv_h) + 1; g.ny = (int)((ymax - g.y0 + 2 * eps) * g.inv_h) + 1;
+    const size_t ncell = (size_t)g.nx * g.ny;
+    std::vector<int> ptr(ncell + 1, 0), items;
+    auto range = [&](int e, int &ix0, int &ix1, int &iy0, int &iy1) {
+        double bx0 = 1e300, bx1 = -1e300, by0 = 1e300, by1 = -1e300;
+        for (int j = 0; j < 3; j++) {
+            const double px = xyz[3 * s.tri[3 * e + j]], py = xyz[3 * s.tri[3 * e + j] + 1];
+            bx0 = std::min(bx0, px); bx1 = std::max(bx1, px); by0 = std::min(by0, py); by1 = std::max(by1, py);
+        }
+        ix0 = std::max(0, (int)((bx0 - eps - g.x0) * g.inv_h)); ix1 = std::min(g.nx - 1, (int)((bx1 + eps - g.x0) * g.inv_h));
+        iy0 = std::max(0, (int)((by0 - eps - g.y0) * g.inv_h)); iy1 = std::min(g.ny - 1, (int)((by1 + eps - g.y0) * g.inv_h));
+    };
+    for (int e = 0; e < s.ne; e++) {
+        int ix0, ix1, iy0, iy1; range(e, ix0, ix1, iy0, iy1);
+        for (int iy = iy0; iy <= iy1; iy++) for (int ix = ix0; ix <= ix1; ix++) ptr[(size_t)iy * g.nx + ix + 1]++;
+    }
+    for (size_t q = 0; q < ncell; q++) ptr[q + 1] += ptr[q];
+    items.resize(std::max(1, ptr[ncell]));
+    std::vector<int> fill(ncell, 0);
+    for (int e = 0; e < s.ne; e++) {   // ascending e => ascending triangle index inside each cell
+        int ix0, ix1, iy0, iy1; range(e, ix0, ix1, iy0, iy1);
+        for (int iy = iy0; iy <= iy1; iy++) for (int ix = ix0; ix <= ix1; ix++) { const size_t q = (size_t)iy * g.nx + ix; items[ptr[q] + fill[q]++] = e; }
+    }
+    CK(c->g_ptr.alloc(ncell + 1)); CK(c->g_items.alloc(items.size()));
+    CK(cudaMemcpy(c->g_ptr.p, ptr.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->g_items.p, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice));
+    g.ptr = c->g_ptr.p; g.items = c->g_items.p;
+    return WCFE_OK;
+}
+
+// (re)size the per-triangle buckets once both meshes are known
+int build_buckets(wcfe_ctx *c) {
+    Surface &cs = c->s[WCFE_CELL], &ss = c->s[WCFE_SUBS];
+    if (!cs.nn || !ss.nn) return WCFE_OK;
+    const double dens = cs.area > 0 ? cs.nn * ss.max_tri_area / cs.area : 1.0;
+    long long cap = 4 * (long long)std::ceil(dens) + 8;
+    cap = std::min<long long>(std::max<long long>(cap, 8), 1 << 16);
+    if ((double)cap * ss.ne * 4.0 > 16e9) return fail(c, WCFE_ERR_CAPACITY, "triangle buckets would exceed 16 GB: substrate far coarser than the cell mesh");
+    c->b_cap = (int)cap;
+    CK(c->b_head.alloc(ss.nep)); CK(c->b_items.alloc((size_t)ss.ne * cap));
+    CK(cudaMemset(c->b_head.p, 0, sizeof(unsigned long long) * ss.nep));
+    c->epoch = 0;
+    return WCFE_OK;
+}
+
+int check_device_errors(wcfe_ctx *c) {
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, c->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (e & ERR_BUCKET_OVERFLOW) return fail(c, WCFE_ERR_CAPACITY, "triangle bucket overflow: more anchors in one substrate triangle than the capacity sized at upload");
+    if (e & ERR_REGION) return fail(c, WCFE_ERR_CAPACITY, "an integrin anchor left the padded cell region; re-commit positions to refresh it");
+    return WCFE_OK;
+}
+
+// ---- one UL update on the device: k_bond, k_cell_node, k_boundary_finish, k_subs_node ---------------------------
+int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const unsigned int *tape_dev) {
+    Surface &cs = c->s[WCFE_CELL], &ss = c->s[WCFE_SUBS];
+    SurfView cv = view(cs), sv = view(ss);
+    sv.X = sv.x;
+    c->epoch++;
+    BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch};
+    const int gc = (cs.nn + kBlock - 1) / kBlock, gs = (ss.nn + kBlock - 1) / kBlock;
+    k_bond<<<gc, kBlock, 0, c->stream>>>(cv, sv, c->grid, bk, c->k, dt_real, c->ibox[0], c->ibox[1], c->ibox[2], c->ibox[3], c->d_flags.p, c->d_loc_bond.p, c->d_loc_cnt.p, c->d_loc_first.p, c->debug, c->d_err.p);
+    // Pr < APrate*dt*exp(-APrate*dt) (UL:1531): the threshold is evaluated on the host with the host libm, as the reference does
+    const double thr = c->prm.ap_rate * dt_real * std::exp(-c->prm.ap_rate * dt_real);
+    BoundaryView bv = bview(cs);
+    if (c->debug)
+        k_cell_node<true><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, dview(cs));
+    else
+        k_cell_node<false><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, DebugView{});
+    if (c->debug) k_boundary_finish<true><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, gc, c->d_partials.p, dt, dt_real, c->d_diag.p, dview(cs));
+    else k_boundary_finish<false><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, gc, c->d_partials.p, dt, dt_real, c->d_diag.p, DebugView{});
+    if (c->debug) k_subs_node<true><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
+    else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+    c->launches += 4;
+    cs.ea_cur ^= 1; ss.ea_cur ^= 1;
+    c->step++;
+    CK(cudaGetLastError());
+    return WCFE_OK;
+}
+
+int ensure_tape(wcfe_ctx *c, size_t count) {
+    if (count <= c->tape_cap) return WCFE_OK;
+    if (c->h_tape) cudaFreeHost(c->h_tape);
+    c->h_tape = nullptr; c->tape_cap = 0;
+    CK(c->d_tape.alloc(count));
+    CK(cudaMallocHost((void **)&c->h_tape, count * sizeof(unsigned int)));
+    c->tape_cap = count;
+    return WCFE_OK;
+}
+// draw n_steps*nb values of the glibc stream (one per boundary vertex per step, ascending vertex order) and ship them
+int stage_tape(wcfe_ctx *c, int n_steps) {
+    const size_t nb = c->s[WCFE_CELL].nb, count = nb * (size_t)n_steps;
+    if (c->rng_mode != WCFE_RNG_GLIBC_REPLAY || !count) return WCFE_OK;
+    int rc = ensure_tape(c, count);
+    if (rc) return rc;
+    for (size_t q = 0; q < count; q++) c->h_tape[q] = c->rng.next();
+    CK(cudaMemcpyAsync(c->d_tape.p, c->h_tape, count * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
+    return WCFE_OK;
+}
+
+int ready(wcfe_ctx *c) {
+    if (!c) return WCFE_ERR_ARG;
+    if (!c->s[0].nn || !c->s[1].nn) return fail(c, WCFE_ERR_ARG, "upload both the cell and the substrate mesh first");
+    return WCFE_OK;
+}
+
+}   // namespace
+
+extern "C" {
+
+int wcfe_default_params(wcfe_params *p, int variant) {
+    if (!p || variant < 0 || variant > 2) return WCFE_ERR_ARG;
+    memset(p, 0, sizeof *p);
+    p->law = variant == WCFE_KMD ? 1 : 0;
+    p->kint_force = variant == WCFE_K1 ? 1000.0 : 31000.0;
+    p->kint_bond = variant == WCFE_K1 ? 1000.0 : (variant == WCFE_K31 ? 31000.0 : -1.0);
+    p->subs_scale = 0.0;
+    p->mu_cell = 1000; p->mu_subs = 1000000;
+    p->t_act_rate = 200.0; p->t_act_max = 400; p->t_act_t1 = 2;
+    p->thick = 1; p->kappa = 0.5; p->thetag_dot = 0.0;
+    p->damp = 0.001; p->rho = 1.0; p->drag = 0.001;
+    p->rho_i_max = 100; p->k_bend = 20.; p->k_area = 1; p->area_0 = 10 * 10 * 3.1416;
+    p->ap_rate = 10; p->ap_quantum = 5; p->ap_density = 100;
+    p->k_on = 1; p->ka = 0.004; p->kb = 10; p->Fa = 15; p->Fb = 15;
+    p->pin_limit = 49.00; p->t_i = 3; p->t_f = 8;
+    const double px[6] = {0., 2.51250583e-03, 4.40265201e-03, 5.91408228e-03, 11.76817302e-03, 17.001e-03};
+    const double py[6] = {-7.15514497, 71.80501308, 356.62420075, 356.96656556, 126.21811585, 528.40481124};
+    const double kk[6] = {31426.8556, 99485.86235, 67080.67086, -7908.39043, 21978.66923, 76858.39733};
+    for (int i = 0; i < 6; i++) { p->md_px[i] = px[i]; p->md_py[i] = py[i]; p->md_k[i] = kk[i]; }
+    p->c_A_init = 100;
+    return WCFE_OK;
+}
+
+int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p) {
+    if (!out || !p) return WCFE_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return WCFE_ERR_CUDA;   // no CPU fallback
+    wcfe_ctx *c = new wcfe_ctx;
+    c->device = device;
+    int rc = check_params(c, p);
+    if (rc) { delete c; return rc; }
+    c->prm = *p; make_consts(c);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return WCFE_ERR_CUDA; }
+    c->stream = c->own_stream;
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    c->rng.seed(1);
+    if (c->d_err.alloc(1) != cudaSuccess || c->d_diag.alloc(8) != cudaSuccess) { delete c; return WCFE_ERR_CUDA; }
+    cudaMemset(c->d_err.p, 0, sizeof(int)); cudaMemset(c->d_diag.p, 0, 8 * sizeof(double));
+    *out = c;
+    return WCFE_OK;
+}
+
+int wcfe_destroy(wcfe_ctx *c) {
+    if (!c) return WCFE_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int q = 0; q < 2; q++) {
+        Surface &s = c->s[q];
+        s.d_tri.release(); s.d_ring_ptr.release(); s.d_ring.release();
+        s.x.release(); s.X.release(); s.V.release(); s.A.release(); s.ea[0].release(); s.ea[1].release();
+        s.cA.release(); s.cB.release(); s.cC.release(); s.fa.release(); s.asum.release();
+        s.d_bnd_node.release(); s.d_bnd_index.release(); s.d_cand_ptr.release(); s.d_cand.release(); s.d_bnd_buf.release();
+        s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
+    }
+    c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release();
+    c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();
+    c->d_partials.release(); c->d_diag.release(); c->d_tape.release();
+    if (c->h_tape) cudaFreeHost(c->h_tape);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return WCFE_OK;
+}
+
+int wcfe_set_params(wcfe_ctx *c, const wcfe_params *p) {
+    if (!c || !p) return WCFE_ERR_ARG;
+    int rc = check_params(c, p);
+    if (rc) return rc;
+    c->prm = *p; make_consts(c);
+    return WCFE_OK;
+}
+
+int wcfe_set_stream(wcfe_ctx *c, void *cuda_stream) {
+    if (!c) return WCFE_ERR_ARG;
+    cudaStreamSynchronize(c->stream);
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return WCFE_OK;
+}
+
+const char *wcfe_last_error(wcfe_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne, const int *tri) {
+    if (!c || surface < 0 || surface > 1 || nn <= 0 || ne <= 0 || !xyz || !tri) return fail(c, WCFE_ERR_ARG, "upload_mesh: bad arguments (empty meshes are not simulated)");
+    for (int q = 0; q < 3 * ne; q++) if (tri[q] < 0 || tri[q] >= nn) return fail(c, WCFE_ERR_ARG, "upload_mesh: triangle refers to a vertex outside [0, nn)");
+    CK(cudaSetDevice(c->device));
+    Surface &s = c->s[surface];
+    s.nn = nn; s.ne = ne; s.np = (nn + 31) / 32 * 32; s.nep = (ne + 31) / 32 * 32;
+    s.tri.assign(tri, tri + 3 * (size_t)ne);
+    // vertex -> triangle CSR in ascending triangle order (nondestructivetrimesh.cpp:138-194)
+    s.ring_ptr.assign((size_t)nn + 1, 0);
+    for (int q = 0; q < 3 * ne; q++) s.ring_ptr[tri[q] + 1]++;
+    for (int v = 0; v < nn; v++) s.ring_ptr[v + 1] += s.ring_ptr[v];
+    s.ring.assign((size_t)3 * ne, 0);
+    {
+        std::vector<int> fill((size_t)nn, 0);
+        for (int e = 0; e < ne; e++) for (int j = 0; j < 3; j++) { const int v = tri[3 * e + j]; s.ring[s.ring_ptr[v] + fill[v]++] = (e << 2) | j; }
+    }
+    // boundary vertices: endpoints of edges with an odd number of incident triangles (:527-543)
+    s.is_bnd.assign((size_t)nn, 0);
+    {
+        std::vector<unsigned long long> edges((size_t)3 * ne);
+        for (int e = 0; e < ne; e++) for (int j = 0; j < 3; j++) {
+            unsigned long long a = (unsigned)tri[3 * e + j], b = (unsigned)tri[3 * e + (j + 1) % 3];
+            if (a > b) std::swap(a, b);
+            edges[(size_t)3 * e + j] = (a << 32) | b;
+        }
+        std::sort(edges.begin(), edges.end());
+        for (size_t q = 0; q < edges.size();) {
+            size_t r = q;
+            while (r < edges.size() && edges[r] == edges[q]) r++;
+            if ((r - q) % 2 == 1) { s.is_bnd[edges[q] >> 32] = 1; s.is_bnd[edges[q] & 0xffffffffu] = 1; }
+            q = r;
+        }
+    }
+    // geometry statistics
+    s.max_edge = 0; s.max_tri_area = 0; s.area = 0;
+    for (int e = 0; e < ne; e++) {
+        const double *a = xyz + 3 * tri[3 * e], *b = xyz + 3 * tri[3 * e + 1], *d = xyz + 3 * tri[3 * e + 2];
+        const double e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {d[0] - a[0], d[1] - a[1], d[2] - a[2]}, e3[3] = {d[0] - b[0], d[1] - b[1], d[2] - b[2]};
+        const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+        const double ar = 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+        s.area += ar; s.max_tri_area = std::max(s.max_tri_area, ar);
+        s.max_edge = std::max({s.max_edge, std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]), std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]),
+                               std::sqrt(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2])});
+    }
+    // device connectivity (SoA)
+    {
+        std::vector<int> soa((size_t)3 * s.nep, 0);
+        for (int e = 0; e < ne; e++) for (int j = 0; j < 3; j++) soa[(size_t)j * s.nep + e] = tri[3 * e + j];
+        CK(s.d_tri.alloc(soa.size())); CK(cudaMemcpy(s.d_tri.p, soa.data(), sizeof(int) * soa.size(), cudaMemcpyHostToDevice));
+        CK(s.d_ring_ptr.alloc((size_t)nn + 1)); CK(cudaMemcpy(s.d_ring_ptr.p, s.ring_ptr.data(), sizeof(int) * ((size_t)nn + 1), cudaMemcpyHostToDevice));
+        CK(s.d_ring.alloc(s.ring.size())); CK(cudaMemcpy(s.d_ring.p, s.ring.data(), sizeof(int) * s.ring.size(), cudaMemcpyHostToDevice));
+    }
+    const size_t np = s.np;
+    CK(s.x.alloc(3 * np)); CK(s.V.alloc(3 * np)); CK(s.A.alloc(3 * np)); CK(s.ea[0].alloc(6 * np)); CK(s.ea[1].alloc(6 * np));
+    s.ea_cur = 0;
+    int rc;
+    if ((rc = put_field(c, s.x.p, xyz, nn, s.np, 3))) return rc;
+    CK(cudaMemset(s.V.p, 0, sizeof(double) * 3 * np)); CK(cudaMemset(s.A.p, 0, sizeof(double) * 3 * np));
+    CK(cudaMemset(s.ea[0].p, 0, sizeof(double) * 6 * np)); CK(cudaMemset(s.ea[1].p, 0, sizeof(double) * 6 * np));
+    s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
+    if (surface == WCFE_CELL) {
+        CK(s.X.alloc(3 * np)); CK(cudaMemcpy(s.X.p, s.x.p, sizeof(double) * 3 * np, cudaMemcpyDeviceToDevice));
+        CK(s.cA.alloc(np)); CK(s.cB.alloc(np)); CK(s.cC.alloc(np)); CK(s.fa.alloc(3 * np)); CK(s.asum.alloc(np));
+        if ((rc = fill_field(c, s.cA.p, nn, s.np, 1, c->prm.c_A_init))) return rc;        // main.cpp:672
+        CK(cudaMemset(s.cB.p, 0, sizeof(double) * np)); CK(cudaMemset(s.cC.p, 0, sizeof(double) * np));
+        CK(cudaMemset(s.fa.p, 0, sizeof(double) * 3 * np)); CK(cudaMemset(s.asum.p, 0, sizeof(double) * np));
+        // boundary tables: candidates (nj, nint) in the reference's scan order (UL:1479-1495)
+        s.bnd_node.clear();
+        std::vector<int> index((size_t)nn, -1), cand_ptr(1, 0), cand;
+        for (int v = 0; v < nn; v++) {
+            if (!s.is_bnd[v]) continue;
+            index[v] = (int)s.bnd_node.size(); s.bnd_node.push_back(v);
+            for (int r = s.ring_ptr[v]; r < s.ring_ptr[v + 1]; r++) {
+                const int *t = tri + 3 * (s.ring[r] >> 2);
+                for (int enj = 0; enj < 3; enj++) {
+                    const int nj = t[enj];
+                    if (s.is_bnd[nj] && nj != v) {
+                        int nint = v;
+                        for (int enk = 0; enk < 3; enk++) if (t[enk] != nj && t[enk] != v) { nint = t[enk]; break; }
+                        cand.push_back(nj); cand.push_back(nint);
+                    }
+                }
+            }
+            cand_ptr.push_back((int)cand.size() / 2);
+        }
+        s.nb = (int)s.bnd_node.size();
+        if (cand.empty()) cand.push_back(0);
+        CK(s.d_bnd_node.alloc(std::max(1, s.nb))); CK(s.d_bnd_index.alloc(nn)); CK(s.d_cand_ptr.alloc(cand_ptr.size())); CK(s.d_cand.alloc(cand.size()));
+        if (s.nb) CK(cudaMemcpy(s.d_bnd_node.p, s.bnd_node.data(), sizeof(int) * s.nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s.d_bnd_index.p, index.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s.d_cand_ptr.p, cand_ptr.data(), sizeof(int) * cand_ptr.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s.d_cand.p, cand.data(), sizeof(int) * cand.size(), cudaMemcpyHostToDevice));
+        CK(s.d_bnd_buf.alloc((size_t)16 * std::max(1, s.nb)));
+        CK(c->d_flags.alloc(nn)); CK(c->d_loc_bond.alloc(nn)); CK(c->d_loc_cnt.alloc(nn)); CK(c->d_loc_first.alloc(nn)); CK(c->d_ap_fire.alloc(nn));
+        CK(cudaMemset(c->d_flags.p, 0, sizeof(int) * nn)); CK(cudaMemset(c->d_loc_bond.p, 0xff, sizeof(int) * nn));
+        CK(cudaMemset(c->d_loc_cnt.p, 0, sizeof(int) * nn)); CK(cudaMemset(c->d_loc_first.p, 0xff, sizeof(int) * nn)); CK(cudaMemset(c->d_ap_fire.p, 0, sizeof(int) * nn));
+        CK(c->d_partials.alloc((size_t)4 * ((nn + kBlock - 1) / kBlock)));
+        update_box(c, xyz, nn);
+    } else {
+        s.X.release();
+        if ((rc = build_grid(c, xyz))) return rc;
+    }
+    if ((rc = build_buckets(c))) return rc;
+    if (c->debug) { if ((rc = alloc_debug(c, surface))) return rc; }
+    c->have_predict[surface] = false;
+    return WCFE_OK;
+}
+
+int wcfe_mesh_sizes(wcfe_ctx *c, int surface, int *nn, int *ne) {
+    if (!c || surface < 0 || surface > 1) return WCFE_ERR_ARG;
+    if (nn) *nn = c->s[surface].nn;
+    if (ne) *ne = c->s[surface].ne;
+    return WCFE_OK;
+}
+
+int wcfe_upload_state(wcfe_ctx *c, int surface, int field, const double *host) {
+    if (!c || surface < 0 || surface > 1 || !host) return WCFE_ERR_ARG;
+    if (field == WCFE_F_XPREV) return fail(c, WCFE_ERR_ARG, "X_prev is read-only");
+    Surface &s = c->s[surface];
+    double *dev = field_dev(c, surface, field);
+    const int w = width_of(field);
+    if (!s.nn || !dev || !w) return fail(c, WCFE_ERR_ARG, "upload_state: no such field on this surface (or no mesh)");
+    CK(cudaSetDevice(c->device));
+    int rc = put_field(c, dev, host, s.nn, s.np, w);
+    if (rc) return rc;
+    if (field == WCFE_F_X) {
+        if (surface == WCFE_CELL) { CK(cudaMemcpyAsync(s.X.p, s.x.p, sizeof(double) * 3 * s.np, cudaMemcpyDeviceToDevice, c->stream)); update_box(c, host, s.nn); }
+        else { rc = build_grid(c, host); if (rc) return rc; }
+    }
+    return WCFE_OK;
+}
+
+int wcfe_download_state(wcfe_ctx *c, int surface, int field, double *host) {
+    if (!c || surface < 0 || surface > 1 || !host) return WCFE_ERR_ARG;
+    Surface &s = c->s[surface];
+    const double *dev = field_dev(c, surface, field);
+    const int w = width_of(field);
+    if (!s.nn || !dev || !w) return fail(c, WCFE_ERR_ARG, "download_state: no such field on this surface (or no mesh)");
+    CK(cudaSetDevice(c->device));
+    return get_field(c, dev, host, s.nn, s.np, w);
+}
+
+int wcfe_set_rng(wcfe_ctx *c, int mode, unsigned int seed) {
+    if (!c || (mode != WCFE_RNG_GLIBC_REPLAY && mode != WCFE_RNG_PHILOX)) return WCFE_ERR_ARG;
+    c->rng_mode = mode; c->seed = seed; c->rng.seed(seed); c->step = 0;
+    return WCFE_OK;
+}
+
+int wcfe_set_debug(wcfe_ctx *c, int on) {
+    if (!c) return WCFE_ERR_ARG;
+    c->debug = on ? 1 : 0;
+    if (on) { int rc; if ((rc = alloc_debug(c, 0))) return rc; if ((rc = alloc_debug(c, 1))) return rc; }
+    return WCFE_OK;
+}
+
+int wcfe_predict(wcfe_ctx *c, int surface, double dt, double t_curr, double *xyz_new_out) {
+    (void)t_curr;
+    int rc = ready(c);
+    if (rc) return rc;
+    if (surface < 0 || surface > 1) return WCFE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    Surface &s = c->s[surface];
+    if (surface == WCFE_CELL) {
+        k_predict_cell<<<(s.nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(s.nn, s.np, s.x.p, s.X.p, s.V.p, s.A.p, dt);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    // substrate: x_new = x + 0*dt*V_hlf (main.cpp:299) == x; V_hlf itself is formed inside the update kernel
+    c->have_predict[surface] = true;
+    if (xyz_new_out) return get_field(c, s.x.p, xyz_new_out, s.nn, s.np, 3);
+    return WCFE_OK;
+}
+
+int wcfe_commit(wcfe_ctx *c, int surface, const double *xyz_final) {
+    int rc = ready(c);
+    if (rc) return rc;
+    if (surface < 0 || surface > 1) return WCFE_ERR_ARG;
+    if (!c->have_predict[surface]) return fail(c, WCFE_ERR_ARG, "commit without predict");
+    if (!xyz_final) return WCFE_OK;
+    CK(cudaSetDevice(c->device));
+    Surface &s = c->s[surface];
+    if (surface == WCFE_SUBS) return WCFE_OK;   // frozen substrate: positions are what they were
+    rc = put_field(c, s.x.p, xyz_final, s.nn, s.np, 3);
+    if (rc) return rc;
+    update_box(c, xyz_final, s.nn);
+    return WCFE_OK;
+}
+
+int wcfe_update(wcfe_ctx *c, double dt_req, double dt_real, double t_curr) {
+    int rc = ready(c);
+    if (rc) return rc;
+    if (!c->have_predict[WCFE_CELL]) return fail(c, WCFE_ERR_ARG, "update without predict(cell)");
+    CK(cudaSetDevice(c->device));
+    if ((rc = stage_tape(c, 1))) return rc;
+    if ((rc = launch_update(c, dt_req, dt_real, t_curr, c->d_tape.p))) return rc;
+    c->have_predict[0] = c->have_predict[1] = false;
+    c->t_last = t_curr + dt_real;
+    return check_device_errors(c);
+}
+
+int wcfe_step_n(wcfe_ctx *c, int n, double dt, double *t_io) {
+    int rc = ready(c);
+    if (rc) return rc;
+    if (n < 0 || !t_io) return WCFE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    if ((rc = stage_tape(c, n))) return rc;
+    Surface &cs = c->s[WCFE_CELL];
+    double t = *t_io;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int q = 0; q < n; q++) {
+        k_predict_cell<<<(cs.nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt);
+        c->launches++;
+        const unsigned int *tape = c->d_tape.p ? c->d_tape.p + (size_t)q * cs.nb : nullptr;
+        if ((rc = launch_update(c, dt, dt, t, tape))) return rc;
+        t += dt;   // sim->m_curr_t += accum_dt (main.cpp:405)
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
+    *t_io = t; c->t_last = t;
+    return check_device_errors(c);
+}
+
+int wcfe_step_n_roundtrip(wcfe_ctx *c, int n, double dt, double *t_io, long long *h2d, long long *d2h) {
+    int rc = ready(c);
+    if (rc) return rc;
+    if (n < 0 || !t_io) return WCFE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    Surface &cs = c->s[WCFE_CELL], &ss = c->s[WCFE_SUBS];
+    const size_t bc = sizeof(double) * 3 * cs.np, bs = sizeof(double) * 3 * ss.np;
+    if ((rc = ensure_stage(c, bc + bs + 64))) return rc;
+    if ((rc = stage_tape(c, n))) return rc;
+    char *hc = (char *)c->h_stage, *hs = hc + bc, *hd = hs + bs;
+    double t = *t_io;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int q = 0; q < n; q++) {
+        k_predict_cell<<<(cs.nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt);
+        c->launches++;
+        // predicted positions to the host integrator, accepted positions back (SoA images; the AoS shuffle is host work)
+        CK(cudaMemcpyAsync(hc, cs.x.p, bc, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(hs, ss.x.p, bs, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));                    // the host integrator would run here
+        CK(cudaMemcpyAsync(cs.x.p, hc, bc, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(ss.x.p, hs, bs, cudaMemcpyHostToDevice, c->stream));
+        const unsigned int *tape = c->d_tape.p ? c->d_tape.p + (size_t)q * cs.nb : nullptr;
+        if ((rc = launch_update(c, dt, dt, t, tape))) return rc;
+        CK(cudaMemcpyAsync(hd, c->d_diag.p, 64, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        t += dt;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
+    if (h2d) *h2d = (long long)(bc + bs);
+    if (d2h) *d2h = (long long)(bc + bs + 64);
+    *t_io = t; c->t_last = t;
+    return check_device_errors(c);
+}
+
+int wcfe_get_diagnostics(wcfe_ctx *c, double *out8) {
+    if (!c || !out8) return WCFE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out8, c->d_diag.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    out8[4] = out8[5] = 0.0;
+    if (c->debug) {   // |Res| norms from the captured residuals
+        for (int q = 0; q < 2; q++) {
+            Surface &s = c->s[q];
+            if (!s.g_res.p) continue;
+            std::vector<double> r((size_t)3 * s.nn);
+            int rc = get_field(c, s.g_res.p, r.data(), s.nn, s.np, 3);
+            if (rc) return rc;
+            double acc = 0; for (double v : r) acc += v * v;
+            out8[4 + q] = std::sqrt(acc);
+        }
+    }
+    out8[6] = (double)c->step; out8[7] = c->t_last;
+    return WCFE_OK;
+}
+
+int wcfe_get_discrete(wcfe_ctx *c, int which, int *out) {
+    if (!c || !out || !c->s[0].nn) return WCFE_ERR_ARG;
+    const int nn = c->s[0].nn;
+    const int *src = nullptr;
+    switch (which) {
+    case WCFE_D_LOC_BOND: src = c->d_loc_bond.p; break;
+    case WCFE_D_LOC_FORCE_CNT: src = c->d_loc_cnt.p; break;
+    case WCFE_D_LOC_FORCE_FIRST: src = c->d_loc_first.p; break;
+    case WCFE_D_AP_FIRE: src = c->d_ap_fire.p; break;
+    case WCFE_D_FA_RESET: case WCFE_D_CC_CLAMP: src = c->d_flags.p; break;
+    default: return WCFE_ERR_ARG;
+    }
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, src, sizeof(int) * nn, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (which == WCFE_D_FA_RESET) for (int i = 0; i < nn; i++) out[i] = out[i] & 1;
+    if (which == WCFE_D_CC_CLAMP) for (int i = 0; i < nn; i++) out[i] = (out[i] >> 1) & 1;
+    if (which == WCFE_D_AP_FIRE) for (int i = 0; i < nn; i++) if (!c->s[0].is_bnd[i]) out[i] = 0;
+    return WCFE_OK;
+}
+
+int wcfe_get_boundary_flags(wcfe_ctx *c, int surface, int *out) {
+    if (!c || surface < 0 || surface > 1 || !out) return WCFE_ERR_ARG;
+    for (int i = 0; i < c->s[surface].nn; i++) out[i] = c->s[surface].is_bnd[i];
+    return WCFE_OK;
+}
+
+long long wcfe_kernel_launches(wcfe_ctx *c) { return c ? c->launches : 0; }
+double wcfe_last_step_ms(wcfe_ctx *c) { return c ? c->last_ms : 0.0; }
+
+int wcfe_force_field(wcfe_ctx *c, int which, double dt, double t_curr, double *out, double *mm, double *res_ea) {
+    (void)dt; (void)t_curr;
+    if (!c || !out) return WCFE_ERR_ARG;
+    if (!c->debug) return fail(c, WCFE_ERR_ARG, "force_field: enable wcfe_set_debug(1) before the update whose forces you want");
+    const int surface = which >= 5 ? WCFE_SUBS : WCFE_CELL;
+    Surface &s = c->s[surface];
+    const double *src = nullptr;
+    switch (which) {
+    case 0: case 5: src = s.g_res.p; break;
+    case 1: case 6: src = s.g_ffa.p; break;
+    case 2: src = s.g_fap.p; break;
+    case 3: src = s.g_fbend.p; break;
+    case 4: src = s.g_farea.p; break;
+    default: return WCFE_ERR_ARG;
+    }
+    if (!src) return fail(c, WCFE_ERR_ARG, "force_field: nothing captured yet");
+    CK(cudaSetDevice(c->device));
+    int rc = get_field(c, src, out, s.nn, s.np, 3);
+    if (rc) return rc;
+    if (mm) { if ((rc = get_field(c, s.g_mm.p, mm, s.nn, s.np, 1))) return rc; }
+    if (res_ea) { if ((rc = get_field(c, s.g_rea.p, res_ea, s.nn, s.np, 6))) return rc; }
+    return WCFE_OK;
+}
+
+int wcfe_sync(wcfe_ctx *c) {
+    if (!c) return WCFE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return WCFE_OK;
+}
+
+}   // extern "C"

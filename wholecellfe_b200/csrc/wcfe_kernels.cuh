@@ -1,0 +1,398 @@
+// wcfe_kernels.cuh -- CUDA kernels of the UL step (sm_100a), general 3-D path ("v1": node-centric gather).
+//
+// Data layout in HBM: struct-of-arrays FP64.  A field of width w lives in one allocation of w*np doubles,
+// component c at [c*np + node] (np = node count padded to 32, so every component starts 256-B aligned and
+// a warp's loads of one component are one or two 128-B lines).  Connectivity is int32 SoA tri[c*nep + e].
+//
+// Deterministic assembly without atomics: every nodal sum (Res, Res_ea, MM, node area) is a gather over the
+// vertex->triangle CSR in ascending element order -- the reference's own summation order at a node
+// (serial scatter-add in element order, UL_growth_explicit.cpp:692-705) -- evaluated by the thread that owns
+// the node.  Elements are recomputed by each of their three nodes (the per-element closed form is ~0.4 kFLOP,
+// wcfe_math.cuh); nothing is staged through HBM.
+#pragma once
+#include "wcfe_math.cuh"
+
+namespace wcfe {
+
+constexpr int kBlock = 128;
+constexpr int kMaxLoc = 8;   // containing triangles recorded per anchor (a point on a mesh vertex has ~6)
+
+struct SurfView {            // device pointers of one surface
+    int nn, np, ne, nep;
+    const int *tri;          // [3*nep]
+    const int *ring_ptr;     // [nn+1]
+    const int *ring;         // (element<<2)|slot, ascending element
+    double *x, *X;           // [3*np] current / start-of-step positions (substrate: X == x, frozen)
+    double *V, *A;           // [3*np]
+    const double *ea_in;     // [6*np]
+    double *ea_out;          // [6*np]
+    double *cC, *fa, *asum;  // cell only: [np], [3*np], [np]
+};
+
+struct GridView {            // uniform grid over substrate triangles (candidate filter for point location)
+    int nx, ny;
+    double x0, y0, inv_h;
+    const int *ptr, *items;  // CSR cell -> triangles, ascending triangle index inside a cell
+};
+
+struct BucketView {          // triangle -> anchored cell nodes, rebuilt every step, no reset pass:
+    unsigned long long *head;   // [ne_subs] (epoch<<32 | count); a stale epoch reads as count 0
+    int *items;                 // [ne_subs*cap]
+    int cap;
+    unsigned int epoch;
+};
+
+struct BoundaryView {        // cell boundary vertices in ascending vertex order (the RNG draw order, UL:1463-1465)
+    int nb;
+    const int *node;         // [nb]
+    const int *index;        // [nn] ordinal or -1
+    const int *cand_ptr;     // [nb+1]
+    const int *cand;         // pairs (nj, nint) in the reference's one-ring scan order (UL:1479-1507)
+    double *buf;             // [16*nb] per boundary vertex: f_pre[3], Res[3], MM, tl, normal[2], ...
+};
+
+struct DebugView {           // optional force-field capture (parity gate on nodal forces)
+    double *res, *f_fa, *f_ap, *f_bend, *f_area, *mm, *res_ea;   // cell or substrate set
+};
+
+enum : int { ERR_BUCKET_OVERFLOW = 1, ERR_LOC_OVERFLOW = 2, ERR_NAN = 4, ERR_REGION = 8 };
+
+// ---- predictor: driverVelocities_Explicit + inline predictor (UL:103-124, main.cpp:224-242) ---------------
+__global__ void __launch_bounds__(kBlock) k_predict_cell(int nn, int np, double *__restrict__ x, double *__restrict__ X,
+                                                         const double *__restrict__ V, const double *__restrict__ A, double dt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn) return;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double xo = x[c * np + i];
+        double vh = V[c * np + i] + (dt / 2.0) * A[c * np + i];
+        if (c == 2) vh = 0.0;
+        X[c * np + i] = xo;
+        x[c * np + i] = xo + dt * vh;
+    }
+}
+
+// ---- point location of one anchor in the substrate -------------------------------------------------------
+// visits candidates in ascending triangle index; calls f(tri, A[3], A_tri) for every containing triangle
+template <class F>
+__device__ __forceinline__ void locate(const GridView &g, const SurfView &s, const double pt[3], F &&f) {
+    const double fx = (pt[0] - g.x0) * g.inv_h, fy = (pt[1] - g.y0) * g.inv_h;
+    if (!(fx >= 0.0) || !(fy >= 0.0) || fx >= (double)g.nx || fy >= (double)g.ny) return;
+    const int cidx = (int)fy * g.nx + (int)fx;
+    const int b = g.ptr[cidx], e = g.ptr[cidx + 1];
+    for (int k = b; k < e; k++) {
+        const int t = g.items[k];
+        const int i0 = s.tri[t], i1 = s.tri[s.nep + t], i2 = s.tri[2 * s.nep + t];
+        const double n1[3] = {s.x[i0], s.x[s.np + i0], s.x[2 * s.np + i0]};
+        const double n2[3] = {s.x[i1], s.x[s.np + i1], s.x[2 * s.np + i1]};
+        const double n3[3] = {s.x[i2], s.x[s.np + i2], s.x[2 * s.np + i2]};
+        double Ar[3], At;
+        if (point_in_triangle(n1, n2, n3, pt, Ar, At)) f(t, Ar, At);
+    }
+}
+
+// ---- updateFA (UL:2005-2114) + anchor location for calculateForce_FA_subs (UL:1301-1340) ---------------------
+// One thread per cell node.  Substrate frozen (main.cpp:299 `0*`): subs_u == 0 whatever triangle holds the anchor,
+// so the reference's first point location only matters for the discrete-state record (debug).
+__global__ void __launch_bounds__(kBlock) k_bond(SurfView c, SurfView s, GridView g, BucketView bk, Consts k, double dt,
+                                                 double ix0, double ix1, double iy0, double iy1,
+                                                 int *__restrict__ d_flags, int *__restrict__ d_loc_bond,
+                                                 int *__restrict__ d_loc_cnt, int *__restrict__ d_loc_first, int debug, int *__restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.nn) return;
+    const double xi[3] = {c.x[i], c.x[c.np + i], c.x[2 * c.np + i]};
+    const double Xi[3] = {c.X[i], c.X[c.np + i], c.X[2 * c.np + i]};
+    double fa[3] = {c.fa[i], c.fa[c.np + i], c.fa[2 * c.np + i]};
+    double cC = c.cC[i];
+    if (debug) {
+        const double pt0[3] = {Xi[0] - fa[0], Xi[1] - fa[1], Xi[2] - fa[2]};     // UL:2020
+        int last = -1;
+        locate(g, s, pt0, [&](int t, const double *, double) { last = t; });     // last match wins, UL:2057-2064
+        d_loc_bond[i] = last;
+    }
+    const double cell_u[3] = {xi[0] - Xi[0], xi[1] - Xi[1], xi[2] - Xi[2]};      // UL:2016
+    const double subs_u[3] = {0.0, 0.0, 0.0};
+    const int fl = bond_update(k, dt, cell_u, subs_u, fa, cC);
+    c.fa[i] = fa[0]; c.fa[c.np + i] = fa[1]; c.fa[2 * c.np + i] = fa[2];
+    c.cC[i] = cC;
+    d_flags[i] = fl;
+    // anchor on the substrate for the force exchange: x_cell - fa_u (UL:1303), current substrate coordinates
+    const double pt[3] = {xi[0] - fa[0], xi[1] - fa[1], xi[2] - fa[2]};
+    // the substrate kernel only looks for anchors near substrate nodes inside the padded region sized on the host
+    if (!(pt[0] >= ix0 && pt[0] <= ix1 && pt[1] >= iy0 && pt[1] <= iy1)) atomicOr(err, ERR_REGION);
+    int cnt = 0, first = -1;
+    locate(g, s, pt, [&](int t, const double *, double) {
+        if (cnt == 0) first = t;
+        cnt++;
+        // append node i to triangle t's bucket (epoch-stamped counter: no reset pass between steps)
+        unsigned long long *h = bk.head + t;
+        unsigned long long old = *h, want;
+        int slot;
+        do {
+            const unsigned long long seen = old;
+            if ((unsigned int)(seen >> 32) != bk.epoch) { want = ((unsigned long long)bk.epoch << 32) | 1ull; slot = 0; }
+            else { want = seen + 1ull; slot = (int)(unsigned int)seen; }
+            old = atomicCAS(h, seen, want);
+            if (old == seen) break;
+        } while (true);
+        if (slot < bk.cap) bk.items[(size_t)t * bk.cap + slot] = i; else atomicOr(err, ERR_BUCKET_OVERFLOW);
+    });
+    d_loc_cnt[i] = cnt; d_loc_first[i] = first;
+}
+
+// ---- gather over the one-ring: shared by cell and substrate ------------------------------------------------------
+struct NodeSums { double res[3], rea[6], mm, asum, area, cen[3]; };
+
+__device__ __forceinline__ void gather_ring(const SurfView &s, int i, double mu, double tk, double theta_g, double thick, NodeSums &a) {
+    for (int k = 0; k < 3; k++) { a.res[k] = 0.0; a.cen[k] = 0.0; }
+    for (int k = 0; k < 6; k++) a.rea[k] = 0.0;
+    a.mm = 0.0; a.asum = 0.0; a.area = 0.0;
+    double eai[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) eai[q] = s.ea_in[q * s.np + i];
+    const int rb = s.ring_ptr[i], re = s.ring_ptr[i + 1];
+    for (int r = rb; r < re; r++) {
+        const int code = s.ring[r];
+        const int e = code >> 2, slot = code & 3;
+        int id[3] = {s.tri[e], s.tri[s.nep + e], s.tri[2 * s.nep + e]};
+        double X[3][3], x[3][3], e6[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { X[j][c] = s.X[c * s.np + id[j]]; x[j][c] = s.x[c * s.np + id[j]]; }
+        }
+        // ea at the integration point: 1/3 e1 + 1/3 e2 + 1/3 e3 (UL:781)
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            e6[q] = 1.0 / 3.0 * s.ea_in[q * s.np + id[0]] + 1.0 / 3.0 * s.ea_in[q * s.np + id[1]] + 1.0 / 3.0 * s.ea_in[q * s.np + id[2]];
+        ElemOut o;
+        elem_eval(X, x, e6, mu, tk, theta_g, thick, o);
+#pragma unroll
+        for (int c = 0; c < 3; c++) a.res[c] += slot == 0 ? -(o.r1[c] + o.r2[c]) : (slot == 1 ? o.r1[c] : o.r2[c]);
+#pragma unroll
+        for (int q = 0; q < 6; q++) a.rea[q] += (1. / 3.) * (o.eas[q] - eai[q]) * o.A0 * thick;       // UL:911
+        a.mm += (1. / 3.) * o.A0 * thick;                                                               // UL:913
+        a.asum += o.a_cur / 3;                                                                          // UL:1251
+        if (slot == 0) {                                                                                // each element once: UL:1655-1661
+            a.area += o.a_cur;
+#pragma unroll
+            for (int c = 0; c < 3; c++) a.cen[c] += (1. / 3.) * ((x[0][c] + x[1][c]) + x[2][c]) * o.a_cur;
+        }
+    }
+}
+
+// deterministic block reduction (fixed tree) of 4 doubles; result valid in thread 0
+__device__ __forceinline__ void block_reduce4(double v[4], double *sh /*[4*32]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], off);
+    if (lane == 0) for (int q = 0; q < 4; q++) sh[q * 32 + wid] = v[q];
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double t = lane < nw ? sh[q * 32 + lane] : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+            v[q] = t;
+        }
+    }
+}
+
+// ---- updateForces_Explicit, cell overload (UL:508-630), fused: residual gather + all nodal forces + update ----------
+// Boundary vertices need the total area (UL:589), a grid-wide sum of this very kernel's element areas: they park
+// their partial force in BoundaryView::buf and are finished by k_boundary_finish.
+template <bool DBG>
+__global__ void __launch_bounds__(kBlock) k_cell_node(SurfView s, BoundaryView b, Consts k, double dt, double dt_real, double t_tot,
+                                                      int rng_mode, const unsigned int *__restrict__ tape, unsigned int seed, unsigned int step,
+                                                      double ap_threshold, double *__restrict__ partials, int *__restrict__ d_ap_fire, DebugView dbg) {
+    __shared__ double sh[4 * 32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[4] = {0.0, 0.0, 0.0, 0.0};
+    if (i < s.nn) {
+        const double theta_g = 1.0 + k.thetag_dot * dt_real;
+        NodeSums a;
+        gather_ring(s, i, k.mu_cell, t_act_of(k, t_tot) * k.kappa, theta_g, k.thick, a);
+        red[0] = a.area; red[1] = a.cen[0]; red[2] = a.cen[1]; red[3] = a.cen[2];
+        const int np = s.np;
+        double V[3] = {s.V[i], s.V[np + i], s.V[2 * np + i]};
+        double A[3] = {s.A[i], s.A[np + i], s.A[2 * np + i]};
+        double Vh[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) Vh[c] = V[c] + (dt / 2.0) * A[c];                     // UL:118
+        Vh[2] = 0.0;
+        // integrin force on the cell node (UL:1258-1261; kMD UL:1246-1269)
+        const double u[3] = {s.fa[i], s.fa[np + i], s.fa[2 * np + i]};
+        const double cC = s.cC[i];
+        double fi[3], F_FA[3], F_vd[3];
+        integrin_force(k, u, fi);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { F_FA[c] = -cC * fi[c] * a.asum * k.rho_i_max; F_vd[c] = -k.drag * Vh[c]; }   // UL:1259, :571
+        s.asum[i] = a.asum;
+        // strain update (UL:607-612)
+#pragma unroll
+        for (int q = 0; q < 6; q++) s.ea_out[q * np + i] = s.ea_in[q * np + i] + a.rea[q] / a.mm;
+        if (DBG) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { dbg.res[c * np + i] = a.res[c]; dbg.f_fa[c * np + i] = F_FA[c]; dbg.f_ap[c * np + i] = 0.0; dbg.f_bend[c * np + i] = 0.0; dbg.f_area[c * np + i] = 0.0; }
+            dbg.mm[i] = a.mm;
+#pragma unroll
+            for (int q = 0; q < 6; q++) dbg.res_ea[q * np + i] = a.rea[q];
+        }
+        const int bi = b.index[i];
+        if (bi < 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double f = F_vd[c] + F_FA[c] - a.res[c];                            // UL:592 with the boundary-only terms == 0
+                node_update(f, a.mm, k.damp, k.rho, dt, dt_real, Vh[c], V[c], A[c]);
+                s.V[c * np + i] = V[c]; s.A[c * np + i] = A[c];
+            }
+        } else {
+            // boundary vertex: neighbours along the boundary curve (UL:1479-1507), later matches overwrite
+            const double xi[3] = {s.x[i], s.x[np + i], s.x[2 * np + i]};
+            double j1[3] = {0, 0, 0}, j2[3] = {0, 0, 0};
+            for (int q = b.cand_ptr[bi]; q < b.cand_ptr[bi + 1]; q++) {
+                const int nj = b.cand[2 * q], nint = b.cand[2 * q + 1];
+                const double xb[3] = {s.x[nj], s.x[np + nj], s.x[2 * np + nj]};
+                const double xin[3] = {s.x[nint], s.x[np + nint], s.x[2 * np + nint]};
+                if (bnd_is_first(xi, xb, xin)) { j1[0] = xb[0]; j1[1] = xb[1]; j1[2] = xb[2]; }
+                else { j2[0] = xb[0]; j2[1] = xb[1]; j2[2] = xb[2]; }
+            }
+            double nrm[3], tl;
+            bnd_normal(xi, j1, j2, nrm, tl);
+            const double kap = bnd_curvature(xi, j1, j2, tl);
+            // actin polymerisation: one draw per boundary vertex per step (UL:1525-1541)
+            double Pr;
+            if (rng_mode == 0) Pr = (double)tape[bi] / 2147483648.0;
+            else Pr = (double)philox_u32(seed, step, (unsigned int)bi) * (1.0 / 4294967296.0);
+            const bool fire = Pr < ap_threshold;
+            const double factin = fire ? k.ap_quantum * ap_trips(k.ap_density, tl) : 0.0;
+            d_ap_fire[i] = fire ? 1 : 0;
+            double *o = b.buf + (size_t)16 * bi;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double F_b = k.k_bend * kap * nrm[c], F_AP = factin * nrm[c];       // UL:1633, :1542
+                o[c] = ((F_vd[c] + F_b) + F_AP) + F_FA[c];                                // UL:592 up to F_area
+                o[3 + c] = a.res[c];
+                if (DBG) { dbg.f_bend[c * np + i] = F_b; dbg.f_ap[c * np + i] = F_AP; }
+            }
+            o[6] = a.mm; o[7] = tl; o[8] = nrm[0]; o[9] = nrm[1]; o[10] = nrm[2];
+        }
+    }
+    block_reduce4(red, sh);
+    if (threadIdx.x == 0) { for (int q = 0; q < 4; q++) partials[(size_t)4 * blockIdx.x + q] = red[q]; }
+}
+
+// ---- total area / centroid (UL:1641-1667) + area-constraint force and update of the boundary vertices (UL:1670-1763) --
+// single block; partial sums are combined in a fixed order, so the result is bit-reproducible run to run
+template <bool DBG>
+__global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k, int npart, const double *__restrict__ partials,
+                                                          double dt, double dt_real, double *__restrict__ diag, DebugView dbg) {
+    __shared__ double sh[4 * 32];
+    __shared__ double tot[4];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    // strided accumulation in a fixed order, then a fixed tree
+    for (int p = threadIdx.x; p < npart; p += blockDim.x)
+        for (int q = 0; q < 4; q++) v[q] += partials[(size_t)4 * p + q];
+    block_reduce4(v, sh);
+    if (threadIdx.x == 0) {
+        tot[0] = v[0]; tot[1] = v[1] / v[0]; tot[2] = v[2] / v[0]; tot[3] = v[3] / v[0];
+        for (int q = 0; q < 4; q++) diag[q] = tot[q];
+    }
+    __syncthreads();
+    const double area_tot = tot[0];
+    const int np = s.np;
+    for (int bi = threadIdx.x; bi < b.nb; bi += blockDim.x) {
+        const int i = b.node[bi];
+        const double *o = b.buf + (size_t)16 * bi;
+        const double mm = o[6], tl = o[7];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double F_area = -k.k_area * (area_tot - k.area_0) / 2 * tl * o[8 + c];   // UL:1757
+            const double f = (o[c] + F_area) - o[3 + c];
+            double V = s.V[c * np + i], A = s.A[c * np + i];
+            double Vh = V + (dt / 2.0) * A;
+            if (c == 2) Vh = 0.0;
+            node_update(f, mm, k.damp, k.rho, dt, dt_real, Vh, V, A);
+            s.V[c * np + i] = V; s.A[c * np + i] = A;
+            if (DBG) dbg.f_area[c * np + i] = F_area;
+        }
+    }
+}
+
+// ---- updateForces_Explicit, substrate overload (UL:429-504) incl. driverVelocities_Biaxial (UL:275-345) and
+//      calculateForce_FA_subs (UL:1297-1454) as a gather over the per-triangle buckets filled by k_bond -----------------
+template <bool DBG>
+__global__ void __launch_bounds__(kBlock) k_subs_node(SurfView s, SurfView c, BucketView bk, Consts k, double dt, double dt_real, double t_tot,
+                                                      double bx0, double bx1, double by0, double by1, DebugView dbg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.nn) return;
+    const double theta_g = 1.0 + k.thetag_dot * dt_real;
+    NodeSums a;
+    gather_ring(s, i, k.mu_subs, 0.0, theta_g, k.thick, a);
+    const int np = s.np;
+    const double Xi[3] = {s.X[i], s.X[np + i], s.X[2 * np + i]};
+    double F_FA[3] = {0.0, 0.0, 0.0};
+    // force from the cell: only substrate nodes inside the (padded) bounding box of the anchors can receive any
+    if (Xi[0] >= bx0 && Xi[0] <= bx1 && Xi[1] >= by0 && Xi[1] <= by1) {
+        const int rb = s.ring_ptr[i], re = s.ring_ptr[i + 1];
+        for (int r = rb; r < re; r++) {
+            const int code = s.ring[r];
+            const int e = code >> 2, slot = code & 3;
+            const unsigned long long h = bk.head[e];
+            if ((unsigned int)(h >> 32) != bk.epoch) continue;
+            int cnt = (int)(unsigned int)h;
+            if (cnt > bk.cap) cnt = bk.cap;
+            const int i0 = s.tri[e], i1 = s.tri[s.nep + e], i2 = s.tri[2 * s.nep + e];
+            const double n1[3] = {s.x[i0], s.x[np + i0], s.x[2 * np + i0]};
+            const double n2[3] = {s.x[i1], s.x[np + i1], s.x[2 * np + i1]};
+            const double n3[3] = {s.x[i2], s.x[np + i2], s.x[2 * np + i2]};
+            // ascending cell-node order inside the bucket (insertion order is not deterministic)
+            int prev = -1;
+            for (int m = 0; m < cnt; m++) {
+                int ni = 0x7fffffff;
+                for (int q = 0; q < cnt; q++) { const int v = bk.items[(size_t)e * bk.cap + q]; if (v > prev && v < ni) ni = v; }
+                prev = ni;
+                const double u[3] = {c.fa[ni], c.fa[c.np + ni], c.fa[2 * c.np + ni]};
+                const double pt[3] = {c.x[ni] - u[0], c.x[c.np + ni] - u[1], c.x[2 * c.np + ni] - u[2]};   // UL:1303
+                double Ar[3], At;
+                point_in_triangle(n1, n2, n3, pt, Ar, At);
+                double fi[3];
+                integrin_force(k, u, fi);
+                const double w = Ar[slot] / At, cC = c.cC[ni], As = c.asum[ni];
+#pragma unroll
+                for (int d = 0; d < 3; d++) F_FA[d] += cC * fi[d] * w * As * k.rho_i_max;                  // UL:1414-1422
+            }
+        }
+    }
+    double V[3] = {s.V[i], s.V[np + i], s.V[2 * np + i]};
+    double A[3] = {s.A[i], s.A[np + i], s.A[2 * np + i]};
+    double Vh[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) Vh[d] = V[d] + (dt / 2.0) * A[d];
+    Vh[2] = 0.0;
+    // pinned edges, UL:298-341 with Vbiax == 0: all three time windows zero the component; nothing fires at t == t_i, t_f
+    if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {
+        if (Xi[0] < -k.pin_limit || Xi[0] > k.pin_limit) Vh[0] = 0.0;
+        if (Xi[1] > k.pin_limit || Xi[1] < -k.pin_limit) Vh[1] = 0.0;
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double f = F_FA[d] - a.res[d];                                              // UL:471
+        node_update(f, a.mm, k.damp, k.rho, dt, dt_real, Vh[d], V[d], A[d]);
+        s.V[d * np + i] = V[d]; s.A[d * np + i] = A[d];
+    }
+#pragma unroll
+    for (int q = 0; q < 6; q++) s.ea_out[q * np + i] = s.ea_in[q * np + i] + a.rea[q] / a.mm;   // UL:486-491
+    if (DBG) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) { dbg.res[d * np + i] = a.res[d]; dbg.f_fa[d * np + i] = F_FA[d]; }
+        dbg.mm[i] = a.mm;
+#pragma unroll
+        for (int q = 0; q < 6; q++) dbg.res_ea[q * np + i] = a.rea[q];
+    }
+}
+
+}   // namespace wcfe

@@ -1,0 +1,158 @@
+"""Host-side mirror of the reference's UL step interface, on top of the C ABI (include/wcfe.h).
+
+`ULSim` owns one cell + one substrate on one GPU and exposes the reference's call sequence
+(cellBP/main.cpp:168-418): predict (driverVelocities_* + inline predictor), commit (positions the host
+integrator accepted), update (updateFA + the two updateForces_Explicit overloads), plus the El-Topo-free
+`step_n` fast path.  Arrays cross this interface in the reference's own array-of-structs layout.
+"""
+import ctypes as C
+import numpy as np
+from . import _lib as B
+
+
+class WcfeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("wcfe error %d: %s" % (code, msg))
+        self.code = code
+
+
+def default_params(variant="k1"):
+    p = B.Params()
+    L = B.load()
+    rc = L.wcfe_default_params(C.byref(p), B.VARIANTS[variant])
+    if rc:
+        raise WcfeError(rc, "default_params")
+    return p
+
+
+def _d(a):
+    return a.ctypes.data_as(B._dp)
+
+
+class ULSim:
+    def __init__(self, variant="k1", device=0, params=None, stream=None):
+        self.L = B.load()
+        self.variant = variant
+        self.params = params if params is not None else default_params(variant)
+        self.h = C.c_void_p()
+        rc = self.L.wcfe_create(C.byref(self.h), device, C.byref(self.params))
+        if rc:
+            self.h = None
+            raise WcfeError(rc, "wcfe_create failed (no CUDA device %d? the product has no CPU fallback)" % device
+                            if rc == B.ERR_CUDA else "wcfe_create: unsupported / invalid parameters")
+        if stream is not None:
+            self._ck(self.L.wcfe_set_stream(self.h, C.c_void_p(stream)))
+        self.nn = [0, 0]
+        self.ne = [0, 0]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wcfe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc:
+            raise WcfeError(rc, self.L.wcfe_last_error(self.h).decode())
+
+    def set_params(self, params):
+        self._ck(self.L.wcfe_set_params(self.h, C.byref(params)))
+        self.params = params
+
+    def upload_mesh(self, surface, xyz, tri):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        tri = np.ascontiguousarray(tri, dtype=np.int32)
+        if xyz.ndim != 2 or xyz.shape[1] != 3 or tri.ndim != 2 or tri.shape[1] != 3:
+            raise WcfeError(B.ERR_ARG, "xyz must be [N,3] and tri [M,3]")
+        self._ck(self.L.wcfe_upload_mesh(self.h, surface, len(xyz), _d(xyz), len(tri), tri.ctypes.data_as(B._ip)))
+        self.nn[surface] = len(xyz)
+        self.ne[surface] = len(tri)
+
+    def set(self, surface, field, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        if arr.size != self.nn[surface] * B.WIDTH[field]:
+            raise WcfeError(B.ERR_ARG, "field %s: wrong size" % field)
+        self._ck(self.L.wcfe_upload_state(self.h, surface, B.FIELDS[field], _d(arr)))
+
+    def get(self, surface, field):
+        n = self.nn[surface]
+        w = B.WIDTH[field]
+        out = np.empty((n, w) if w > 1 else (n,), dtype=np.float64)
+        self._ck(self.L.wcfe_download_state(self.h, surface, B.FIELDS[field], _d(out)))
+        return out
+
+    def set_rng(self, mode, seed):
+        self._ck(self.L.wcfe_set_rng(self.h, mode, seed))
+
+    def srand(self, seed):
+        self.set_rng(B.RNG_GLIBC_REPLAY, seed)
+
+    def set_debug(self, on):
+        self._ck(self.L.wcfe_set_debug(self.h, 1 if on else 0))
+
+    def predict(self, surface, dt, t_curr, download=True):
+        out = np.empty((self.nn[surface], 3)) if download else None
+        self._ck(self.L.wcfe_predict(self.h, surface, dt, t_curr, _d(out) if download else None))
+        return out
+
+    def commit(self, surface, xyz=None):
+        if xyz is not None:
+            xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        self._ck(self.L.wcfe_commit(self.h, surface, _d(xyz) if xyz is not None else None))
+
+    def update(self, dt_req, dt_real, t_curr):
+        self._ck(self.L.wcfe_update(self.h, dt_req, dt_real, t_curr))
+
+    def step(self, dt, t_curr):
+        """One El-Topo-free step; same signature as the oracle's step()."""
+        t = C.c_double(t_curr)
+        self._ck(self.L.wcfe_step_n(self.h, 1, dt, C.byref(t)))
+        return t.value
+
+    def step_n(self, n, dt, t0):
+        t = C.c_double(t0)
+        self._ck(self.L.wcfe_step_n(self.h, n, dt, C.byref(t)))
+        return t.value
+
+    def step_n_roundtrip(self, n, dt, t0):
+        t = C.c_double(t0)
+        a = C.c_longlong()
+        b = C.c_longlong()
+        self._ck(self.L.wcfe_step_n_roundtrip(self.h, n, dt, C.byref(t), C.byref(a), C.byref(b)))
+        return t.value, a.value, b.value
+
+    def diagnostics(self):
+        out = np.zeros(8)
+        self._ck(self.L.wcfe_get_diagnostics(self.h, _d(out)))
+        return out
+
+    def discrete(self, which):
+        out = np.empty(self.nn[0], dtype=np.int32)
+        self._ck(self.L.wcfe_get_discrete(self.h, B.DISCRETE[which], out.ctypes.data_as(B._ip)))
+        return out
+
+    def boundary_flags(self, surface):
+        out = np.empty(self.nn[surface], dtype=np.int32)
+        self._ck(self.L.wcfe_get_boundary_flags(self.h, surface, out.ctypes.data_as(B._ip)))
+        return out
+
+    def force_field(self, which):
+        w = B.FORCE_FIELDS[which]
+        surf = 1 if w >= 5 else 0
+        n = self.nn[surf]
+        out = np.zeros((n, 3))
+        mm = np.zeros(n)
+        rea = np.zeros((n, 6))
+        self._ck(self.L.wcfe_force_field(self.h, w, 0.0, 0.0, _d(out), _d(mm), _d(rea)))
+        return {"F": out, "MM": mm, "Res_ea": rea}
+
+    def kernel_launches(self):
+        return int(self.L.wcfe_kernel_launches(self.h))
+
+    def last_step_ms(self):
+        return float(self.L.wcfe_last_step_ms(self.h))
+
+    def sync(self):
+        self._ck(self.L.wcfe_sync(self.h))
