@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- element-steps/s of the explicit UL step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[3], "synthetic 1M-triangle cell on 4M-node substrate" -- the
+configuration the metric's roofline target is quoted on; it fits one GPU (1.1 GB of state).  A "step" is one full UL
+step (predict, bond kinetics + point location, cell forces + update, substrate forces + update) over that pair of
+meshes with the state resident in HBM.  N > 1: every rank advances its own independent cell+substrate replica (the
+reference's only parallel mode is independent processes, s_sim_031021_1.sub) -- no data-path collective, weak scaling.
+The state (1.1 GB) is ~9x the 126 MB L2, so successive steps stream from HBM: no explicit L2 flush is needed.
+
+The JSON line carries, beside the base contract:
+  roofline      the dominant kernel (k_subs_node): algorithmic bytes per launch (216 B/substrate node + 12 B/element,
+                SURVEY.md 8d) / its CUDA-event duration measured live, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle's C restatement ("port", grid point location) timed on this box's host on a bounded sample
+  e2e           the same metric through the adapter-mode C-ABI call with host round trips every step
+`--impl reference` times the reference CPU path instead (oracle/_ref where it was built, else the oracle port) on all
+host cores as independent replicas, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+METRIC = "element_steps_per_sec"
+UNIT = "element-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cell-tris", type=int, default=1000000)
+    ap.add_argument("--subs-side", type=int, default=2000, help="substrate nodes per side (2000 -> 4M nodes, 8M triangles)")
+    ap.add_argument("--variant", default="k31", choices=["k1", "k31", "kMD"])
+    ap.add_argument("--dt", type=float, default=2e-5, help="explicit step below the substrate CFL limit h*sqrt(rho/mu) = 5e-5")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-div", type=int, default=16, help="CPU baseline sample = workload / this (both meshes)")
+    return ap.parse_args()
+
+
+def workload_meshes(cell_tris, subs_side):
+    from wholecellfe_b200.meshgen import disk_mesh, square_mesh
+    xc, tc = disk_mesh(cell_tris)
+    xs, ts = square_mesh(subs_side)
+    return xc, tc, xs, ts
+
+
+def algorithmic_bytes(nn_c, ne_c, nn_s, ne_s):
+    """SURVEY.md 8d / BASELINE.md 3.4: every live state word read once + written once, int32 connectivity read once."""
+    return 304 * nn_c + 216 * nn_s + 12 * (ne_c + ne_s)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.stop_flag = False; self.rows = []
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                              timeout=5).decode().strip()
+                self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def time_oracle_port(variant, xc, tc, xs, ts, dt, steps):
+    from oracle.oracle import OracleSim
+    o = OracleSim(variant, xc, tc, xs, ts, use_grid=True)
+    o.srand(1)
+    t = 0.0
+    o.step(dt, t); t += dt        # warm-up (page in, first grid build)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step(dt, t); t += dt
+    return (len(tc) + len(ts)) * steps / (time.perf_counter() - t0)
+
+
+def _replica_worker(args):
+    kind, variant, cell_tris, subs_side, dt, steps, warmup = args
+    xc, tc, xs, ts = workload_meshes(cell_tris, subs_side)
+    if kind == "reference":
+        from oracle.refrun import RefSim
+        sim = RefSim(variant, xc, tc, xs, ts); sim.srand(1)
+    else:
+        from oracle.oracle import OracleSim
+        sim = OracleSim(variant, xc, tc, xs, ts, use_grid=True); sim.srand(1)
+    t = 0.0
+    for _ in range(warmup):
+        sim.step(dt, t); t += dt
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.step(dt, t); t += dt
+    return time.perf_counter() - t0, len(tc) + len(ts)
+
+
+def run_reference_arm(a):
+    """The reference's CPU implementation of the path, all host cores as independent replicas (its only parallel mode)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle.refrun import ref_available
+    cores = os.cpu_count() or 1
+    div = a.cpu_sample_div
+    use_ref = ref_available(a.variant)
+    # the unmodified reference locates anchors by brute force, O(Nn_cell * Ne_subs) twice per step (UL:1309, :2026): at the
+    # bench workload that is ~8e12 predicate evaluations per step, so it is only runnable on a far smaller sample
+    if use_ref:
+        kind, cell_tris, subs_side = "reference", max(600, a.cell_tris // 1024), max(24, a.subs_side // 32)
+    else:
+        kind, cell_tris, subs_side = "port", max(600, a.cell_tris // div), max(24, int(a.subs_side / math.sqrt(div)))
+    steps = max(1, min(a.steps, 4))
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_replica_worker, [(kind, a.variant, cell_tris, subs_side, a.dt, steps, 1)] * cores)
+    wall = max(r[0] for r in res)
+    value = sum(r[1] for r in res) * steps / wall
+    sample = ("%d independent replicas (one per core) x %d steps of a %d-triangle cell on a %d-node substrate (%s point location)"
+              % (cores, steps, cell_tris, subs_side * subs_side, "brute-force" if use_ref else "grid"))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "gpu_launches": 0,
+            "config": {"workload": "synthetic %d-triangle cell on %d-node substrate (BASELINE configs[3]); CPU arm runs a bounded sample"
+                                   % (a.cell_tris, a.subs_side ** 2), "variant": a.variant, "dt": a.dt},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+    import torch
+    import torch.distributed as dist
+    import wholecellfe_b200 as W
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the UL step has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+
+    xc, tc, xs, ts = workload_meshes(a.cell_tris, a.subs_side)
+    nn_c, ne_c, nn_s, ne_s = len(xc), len(tc), len(xs), len(ts)
+    sim = W.ULSim(a.variant, device=local, stream=stream.cuda_stream)
+    sim.upload_mesh(W.CELL, xc, tc); sim.upload_mesh(W.SUBS, xs, ts)
+    sim.set_rng(1, 1 + rank)                     # counter-based Philox, one stream per replica
+    t = 0.0
+    launches0 = sim.kernel_launches()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t = sim.step_n(a.warmup, a.dt, t)
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    l0 = sim.kernel_launches()
+    e0.record(stream)
+    t = sim.step_n(a.steps, a.dt, t)
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = sim.kernel_launches() - l0
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = (ne_c + ne_s) * a.steps * world / (ms_max * 1e-3)
+
+    # per-kernel durations (CUDA events on the launching stream), separate pass so the events do not perturb `value`
+    sim.set_profile(True)
+    t = sim.step_n(max(3, min(a.steps, 10)), a.dt, t)
+    kms, kcnt = sim.kernel_ms()
+    sim.set_profile(False)
+    names = ["k_predict_cell", "k_bond", "k_cell_node", "k_boundary_finish", "k_subs_node"]
+    per_kernel = {n: (kms[i] / kcnt[i] if kcnt[i] else 0.0) for i, n in enumerate(names)}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+    dom = "k_subs_node"
+    dom_bytes = 216 * nn_s + 12 * ne_s
+    dom_ms = per_kernel[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    step_bytes = algorithmic_bytes(nn_c, ne_c, nn_s, ne_s)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+                "per_kernel_ms": per_kernel, "share_of_step": dom_ms / max(sum(per_kernel.values()), 1e-30),
+                "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_max / a.steps * 1e-3) / 1e9,
+                               "frac": step_bytes / (ms_max / a.steps * 1e-3) / 1e9 / peak}}
+    # ncu dram__bytes of the same kernel, if a capture has been summarised under profiles/
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = tr.get(dom)
+    except Exception:
+        pass
+
+    # end to end: the adapter-mode call sequence with host round trips every step (pinned buffers)
+    e2e_steps = max(2, min(a.steps, 5))
+    barrier()
+    w0 = time.perf_counter()
+    t, h2d, d2h = sim.step_n_roundtrip(e2e_steps, a.dt, t)
+    torch.cuda.synchronize()
+    w1 = time.perf_counter()
+    te = torch.tensor([w1 - w0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": (ne_c + ne_s) * e2e_steps * world / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": e2e_steps, "what": "wcfe_step_n_roundtrip: predict -> D2H predicted positions (cell+substrate) -> H2D accepted positions -> update -> D2H diagnostics, every step"}
+    x = sim.get(W.CELL, "x")
+    if not np.isfinite(x).all():
+        raise SystemExit("bench.py: non-finite positions after the run")
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        div = a.cpu_sample_div
+        cxc, ctc, cxs, cts = workload_meshes(max(600, a.cell_tris // div), max(24, int(a.subs_side / math.sqrt(div))))
+        v = time_oracle_port(a.variant, cxc, ctc, cxs, cts, a.dt, 2)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "2 steps of a 1/%d-size copy of the workload (%d-triangle cell on %d-node substrate), oracle C restatement with grid point location, 1 thread"
+                         % (div, len(ctc), len(cxs))}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "synthetic %d-triangle cell (%d nodes) on %d-node substrate (%d triangles), BASELINE configs[3]; one independent replica per GPU"
+                                       % (ne_c, nn_c, nn_s, ne_s), "variant": a.variant, "dt": a.dt, "rng": "philox", "parallelism": "ensemble x%d (no comms)" % world,
+                           "l2": "state %.2f GB >> 126 MB L2, no flush" % (step_bytes / 2 / 1e9)},
+                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

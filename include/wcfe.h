@@ -106,7 +106,13 @@ int wcfe_download_state(wcfe_ctx *c, int surface, int field, double *host);
 int wcfe_mesh_sizes(wcfe_ctx *c, int surface, int *nn, int *ne);
 
 int wcfe_set_rng(wcfe_ctx *c, int mode, unsigned int seed);
-int wcfe_set_debug(wcfe_ctx *c, int on);   /* also record WCFE_D_LOC_BOND (extra point location per step) */
+/* resume a glibc replay mid-run (checkpoint/restart): discard n_draws values (one per boundary vertex per step) */
+int wcfe_rng_skip(wcfe_ctx *c, long long n_draws);
+int wcfe_set_debug(wcfe_ctx *c, int on);   /* also record WCFE_D_LOC_BOND (extra point location per step) and force fields */
+/* per-kernel CUDA-event timing of wcfe_step_n (events on the launching stream); ids: 0 k_predict_cell 1 k_bond
+ * 2 k_cell_node 3 k_boundary_finish 4 k_subs_node.  ms8 = accumulated ms, count8 = launches timed. */
+int wcfe_set_profile(wcfe_ctx *c, int on);
+int wcfe_get_kernel_ms(wcfe_ctx *c, double *ms8, long long *count8);
 
 /* ---- the reference's call sequence, one entry point per call site of advance_sim() --------------- */
 

@@ -17,3 +17,18 @@ int hm_point_in_triangle(const double *n1, const double *n2, const double *n3, c
 }
 unsigned int hm_philox(unsigned int seed, unsigned int step, unsigned int ord) { return philox_u32(seed, step, ord); }
 }
+extern "C" {
+static Consts mk(int law, double kf, double kb, const double *px, const double *py, const double *kk) {
+    Consts c; memset(&c, 0, sizeof c);
+    c.law = law; c.kint_force = kf; c.kint_bond = kb; c.k_on = 1; c.ka = 0.004; c.kb = 10; c.Fa = 15; c.Fb = 15;
+    for (int i = 0; i < 6; i++) { c.md_px[i] = px[i]; c.md_py[i] = py[i]; c.md_k[i] = kk[i]; }
+    return c;
+}
+void hm_integrin_force(int law, double kf, const double *px, const double *py, const double *kk, const double *u, double *f) {
+    Consts c = mk(law, kf, kf, px, py, kk); integrin_force(c, u, f);
+}
+int hm_bond_update(int law, double kf, double kb, const double *px, const double *py, const double *kk, double dt,
+                   const double *cell_u, const double *subs_u, double *fa, double *cC) {
+    Consts c = mk(law, kf, kb, px, py, kk); return bond_update(c, dt, cell_u, subs_u, fa, *cC);
+}
+}

@@ -101,6 +101,11 @@ struct wcfe_ctx {
     int rng_mode = WCFE_RNG_GLIBC_REPLAY; unsigned int seed = 1; HostRng rng;
     unsigned int step = 0;
     int debug = 0;
+    int profile = 0;                      // per-kernel CUDA-event timing (bench roofline leg)
+    std::vector<cudaEvent_t> pev;         // event pool, pairs
+    std::vector<int> pev_kernel;          // kernel id of each pair in flight
+    double kms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long kcnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long launches = 0;
     double last_ms = 0, t_last = 0;
     bool have_predict[2] = {false, false};
@@ -301,6 +306,29 @@ int check_device_errors(wcfe_ctx *c) {
     return WCFE_OK;
 }
 
+// per-kernel timing: an event pair around a launch, harvested after the stream has drained
+struct ProfScope {
+    wcfe_ctx *c; int idx = -1;
+    ProfScope(wcfe_ctx *c_, int kernel_id) : c(c_) {
+        if (!c->profile) return;
+        idx = (int)c->pev_kernel.size();
+        if (c->pev.size() < (size_t)2 * (idx + 1)) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); c->pev.push_back(a); c->pev.push_back(b); }
+        c->pev_kernel.push_back(kernel_id);
+        cudaEventRecord(c->pev[2 * idx], c->stream);
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(c->pev[2 * idx + 1], c->stream); }
+};
+void harvest_profile(wcfe_ctx *c) {
+    if (!c->profile) return;
+    cudaStreamSynchronize(c->stream);
+    for (size_t q = 0; q < c->pev_kernel.size(); q++) {
+        float ms = 0; cudaEventElapsedTime(&ms, c->pev[2 * q], c->pev[2 * q + 1]);
+        c->kms[c->pev_kernel[q]] += ms; c->kcnt[c->pev_kernel[q]]++;
+    }
+    c->pev_kernel.clear();
+}
+enum { K_PREDICT = 0, K_BOND = 1, K_CELL = 2, K_FINISH = 3, K_SUBS = 4 };
+
 // ---- one UL update on the device: k_bond, k_cell_node, k_boundary_finish, k_subs_node ---------------------------
 int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const unsigned int *tape_dev) {
     Surface &cs = c->s[WCFE_CELL], &ss = c->s[WCFE_SUBS];
@@ -309,18 +337,22 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     c->epoch++;
     BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch};
     const int gc = (cs.nn + kBlock - 1) / kBlock, gs = (ss.nn + kBlock - 1) / kBlock;
-    k_bond<<<gc, kBlock, 0, c->stream>>>(cv, sv, c->grid, bk, c->k, dt_real, c->ibox[0], c->ibox[1], c->ibox[2], c->ibox[3], c->d_flags.p, c->d_loc_bond.p, c->d_loc_cnt.p, c->d_loc_first.p, c->debug, c->d_err.p);
+    { ProfScope ps(c, K_BOND);
+    k_bond<<<gc, kBlock, 0, c->stream>>>(cv, sv, c->grid, bk, c->k, dt_real, c->ibox[0], c->ibox[1], c->ibox[2], c->ibox[3], c->d_flags.p, c->d_loc_bond.p, c->d_loc_cnt.p, c->d_loc_first.p, c->debug, c->d_err.p); }
     // Pr < APrate*dt*exp(-APrate*dt) (UL:1531): the threshold is evaluated on the host with the host libm, as the reference does
     const double thr = c->prm.ap_rate * dt_real * std::exp(-c->prm.ap_rate * dt_real);
     BoundaryView bv = bview(cs);
+    { ProfScope ps(c, K_CELL);
     if (c->debug)
         k_cell_node<true><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, dview(cs));
     else
-        k_cell_node<false><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, DebugView{});
+        k_cell_node<false><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, DebugView{}); }
+    { ProfScope ps(c, K_FINISH);
     if (c->debug) k_boundary_finish<true><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, gc, c->d_partials.p, dt, dt_real, c->d_diag.p, dview(cs));
-    else k_boundary_finish<false><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, gc, c->d_partials.p, dt, dt_real, c->d_diag.p, DebugView{});
+    else k_boundary_finish<false><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, gc, c->d_partials.p, dt, dt_real, c->d_diag.p, DebugView{}); }
+    { ProfScope ps(c, K_SUBS);
     if (c->debug) k_subs_node<true><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
-    else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+    else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}); }
     c->launches += 4;
     cs.ea_cur ^= 1; ss.ea_cur ^= 1;
     c->step++;
@@ -418,6 +450,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     c->d_partials.release(); c->d_diag.release(); c->d_tape.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -590,6 +623,25 @@ int wcfe_set_rng(wcfe_ctx *c, int mode, unsigned int seed) {
     return WCFE_OK;
 }
 
+int wcfe_rng_skip(wcfe_ctx *c, long long n_draws) {
+    if (!c || n_draws < 0) return WCFE_ERR_ARG;
+    for (long long q = 0; q < n_draws; q++) c->rng.next();
+    return WCFE_OK;
+}
+
+int wcfe_set_profile(wcfe_ctx *c, int on) {
+    if (!c) return WCFE_ERR_ARG;
+    c->profile = on ? 1 : 0;
+    if (on) { for (int q = 0; q < 8; q++) { c->kms[q] = 0; c->kcnt[q] = 0; } c->pev_kernel.clear(); }
+    return WCFE_OK;
+}
+
+int wcfe_get_kernel_ms(wcfe_ctx *c, double *ms8, long long *count8) {
+    if (!c || !ms8 || !count8) return WCFE_ERR_ARG;
+    for (int q = 0; q < 8; q++) { ms8[q] = c->kms[q]; count8[q] = c->kcnt[q]; }
+    return WCFE_OK;
+}
+
 int wcfe_set_debug(wcfe_ctx *c, int on) {
     if (!c) return WCFE_ERR_ARG;
     c->debug = on ? 1 : 0;
@@ -652,7 +704,8 @@ int wcfe_step_n(wcfe_ctx *c, int n, double dt, double *t_io) {
     double t = *t_io;
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int q = 0; q < n; q++) {
-        k_predict_cell<<<(cs.nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt);
+        { ProfScope ps(c, K_PREDICT);
+        k_predict_cell<<<(cs.nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt); }
         c->launches++;
         const unsigned int *tape = c->d_tape.p ? c->d_tape.p + (size_t)q * cs.nb : nullptr;
         if ((rc = launch_update(c, dt, dt, t, tape))) return rc;
@@ -660,6 +713,7 @@ int wcfe_step_n(wcfe_ctx *c, int n, double dt, double *t_io) {
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaEventSynchronize(c->ev1));
+    harvest_profile(c);
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
     *t_io = t; c->t_last = t;
     return check_device_errors(c);

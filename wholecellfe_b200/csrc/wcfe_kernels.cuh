@@ -64,11 +64,13 @@ __global__ void __launch_bounds__(kBlock) k_predict_cell(int nn, int np, double 
     if (i >= nn) return;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
+        // uncontracted (two roundings per multiply-add) so that x_new, and with it cell_u = x - X in updateFA, is
+        // bit-identical to the x86 reference given the same V, A
         const double xo = x[c * np + i];
-        double vh = V[c * np + i] + (dt / 2.0) * A[c * np + i];
+        double vh = WCFE_ADD(V[c * np + i], WCFE_MUL(dt / 2.0, A[c * np + i]));
         if (c == 2) vh = 0.0;
         X[c * np + i] = xo;
-        x[c * np + i] = xo + dt * vh;
+        x[c * np + i] = WCFE_ADD(xo, WCFE_MUL(dt, vh));
     }
 }
 

@@ -89,6 +89,18 @@ class ULSim:
     def srand(self, seed):
         self.set_rng(B.RNG_GLIBC_REPLAY, seed)
 
+    def rng_skip(self, n_draws):
+        self._ck(self.L.wcfe_rng_skip(self.h, int(n_draws)))
+
+    def set_profile(self, on):
+        self._ck(self.L.wcfe_set_profile(self.h, 1 if on else 0))
+
+    def kernel_ms(self):
+        ms = np.zeros(8)
+        cnt = (C.c_longlong * 8)()
+        self._ck(self.L.wcfe_get_kernel_ms(self.h, _d(ms), cnt))
+        return ms, np.array(list(cnt))
+
     def set_debug(self, on):
         self._ck(self.L.wcfe_set_debug(self.h, 1 if on else 0))
 
