@@ -112,6 +112,11 @@ int wcfe_set_debug(wcfe_ctx *c, int on);   /* also record WCFE_D_LOC_BOND (extra
 /* per-kernel CUDA-event timing of wcfe_step_n (events on the launching stream); ids: 0 k_predict_cell 1 k_bond
  * 2 k_cell_node 3 k_boundary_finish 4 k_subs_node.  ms8 = accumulated ms, count8 = launches timed. */
 int wcfe_set_profile(wcfe_ctx *c, int on);
+/* test hook: run the general 3-D (node-centric) kernels even when the state is planar */
+int wcfe_set_force_general(wcfe_ctx *c, int on);
+/* out8: planar fast path active (0/1), patch-local elements / elements for cell and substrate (recompute overhead),
+ * max halo nodes and max elements per patch for cell and substrate, triangle-bucket capacity */
+int wcfe_get_path_info(wcfe_ctx *c, double *out8);
 int wcfe_get_kernel_ms(wcfe_ctx *c, double *ms8, long long *count8);
 
 /* ---- the reference's call sequence, one entry point per call site of advance_sim() --------------- */

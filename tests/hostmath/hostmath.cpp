@@ -32,3 +32,10 @@ int hm_bond_update(int law, double kf, double kb, const double *px, const double
     Consts c = mk(law, kf, kb, px, py, kk); return bond_update(c, dt, cell_u, subs_u, fa, *cC);
 }
 }
+extern "C" void hm_elem_eval_planar(const double *X6, const double *x6, const double *e3, double mu, double tk, double thick,
+                                    double *r1, double *r2, double *eas, double *A0, double *acur) {
+    double X[3][2], x[3][2];
+    memcpy(X, X6, sizeof X); memcpy(x, x6, sizeof x);
+    ElemOut2 o; elem_eval_planar(X, x, e3, mu, tk, thick, o);
+    memcpy(r1, o.r1, 16); memcpy(r2, o.r2, 16); memcpy(eas, o.eas, 24); *A0 = o.A0; *acur = o.a_cur;
+}

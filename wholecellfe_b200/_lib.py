@@ -19,7 +19,7 @@ RNG_GLIBC_REPLAY, RNG_PHILOX = 0, 1
 # every symbol include/wcfe.h declares
 SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_params", "wcfe_set_stream", "wcfe_last_error",
            "wcfe_upload_mesh", "wcfe_upload_state", "wcfe_download_state", "wcfe_mesh_sizes", "wcfe_set_rng", "wcfe_set_debug",
-           "wcfe_rng_skip", "wcfe_set_profile", "wcfe_get_kernel_ms",
+           "wcfe_rng_skip", "wcfe_set_profile", "wcfe_get_kernel_ms", "wcfe_set_force_general", "wcfe_get_path_info",
            "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_step_n", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
            "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_sync"]
 
@@ -65,6 +65,8 @@ def load():
     L.wcfe_set_debug.argtypes = [vp, C.c_int]
     L.wcfe_rng_skip.argtypes = [vp, C.c_longlong]
     L.wcfe_set_profile.argtypes = [vp, C.c_int]
+    L.wcfe_set_force_general.argtypes = [vp, C.c_int]
+    L.wcfe_get_path_info.argtypes = [vp, _dp]
     L.wcfe_get_kernel_ms.argtypes = [vp, _dp, C.POINTER(C.c_longlong)]
     L.wcfe_predict.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp]
     L.wcfe_commit.argtypes = [vp, C.c_int, _dp]

@@ -7,6 +7,7 @@
 // but lays it out as SoA FP64 on the device and never runs the physics on the CPU.
 #include "../../include/wcfe.h"
 #include "wcfe_kernels.cuh"
+#include "wcfe_patch.cuh"
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -71,6 +72,12 @@ struct Surface {
     // debug capture
     DevBuf<double> g_res, g_ffa, g_fap, g_fbend, g_farea, g_mm, g_rea;
     double max_edge = 0, max_tri_area = 0, area = 0;
+    // planar fast path: patch tables (wcfe_patch.cuh)
+    bool planar = false;                  // z == 0 everywhere, no out-of-plane state
+    int npatch = 0, max_halo = 0, max_elem = 0;
+    double halo_elem_ratio = 0;           // patch-local elements / elements: the recompute overhead
+    DevBuf<int> p_elem_ptr, p_elem_gid, p_halo_ptr, p_halo_ids;
+    DevBuf<unsigned short> p_elem_lv, p_ring16, p_cand_l;
 };
 
 }   // namespace
@@ -101,6 +108,7 @@ struct wcfe_ctx {
     int rng_mode = WCFE_RNG_GLIBC_REPLAY; unsigned int seed = 1; HostRng rng;
     unsigned int step = 0;
     int debug = 0;
+    int force_general = 0;                // test hook: run the general 3-D kernels even on planar states
     int profile = 0;                      // per-kernel CUDA-event timing (bench roofline leg)
     std::vector<cudaEvent_t> pev;         // event pool, pairs
     std::vector<int> pev_kernel;          // kernel id of each pair in flight
@@ -224,7 +232,11 @@ int alloc_debug(wcfe_ctx *c, int surface) {
     if (!s.nn || s.g_res.p) return WCFE_OK;
     const size_t np = s.np;
     CK(s.g_res.alloc(3 * np)); CK(s.g_ffa.alloc(3 * np)); CK(s.g_mm.alloc(np)); CK(s.g_rea.alloc(6 * np));
-    if (surface == WCFE_CELL) { CK(s.g_fap.alloc(3 * np)); CK(s.g_fbend.alloc(3 * np)); CK(s.g_farea.alloc(3 * np)); }
+    CK(cudaMemset(s.g_res.p, 0, 24 * np)); CK(cudaMemset(s.g_ffa.p, 0, 24 * np)); CK(cudaMemset(s.g_mm.p, 0, 8 * np)); CK(cudaMemset(s.g_rea.p, 0, 48 * np));
+    if (surface == WCFE_CELL) {
+        CK(s.g_fap.alloc(3 * np)); CK(s.g_fbend.alloc(3 * np)); CK(s.g_farea.alloc(3 * np));
+        CK(cudaMemset(s.g_fap.p, 0, 24 * np)); CK(cudaMemset(s.g_fbend.p, 0, 24 * np)); CK(cudaMemset(s.g_farea.p, 0, 24 * np));
+    }
     return WCFE_OK;
 }
 
@@ -281,6 +293,73 @@ int build_grid(wcfe_ctx *c, const double *xyz) {
     g.ptr = c->g_ptr.p; g.items = c->g_items.p;
     return WCFE_OK;
 }
+
+// patch tables for the planar fused kernels: kPatch consecutive nodes per patch, every incident element listed once per patch
+int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
+    Surface &s = c->s[surface];
+    const int P = kPatch;
+    s.npatch = (s.nn + P - 1) / P;
+    std::vector<int> elem_ptr(1, 0), elem_gid, halo_ptr(1, 0), halo_ids;
+    std::vector<unsigned short> elem_lv, ring16(s.ring.size(), 0), cand_l(cand.size(), 0);
+    std::vector<int> el, hl;
+    s.max_halo = 0; s.max_elem = 0;
+    size_t cand_pos = 0;
+    for (int p = 0; p < s.npatch; p++) {
+        const int n0 = p * P, n1 = std::min(s.nn, n0 + P);
+        el.clear(); hl.clear();
+        for (int r = s.ring_ptr[n0]; r < s.ring_ptr[n1]; r++) el.push_back(s.ring[r] >> 2);
+        std::sort(el.begin(), el.end()); el.erase(std::unique(el.begin(), el.end()), el.end());
+        for (int e : el) for (int j = 0; j < 3; j++) { const int v = s.tri[3 * (size_t)e + j]; if (v < n0 || v >= n1) hl.push_back(v); }
+        std::sort(hl.begin(), hl.end()); hl.erase(std::unique(hl.begin(), hl.end()), hl.end());
+        if ((int)el.size() > 16383 || P + (int)hl.size() > 65535) return fail(c, WCFE_ERR_CAPACITY, "patch tables: a vertex of extreme valence overflows the 16-bit local ids");
+        auto local = [&](int v) -> unsigned short {
+            if (v >= n0 && v < n1) return (unsigned short)(v - n0);
+            return (unsigned short)(P + (std::lower_bound(hl.begin(), hl.end(), v) - hl.begin()));
+        };
+        for (int e : el) { elem_gid.push_back(e); for (int j = 0; j < 3; j++) elem_lv.push_back(local(s.tri[3 * (size_t)e + j])); }
+        for (int r = s.ring_ptr[n0]; r < s.ring_ptr[n1]; r++) {
+            const int e = s.ring[r] >> 2, slot = s.ring[r] & 3;
+            ring16[r] = (unsigned short)(((std::lower_bound(el.begin(), el.end(), e) - el.begin()) << 2) | slot);
+        }
+        if (surface == WCFE_CELL) {        // boundary candidates of the owned boundary vertices, in table order
+            for (int v = n0; v < n1; v++) {
+                if (!s.is_bnd[v]) continue;
+                // the candidate table was built in ascending vertex order: consume this vertex's pairs
+                int npairs = 0;
+                for (int r = s.ring_ptr[v]; r < s.ring_ptr[v + 1]; r++) {
+                    const int *t = &s.tri[3 * (size_t)(s.ring[r] >> 2)];
+                    for (int j = 0; j < 3; j++) if (s.is_bnd[t[j]] && t[j] != v) npairs++;
+                }
+                for (int q = 0; q < 2 * npairs; q++, cand_pos++) cand_l[cand_pos] = local(cand[cand_pos]);
+            }
+        }
+        elem_ptr.push_back((int)elem_gid.size()); halo_ptr.push_back((int)halo_ids.size() + (int)hl.size());
+        halo_ids.insert(halo_ids.end(), hl.begin(), hl.end());
+        s.max_halo = std::max(s.max_halo, (int)hl.size()); s.max_elem = std::max(s.max_elem, (int)el.size());
+    }
+    s.halo_elem_ratio = (double)elem_gid.size() / std::max(1, s.ne);
+    if (halo_ids.empty()) halo_ids.push_back(0);
+    if (cand_l.empty()) cand_l.push_back(0);
+    CK(s.p_elem_ptr.alloc(elem_ptr.size())); CK(s.p_elem_gid.alloc(elem_gid.size())); CK(s.p_elem_lv.alloc(elem_lv.size()));
+    CK(s.p_halo_ptr.alloc(halo_ptr.size())); CK(s.p_halo_ids.alloc(halo_ids.size())); CK(s.p_ring16.alloc(ring16.size())); CK(s.p_cand_l.alloc(cand_l.size()));
+    CK(cudaMemcpy(s.p_elem_ptr.p, elem_ptr.data(), sizeof(int) * elem_ptr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.p_elem_gid.p, elem_gid.data(), sizeof(int) * elem_gid.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.p_elem_lv.p, elem_lv.data(), sizeof(unsigned short) * elem_lv.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.p_halo_ptr.p, halo_ptr.data(), sizeof(int) * halo_ptr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.p_halo_ids.p, halo_ids.data(), sizeof(int) * halo_ids.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.p_ring16.p, ring16.data(), sizeof(unsigned short) * ring16.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.p_cand_l.p, cand_l.data(), sizeof(unsigned short) * cand_l.size(), cudaMemcpyHostToDevice));
+    return WCFE_OK;
+}
+PatchView pview(Surface &s) {
+    PatchView v{};
+    v.npatch = s.npatch; v.max_halo = s.max_halo; v.max_elem = s.max_elem;
+    v.elem_ptr = s.p_elem_ptr.p; v.elem_gid = s.p_elem_gid.p; v.elem_lv = s.p_elem_lv.p; v.halo_ptr = s.p_halo_ptr.p; v.halo_ids = s.p_halo_ids.p;
+    v.ring16 = s.p_ring16.p; v.cand_l = s.p_cand_l.p;
+    return v;
+}
+bool planar_positions(const double *xyz, int nn) { for (int i = 0; i < nn; i++) if (xyz[3 * i + 2] != 0.0) return false; return true; }
+bool use_planar(wcfe_ctx *c) { return c->s[0].planar && c->s[1].planar && c->prm.thetag_dot == 0.0 && !c->force_general; }
 
 // (re)size the per-triangle buckets once both meshes are known
 int build_buckets(wcfe_ctx *c) {
@@ -350,6 +429,13 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     { ProfScope ps(c, K_FINISH);
     if (c->debug) k_boundary_finish<true><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, gc, c->d_partials.p, dt, dt_real, c->d_diag.p, dview(cs));
     else k_boundary_finish<false><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, gc, c->d_partials.p, dt, dt_real, c->d_diag.p, DebugView{}); }
+    if (use_planar(c)) {
+        ProfScope ps(c, K_SUBS);
+        const size_t smem = patch_smem_bytes(5, 8, ss.max_halo, ss.max_elem);
+        PatchView pvs = pview(ss);
+        if (c->debug) k_subs_patch<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
+        else k_subs_patch<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+    } else
     { ProfScope ps(c, K_SUBS);
     if (c->debug) k_subs_node<true><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
     else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}); }
@@ -427,6 +513,8 @@ int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p) {
     c->stream = c->own_stream;
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     c->rng.seed(1);
+    cudaFuncSetAttribute(k_subs_patch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_subs_patch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (c->d_err.alloc(1) != cudaSuccess || c->d_diag.alloc(8) != cudaSuccess) { delete c; return WCFE_ERR_CUDA; }
     cudaMemset(c->d_err.p, 0, sizeof(int)); cudaMemset(c->d_diag.p, 0, 8 * sizeof(double));
     *out = c;
@@ -444,6 +532,7 @@ int wcfe_destroy(wcfe_ctx *c) {
         s.cA.release(); s.cB.release(); s.cC.release(); s.fa.release(); s.asum.release();
         s.d_bnd_node.release(); s.d_bnd_index.release(); s.d_cand_ptr.release(); s.d_cand.release(); s.d_bnd_buf.release();
         s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
+        s.p_elem_ptr.release(); s.p_elem_gid.release(); s.p_halo_ptr.release(); s.p_halo_ids.release(); s.p_elem_lv.release(); s.p_ring16.release(); s.p_cand_l.release();
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();
@@ -531,6 +620,8 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
     CK(s.x.alloc(3 * np)); CK(s.V.alloc(3 * np)); CK(s.A.alloc(3 * np)); CK(s.ea[0].alloc(6 * np)); CK(s.ea[1].alloc(6 * np));
     s.ea_cur = 0;
     int rc;
+    std::vector<int> cand;
+    s.planar = planar_positions(xyz, nn);
     if ((rc = put_field(c, s.x.p, xyz, nn, s.np, 3))) return rc;
     CK(cudaMemset(s.V.p, 0, sizeof(double) * 3 * np)); CK(cudaMemset(s.A.p, 0, sizeof(double) * 3 * np));
     CK(cudaMemset(s.ea[0].p, 0, sizeof(double) * 6 * np)); CK(cudaMemset(s.ea[1].p, 0, sizeof(double) * 6 * np));
@@ -543,7 +634,7 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
         CK(cudaMemset(s.fa.p, 0, sizeof(double) * 3 * np)); CK(cudaMemset(s.asum.p, 0, sizeof(double) * np));
         // boundary tables: candidates (nj, nint) in the reference's scan order (UL:1479-1495)
         s.bnd_node.clear();
-        std::vector<int> index((size_t)nn, -1), cand_ptr(1, 0), cand;
+        std::vector<int> index((size_t)nn, -1), cand_ptr(1, 0);
         for (int v = 0; v < nn; v++) {
             if (!s.is_bnd[v]) continue;
             index[v] = (int)s.bnd_node.size(); s.bnd_node.push_back(v);
@@ -561,6 +652,7 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
             cand_ptr.push_back((int)cand.size() / 2);
         }
         s.nb = (int)s.bnd_node.size();
+        if ((rc = build_patches(c, surface, cand))) return rc;
         if (cand.empty()) cand.push_back(0);
         CK(s.d_bnd_node.alloc(std::max(1, s.nb))); CK(s.d_bnd_index.alloc(nn)); CK(s.d_cand_ptr.alloc(cand_ptr.size())); CK(s.d_cand.alloc(cand.size()));
         if (s.nb) CK(cudaMemcpy(s.d_bnd_node.p, s.bnd_node.data(), sizeof(int) * s.nb, cudaMemcpyHostToDevice));
@@ -576,6 +668,7 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
     } else {
         s.X.release();
         if ((rc = build_grid(c, xyz))) return rc;
+        if ((rc = build_patches(c, surface, cand))) return rc;
     }
     if ((rc = build_buckets(c))) return rc;
     if (c->debug) { if ((rc = alloc_debug(c, surface))) return rc; }
@@ -600,6 +693,10 @@ int wcfe_upload_state(wcfe_ctx *c, int surface, int field, const double *host) {
     CK(cudaSetDevice(c->device));
     int rc = put_field(c, dev, host, s.nn, s.np, w);
     if (rc) return rc;
+    // the planar fast path needs every out-of-plane word to be exactly zero; once that is violated it stays off
+    if (field == WCFE_F_X || field == WCFE_F_V || field == WCFE_F_A || field == WCFE_F_FAU) { for (int i = 0; i < s.nn && s.planar; i++) if (host[3 * (size_t)i + 2] != 0.0) s.planar = false; }
+    if (field == WCFE_F_EA) { for (int i = 0; i < s.nn && s.planar; i++) if (host[6 * (size_t)i + 2] != 0.0 || host[6 * (size_t)i + 4] != 0.0 || host[6 * (size_t)i + 5] != 0.0) s.planar = false; }
+    if (field == WCFE_F_EA && s.planar) CK(cudaMemsetAsync(s.ea[s.ea_cur ^ 1].p, 0, sizeof(double) * 6 * s.np, c->stream));
     if (field == WCFE_F_X) {
         if (surface == WCFE_CELL) { CK(cudaMemcpyAsync(s.X.p, s.x.p, sizeof(double) * 3 * s.np, cudaMemcpyDeviceToDevice, c->stream)); update_box(c, host, s.nn); }
         else { rc = build_grid(c, host); if (rc) return rc; }
@@ -642,6 +739,20 @@ int wcfe_get_kernel_ms(wcfe_ctx *c, double *ms8, long long *count8) {
     return WCFE_OK;
 }
 
+int wcfe_set_force_general(wcfe_ctx *c, int on) {
+    if (!c) return WCFE_ERR_ARG;
+    c->force_general = on ? 1 : 0;
+    return WCFE_OK;
+}
+
+int wcfe_get_path_info(wcfe_ctx *c, double *out8) {
+    if (!c || !out8) return WCFE_ERR_ARG;
+    out8[0] = use_planar(c) ? 1.0 : 0.0;
+    out8[1] = c->s[0].halo_elem_ratio; out8[2] = c->s[1].halo_elem_ratio;
+    out8[3] = c->s[0].max_halo; out8[4] = c->s[0].max_elem; out8[5] = c->s[1].max_halo; out8[6] = c->s[1].max_elem; out8[7] = c->b_cap;
+    return WCFE_OK;
+}
+
 int wcfe_set_debug(wcfe_ctx *c, int on) {
     if (!c) return WCFE_ERR_ARG;
     c->debug = on ? 1 : 0;
@@ -678,6 +789,7 @@ int wcfe_commit(wcfe_ctx *c, int surface, const double *xyz_final) {
     if (surface == WCFE_SUBS) return WCFE_OK;   // frozen substrate: positions are what they were
     rc = put_field(c, s.x.p, xyz_final, s.nn, s.np, 3);
     if (rc) return rc;
+    if (s.planar && !planar_positions(xyz_final, s.nn)) s.planar = false;
     update_box(c, xyz_final, s.nn);
     return WCFE_OK;
 }
