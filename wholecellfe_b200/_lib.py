@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwcfe.so")
+LIB_PATH = os.environ.get("WCFE_LIB") or os.path.join(HERE, "libwcfe.so")   # WCFE_LIB: a tuning variant built by build.py
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 

@@ -20,13 +20,15 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: tuning variants (e.g. defines=("WCFE_PATCH=128",), out="libwcfe_p128.so"), loaded via env WCFE_LIB."""
+    target = os.path.join(HERE, out) if out else LIB
+    if not force and not out and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + sources()
     subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -76,8 +76,10 @@ struct Surface {
     bool planar = false;                  // z == 0 everywhere, no out-of-plane state
     int npatch = 0, max_halo = 0, max_elem = 0;
     double halo_elem_ratio = 0;           // patch-local elements / elements: the recompute overhead
-    DevBuf<int> p_elem_ptr, p_elem_gid, p_halo_ptr, p_halo_ids;
-    DevBuf<unsigned short> p_elem_lv, p_ring16, p_cand_l;
+    int stride = 0, off_halo = 0, off_lv = 0, off_rptr = 0, off_ring = 0;   // blob layout (wcfe_patch.cuh)
+    DevBuf<unsigned char> p_blob;
+    DevBuf<int> p_elem_ptr, p_elem_gid;
+    DevBuf<unsigned short> p_cand_l;
 };
 
 }   // namespace
@@ -122,7 +124,8 @@ struct wcfe_ctx {
 
 namespace {
 
-int fail(wcfe_ctx *c, int code, const std::string &msg) { if (c) c->err = msg; return code; }
+std::string g_create_err = "null context";   // wcfe_last_error(NULL): why the last wcfe_create failed
+int fail(wcfe_ctx *c, int code, const std::string &msg) { if (c) c->err = msg; else g_create_err = msg; return code; }
 #define CK(call)                                                                                     \
     do {                                                                                             \
         cudaError_t e_ = (call);                                                                     \
@@ -294,72 +297,101 @@ int build_grid(wcfe_ctx *c, const double *xyz) {
     return WCFE_OK;
 }
 
-// patch tables for the planar fused kernels: kPatch consecutive nodes per patch, every incident element listed once per patch
+// patch tables for the planar fused kernels: kPatch consecutive nodes per patch, every incident element listed once per
+// patch; each patch's tables are packed into one fixed-stride blob (layout: wcfe_patch.cuh) for a single TMA bulk copy
 int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
     Surface &s = c->s[surface];
     const int P = kPatch;
     s.npatch = (s.nn + P - 1) / P;
-    std::vector<int> elem_ptr(1, 0), elem_gid, halo_ptr(1, 0), halo_ids;
-    std::vector<unsigned short> elem_lv, ring16(s.ring.size(), 0), cand_l(cand.size(), 0);
-    std::vector<int> el, hl;
+    struct Tmp { std::vector<int> halo; std::vector<unsigned short> lv, rptr, ring; int nel; };
+    std::vector<Tmp> tmp((size_t)s.npatch);
+    std::vector<int> elem_ptr(1, 0), elem_gid;
+    std::vector<unsigned short> cand_l(cand.size(), 0);
+    std::vector<int> el;
     s.max_halo = 0; s.max_elem = 0;
+    int max_ring = 0;
     size_t cand_pos = 0;
     for (int p = 0; p < s.npatch; p++) {
         const int n0 = p * P, n1 = std::min(s.nn, n0 + P);
-        el.clear(); hl.clear();
+        Tmp &t = tmp[p];
+        el.clear();
         for (int r = s.ring_ptr[n0]; r < s.ring_ptr[n1]; r++) el.push_back(s.ring[r] >> 2);
         std::sort(el.begin(), el.end()); el.erase(std::unique(el.begin(), el.end()), el.end());
+        std::vector<int> &hl = t.halo;
         for (int e : el) for (int j = 0; j < 3; j++) { const int v = s.tri[3 * (size_t)e + j]; if (v < n0 || v >= n1) hl.push_back(v); }
         std::sort(hl.begin(), hl.end()); hl.erase(std::unique(hl.begin(), hl.end()), hl.end());
-        if ((int)el.size() > 16383 || P + (int)hl.size() > 65535) return fail(c, WCFE_ERR_CAPACITY, "patch tables: a vertex of extreme valence overflows the 16-bit local ids");
+        const int nring = s.ring_ptr[n1] - s.ring_ptr[n0];
+        if ((int)el.size() > 16383 || P + (int)hl.size() > 65535 || nring > 65535)
+            return fail(c, WCFE_ERR_CAPACITY, "patch tables: a vertex of extreme valence overflows the 16-bit local ids");
         auto local = [&](int v) -> unsigned short {
             if (v >= n0 && v < n1) return (unsigned short)(v - n0);
             return (unsigned short)(P + (std::lower_bound(hl.begin(), hl.end(), v) - hl.begin()));
         };
-        for (int e : el) { elem_gid.push_back(e); for (int j = 0; j < 3; j++) elem_lv.push_back(local(s.tri[3 * (size_t)e + j])); }
+        for (int e : el) { elem_gid.push_back(e); for (int j = 0; j < 3; j++) t.lv.push_back(local(s.tri[3 * (size_t)e + j])); }
+        t.nel = (int)el.size();
+        t.rptr.assign((size_t)P + 1, (unsigned short)nring);
+        for (int v = n0; v <= n1; v++) t.rptr[v - n0] = (unsigned short)(s.ring_ptr[v] - s.ring_ptr[n0]);
         for (int r = s.ring_ptr[n0]; r < s.ring_ptr[n1]; r++) {
             const int e = s.ring[r] >> 2, slot = s.ring[r] & 3;
-            ring16[r] = (unsigned short)(((std::lower_bound(el.begin(), el.end(), e) - el.begin()) << 2) | slot);
+            t.ring.push_back((unsigned short)(((std::lower_bound(el.begin(), el.end(), e) - el.begin()) << 2) | slot));
         }
         if (surface == WCFE_CELL) {        // boundary candidates of the owned boundary vertices, in table order
             for (int v = n0; v < n1; v++) {
                 if (!s.is_bnd[v]) continue;
-                // the candidate table was built in ascending vertex order: consume this vertex's pairs
                 int npairs = 0;
                 for (int r = s.ring_ptr[v]; r < s.ring_ptr[v + 1]; r++) {
-                    const int *t = &s.tri[3 * (size_t)(s.ring[r] >> 2)];
-                    for (int j = 0; j < 3; j++) if (s.is_bnd[t[j]] && t[j] != v) npairs++;
+                    const int *tr = &s.tri[3 * (size_t)(s.ring[r] >> 2)];
+                    for (int j = 0; j < 3; j++) if (s.is_bnd[tr[j]] && tr[j] != v) npairs++;
                 }
                 for (int q = 0; q < 2 * npairs; q++, cand_pos++) cand_l[cand_pos] = local(cand[cand_pos]);
             }
         }
-        elem_ptr.push_back((int)elem_gid.size()); halo_ptr.push_back((int)halo_ids.size() + (int)hl.size());
-        halo_ids.insert(halo_ids.end(), hl.begin(), hl.end());
+        elem_ptr.push_back((int)elem_gid.size());
         s.max_halo = std::max(s.max_halo, (int)hl.size()); s.max_elem = std::max(s.max_elem, (int)el.size());
+        max_ring = std::max(max_ring, nring);
     }
     s.halo_elem_ratio = (double)elem_gid.size() / std::max(1, s.ne);
-    if (halo_ids.empty()) halo_ids.push_back(0);
+    s.max_halo = (s.max_halo + 3) / 4 * 4;      // node arrays in shared memory are TMA destinations: keep their stride 16-B aligned
+    auto pad16 = [](size_t b) { return (b + 15) / 16 * 16; };
+    s.off_halo = 16;
+    s.off_lv = (int)(s.off_halo + pad16(4 * (size_t)s.max_halo));
+    s.off_rptr = (int)(s.off_lv + pad16(6 * (size_t)s.max_elem));
+    s.off_ring = (int)(s.off_rptr + pad16(2 * ((size_t)P + 8)));
+    s.stride = (int)(s.off_ring + pad16(2 * (size_t)max_ring));
+    std::vector<unsigned char> blob((size_t)s.npatch * s.stride, 0);
+    for (int p = 0; p < s.npatch; p++) {
+        unsigned char *b = blob.data() + (size_t)p * s.stride;
+        const Tmp &t = tmp[p];
+        int hdr[4] = {(int)t.halo.size(), t.nel, 0, 0};
+        memcpy(b, hdr, 16);
+        if (!t.halo.empty()) memcpy(b + s.off_halo, t.halo.data(), 4 * t.halo.size());
+        if (!t.lv.empty()) memcpy(b + s.off_lv, t.lv.data(), 2 * t.lv.size());
+        memcpy(b + s.off_rptr, t.rptr.data(), 2 * t.rptr.size());
+        if (!t.ring.empty()) memcpy(b + s.off_ring, t.ring.data(), 2 * t.ring.size());
+    }
     if (cand_l.empty()) cand_l.push_back(0);
-    CK(s.p_elem_ptr.alloc(elem_ptr.size())); CK(s.p_elem_gid.alloc(elem_gid.size())); CK(s.p_elem_lv.alloc(elem_lv.size()));
-    CK(s.p_halo_ptr.alloc(halo_ptr.size())); CK(s.p_halo_ids.alloc(halo_ids.size())); CK(s.p_ring16.alloc(ring16.size())); CK(s.p_cand_l.alloc(cand_l.size()));
+    CK(s.p_blob.alloc(blob.size())); CK(s.p_elem_ptr.alloc(elem_ptr.size())); CK(s.p_elem_gid.alloc(elem_gid.size())); CK(s.p_cand_l.alloc(cand_l.size()));
+    CK(cudaMemcpy(s.p_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.p_elem_ptr.p, elem_ptr.data(), sizeof(int) * elem_ptr.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.p_elem_gid.p, elem_gid.data(), sizeof(int) * elem_gid.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s.p_elem_lv.p, elem_lv.data(), sizeof(unsigned short) * elem_lv.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s.p_halo_ptr.p, halo_ptr.data(), sizeof(int) * halo_ptr.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s.p_halo_ids.p, halo_ids.data(), sizeof(int) * halo_ids.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s.p_ring16.p, ring16.data(), sizeof(unsigned short) * ring16.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.p_cand_l.p, cand_l.data(), sizeof(unsigned short) * cand_l.size(), cudaMemcpyHostToDevice));
     return WCFE_OK;
 }
 PatchView pview(Surface &s) {
     PatchView v{};
     v.npatch = s.npatch; v.max_halo = s.max_halo; v.max_elem = s.max_elem;
-    v.elem_ptr = s.p_elem_ptr.p; v.elem_gid = s.p_elem_gid.p; v.elem_lv = s.p_elem_lv.p; v.halo_ptr = s.p_halo_ptr.p; v.halo_ids = s.p_halo_ids.p;
-    v.ring16 = s.p_ring16.p; v.cand_l = s.p_cand_l.p;
+    v.stride = s.stride; v.off_halo = s.off_halo; v.off_lv = s.off_lv; v.off_rptr = s.off_rptr; v.off_ring = s.off_ring;
+    v.blob = s.p_blob.p; v.elem_ptr = s.p_elem_ptr.p; v.elem_gid = s.p_elem_gid.p; v.cand_l = s.p_cand_l.p;
     return v;
 }
 bool planar_positions(const double *xyz, int nn) { for (int i = 0; i < nn; i++) if (xyz[3 * i + 2] != 0.0) return false; return true; }
-bool use_planar(wcfe_ctx *c) { return c->s[0].planar && c->s[1].planar && c->prm.thetag_dot == 0.0 && !c->force_general; }
+constexpr int kPatchSmemMax = 224 * 1024;
+bool use_planar(wcfe_ctx *c) {
+    if (!(c->s[0].planar && c->s[1].planar && c->prm.thetag_dot == 0.0 && !c->force_general)) return false;
+    // a mesh numbered without locality can blow the per-patch tables past shared memory: use the general kernels then
+    return patch_smem_bytes(7, 9, c->s[0].max_halo, c->s[0].max_elem, c->s[0].stride) <= (size_t)kPatchSmemMax &&
+           patch_smem_bytes(5, 8, c->s[1].max_halo, c->s[1].max_elem, c->s[1].stride) <= (size_t)kPatchSmemMax;
+}
 
 // (re)size the per-triangle buckets once both meshes are known
 int build_buckets(wcfe_ctx *c) {
@@ -409,37 +441,70 @@ void harvest_profile(wcfe_ctx *c) {
 enum { K_PREDICT = 0, K_BOND = 1, K_CELL = 2, K_FINISH = 3, K_SUBS = 4 };
 
 // ---- one UL update on the device: k_bond, k_cell_node, k_boundary_finish, k_subs_node ---------------------------
-int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const unsigned int *tape_dev) {
+int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const unsigned int *tape_dev, bool fuse_predict) {
     Surface &cs = c->s[WCFE_CELL], &ss = c->s[WCFE_SUBS];
     SurfView cv = view(cs), sv = view(ss);
     sv.X = sv.x;
     c->epoch++;
     BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch};
     const int gc = (cs.nn + kBlock - 1) / kBlock, gs = (ss.nn + kBlock - 1) / kBlock;
-    { ProfScope ps(c, K_BOND);
-    k_bond<<<gc, kBlock, 0, c->stream>>>(cv, sv, c->grid, bk, c->k, dt_real, c->ibox[0], c->ibox[1], c->ibox[2], c->ibox[3], c->d_flags.p, c->d_loc_bond.p, c->d_loc_cnt.p, c->d_loc_first.p, c->debug, c->d_err.p); }
     // Pr < APrate*dt*exp(-APrate*dt) (UL:1531): the threshold is evaluated on the host with the host libm, as the reference does
     const double thr = c->prm.ap_rate * dt_real * std::exp(-c->prm.ap_rate * dt_real);
     BoundaryView bv = bview(cs);
-    { ProfScope ps(c, K_CELL);
-    if (c->debug)
-        k_cell_node<true><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, dview(cs));
-    else
-        k_cell_node<false><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, DebugView{}); }
+    const bool planar = use_planar(c);
+    int npart = gc;
+    if (planar) {
+        // fused cell kernel: (predict) + updateFA + anchor location + forces + update, one CTA per patch
+        ProfScope ps(c, K_CELL);
+        PatchView pvc = pview(cs);
+        CellStepArgs a{};
+        a.dt = dt; a.dt_real = dt_real; a.t_tot = t_tot; a.ap_threshold = thr;
+        a.ix0 = c->ibox[0]; a.ix1 = c->ibox[1]; a.iy0 = c->ibox[2]; a.iy1 = c->ibox[3];
+        a.rng_mode = c->rng_mode; a.seed = c->seed; a.step = c->step; a.tape = tape_dev; a.partials = c->d_partials.p;
+        a.d_flags = c->d_flags.p; a.d_loc_bond = c->d_loc_bond.p; a.d_loc_cnt = c->d_loc_cnt.p; a.d_loc_first = c->d_loc_first.p;
+        a.d_ap_fire = c->d_ap_fire.p; a.err = c->d_err.p; a.debug = c->debug;
+        const size_t smem = patch_smem_bytes(7, 9, cs.max_halo, cs.max_elem, cs.stride);
+        npart = cs.npatch;
+        if (fuse_predict) {
+            if (c->debug) k_cell_patch<true, true><<<cs.npatch, kPatch, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, dview(cs));
+            else k_cell_patch<true, false><<<cs.npatch, kPatch, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, DebugView{});
+            std::swap(cs.x.p, cs.X.p);      // the buffer just read holds X_t, the one just written x_{t+dt}
+            cv = view(cs);
+        } else {
+            if (c->debug) k_cell_patch<false, true><<<cs.npatch, kPatch, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, dview(cs));
+            else k_cell_patch<false, false><<<cs.npatch, kPatch, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, DebugView{});
+        }
+        c->launches += 1;
+    } else {
+        if (fuse_predict) {
+            ProfScope ps(c, K_PREDICT);
+            k_predict_cell<<<gc, kBlock, 0, c->stream>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt);
+            c->launches += 1;
+        }
+        { ProfScope ps(c, K_BOND);
+        k_bond<<<gc, kBlock, 0, c->stream>>>(cv, sv, c->grid, bk, c->k, dt_real, c->ibox[0], c->ibox[1], c->ibox[2], c->ibox[3], c->d_flags.p, c->d_loc_bond.p, c->d_loc_cnt.p, c->d_loc_first.p, c->debug, c->d_err.p); }
+        { ProfScope ps(c, K_CELL);
+        if (c->debug)
+            k_cell_node<true><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, dview(cs));
+        else
+            k_cell_node<false><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, DebugView{}); }
+        c->launches += 2;
+    }
     { ProfScope ps(c, K_FINISH);
-    if (c->debug) k_boundary_finish<true><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, gc, c->d_partials.p, dt, dt_real, c->d_diag.p, dview(cs));
-    else k_boundary_finish<false><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, gc, c->d_partials.p, dt, dt_real, c->d_diag.p, DebugView{}); }
-    if (use_planar(c)) {
+    if (c->debug) k_boundary_finish<true><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, dt, dt_real, c->d_diag.p, dview(cs));
+    else k_boundary_finish<false><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, dt, dt_real, c->d_diag.p, DebugView{}); }
+    if (planar) {
         ProfScope ps(c, K_SUBS);
-        const size_t smem = patch_smem_bytes(5, 8, ss.max_halo, ss.max_elem);
+        const size_t smem = patch_smem_bytes(5, 8, ss.max_halo, ss.max_elem, ss.stride);
         PatchView pvs = pview(ss);
         if (c->debug) k_subs_patch<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
         else k_subs_patch<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
-    } else
-    { ProfScope ps(c, K_SUBS);
-    if (c->debug) k_subs_node<true><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
-    else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}); }
-    c->launches += 4;
+    } else {
+        ProfScope ps(c, K_SUBS);
+        if (c->debug) k_subs_node<true><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
+        else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+    }
+    c->launches += 2;
     cs.ea_cur ^= 1; ss.ea_cur ^= 1;
     c->step++;
     CK(cudaGetLastError());
@@ -503,19 +568,32 @@ int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p) {
     if (!out || !p) return WCFE_ERR_ARG;
     *out = nullptr;
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return WCFE_ERR_CUDA;   // no CPU fallback
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {   // no CPU fallback
+        cudaGetLastError();
+        return fail(nullptr, WCFE_ERR_CUDA, std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range"));
+    }
     wcfe_ctx *c = new wcfe_ctx;
     c->device = device;
     int rc = check_params(c, p);
-    if (rc) { delete c; return rc; }
+    if (rc) { g_create_err = c->err; delete c; return rc; }
     c->prm = *p; make_consts(c);
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return WCFE_ERR_CUDA; }
+    auto bail = [&](const char *what, cudaError_t err) { g_create_err = std::string(what) + ": " + cudaGetErrorString(err); cudaGetLastError(); delete c; return WCFE_ERR_CUDA; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     c->stream = c->own_stream;
-    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
     c->rng.seed(1);
-    cudaFuncSetAttribute(k_subs_patch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(k_subs_patch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (c->d_err.alloc(1) != cudaSuccess || c->d_diag.alloc(8) != cudaSuccess) { delete c; return WCFE_ERR_CUDA; }
+    {
+        const void *pk[] = {(const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
+                            (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>};
+        for (const void *f : pk) {
+            // 227 KB is the per-CTA limit including the kernels' small static arrays
+            if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kPatchSmemMax)) != cudaSuccess) return bail("cudaFuncSetAttribute(max dynamic smem)", e);
+            if ((e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return bail("cudaFuncSetAttribute(carveout)", e);
+        }
+    }
+    if ((e = c->d_err.alloc(1)) != cudaSuccess || (e = c->d_diag.alloc(8)) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemset(c->d_err.p, 0, sizeof(int)); cudaMemset(c->d_diag.p, 0, 8 * sizeof(double));
     *out = c;
     return WCFE_OK;
@@ -532,7 +610,7 @@ int wcfe_destroy(wcfe_ctx *c) {
         s.cA.release(); s.cB.release(); s.cC.release(); s.fa.release(); s.asum.release();
         s.d_bnd_node.release(); s.d_bnd_index.release(); s.d_cand_ptr.release(); s.d_cand.release(); s.d_bnd_buf.release();
         s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
-        s.p_elem_ptr.release(); s.p_elem_gid.release(); s.p_halo_ptr.release(); s.p_halo_ids.release(); s.p_elem_lv.release(); s.p_ring16.release(); s.p_cand_l.release();
+        s.p_blob.release(); s.p_elem_ptr.release(); s.p_elem_gid.release(); s.p_cand_l.release();
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();
@@ -562,7 +640,7 @@ int wcfe_set_stream(wcfe_ctx *c, void *cuda_stream) {
     return WCFE_OK;
 }
 
-const char *wcfe_last_error(wcfe_ctx *c) { return c ? c->err.c_str() : "null context"; }
+const char *wcfe_last_error(wcfe_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
 
 int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne, const int *tri) {
     if (!c || surface < 0 || surface > 1 || nn <= 0 || ne <= 0 || !xyz || !tri) return fail(c, WCFE_ERR_ARG, "upload_mesh: bad arguments (empty meshes are not simulated)");
@@ -663,7 +741,7 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
         CK(c->d_flags.alloc(nn)); CK(c->d_loc_bond.alloc(nn)); CK(c->d_loc_cnt.alloc(nn)); CK(c->d_loc_first.alloc(nn)); CK(c->d_ap_fire.alloc(nn));
         CK(cudaMemset(c->d_flags.p, 0, sizeof(int) * nn)); CK(cudaMemset(c->d_loc_bond.p, 0xff, sizeof(int) * nn));
         CK(cudaMemset(c->d_loc_cnt.p, 0, sizeof(int) * nn)); CK(cudaMemset(c->d_loc_first.p, 0xff, sizeof(int) * nn)); CK(cudaMemset(c->d_ap_fire.p, 0, sizeof(int) * nn));
-        CK(c->d_partials.alloc((size_t)4 * ((nn + kBlock - 1) / kBlock)));
+        CK(c->d_partials.alloc((size_t)4 * ((nn + kBlock - 1) / kBlock + 1)));
         update_box(c, xyz, nn);
     } else {
         s.X.release();
@@ -800,7 +878,7 @@ int wcfe_update(wcfe_ctx *c, double dt_req, double dt_real, double t_curr) {
     if (!c->have_predict[WCFE_CELL]) return fail(c, WCFE_ERR_ARG, "update without predict(cell)");
     CK(cudaSetDevice(c->device));
     if ((rc = stage_tape(c, 1))) return rc;
-    if ((rc = launch_update(c, dt_req, dt_real, t_curr, c->d_tape.p))) return rc;
+    if ((rc = launch_update(c, dt_req, dt_real, t_curr, c->d_tape.p, false))) return rc;
     c->have_predict[0] = c->have_predict[1] = false;
     c->t_last = t_curr + dt_real;
     return check_device_errors(c);
@@ -816,11 +894,8 @@ int wcfe_step_n(wcfe_ctx *c, int n, double dt, double *t_io) {
     double t = *t_io;
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int q = 0; q < n; q++) {
-        { ProfScope ps(c, K_PREDICT);
-        k_predict_cell<<<(cs.nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt); }
-        c->launches++;
         const unsigned int *tape = c->d_tape.p ? c->d_tape.p + (size_t)q * cs.nb : nullptr;
-        if ((rc = launch_update(c, dt, dt, t, tape))) return rc;
+        if ((rc = launch_update(c, dt, dt, t, tape, true))) return rc;
         t += dt;   // sim->m_curr_t += accum_dt (main.cpp:405)
     }
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -853,7 +928,7 @@ int wcfe_step_n_roundtrip(wcfe_ctx *c, int n, double dt, double *t_io, long long
         CK(cudaMemcpyAsync(cs.x.p, hc, bc, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(ss.x.p, hs, bs, cudaMemcpyHostToDevice, c->stream));
         const unsigned int *tape = c->d_tape.p ? c->d_tape.p + (size_t)q * cs.nb : nullptr;
-        if ((rc = launch_update(c, dt, dt, t, tape))) return rc;
+        if ((rc = launch_update(c, dt, dt, t, tape, false))) return rc;
         CK(cudaMemcpyAsync(hd, c->d_diag.p, 64, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         t += dt;

@@ -19,51 +19,107 @@
 
 namespace wcfe {
 
-constexpr int kPatch = 256;          // owned nodes per patch == threads per CTA
+#ifndef WCFE_PATCH
+#define WCFE_PATCH 128
+#endif
+#ifndef WCFE_MINBLK
+#define WCFE_MINBLK 6
+#endif
+constexpr int kPatch = WCFE_PATCH;   // owned nodes per patch == threads per CTA
+constexpr int kMinBlk = WCFE_MINBLK; // resident CTAs per SM the register allocation is tuned for
 
+// Per-patch descriptor ("blob"): everything a CTA needs to know about its patch, contiguous and of one fixed stride for
+// all patches of a surface, so that ONE TMA bulk copy (cp.async.bulk -> UBLKCP) stages it without any dependent lookup:
+//   int32  hdr[4]           nh (halo nodes), nel (patch-local elements), 0, 0
+//   int32  halo_ids[Hp]     global node ids of the halo nodes
+//   uint16 elem_lv[3*Ep]    local vertex ids per element: < kPatch owned (node - first), >= kPatch halo
+//   uint16 ring_ptr[kPatch+8]  CSR offsets of the owned nodes into ring16 (patch-relative)
+//   uint16 ring16[Rp]       (local element << 2) | slot, ascending global element id per node
+// (every section padded to 16 B).  The owned nodes' state arrays are contiguous too and ride the same mbarrier.
 struct PatchView {
     int npatch;
-    int max_halo, max_elem;          // shared-memory strides
-    const int *elem_ptr;             // [npatch+1] into elem_gid / elem_lv
-    const int *elem_gid;             // global element id of every patch-local element (ascending inside a patch)
-    const unsigned short *elem_lv;   // [3*total] local vertex ids: < kPatch owned (node - first), >= kPatch halo
-    const int *halo_ptr;             // [npatch+1] into halo_ids
-    const int *halo_ids;             // global node ids of the halo nodes
-    const unsigned short *ring16;    // parallel to SurfView::ring: (local element << 2) | slot
+    int max_halo, max_elem;          // shared-memory strides of the node / record arrays
+    int stride;                      // blob bytes per patch
+    int off_halo, off_lv, off_rptr, off_ring;   // byte offsets of the sections inside a blob
+    const unsigned char *blob;       // [npatch * stride]
+    const int *elem_ptr;             // [npatch+1] into elem_gid
+    const int *elem_gid;             // global element id of every patch-local element (substrate: bucket lookup)
     const unsigned short *cand_l;    // parallel to BoundaryView::cand: local node ids (cell only)
 };
 
-__host__ __device__ inline size_t patch_smem_bytes(int n_node_arrays, int n_rec, int max_halo, int max_elem) {
+__host__ __device__ inline size_t patch_smem_bytes(int n_node_arrays, int n_rec, int max_halo, int max_elem, int stride) {
     const size_t NL = (size_t)kPatch + max_halo, EM = (size_t)max_elem;
-    return sizeof(double) * (n_node_arrays * NL + n_rec * EM);
+    return 16 + (size_t)stride + sizeof(double) * (n_node_arrays * NL + n_rec * EM);
+}
+
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ----------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned int bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int phase) {
+    unsigned int ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    } while (!ok);
 }
 
 // ---- substrate: updateForces_Explicit (UL:429-504) + driverVelocities_Biaxial (UL:275-345) + calculateForce_FA_subs ---
 // (UL:1297-1454) for a frozen substrate (main.cpp:299): X == x, so only x is staged.
 template <bool DBG>
-__global__ void __launch_bounds__(kPatch) k_subs_patch(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
+__global__ void __launch_bounds__(kPatch, kMinBlk) k_subs_patch(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
                                                        double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(128) unsigned char smraw[];
     const int NL = kPatch + pv.max_halo, EM = pv.max_elem;
-    double *sx0 = sm, *sx1 = sx0 + NL, *se0 = sx1 + NL, *se1 = se0 + NL, *se3 = se1 + NL;
+    unsigned long long *bar = (unsigned long long *)smraw;
+    unsigned char *sblob = smraw + 16;
+    double *sx0 = (double *)(sblob + pv.stride), *sx1 = sx0 + NL, *se0 = sx1 + NL, *se1 = se0 + NL, *se3 = se1 + NL;
     double *rec = se3 + NL;                       // [8][EM]: r1x r1y r2x r2y es0 es1 es3 A0
     const int p = blockIdx.x, tid = threadIdx.x;
     const int n0 = p * kPatch;
     const int nown = min(kPatch, s.nn - n0);
-    const int h0 = pv.halo_ptr[p], nh = pv.halo_ptr[p + 1] - h0;
-    const int e0 = pv.elem_ptr[p], nel = pv.elem_ptr[p + 1] - e0;
+    const int ncopy = min(kPatch, s.np - n0);     // padded count: bulk copies move multiples of 16 B
     const int np = s.np;
-    // ---- load
-    for (int l = tid; l < kPatch + nh; l += kPatch) {
-        int g;
-        if (l < kPatch) { if (l >= nown) continue; g = n0 + l; } else g = pv.halo_ids[h0 + l - kPatch];
-        sx0[l] = s.x[g]; sx1[l] = s.x[np + g];
-        se0[l] = s.ea_in[g]; se1[l] = s.ea_in[np + g]; se3[l] = s.ea_in[3 * np + g];
+    // ---- stage: one thread issues the TMA bulk copies (descriptor + the owned nodes' five state arrays)
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        const unsigned int nb = (unsigned int)ncopy * 8u;
+        mbar_expect_tx(bar, (unsigned int)pv.stride + 5u * nb);
+        bulk_g2s(sblob, pv.blob + (size_t)p * pv.stride, (unsigned int)pv.stride, bar);
+        bulk_g2s(sx0, s.x + n0, nb, bar); bulk_g2s(sx1, s.x + np + n0, nb, bar);
+        bulk_g2s(se0, s.ea_in + n0, nb, bar); bulk_g2s(se1, s.ea_in + np + n0, nb, bar); bulk_g2s(se3, s.ea_in + 3 * (size_t)np + n0, nb, bar);
+    }
+    // own V, A straight to registers while the copies fly
+    const int i = n0 + tid;
+    double V0 = 0, V1 = 0, A0v = 0, A1v = 0;
+    if (tid < nown) { V0 = s.V[i]; V1 = s.V[np + i]; A0v = s.A[i]; A1v = s.A[np + i]; }
+    __syncthreads();                              // barrier init visible to all waiters
+    mbar_wait(bar, 0);
+    const int *hdr = (const int *)sblob;
+    const int nh = hdr[0], nel = hdr[1];
+    const int *halo_ids = (const int *)(sblob + pv.off_halo);
+    const unsigned short *elem_lv = (const unsigned short *)(sblob + pv.off_lv);
+    const unsigned short *rptr = (const unsigned short *)(sblob + pv.off_rptr);
+    const unsigned short *ring16 = (const unsigned short *)(sblob + pv.off_ring);
+    // ---- halo gather (L2-resident: these nodes are owned by neighbouring patches)
+    for (int l = tid; l < nh; l += kPatch) {
+        const int g = halo_ids[l];
+        sx0[kPatch + l] = s.x[g]; sx1[kPatch + l] = s.x[np + g];
+        se0[kPatch + l] = s.ea_in[g]; se1[kPatch + l] = s.ea_in[np + g]; se3[kPatch + l] = s.ea_in[3 * (size_t)np + g];
     }
     __syncthreads();
     // ---- elements
     for (int el = tid; el < nel; el += kPatch) {
-        const unsigned short *lv = pv.elem_lv + (size_t)3 * (e0 + el);
+        const unsigned short *lv = elem_lv + 3 * el;
         const int a = lv[0], b = lv[1], d = lv[2];
         const double X[3][2] = {{sx0[a], sx1[a]}, {sx0[b], sx1[b]}, {sx0[d], sx1[d]}};
         const double e3[3] = {1.0 / 3.0 * se0[a] + 1.0 / 3.0 * se0[b] + 1.0 / 3.0 * se0[d], 1.0 / 3.0 * se1[a] + 1.0 / 3.0 * se1[b] + 1.0 / 3.0 * se1[d],
@@ -76,12 +132,11 @@ __global__ void __launch_bounds__(kPatch) k_subs_patch(SurfView s, PatchView pv,
     __syncthreads();
     // ---- nodes
     if (tid >= nown) return;
-    const int i = n0 + tid;
     const double ea0 = se0[tid], ea1 = se1[tid], ea3 = se3[tid];
     double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
-    const int rb = s.ring_ptr[i], re = s.ring_ptr[i + 1];
+    const int rb = rptr[tid], re = rptr[tid + 1];
     for (int r = rb; r < re; r++) {
-        const int code = pv.ring16[r];
+        const int code = ring16[r];
         const int el = code >> 2, slot = code & 3;
         const double r1x = rec[el], r1y = rec[EM + el], r2x = rec[2 * EM + el], r2y = rec[3 * EM + el];
         rx += slot == 0 ? -(r1x + r2x) : (slot == 1 ? r1x : r2x);
@@ -95,15 +150,16 @@ __global__ void __launch_bounds__(kPatch) k_subs_patch(SurfView s, PatchView pv,
     const double Xi0 = sx0[tid], Xi1 = sx1[tid];
     double Fx = 0.0, Fy = 0.0;
     if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
+        const int e0 = pv.elem_ptr[p];
         for (int r = rb; r < re; r++) {
-            const int code = pv.ring16[r];
+            const int code = ring16[r];
             const int el = code >> 2, slot = code & 3;
             const int e = pv.elem_gid[e0 + el];
             const unsigned long long h = bk.head[e];
             if ((unsigned int)(h >> 32) != bk.epoch) continue;
             int cnt = (int)(unsigned int)h;
             if (cnt > bk.cap) cnt = bk.cap;
-            const unsigned short *lv = pv.elem_lv + (size_t)3 * (e0 + el);
+            const unsigned short *lv = elem_lv + 3 * el;
             const double n1[3] = {sx0[lv[0]], sx1[lv[0]], 0.0}, n2[3] = {sx0[lv[1]], sx1[lv[1]], 0.0}, n3[3] = {sx0[lv[2]], sx1[lv[2]], 0.0};
             int prev = -1;
             for (int m = 0; m < cnt; m++) {          // ascending cell-node order: deterministic whatever the insertion order was
@@ -122,7 +178,6 @@ __global__ void __launch_bounds__(kPatch) k_subs_patch(SurfView s, PatchView pv,
             }
         }
     }
-    double V0 = s.V[i], V1 = s.V[np + i], A0v = s.A[i], A1v = s.A[np + i];
     double Vh0 = V0 + (dt / 2.0) * A0v, Vh1 = V1 + (dt / 2.0) * A1v;
     if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {            // UL:298-341, Vbiax == 0
         if (Xi0 < -k.pin_limit || Xi0 > k.pin_limit) Vh0 = 0.0;
@@ -136,6 +191,217 @@ __global__ void __launch_bounds__(kPatch) k_subs_patch(SurfView s, PatchView pv,
         dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
         dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
     }
+}
+
+
+// ---- cell: the whole cell side of one UL step in ONE kernel ---------------------------------------------------------
+//   PREDICT: driverVelocities_Explicit + inline predictor (UL:103-124, main.cpp:224-242) for owned AND halo nodes, read
+//            from the current position buffer and written to the other one (ping-pong: the old buffer becomes X_t);
+//   updateFA (UL:2005-2114) and the anchor location / bucket insertion for calculateForce_FA_subs (UL:1301-1340);
+//   updateForces_Explicit, cell overload (UL:508-630): residual, integrin, drag, bending, actin, update.
+// Boundary vertices wait for the total area exactly as in k_cell_node (finished by k_boundary_finish).
+struct CellStepArgs {
+    double dt, dt_real, t_tot, ap_threshold;
+    double ix0, ix1, iy0, iy1;
+    int rng_mode; unsigned int seed, step;
+    const unsigned int *tape;
+    double *partials;
+    int *d_flags, *d_loc_bond, *d_loc_cnt, *d_loc_first, *d_ap_fire, *err;
+    int debug;
+};
+
+template <bool PREDICT, bool DBG>
+__global__ void __launch_bounds__(kPatch, kMinBlk) k_cell_patch(SurfView s, PatchView pv, SurfView sub, GridView g, BucketView bk, BoundaryView b, Consts k,
+                                                       CellStepArgs a, const double *__restrict__ x_in, double *__restrict__ x_out, DebugView dbg) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ double shred[4 * 32];
+    const int NL = kPatch + pv.max_halo, EM = pv.max_elem;
+    unsigned long long *bar = (unsigned long long *)smraw;
+    unsigned char *sblob = smraw + 16;
+    double *sX0 = (double *)(sblob + pv.stride), *sX1 = sX0 + NL, *sx0 = sX1 + NL, *sx1 = sx0 + NL, *se0 = sx1 + NL, *se1 = se0 + NL, *se3 = se1 + NL;
+    double *rec = se3 + NL;                       // [9][EM]: r1x r1y r2x r2y es0 es1 es3 A0 a_cur
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int n0 = p * kPatch;
+    const int nown = min(kPatch, s.nn - n0);
+    const int ncopy = min(kPatch, s.np - n0);
+    const int np = s.np;
+    // ---- stage: TMA bulk copies of the patch descriptor and of the owned nodes' state
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        const unsigned int nb = (unsigned int)ncopy * 8u;
+        mbar_expect_tx(bar, (unsigned int)pv.stride + (PREDICT ? 5u : 7u) * nb);
+        bulk_g2s(sblob, pv.blob + (size_t)p * pv.stride, (unsigned int)pv.stride, bar);
+        if (PREDICT) { bulk_g2s(sX0, x_in + n0, nb, bar); bulk_g2s(sX1, x_in + np + n0, nb, bar); }
+        else { bulk_g2s(sX0, s.X + n0, nb, bar); bulk_g2s(sX1, s.X + np + n0, nb, bar); bulk_g2s(sx0, s.x + n0, nb, bar); bulk_g2s(sx1, s.x + np + n0, nb, bar); }
+        bulk_g2s(se0, s.ea_in + n0, nb, bar); bulk_g2s(se1, s.ea_in + np + n0, nb, bar); bulk_g2s(se3, s.ea_in + 3 * (size_t)np + n0, nb, bar);
+    }
+    const bool own = tid < nown;
+    const int i = n0 + tid;
+    double V0 = 0, V1 = 0, Av0 = 0, Av1 = 0;      // own node's V, A (kept for the update)
+    double fa0 = 0, fa1 = 0, cC = 0;
+    if (own) { V0 = s.V[i]; V1 = s.V[np + i]; Av0 = s.A[i]; Av1 = s.A[np + i]; fa0 = s.fa[i]; fa1 = s.fa[np + i]; cC = s.cC[i]; }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const int *hdr = (const int *)sblob;
+    const int nh = hdr[0], nel = hdr[1];
+    const int *halo_ids = (const int *)(sblob + pv.off_halo);
+    const unsigned short *elem_lv = (const unsigned short *)(sblob + pv.off_lv);
+    const unsigned short *rptr = (const unsigned short *)(sblob + pv.off_rptr);
+    const unsigned short *ring16 = (const unsigned short *)(sblob + pv.off_ring);
+    // ---- predictor for the own node (UL:118, main.cpp:228; uncontracted so that x_new is bit-identical to the x86 reference)
+    if (PREDICT && own) {
+        const double vh0 = WCFE_ADD(V0, WCFE_MUL(a.dt / 2.0, Av0)), vh1 = WCFE_ADD(V1, WCFE_MUL(a.dt / 2.0, Av1));
+        const double xn0 = WCFE_ADD(sX0[tid], WCFE_MUL(a.dt, vh0)), xn1 = WCFE_ADD(sX1[tid], WCFE_MUL(a.dt, vh1));
+        sx0[tid] = xn0; sx1[tid] = xn1;
+        x_out[i] = xn0; x_out[np + i] = xn1;
+    }
+    // ---- halo gather (+ the same predictor: every patch that sees a node computes the same x_new)
+    for (int l = tid; l < nh; l += kPatch) {
+        const int gi = halo_ids[l];
+        const int d = kPatch + l;
+        if (PREDICT) {
+            const double xo0 = x_in[gi], xo1 = x_in[np + gi];
+            const double v0 = s.V[gi], v1 = s.V[np + gi], a0 = s.A[gi], a1 = s.A[np + gi];
+            const double vh0 = WCFE_ADD(v0, WCFE_MUL(a.dt / 2.0, a0)), vh1 = WCFE_ADD(v1, WCFE_MUL(a.dt / 2.0, a1));
+            sX0[d] = xo0; sX1[d] = xo1; sx0[d] = WCFE_ADD(xo0, WCFE_MUL(a.dt, vh0)); sx1[d] = WCFE_ADD(xo1, WCFE_MUL(a.dt, vh1));
+        } else {
+            sX0[d] = s.X[gi]; sX1[d] = s.X[np + gi]; sx0[d] = s.x[gi]; sx1[d] = s.x[np + gi];
+        }
+        se0[d] = s.ea_in[gi]; se1[d] = s.ea_in[np + gi]; se3[d] = s.ea_in[3 * (size_t)np + gi];
+    }
+    // ---- bond kinetics + anchor location for the own node (needs only its own X, x)
+    if (own) {
+        const double Xi[3] = {sX0[tid], sX1[tid], 0.0}, xi[3] = {sx0[tid], sx1[tid], 0.0};
+        double fa[3] = {fa0, fa1, 0.0};
+        if (a.debug) {
+            const double pt0[3] = {Xi[0] - fa[0], Xi[1] - fa[1], 0.0};                  // UL:2020
+            int last = -1;
+            locate(g, sub, pt0, [&](int t, const double *, double) { last = t; });
+            a.d_loc_bond[i] = last;
+        }
+        const double cell_u[3] = {xi[0] - Xi[0], xi[1] - Xi[1], 0.0}, subs_u[3] = {0.0, 0.0, 0.0};
+        a.d_flags[i] = bond_update(k, a.dt_real, cell_u, subs_u, fa, cC);
+        fa0 = fa[0]; fa1 = fa[1];
+        s.fa[i] = fa0; s.fa[np + i] = fa1; s.cC[i] = cC;
+        const double pt[3] = {xi[0] - fa0, xi[1] - fa1, 0.0};                           // UL:1303
+        if (!(pt[0] >= a.ix0 && pt[0] <= a.ix1 && pt[1] >= a.iy0 && pt[1] <= a.iy1)) atomicOr(a.err, ERR_REGION);
+        int cnt = 0, first = -1;
+        auto insert = [&](int t, const double *, double) {
+            if (cnt == 0) first = t;
+            cnt++;
+            unsigned long long *h = bk.head + t;
+            unsigned long long old = *h, want;
+            int slot;
+            do {
+                const unsigned long long seen = old;
+                if ((unsigned int)(seen >> 32) != bk.epoch) { want = ((unsigned long long)bk.epoch << 32) | 1ull; slot = 0; }
+                else { want = seen + 1ull; slot = (int)(unsigned int)seen; }
+                old = atomicCAS(h, seen, want);
+                if (old == seen) break;
+            } while (true);
+            if (slot < bk.cap) bk.items[(size_t)t * bk.cap + slot] = i; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
+        };
+        // Anchors rarely change triangle between steps: try the triangle of the previous step first.  A point STRICTLY inside
+        // it (all three sub-areas > 0) lies in no other triangle of a conforming substrate mesh, so the grid search -- which
+        // finds every containing triangle, as the reference's exhaustive loop does (UL:1309-1452) -- is only needed otherwise.
+        bool done = false;
+        const int tprev = a.d_loc_first[i];
+        if (tprev >= 0 && tprev < sub.ne) {
+            const int i0 = sub.tri[tprev], i1 = sub.tri[sub.nep + tprev], i2 = sub.tri[2 * sub.nep + tprev];
+            const double n1[3] = {sub.x[i0], sub.x[sub.np + i0], sub.x[2 * sub.np + i0]};
+            const double n2[3] = {sub.x[i1], sub.x[sub.np + i1], sub.x[2 * sub.np + i1]};
+            const double n3[3] = {sub.x[i2], sub.x[sub.np + i2], sub.x[2 * sub.np + i2]};
+            double Ar[3], At;
+            if (point_in_triangle(n1, n2, n3, pt, Ar, At) && Ar[0] > 0 && Ar[1] > 0 && Ar[2] > 0) { insert(tprev, Ar, At); done = true; }
+        }
+        if (!done) locate(g, sub, pt, insert);
+        a.d_loc_cnt[i] = cnt; a.d_loc_first[i] = first;
+    }
+    __syncthreads();
+    // ---- elements
+    const double tk = t_act_of(k, a.t_tot) * k.kappa;
+    for (int el = tid; el < nel; el += kPatch) {
+        const unsigned short *lv = elem_lv + 3 * el;
+        const int n1 = lv[0], n2 = lv[1], n3 = lv[2];
+        const double X[3][2] = {{sX0[n1], sX1[n1]}, {sX0[n2], sX1[n2]}, {sX0[n3], sX1[n3]}};
+        const double x[3][2] = {{sx0[n1], sx1[n1]}, {sx0[n2], sx1[n2]}, {sx0[n3], sx1[n3]}};
+        const double e3[3] = {1.0 / 3.0 * se0[n1] + 1.0 / 3.0 * se0[n2] + 1.0 / 3.0 * se0[n3], 1.0 / 3.0 * se1[n1] + 1.0 / 3.0 * se1[n2] + 1.0 / 3.0 * se1[n3],
+                              1.0 / 3.0 * se3[n1] + 1.0 / 3.0 * se3[n2] + 1.0 / 3.0 * se3[n3]};
+        ElemOut2 o;
+        elem_eval_planar(X, x, e3, k.mu_cell, tk, k.thick, o);
+        rec[el] = o.r1[0]; rec[EM + el] = o.r1[1]; rec[2 * EM + el] = o.r2[0]; rec[3 * EM + el] = o.r2[1];
+        rec[4 * EM + el] = o.eas[0]; rec[5 * EM + el] = o.eas[1]; rec[6 * EM + el] = o.eas[2]; rec[7 * EM + el] = o.A0; rec[8 * EM + el] = o.a_cur;
+    }
+    __syncthreads();
+    // ---- nodes
+    double red[4] = {0.0, 0.0, 0.0, 0.0};
+    if (own) {
+        const double ea0 = se0[tid], ea1 = se1[tid], ea3 = se3[tid];
+        double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0, asum = 0.0;
+        const int rb = rptr[tid], re = rptr[tid + 1];
+        for (int r = rb; r < re; r++) {
+            const int code = ring16[r];
+            const int el = code >> 2, slot = code & 3;
+            const double r1x = rec[el], r1y = rec[EM + el], r2x = rec[2 * EM + el], r2y = rec[3 * EM + el];
+            rx += slot == 0 ? -(r1x + r2x) : (slot == 1 ? r1x : r2x);
+            ry += slot == 0 ? -(r1y + r2y) : (slot == 1 ? r1y : r2y);
+            const double A0 = rec[7 * EM + el], ac = rec[8 * EM + el];
+            q0 += (1. / 3.) * (rec[4 * EM + el] - ea0) * A0 * k.thick;               // UL:911
+            q1 += (1. / 3.) * (rec[5 * EM + el] - ea1) * A0 * k.thick;
+            q3 += (1. / 3.) * (rec[6 * EM + el] - ea3) * A0 * k.thick;
+            mm += (1. / 3.) * A0 * k.thick;                                          // UL:913
+            asum += ac / 3;                                                          // UL:1251
+            if (slot == 0) {                                                         // UL:1655-1661, each element once
+                const unsigned short *lv = elem_lv + 3 * el;
+                red[0] += ac;
+                red[1] += (1. / 3.) * ((sx0[lv[0]] + sx0[lv[1]]) + sx0[lv[2]]) * ac;
+                red[2] += (1. / 3.) * ((sx1[lv[0]] + sx1[lv[1]]) + sx1[lv[2]]) * ac;
+            }
+        }
+        double Vh0 = V0 + (a.dt / 2.0) * Av0, Vh1 = V1 + (a.dt / 2.0) * Av1;         // UL:118
+        const double u[3] = {fa0, fa1, 0.0};
+        double fi[3];
+        integrin_force(k, u, fi);
+        const double Ffx = -cC * fi[0] * asum * k.rho_i_max, Ffy = -cC * fi[1] * asum * k.rho_i_max;   // UL:1259
+        const double Fvx = -k.drag * Vh0, Fvy = -k.drag * Vh1;                       // UL:571
+        s.asum[i] = asum;
+        s.ea_out[i] = ea0 + q0 / mm; s.ea_out[np + i] = ea1 + q1 / mm; s.ea_out[3 * np + i] = ea3 + q3 / mm;   // UL:607-612
+        if (DBG) {
+            dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Ffx; dbg.f_fa[np + i] = Ffy; dbg.mm[i] = mm;
+            dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
+            dbg.f_ap[i] = 0.0; dbg.f_ap[np + i] = 0.0; dbg.f_bend[i] = 0.0; dbg.f_bend[np + i] = 0.0; dbg.f_area[i] = 0.0; dbg.f_area[np + i] = 0.0;
+        }
+        const int bi = b.index[i];
+        if (bi < 0) {
+            node_update(Fvx + Ffx - rx, mm, k.damp, k.rho, a.dt, a.dt_real, Vh0, V0, Av0);           // UL:592-628
+            node_update(Fvy + Ffy - ry, mm, k.damp, k.rho, a.dt, a.dt_real, Vh1, V1, Av1);
+            s.V[i] = V0; s.V[np + i] = V1; s.A[i] = Av0; s.A[np + i] = Av1;
+        } else {
+            const double xi[3] = {sx0[tid], sx1[tid], 0.0};
+            double j1[3] = {0, 0, 0}, j2[3] = {0, 0, 0};
+            for (int q = b.cand_ptr[bi]; q < b.cand_ptr[bi + 1]; q++) {                                // UL:1479-1507
+                const int lj = pv.cand_l[2 * q], lint = pv.cand_l[2 * q + 1];
+                const double xb[3] = {sx0[lj], sx1[lj], 0.0}, xin[3] = {sx0[lint], sx1[lint], 0.0};
+                if (bnd_is_first(xi, xb, xin)) { j1[0] = xb[0]; j1[1] = xb[1]; } else { j2[0] = xb[0]; j2[1] = xb[1]; }
+            }
+            double nrm[3], tl;
+            bnd_normal(xi, j1, j2, nrm, tl);
+            const double kap = bnd_curvature(xi, j1, j2, tl);
+            double Pr;
+            if (a.rng_mode == 0) Pr = (double)a.tape[bi] / 2147483648.0;                               // UL:1525
+            else Pr = (double)philox_u32(a.seed, a.step, (unsigned int)bi) * (1.0 / 4294967296.0);
+            const bool fire = Pr < a.ap_threshold;
+            const double factin = fire ? k.ap_quantum * ap_trips(k.ap_density, tl) : 0.0;
+            a.d_ap_fire[i] = fire ? 1 : 0;
+            double *o = b.buf + (size_t)16 * bi;
+            const double Fbx = k.k_bend * kap * nrm[0], Fby = k.k_bend * kap * nrm[1], Fax = factin * nrm[0], Fay = factin * nrm[1];
+            o[0] = ((Fvx + Fbx) + Fax) + Ffx; o[1] = ((Fvy + Fby) + Fay) + Ffy; o[2] = 0.0;
+            o[3] = rx; o[4] = ry; o[5] = 0.0; o[6] = mm; o[7] = tl; o[8] = nrm[0]; o[9] = nrm[1]; o[10] = 0.0;
+            if (DBG) { dbg.f_bend[i] = Fbx; dbg.f_bend[np + i] = Fby; dbg.f_ap[i] = Fax; dbg.f_ap[np + i] = Fay; }
+        }
+    }
+    block_reduce4(red, shred);
+    if (tid == 0) { for (int q = 0; q < 4; q++) a.partials[(size_t)4 * blockIdx.x + q] = red[q]; }
 }
 
 }   // namespace wcfe

@@ -38,8 +38,8 @@ class ULSim:
         rc = self.L.wcfe_create(C.byref(self.h), device, C.byref(self.params))
         if rc:
             self.h = None
-            raise WcfeError(rc, "wcfe_create failed (no CUDA device %d? the product has no CPU fallback)" % device
-                            if rc == B.ERR_CUDA else "wcfe_create: unsupported / invalid parameters")
+            why = self.L.wcfe_last_error(None).decode()
+            raise WcfeError(rc, "wcfe_create(device %d) failed: %s%s" % (device, why, " -- the product has no CPU fallback" if rc == B.ERR_CUDA else ""))
         if stream is not None:
             self._ck(self.L.wcfe_set_stream(self.h, C.c_void_p(stream)))
         self.nn = [0, 0]
