@@ -39,3 +39,9 @@ extern "C" void hm_elem_eval_planar(const double *X6, const double *x6, const do
     ElemOut2 o; elem_eval_planar(X, x, e3, mu, tk, thick, o);
     memcpy(r1, o.r1, 16); memcpy(r2, o.r2, 16); memcpy(eas, o.eas, 24); *A0 = o.A0; *acur = o.a_cur;
 }
+
+extern "C" void hm_elem_eval_frozen(const double *X6, const double *e3, double mu, double thick, double *r1, double *r2, double *A0) {
+    double X[3][2]; memcpy(X, X6, sizeof X);
+    ElemOutFrozen o; elem_eval_frozen(X, e3, mu, thick, o);
+    memcpy(r1, o.r1, 16); memcpy(r2, o.r2, 16); *A0 = o.A0;
+}

@@ -466,13 +466,13 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         const size_t smem = patch_smem_bytes(7, 9, cs.max_halo, cs.max_elem, cs.stride);
         npart = cs.npatch;
         if (fuse_predict) {
-            if (c->debug) k_cell_patch<true, true><<<cs.npatch, kPatch, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, dview(cs));
-            else k_cell_patch<true, false><<<cs.npatch, kPatch, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, DebugView{});
+            if (c->debug) k_cell_patch<true, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, dview(cs));
+            else k_cell_patch<true, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, DebugView{});
             std::swap(cs.x.p, cs.X.p);      // the buffer just read holds X_t, the one just written x_{t+dt}
             cv = view(cs);
         } else {
-            if (c->debug) k_cell_patch<false, true><<<cs.npatch, kPatch, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, dview(cs));
-            else k_cell_patch<false, false><<<cs.npatch, kPatch, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, DebugView{});
+            if (c->debug) k_cell_patch<false, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, dview(cs));
+            else k_cell_patch<false, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, DebugView{});
         }
         c->launches += 1;
     } else {
@@ -497,8 +497,8 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         ProfScope ps(c, K_SUBS);
         const size_t smem = patch_smem_bytes(5, 8, ss.max_halo, ss.max_elem, ss.stride);
         PatchView pvs = pview(ss);
-        if (c->debug) k_subs_patch<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
-        else k_subs_patch<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+        if (c->debug) k_subs_patch<true><<<ss.npatch, kThreads, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
+        else k_subs_patch<false><<<ss.npatch, kThreads, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
     } else {
         ProfScope ps(c, K_SUBS);
         if (c->debug) k_subs_node<true><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));

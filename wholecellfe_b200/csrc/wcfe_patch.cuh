@@ -25,8 +25,13 @@ namespace wcfe {
 #ifndef WCFE_MINBLK
 #define WCFE_MINBLK 6
 #endif
-constexpr int kPatch = WCFE_PATCH;   // owned nodes per patch == threads per CTA
-constexpr int kMinBlk = WCFE_MINBLK; // resident CTAs per SM the register allocation is tuned for
+#ifndef WCFE_THREADS
+#define WCFE_THREADS 128
+#endif
+constexpr int kPatch = WCFE_PATCH;     // owned nodes per patch
+constexpr int kThreads = WCFE_THREADS; // threads per CTA: a patch has ~2.35 elements per owned node, so 1.25 x kPatch threads
+                                       // finish the element phase in two full rounds instead of two and a tail
+constexpr int kMinBlk = WCFE_MINBLK;   // resident CTAs per SM the register allocation is tuned for
 
 // Per-patch descriptor ("blob"): everything a CTA needs to know about its patch, contiguous and of one fixed stride for
 // all patches of a surface, so that ONE TMA bulk copy (cp.async.bulk -> UBLKCP) stages it without any dependent lookup:
@@ -49,7 +54,10 @@ struct PatchView {
 
 __host__ __device__ inline size_t patch_smem_bytes(int n_node_arrays, int n_rec, int max_halo, int max_elem, int stride) {
     const size_t NL = (size_t)kPatch + max_halo, EM = (size_t)max_elem;
-    return 16 + (size_t)stride + sizeof(double) * (n_node_arrays * NL + n_rec * EM);
+    size_t recs = sizeof(double) * n_rec * EM;
+    const size_t staging = sizeof(double) * 8 * (size_t)kPatch;      // owned-node SoA landing zone (aliases the record area)
+    if (recs < staging) recs = staging;
+    return 16 + (size_t)stride + sizeof(double) * n_node_arrays * NL + recs + 64;
 }
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ----------------------------------------------------------------------
@@ -74,34 +82,40 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
 }
 
 // ---- substrate: updateForces_Explicit (UL:429-504) + driverVelocities_Biaxial (UL:275-345) + calculateForce_FA_subs ---
-// (UL:1297-1454) for a frozen substrate (main.cpp:299): X == x, so only x is staged.
+// (UL:1297-1454) for a frozen substrate (main.cpp:299): X == x, F == I, closed form elem_eval_frozen.
+// Shared memory: node table packed as (x,y) / (e_xx,e_yy) double2 + e_xy, element records as four double2 per element
+// (force on local node 1, 2; (e_s.xx,e_s.yy); (e_s.xy, A0)) so that gathers are 128-bit and branch-free.
 template <bool DBG>
-__global__ void __launch_bounds__(kPatch, kMinBlk) k_subs_patch(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
-                                                       double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg) {
+__global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
+                                                                  double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg) {
     extern __shared__ __align__(128) unsigned char smraw[];
     const int NL = kPatch + pv.max_halo, EM = pv.max_elem;
     unsigned long long *bar = (unsigned long long *)smraw;
     unsigned char *sblob = smraw + 16;
-    double *sx0 = (double *)(sblob + pv.stride), *sx1 = sx0 + NL, *se0 = sx1 + NL, *se1 = se0 + NL, *se3 = se1 + NL;
-    double *rec = se3 + NL;                       // [8][EM]: r1x r1y r2x r2y es0 es1 es3 A0
+    double2 *sxy = (double2 *)(sblob + pv.stride);       // [NL]
+    double2 *se01 = sxy + NL;                             // [NL]
+    double *se3 = (double *)(se01 + NL);                  // [NL] (NL is a multiple of 4)
+    double2 *rec = (double2 *)(se3 + NL);                 // [4][EM]; first used as the SoA landing zone of the bulk copies
+    double *stage = (double *)rec;                        // [5][kPatch]: x0 x1 e0 e1 e3 of the owned nodes
     const int p = blockIdx.x, tid = threadIdx.x;
     const int n0 = p * kPatch;
     const int nown = min(kPatch, s.nn - n0);
     const int ncopy = min(kPatch, s.np - n0);     // padded count: bulk copies move multiples of 16 B
     const int np = s.np;
-    // ---- stage: one thread issues the TMA bulk copies (descriptor + the owned nodes' five state arrays)
     if (tid == 0) {
         mbar_init(bar, 1);
         const unsigned int nb = (unsigned int)ncopy * 8u;
         mbar_expect_tx(bar, (unsigned int)pv.stride + 5u * nb);
         bulk_g2s(sblob, pv.blob + (size_t)p * pv.stride, (unsigned int)pv.stride, bar);
-        bulk_g2s(sx0, s.x + n0, nb, bar); bulk_g2s(sx1, s.x + np + n0, nb, bar);
-        bulk_g2s(se0, s.ea_in + n0, nb, bar); bulk_g2s(se1, s.ea_in + np + n0, nb, bar); bulk_g2s(se3, s.ea_in + 3 * (size_t)np + n0, nb, bar);
+        bulk_g2s(stage, s.x + n0, nb, bar); bulk_g2s(stage + kPatch, s.x + np + n0, nb, bar);
+        bulk_g2s(stage + 2 * kPatch, s.ea_in + n0, nb, bar); bulk_g2s(stage + 3 * kPatch, s.ea_in + np + n0, nb, bar);
+        bulk_g2s(stage + 4 * kPatch, s.ea_in + 3 * (size_t)np + n0, nb, bar);
     }
     // own V, A straight to registers while the copies fly
     const int i = n0 + tid;
+    const bool own = tid < nown;
     double V0 = 0, V1 = 0, A0v = 0, A1v = 0;
-    if (tid < nown) { V0 = s.V[i]; V1 = s.V[np + i]; A0v = s.A[i]; A1v = s.A[np + i]; }
+    if (own) { V0 = s.V[i]; V1 = s.V[np + i]; A0v = s.A[i]; A1v = s.A[np + i]; }
     __syncthreads();                              // barrier init visible to all waiters
     mbar_wait(bar, 0);
     const int *hdr = (const int *)sblob;
@@ -110,44 +124,51 @@ __global__ void __launch_bounds__(kPatch, kMinBlk) k_subs_patch(SurfView s, Patc
     const unsigned short *elem_lv = (const unsigned short *)(sblob + pv.off_lv);
     const unsigned short *rptr = (const unsigned short *)(sblob + pv.off_rptr);
     const unsigned short *ring16 = (const unsigned short *)(sblob + pv.off_ring);
-    // ---- halo gather (L2-resident: these nodes are owned by neighbouring patches)
-    for (int l = tid; l < nh; l += kPatch) {
-        const int g = halo_ids[l];
-        sx0[kPatch + l] = s.x[g]; sx1[kPatch + l] = s.x[np + g];
-        se0[kPatch + l] = s.ea_in[g]; se1[kPatch + l] = s.ea_in[np + g]; se3[kPatch + l] = s.ea_in[3 * (size_t)np + g];
+    // repack the owned nodes, gather the halo nodes (L2-resident: owned by neighbouring patches)
+    double2 myxy = make_double2(0, 0), mye01 = make_double2(0, 0); double mye3 = 0;
+    if (tid < kPatch) {
+        myxy = make_double2(stage[tid], stage[kPatch + tid]); mye01 = make_double2(stage[2 * kPatch + tid], stage[3 * kPatch + tid]); mye3 = stage[4 * kPatch + tid];
+        sxy[tid] = myxy; se01[tid] = mye01; se3[tid] = mye3;
     }
-    __syncthreads();
+    for (int l = tid; l < nh; l += kThreads) {
+        const int g = halo_ids[l];
+        sxy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
+        se01[kPatch + l] = make_double2(s.ea_in[g], s.ea_in[np + g]);
+        se3[kPatch + l] = s.ea_in[3 * (size_t)np + g];
+    }
+    __syncthreads();                              // node table complete; the landing zone may now be overwritten by records
     // ---- elements
-    for (int el = tid; el < nel; el += kPatch) {
+    for (int el = tid; el < nel; el += kThreads) {
         const unsigned short *lv = elem_lv + 3 * el;
         const int a = lv[0], b = lv[1], d = lv[2];
-        const double X[3][2] = {{sx0[a], sx1[a]}, {sx0[b], sx1[b]}, {sx0[d], sx1[d]}};
-        const double e3[3] = {1.0 / 3.0 * se0[a] + 1.0 / 3.0 * se0[b] + 1.0 / 3.0 * se0[d], 1.0 / 3.0 * se1[a] + 1.0 / 3.0 * se1[b] + 1.0 / 3.0 * se1[d],
-                              1.0 / 3.0 * se3[a] + 1.0 / 3.0 * se3[b] + 1.0 / 3.0 * se3[d]};
-        ElemOut2 o;
-        elem_eval_planar(X, X, e3, k.mu_subs, 0.0, k.thick, o);
-        rec[el] = o.r1[0]; rec[EM + el] = o.r1[1]; rec[2 * EM + el] = o.r2[0]; rec[3 * EM + el] = o.r2[1];
-        rec[4 * EM + el] = o.eas[0]; rec[5 * EM + el] = o.eas[1]; rec[6 * EM + el] = o.eas[2]; rec[7 * EM + el] = o.A0;
+        const double2 pa = sxy[a], pb = sxy[b], pd = sxy[d], ea = se01[a], eb = se01[b], ed = se01[d];
+        const double X[3][2] = {{pa.x, pa.y}, {pb.x, pb.y}, {pd.x, pd.y}};
+        const double e3[3] = {1.0 / 3.0 * ea.x + 1.0 / 3.0 * eb.x + 1.0 / 3.0 * ed.x, 1.0 / 3.0 * ea.y + 1.0 / 3.0 * eb.y + 1.0 / 3.0 * ed.y,
+                              1.0 / 3.0 * se3[a] + 1.0 / 3.0 * se3[b] + 1.0 / 3.0 * se3[d]};          // UL:1055
+        ElemOutFrozen o;
+        elem_eval_frozen(X, e3, k.mu_subs, k.thick, o);
+        rec[el] = make_double2(o.r1[0], o.r1[1]);
+        rec[EM + el] = make_double2(o.r2[0], o.r2[1]);
+        rec[2 * EM + el] = make_double2(e3[0], e3[1]);           // e_s == averaged e for F == I
+        rec[3 * EM + el] = make_double2(e3[2], o.A0);
     }
     __syncthreads();
     // ---- nodes
-    if (tid >= nown) return;
-    const double ea0 = se0[tid], ea1 = se1[tid], ea3 = se3[tid];
+    if (!own) return;
+    const double ea0 = mye01.x, ea1 = mye01.y, ea3 = mye3;
     double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
     const int rb = rptr[tid], re = rptr[tid + 1];
     for (int r = rb; r < re; r++) {
         const int code = ring16[r];
         const int el = code >> 2, slot = code & 3;
-        const double r1x = rec[el], r1y = rec[EM + el], r2x = rec[2 * EM + el], r2y = rec[3 * EM + el];
-        rx += slot == 0 ? -(r1x + r2x) : (slot == 1 ? r1x : r2x);
-        ry += slot == 0 ? -(r1y + r2y) : (slot == 1 ? r1y : r2y);
-        const double A0 = rec[7 * EM + el];
-        q0 += (1. / 3.) * (rec[4 * EM + el] - ea0) * A0 * k.thick;       // UL:1170
-        q1 += (1. / 3.) * (rec[5 * EM + el] - ea1) * A0 * k.thick;
-        q3 += (1. / 3.) * (rec[6 * EM + el] - ea3) * A0 * k.thick;
-        mm += (1. / 3.) * A0 * k.thick;                                  // UL:1172
+        const double2 f1 = rec[el], f2 = rec[EM + el], es = rec[2 * EM + el], ez = rec[3 * EM + el];
+        rx += slot == 0 ? -(f1.x + f2.x) : (slot == 1 ? f1.x : f2.x);
+        ry += slot == 0 ? -(f1.y + f2.y) : (slot == 1 ? f1.y : f2.y);
+        const double w = (1. / 3.) * ez.y * k.thick;                     // UL:1172 == the weight of UL:1170
+        q0 += (es.x - ea0) * w; q1 += (es.y - ea1) * w; q3 += (ez.x - ea3) * w;
+        mm += w;
     }
-    const double Xi0 = sx0[tid], Xi1 = sx1[tid];
+    const double Xi0 = myxy.x, Xi1 = myxy.y;
     double Fx = 0.0, Fy = 0.0;
     if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
         const int e0 = pv.elem_ptr[p];
@@ -160,7 +181,8 @@ __global__ void __launch_bounds__(kPatch, kMinBlk) k_subs_patch(SurfView s, Patc
             int cnt = (int)(unsigned int)h;
             if (cnt > bk.cap) cnt = bk.cap;
             const unsigned short *lv = elem_lv + 3 * el;
-            const double n1[3] = {sx0[lv[0]], sx1[lv[0]], 0.0}, n2[3] = {sx0[lv[1]], sx1[lv[1]], 0.0}, n3[3] = {sx0[lv[2]], sx1[lv[2]], 0.0};
+            const double2 p1 = sxy[lv[0]], p2 = sxy[lv[1]], p3 = sxy[lv[2]];
+            const double n1[3] = {p1.x, p1.y, 0.0}, n2[3] = {p2.x, p2.y, 0.0}, n3[3] = {p3.x, p3.y, 0.0};
             int prev = -1;
             for (int m = 0; m < cnt; m++) {          // ascending cell-node order: deterministic whatever the insertion order was
                 int ni = 0x7fffffff;
@@ -178,21 +200,21 @@ __global__ void __launch_bounds__(kPatch, kMinBlk) k_subs_patch(SurfView s, Patc
             }
         }
     }
-    double Vh0 = V0 + (dt / 2.0) * A0v, Vh1 = V1 + (dt / 2.0) * A1v;
+    double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt / 2.0, A1v));   // UL:295
     if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {            // UL:298-341, Vbiax == 0
         if (Xi0 < -k.pin_limit || Xi0 > k.pin_limit) Vh0 = 0.0;
         if (Xi1 > k.pin_limit || Xi1 < -k.pin_limit) Vh1 = 0.0;
     }
-    node_update(Fx - rx, mm, k.damp, k.rho, dt, dt_real, Vh0, V0, A0v);                  // UL:471-503
-    node_update(Fy - ry, mm, k.damp, k.rho, dt, dt_real, Vh1, V1, A1v);
+    const double imm = 1.0 / mm;                                                          // one reciprocal for the five quotients
+    node_update_r(Fx - rx, mm, imm, k.damp, k.rho, dt, dt_real, Vh0, V0, A0v);            // UL:471-503
+    node_update_r(Fy - ry, mm, imm, k.damp, k.rho, dt, dt_real, Vh1, V1, A1v);
     s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
-    s.ea_out[i] = ea0 + q0 / mm; s.ea_out[np + i] = ea1 + q1 / mm; s.ea_out[3 * np + i] = ea3 + q3 / mm;
+    s.ea_out[i] = ea0 + q0 * imm; s.ea_out[np + i] = ea1 + q1 * imm; s.ea_out[3 * np + i] = ea3 + q3 * imm;
     if (DBG) {
         dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
         dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
     }
 }
-
 
 // ---- cell: the whole cell side of one UL step in ONE kernel ---------------------------------------------------------
 //   PREDICT: driverVelocities_Explicit + inline predictor (UL:103-124, main.cpp:224-242) for owned AND halo nodes, read
@@ -211,7 +233,7 @@ struct CellStepArgs {
 };
 
 template <bool PREDICT, bool DBG>
-__global__ void __launch_bounds__(kPatch, kMinBlk) k_cell_patch(SurfView s, PatchView pv, SurfView sub, GridView g, BucketView bk, BoundaryView b, Consts k,
+__global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, PatchView pv, SurfView sub, GridView g, BucketView bk, BoundaryView b, Consts k,
                                                        CellStepArgs a, const double *__restrict__ x_in, double *__restrict__ x_out, DebugView dbg) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ double shred[4 * 32];
@@ -256,7 +278,7 @@ __global__ void __launch_bounds__(kPatch, kMinBlk) k_cell_patch(SurfView s, Patc
         x_out[i] = xn0; x_out[np + i] = xn1;
     }
     // ---- halo gather (+ the same predictor: every patch that sees a node computes the same x_new)
-    for (int l = tid; l < nh; l += kPatch) {
+    for (int l = tid; l < nh; l += kThreads) {
         const int gi = halo_ids[l];
         const int d = kPatch + l;
         if (PREDICT) {
@@ -320,7 +342,7 @@ __global__ void __launch_bounds__(kPatch, kMinBlk) k_cell_patch(SurfView s, Patc
     __syncthreads();
     // ---- elements
     const double tk = t_act_of(k, a.t_tot) * k.kappa;
-    for (int el = tid; el < nel; el += kPatch) {
+    for (int el = tid; el < nel; el += kThreads) {
         const unsigned short *lv = elem_lv + 3 * el;
         const int n1 = lv[0], n2 = lv[1], n3 = lv[2];
         const double X[3][2] = {{sX0[n1], sX1[n1]}, {sX0[n2], sX1[n2]}, {sX0[n3], sX1[n3]}};
