@@ -12,7 +12,7 @@ reference's only parallel mode is independent processes, s_sim_031021_1.sub) -- 
 The state (1.1 GB) is ~9x the 126 MB L2, so successive steps stream from HBM: no explicit L2 flush is needed.
 
 The JSON line carries, beside the base contract:
-  roofline      the dominant kernel (k_subs_node): algorithmic bytes per launch (216 B/substrate node + 12 B/element,
+  roofline      the dominant kernel (k_subs_patch): algorithmic bytes per launch (216 B/substrate node + 12 B/element,
                 SURVEY.md 8d) / its CUDA-event duration measured live, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the oracle's C restatement ("port", grid point location) timed on this box's host on a bounded sample
   e2e           the same metric through the adapter-mode C-ABI call with host round trips every step
@@ -208,15 +208,17 @@ def main():
     t = sim.step_n(max(3, min(a.steps, 10)), a.dt, t)
     kms, kcnt = sim.kernel_ms()
     sim.set_profile(False)
-    names = ["k_predict_cell", "k_bond", "k_cell_node", "k_boundary_finish", "k_subs_node"]
-    per_kernel = {n: (kms[i] / kcnt[i] if kcnt[i] else 0.0) for i, n in enumerate(names)}
+    info = sim.path_info()
+    names = (["k_predict_cell", "k_bond", "k_cell_patch", "k_boundary_finish", "k_subs_patch"] if info["planar"]
+             else ["k_predict_cell", "k_bond", "k_cell_node", "k_boundary_finish", "k_subs_node"])
+    per_kernel = {n: kms[i] / kcnt[i] for i, n in enumerate(names) if kcnt[i]}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
-    dom = "k_subs_node"
+    dom = names[4]
     dom_bytes = 216 * nn_s + 12 * ne_s
     dom_ms = per_kernel[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
@@ -224,6 +226,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
                 "per_kernel_ms": per_kernel, "share_of_step": dom_ms / max(sum(per_kernel.values()), 1e-30),
+                "path": "planar patch kernels (TMA-staged)" if info["planar"] else "general 3-D node-centric kernels",
+                "patch_elements_per_element": {"cell": info["cell_patch_elem_ratio"], "substrate": info["subs_patch_elem_ratio"]},
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_max / a.steps * 1e-3) / 1e9,
                                "frac": step_bytes / (ms_max / a.steps * 1e-3) / 1e9 / peak}}
     # ncu dram__bytes of the same kernel, if a capture has been summarised under profiles/

@@ -1,0 +1,55 @@
+"""Ensembles of independent cells (BASELINE.json configs[4]): the path shards by whole cells, with no
+data-path communication -- the reference's own ensemble mechanism is a loop of independent processes
+(s_sim_031021_1.sub).  This module holds the host logic: the parameter sweep (integrin stiffness law x ligand density
+x RNG seed), its partition over ranks, and the max-over-ranks timing reduction used by bench.py.
+"""
+import itertools
+import numpy as np
+
+
+def sweep_grid(n_cells, laws=("k1", "k31", "kMD"), rho_min=1.0, rho_max=1000.0):
+    """n_cells (variant, rho_i_max, seed) triples: laws x log-spaced ligand densities (rho_i_max, UL:1231) x seeds.
+
+    Deterministic: cell id -> parameters, so every rank can rebuild the table without communication."""
+    n_rho = max(1, int(round((n_cells / len(laws)) ** 0.5)))
+    rhos = np.geomspace(rho_min, rho_max, n_rho)
+    base = list(itertools.product(laws, rhos))
+    cells = []
+    seed = 1
+    while len(cells) < n_cells:
+        for law, rho in base:
+            if len(cells) == n_cells:
+                break
+            cells.append({"id": len(cells), "variant": law, "rho_i_max": float(rho), "seed": seed})
+        seed += 1
+    return cells
+
+
+def partition(n_cells, world, rank):
+    """Contiguous, balanced shard of cell ids for `rank` (sizes differ by at most one)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    base, extra = divmod(n_cells, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return range(lo, hi)
+
+
+def max_over_ranks(seconds, dist=None, device=None):
+    """The time a multi-rank job took is the slowest rank's (bench contract); dist = torch.distributed or None."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(seconds)
+    import torch
+    t = torch.tensor([seconds], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_counts(count, dist=None, device=None):
+    """Units processed by all ranks (whole-job throughput numerator)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return int(count)
+    import torch
+    t = torch.tensor([count], dtype=torch.int64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
