@@ -39,7 +39,7 @@ UNIT = "element-steps/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cell-tris", type=int, default=1000000)
@@ -63,32 +63,44 @@ def algorithmic_bytes(nn_c, ne_c, nn_s, ne_s):
     return 304 * nn_c + 216 * nn_s + 12 * (ne_c + ne_s)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the GPU is under load (B200_PROFILING.md recipe): one persistent
+    `nvidia-smi -lms` process, started before the warm-up and stopped after the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index; self.stop_flag = False; self.rows = []
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
 
-    def run(self):
-        while not self.stop_flag:
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
             try:
-                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                              timeout=5).decode().strip()
-                self.rows.append([c.strip() for c in out.split(",")])
+                self.proc.wait(timeout=2)
             except Exception:
-                pass
-            time.sleep(0.1)
+                self.proc.kill()
 
     def summary(self):
-        if not self.rows:
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        busy = [r for r in rows if r[6].isdigit() and int(r[6]) > 0] or rows
+        sm = sorted(float(r[0]) for r in busy)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in busy)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows), "samples_under_load": len(busy)}
 
 
 def time_oracle_port(variant, xc, tc, xs, ts, dt, steps):
@@ -134,7 +146,7 @@ def run_reference_arm(a):
     # the unmodified reference locates anchors by brute force, O(Nn_cell * Ne_subs) twice per step (UL:1309, :2026): at the
     # bench workload that is ~8e12 predicate evaluations per step, so it is only runnable on a far smaller sample
     if use_ref:
-        kind, cell_tris, subs_side = "reference", max(600, a.cell_tris // 1024), max(24, a.subs_side // 32)
+        kind, cell_tris, subs_side = "reference", max(600, a.cell_tris // 256), max(24, a.subs_side // 16)
     else:
         kind, cell_tris, subs_side = "port", max(600, a.cell_tris // div), max(24, int(a.subs_side / math.sqrt(div)))
     steps = max(1, min(a.steps, 4))
@@ -185,8 +197,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
     t = sim.step_n(a.warmup, a.dt, t)
-    sampler = ClockSampler(local); sampler.start()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     l0 = sim.kernel_launches()
@@ -194,7 +206,7 @@ def main():
     t = sim.step_n(a.steps, a.dt, t)
     e1.record(stream)
     barrier()
-    sampler.stop_flag = True
+    sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = sim.kernel_launches() - l0
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -238,7 +250,7 @@ def main():
         pass
 
     # end to end: the adapter-mode call sequence with host round trips every step (pinned buffers)
-    e2e_steps = max(2, min(a.steps, 5))
+    e2e_steps = max(2, min(a.steps, 10))
     barrier()
     w0 = time.perf_counter()
     t, h2d, d2h = sim.step_n_roundtrip(e2e_steps, a.dt, t)
