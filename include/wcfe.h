@@ -48,7 +48,7 @@ extern "C" {
 #define WCFE_F_CB 5     /* 1                           m_cB   (cell only; never read by the UL path) */
 #define WCFE_F_CC 6     /* 1  bound integrin fraction  m_cC   (cell only) */
 #define WCFE_F_FAU 7    /* 3  integrin anchor vector   m_fau  (cell only) */
-#define WCFE_F_XPREV 8  /* 3  positions at the start of the last step (read-only) */
+#define WCFE_F_XPREV 8  /* 3  positions at the start of the step, X_t (cell; uploadable in adapter mode, after WCFE_F_X) */
 
 /* discrete state of the last step, one int per cell node (parity gates of SURVEY.md 8d) */
 #define WCFE_D_LOC_BOND 0         /* containing substrate triangle in updateFA (last match), -1 none; debug mode only */
@@ -131,6 +131,16 @@ int wcfe_predict(wcfe_ctx *c, int surface, double dt, double t_curr, double *xyz
 int wcfe_commit(wcfe_ctx *c, int surface, const double *xyz_final);
 /* updateFA + updateForces_Explicit(cell) + updateForces_Explicit(substrate) (main.cpp:354,:360,:361) */
 int wcfe_update(wcfe_ctx *c, double dt_req, double dt_real, double t_curr);
+/* the same in two halves, for the adapter: the reference hands the cell's V, A, ea to updateForces_Explicit(cell)
+ * (main.cpp:360) and the substrate's only to the substrate overload (main.cpp:361).  _cell = updateFA + cell overload
+ * (+ anchor buckets), _subs = substrate overload; _subs must follow the _cell of the same step. */
+int wcfe_update_cell(wcfe_ctx *c, double dt_req, double dt_real, double t_curr);
+int wcfe_update_subs(wcfe_ctx *c, double dt_req, double dt_real, double t_curr);
+/* driverVelocities_Explicit (surface == WCFE_CELL, UL:103-124) / driverVelocities_Biaxial (WCFE_SUBS, UL:275-345) as a pure
+ * function of host-owned arrays (AoS [3*nn]): V_hlf = V + dt/2 A, z = 0, substrate edge pins.  Computed on the device. */
+int wcfe_driver_velocities(wcfe_ctx *c, int surface, int nn, const double *X, const double *V, const double *A, double dt, double t_curr, double *Vh_out);
+/* adapter mode: x (WCFE_F_X) and X_prev (WCFE_F_XPREV) were uploaded by the host integrator instead of predict/commit */
+int wcfe_mark_positions_committed(wcfe_ctx *c);
 
 /* El-Topo-free fast path: n x (predict, commit(NULL), update) without leaving the device; time advances
  * as sim->m_curr_t += accum_dt does (main.cpp:405).  *t_io: in = time at the start, out = time after. */

@@ -87,16 +87,28 @@ struct ulref {
 
 extern "C" {
 
+#ifdef ULREF_ADAPTER_ONLY
+// Adapter build: the very same driver, linked against wholecellfe_b200/csrc/ul_adapter.cpp + libwcfe.so instead of the
+// reference's UL_growth_explicit.o -- i.e. the five symbols below resolve to the GPU drop-in.
+void wcfe_adapter_seed(unsigned int);
+void wcfe_adapter_reset(void);
+void ulref_srand(unsigned int seed) { wcfe_adapter_seed(seed); }
+int ulref_rand(void) { return 0; }
+#else
 // target of -Wl,--wrap=srand for every srand() call in this .so: a no-op
 void __wrap_srand(unsigned int) {}
 void __real_srand(unsigned int);
 
 void ulref_srand(unsigned int seed) { __real_srand(seed); }   // main.cpp:709 does srand(1)
 int ulref_rand(void) { return rand(); }
+#endif
 double ulref_default_kint(void) { return (double)(ULREF_KINT); }
 
 ulref *ulref_create(int nn_c, const double *xyz_c, int ne_c, const int *tri_c,
                     int nn_s, const double *xyz_s, int ne_s, const int *tri_s) {
+#ifdef ULREF_ADAPTER_ONLY
+    wcfe_adapter_reset();
+#endif
     ulref *h = new ulref;
     h->cell.init(nn_c, xyz_c, ne_c, tri_c);
     h->subs.init(nn_s, xyz_s, ne_s, tri_s);
@@ -174,6 +186,7 @@ void ulref_step(ulref *h, double dt, double t_curr, double kint, double subs_sca
     updateForces_Explicit(h->Xs_prev, s.x, s.V, h->Vh_s, s.A, s.ea, dt, dt, s.mesh, t_curr, c.fa_u, c.cC, c.x, c.mesh);   // :361
 }
 
+#ifndef ULREF_ADAPTER_ONLY
 // ---- fine-grained entry points for known-answer tests -------------------------------------------
 
 void ulref_eval_element(int mat, const double *X9, const double *x9, const double *ea18, const double *cA3, const double *cC3,
@@ -247,5 +260,6 @@ int ulref_force_field(ulref *h, int which, double dt, double t_curr, double kint
     for (int i = 0; i < nc * 3; i++) out[i] = F(i);
     return 0;
 }
+#endif   // ULREF_ADAPTER_ONLY
 
 }  // extern "C"

@@ -19,8 +19,24 @@ def ref_available(variant="k1"):
     return os.path.exists(os.path.join(HERE, "_ref", "libulref_%s.so" % variant))
 
 
-def _load(variant):
-    lib = C.CDLL(os.path.join(HERE, "_ref", "libulref_%s.so" % variant))
+def adapter_available(variant="k1"):
+    """oracle/_ref/libuladapter_*.so: this same driver linked against ul_adapter.cpp + libwcfe.so (the GPU drop-in)."""
+    return os.path.exists(os.path.join(HERE, "_ref", "libuladapter_%s.so" % variant))
+
+
+def _load(variant, kind="ref"):
+    lib = C.CDLL(os.path.join(HERE, "_ref", "lib%s_%s.so" % ("ulref" if kind == "ref" else "uladapter", variant)))
+    if kind != "ref":
+        lib.ulref_create.restype = C.c_void_p
+        lib.ulref_create.argtypes = [C.c_int, _dp, C.c_int, _ip, C.c_int, _dp, C.c_int, _ip]
+        lib.ulref_destroy.argtypes = [C.c_void_p]
+        lib.ulref_srand.argtypes = [C.c_uint]
+        lib.ulref_default_kint.restype = C.c_double
+        lib.ulref_get.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+        lib.ulref_set.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+        lib.ulref_boundary_flags.argtypes = [C.c_void_p, C.c_int, _ip]
+        lib.ulref_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+        return lib
     lib.ulref_create.restype = C.c_void_p
     lib.ulref_create.argtypes = [C.c_int, _dp, C.c_int, _ip, C.c_int, _dp, C.c_int, _ip]
     lib.ulref_destroy.argtypes = [C.c_void_p]
@@ -44,9 +60,9 @@ def _d(a):
 class RefSim:
     """The reference UL step (El Topo off) on one cell + one substrate mesh."""
 
-    def __init__(self, variant, xyz_c, tri_c, xyz_s, tri_s):
+    def __init__(self, variant, xyz_c, tri_c, xyz_s, tri_s, kind="ref"):
         self.variant = variant
-        self.lib = _load(variant)
+        self.lib = _load(variant, kind)
         xyz_c = np.ascontiguousarray(xyz_c, dtype=np.float64); xyz_s = np.ascontiguousarray(xyz_s, dtype=np.float64)
         tri_c = np.ascontiguousarray(tri_c, dtype=np.int32); tri_s = np.ascontiguousarray(tri_s, dtype=np.int32)
         self.nn = (len(xyz_c), len(xyz_s)); self.ne = (len(tri_c), len(tri_s))

@@ -20,7 +20,8 @@ RNG_GLIBC_REPLAY, RNG_PHILOX = 0, 1
 SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_params", "wcfe_set_stream", "wcfe_last_error",
            "wcfe_upload_mesh", "wcfe_upload_state", "wcfe_download_state", "wcfe_mesh_sizes", "wcfe_set_rng", "wcfe_set_debug",
            "wcfe_rng_skip", "wcfe_set_profile", "wcfe_get_kernel_ms", "wcfe_set_force_general", "wcfe_get_path_info",
-           "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_step_n", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
+           "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities",
+           "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
            "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_sync"]
 
 
@@ -71,6 +72,10 @@ def load():
     L.wcfe_predict.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp]
     L.wcfe_commit.argtypes = [vp, C.c_int, _dp]
     L.wcfe_update.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    L.wcfe_update_cell.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    L.wcfe_update_subs.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    L.wcfe_driver_velocities.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
+    L.wcfe_mark_positions_committed.argtypes = [vp]
     L.wcfe_step_n.argtypes = [vp, C.c_int, C.c_double, _dp]
     L.wcfe_step_n_roundtrip.argtypes = [vp, C.c_int, C.c_double, _dp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.wcfe_get_diagnostics.argtypes = [vp, _dp]

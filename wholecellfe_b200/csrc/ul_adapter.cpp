@@ -1,0 +1,163 @@
+// ul_adapter.cpp -- the reference's five UL entry points on top of the C ABI (include/wcfe.h).
+//
+// Compile this translation unit against the REFERENCE's own headers (common/vec.h, eltopo3d/nondestructivetrimesh.h,
+// cellBP/Eigen) and link it, together with libwcfe.so, in place of cellBP/UL_growth_explicit.o: the unmodified
+// cellBP/main.cpp then runs its explicit updated-Lagrangian step on the GPU.  The prototypes below are
+// the ones main.cpp re-declares by hand (wholeCellFE_k1/cellBP/main.cpp:72-84) and calls from advance_sim()
+// (main.cpp:224, :293, :329, :354, :360, :361).
+//
+// Ownership follows the reference: the caller (SurfTrack) owns every array; V_t, A_t, ea_t, c_C, c_A, fa_u are mutated in
+// place; V_hlf is the caller's temporary.  Because El Topo may remesh between steps, the host-owned nodal state is
+// re-uploaded every step and connectivity whenever it changed.  All physics runs on the device; this file only moves data.
+//
+//   -DWCFE_VARIANT=WCFE_K1 | WCFE_K31 | WCFE_KMD   selects which reference tree is being replaced (default WCFE_K1).
+#include "wcfe.h"
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <Eigen/Dense>
+#include "vec.h"
+#include "nondestructivetrimesh.h"
+
+#ifndef WCFE_VARIANT
+#define WCFE_VARIANT WCFE_K1
+#endif
+
+namespace {
+
+struct MeshSig { size_t nv = 0, nt = 0; unsigned long long hash = 0; };
+
+struct Adapter {
+    wcfe_ctx *ctx = nullptr;
+    MeshSig sig[2];
+    std::vector<double> buf;          // AoS scratch
+    double dt_real = 0;
+    bool cell_pending = false;        // updateFA seen, device step not yet run
+} g;
+
+void die(const char *where, int rc) {
+    std::fprintf(stderr, "wcfe adapter: %s failed (%d): %s\n", where, rc, wcfe_last_error(g.ctx));
+    std::abort();                     // the reference is fail-stop as well (assert / exit)
+}
+#define OK(call) do { int rc_ = (call); if (rc_ != WCFE_OK) die(#call, rc_); } while (0)
+
+void ensure_context() {
+    if (g.ctx) return;
+    wcfe_params p;
+    OK(wcfe_default_params(&p, WCFE_VARIANT));
+    int dev = 0;
+    if (const char *e = std::getenv("WCFE_DEVICE")) dev = std::atoi(e);
+    int rc = wcfe_create(&g.ctx, dev, &p);
+    if (rc != WCFE_OK) { std::fprintf(stderr, "wcfe adapter: wcfe_create failed (%d): %s\n", rc, wcfe_last_error(nullptr)); std::abort(); }
+    unsigned int seed = 1;            // main.cpp:709 srand(1); the per-step srand(time(NULL)) of UL:1460 is dropped
+    if (const char *e = std::getenv("WCFE_SEED")) seed = (unsigned int)std::strtoul(e, nullptr, 10);
+    OK(wcfe_set_rng(g.ctx, WCFE_RNG_GLIBC_REPLAY, seed));
+}
+
+const double *flat(const std::vector<Vec3d> &v) { return v.empty() ? nullptr : &v[0][0]; }   // Vec3d == 3 contiguous doubles
+double *flat(std::vector<Vec3d> &v) { return v.empty() ? nullptr : &v[0][0]; }
+
+// (re)upload connectivity when the mesh changed (remeshing: SurfTrack::improve_mesh / defrag_mesh)
+void sync_mesh(int surface, const std::vector<Vec3d> &x, const NonDestructiveTriMesh &mesh) {
+    MeshSig s;
+    s.nv = x.size(); s.nt = mesh.num_triangles();
+    unsigned long long h = 1469598103934665603ull;
+    for (size_t t = 0; t < s.nt; t++) {
+        const Vec3st &tri = mesh.get_triangle(t);
+        for (int j = 0; j < 3; j++) { h ^= (unsigned long long)tri[j]; h *= 1099511628211ull; }
+    }
+    s.hash = h;
+    MeshSig &old = g.sig[surface];
+    if (old.nv == s.nv && old.nt == s.nt && old.hash == s.hash) return;
+    std::vector<int> tris(3 * s.nt);
+    for (size_t t = 0; t < s.nt; t++) { const Vec3st &tri = mesh.get_triangle(t); for (int j = 0; j < 3; j++) tris[3 * t + j] = (int)tri[j]; }
+    OK(wcfe_upload_mesh(g.ctx, surface, (int)s.nv, flat(x), (int)s.nt, tris.data()));
+    old = s;
+}
+
+void put_ea(int surface, const std::vector<Eigen::VectorXd> &ea) {
+    g.buf.resize(6 * ea.size());
+    for (size_t i = 0; i < ea.size(); i++) for (int q = 0; q < 6; q++) g.buf[6 * i + q] = ea[i](q);
+    OK(wcfe_upload_state(g.ctx, surface, WCFE_F_EA, g.buf.data()));
+}
+void get_ea(int surface, std::vector<Eigen::VectorXd> &ea) {
+    g.buf.resize(6 * ea.size());
+    OK(wcfe_download_state(g.ctx, surface, WCFE_F_EA, g.buf.data()));
+    for (size_t i = 0; i < ea.size(); i++) for (int q = 0; q < 6; q++) ea[i](q) = g.buf[6 * i + q];
+}
+
+}   // namespace
+
+// main.cpp:224, :329
+void driverVelocities_Explicit(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt) {
+    ensure_context();
+    OK(wcfe_driver_velocities(g.ctx, WCFE_CELL, (int)X_t.size(), flat(X_t), flat(V_t), flat(A_t), dt, 0.0, flat(V_t_hlf)));
+}
+
+// main.cpp:293
+void driverVelocities_Biaxial(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot) {
+    ensure_context();
+    OK(wcfe_driver_velocities(g.ctx, WCFE_SUBS, (int)X_t.size(), flat(X_t), flat(V_t), flat(A_t), dt, t_tot, flat(V_t_hlf)));
+}
+
+// main.cpp:354.  The device step needs V, A, ea too, which the reference only hands to updateForces_Explicit; main.cpp does
+// not look at c_C / fa_u between the two calls (it passes the same vectors on), so positions and bond state are uploaded
+// here and the step itself runs inside updateForces_Explicit(cell), which then writes c_C, c_A, fa_u back as well.
+void updateFA(std::vector<double> &c_A, std::vector<double> &c_C, std::vector<Vec3d> &fa_u, double dt_real,
+              const std::vector<Vec3d> &X_t_cell, const std::vector<Vec3d> &x_t_cell, const NonDestructiveTriMesh &mesh_cell,
+              const std::vector<Vec3d> &X_t_subs, const std::vector<Vec3d> &x_t_subs, const NonDestructiveTriMesh &mesh_subs, double kint) {
+    (void)kint; (void)x_t_subs;       // kint is fixed by the variant (main.cpp:350-354); the substrate is frozen (main.cpp:299)
+    ensure_context();
+    sync_mesh(WCFE_SUBS, X_t_subs, mesh_subs);
+    sync_mesh(WCFE_CELL, X_t_cell, mesh_cell);
+    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_X, flat(x_t_cell)));
+    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_XPREV, flat(X_t_cell)));
+    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_CA, c_A.data()));
+    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_CC, c_C.data()));
+    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_FAU, flat(fa_u)));
+    OK(wcfe_mark_positions_committed(g.ctx));
+    g.dt_real = dt_real;
+    g.cell_pending = true;
+}
+
+// main.cpp:360
+void updateForces_Explicit(const std::vector<Vec3d> &X_t, const std::vector<Vec3d> &x_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf,
+                           std::vector<Vec3d> &A_t, std::vector<Eigen::VectorXd> &ea_t, std::vector<double> &c_A, std::vector<double> &c_B,
+                           std::vector<double> &c_C, std::vector<Vec3d> &fa_u, double dt, double dt_real, const NonDestructiveTriMesh &mesh, double t_tot) {
+    (void)X_t; (void)x_t; (void)V_t_hlf; (void)c_B; (void)mesh;
+    if (!g.cell_pending) { std::fprintf(stderr, "wcfe adapter: updateForces_Explicit(cell) without a preceding updateFA\n"); std::abort(); }
+    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_V, flat(V_t)));
+    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_A, flat(A_t)));
+    put_ea(WCFE_CELL, ea_t);
+    OK(wcfe_update_cell(g.ctx, dt, dt_real, t_tot));
+    OK(wcfe_download_state(g.ctx, WCFE_CELL, WCFE_F_V, flat(V_t)));
+    OK(wcfe_download_state(g.ctx, WCFE_CELL, WCFE_F_A, flat(A_t)));
+    get_ea(WCFE_CELL, ea_t);
+    OK(wcfe_download_state(g.ctx, WCFE_CELL, WCFE_F_CA, c_A.data()));
+    OK(wcfe_download_state(g.ctx, WCFE_CELL, WCFE_F_CC, c_C.data()));
+    OK(wcfe_download_state(g.ctx, WCFE_CELL, WCFE_F_FAU, flat(fa_u)));
+    g.cell_pending = false;
+}
+
+// main.cpp:361
+void updateForces_Explicit(const std::vector<Vec3d> &X_t, const std::vector<Vec3d> &x_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf,
+                           std::vector<Vec3d> &A_t, std::vector<Eigen::VectorXd> &ea_t, double dt, double dt_real, const NonDestructiveTriMesh &mesh,
+                           double t_tot, std::vector<Vec3d> &fa_u, const std::vector<double> &c_C, const std::vector<Vec3d> &x_cell,
+                           const NonDestructiveTriMesh &mesh_cell) {
+    (void)X_t; (void)x_t; (void)V_t_hlf; (void)mesh; (void)fa_u; (void)c_C; (void)x_cell; (void)mesh_cell;   // already on the device
+    OK(wcfe_upload_state(g.ctx, WCFE_SUBS, WCFE_F_V, flat(V_t)));
+    OK(wcfe_upload_state(g.ctx, WCFE_SUBS, WCFE_F_A, flat(A_t)));
+    put_ea(WCFE_SUBS, ea_t);
+    OK(wcfe_update_subs(g.ctx, dt, dt_real, t_tot));
+    OK(wcfe_download_state(g.ctx, WCFE_SUBS, WCFE_F_V, flat(V_t)));
+    OK(wcfe_download_state(g.ctx, WCFE_SUBS, WCFE_F_A, flat(A_t)));
+    get_ea(WCFE_SUBS, ea_t);
+}
+
+// test hooks (used by the adapter parity test; harmless in production)
+extern "C" void wcfe_adapter_reset(void) {
+    if (g.ctx) wcfe_destroy(g.ctx);
+    g = Adapter();
+}
+extern "C" void wcfe_adapter_seed(unsigned int seed) { ensure_context(); OK(wcfe_set_rng(g.ctx, WCFE_RNG_GLIBC_REPLAY, seed)); }

@@ -104,6 +104,7 @@ struct wcfe_ctx {
     DevBuf<int> d_flags, d_loc_bond, d_loc_cnt, d_loc_first, d_ap_fire, d_err;
     DevBuf<double> d_partials, d_diag;
     DevBuf<unsigned int> d_tape;
+    DevBuf<double> d_drv;                 // scratch of wcfe_driver_velocities
     size_t tape_cap = 0;
     unsigned int *h_tape = nullptr;       // pinned
     double *h_stage = nullptr; size_t stage_bytes = 0;   // pinned staging for up/downloads
@@ -441,11 +442,11 @@ void harvest_profile(wcfe_ctx *c) {
 enum { K_PREDICT = 0, K_BOND = 1, K_CELL = 2, K_FINISH = 3, K_SUBS = 4 };
 
 // ---- one UL update on the device: k_bond, k_cell_node, k_boundary_finish, k_subs_node ---------------------------
-int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const unsigned int *tape_dev, bool fuse_predict) {
+int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const unsigned int *tape_dev, bool fuse_predict, int which = 3) {
     Surface &cs = c->s[WCFE_CELL], &ss = c->s[WCFE_SUBS];
     SurfView cv = view(cs), sv = view(ss);
     sv.X = sv.x;
-    c->epoch++;
+    if (which & 1) c->epoch++;            // the cell half fills the triangle buckets of this epoch, the substrate half reads them
     BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch};
     const int gc = (cs.nn + kBlock - 1) / kBlock, gs = (ss.nn + kBlock - 1) / kBlock;
     // Pr < APrate*dt*exp(-APrate*dt) (UL:1531): the threshold is evaluated on the host with the host libm, as the reference does
@@ -453,6 +454,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     BoundaryView bv = bview(cs);
     const bool planar = use_planar(c);
     int npart = gc;
+    if (!(which & 1)) goto subs_half;
     if (planar) {
         // fused cell kernel: (predict) + updateFA + anchor location + forces + update, one CTA per patch
         ProfScope ps(c, K_CELL);
@@ -493,6 +495,11 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     { ProfScope ps(c, K_FINISH);
     if (c->debug) k_boundary_finish<true><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, dt, dt_real, c->d_diag.p, dview(cs));
     else k_boundary_finish<false><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, dt, dt_real, c->d_diag.p, DebugView{}); }
+    c->launches += 1;
+    cs.ea_cur ^= 1;
+subs_half:
+    if (!(which & 2)) { CK(cudaGetLastError()); return WCFE_OK; }
+    cv = view(cs);
     if (planar) {
         ProfScope ps(c, K_SUBS);
         const size_t smem = patch_smem_bytes(5, 8, ss.max_halo, ss.max_elem, ss.stride);
@@ -504,8 +511,8 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         if (c->debug) k_subs_node<true><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
         else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
     }
-    c->launches += 2;
-    cs.ea_cur ^= 1; ss.ea_cur ^= 1;
+    c->launches += 1;
+    ss.ea_cur ^= 1;
     c->step++;
     CK(cudaGetLastError());
     return WCFE_OK;
@@ -614,7 +621,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();
-    c->d_partials.release(); c->d_diag.release(); c->d_tape.release();
+    c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
@@ -763,7 +770,7 @@ int wcfe_mesh_sizes(wcfe_ctx *c, int surface, int *nn, int *ne) {
 
 int wcfe_upload_state(wcfe_ctx *c, int surface, int field, const double *host) {
     if (!c || surface < 0 || surface > 1 || !host) return WCFE_ERR_ARG;
-    if (field == WCFE_F_XPREV) return fail(c, WCFE_ERR_ARG, "X_prev is read-only");
+    if (field == WCFE_F_XPREV && surface != WCFE_CELL) return fail(c, WCFE_ERR_ARG, "X_prev of the frozen substrate is its position");
     Surface &s = c->s[surface];
     double *dev = field_dev(c, surface, field);
     const int w = width_of(field);
@@ -772,7 +779,7 @@ int wcfe_upload_state(wcfe_ctx *c, int surface, int field, const double *host) {
     int rc = put_field(c, dev, host, s.nn, s.np, w);
     if (rc) return rc;
     // the planar fast path needs every out-of-plane word to be exactly zero; once that is violated it stays off
-    if (field == WCFE_F_X || field == WCFE_F_V || field == WCFE_F_A || field == WCFE_F_FAU) { for (int i = 0; i < s.nn && s.planar; i++) if (host[3 * (size_t)i + 2] != 0.0) s.planar = false; }
+    if (field == WCFE_F_X || field == WCFE_F_XPREV || field == WCFE_F_V || field == WCFE_F_A || field == WCFE_F_FAU) { for (int i = 0; i < s.nn && s.planar; i++) if (host[3 * (size_t)i + 2] != 0.0) s.planar = false; }
     if (field == WCFE_F_EA) { for (int i = 0; i < s.nn && s.planar; i++) if (host[6 * (size_t)i + 2] != 0.0 || host[6 * (size_t)i + 4] != 0.0 || host[6 * (size_t)i + 5] != 0.0) s.planar = false; }
     if (field == WCFE_F_EA && s.planar) CK(cudaMemsetAsync(s.ea[s.ea_cur ^ 1].p, 0, sizeof(double) * 6 * s.np, c->stream));
     if (field == WCFE_F_X) {
@@ -872,16 +879,48 @@ int wcfe_commit(wcfe_ctx *c, int surface, const double *xyz_final) {
     return WCFE_OK;
 }
 
-int wcfe_update(wcfe_ctx *c, double dt_req, double dt_real, double t_curr) {
+static int update_impl(wcfe_ctx *c, double dt_req, double dt_real, double t_curr, int which) {
     int rc = ready(c);
     if (rc) return rc;
-    if (!c->have_predict[WCFE_CELL]) return fail(c, WCFE_ERR_ARG, "update without predict(cell)");
     CK(cudaSetDevice(c->device));
-    if ((rc = stage_tape(c, 1))) return rc;
-    if ((rc = launch_update(c, dt_req, dt_real, t_curr, c->d_tape.p, false))) return rc;
-    c->have_predict[0] = c->have_predict[1] = false;
-    c->t_last = t_curr + dt_real;
+    if (which & 1) {
+        if (!c->have_predict[WCFE_CELL]) return fail(c, WCFE_ERR_ARG, "update without predict(cell) (or upload of x and X_prev)");
+        if ((rc = stage_tape(c, 1))) return rc;
+    }
+    if ((rc = launch_update(c, dt_req, dt_real, t_curr, c->d_tape.p, false, which))) return rc;
+    if (which & 1) c->have_predict[0] = false;
+    if (which & 2) { c->have_predict[1] = false; c->t_last = t_curr + dt_real; }
     return check_device_errors(c);
+}
+int wcfe_update(wcfe_ctx *c, double dt_req, double dt_real, double t_curr) { return update_impl(c, dt_req, dt_real, t_curr, 3); }
+int wcfe_update_cell(wcfe_ctx *c, double dt_req, double dt_real, double t_curr) { return update_impl(c, dt_req, dt_real, t_curr, 1); }
+int wcfe_update_subs(wcfe_ctx *c, double dt_req, double dt_real, double t_curr) { return update_impl(c, dt_req, dt_real, t_curr, 2); }
+
+int wcfe_driver_velocities(wcfe_ctx *c, int surface, int nn, const double *X, const double *V, const double *A, double dt, double t_curr, double *Vh_out) {
+    if (!c || surface < 0 || surface > 1 || nn <= 0 || !X || !V || !A || !Vh_out) return fail(c, WCFE_ERR_ARG, "driver_velocities: bad arguments");
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = sizeof(double) * 3 * (size_t)nn;
+    int rc = ensure_stage(c, 4 * bytes);
+    if (rc) return rc;
+    if (c->d_drv.n < 12 * (size_t)nn) CK(c->d_drv.alloc(12 * (size_t)nn));
+    char *h = (char *)c->h_stage;
+    memcpy(h, X, bytes); memcpy(h + bytes, V, bytes); memcpy(h + 2 * bytes, A, bytes);
+    CK(cudaMemcpyAsync(c->d_drv.p, h, 3 * bytes, cudaMemcpyHostToDevice, c->stream));
+    double *d = c->d_drv.p;
+    k_driver<<<(nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(surface, nn, d, d + 3 * (size_t)nn, d + 6 * (size_t)nn, d + 9 * (size_t)nn, c->k, dt, t_curr);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h + 3 * bytes, d + 9 * (size_t)nn, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(Vh_out, h + 3 * bytes, bytes);
+    return WCFE_OK;
+}
+
+/* adapter mode: the host integrator owns the positions; declare that x and X_prev of the cell have been uploaded */
+int wcfe_mark_positions_committed(wcfe_ctx *c) {
+    if (!c) return WCFE_ERR_ARG;
+    c->have_predict[0] = c->have_predict[1] = true;
+    return WCFE_OK;
 }
 
 int wcfe_step_n(wcfe_ctx *c, int n, double dt, double *t_io) {

@@ -74,6 +74,23 @@ __global__ void __launch_bounds__(kBlock) k_predict_cell(int nn, int np, double 
     }
 }
 
+// ---- stand-alone drivers for the adapter: host-owned X, V, A in, V_hlf out (UL:103-124 cell, UL:275-345 substrate) -----------
+__global__ void __launch_bounds__(kBlock) k_driver(int surface, int nn, const double *__restrict__ X, const double *__restrict__ V,
+                                                   const double *__restrict__ A, double *__restrict__ Vh, Consts k, double dt, double t_tot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn) return;
+    double v[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) v[c] = WCFE_ADD(V[3 * i + c], WCFE_MUL(dt / 2.0, A[3 * i + c]));
+    v[2] = 0.0;
+    if (surface == 1 && (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f)) {
+        if (X[3 * i] < -k.pin_limit || X[3 * i] > k.pin_limit) v[0] = 0.0;
+        if (X[3 * i + 1] > k.pin_limit || X[3 * i + 1] < -k.pin_limit) v[1] = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) Vh[3 * i + c] = v[c];
+}
+
 // ---- point location of one anchor in the substrate -------------------------------------------------------
 // visits candidates in ascending triangle index; calls f(tri, A[3], A_tri) for every containing triangle
 template <class F>
