@@ -260,6 +260,29 @@ int ulref_force_field(ulref *h, int which, double dt, double t_curr, double kint
     for (int i = 0; i < nc * 3; i++) out[i] = F(i);
     return 0;
 }
+
+// ---- the reference's own .vtk writers and mesh reader (cellBP/iomesh.cpp), for byte-level golden files ------------
+}  // extern "C"
+#include <iomesh.h>
+extern "C" {
+int ulref_write_vtk_cell(ulref *h, double time, const char *path) {
+    Surface &c = h->cell;
+#if ULREF_KINT < 0
+    write_vtk(c.mesh, c.x, c.cA, c.cB, c.cC, c.fa_u, c.ea, time, path, (double)(ULREF_KINT));   // kMD main.cpp:448-450
+#else
+    write_vtk(c.mesh, c.x, c.cA, c.cB, c.cC, c.fa_u, c.ea, time, path);                         // main.cpp:446-447
+#endif
+    return 0;
+}
+// fa_source: the reference hands the substrate writer the CELL's fa_u at frame 0 (main.cpp:722) -- pass 0 for that; 1 writes
+// a zero vector of the substrate's size (what g_surf_subs->get_fa_u() would hold if it were sized correctly, quirk q6)
+int ulref_write_vtk_subs(ulref *h, double time, const char *path, int fa_source) {
+    Surface &s = h->subs;
+    std::vector<Vec3d> fa = fa_source == 0 ? h->cell.fa_u : std::vector<Vec3d>(s.x.size(), Vec3d(0, 0, 0));
+    if (fa.size() < s.x.size()) fa.resize(s.x.size(), Vec3d(0, 0, 0));
+    write_vtk(s.mesh, s.x, s.ea, fa, time, path);                                               // main.cpp:451
+    return 0;
+}
 #endif   // ULREF_ADAPTER_ONLY
 
 }  // extern "C"

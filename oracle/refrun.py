@@ -50,6 +50,8 @@ def _load(variant, kind="ref"):
     lib.ulref_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.ulref_eval_element.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, C.c_double, _dp, _dp, _dp]
     lib.ulref_force_field.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp, _dp]
+    lib.ulref_write_vtk_cell.argtypes = [C.c_void_p, C.c_double, C.c_char_p]
+    lib.ulref_write_vtk_subs.argtypes = [C.c_void_p, C.c_double, C.c_char_p, C.c_int]
     return lib
 
 
@@ -90,6 +92,13 @@ class RefSim:
 
     def step(self, dt, t_curr, subs_scale=0.0):
         self.lib.ulref_step(self.h, dt, t_curr, self.kint, subs_scale)
+
+    def write_vtk(self, surface, time, path, fa_source=0):
+        """the reference's own writer (cellBP/iomesh.cpp)"""
+        if surface == 0:
+            self.lib.ulref_write_vtk_cell(self.h, time, path.encode())
+        else:
+            self.lib.ulref_write_vtk_subs(self.h, time, path.encode(), fa_source)
 
     def boundary_flags(self, surface):
         out = np.empty(self.nn[surface], dtype=np.int32)

@@ -93,6 +93,25 @@ def main():
         Re[i], Rea[i], MMe[i] = ref_eval_element("k1", int(mat[i]), X[i].ravel(), x[i].ravel(), ea[i].ravel(),
                                                  np.full(3, 100.0), np.zeros(3), DT, cen[i], float(time[i]))
     np.savez_compressed(os.path.join(HERE, "elements.npz"), X=X, x=x, ea=ea, mat=mat, time=time, centroid=cen, Re=Re, Re_ea=Rea, MMe=MMe)
+    # .vtk frames written by the reference's own writers (cellBP/iomesh.cpp) from the state at the end of frame 0 (8 steps)
+    import tempfile
+    vt = {}
+    for var in ("k1", "kMD"):
+        sim = RefSim(var, xc, tc, xs, ts)
+        sim.srand(1)
+        t = 0.0
+        for _ in range(8):
+            sim.step(DT, t)
+            t += DT
+        with tempfile.TemporaryDirectory() as d:
+            sim.write_vtk(0, t, os.path.join(d, "c.vtk")); sim.write_vtk(1, t, os.path.join(d, "s.vtk"), 0)
+            vt[var + "_cell_vtk"] = np.frombuffer(open(os.path.join(d, "c.vtk"), "rb").read(), dtype=np.uint8)
+            vt[var + "_subs_vtk"] = np.frombuffer(open(os.path.join(d, "s.vtk"), "rb").read(), dtype=np.uint8)
+        vt[var + "_t"] = t
+        for f in ("x", "cA", "cC", "fa_u", "ea"):
+            vt[var + "_c_" + f] = sim.get(0, f)
+        vt[var + "_s_ea"] = sim.get(1, "ea")
+    np.savez_compressed(os.path.join(HERE, "vtk_frames.npz"), **vt)
     print("golden fixtures written to", HERE)
 
 
