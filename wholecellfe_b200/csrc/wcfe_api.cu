@@ -112,6 +112,9 @@ struct wcfe_ctx {
     unsigned int step = 0;
     int debug = 0;
     int force_general = 0;                // test hook: run the general 3-D kernels even on planar states
+    int use_pipe = 0;                     // substrate: persistent software-pipelined kernel (k_subs_pipe) instead of k_subs_patch;
+                                          // measured slower on B200 (0.43 vs 0.355 ms: its 73 KB of stages leave 12 consumer warps per SM)
+    int num_sms = 148;
     int profile = 0;                      // per-kernel CUDA-event timing (bench roofline leg)
     std::vector<cudaEvent_t> pev;         // event pool, pairs
     std::vector<int> pev_kernel;          // kernel id of each pair in flight
@@ -390,6 +393,7 @@ constexpr int kPatchSmemMax = 224 * 1024;
 bool use_planar(wcfe_ctx *c) {
     if (!(c->s[0].planar && c->s[1].planar && c->prm.thetag_dot == 0.0 && !c->force_general)) return false;
     // a mesh numbered without locality can blow the per-patch tables past shared memory: use the general kernels then
+    if (c->use_pipe && pipe_layout(c->s[1].stride, c->s[1].max_halo, c->s[1].max_elem).total > kPatchSmemMax) return false;
     return patch_smem_bytes(7, 9, c->s[0].max_halo, c->s[0].max_elem, c->s[0].stride) <= (size_t)kPatchSmemMax &&
            patch_smem_bytes(5, 8, c->s[1].max_halo, c->s[1].max_elem, c->s[1].stride) <= (size_t)kPatchSmemMax;
 }
@@ -493,14 +497,23 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         c->launches += 2;
     }
     { ProfScope ps(c, K_FINISH);
-    if (c->debug) k_boundary_finish<true><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, dt, dt_real, c->d_diag.p, dview(cs));
-    else k_boundary_finish<false><<<1, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, dt, dt_real, c->d_diag.p, DebugView{}); }
+    const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few blocks: the kernel is latency-, not throughput-bound
+    if (c->debug) k_boundary_finish<true><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, dt, dt_real, c->d_diag.p, dview(cs));
+    else k_boundary_finish<false><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, dt, dt_real, c->d_diag.p, DebugView{}); }
     c->launches += 1;
     cs.ea_cur ^= 1;
 subs_half:
     if (!(which & 2)) { CK(cudaGetLastError()); return WCFE_OK; }
     cv = view(cs);
-    if (planar) {
+    if (planar && c->use_pipe) {
+        // persistent, software-pipelined substrate kernel: grid = SMs x 3 resident CTAs
+        ProfScope ps(c, K_SUBS);
+        const PipeLayout L = pipe_layout(ss.stride, ss.max_halo, ss.max_elem);
+        PatchView pvs = pview(ss);
+        const int grid = std::min(ss.npatch, c->num_sms * 3);
+        if (c->debug) k_subs_pipe<true><<<grid, kPipeThreads, L.total, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
+        else k_subs_pipe<false><<<grid, kPipeThreads, L.total, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+    } else if (planar) {
         ProfScope ps(c, K_SUBS);
         const size_t smem = patch_smem_bytes(5, 8, ss.max_halo, ss.max_elem, ss.stride);
         PatchView pvs = pview(ss);
@@ -592,7 +605,10 @@ int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p) {
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
     c->rng.seed(1);
     {
-        const void *pk[] = {(const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+        if (const char *e = std::getenv("WCFE_SUBS_PIPE")) c->use_pipe = std::atoi(e);
+        const void *pk[] = {(const void *)k_subs_pipe<false>, (const void *)k_subs_pipe<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
                             (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>};
         for (const void *f : pk) {
             // 227 KB is the per-CTA limit including the kernels' small static arrays

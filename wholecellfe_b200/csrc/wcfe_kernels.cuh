@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(kBlock) k_cell_node(SurfView s, BoundaryView b
 }
 
 // ---- total area / centroid (UL:1641-1667) + area-constraint force and update of the boundary vertices (UL:1670-1763) --
-// single block; partial sums are combined in a fixed order, so the result is bit-reproducible run to run
+// every block reduces the partial sums itself, in the same fixed order (bit-reproducible run to run and identical across
+// blocks), then finishes its share of the boundary vertices; block 0 publishes the diagnostics
 template <bool DBG>
 __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k, int npart, const double *__restrict__ partials,
                                                           double dt, double dt_real, double *__restrict__ diag, DebugView dbg) {
@@ -318,12 +319,12 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
     block_reduce4(v, sh);
     if (threadIdx.x == 0) {
         tot[0] = v[0]; tot[1] = v[1] / v[0]; tot[2] = v[2] / v[0]; tot[3] = v[3] / v[0];
-        for (int q = 0; q < 4; q++) diag[q] = tot[q];
+        if (blockIdx.x == 0) for (int q = 0; q < 4; q++) diag[q] = tot[q];
     }
     __syncthreads();
     const double area_tot = tot[0];
     const int np = s.np;
-    for (int bi = threadIdx.x; bi < b.nb; bi += blockDim.x) {
+    for (int bi = blockIdx.x * blockDim.x + threadIdx.x; bi < b.nb; bi += gridDim.x * blockDim.x) {
         const int i = b.node[bi];
         const double *o = b.buf + (size_t)16 * bi;
         const double mm = o[6], tl = o[7];

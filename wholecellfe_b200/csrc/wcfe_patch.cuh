@@ -74,6 +74,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int phase) {
     unsigned int ok;
     do {
@@ -213,6 +217,181 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
     if (DBG) {
         dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
         dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
+    }
+}
+
+// ---- substrate, software-pipelined persistent version ---------------------------------------------------------------------------
+// Same arithmetic as k_subs_patch, different choreography: a persistent CTA (grid = SMs x resident CTAs) walks over patches with
+// TWO shared-memory stages.  Warp 4 is the producer: for patch k+1 it issues the TMA bulk copies (descriptor + the owned nodes'
+// x, e, V, A), waits for them, packs the node table and gathers the halo nodes -- while warps 0-3 (consumers, one thread per
+// owned node) run the element and node phases of patch k entirely out of shared memory.  full/empty mbarriers hand the stages
+// back and forth; the consumers never wait on global memory except for their coalesced stores.
+constexpr int kPipeConsumers = kPatch;                  // 4 warps at kPatch = 128
+constexpr int kPipeThreads = kPatch + 32;
+struct PipeLayout { int blob, soa, table, stage, rec, total; };
+__host__ __device__ inline PipeLayout pipe_layout(int stride, int max_halo, int max_elem) {
+    PipeLayout L;
+    L.blob = 0;
+    L.soa = (stride + 127) / 128 * 128;                                  // [9][kPatch] doubles: x0 x1 e0 e1 e3 V0 V1 A0 A1
+    L.table = L.soa + 9 * kPatch * 8;                                    // packed node table: (x,y) (e0,e1) e3  -> 40 B per node
+    L.stage = (L.table + 40 * (kPatch + max_halo) + 127) / 128 * 128;
+    L.rec = 128 + 2 * L.stage;                                           // after the barriers and the two stages
+    L.total = L.rec + 64 * max_elem + 128;
+    return L;
+}
+
+template <bool DBG>
+__global__ void __launch_bounds__(kPipeThreads, 3) k_subs_pipe(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
+                                                               double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const PipeLayout L = pipe_layout(pv.stride, pv.max_halo, pv.max_elem);
+    unsigned long long *bars = (unsigned long long *)smraw;              // [0..1] tma, [2..3] full, [4..5] empty
+    unsigned char *stage0 = smraw + 128;
+    double2 *rec = (double2 *)(smraw + L.rec);                           // [4][EM]
+    const int NLt = kPatch + pv.max_halo, EM = pv.max_elem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int np = s.np;
+    if (tid == 0) {
+        for (int q = 0; q < 2; q++) { mbar_init(bars + q, 1); mbar_init(bars + 2 + q, 1); mbar_init(bars + 4 + q, kPipeConsumers); }
+    }
+    __syncthreads();
+    const int first = blockIdx.x, step = gridDim.x;
+    if (warp == kPipeConsumers / 32) {
+        // ================= producer warp =================
+        int it = 0;
+        for (int p = first; p < pv.npatch; p += step, it++) {
+            const int sidx = it & 1; const unsigned int ph = (it >> 1) & 1;
+            unsigned char *st = stage0 + (size_t)sidx * L.stage;
+            double *soa = (double *)(st + L.soa);
+            double2 *txy = (double2 *)(st + L.table); double2 *te01 = txy + NLt; double *te3 = (double *)(te01 + NLt);
+            mbar_wait(bars + 4 + sidx, ph ^ 1);                          // stage free (passes immediately the first time round)
+            const int n0 = p * kPatch;
+            const int ncopy = min(kPatch, s.np - n0);
+            if (lane == 0) {
+                const unsigned int nb = (unsigned int)ncopy * 8u;
+                mbar_expect_tx(bars + sidx, (unsigned int)pv.stride + 9u * nb);
+                bulk_g2s(st + L.blob, pv.blob + (size_t)p * pv.stride, (unsigned int)pv.stride, bars + sidx);
+                bulk_g2s(soa, s.x + n0, nb, bars + sidx); bulk_g2s(soa + kPatch, s.x + np + n0, nb, bars + sidx);
+                bulk_g2s(soa + 2 * kPatch, s.ea_in + n0, nb, bars + sidx); bulk_g2s(soa + 3 * kPatch, s.ea_in + np + n0, nb, bars + sidx);
+                bulk_g2s(soa + 4 * kPatch, s.ea_in + 3 * (size_t)np + n0, nb, bars + sidx);
+                bulk_g2s(soa + 5 * kPatch, s.V + n0, nb, bars + sidx); bulk_g2s(soa + 6 * kPatch, s.V + np + n0, nb, bars + sidx);
+                bulk_g2s(soa + 7 * kPatch, s.A + n0, nb, bars + sidx); bulk_g2s(soa + 8 * kPatch, s.A + np + n0, nb, bars + sidx);
+            }
+            mbar_wait(bars + sidx, ph);
+            const int nh = ((const int *)(st + L.blob))[0];
+            const int *halo_ids = (const int *)(st + L.blob + pv.off_halo);
+            for (int l = lane; l < nh; l += 32) {                        // halo gather first: its loads overlap the repack below
+                const int g = halo_ids[l];
+                txy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
+                te01[kPatch + l] = make_double2(s.ea_in[g], s.ea_in[np + g]);
+                te3[kPatch + l] = s.ea_in[3 * (size_t)np + g];
+            }
+            for (int l = lane; l < kPatch; l += 32) {
+                txy[l] = make_double2(soa[l], soa[kPatch + l]); te01[l] = make_double2(soa[2 * kPatch + l], soa[3 * kPatch + l]); te3[l] = soa[4 * kPatch + l];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 2 + sidx);                 // stage full
+        }
+        return;
+    }
+    // ================= consumer warps =================
+    int it = 0;
+    for (int p = first; p < pv.npatch; p += step, it++) {
+        const int sidx = it & 1; const unsigned int ph = (it >> 1) & 1;
+        unsigned char *st = stage0 + (size_t)sidx * L.stage;
+        const double *soa = (const double *)(st + L.soa);
+        const double2 *txy = (const double2 *)(st + L.table); const double2 *te01 = txy + NLt; const double *te3 = (const double *)(te01 + NLt);
+        const int n0 = p * kPatch;
+        const int nown = min(kPatch, s.nn - n0);
+        const int i = n0 + tid;
+        const bool own = tid < nown;
+        mbar_wait(bars + 2 + sidx, ph);
+        const int nel = ((const int *)(st + L.blob))[1];
+        const unsigned short *elem_lv = (const unsigned short *)(st + L.blob + pv.off_lv);
+        const unsigned short *rptr = (const unsigned short *)(st + L.blob + pv.off_rptr);
+        const unsigned short *ring16 = (const unsigned short *)(st + L.blob + pv.off_ring);
+        // ---- elements
+        for (int el = tid; el < nel; el += kPipeConsumers) {
+            const unsigned short *lv = elem_lv + 3 * el;
+            const int a = lv[0], b = lv[1], d = lv[2];
+            const double2 pa = txy[a], pb = txy[b], pd = txy[d], ea = te01[a], eb = te01[b], ed = te01[d];
+            const double X[3][2] = {{pa.x, pa.y}, {pb.x, pb.y}, {pd.x, pd.y}};
+            const double e3[3] = {1.0 / 3.0 * ea.x + 1.0 / 3.0 * eb.x + 1.0 / 3.0 * ed.x, 1.0 / 3.0 * ea.y + 1.0 / 3.0 * eb.y + 1.0 / 3.0 * ed.y,
+                                  1.0 / 3.0 * te3[a] + 1.0 / 3.0 * te3[b] + 1.0 / 3.0 * te3[d]};      // UL:1055
+            ElemOutFrozen o;
+            elem_eval_frozen(X, e3, k.mu_subs, k.thick, o);
+            rec[el] = make_double2(o.r1[0], o.r1[1]);
+            rec[EM + el] = make_double2(o.r2[0], o.r2[1]);
+            rec[2 * EM + el] = make_double2(e3[0], e3[1]);
+            rec[3 * EM + el] = make_double2(e3[2], o.A0);
+        }
+        named_bar_sync(1, kPipeConsumers);
+        // ---- nodes
+        if (own) {
+            const double2 myxy = txy[tid], mye01 = te01[tid];
+            const double ea0 = mye01.x, ea1 = mye01.y, ea3 = te3[tid];
+            double V0 = soa[5 * kPatch + tid], V1 = soa[6 * kPatch + tid], A0v = soa[7 * kPatch + tid], A1v = soa[8 * kPatch + tid];
+            double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
+            const int rb = rptr[tid], re = rptr[tid + 1];
+            for (int r = rb; r < re; r++) {
+                const int code = ring16[r];
+                const int el = code >> 2, slot = code & 3;
+                const double2 f1 = rec[el], f2 = rec[EM + el], es = rec[2 * EM + el], ez = rec[3 * EM + el];
+                rx += slot == 0 ? -(f1.x + f2.x) : (slot == 1 ? f1.x : f2.x);
+                ry += slot == 0 ? -(f1.y + f2.y) : (slot == 1 ? f1.y : f2.y);
+                const double w = (1. / 3.) * ez.y * k.thick;                 // UL:1172 == the weight of UL:1170
+                q0 += (es.x - ea0) * w; q1 += (es.y - ea1) * w; q3 += (ez.x - ea3) * w;
+                mm += w;
+            }
+            const double Xi0 = myxy.x, Xi1 = myxy.y;
+            double Fx = 0.0, Fy = 0.0;
+            if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
+                const int e0 = pv.elem_ptr[p];
+                for (int r = rb; r < re; r++) {
+                    const int code = ring16[r];
+                    const int el = code >> 2, slot = code & 3;
+                    const int e = pv.elem_gid[e0 + el];
+                    const unsigned long long h = bk.head[e];
+                    if ((unsigned int)(h >> 32) != bk.epoch) continue;
+                    int cnt = (int)(unsigned int)h;
+                    if (cnt > bk.cap) cnt = bk.cap;
+                    const unsigned short *lv = elem_lv + 3 * el;
+                    const double2 p1 = txy[lv[0]], p2 = txy[lv[1]], p3 = txy[lv[2]];
+                    const double n1[3] = {p1.x, p1.y, 0.0}, n2[3] = {p2.x, p2.y, 0.0}, n3[3] = {p3.x, p3.y, 0.0};
+                    int prev = -1;
+                    for (int m = 0; m < cnt; m++) {
+                        int ni = 0x7fffffff;
+                        for (int q = 0; q < cnt; q++) { const int v = bk.items[(size_t)e * bk.cap + q]; if (v > prev && v < ni) ni = v; }
+                        prev = ni;
+                        const double u[3] = {c.fa[ni], c.fa[c.np + ni], 0.0};
+                        const double pt[3] = {c.x[ni] - u[0], c.x[c.np + ni] - u[1], 0.0};     // UL:1303
+                        double Ar[3], At;
+                        point_in_triangle(n1, n2, n3, pt, Ar, At);
+                        double fi[3];
+                        integrin_force(k, u, fi);
+                        const double w = Ar[slot] / At, cC = c.cC[ni], As = c.asum[ni];
+                        Fx += cC * fi[0] * w * As * k.rho_i_max;                                 // UL:1414-1422
+                        Fy += cC * fi[1] * w * As * k.rho_i_max;
+                    }
+                }
+            }
+            double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt / 2.0, A1v));   // UL:295
+            if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {            // UL:298-341, Vbiax == 0
+                if (Xi0 < -k.pin_limit || Xi0 > k.pin_limit) Vh0 = 0.0;
+                if (Xi1 > k.pin_limit || Xi1 < -k.pin_limit) Vh1 = 0.0;
+            }
+            const double imm = 1.0 / mm;
+            node_update_r(Fx - rx, mm, imm, k.damp, k.rho, dt, dt_real, Vh0, V0, A0v);            // UL:471-503
+            node_update_r(Fy - ry, mm, imm, k.damp, k.rho, dt, dt_real, Vh1, V1, A1v);
+            s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
+            s.ea_out[i] = ea0 + q0 * imm; s.ea_out[np + i] = ea1 + q1 * imm; s.ea_out[3 * np + i] = ea3 + q3 * imm;
+            if (DBG) {
+                dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
+                dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
+            }
+        }
+        mbar_arrive(bars + 4 + sidx);                                    // this thread is done with the stage
+        named_bar_sync(1, kPipeConsumers);                               // records may be overwritten by the next patch
     }
 }
 
