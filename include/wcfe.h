@@ -146,6 +146,10 @@ int wcfe_mark_positions_committed(wcfe_ctx *c);
  * as sim->m_curr_t += accum_dt does (main.cpp:405).  *t_io: in = time at the start, out = time after. */
 int wcfe_step_n(wcfe_ctx *c, int n, double dt, double *t_io);
 
+/* the same without waiting: returns once the n steps are queued on the context's stream (ensembles of many small
+ * independent cells per GPU: one host thread keeps every context busy).  wcfe_sync() waits and reports device errors. */
+int wcfe_step_n_async(wcfe_ctx *c, int n, double dt, double *t_io);
+
 /* host round trip per step, as the adapter drives it with El Topo in the loop: predict -> D2H predicted
  * positions of both surfaces into pinned buffers -> H2D of the same buffers as "accepted" positions ->
  * update -> D2H diagnostics.  Used for the end-to-end measurement; returns bytes moved per step. */

@@ -21,7 +21,7 @@ SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_param
            "wcfe_upload_mesh", "wcfe_upload_state", "wcfe_download_state", "wcfe_mesh_sizes", "wcfe_set_rng", "wcfe_set_debug",
            "wcfe_rng_skip", "wcfe_set_profile", "wcfe_get_kernel_ms", "wcfe_set_force_general", "wcfe_get_path_info",
            "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities",
-           "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
+           "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
            "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_sync"]
 
 
@@ -77,6 +77,7 @@ def load():
     L.wcfe_driver_velocities.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
     L.wcfe_mark_positions_committed.argtypes = [vp]
     L.wcfe_step_n.argtypes = [vp, C.c_int, C.c_double, _dp]
+    L.wcfe_step_n_async.argtypes = [vp, C.c_int, C.c_double, _dp]
     L.wcfe_step_n_roundtrip.argtypes = [vp, C.c_int, C.c_double, _dp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.wcfe_get_diagnostics.argtypes = [vp, _dp]
     L.wcfe_get_discrete.argtypes = [vp, C.c_int, _ip]

@@ -62,7 +62,7 @@ struct Surface {
     std::vector<unsigned char> is_bnd;
     std::vector<int> ring_ptr, ring;      // host CSR
     DevBuf<int> d_tri, d_ring_ptr, d_ring;
-    DevBuf<double> x, X, V, A, ea[2], cA, cB, cC, fa, asum;
+    DevBuf<double> x, X, V, A, V2, A2, ea[2], cA, cB, cC, fa, asum;   // V2/A2: write buffers of the planar cell kernel
     int ea_cur = 0;
     // boundary (cell)
     int nb = 0;
@@ -123,6 +123,7 @@ struct wcfe_ctx {
     long long launches = 0;
     double last_ms = 0, t_last = 0;
     bool have_predict[2] = {false, false};
+    bool tape_busy = false;               // an async step_n may still be reading the pinned RNG tape
     std::string err;
 };
 
@@ -458,6 +459,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     BoundaryView bv = bview(cs);
     const bool planar = use_planar(c);
     int npart = gc;
+    const double *v_old = cs.V.p, *a_old = cs.A.p;      // general path: V, A are updated in place
     if (!(which & 1)) goto subs_half;
     if (planar) {
         // fused cell kernel: (predict) + updateFA + anchor location + forces + update, one CTA per patch
@@ -472,14 +474,18 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         const size_t smem = patch_smem_bytes(7, 9, cs.max_halo, cs.max_elem, cs.stride);
         npart = cs.npatch;
         if (fuse_predict) {
-            if (c->debug) k_cell_patch<true, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, dview(cs));
-            else k_cell_patch<true, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, DebugView{});
+            if (c->debug) k_cell_patch<true, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, dview(cs));
+            else k_cell_patch<true, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{});
             std::swap(cs.x.p, cs.X.p);      // the buffer just read holds X_t, the one just written x_{t+dt}
-            cv = view(cs);
         } else {
-            if (c->debug) k_cell_patch<false, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, dview(cs));
-            else k_cell_patch<false, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, DebugView{});
+            if (c->debug) k_cell_patch<false, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, cs.V2.p, cs.A2.p, dview(cs));
+            else k_cell_patch<false, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, cs.V2.p, cs.A2.p, DebugView{});
         }
+        // V, A were written to the second buffers (neighbouring patches read the old ones for their halo predictor): swap, so
+        // that cs.V / cs.A are the new state and cs.V2 / cs.A2 hold the start-of-step values k_boundary_finish still needs
+        std::swap(cs.V.p, cs.V2.p); std::swap(cs.A.p, cs.A2.p);
+        cv = view(cs);
+        v_old = cs.V2.p; a_old = cs.A2.p;
         c->launches += 1;
     } else {
         if (fuse_predict) {
@@ -498,8 +504,8 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     }
     { ProfScope ps(c, K_FINISH);
     const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few blocks: the kernel is latency-, not throughput-bound
-    if (c->debug) k_boundary_finish<true><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, dt, dt_real, c->d_diag.p, dview(cs));
-    else k_boundary_finish<false><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, dt, dt_real, c->d_diag.p, DebugView{}); }
+    if (c->debug) k_boundary_finish<true><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, dview(cs));
+    else k_boundary_finish<false><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, DebugView{}); }
     c->launches += 1;
     cs.ea_cur ^= 1;
 subs_half:
@@ -629,7 +635,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     for (int q = 0; q < 2; q++) {
         Surface &s = c->s[q];
         s.d_tri.release(); s.d_ring_ptr.release(); s.d_ring.release();
-        s.x.release(); s.X.release(); s.V.release(); s.A.release(); s.ea[0].release(); s.ea[1].release();
+        s.x.release(); s.X.release(); s.V.release(); s.A.release(); s.V2.release(); s.A2.release(); s.ea[0].release(); s.ea[1].release();
         s.cA.release(); s.cB.release(); s.cC.release(); s.fa.release(); s.asum.release();
         s.d_bnd_node.release(); s.d_bnd_index.release(); s.d_cand_ptr.release(); s.d_cand.release(); s.d_bnd_buf.release();
         s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
@@ -729,6 +735,8 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
     s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
     if (surface == WCFE_CELL) {
         CK(s.X.alloc(3 * np)); CK(cudaMemcpy(s.X.p, s.x.p, sizeof(double) * 3 * np, cudaMemcpyDeviceToDevice));
+        CK(s.V2.alloc(3 * np)); CK(s.A2.alloc(3 * np));
+        CK(cudaMemset(s.V2.p, 0, sizeof(double) * 3 * np)); CK(cudaMemset(s.A2.p, 0, sizeof(double) * 3 * np));
         CK(s.cA.alloc(np)); CK(s.cB.alloc(np)); CK(s.cC.alloc(np)); CK(s.fa.alloc(3 * np)); CK(s.asum.alloc(np));
         if ((rc = fill_field(c, s.cA.p, nn, s.np, 1, c->prm.c_A_init))) return rc;        // main.cpp:672
         CK(cudaMemset(s.cB.p, 0, sizeof(double) * np)); CK(cudaMemset(s.cC.p, 0, sizeof(double) * np));
@@ -961,6 +969,27 @@ int wcfe_step_n(wcfe_ctx *c, int n, double dt, double *t_io) {
     return check_device_errors(c);
 }
 
+/* launch n steps without waiting for them: lets one host thread keep many small contexts (an ensemble of independent
+ * cells) busy on one GPU, each on its own stream; wcfe_sync() later waits and reports device-side errors */
+int wcfe_step_n_async(wcfe_ctx *c, int n, double dt, double *t_io) {
+    int rc = ready(c);
+    if (rc) return rc;
+    if (n < 0 || !t_io) return WCFE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    if (c->rng_mode == WCFE_RNG_GLIBC_REPLAY && c->tape_busy) { CK(cudaStreamSynchronize(c->stream)); c->tape_busy = false; }   // pinned tape still in flight
+    if ((rc = stage_tape(c, n))) return rc;
+    c->tape_busy = true;
+    Surface &cs = c->s[WCFE_CELL];
+    double t = *t_io;
+    for (int q = 0; q < n; q++) {
+        const unsigned int *tape = c->d_tape.p ? c->d_tape.p + (size_t)q * cs.nb : nullptr;
+        if ((rc = launch_update(c, dt, dt, t, tape, true))) return rc;
+        t += dt;
+    }
+    *t_io = t; c->t_last = t;
+    return WCFE_OK;
+}
+
 int wcfe_step_n_roundtrip(wcfe_ctx *c, int n, double dt, double *t_io, long long *h2d, long long *d2h) {
     int rc = ready(c);
     if (rc) return rc;
@@ -1076,7 +1105,8 @@ int wcfe_sync(wcfe_ctx *c) {
     if (!c) return WCFE_ERR_ARG;
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    return WCFE_OK;
+    c->tape_busy = false;
+    return (c->s[0].nn && c->s[1].nn) ? check_device_errors(c) : WCFE_OK;
 }
 
 }   // extern "C"

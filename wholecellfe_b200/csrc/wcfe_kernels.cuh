@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(kBlock) k_cell_node(SurfView s, BoundaryView b
 // blocks), then finishes its share of the boundary vertices; block 0 publishes the diagnostics
 template <bool DBG>
 __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k, int npart, const double *__restrict__ partials,
+                                                          const double *__restrict__ V_in, const double *__restrict__ A_in,
                                                           double dt, double dt_real, double *__restrict__ diag, DebugView dbg) {
     __shared__ double sh[4 * 32];
     __shared__ double tot[4];
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
         for (int c = 0; c < 3; c++) {
             const double F_area = -k.k_area * (area_tot - k.area_0) / 2 * tl * o[8 + c];   // UL:1757
             const double f = (o[c] + F_area) - o[3 + c];
-            double V = s.V[c * np + i], A = s.A[c * np + i];
+            double V = V_in[c * np + i], A = A_in[c * np + i];       // start-of-step values (the planar path double-buffers V, A)
             double Vh = V + (dt / 2.0) * A;
             if (c == 2) Vh = 0.0;
             node_update(f, mm, k.damp, k.rho, dt, dt_real, Vh, V, A);

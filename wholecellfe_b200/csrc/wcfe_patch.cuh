@@ -397,7 +397,9 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_subs_pipe(SurfView s, Patch
 
 // ---- cell: the whole cell side of one UL step in ONE kernel ---------------------------------------------------------
 //   PREDICT: driverVelocities_Explicit + inline predictor (UL:103-124, main.cpp:224-242) for owned AND halo nodes, read
-//            from the current position buffer and written to the other one (ping-pong: the old buffer becomes X_t);
+//            from the current position buffer and written to the other one (ping-pong: the old buffer becomes X_t).
+//            Because a patch predicts its halo nodes from THEIR V, A, no patch may overwrite V, A in place: x, V, A and ea
+//            are all double-buffered (read buffer / write buffer, swapped by the host after the launch);
 //   updateFA (UL:2005-2114) and the anchor location / bucket insertion for calculateForce_FA_subs (UL:1301-1340);
 //   updateForces_Explicit, cell overload (UL:508-630): residual, integrin, drag, bending, actin, update.
 // Boundary vertices wait for the total area exactly as in k_cell_node (finished by k_boundary_finish).
@@ -413,7 +415,8 @@ struct CellStepArgs {
 
 template <bool PREDICT, bool DBG>
 __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, PatchView pv, SurfView sub, GridView g, BucketView bk, BoundaryView b, Consts k,
-                                                       CellStepArgs a, const double *__restrict__ x_in, double *__restrict__ x_out, DebugView dbg) {
+                                                       CellStepArgs a, const double *__restrict__ x_in, double *__restrict__ x_out,
+                                                       double *__restrict__ V_out, double *__restrict__ A_out, DebugView dbg) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ double shred[4 * 32];
     const int NL = kPatch + pv.max_halo, EM = pv.max_elem;
@@ -576,7 +579,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         if (bi < 0) {
             node_update(Fvx + Ffx - rx, mm, k.damp, k.rho, a.dt, a.dt_real, Vh0, V0, Av0);           // UL:592-628
             node_update(Fvy + Ffy - ry, mm, k.damp, k.rho, a.dt, a.dt_real, Vh1, V1, Av1);
-            s.V[i] = V0; s.V[np + i] = V1; s.A[i] = Av0; s.A[np + i] = Av1;
+            // V, A go to the OTHER buffer: neighbouring patches still read this node's old V, A for their halo predictor
+            V_out[i] = V0; V_out[np + i] = V1; A_out[i] = Av0; A_out[np + i] = Av1;
         } else {
             const double xi[3] = {sx0[tid], sx1[tid], 0.0};
             double j1[3] = {0, 0, 0}, j2[3] = {0, 0, 0};

@@ -137,6 +137,12 @@ class ULSim:
         self._ck(self.L.wcfe_step_n(self.h, n, dt, C.byref(t)))
         return t.value
 
+    def step_n_async(self, n, dt, t0):
+        """Queue n steps and return immediately (sync() waits and checks for device-side errors)."""
+        t = C.c_double(t0)
+        self._ck(self.L.wcfe_step_n_async(self.h, n, dt, C.byref(t)))
+        return t.value
+
     def step_n_roundtrip(self, n, dt, t0):
         t = C.c_double(t0)
         a = C.c_longlong()
