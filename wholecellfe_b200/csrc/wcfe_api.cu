@@ -396,7 +396,7 @@ bool use_planar(wcfe_ctx *c) {
     // a mesh numbered without locality can blow the per-patch tables past shared memory: use the general kernels then
     if (c->use_pipe && pipe_layout(c->s[1].stride, c->s[1].max_halo, c->s[1].max_elem).total > kPatchSmemMax) return false;
     return patch_smem_bytes(7, 9, c->s[0].max_halo, c->s[0].max_elem, c->s[0].stride) <= (size_t)kPatchSmemMax &&
-           patch_smem_bytes(5, 8, c->s[1].max_halo, c->s[1].max_elem, c->s[1].stride) <= (size_t)kPatchSmemMax;
+           patch_smem_bytes(5, 10, c->s[1].max_halo, c->s[1].max_elem, c->s[1].stride) <= (size_t)kPatchSmemMax;
 }
 
 // (re)size the per-triangle buckets once both meshes are known
@@ -521,7 +521,7 @@ subs_half:
         else k_subs_pipe<false><<<grid, kPipeThreads, L.total, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
     } else if (planar) {
         ProfScope ps(c, K_SUBS);
-        const size_t smem = patch_smem_bytes(5, 8, ss.max_halo, ss.max_elem, ss.stride);
+        const size_t smem = patch_smem_bytes(5, 10, ss.max_halo, ss.max_elem, ss.stride);
         PatchView pvs = pview(ss);
         if (c->debug) k_subs_patch<true><<<ss.npatch, kThreads, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
         else k_subs_patch<false><<<ss.npatch, kThreads, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});

@@ -23,7 +23,7 @@ namespace wcfe {
 #define WCFE_PATCH 128
 #endif
 #ifndef WCFE_MINBLK
-#define WCFE_MINBLK 6
+#define WCFE_MINBLK 5
 #endif
 #ifndef WCFE_THREADS
 #define WCFE_THREADS 128
@@ -32,6 +32,10 @@ constexpr int kPatch = WCFE_PATCH;     // owned nodes per patch
 constexpr int kThreads = WCFE_THREADS; // threads per CTA: a patch has ~2.35 elements per owned node, so 1.25 x kPatch threads
                                        // finish the element phase in two full rounds instead of two and a tail
 constexpr int kMinBlk = WCFE_MINBLK;   // resident CTAs per SM the register allocation is tuned for
+#ifndef WCFE_RING_CHUNK
+#define WCFE_RING_CHUNK 3
+#endif
+constexpr int kRingChunk = WCFE_RING_CHUNK;   // one-ring entries gathered per batch of independent shared-memory loads
 
 // Per-patch descriptor ("blob"): everything a CTA needs to know about its patch, contiguous and of one fixed stride for
 // all patches of a surface, so that ONE TMA bulk copy (cp.async.bulk -> UBLKCP) stages it without any dependent lookup:
@@ -87,8 +91,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
 
 // ---- substrate: updateForces_Explicit (UL:429-504) + driverVelocities_Biaxial (UL:275-345) + calculateForce_FA_subs ---
 // (UL:1297-1454) for a frozen substrate (main.cpp:299): X == x, F == I, closed form elem_eval_frozen.
-// Shared memory: node table packed as (x,y) / (e_xx,e_yy) double2 + e_xy, element records as four double2 per element
-// (force on local node 1, 2; (e_s.xx,e_s.yy); (e_s.xy, A0)) so that gathers are 128-bit and branch-free.
+// Shared memory: node table packed as (x,y) / (e_xx,e_yy) double2 + e_xy, element records as five double2 per element
+// (force on local node 0, 1, 2; (e_s.xx,e_s.yy); (e_s.xy, A0)) so that gathers are 128-bit and branch-free.
 template <bool DBG>
 __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
                                                                   double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg) {
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
     double2 *sxy = (double2 *)(sblob + pv.stride);       // [NL]
     double2 *se01 = sxy + NL;                             // [NL]
     double *se3 = (double *)(se01 + NL);                  // [NL] (NL is a multiple of 4)
-    double2 *rec = (double2 *)(se3 + NL);                 // [4][EM]; first used as the SoA landing zone of the bulk copies
+    double2 *rec = (double2 *)(se3 + NL);                 // [5][EM]; first used as the SoA landing zone of the bulk copies
     double *stage = (double *)rec;                        // [5][kPatch]: x0 x1 e0 e1 e3 of the owned nodes
     const int p = blockIdx.x, tid = threadIdx.x;
     const int n0 = p * kPatch;
@@ -151,10 +155,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
                               1.0 / 3.0 * se3[a] + 1.0 / 3.0 * se3[b] + 1.0 / 3.0 * se3[d]};          // UL:1055
         ElemOutFrozen o;
         elem_eval_frozen(X, e3, k.mu_subs, k.thick, o);
-        rec[el] = make_double2(o.r1[0], o.r1[1]);
-        rec[EM + el] = make_double2(o.r2[0], o.r2[1]);
-        rec[2 * EM + el] = make_double2(e3[0], e3[1]);           // e_s == averaged e for F == I
-        rec[3 * EM + el] = make_double2(e3[2], o.A0);
+        rec[el] = make_double2(-(o.r1[0] + o.r2[0]), -(o.r1[1] + o.r2[1]));   // force on local node 0, 1, 2: the node phase
+        rec[EM + el] = make_double2(o.r1[0], o.r1[1]);                       // reads only the one of its slot
+        rec[2 * EM + el] = make_double2(o.r2[0], o.r2[1]);
+        rec[3 * EM + el] = make_double2(e3[0], e3[1]);           // e_s == averaged e for F == I
+        rec[4 * EM + el] = make_double2(e3[2], o.A0);
     }
     __syncthreads();
     // ---- nodes
@@ -162,15 +167,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
     const double ea0 = mye01.x, ea1 = mye01.y, ea3 = mye3;
     double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
     const int rb = rptr[tid], re = rptr[tid + 1];
-    for (int r = rb; r < re; r++) {
-        const int code = ring16[r];
-        const int el = code >> 2, slot = code & 3;
-        const double2 f1 = rec[el], f2 = rec[EM + el], es = rec[2 * EM + el], ez = rec[3 * EM + el];
-        rx += slot == 0 ? -(f1.x + f2.x) : (slot == 1 ? f1.x : f2.x);
-        ry += slot == 0 ? -(f1.y + f2.y) : (slot == 1 ? f1.y : f2.y);
-        const double w = (1. / 3.) * ez.y * k.thick;                     // UL:1172 == the weight of UL:1170
-        q0 += (es.x - ea0) * w; q1 += (es.y - ea1) * w; q3 += (ez.x - ea3) * w;
-        mm += w;
+    // The one-ring gather is a chain of dependent shared-memory loads (code -> record); process the ring in chunks of
+    // kRingChunk entries with every load of a chunk issued before the first use, padding short chunks with zero-weight
+    // entries (adding +0 leaves the ascending-element summation order and the result unchanged).
+    for (int base = rb; base < re; base += kRingChunk) {
+        int code[kRingChunk];
+#pragma unroll
+        for (int j = 0; j < kRingChunk; j++) code[j] = base + j < re ? (int)ring16[base + j] : -1;
+        double2 f[kRingChunk], es[kRingChunk], ez[kRingChunk];
+#pragma unroll
+        for (int j = 0; j < kRingChunk; j++) {
+            const int el = code[j] < 0 ? 0 : code[j] >> 2, slot = code[j] & 3;
+            f[j] = rec[slot * EM + el]; es[j] = rec[3 * EM + el]; ez[j] = rec[4 * EM + el];   // 48 B per (node, element)
+        }
+#pragma unroll
+        for (int j = 0; j < kRingChunk; j++) {
+            const bool on = code[j] >= 0;
+            const double w = on ? (1. / 3.) * ez[j].y * k.thick : 0.0;   // UL:1172 == the weight of UL:1170
+            rx += on ? f[j].x : 0.0; ry += on ? f[j].y : 0.0;
+            q0 += (es[j].x - ea0) * w; q1 += (es[j].y - ea1) * w; q3 += (ez[j].x - ea3) * w;
+            mm += w;
+        }
     }
     const double Xi0 = myxy.x, Xi1 = myxy.y;
     double Fx = 0.0, Fy = 0.0;
