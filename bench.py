@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--subs-side", type=int, default=2000, help="substrate nodes per side (2000 -> 4M nodes, 8M triangles)")
     ap.add_argument("--variant", default="k31", choices=["k1", "k31", "kMD"])
     ap.add_argument("--dt", type=float, default=2e-5, help="explicit step below the substrate CFL limit h*sqrt(rho/mu) = 5e-5")
+    ap.add_argument("--mode", default="ensemble", choices=["ensemble", "partition"],
+                    help="N > 1: independent replicas (weak scaling, default) or ONE workload with the substrate cut into strips and a "
+                         "per-step NCCL halo exchange (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-div", type=int, default=16, help="CPU baseline sample = workload / this (both meshes)")
     return ap.parse_args()
@@ -166,6 +169,35 @@ def run_reference_arm(a):
     print(json.dumps(line), flush=True)
 
 
+def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
+    """Strong scaling: ONE cell + substrate; the substrate is cut into `world` strips (cell replicated, it is 1/9 of the
+    elements), every step ends with the NCCL exchange of the strip-border strains.  value counts every element once."""
+    import torch
+    from wholecellfe_b200.partition import PartitionedSim
+    sim = PartitionedSim(a.variant, cell_mesh, subs_mesh, dist, local, rng=(1, 1))
+    ne = len(cell_mesh[1]) + len(subs_mesh[1])
+    sim.step_n(a.warmup, a.dt)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    l0 = sim.sim.kernel_launches()
+    e0.record()
+    sim.step_n(a.steps, a.dt)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    halo = sum(len(v) for v in sim.part.send.values())
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": ne * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "ONE synthetic %d-triangle cell on %d-node substrate, substrate in %d strips, cell replicated"
+                                                 % (len(cell_mesh[1]), len(subs_mesh[0]), world), "variant": a.variant, "dt": a.dt,
+                                     "parallelism": "substrate strip partition x%d + per-step NCCL halo exchange (%d border nodes x 24 B per neighbour)" % (world, halo)},
+                          "gpu_launches": sim.sim.kernel_launches() - l0}), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -185,6 +217,9 @@ def main():
 
     xc, tc, xs, ts = workload_meshes(a.cell_tris, a.subs_side)
     nn_c, ne_c, nn_s, ne_s = len(xc), len(tc), len(xs), len(ts)
+    if a.mode == "partition" and world > 1:
+        run_partition_mode(a, dist, rank, world, local, (xc, tc), (xs, ts))
+        return
     sim = W.ULSim(a.variant, device=local, stream=stream.cuda_stream)
     sim.upload_mesh(W.CELL, xc, tc); sim.upload_mesh(W.SUBS, xs, ts)
     sim.set_rng(1, 1 + rank)                     # counter-based Philox, one stream per replica

@@ -167,6 +167,9 @@ double wcfe_last_step_ms(wcfe_ctx *c);
  * 0 Res(cell) 1 F_FA 2 F_AP 3 F_bending 4 F_area 5 Res(subs) 6 F_FA_subs; out[3*nn]; mm[nn] / res_ea[6*nn]
  * may be NULL.  Diagnostic entry point for the force-level parity gate (1e-10). */
 int wcfe_force_field(wcfe_ctx *c, int which, double dt, double t_curr, double *out, double *mm, double *res_ea);
+/* raw device pointer of a state field (SoA: component q of node i at ptr[q*pitch + i]); x, V, A, ea are double-buffered, so
+ * ask again after every step.  Zero-copy interop with torch.distributed for the halo exchange of partitioned meshes. */
+int wcfe_device_ptr(wcfe_ctx *c, int surface, int field, void **ptr, long long *pitch);
 int wcfe_sync(wcfe_ctx *c);
 
 #ifdef __cplusplus

@@ -22,7 +22,7 @@ SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_param
            "wcfe_rng_skip", "wcfe_set_profile", "wcfe_get_kernel_ms", "wcfe_set_force_general", "wcfe_get_path_info",
            "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities",
            "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
-           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_sync"]
+           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync"]
 
 
 class Params(C.Structure):
@@ -85,6 +85,7 @@ def load():
     L.wcfe_kernel_launches.argtypes = [vp]; L.wcfe_kernel_launches.restype = C.c_longlong
     L.wcfe_last_step_ms.argtypes = [vp]; L.wcfe_last_step_ms.restype = C.c_double
     L.wcfe_force_field.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp]
+    L.wcfe_device_ptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
     L.wcfe_sync.argtypes = [vp]
     _lib = L
     return L

@@ -1101,6 +1101,16 @@ int wcfe_force_field(wcfe_ctx *c, int which, double dt, double t_curr, double *o
     return WCFE_OK;
 }
 
+/* raw device pointer of a state field (SoA: component q of node i at ptr[q*pitch + i]); valid until the next step for the
+ * double-buffered fields (x, V, A, ea).  For zero-copy interop with torch.distributed (halo exchange of partitioned meshes). */
+int wcfe_device_ptr(wcfe_ctx *c, int surface, int field, void **ptr, long long *pitch) {
+    if (!c || surface < 0 || surface > 1 || !ptr || !pitch) return WCFE_ERR_ARG;
+    double *d = field_dev(c, surface, field);
+    if (!d || !c->s[surface].nn) return fail(c, WCFE_ERR_ARG, "device_ptr: no such field on this surface (or no mesh)");
+    *ptr = d; *pitch = c->s[surface].np;
+    return WCFE_OK;
+}
+
 int wcfe_sync(wcfe_ctx *c) {
     if (!c) return WCFE_ERR_ARG;
     CK(cudaSetDevice(c->device));

@@ -1,0 +1,150 @@
+"""Element-partitioned substrate with a per-step halo exchange (BASELINE configs[3]; SURVEY.md 8e, second mode).
+
+Round-1 scope: the SUBSTRATE (8 of the 9 million elements of config 4, and frozen in space, main.cpp:299) is cut into
+vertical strips, one per rank; the cell (the remaining ninth) is replicated on every rank, where it evolves identically
+because every kernel is deterministic -- so the only data that has to cross between GPUs each step is the strain `ea` of the
+substrate nodes on the strip borders (3 doubles per node; positions never change, V and A are only read by their owner).
+Ghost nodes are recomputed with incomplete one-rings and overwritten by the exchange before anything reads them.
+
+Host logic only: strip partition, local meshes, send/receive index lists, and the exchange itself through torch.distributed
+(NCCL on device tensors that alias libwcfe's own buffers; gloo on CPU tensors in the tests).
+"""
+import numpy as np
+
+
+class StripPart:
+    """What one rank holds of the partitioned substrate."""
+
+    def __init__(self, rank, world, owned, ghosts, local_nodes, tri_local, elem_gid, send, recv):
+        self.rank, self.world = rank, world
+        self.owned = owned                  # global ids of owned nodes (ascending)
+        self.ghosts = ghosts                # global ids of ghost nodes (ascending)
+        self.local_nodes = local_nodes      # global id of every local node, ascending (owned and ghosts interleaved)
+        self.tri_local = tri_local          # [m,3] local vertex ids, elements in ascending global element id
+        self.elem_gid = elem_gid            # global element ids of the local elements
+        self.send = send                    # {neighbour rank: local ids of owned nodes that are ghosts there}
+        self.recv = recv                    # {neighbour rank: local ids of ghost nodes owned there}
+        self.owned_local = np.searchsorted(local_nodes, owned)
+
+
+def strip_partition(xyz, tri, world):
+    """Cut the mesh into `world` vertical strips of (almost) equal node count.  Returns the list of StripPart.
+
+    A node belongs to the strip its x coordinate falls in (ties by node id); a rank holds every element with at least one
+    owned vertex, hence a one-ring of ghost nodes.  Local numbering keeps the global (space-filling-curve) order, and local
+    elements keep ascending global ids, so every nodal sum is formed in the same order as on a single GPU."""
+    xyz = np.asarray(xyz); tri = np.asarray(tri)
+    nn = len(xyz)
+    order = np.lexsort((np.arange(nn), xyz[:, 0]))
+    owner = np.empty(nn, dtype=np.int32)
+    bounds = [(nn * r) // world for r in range(world + 1)]
+    for r in range(world):
+        owner[order[bounds[r]:bounds[r + 1]]] = r
+    tri_owner = owner[tri]                                   # [m,3]
+    parts = []
+    for r in range(world):
+        emask = (tri_owner == r).any(axis=1)
+        elem_gid = np.nonzero(emask)[0]
+        local_nodes = np.unique(tri[elem_gid])
+        is_owned = owner[local_nodes] == r
+        owned = local_nodes[is_owned]
+        ghosts = local_nodes[~is_owned]
+        # nodes owned by r that no element touches cannot exist in a valid mesh; owned nodes all appear in local_nodes
+        tri_local = np.searchsorted(local_nodes, tri[elem_gid]).astype(np.int32)
+        parts.append([r, owned, ghosts, local_nodes, tri_local, elem_gid])
+    out = []
+    for r in range(world):
+        _, owned, ghosts, local_nodes, tri_local, elem_gid = parts[r]
+        recv = {}
+        for q in np.unique(owner[ghosts]):
+            g = ghosts[owner[ghosts] == q]
+            recv[int(q)] = np.searchsorted(local_nodes, g)
+        send = {}
+        for q in range(world):
+            if q == r:
+                continue
+            gq = parts[q][2]
+            mine = gq[owner[gq] == r]                        # ghosts of q that r owns, in q's ascending order
+            if len(mine):
+                send[q] = np.searchsorted(local_nodes, mine)
+        out.append(StripPart(r, world, owned, ghosts, local_nodes, tri_local, elem_gid, send, recv))
+    return out
+
+
+class _CudaView:
+    """__cuda_array_interface__ holder: lets torch alias a libwcfe device buffer without copying."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def exchange_rows(dist, table, part, comps, device):
+    """Refresh the ghost rows of `table` ([ncomp, pitch] tensor, node index last) from their owners.  Pairwise send/recv with
+    every neighbour, batched (NCCL groups them into one launch).  With the gloo backend (CPU tests, or several ranks sharing
+    one GPU) the packed rows are staged through host memory, since gloo cannot send device tensors."""
+    import torch
+    staged = dist.get_backend() == "gloo" and table.is_cuda
+    comm = torch.device("cpu") if staged else device
+    ops, keep = [], []
+    comps_t = torch.as_tensor(comps, device=device)
+    for q, ids in sorted(part.send.items()):
+        idx = torch.as_tensor(ids, device=device)
+        buf = table.index_select(0, comps_t).index_select(1, idx).contiguous().to(comm)
+        ops.append(dist.P2POp(dist.isend, buf, q))
+        keep.append(buf)
+    rbufs = []
+    for q, ids in sorted(part.recv.items()):
+        buf = torch.empty((len(comps), len(ids)), dtype=table.dtype, device=comm)
+        ops.append(dist.P2POp(dist.irecv, buf, q))
+        rbufs.append((ids, buf))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for ids, buf in rbufs:
+        idx = torch.as_tensor(ids, device=device)
+        buf = buf.to(device)
+        for k, cmp in enumerate(comps):
+            table[cmp].index_copy_(0, idx, buf[k])
+
+
+class PartitionedSim:
+    """One rank of a substrate-partitioned run: full cell + this rank's substrate strip on one GPU."""
+
+    def __init__(self, variant, cell_mesh, subs_mesh, dist, device_index, rng=(1, 1), params=None):
+        import torch
+        from . import ulstep
+        from ._lib import CELL, SUBS
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = torch.device("cuda", device_index)
+        xs, ts = subs_mesh
+        self.part = strip_partition(xs, ts, self.world)[self.rank]
+        self.sim = ulstep.ULSim(variant, device=device_index, params=params, stream=torch.cuda.current_stream().cuda_stream)
+        self.sim.upload_mesh(CELL, cell_mesh[0], cell_mesh[1])
+        self.sim.upload_mesh(SUBS, xs[self.part.local_nodes], self.part.tri_local)
+        self.sim.set_rng(*rng)
+        self.SUBS = SUBS
+        self.n_owned_elements = int((np.isin(ts, self.part.owned).any(axis=1)).sum())   # == local elements
+        self.t = 0.0
+
+    def _ea_table(self):
+        ptr, pitch = self.sim.device_ptr(self.SUBS, "ea")
+        return self.torch.as_tensor(_CudaView(ptr, (6, pitch)), device=self.device)
+
+    def step(self, dt):
+        """one UL step on every rank, then the halo exchange of the substrate strain (xx, yy, xy: the planar components)"""
+        self.t = self.sim.step_n_async(1, dt, self.t)
+        exchange_rows(self.dist, self._ea_table(), self.part, [0, 1, 3], self.device)
+
+    def step_n(self, n, dt):
+        for _ in range(n):
+            self.step(dt)
+        self.sim.sync()
+
+    def set_subs_field(self, field, global_values):
+        """upload a substrate field given for the WHOLE substrate ([Nn_global, w]); every rank keeps its local rows"""
+        self.sim.set(self.SUBS, field, np.asarray(global_values)[self.part.local_nodes])
+
+    def owned_field(self, field):
+        """(global node ids, values) of this rank's owned substrate nodes"""
+        return self.part.owned, self.sim.get(self.SUBS, field)[self.part.owned_local]

@@ -175,6 +175,13 @@ class ULSim:
         self._ck(self.L.wcfe_force_field(self.h, w, 0.0, 0.0, _d(out), _d(mm), _d(rea)))
         return {"F": out, "MM": mm, "Res_ea": rea}
 
+    def device_ptr(self, surface, field):
+        """(address, pitch) of a SoA state field on the device: component q of node i lives at address + 8*(q*pitch + i)."""
+        ptr = C.c_void_p()
+        pitch = C.c_longlong()
+        self._ck(self.L.wcfe_device_ptr(self.h, surface, B.FIELDS[field], C.byref(ptr), C.byref(pitch)))
+        return ptr.value, pitch.value
+
     def kernel_launches(self):
         return int(self.L.wcfe_kernel_launches(self.h))
 
