@@ -92,7 +92,8 @@ int wcfe_default_params(wcfe_params *p, int variant);
 int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p);
 int wcfe_destroy(wcfe_ctx *c);
 int wcfe_set_params(wcfe_ctx *c, const wcfe_params *p);
-/* run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own */
+/* run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own non-blocking stream;
+ * pass cudaStreamLegacy ((cudaStream_t)0x1) to name the legacy default stream explicitly */
 int wcfe_set_stream(wcfe_ctx *c, void *cuda_stream);
 const char *wcfe_last_error(wcfe_ctx *c);
 

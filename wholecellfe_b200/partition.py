@@ -85,26 +85,31 @@ def exchange_rows(dist, table, part, comps, device):
     import torch
     staged = dist.get_backend() == "gloo" and table.is_cuda
     comm = torch.device("cpu") if staged else device
+    cache = part.__dict__.setdefault("_idx_cache", {})
+    key = (str(device), tuple(comps))
+    if key not in cache:                                    # index tensors live on the device for the whole run
+        cache[key] = (torch.as_tensor(comps, device=device),
+                      {q: torch.as_tensor(ids, device=device) for q, ids in part.send.items()},
+                      {q: torch.as_tensor(ids, device=device) for q, ids in part.recv.items()})
+    comps_t, send_idx, recv_idx = cache[key]
+    sub = table.index_select(0, comps_t)                    # [len(comps), pitch]
     ops, keep = [], []
-    comps_t = torch.as_tensor(comps, device=device)
-    for q, ids in sorted(part.send.items()):
-        idx = torch.as_tensor(ids, device=device)
-        buf = table.index_select(0, comps_t).index_select(1, idx).contiguous().to(comm)
+    for q in sorted(send_idx):
+        buf = sub.index_select(1, send_idx[q]).contiguous().to(comm)
         ops.append(dist.P2POp(dist.isend, buf, q))
         keep.append(buf)
     rbufs = []
-    for q, ids in sorted(part.recv.items()):
-        buf = torch.empty((len(comps), len(ids)), dtype=table.dtype, device=comm)
+    for q in sorted(recv_idx):
+        buf = torch.empty((len(comps), len(recv_idx[q])), dtype=table.dtype, device=comm)
         ops.append(dist.P2POp(dist.irecv, buf, q))
-        rbufs.append((ids, buf))
+        rbufs.append((q, buf))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    for ids, buf in rbufs:
-        idx = torch.as_tensor(ids, device=device)
+    for q, buf in rbufs:
         buf = buf.to(device)
         for k, cmp in enumerate(comps):
-            table[cmp].index_copy_(0, idx, buf[k])
+            table[cmp].index_copy_(0, recv_idx[q], buf[k])
 
 
 class PartitionedSim:

@@ -41,7 +41,9 @@ class ULSim:
             why = self.L.wcfe_last_error(None).decode()
             raise WcfeError(rc, "wcfe_create(device %d) failed: %s%s" % (device, why, " -- the product has no CPU fallback" if rc == B.ERR_CUDA else ""))
         if stream is not None:
-            self._ck(self.L.wcfe_set_stream(self.h, C.c_void_p(stream)))
+            # torch reports the legacy default stream as handle 0, which the C ABI reads as "use the context's own stream";
+            # cudaStreamLegacy (0x1) names the default stream explicitly
+            self._ck(self.L.wcfe_set_stream(self.h, C.c_void_p(stream if stream != 0 else 1)))
         self.nn = [0, 0]
         self.ne = [0, 0]
 
