@@ -77,7 +77,9 @@ struct Surface {
     int npatch = 0, max_halo = 0, max_elem = 0;
     double halo_elem_ratio = 0;           // patch-local elements / elements: the recompute overhead
     int stride = 0, off_halo = 0, off_lv = 0, off_rptr = 0, off_ring = 0;   // blob layout (wcfe_patch.cuh)
-    DevBuf<unsigned char> p_blob;
+    DevBuf<unsigned char> p_blob, p_ring_blob;
+    DevBuf<int> p_ring_cyc;
+    int ring_stride = 0, roff_halo = 0, roff_rptr = 0, roff_jk = 0;
     DevBuf<int> p_elem_ptr, p_elem_gid;
     DevBuf<unsigned short> p_cand_l;
 };
@@ -115,6 +117,7 @@ struct wcfe_ctx {
     int use_pipe = 0;                     // substrate: persistent software-pipelined kernel (k_subs_pipe) instead of k_subs_patch;
                                           // measured slower on B200 (0.43 vs 0.355 ms: its 73 KB of stages leave 12 consumer warps per SM)
     int num_sms = 148;
+    int subs_kernel = 2;                  // planar substrate kernel: 2 = k_subs_ring (node-centric, default), 0 = k_subs_patch (element-once)
     int profile = 0;                      // per-kernel CUDA-event timing (bench roofline leg)
     std::vector<cudaEvent_t> pev;         // event pool, pairs
     std::vector<int> pev_kernel;          // kernel id of each pair in flight
@@ -308,7 +311,7 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
     Surface &s = c->s[surface];
     const int P = kPatch;
     s.npatch = (s.nn + P - 1) / P;
-    struct Tmp { std::vector<int> halo; std::vector<unsigned short> lv, rptr, ring; int nel; };
+    struct Tmp { std::vector<int> halo; std::vector<unsigned short> lv, rptr, ring, jk; std::vector<int> cyc_code; int nel; };
     std::vector<Tmp> tmp((size_t)s.npatch);
     std::vector<int> elem_ptr(1, 0), elem_gid;
     std::vector<unsigned short> cand_l(cand.size(), 0);
@@ -339,6 +342,37 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
         for (int r = s.ring_ptr[n0]; r < s.ring_ptr[n1]; r++) {
             const int e = s.ring[r] >> 2, slot = s.ring[r] & 3;
             t.ring.push_back((unsigned short)(((std::lower_bound(el.begin(), el.end(), e) - el.begin()) << 2) | slot));
+        }
+        if (surface == WCFE_SUBS) {
+            // k_subs_ring walks each node's fan in CYCLIC order (entry r+1 starts at the vertex entry r ended on), so that every
+            // neighbour is read from shared memory once instead of twice; chains start at the open end of a boundary fan, or at
+            // the lowest element id of a closed fan (deterministic)
+            for (int v = n0; v < n1; v++) {
+                const int rb = s.ring_ptr[v], m = s.ring_ptr[v + 1] - rb;
+                std::vector<int> J(m), K(m), used(m, 0);
+                for (int q = 0; q < m; q++) {
+                    const int e = s.ring[rb + q] >> 2, slot = s.ring[rb + q] & 3;
+                    J[q] = s.tri[3 * (size_t)e + (slot + 1) % 3]; K[q] = s.tri[3 * (size_t)e + (slot + 2) % 3];
+                }
+                for (int done = 0; done < m;) {
+                    int start = -1;
+                    for (int q = 0; q < m && start < 0; q++) {            // an entry nobody leads into = open end of a fan
+                        if (used[q]) continue;
+                        bool has_pred = false;
+                        for (int w = 0; w < m; w++) if (!used[w] && w != q && K[w] == J[q]) has_pred = true;
+                        if (!has_pred) start = q;
+                    }
+                    if (start < 0) for (int q = 0; q < m; q++) if (!used[q]) { start = q; break; }   // closed fan: lowest element id
+                    for (int cur = start; cur >= 0;) {
+                        used[cur] = 1; done++;
+                        t.jk.push_back(local(J[cur])); t.jk.push_back(local(K[cur]));
+                        t.cyc_code.push_back(s.ring[rb + cur]);
+                        int nxt = -1;
+                        for (int w = 0; w < m; w++) if (!used[w] && J[w] == K[cur]) { nxt = w; break; }
+                        cur = nxt;
+                    }
+                }
+            }
         }
         if (surface == WCFE_CELL) {        // boundary candidates of the owned boundary vertices, in table order
             for (int v = n0; v < n1; v++) {
@@ -374,6 +408,31 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
         memcpy(b + s.off_rptr, t.rptr.data(), 2 * t.rptr.size());
         if (!t.ring.empty()) memcpy(b + s.off_ring, t.ring.data(), 2 * t.ring.size());
     }
+    // second blob for the node-centric substrate kernel
+    s.roff_halo = 16;
+    s.roff_rptr = (int)(s.roff_halo + pad16(4 * (size_t)s.max_halo));
+    s.roff_jk = (int)(s.roff_rptr + pad16(2 * ((size_t)P + 8)));
+    s.ring_stride = (int)(s.roff_jk + pad16(4 * (size_t)max_ring));
+    if (surface == WCFE_SUBS) {
+        std::vector<unsigned char> rb((size_t)s.npatch * s.ring_stride, 0);
+        for (int p = 0; p < s.npatch; p++) {
+            unsigned char *b = rb.data() + (size_t)p * s.ring_stride;
+            const Tmp &t = tmp[p];
+            int hdr[4] = {(int)t.halo.size(), t.nel, 0, 0};
+            memcpy(b, hdr, 16);
+            if (!t.halo.empty()) memcpy(b + s.roff_halo, t.halo.data(), 4 * t.halo.size());
+            memcpy(b + s.roff_rptr, t.rptr.data(), 2 * t.rptr.size());
+            if (!t.jk.empty()) memcpy(b + s.roff_jk, t.jk.data(), 2 * t.jk.size());
+        }
+        CK(s.p_ring_blob.alloc(rb.size()));
+        CK(cudaMemcpy(s.p_ring_blob.p, rb.data(), rb.size(), cudaMemcpyHostToDevice));
+        // (element << 2 | slot) of every ring entry in the cyclic order, for the bucket lookup of the integrin gather
+        std::vector<int> cyc((size_t)s.ring.size());
+        size_t pos = 0;
+        for (int p = 0; p < s.npatch; p++) { memcpy(cyc.data() + pos, tmp[p].cyc_code.data(), 4 * tmp[p].cyc_code.size()); pos += tmp[p].cyc_code.size(); }
+        CK(s.p_ring_cyc.alloc(cyc.size()));
+        CK(cudaMemcpy(s.p_ring_cyc.p, cyc.data(), 4 * cyc.size(), cudaMemcpyHostToDevice));
+    }
     if (cand_l.empty()) cand_l.push_back(0);
     CK(s.p_blob.alloc(blob.size())); CK(s.p_elem_ptr.alloc(elem_ptr.size())); CK(s.p_elem_gid.alloc(elem_gid.size())); CK(s.p_cand_l.alloc(cand_l.size()));
     CK(cudaMemcpy(s.p_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
@@ -386,6 +445,7 @@ PatchView pview(Surface &s) {
     PatchView v{};
     v.npatch = s.npatch; v.max_halo = s.max_halo; v.max_elem = s.max_elem;
     v.stride = s.stride; v.off_halo = s.off_halo; v.off_lv = s.off_lv; v.off_rptr = s.off_rptr; v.off_ring = s.off_ring;
+    v.ring_stride = s.ring_stride; v.roff_halo = s.roff_halo; v.roff_rptr = s.roff_rptr; v.roff_jk = s.roff_jk; v.ring_blob = s.p_ring_blob.p; v.ring_cyc = s.p_ring_cyc.p;
     v.blob = s.p_blob.p; v.elem_ptr = s.p_elem_ptr.p; v.elem_gid = s.p_elem_gid.p; v.cand_l = s.p_cand_l.p;
     return v;
 }
@@ -511,7 +571,14 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
 subs_half:
     if (!(which & 2)) { CK(cudaGetLastError()); return WCFE_OK; }
     cv = view(cs);
-    if (planar && c->use_pipe) {
+    if (planar && c->subs_kernel == 2) {
+        // node-centric frozen-substrate kernel
+        ProfScope ps(c, K_SUBS);
+        const size_t smem = ring_smem_bytes(ss.max_halo, ss.ring_stride);
+        PatchView pvs = pview(ss);
+        if (c->debug) k_subs_ring<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
+        else k_subs_ring<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+    } else if (planar && c->use_pipe) {
         // persistent, software-pipelined substrate kernel: grid = SMs x 3 resident CTAs
         ProfScope ps(c, K_SUBS);
         const PipeLayout L = pipe_layout(ss.stride, ss.max_halo, ss.max_elem);
@@ -613,8 +680,9 @@ int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p) {
     {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
-        if (const char *e = std::getenv("WCFE_SUBS_PIPE")) c->use_pipe = std::atoi(e);
-        const void *pk[] = {(const void *)k_subs_pipe<false>, (const void *)k_subs_pipe<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
+        if (const char *e = std::getenv("WCFE_SUBS_PIPE")) { c->use_pipe = std::atoi(e); if (c->use_pipe) c->subs_kernel = 1; }
+        if (const char *e = std::getenv("WCFE_SUBS_KERNEL")) c->subs_kernel = std::atoi(e);
+        const void *pk[] = {(const void *)k_subs_ring<false>, (const void *)k_subs_ring<true>, (const void *)k_subs_pipe<false>, (const void *)k_subs_pipe<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
                             (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>};
         for (const void *f : pk) {
             // 227 KB is the per-CTA limit including the kernels' small static arrays
@@ -639,7 +707,7 @@ int wcfe_destroy(wcfe_ctx *c) {
         s.cA.release(); s.cB.release(); s.cC.release(); s.fa.release(); s.asum.release();
         s.d_bnd_node.release(); s.d_bnd_index.release(); s.d_cand_ptr.release(); s.d_cand.release(); s.d_bnd_buf.release();
         s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
-        s.p_blob.release(); s.p_elem_ptr.release(); s.p_elem_gid.release(); s.p_cand_l.release();
+        s.p_blob.release(); s.p_ring_blob.release(); s.p_ring_cyc.release(); s.p_elem_ptr.release(); s.p_elem_gid.release(); s.p_cand_l.release();
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();

@@ -54,8 +54,15 @@ struct PatchView {
     const int *elem_ptr;             // [npatch+1] into elem_gid
     const int *elem_gid;             // global element id of every patch-local element (substrate: bucket lookup)
     const unsigned short *cand_l;    // parallel to BoundaryView::cand: local node ids (cell only)
+    // node-centric substrate kernel (k_subs_ring): hdr | halo ids | ring_ptr | (j,k) local vertex pairs per ring entry
+    int ring_stride, roff_halo, roff_rptr, roff_jk;
+    const unsigned char *ring_blob;
+    const int *ring_cyc;             // (element << 2 | slot) per ring entry in the blob's cyclic order (same offsets as SurfView::ring)
 };
 
+__host__ __device__ inline size_t ring_smem_bytes(int max_halo, int ring_stride) {
+    return 16 + (size_t)ring_stride + sizeof(double) * 5 * ((size_t)kPatch + max_halo) + sizeof(double) * 5 * kPatch + 64;
+}
 __host__ __device__ inline size_t patch_smem_bytes(int n_node_arrays, int n_rec, int max_halo, int max_elem, int stride) {
     const size_t NL = (size_t)kPatch + max_halo, EM = (size_t)max_elem;
     size_t recs = sizeof(double) * n_rec * EM;
@@ -227,6 +234,143 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
         if (Xi1 > k.pin_limit || Xi1 < -k.pin_limit) Vh1 = 0.0;
     }
     const double imm = 1.0 / mm;                                                          // one reciprocal for the five quotients
+    node_update_r(Fx - rx, mm, imm, k.damp, k.rho, dt, dt_real, Vh0, V0, A0v);            // UL:471-503
+    node_update_r(Fy - ry, mm, imm, k.damp, k.rho, dt, dt_real, Vh1, V1, A1v);
+    s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
+    s.ea_out[i] = ea0 + q0 * imm; s.ea_out[np + i] = ea1 + q1 * imm; s.ea_out[3 * np + i] = ea3 + q3 * imm;
+    if (DBG) {
+        dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
+        dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
+    }
+}
+
+// ---- substrate, node-centric variant -----------------------------------------------------------------------------------------
+// The frozen-substrate element is so cheap (one division) that recomputing it at each of its three nodes costs fewer
+// instructions AND less shared-memory traffic than computing it once and handing an 80-byte record to three gatherers
+// (measured: k_subs_patch runs at 80 % of the shared-memory wavefront peak, 44 % of those wavefronts bank conflicts).  Here
+// a thread owns a node and walks its one-ring: for every incident element it reads the two other vertices (x, y, e) from
+// the packed node table and evaluates, with itself as local vertex 0,
+//     S = mu (b_t - det(I-2e) I),   f_me = -(r1 + r2) = -(t/2) sign(W) S (G2y-G1y, G1x-G2x),   A0 = |W|/2,
+// i.e. no element phase, no records, one barrier, 17 KB of shared memory per CTA.  Each node's fan is walked in cyclic order so
+// that consecutive elements share a vertex already in registers (half the shared-memory reads); the nodal sums are therefore
+// formed in fan order, not in the reference's ascending element order (UL:977-982): same terms, rounding-level difference,
+// still fixed and bit-reproducible.
+// Extra blob section for this kernel: uint16 pairs (j, k) = local ids of the element's other two vertices in cyclic order.
+#ifndef WCFE_RING_MINBLK
+#define WCFE_RING_MINBLK 6
+#endif
+template <bool DBG>
+__global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
+                                                         double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int NL = kPatch + pv.max_halo;
+    unsigned long long *bar = (unsigned long long *)smraw;
+    unsigned char *sblob = smraw + 16;
+    double2 *sxy = (double2 *)(sblob + pv.ring_stride);  // [NL]
+    double2 *se01 = sxy + NL;                             // [NL]
+    double *se3 = (double *)(se01 + NL);                  // [NL]
+    double *stage = se3 + NL;                             // [5][kPatch] landing zone of the bulk copies
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int n0 = p * kPatch;
+    const int nown = min(kPatch, s.nn - n0);
+    const int ncopy = min(kPatch, s.np - n0);
+    const int np = s.np;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        const unsigned int nb = (unsigned int)ncopy * 8u;
+        mbar_expect_tx(bar, (unsigned int)pv.ring_stride + 5u * nb);
+        bulk_g2s(sblob, pv.ring_blob + (size_t)p * pv.ring_stride, (unsigned int)pv.ring_stride, bar);
+        bulk_g2s(stage, s.x + n0, nb, bar); bulk_g2s(stage + kPatch, s.x + np + n0, nb, bar);
+        bulk_g2s(stage + 2 * kPatch, s.ea_in + n0, nb, bar); bulk_g2s(stage + 3 * kPatch, s.ea_in + np + n0, nb, bar);
+        bulk_g2s(stage + 4 * kPatch, s.ea_in + 3 * (size_t)np + n0, nb, bar);
+    }
+    const int i = n0 + tid;
+    const bool own = tid < nown;
+    double V0 = 0, V1 = 0, A0v = 0, A1v = 0;
+    if (own) { V0 = s.V[i]; V1 = s.V[np + i]; A0v = s.A[i]; A1v = s.A[np + i]; }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const int nh = ((const int *)sblob)[0];
+    const int *halo_ids = (const int *)(sblob + pv.roff_halo);
+    const unsigned short *rptr = (const unsigned short *)(sblob + pv.roff_rptr);
+    const unsigned short *rjk = (const unsigned short *)(sblob + pv.roff_jk);
+    const double2 myxy = make_double2(stage[tid], stage[kPatch + tid]), mye01 = make_double2(stage[2 * kPatch + tid], stage[3 * kPatch + tid]);
+    const double mye3 = stage[4 * kPatch + tid];
+    sxy[tid] = myxy; se01[tid] = mye01; se3[tid] = mye3;
+    for (int l = tid; l < nh; l += kPatch) {
+        const int g = halo_ids[l];
+        sxy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
+        se01[kPatch + l] = make_double2(s.ea_in[g], s.ea_in[np + g]);
+        se3[kPatch + l] = s.ea_in[3 * (size_t)np + g];
+    }
+    __syncthreads();
+    if (!own) return;
+    const double ea0 = mye01.x, ea1 = mye01.y, ea3 = mye3;
+    double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
+    const int rb = rptr[tid], re = rptr[tid + 1];
+    const double third = 1.0 / 3.0;
+    int lastk = -1;
+    double2 pk = make_double2(0, 0), ek = make_double2(0, 0);
+    double e3k = 0;
+    for (int r = rb; r < re; r++) {
+        const int j = rjk[2 * r], kk = rjk[2 * r + 1];
+        double2 pj, ej; double e3j;
+        if (j == lastk) { pj = pk; ej = ek; e3j = e3k; }                 // fan in cyclic order: this vertex closed the previous element
+        else { pj = sxy[j]; ej = se01[j]; e3j = se3[j]; }
+        pk = sxy[kk]; ek = se01[kk]; e3k = se3[kk]; lastk = kk;
+        // averaged strain in the element's own vertex order is a sum of three equal-weight terms: order-independent up to rounding
+        const double e0 = third * ea0 + third * ej.x + third * ek.x, e1 = third * ea1 + third * ej.y + third * ek.y, e3 = third * ea3 + third * e3j + third * e3k;
+        const double G1x = pj.x - myxy.x, G1y = pj.y - myxy.y, G2x = pk.x - myxy.x, G2y = pk.y - myxy.y;
+        const double Wz = G1x * G2y - G1y * G2x;
+        const double a00 = 1.0 - 2.0 * e0, a11 = 1.0 - 2.0 * e1, a01 = -2.0 * e3;
+        const double det2 = a00 * a11 - a01 * a01;
+        const double idet = 1.0 / det2;
+        const double S00 = k.mu_subs * (a11 * idet - det2), S11 = k.mu_subs * (a00 * idet - det2), S01 = -k.mu_subs * a01 * idet;
+        const double dx = G2y - G1y, dy = G1x - G2x;
+        const double hs = Wz > 0 ? -0.5 * k.thick : 0.5 * k.thick;       // -(t/2) sign(W)
+        rx += hs * (S00 * dx + S01 * dy); ry += hs * (S01 * dx + S11 * dy);
+        const double w = third * (0.5 * fabs(Wz)) * k.thick;             // UL:1172
+        q0 += (e0 - ea0) * w; q1 += (e1 - ea1) * w; q3 += (e3 - ea3) * w; // UL:1170 with e_s == e for F == I
+        mm += w;
+    }
+    const double Xi0 = myxy.x, Xi1 = myxy.y;
+    double Fx = 0.0, Fy = 0.0;
+    if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
+        const int gb = s.ring_ptr[i];
+        for (int r = rb; r < re; r++) {
+            const int code = pv.ring_cyc[gb + (r - rb)];
+            const int e = code >> 2, slot = code & 3;
+            const unsigned long long h = bk.head[e];
+            if ((unsigned int)(h >> 32) != bk.epoch) continue;
+            int cnt = (int)(unsigned int)h;
+            if (cnt > bk.cap) cnt = bk.cap;
+            // the element's vertices in their ORIGINAL order (the sub-areas of the predicate are order dependent)
+            const int lid[3] = {tid, (int)rjk[2 * r], (int)rjk[2 * r + 1]};
+            const double2 p1 = sxy[lid[(3 - slot) % 3]], p2 = sxy[lid[(4 - slot) % 3]], p3 = sxy[lid[(5 - slot) % 3]];
+            const double n1[3] = {p1.x, p1.y, 0.0}, n2[3] = {p2.x, p2.y, 0.0}, n3[3] = {p3.x, p3.y, 0.0};
+            int prev = -1;
+            for (int m = 0; m < cnt; m++) {
+                int ni = 0x7fffffff;
+                for (int q = 0; q < cnt; q++) { const int v = bk.items[(size_t)e * bk.cap + q]; if (v > prev && v < ni) ni = v; }
+                prev = ni;
+                const double u[3] = {c.fa[ni], c.fa[c.np + ni], 0.0};
+                const double pt[3] = {c.x[ni] - u[0], c.x[c.np + ni] - u[1], 0.0};     // UL:1303
+                double Ar[3], At;
+                point_in_triangle(n1, n2, n3, pt, Ar, At);
+                double fi[3];
+                integrin_force(k, u, fi);
+                const double w = Ar[slot] / At, cC = c.cC[ni], As = c.asum[ni];
+                Fx += cC * fi[0] * w * As * k.rho_i_max;                                 // UL:1414-1422
+                Fy += cC * fi[1] * w * As * k.rho_i_max;
+            }
+        }
+    }
+    double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt / 2.0, A1v));   // UL:295
+    if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {            // UL:298-341, Vbiax == 0
+        if (Xi0 < -k.pin_limit || Xi0 > k.pin_limit) Vh0 = 0.0;
+        if (Xi1 > k.pin_limit || Xi1 < -k.pin_limit) Vh1 = 0.0;
+    }
+    const double imm = 1.0 / mm;
     node_update_r(Fx - rx, mm, imm, k.damp, k.rho, dt, dt_real, Vh0, V0, A0v);            // UL:471-503
     node_update_r(Fy - ry, mm, imm, k.damp, k.rho, dt, dt_real, Vh1, V1, A1v);
     s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
