@@ -49,15 +49,16 @@ def parse():
     ap.add_argument("--mode", default="ensemble", choices=["ensemble", "partition"],
                     help="N > 1: independent replicas (weak scaling, default) or ONE workload with the substrate cut into strips and a "
                          "per-step NCCL halo exchange (strong scaling)")
+    ap.add_argument("--order", default="morton", choices=["morton", "morton_rows"], help="node numbering of the synthetic meshes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-div", type=int, default=16, help="CPU baseline sample = workload / this (both meshes)")
     return ap.parse_args()
 
 
-def workload_meshes(cell_tris, subs_side):
+def workload_meshes(cell_tris, subs_side, order="morton"):
     from wholecellfe_b200.meshgen import disk_mesh, square_mesh
-    xc, tc = disk_mesh(cell_tris)
-    xs, ts = square_mesh(subs_side)
+    xc, tc = disk_mesh(cell_tris, order=order)
+    xs, ts = square_mesh(subs_side, order=order)
     return xc, tc, xs, ts
 
 
@@ -215,7 +216,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.current_stream()
 
-    xc, tc, xs, ts = workload_meshes(a.cell_tris, a.subs_side)
+    xc, tc, xs, ts = workload_meshes(a.cell_tris, a.subs_side, a.order)
     nn_c, ne_c, nn_s, ne_s = len(xc), len(tc), len(xs), len(ts)
     if a.mode == "partition" and world > 1:
         run_partition_mode(a, dist, rank, world, local, (xc, tc), (xs, ts))

@@ -59,6 +59,7 @@ template <class T> struct DevBuf {
 struct Surface {
     int nn = 0, np = 0, ne = 0, nep = 0;
     std::vector<int> tri;                 // host copy, [3*ne] AoS as uploaded
+    std::vector<double> host_xy;          // host copy of the in-plane coordinates at upload (patch preprocessing)
     std::vector<unsigned char> is_bnd;
     std::vector<int> ring_ptr, ring;      // host CSR
     DevBuf<int> d_tri, d_ring_ptr, d_ring;
@@ -79,7 +80,7 @@ struct Surface {
     int stride = 0, off_halo = 0, off_lv = 0, off_rptr = 0, off_ring = 0;   // blob layout (wcfe_patch.cuh)
     DevBuf<unsigned char> p_blob, p_ring_blob;
     DevBuf<int> p_ring_cyc;
-    int ring_stride = 0, roff_halo = 0, roff_rptr = 0, roff_jk = 0;
+    int ring_stride = 0, roff_halo = 0, roff_rptr = 0, roff_jk = 0, max_val = 0;
     DevBuf<int> p_elem_ptr, p_elem_gid;
     DevBuf<unsigned short> p_cand_l;
 };
@@ -329,6 +330,7 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
         for (int e : el) for (int j = 0; j < 3; j++) { const int v = s.tri[3 * (size_t)e + j]; if (v < n0 || v >= n1) hl.push_back(v); }
         std::sort(hl.begin(), hl.end()); hl.erase(std::unique(hl.begin(), hl.end()), hl.end());
         const int nring = s.ring_ptr[n1] - s.ring_ptr[n0];
+        for (int v = n0; v < n1; v++) if (s.ring_ptr[v + 1] - s.ring_ptr[v] > 255) return fail(c, WCFE_ERR_CAPACITY, "patch tables: vertex valence above 255");
         if ((int)el.size() > 16383 || P + (int)hl.size() > 65535 || nring > 65535)
             return fail(c, WCFE_ERR_CAPACITY, "patch tables: a vertex of extreme valence overflows the 16-bit local ids");
         auto local = [&](int v) -> unsigned short {
@@ -362,7 +364,17 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
                         for (int w = 0; w < m; w++) if (!used[w] && w != q && K[w] == J[q]) has_pred = true;
                         if (!has_pred) start = q;
                     }
-                    if (start < 0) for (int q = 0; q < m; q++) if (!used[q]) { start = q; break; }   // closed fan: lowest element id
+                    if (start < 0) {
+                        // closed fan: start at the neighbour of smallest polar angle, so that neighbouring nodes (= neighbouring
+                        // lanes) visit their neighbours in the same geometric sequence and their shared-memory reads fall on
+                        // consecutive table slots instead of random ones (bank conflicts)
+                        double best = 1e300;
+                        for (int q = 0; q < m; q++) {
+                            if (used[q]) continue;
+                            const double ang = std::atan2(s.host_xy[2 * (size_t)J[q] + 1] - s.host_xy[2 * (size_t)v + 1], s.host_xy[2 * (size_t)J[q]] - s.host_xy[2 * (size_t)v]);
+                            if (ang < best) { best = ang; start = q; }
+                        }
+                    }
                     for (int cur = start; cur >= 0;) {
                         used[cur] = 1; done++;
                         t.jk.push_back(local(J[cur])); t.jk.push_back(local(K[cur]));
@@ -409,10 +421,14 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
         if (!t.ring.empty()) memcpy(b + s.off_ring, t.ring.data(), 2 * t.ring.size());
     }
     // second blob for the node-centric substrate kernel
+    // layout: hdr | halo ids | valence[kPatch] (uint8) | jk[step][node] (ushort2, step-major so that a warp reads consecutive words)
+    int max_val = 1;
+    for (int v = 0; v < s.nn; v++) max_val = std::max(max_val, s.ring_ptr[v + 1] - s.ring_ptr[v]);
+    s.max_val = max_val;
     s.roff_halo = 16;
     s.roff_rptr = (int)(s.roff_halo + pad16(4 * (size_t)s.max_halo));
-    s.roff_jk = (int)(s.roff_rptr + pad16(2 * ((size_t)P + 8)));
-    s.ring_stride = (int)(s.roff_jk + pad16(4 * (size_t)max_ring));
+    s.roff_jk = (int)(s.roff_rptr + pad16((size_t)P));
+    s.ring_stride = (int)(s.roff_jk + pad16(4 * (size_t)max_val * P));
     if (surface == WCFE_SUBS) {
         std::vector<unsigned char> rb((size_t)s.npatch * s.ring_stride, 0);
         for (int p = 0; p < s.npatch; p++) {
@@ -421,8 +437,13 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
             int hdr[4] = {(int)t.halo.size(), t.nel, 0, 0};
             memcpy(b, hdr, 16);
             if (!t.halo.empty()) memcpy(b + s.roff_halo, t.halo.data(), 4 * t.halo.size());
-            memcpy(b + s.roff_rptr, t.rptr.data(), 2 * t.rptr.size());
-            if (!t.jk.empty()) memcpy(b + s.roff_jk, t.jk.data(), 2 * t.jk.size());
+            unsigned char *val = b + s.roff_rptr;
+            unsigned short *jkT = (unsigned short *)(b + s.roff_jk);
+            for (int l = 0; l < P; l++) {
+                const int r0 = t.rptr[l], r1 = t.rptr[l + 1];
+                val[l] = (unsigned char)(r1 - r0);
+                for (int r = r0; r < r1; r++) { jkT[2 * ((size_t)(r - r0) * P + l)] = t.jk[2 * r]; jkT[2 * ((size_t)(r - r0) * P + l) + 1] = t.jk[2 * r + 1]; }
+            }
         }
         CK(s.p_ring_blob.alloc(rb.size()));
         CK(cudaMemcpy(s.p_ring_blob.p, rb.data(), rb.size(), cudaMemcpyHostToDevice));
@@ -746,6 +767,8 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
     Surface &s = c->s[surface];
     s.nn = nn; s.ne = ne; s.np = (nn + 31) / 32 * 32; s.nep = (ne + 31) / 32 * 32;
     s.tri.assign(tri, tri + 3 * (size_t)ne);
+    s.host_xy.resize(2 * (size_t)nn);
+    for (int v = 0; v < nn; v++) { s.host_xy[2 * (size_t)v] = xyz[3 * (size_t)v]; s.host_xy[2 * (size_t)v + 1] = xyz[3 * (size_t)v + 1]; }
     // vertex -> triangle CSR in ascending triangle order (nondestructivetrimesh.cpp:138-194)
     s.ring_ptr.assign((size_t)nn + 1, 0);
     for (int q = 0; q < 3 * ne; q++) s.ring_ptr[tri[q] + 1]++;

@@ -25,6 +25,19 @@ def _renumber(xyz, tri, order="morton"):
     lo = xyz[:, :2].min(axis=0); span = np.maximum(xyz[:, :2].max(axis=0) - lo, 1e-300)
     q = np.minimum(((xyz[:, :2] - lo) / span * 65535.0).astype(np.int64), 65535)
     perm = np.argsort(_morton_key(q[:, 0], q[:, 1]), kind="stable")       # new -> old
+    if order == "morton_rows":
+        # inside every chunk of `chunk` consecutive Morton nodes (= one GPU patch) re-sort by rows (y band, then x): neighbouring
+        # nodes then sit in neighbouring slots of the patch's shared-memory node table, which is what keeps the one-ring gathers
+        # of the patch kernels free of bank conflicts
+        chunk = 128
+        p2 = perm.copy()
+        for b in range(0, len(perm), chunk):
+            ids = perm[b:b + chunk]
+            pts = xyz[ids, :2]
+            hrow = np.sqrt(max((pts[:, 0].max() - pts[:, 0].min()) * (pts[:, 1].max() - pts[:, 1].min()), 1e-300) / max(len(ids), 1))
+            row = np.floor((pts[:, 1] - pts[:, 1].min()) / max(hrow, 1e-300) + 0.5)
+            p2[b:b + chunk] = ids[np.lexsort((pts[:, 0], row))]
+        perm = p2
     inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
     xyz = xyz[perm]
     tri = inv[tri].astype(np.int32)
