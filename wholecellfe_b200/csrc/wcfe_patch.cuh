@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
 // that consecutive elements share a vertex already in registers (half the shared-memory reads); the nodal sums are therefore
 // formed in fan order, not in the reference's ascending element order (UL:977-982): same terms, rounding-level difference,
 // still fixed and bit-reproducible.
-// Extra blob section for this kernel: uint16 pairs (j, k) = local ids of the element's other two vertices in cyclic order.
+// Its own descriptor blob: hdr | halo ids | valence[kPatch] (uint8) | (j, k)[step][node] (ushort2: local ids of the element's
+// other two vertices in cyclic order; step-major so that a warp's index loads are conflict-free).
 #ifndef WCFE_RING_MINBLK
 #define WCFE_RING_MINBLK 6
 #endif
@@ -292,8 +293,8 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     mbar_wait(bar, 0);
     const int nh = ((const int *)sblob)[0];
     const int *halo_ids = (const int *)(sblob + pv.roff_halo);
-    const unsigned short *rptr = (const unsigned short *)(sblob + pv.roff_rptr);
-    const unsigned short *rjk = (const unsigned short *)(sblob + pv.roff_jk);
+    const unsigned char *valence = sblob + pv.roff_rptr;
+    const ushort2 *rjk = (const ushort2 *)(sblob + pv.roff_jk);          // [step][node]: conflict-free across a warp
     const double2 myxy = make_double2(stage[tid], stage[kPatch + tid]), mye01 = make_double2(stage[2 * kPatch + tid], stage[3 * kPatch + tid]);
     const double mye3 = stage[4 * kPatch + tid];
     sxy[tid] = myxy; se01[tid] = mye01; se3[tid] = mye3;
@@ -307,13 +308,14 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     if (!own) return;
     const double ea0 = mye01.x, ea1 = mye01.y, ea3 = mye3;
     double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
-    const int rb = rptr[tid], re = rptr[tid + 1];
+    const int nring = valence[tid];
     const double third = 1.0 / 3.0;
     int lastk = -1;
     double2 pk = make_double2(0, 0), ek = make_double2(0, 0);
     double e3k = 0;
-    for (int r = rb; r < re; r++) {
-        const int j = rjk[2 * r], kk = rjk[2 * r + 1];
+    for (int r = 0; r < nring; r++) {
+        const ushort2 jk = rjk[r * kPatch + tid];
+        const int j = jk.x, kk = jk.y;
         double2 pj, ej; double e3j;
         if (j == lastk) { pj = pk; ej = ek; e3j = e3k; }                 // fan in cyclic order: this vertex closed the previous element
         else { pj = sxy[j]; ej = se01[j]; e3j = se3[j]; }
@@ -337,15 +339,16 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     double Fx = 0.0, Fy = 0.0;
     if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
         const int gb = s.ring_ptr[i];
-        for (int r = rb; r < re; r++) {
-            const int code = pv.ring_cyc[gb + (r - rb)];
+        for (int r = 0; r < nring; r++) {
+            const int code = pv.ring_cyc[gb + r];
             const int e = code >> 2, slot = code & 3;
             const unsigned long long h = bk.head[e];
             if ((unsigned int)(h >> 32) != bk.epoch) continue;
             int cnt = (int)(unsigned int)h;
             if (cnt > bk.cap) cnt = bk.cap;
             // the element's vertices in their ORIGINAL order (the sub-areas of the predicate are order dependent)
-            const int lid[3] = {tid, (int)rjk[2 * r], (int)rjk[2 * r + 1]};
+            const ushort2 jk = rjk[r * kPatch + tid];
+            const int lid[3] = {tid, (int)jk.x, (int)jk.y};
             const double2 p1 = sxy[lid[(3 - slot) % 3]], p2 = sxy[lid[(4 - slot) % 3]], p3 = sxy[lid[(5 - slot) % 3]];
             const double n1[3] = {p1.x, p1.y, 0.0}, n2[3] = {p2.x, p2.y, 0.0}, n3[3] = {p3.x, p3.y, 0.0};
             int prev = -1;
