@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
 // Its own descriptor blob: hdr | halo ids | valence[kPatch] (uint8) | (j, k)[step][node] (ushort2: local ids of the element's
 // other two vertices in cyclic order; step-major so that a warp's index loads are conflict-free).
 #ifndef WCFE_RING_MINBLK
-#define WCFE_RING_MINBLK 6
+#define WCFE_RING_MINBLK 5
 #endif
 template <bool DBG>
 __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
@@ -309,20 +309,15 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     const double ea0 = mye01.x, ea1 = mye01.y, ea3 = mye3;
     double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
     const int nring = valence[tid];
-    const double third = 1.0 / 3.0;
-    int lastk = -1;
-    double2 pk = make_double2(0, 0), ek = make_double2(0, 0);
-    double e3k = 0;
-    for (int r = 0; r < nring; r++) {
-        const ushort2 jk = rjk[r * kPatch + tid];
-        const int j = jk.x, kk = jk.y;
-        double2 pj, ej; double e3j;
-        if (j == lastk) { pj = pk; ej = ek; e3j = e3k; }                 // fan in cyclic order: this vertex closed the previous element
-        else { pj = sxy[j]; ej = se01[j]; e3j = se3[j]; }
-        pk = sxy[kk]; ek = se01[kk]; e3k = se3[kk]; lastk = kk;
+    // one incident element, with this node as local vertex 0 and (j, k) the other two in cyclic order
+    struct Nb { double2 p, e; double e3; };
+    auto load_nb = [&](int l) { Nb n; n.p = sxy[l]; n.e = se01[l]; n.e3 = se3[l]; return n; };
+    struct Contrib { double fx, fy, d0, d1, d3, w; };
+    auto entry = [&](const Nb &J, const Nb &K) {
+        const double third = 1.0 / 3.0;
         // averaged strain in the element's own vertex order is a sum of three equal-weight terms: order-independent up to rounding
-        const double e0 = third * ea0 + third * ej.x + third * ek.x, e1 = third * ea1 + third * ej.y + third * ek.y, e3 = third * ea3 + third * e3j + third * e3k;
-        const double G1x = pj.x - myxy.x, G1y = pj.y - myxy.y, G2x = pk.x - myxy.x, G2y = pk.y - myxy.y;
+        const double e0 = third * ea0 + third * J.e.x + third * K.e.x, e1 = third * ea1 + third * J.e.y + third * K.e.y, e3 = third * ea3 + third * J.e3 + third * K.e3;
+        const double G1x = J.p.x - myxy.x, G1y = J.p.y - myxy.y, G2x = K.p.x - myxy.x, G2y = K.p.y - myxy.y;
         const double Wz = G1x * G2y - G1y * G2x;
         const double a00 = 1.0 - 2.0 * e0, a11 = 1.0 - 2.0 * e1, a01 = -2.0 * e3;
         const double det2 = a00 * a11 - a01 * a01;
@@ -330,10 +325,33 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
         const double S00 = k.mu_subs * (a11 * idet - det2), S11 = k.mu_subs * (a00 * idet - det2), S01 = -k.mu_subs * a01 * idet;
         const double dx = G2y - G1y, dy = G1x - G2x;
         const double hs = Wz > 0 ? -0.5 * k.thick : 0.5 * k.thick;       // -(t/2) sign(W)
-        rx += hs * (S00 * dx + S01 * dy); ry += hs * (S01 * dx + S11 * dy);
-        const double w = third * (0.5 * fabs(Wz)) * k.thick;             // UL:1172
-        q0 += (e0 - ea0) * w; q1 += (e1 - ea1) * w; q3 += (e3 - ea3) * w; // UL:1170 with e_s == e for F == I
-        mm += w;
+        Contrib c;
+        c.fx = hs * (S00 * dx + S01 * dy); c.fy = hs * (S01 * dx + S11 * dy);
+        c.w = third * (0.5 * fabs(Wz)) * k.thick;                        // UL:1172
+        c.d0 = (e0 - ea0) * c.w; c.d1 = (e1 - ea1) * c.w; c.d3 = (e3 - ea3) * c.w;   // UL:1170 with e_s == e for F == I
+        return c;
+    };
+    auto add = [&](const Contrib &c) { rx += c.fx; ry += c.fy; q0 += c.d0; q1 += c.d1; q3 += c.d3; mm += c.w; };
+    // The fan is walked two elements at a time: their dependency chains (loads -> strain -> determinant -> reciprocal -> stress)
+    // are independent, which doubles the instruction-level parallelism of a loop that is otherwise latency bound.
+    int lastk = -1;
+    Nb prev = {make_double2(0, 0), make_double2(0, 0), 0.0};
+    int r = 0;
+    for (; r + 1 < nring; r += 2) {
+        const ushort2 jkA = rjk[r * kPatch + tid], jkB = rjk[(r + 1) * kPatch + tid];
+        const Nb JA = (int)jkA.x == lastk ? prev : load_nb(jkA.x);
+        const Nb KA = load_nb(jkA.y);
+        const Nb JB = jkB.x == jkA.y ? KA : load_nb(jkB.x);
+        const Nb KB = load_nb(jkB.y);
+        const Contrib cA = entry(JA, KA), cB = entry(JB, KB);
+        add(cA); add(cB);
+        prev = KB; lastk = jkB.y;
+    }
+    if (r < nring) {
+        const ushort2 jk = rjk[r * kPatch + tid];
+        const Nb J = (int)jk.x == lastk ? prev : load_nb(jk.x);
+        const Nb K = load_nb(jk.y);
+        add(entry(J, K));
     }
     const double Xi0 = myxy.x, Xi1 = myxy.y;
     double Fx = 0.0, Fy = 0.0;
