@@ -116,7 +116,8 @@ int wcfe_set_profile(wcfe_ctx *c, int on);
 /* test hook: run the general 3-D (node-centric) kernels even when the state is planar */
 int wcfe_set_force_general(wcfe_ctx *c, int on);
 /* out8: planar fast path active (0/1), patch-local elements / elements for cell and substrate (recompute overhead),
- * max halo nodes and max elements per patch for cell and substrate, triangle-bucket capacity */
+ * max halo nodes / max elements per cell patch, max halo nodes per substrate patch, substrate kernel in use (2 k_subs_ring,
+ * 0 k_subs_patch, 1 k_subs_pipe), triangle-bucket capacity */
 int wcfe_get_path_info(wcfe_ctx *c, double *out8);
 int wcfe_get_kernel_ms(wcfe_ctx *c, double *ms8, long long *count8);
 

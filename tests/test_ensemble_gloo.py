@@ -26,7 +26,7 @@ def test_sweep_grid_is_deterministic_and_covers_laws():
     assert a == b and len(a) == 4096
     assert {c["variant"] for c in a} == {"k1", "k31", "kMD"}
     rhos = sorted({c["rho_i_max"] for c in a})
-    assert abs(rhos[0] - 1.0) < 1e-12 and abs(rhos[-1] - 1000.0) < 1e-9
+    assert abs(rhos[0] - 1.0) < 1e-12 and abs(rhos[-1] - 100.0) < 1e-9
     assert len({(c["variant"], c["rho_i_max"], c["seed"]) for c in a}) == 4096
 
 

@@ -499,6 +499,7 @@ int check_device_errors(wcfe_ctx *c) {
     int e = 0;
     CK(cudaMemcpyAsync(&e, c->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (e & ERR_NAN) return fail(c, WCFE_ERR_NUMERIC, "non-finite cell area / centroid: the explicit step went unstable (dt above the stability limit of the stiffest spring?)");
     if (e & ERR_BUCKET_OVERFLOW) return fail(c, WCFE_ERR_CAPACITY, "triangle bucket overflow: more anchors in one substrate triangle than the capacity sized at upload");
     if (e & ERR_REGION) return fail(c, WCFE_ERR_CAPACITY, "an integrin anchor left the padded cell region; re-commit positions to refresh it");
     return WCFE_OK;
@@ -585,8 +586,8 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     }
     { ProfScope ps(c, K_FINISH);
     const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few blocks: the kernel is latency-, not throughput-bound
-    if (c->debug) k_boundary_finish<true><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, dview(cs));
-    else k_boundary_finish<false><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, DebugView{}); }
+    if (c->debug) k_boundary_finish<true><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs));
+    else k_boundary_finish<false><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}); }
     c->launches += 1;
     cs.ea_cur ^= 1;
 subs_half:
@@ -949,7 +950,7 @@ int wcfe_get_path_info(wcfe_ctx *c, double *out8) {
     if (!c || !out8) return WCFE_ERR_ARG;
     out8[0] = use_planar(c) ? 1.0 : 0.0;
     out8[1] = c->s[0].halo_elem_ratio; out8[2] = c->s[1].halo_elem_ratio;
-    out8[3] = c->s[0].max_halo; out8[4] = c->s[0].max_elem; out8[5] = c->s[1].max_halo; out8[6] = c->s[1].max_elem; out8[7] = c->b_cap;
+    out8[3] = c->s[0].max_halo; out8[4] = c->s[0].max_elem; out8[5] = c->s[1].max_halo; out8[6] = c->subs_kernel; out8[7] = c->b_cap;
     return WCFE_OK;
 }
 

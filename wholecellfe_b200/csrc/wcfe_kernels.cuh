@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kBlock) k_cell_node(SurfView s, BoundaryView b
 template <bool DBG>
 __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k, int npart, const double *__restrict__ partials,
                                                           const double *__restrict__ V_in, const double *__restrict__ A_in,
-                                                          double dt, double dt_real, double *__restrict__ diag, DebugView dbg) {
+                                                          double dt, double dt_real, double *__restrict__ diag, int *__restrict__ err, DebugView dbg) {
     __shared__ double sh[4 * 32];
     __shared__ double tot[4];
     double v[4] = {0.0, 0.0, 0.0, 0.0};
@@ -320,7 +320,11 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
     block_reduce4(v, sh);
     if (threadIdx.x == 0) {
         tot[0] = v[0]; tot[1] = v[1] / v[0]; tot[2] = v[2] / v[0]; tot[3] = v[3] / v[0];
-        if (blockIdx.x == 0) for (int q = 0; q < 4; q++) diag[q] = tot[q];
+        if (blockIdx.x == 0) {
+            for (int q = 0; q < 4; q++) diag[q] = tot[q];
+            // NaN/Inf sentinel: the total area and the centroid see every cell node's position once per step
+            if (!(isfinite(tot[0]) && isfinite(tot[1]) && isfinite(tot[2]))) atomicOr(err, ERR_NAN);
+        }
     }
     __syncthreads();
     const double area_tot = tot[0];

@@ -7,10 +7,12 @@ import itertools
 import numpy as np
 
 
-def sweep_grid(n_cells, laws=("k1", "k31", "kMD"), rho_min=1.0, rho_max=1000.0):
+def sweep_grid(n_cells, laws=("k1", "k31", "kMD"), rho_min=1.0, rho_max=100.0):
     """n_cells (variant, rho_i_max, seed) triples: laws x log-spaced ligand densities (rho_i_max, UL:1231) x seeds.
 
-    Deterministic: cell id -> parameters, so every rank can rebuild the table without communication."""
+    Deterministic: cell id -> parameters, so every rank can rebuild the table without communication.  The default range
+    stops at the reference's own rho_i_max = 100: with the example scripts' dt = 0.005 the explicit step is unstable for
+    denser, i.e. stiffer, adhesion (omega^2 ~ kint rho c_C)."""
     n_rho = max(1, int(round((n_cells / len(laws)) ** 0.5)))
     rhos = np.geomspace(rho_min, rho_max, n_rho)
     base = list(itertools.product(laws, rhos))
