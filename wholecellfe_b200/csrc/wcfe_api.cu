@@ -108,6 +108,7 @@ struct wcfe_ctx {
     DevBuf<double> d_partials, d_diag;
     DevBuf<unsigned int> d_tape;
     DevBuf<double> d_drv;                 // scratch of wcfe_driver_velocities
+    DevBuf<double> d_aos;                 // AoS image of one field (or of both position arrays) for host transfers
     size_t tape_cap = 0;
     unsigned int *h_tape = nullptr;       // pinned
     double *h_stage = nullptr; size_t stage_bytes = 0;   // pinned staging for up/downloads
@@ -174,26 +175,30 @@ int ensure_stage(wcfe_ctx *c, size_t bytes) {
     return WCFE_OK;
 }
 
-// AoS host [n*w] -> SoA device [w*np] through the pinned staging buffer
+// AoS host [n*w] <-> SoA device [w*np]: the copy moves the caller's AoS image as it is, the transposition runs on the device
+int ensure_aos(wcfe_ctx *c, size_t count) {
+    if (c->d_aos.n >= count) return WCFE_OK;
+    CK(c->d_aos.alloc(count));
+    return WCFE_OK;
+}
+inline unsigned int aos_grid(size_t items) { return (unsigned int)((items + kBlock - 1) / kBlock); }
 int put_field(wcfe_ctx *c, double *dev, const double *host, int nn, int np, int w) {
-    int rc = ensure_stage(c, sizeof(double) * (size_t)w * np);
+    int rc = ensure_aos(c, (size_t)w * np);
     if (rc) return rc;
-    double *st = c->h_stage;
-    for (int q = 0; q < w; q++) {
-        for (int i = 0; i < nn; i++) st[(size_t)q * np + i] = host[(size_t)i * w + q];
-        for (int i = nn; i < np; i++) st[(size_t)q * np + i] = 0.0;
-    }
-    CK(cudaMemcpyAsync(dev, st, sizeof(double) * (size_t)w * np, cudaMemcpyHostToDevice, c->stream));
+    if (nn > 0) CK(cudaMemcpyAsync(c->d_aos.p, host, sizeof(double) * (size_t)w * nn, cudaMemcpyHostToDevice, c->stream));
+    k_aos_to_soa<<<aos_grid((size_t)w * np), kBlock, 0, c->stream>>>(nn, np, w, c->d_aos.p, dev);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     return WCFE_OK;
 }
 int get_field(wcfe_ctx *c, const double *dev, double *host, int nn, int np, int w) {
-    int rc = ensure_stage(c, sizeof(double) * (size_t)w * np);
+    if (nn <= 0) return WCFE_OK;
+    int rc = ensure_aos(c, (size_t)w * np);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(c->h_stage, dev, sizeof(double) * (size_t)w * np, cudaMemcpyDeviceToHost, c->stream));
+    k_soa_to_aos<<<aos_grid((size_t)w * nn), kBlock, 0, c->stream>>>(nn, np, w, dev, c->d_aos.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, c->d_aos.p, sizeof(double) * (size_t)w * nn, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    const double *st = c->h_stage;
-    for (int q = 0; q < w; q++) for (int i = 0; i < nn; i++) host[(size_t)i * w + q] = st[(size_t)q * np + i];
     return WCFE_OK;
 }
 int fill_field(wcfe_ctx *c, double *dev, int nn, int np, int w, double value) {
@@ -733,7 +738,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();
-    c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release();
+    c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
@@ -1088,21 +1093,26 @@ int wcfe_step_n_roundtrip(wcfe_ctx *c, int n, double dt, double *t_io, long long
     if (n < 0 || !t_io) return WCFE_ERR_ARG;
     CK(cudaSetDevice(c->device));
     Surface &cs = c->s[WCFE_CELL], &ss = c->s[WCFE_SUBS];
-    const size_t bc = sizeof(double) * 3 * cs.np, bs = sizeof(double) * 3 * ss.np;
-    if ((rc = ensure_stage(c, bc + bs + 64))) return rc;
+    // host images in the reference's own layout: x_cell then x_subs as arrays of Vec3d (3 contiguous doubles per node)
+    const size_t nc3 = (size_t)3 * cs.nn, ns3 = (size_t)3 * ss.nn, bytes = sizeof(double) * (nc3 + ns3);
+    if ((rc = ensure_stage(c, bytes + 64))) return rc;
+    if ((rc = ensure_aos(c, nc3 + ns3))) return rc;
     if ((rc = stage_tape(c, n))) return rc;
-    char *hc = (char *)c->h_stage, *hs = hc + bc, *hd = hs + bs;
+    char *hx = (char *)c->h_stage, *hd = hx + bytes;
+    double *dc = c->d_aos.p, *ds = dc + nc3;
     double t = *t_io;
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int q = 0; q < n; q++) {
         k_predict_cell<<<(cs.nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt);
-        c->launches++;
-        // predicted positions to the host integrator, accepted positions back (SoA images; the AoS shuffle is host work)
-        CK(cudaMemcpyAsync(hc, cs.x.p, bc, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(hs, ss.x.p, bs, cudaMemcpyDeviceToHost, c->stream));
+        // predicted positions to the host integrator (El Topo's integrate(), main.cpp:248/:316), accepted positions back
+        k_soa_to_aos<<<aos_grid(nc3), kBlock, 0, c->stream>>>(cs.nn, cs.np, 3, cs.x.p, dc);
+        k_soa_to_aos<<<aos_grid(ns3), kBlock, 0, c->stream>>>(ss.nn, ss.np, 3, ss.x.p, ds);
+        CK(cudaMemcpyAsync(hx, dc, bytes, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));                    // the host integrator would run here
-        CK(cudaMemcpyAsync(cs.x.p, hc, bc, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(ss.x.p, hs, bs, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(dc, hx, bytes, cudaMemcpyHostToDevice, c->stream));
+        k_aos_to_soa<<<aos_grid((size_t)3 * cs.np), kBlock, 0, c->stream>>>(cs.nn, cs.np, 3, dc, cs.x.p);
+        k_aos_to_soa<<<aos_grid((size_t)3 * ss.np), kBlock, 0, c->stream>>>(ss.nn, ss.np, 3, ds, ss.x.p);
+        c->launches += 5;
         const unsigned int *tape = c->d_tape.p ? c->d_tape.p + (size_t)q * cs.nb : nullptr;
         if ((rc = launch_update(c, dt, dt, t, tape, false))) return rc;
         CK(cudaMemcpyAsync(hd, c->d_diag.p, 64, cudaMemcpyDeviceToHost, c->stream));
@@ -1112,8 +1122,8 @@ int wcfe_step_n_roundtrip(wcfe_ctx *c, int n, double dt, double *t_io, long long
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaEventSynchronize(c->ev1));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
-    if (h2d) *h2d = (long long)(bc + bs);
-    if (d2h) *d2h = (long long)(bc + bs + 64);
+    if (h2d) *h2d = (long long)bytes;
+    if (d2h) *d2h = (long long)(bytes + 64);
     *t_io = t; c->t_last = t;
     return check_device_errors(c);
 }

@@ -74,6 +74,20 @@ __global__ void __launch_bounds__(kBlock) k_predict_cell(int nn, int np, double 
     }
 }
 
+// ---- host images: the reference's arrays are AoS (std::vector<Vec3d>, 6-vector strains); the device state is SoA --------------
+__global__ void __launch_bounds__(kBlock) k_aos_to_soa(int nn, int np, int w, const double *__restrict__ aos, double *__restrict__ soa) {
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= (long long)np * w) return;
+    const int i = (int)(idx / w), q = (int)(idx - (long long)i * w);
+    soa[(size_t)q * np + i] = i < nn ? aos[idx] : 0.0;
+}
+__global__ void __launch_bounds__(kBlock) k_soa_to_aos(int nn, int np, int w, const double *__restrict__ soa, double *__restrict__ aos) {
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= (long long)nn * w) return;
+    const int i = (int)(idx / w), q = (int)(idx - (long long)i * w);
+    aos[idx] = soa[(size_t)q * np + i];
+}
+
 // ---- stand-alone drivers for the adapter: host-owned X, V, A in, V_hlf out (UL:103-124 cell, UL:275-345 substrate) -----------
 __global__ void __launch_bounds__(kBlock) k_driver(int surface, int nn, const double *__restrict__ X, const double *__restrict__ V,
                                                    const double *__restrict__ A, double *__restrict__ Vh, Consts k, double dt, double t_tot) {
