@@ -91,6 +91,18 @@ int wcfe_default_params(wcfe_params *p, int variant);
 /* lifetime; `device` is the CUDA ordinal (one context per process per GPU) */
 int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p);
 int wcfe_destroy(wcfe_ctx *c);
+/* Ensembles (the reference runs parameter sweeps as independent processes, s_sim_031021_1.sub): ONE context that
+ * holds `replicas` independent copies of the same cell + substrate pair, params[r] the parameters of replica r (spring law, ligand
+ * density, ... ; ap_rate must be common).  wcfe_upload_mesh initialises every replica alike; wcfe_step_n advances them all in
+ * lockstep with one launch per kernel (gridDim.y = replicas) on the same random-number tape (common random numbers); state
+ * up/downloads, wcfe_set_params, wcfe_get_discrete and wcfe_get_diagnostics address the replica chosen by wcfe_select_replica
+ * (default 0).  The piecewise entry points (predict / commit / update*, round trip, debug capture) are single-replica only and
+ * return WCFE_ERR_UNSUPPORTED on a batched context; so does a non-planar mesh. */
+int wcfe_create_batch(wcfe_ctx **out, int device, const wcfe_params *params, int replicas);
+int wcfe_select_replica(wcfe_ctx *c, int replica);
+int wcfe_replicas(wcfe_ctx *c);
+/* per-replica Philox key (WCFE_RNG_PHILOX only); wcfe_set_rng resets every replica to its common seed */
+int wcfe_set_replica_seed(wcfe_ctx *c, int replica, unsigned int seed);
 int wcfe_set_params(wcfe_ctx *c, const wcfe_params *p);
 /* run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own non-blocking stream;
  * pass cudaStreamLegacy ((cudaStream_t)0x1) to name the legacy default stream explicitly */

@@ -22,7 +22,8 @@ SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_param
            "wcfe_rng_skip", "wcfe_set_profile", "wcfe_get_kernel_ms", "wcfe_set_force_general", "wcfe_get_path_info",
            "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities",
            "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
-           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync"]
+           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync",
+           "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed"]
 
 
 class Params(C.Structure):
@@ -55,6 +56,10 @@ def load():
     L.wcfe_default_params.argtypes = [C.POINTER(Params), C.c_int]
     L.wcfe_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Params)]
     L.wcfe_destroy.argtypes = [vp]
+    L.wcfe_create_batch.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Params), C.c_int]
+    L.wcfe_select_replica.argtypes = [vp, C.c_int]
+    L.wcfe_replicas.argtypes = [vp]
+    L.wcfe_set_replica_seed.argtypes = [vp, C.c_int, C.c_uint]
     L.wcfe_set_params.argtypes = [vp, C.POINTER(Params)]
     L.wcfe_set_stream.argtypes = [vp, vp]
     L.wcfe_last_error.argtypes = [vp]; L.wcfe_last_error.restype = C.c_char_p

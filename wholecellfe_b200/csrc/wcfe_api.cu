@@ -91,6 +91,13 @@ struct wcfe_ctx {
     int device = 0;
     wcfe_params prm;
     Consts k;
+    // ensemble batching: nrep replicas of the same meshes in one context (kernels launched with gridDim.y = nrep); state up/downloads
+    // address replica `sel`.  Every per-replica device array holds nrep consecutive images.
+    int nrep = 1, sel = 0;
+    std::vector<wcfe_params> rprm;        // per-replica parameters (batch mode)
+    DevBuf<Consts> d_kb;                  // their device-side constants
+    DevBuf<unsigned int> d_seeds; bool own_seeds = false;   // per-replica Philox keys (wcfe_set_replica_seed)
+    std::vector<unsigned int> rseed;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Surface s[2];
@@ -152,16 +159,17 @@ int width_of(int field) {
 }
 double *field_dev(wcfe_ctx *c, int surface, int field) {
     Surface &s = c->s[surface];
+    auto sel = [&](DevBuf<double> &b) -> double * { return b.p ? b.p + (b.n / (size_t)c->nrep) * (size_t)c->sel : nullptr; };
     switch (field) {
-    case WCFE_F_X: return s.x.p;
-    case WCFE_F_XPREV: return surface == WCFE_SUBS ? s.x.p : s.X.p;
-    case WCFE_F_V: return s.V.p;
-    case WCFE_F_A: return s.A.p;
-    case WCFE_F_EA: return s.ea[s.ea_cur].p;
-    case WCFE_F_CA: return surface == WCFE_CELL ? s.cA.p : nullptr;
-    case WCFE_F_CB: return surface == WCFE_CELL ? s.cB.p : nullptr;
-    case WCFE_F_CC: return surface == WCFE_CELL ? s.cC.p : nullptr;
-    case WCFE_F_FAU: return surface == WCFE_CELL ? s.fa.p : nullptr;
+    case WCFE_F_X: return sel(s.x);
+    case WCFE_F_XPREV: return surface == WCFE_SUBS ? sel(s.x) : sel(s.X);
+    case WCFE_F_V: return sel(s.V);
+    case WCFE_F_A: return sel(s.A);
+    case WCFE_F_EA: return sel(s.ea[s.ea_cur]);
+    case WCFE_F_CA: return surface == WCFE_CELL ? sel(s.cA) : nullptr;
+    case WCFE_F_CB: return surface == WCFE_CELL ? sel(s.cB) : nullptr;
+    case WCFE_F_CC: return surface == WCFE_CELL ? sel(s.cC) : nullptr;
+    case WCFE_F_FAU: return surface == WCFE_CELL ? sel(s.fa) : nullptr;
     }
     return nullptr;
 }
@@ -206,8 +214,8 @@ int fill_field(wcfe_ctx *c, double *dev, int nn, int np, int w, double value) {
     return put_field(c, dev, h.data(), nn, np, w);
 }
 
-void make_consts(wcfe_ctx *c) {
-    const wcfe_params &p = c->prm; Consts &k = c->k;
+Consts consts_of(const wcfe_params &p) {
+    Consts k;
     k.law = p.law; k.kint_force = p.kint_force; k.kint_bond = p.kint_bond;
     k.mu_cell = p.mu_cell; k.mu_subs = p.mu_subs; k.t_act_rate = p.t_act_rate; k.t_act_max = p.t_act_max; k.t_act_t1 = p.t_act_t1;
     k.thick = p.thick; k.kappa = p.kappa; k.thetag_dot = p.thetag_dot;
@@ -216,7 +224,12 @@ void make_consts(wcfe_ctx *c) {
     k.k_on = p.k_on; k.ka = p.ka; k.kb = p.kb; k.Fa = p.Fa; k.Fb = p.Fb;
     k.pin_limit = p.pin_limit; k.t_i = p.t_i; k.t_f = p.t_f;
     for (int i = 0; i < 6; i++) { k.md_px[i] = p.md_px[i]; k.md_py[i] = p.md_py[i]; k.md_k[i] = p.md_k[i]; }
+    return k;
 }
+void make_consts(wcfe_ctx *c) { c->k = consts_of(c->prm); }
+// selected replica's image inside a per-replica array
+template <class T> T *rsel(wcfe_ctx *c, DevBuf<T> &b) { return b.p ? b.p + (b.n / (size_t)c->nrep) * (size_t)c->sel : nullptr; }
+#define NO_BATCH(c, what) do { if ((c)->nrep > 1) return fail((c), WCFE_ERR_UNSUPPORTED, what ": not available on a batched context (wcfe_create_batch); batches advance with wcfe_step_n only"); } while (0)
 int check_params(wcfe_ctx *c, const wcfe_params *p) {
     if (p->subs_scale != 0.0) return fail(c, WCFE_ERR_UNSUPPORTED, "subs_scale != 0: a moving substrate (main.cpp:299 without the 0*) is not implemented on the GPU path");
     if (p->kappa != 0.5) return fail(c, WCFE_ERR_UNSUPPORTED, "kappa != 0.5: the anisotropic active-stress term (UL:877) needs the centroid of the same step and is not implemented");
@@ -494,16 +507,28 @@ int build_buckets(wcfe_ctx *c) {
     cap = std::min<long long>(std::max<long long>(cap, 8), 1 << 16);
     if ((double)cap * ss.ne * 4.0 > 16e9) return fail(c, WCFE_ERR_CAPACITY, "triangle buckets would exceed 16 GB: substrate far coarser than the cell mesh");
     c->b_cap = (int)cap;
-    CK(c->b_head.alloc(ss.nep)); CK(c->b_items.alloc((size_t)ss.ne * cap));
-    CK(cudaMemset(c->b_head.p, 0, sizeof(unsigned long long) * ss.nep));
+    CK(c->b_head.alloc((size_t)ss.nep * c->nrep)); CK(c->b_items.alloc((size_t)ss.ne * cap * c->nrep));
+    CK(cudaMemset(c->b_head.p, 0, sizeof(unsigned long long) * ss.nep * c->nrep));
     c->epoch = 0;
     return WCFE_OK;
 }
 
+int check_device_errors_bits(wcfe_ctx *c, int e);
 int check_device_errors(wcfe_ctx *c) {
     int e = 0;
-    CK(cudaMemcpyAsync(&e, c->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int> er((size_t)c->nrep, 0);
+    CK(cudaMemcpyAsync(er.data(), c->d_err.p, sizeof(int) * c->nrep, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    int bad = -1;
+    for (int r = 0; r < c->nrep; r++) { e |= er[r]; if (er[r] && bad < 0) bad = r; }
+    if (e && c->nrep > 1) {     // name the first offending replica; the flags stay set (the state is no longer trustworthy)
+        const int rc = check_device_errors_bits(c, e);
+        c->err += " [first flagged replica: " + std::to_string(bad) + "]";
+        return rc;
+    }
+    return check_device_errors_bits(c, e);
+}
+int check_device_errors_bits(wcfe_ctx *c, int e) {
     if (e & ERR_NAN) return fail(c, WCFE_ERR_NUMERIC, "non-finite cell area / centroid: the explicit step went unstable (dt above the stability limit of the stiffest spring?)");
     if (e & ERR_BUCKET_OVERFLOW) return fail(c, WCFE_ERR_CAPACITY, "triangle bucket overflow: more anchors in one substrate triangle than the capacity sized at upload");
     if (e & ERR_REGION) return fail(c, WCFE_ERR_CAPACITY, "an integrin anchor left the padded cell region; re-commit positions to refresh it");
@@ -546,6 +571,16 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     BoundaryView bv = bview(cs);
     const bool planar = use_planar(c);
     int npart = gc;
+    const bool batch = c->nrep > 1;
+    BatchView bt{};
+    if (batch) {
+        if (!planar || !fuse_predict || which != 3 || c->debug || c->subs_kernel != 2)
+            return fail(c, WCFE_ERR_UNSUPPORTED, "batched contexts run the fused planar step only (flat meshes, wcfe_step_n, no debug capture)");
+        const size_t R = (size_t)c->nrep;
+        bt.k = c->d_kb.p; bt.seed = (c->own_seeds && c->rng_mode == WCFE_RNG_PHILOX) ? c->d_seeds.p : nullptr; bt.flags = (long long)(c->d_flags.n / R); bt.partials = (long long)(c->d_partials.n / R); bt.bnd = (long long)(cs.d_bnd_buf.n / R);
+        bt.head = (long long)(c->b_head.n / R); bt.items = (long long)(c->b_items.n / R);
+    }
+    const unsigned int R = (unsigned int)c->nrep;
     const double *v_old = cs.V.p, *a_old = cs.A.p;      // general path: V, A are updated in place
     if (!(which & 1)) goto subs_half;
     if (planar) {
@@ -560,13 +595,16 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         a.d_ap_fire = c->d_ap_fire.p; a.err = c->d_err.p; a.debug = c->debug;
         const size_t smem = patch_smem_bytes(7, 9, cs.max_halo, cs.max_elem, cs.stride);
         npart = cs.npatch;
-        if (fuse_predict) {
-            if (c->debug) k_cell_patch<true, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, dview(cs));
-            else k_cell_patch<true, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{});
+        if (batch) {
+            k_cell_patch<true, false, true><<<dim3(cs.npatch, R), kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt);
+            std::swap(cs.x.p, cs.X.p);
+        } else if (fuse_predict) {
+            if (c->debug) k_cell_patch<true, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, dview(cs), bt);
+            else k_cell_patch<true, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt);
             std::swap(cs.x.p, cs.X.p);      // the buffer just read holds X_t, the one just written x_{t+dt}
         } else {
-            if (c->debug) k_cell_patch<false, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, cs.V2.p, cs.A2.p, dview(cs));
-            else k_cell_patch<false, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, cs.V2.p, cs.A2.p, DebugView{});
+            if (c->debug) k_cell_patch<false, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, cs.V2.p, cs.A2.p, dview(cs), bt);
+            else k_cell_patch<false, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, nullptr, nullptr, cs.V2.p, cs.A2.p, DebugView{}, bt);
         }
         // V, A were written to the second buffers (neighbouring patches read the old ones for their halo predictor): swap, so
         // that cs.V / cs.A are the new state and cs.V2 / cs.A2 hold the start-of-step values k_boundary_finish still needs
@@ -591,8 +629,9 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     }
     { ProfScope ps(c, K_FINISH);
     const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few blocks: the kernel is latency-, not throughput-bound
-    if (c->debug) k_boundary_finish<true><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs));
-    else k_boundary_finish<false><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}); }
+    if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt);
+    else if (c->debug) k_boundary_finish<true><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt);
+    else k_boundary_finish<false><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt); }
     c->launches += 1;
     cs.ea_cur ^= 1;
 subs_half:
@@ -603,8 +642,9 @@ subs_half:
         ProfScope ps(c, K_SUBS);
         const size_t smem = ring_smem_bytes(ss.max_halo, ss.ring_stride);
         PatchView pvs = pview(ss);
-        if (c->debug) k_subs_ring<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
-        else k_subs_ring<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+        if (batch) k_subs_ring<false, true><<<dim3(ss.npatch, R), kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt);
+        else if (c->debug) k_subs_ring<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss), bt);
+        else k_subs_ring<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt);
     } else if (planar && c->use_pipe) {
         // persistent, software-pipelined substrate kernel: grid = SMs x 3 resident CTAs
         ProfScope ps(c, K_SUBS);
@@ -651,6 +691,26 @@ int stage_tape(wcfe_ctx *c, int n_steps) {
     return WCFE_OK;
 }
 
+// batch mode: copy replica 0's freshly initialised image of every per-replica array of this surface to the other replicas
+template <class T> int replicate_buf(wcfe_ctx *c, DevBuf<T> &b) {
+    if (!b.p) return WCFE_OK;
+    const size_t per = b.n / (size_t)c->nrep;
+    for (int r = 1; r < c->nrep; r++) CK(cudaMemcpyAsync(b.p + per * r, b.p, sizeof(T) * per, cudaMemcpyDeviceToDevice, c->stream));
+    return WCFE_OK;
+}
+int replicate_state(wcfe_ctx *c, int surface) {
+    Surface &s = c->s[surface];
+    int rc;
+    DevBuf<double> *d[] = {&s.x, &s.X, &s.V, &s.A, &s.V2, &s.A2, &s.ea[0], &s.ea[1], &s.cA, &s.cB, &s.cC, &s.fa, &s.asum};
+    for (auto *b : d) if ((rc = replicate_buf(c, *b))) return rc;
+    if (surface == WCFE_CELL) {
+        DevBuf<int> *di[] = {&c->d_flags, &c->d_loc_bond, &c->d_loc_cnt, &c->d_loc_first, &c->d_ap_fire};
+        for (auto *b : di) if ((rc = replicate_buf(c, *b))) return rc;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return WCFE_OK;
+}
+
 int ready(wcfe_ctx *c) {
     if (!c) return WCFE_ERR_ARG;
     if (!c->s[0].nn || !c->s[1].nn) return fail(c, WCFE_ERR_ARG, "upload both the cell and the substrate mesh first");
@@ -684,8 +744,8 @@ int wcfe_default_params(wcfe_params *p, int variant) {
     return WCFE_OK;
 }
 
-int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p) {
-    if (!out || !p) return WCFE_ERR_ARG;
+static int create_impl(wcfe_ctx **out, int device, const wcfe_params *p, int replicas) {
+    if (!out || !p || replicas < 1) return WCFE_ERR_ARG;
     *out = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -695,9 +755,13 @@ int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p) {
     }
     wcfe_ctx *c = new wcfe_ctx;
     c->device = device;
-    int rc = check_params(c, p);
+    int rc = WCFE_OK;
+    for (int r = 0; r < replicas && !rc; r++) rc = check_params(c, p + r);
+    if (!rc && replicas > 1) for (int r = 1; r < replicas && !rc; r++)
+        if (p[r].ap_rate != p[0].ap_rate) rc = fail(c, WCFE_ERR_UNSUPPORTED, "batched replicas must share ap_rate (the protrusion threshold is one host-evaluated number per launch)");
     if (rc) { g_create_err = c->err; delete c; return rc; }
     c->prm = *p; make_consts(c);
+    c->nrep = replicas;
     auto bail = [&](const char *what, cudaError_t err) { g_create_err = std::string(what) + ": " + cudaGetErrorString(err); cudaGetLastError(); delete c; return WCFE_ERR_CUDA; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
@@ -710,18 +774,35 @@ int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p) {
         if (const char *e = std::getenv("WCFE_SUBS_PIPE")) { c->use_pipe = std::atoi(e); if (c->use_pipe) c->subs_kernel = 1; }
         if (const char *e = std::getenv("WCFE_SUBS_KERNEL")) c->subs_kernel = std::atoi(e);
         const void *pk[] = {(const void *)k_subs_ring<false>, (const void *)k_subs_ring<true>, (const void *)k_subs_pipe<false>, (const void *)k_subs_pipe<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
-                            (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>};
+                            (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>,
+                            (const void *)k_cell_patch<true, false, true>, (const void *)k_subs_ring<false, true>};
         for (const void *f : pk) {
             // 227 KB is the per-CTA limit including the kernels' small static arrays
             if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kPatchSmemMax)) != cudaSuccess) return bail("cudaFuncSetAttribute(max dynamic smem)", e);
             if ((e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return bail("cudaFuncSetAttribute(carveout)", e);
         }
     }
-    if ((e = c->d_err.alloc(1)) != cudaSuccess || (e = c->d_diag.alloc(8)) != cudaSuccess) return bail("cudaMalloc", e);
-    cudaMemset(c->d_err.p, 0, sizeof(int)); cudaMemset(c->d_diag.p, 0, 8 * sizeof(double));
+    if ((e = c->d_err.alloc((size_t)replicas)) != cudaSuccess || (e = c->d_diag.alloc((size_t)8 * replicas)) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(c->d_err.p, 0, sizeof(int) * replicas); cudaMemset(c->d_diag.p, 0, 8 * sizeof(double) * replicas);
+    if (replicas > 1) {
+        c->rprm.assign(p, p + replicas);
+        std::vector<Consts> kb((size_t)replicas);
+        for (int r = 0; r < replicas; r++) kb[r] = consts_of(p[r]);
+        if ((e = c->d_kb.alloc((size_t)replicas)) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMemcpy(c->d_kb.p, kb.data(), sizeof(Consts) * replicas, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+    }
     *out = c;
     return WCFE_OK;
 }
+int wcfe_create(wcfe_ctx **out, int device, const wcfe_params *p) { return create_impl(out, device, p, 1); }
+int wcfe_create_batch(wcfe_ctx **out, int device, const wcfe_params *params, int replicas) { return create_impl(out, device, params, replicas); }
+int wcfe_select_replica(wcfe_ctx *c, int replica) {
+    if (!c) return WCFE_ERR_ARG;
+    if (replica < 0 || replica >= c->nrep) return fail(c, WCFE_ERR_ARG, "select_replica: index outside [0, replicas)");
+    c->sel = replica;
+    return WCFE_OK;
+}
+int wcfe_replicas(wcfe_ctx *c) { return c ? c->nrep : 0; }
 
 int wcfe_destroy(wcfe_ctx *c) {
     if (!c) return WCFE_ERR_ARG;
@@ -738,7 +819,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();
-    c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
+    c->d_kb.release(); c->d_seeds.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
@@ -753,6 +834,16 @@ int wcfe_set_params(wcfe_ctx *c, const wcfe_params *p) {
     if (!c || !p) return WCFE_ERR_ARG;
     int rc = check_params(c, p);
     if (rc) return rc;
+    if (c->nrep > 1) {          // batched context: the selected replica's parameters
+        if (p->ap_rate != c->rprm[0].ap_rate) return fail(c, WCFE_ERR_UNSUPPORTED, "batched replicas must share ap_rate");
+        c->rprm[c->sel] = *p;
+        const Consts k = consts_of(*p);
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemcpyAsync(c->d_kb.p + c->sel, &k, sizeof(Consts), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->sel == 0) { c->prm = *p; make_consts(c); }
+        return WCFE_OK;
+    }
     c->prm = *p; make_consts(c);
     return WCFE_OK;
 }
@@ -820,8 +911,8 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
         CK(s.d_ring_ptr.alloc((size_t)nn + 1)); CK(cudaMemcpy(s.d_ring_ptr.p, s.ring_ptr.data(), sizeof(int) * ((size_t)nn + 1), cudaMemcpyHostToDevice));
         CK(s.d_ring.alloc(s.ring.size())); CK(cudaMemcpy(s.d_ring.p, s.ring.data(), sizeof(int) * s.ring.size(), cudaMemcpyHostToDevice));
     }
-    const size_t np = s.np;
-    CK(s.x.alloc(3 * np)); CK(s.V.alloc(3 * np)); CK(s.A.alloc(3 * np)); CK(s.ea[0].alloc(6 * np)); CK(s.ea[1].alloc(6 * np));
+    const size_t np = s.np, R = (size_t)c->nrep;     // per-replica arrays hold R images; replica 0 is initialised here and copied below
+    CK(s.x.alloc(3 * np * R)); CK(s.V.alloc(3 * np * R)); CK(s.A.alloc(3 * np * R)); CK(s.ea[0].alloc(6 * np * R)); CK(s.ea[1].alloc(6 * np * R));
     s.ea_cur = 0;
     int rc;
     std::vector<int> cand;
@@ -831,10 +922,10 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
     CK(cudaMemset(s.ea[0].p, 0, sizeof(double) * 6 * np)); CK(cudaMemset(s.ea[1].p, 0, sizeof(double) * 6 * np));
     s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
     if (surface == WCFE_CELL) {
-        CK(s.X.alloc(3 * np)); CK(cudaMemcpy(s.X.p, s.x.p, sizeof(double) * 3 * np, cudaMemcpyDeviceToDevice));
-        CK(s.V2.alloc(3 * np)); CK(s.A2.alloc(3 * np));
+        CK(s.X.alloc(3 * np * R)); CK(cudaMemcpy(s.X.p, s.x.p, sizeof(double) * 3 * np, cudaMemcpyDeviceToDevice));
+        CK(s.V2.alloc(3 * np * R)); CK(s.A2.alloc(3 * np * R));
         CK(cudaMemset(s.V2.p, 0, sizeof(double) * 3 * np)); CK(cudaMemset(s.A2.p, 0, sizeof(double) * 3 * np));
-        CK(s.cA.alloc(np)); CK(s.cB.alloc(np)); CK(s.cC.alloc(np)); CK(s.fa.alloc(3 * np)); CK(s.asum.alloc(np));
+        CK(s.cA.alloc(np * R)); CK(s.cB.alloc(np * R)); CK(s.cC.alloc(np * R)); CK(s.fa.alloc(3 * np * R)); CK(s.asum.alloc(np * R));
         if ((rc = fill_field(c, s.cA.p, nn, s.np, 1, c->prm.c_A_init))) return rc;        // main.cpp:672
         CK(cudaMemset(s.cB.p, 0, sizeof(double) * np)); CK(cudaMemset(s.cC.p, 0, sizeof(double) * np));
         CK(cudaMemset(s.fa.p, 0, sizeof(double) * 3 * np)); CK(cudaMemset(s.asum.p, 0, sizeof(double) * np));
@@ -865,11 +956,12 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
         CK(cudaMemcpy(s.d_bnd_index.p, index.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(s.d_cand_ptr.p, cand_ptr.data(), sizeof(int) * cand_ptr.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(s.d_cand.p, cand.data(), sizeof(int) * cand.size(), cudaMemcpyHostToDevice));
-        CK(s.d_bnd_buf.alloc((size_t)16 * std::max(1, s.nb)));
-        CK(c->d_flags.alloc(nn)); CK(c->d_loc_bond.alloc(nn)); CK(c->d_loc_cnt.alloc(nn)); CK(c->d_loc_first.alloc(nn)); CK(c->d_ap_fire.alloc(nn));
+        CK(s.d_bnd_buf.alloc((size_t)16 * std::max(1, s.nb) * R));
+        CK(cudaMemset(s.d_bnd_buf.p, 0, sizeof(double) * s.d_bnd_buf.n));
+        CK(c->d_flags.alloc(nn * R)); CK(c->d_loc_bond.alloc(nn * R)); CK(c->d_loc_cnt.alloc(nn * R)); CK(c->d_loc_first.alloc(nn * R)); CK(c->d_ap_fire.alloc(nn * R));
         CK(cudaMemset(c->d_flags.p, 0, sizeof(int) * nn)); CK(cudaMemset(c->d_loc_bond.p, 0xff, sizeof(int) * nn));
         CK(cudaMemset(c->d_loc_cnt.p, 0, sizeof(int) * nn)); CK(cudaMemset(c->d_loc_first.p, 0xff, sizeof(int) * nn)); CK(cudaMemset(c->d_ap_fire.p, 0, sizeof(int) * nn));
-        CK(c->d_partials.alloc((size_t)4 * ((nn + kBlock - 1) / kBlock + 1)));
+        CK(c->d_partials.alloc((size_t)4 * ((nn + kBlock - 1) / kBlock + 1) * R));
         update_box(c, xyz, nn);
     } else {
         s.X.release();
@@ -879,6 +971,7 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
     if ((rc = build_buckets(c))) return rc;
     if (c->debug) { if ((rc = alloc_debug(c, surface))) return rc; }
     c->have_predict[surface] = false;
+    if (c->nrep > 1 && (rc = replicate_state(c, surface))) return rc;
     return WCFE_OK;
 }
 
@@ -902,9 +995,9 @@ int wcfe_upload_state(wcfe_ctx *c, int surface, int field, const double *host) {
     // the planar fast path needs every out-of-plane word to be exactly zero; once that is violated it stays off
     if (field == WCFE_F_X || field == WCFE_F_XPREV || field == WCFE_F_V || field == WCFE_F_A || field == WCFE_F_FAU) { for (int i = 0; i < s.nn && s.planar; i++) if (host[3 * (size_t)i + 2] != 0.0) s.planar = false; }
     if (field == WCFE_F_EA) { for (int i = 0; i < s.nn && s.planar; i++) if (host[6 * (size_t)i + 2] != 0.0 || host[6 * (size_t)i + 4] != 0.0 || host[6 * (size_t)i + 5] != 0.0) s.planar = false; }
-    if (field == WCFE_F_EA && s.planar) CK(cudaMemsetAsync(s.ea[s.ea_cur ^ 1].p, 0, sizeof(double) * 6 * s.np, c->stream));
+    if (field == WCFE_F_EA && s.planar) CK(cudaMemsetAsync(rsel(c, s.ea[s.ea_cur ^ 1]), 0, sizeof(double) * 6 * s.np, c->stream));
     if (field == WCFE_F_X) {
-        if (surface == WCFE_CELL) { CK(cudaMemcpyAsync(s.X.p, s.x.p, sizeof(double) * 3 * s.np, cudaMemcpyDeviceToDevice, c->stream)); update_box(c, host, s.nn); }
+        if (surface == WCFE_CELL) { CK(cudaMemcpyAsync(rsel(c, s.X), rsel(c, s.x), sizeof(double) * 3 * s.np, cudaMemcpyDeviceToDevice, c->stream)); update_box(c, host, s.nn); }
         else { rc = build_grid(c, host); if (rc) return rc; }
     }
     return WCFE_OK;
@@ -923,6 +1016,21 @@ int wcfe_download_state(wcfe_ctx *c, int surface, int field, double *host) {
 int wcfe_set_rng(wcfe_ctx *c, int mode, unsigned int seed) {
     if (!c || (mode != WCFE_RNG_GLIBC_REPLAY && mode != WCFE_RNG_PHILOX)) return WCFE_ERR_ARG;
     c->rng_mode = mode; c->seed = seed; c->rng.seed(seed); c->step = 0;
+    c->own_seeds = false;      // batched contexts: back to common random numbers until wcfe_set_replica_seed says otherwise
+    return WCFE_OK;
+}
+
+int wcfe_set_replica_seed(wcfe_ctx *c, int replica, unsigned int seed) {
+    if (!c) return WCFE_ERR_ARG;
+    if (replica < 0 || replica >= c->nrep) return fail(c, WCFE_ERR_ARG, "set_replica_seed: index outside [0, replicas)");
+    if (c->rng_mode != WCFE_RNG_PHILOX) return fail(c, WCFE_ERR_UNSUPPORTED, "per-replica seeds need the counter-based generator (WCFE_RNG_PHILOX); the glibc replay tape is shared by all replicas");
+    if (c->nrep == 1) { c->seed = seed; return WCFE_OK; }
+    CK(cudaSetDevice(c->device));
+    if (!c->own_seeds) { c->rseed.assign((size_t)c->nrep, c->seed); c->own_seeds = true; }
+    c->rseed[replica] = seed;
+    if (!c->d_seeds.p) CK(c->d_seeds.alloc((size_t)c->nrep));
+    CK(cudaMemcpyAsync(c->d_seeds.p, c->rseed.data(), sizeof(unsigned int) * c->nrep, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return WCFE_OK;
 }
 
@@ -947,6 +1055,7 @@ int wcfe_get_kernel_ms(wcfe_ctx *c, double *ms8, long long *count8) {
 
 int wcfe_set_force_general(wcfe_ctx *c, int on) {
     if (!c) return WCFE_ERR_ARG;
+    if (on) NO_BATCH(c, "set_force_general");
     c->force_general = on ? 1 : 0;
     return WCFE_OK;
 }
@@ -961,6 +1070,7 @@ int wcfe_get_path_info(wcfe_ctx *c, double *out8) {
 
 int wcfe_set_debug(wcfe_ctx *c, int on) {
     if (!c) return WCFE_ERR_ARG;
+    if (on) NO_BATCH(c, "set_debug");
     c->debug = on ? 1 : 0;
     if (on) { int rc; if ((rc = alloc_debug(c, 0))) return rc; if ((rc = alloc_debug(c, 1))) return rc; }
     return WCFE_OK;
@@ -971,6 +1081,7 @@ int wcfe_predict(wcfe_ctx *c, int surface, double dt, double t_curr, double *xyz
     int rc = ready(c);
     if (rc) return rc;
     if (surface < 0 || surface > 1) return WCFE_ERR_ARG;
+    NO_BATCH(c, "predict");
     CK(cudaSetDevice(c->device));
     Surface &s = c->s[surface];
     if (surface == WCFE_CELL) {
@@ -988,6 +1099,7 @@ int wcfe_commit(wcfe_ctx *c, int surface, const double *xyz_final) {
     int rc = ready(c);
     if (rc) return rc;
     if (surface < 0 || surface > 1) return WCFE_ERR_ARG;
+    NO_BATCH(c, "commit");
     if (!c->have_predict[surface]) return fail(c, WCFE_ERR_ARG, "commit without predict");
     if (!xyz_final) return WCFE_OK;
     CK(cudaSetDevice(c->device));
@@ -1003,6 +1115,7 @@ int wcfe_commit(wcfe_ctx *c, int surface, const double *xyz_final) {
 static int update_impl(wcfe_ctx *c, double dt_req, double dt_real, double t_curr, int which) {
     int rc = ready(c);
     if (rc) return rc;
+    NO_BATCH(c, "update");
     CK(cudaSetDevice(c->device));
     if (which & 1) {
         if (!c->have_predict[WCFE_CELL]) return fail(c, WCFE_ERR_ARG, "update without predict(cell) (or upload of x and X_prev)");
@@ -1090,6 +1203,7 @@ int wcfe_step_n_async(wcfe_ctx *c, int n, double dt, double *t_io) {
 int wcfe_step_n_roundtrip(wcfe_ctx *c, int n, double dt, double *t_io, long long *h2d, long long *d2h) {
     int rc = ready(c);
     if (rc) return rc;
+    NO_BATCH(c, "step_n_roundtrip");
     if (n < 0 || !t_io) return WCFE_ERR_ARG;
     CK(cudaSetDevice(c->device));
     Surface &cs = c->s[WCFE_CELL], &ss = c->s[WCFE_SUBS];
@@ -1131,7 +1245,7 @@ int wcfe_step_n_roundtrip(wcfe_ctx *c, int n, double dt, double *t_io, long long
 int wcfe_get_diagnostics(wcfe_ctx *c, double *out8) {
     if (!c || !out8) return WCFE_ERR_ARG;
     CK(cudaSetDevice(c->device));
-    CK(cudaMemcpyAsync(out8, c->d_diag.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out8, c->d_diag.p + (size_t)8 * c->sel, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     out8[4] = out8[5] = 0.0;
     if (c->debug) {   // |Res| norms from the captured residuals
@@ -1154,11 +1268,11 @@ int wcfe_get_discrete(wcfe_ctx *c, int which, int *out) {
     const int nn = c->s[0].nn;
     const int *src = nullptr;
     switch (which) {
-    case WCFE_D_LOC_BOND: src = c->d_loc_bond.p; break;
-    case WCFE_D_LOC_FORCE_CNT: src = c->d_loc_cnt.p; break;
-    case WCFE_D_LOC_FORCE_FIRST: src = c->d_loc_first.p; break;
-    case WCFE_D_AP_FIRE: src = c->d_ap_fire.p; break;
-    case WCFE_D_FA_RESET: case WCFE_D_CC_CLAMP: src = c->d_flags.p; break;
+    case WCFE_D_LOC_BOND: src = rsel(c, c->d_loc_bond); break;
+    case WCFE_D_LOC_FORCE_CNT: src = rsel(c, c->d_loc_cnt); break;
+    case WCFE_D_LOC_FORCE_FIRST: src = rsel(c, c->d_loc_first); break;
+    case WCFE_D_AP_FIRE: src = rsel(c, c->d_ap_fire); break;
+    case WCFE_D_FA_RESET: case WCFE_D_CC_CLAMP: src = rsel(c, c->d_flags); break;
     default: return WCFE_ERR_ARG;
     }
     CK(cudaSetDevice(c->device));

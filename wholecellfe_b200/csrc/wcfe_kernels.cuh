@@ -55,6 +55,22 @@ struct DebugView {           // optional force-field capture (parity gate on nod
     double *res, *f_fa, *f_ap, *f_bend, *f_area, *mm, *res_ea;   // cell or substrate set
 };
 
+// Ensembles: R independent replicas of the same two meshes advance in lockstep in ONE launch per kernel
+// (gridDim.y = R).  Connectivity, patch descriptors and boundary tables are shared; every state array holds R consecutive
+// images, and a CTA shifts its views to replica blockIdx.y before it starts.  Per-replica constants (spring law, ligand
+// density, ...) come from BatchView::k instead of the by-value kernel parameter.
+struct BatchView {
+    const Consts *k;             // [R]
+    const unsigned int *seed;    // [R] Philox keys, or nullptr: every replica draws the same numbers (common random numbers)
+    long long flags, partials, bnd, head, items;   // per-replica element counts: int flag arrays, area partials, boundary buffer, bucket heads / items
+};
+__device__ __forceinline__ void batch_shift(SurfView &s, size_t r) {
+    const size_t n = (size_t)s.np * r;
+    s.x += 3 * n; s.X += 3 * n; s.V += 3 * n; s.A += 3 * n; s.ea_in += 6 * n; s.ea_out += 6 * n;
+    if (s.cC) { s.cC += n; s.fa += 3 * n; s.asum += n; }
+}
+__device__ __forceinline__ void batch_shift(BucketView &bk, const BatchView &bt, size_t r) { bk.head += bt.head * r; bk.items += bt.items * r; }
+
 enum : int { ERR_BUCKET_OVERFLOW = 1, ERR_LOC_OVERFLOW = 2, ERR_NAN = 4, ERR_REGION = 8 };
 
 // ---- predictor: driverVelocities_Explicit + inline predictor (UL:103-124, main.cpp:224-242) ---------------
@@ -321,12 +337,19 @@ __global__ void __launch_bounds__(kBlock) k_cell_node(SurfView s, BoundaryView b
 // ---- total area / centroid (UL:1641-1667) + area-constraint force and update of the boundary vertices (UL:1670-1763) --
 // every block reduces the partial sums itself, in the same fixed order (bit-reproducible run to run and identical across
 // blocks), then finishes its share of the boundary vertices; block 0 publishes the diagnostics
-template <bool DBG>
-__global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k, int npart, const double *__restrict__ partials,
+template <bool DBG, bool BATCH = false>
+__global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k_, int npart, const double *__restrict__ partials,
                                                           const double *__restrict__ V_in, const double *__restrict__ A_in,
-                                                          double dt, double dt_real, double *__restrict__ diag, int *__restrict__ err, DebugView dbg) {
+                                                          double dt, double dt_real, double *__restrict__ diag, int *__restrict__ err, DebugView dbg,
+                                                          BatchView bt) {
     __shared__ double sh[4 * 32];
     __shared__ double tot[4];
+    const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
+    if (BATCH) {
+        const size_t r = blockIdx.y;
+        batch_shift(s, r);
+        b.buf += bt.bnd * r; partials += bt.partials * r; V_in += 3 * (size_t)s.np * r; A_in += 3 * (size_t)s.np * r; diag += 8 * r; err += r;
+    }
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     // strided accumulation in a fixed order, then a fixed tree
     for (int p = threadIdx.x; p < npart; p += blockDim.x)

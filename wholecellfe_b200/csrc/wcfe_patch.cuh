@@ -260,10 +260,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
 #ifndef WCFE_RING_MINBLK
 #define WCFE_RING_MINBLK 5
 #endif
-template <bool DBG>
-__global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
-                                                         double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg) {
+template <bool DBG, bool BATCH = false>
+__global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k_, double dt, double dt_real,
+                                                         double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg, BatchView bt) {
     extern __shared__ __align__(128) unsigned char smraw[];
+    const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
+    if (BATCH) { const size_t r = blockIdx.y; batch_shift(s, r); batch_shift(c, r); batch_shift(bk, bt, r); }
     const int NL = kPatch + pv.max_halo;
     unsigned long long *bar = (unsigned long long *)smraw;
     unsigned char *sblob = smraw + 16;
@@ -595,12 +597,22 @@ struct CellStepArgs {
     int debug;
 };
 
-template <bool PREDICT, bool DBG>
-__global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, PatchView pv, SurfView sub, GridView g, BucketView bk, BoundaryView b, Consts k,
+template <bool PREDICT, bool DBG, bool BATCH = false>
+__global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, PatchView pv, SurfView sub, GridView g, BucketView bk, BoundaryView b, Consts k_,
                                                        CellStepArgs a, const double *__restrict__ x_in, double *__restrict__ x_out,
-                                                       double *__restrict__ V_out, double *__restrict__ A_out, DebugView dbg) {
+                                                       double *__restrict__ V_out, double *__restrict__ A_out, DebugView dbg, BatchView bt) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ double shred[4 * 32];
+    const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
+    if (BATCH) {
+        const size_t r = blockIdx.y, n3 = 3 * (size_t)s.np * r;
+        batch_shift(s, r); batch_shift(sub, r); batch_shift(bk, bt, r);
+        b.buf += bt.bnd * r; a.partials += bt.partials * r;
+        a.d_flags += bt.flags * r; a.d_loc_bond += bt.flags * r; a.d_loc_cnt += bt.flags * r; a.d_loc_first += bt.flags * r; a.d_ap_fire += bt.flags * r; a.err += r;
+        if (bt.seed) a.seed = bt.seed[r];
+        if (PREDICT) { x_in += n3; x_out += n3; }
+        V_out += n3; A_out += n3;
+    }
     const int NL = kPatch + pv.max_halo, EM = pv.max_elem;
     unsigned long long *bar = (unsigned long long *)smraw;
     unsigned char *sblob = smraw + 16;

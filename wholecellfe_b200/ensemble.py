@@ -58,24 +58,56 @@ def gather_counts(count, dist=None, device=None):
 
 
 class EnsembleRunner:
-    """This rank's shard of an ensemble: one device context (own CUDA stream) per cell, stepped asynchronously so that the
-    small kernels of different cells overlap on the GPU.  Cells never communicate."""
+    """This rank's shard of an ensemble.  Cells never communicate.
 
-    def __init__(self, cells, cell_mesh, subs_mesh, device=0, rng_mode=1):
+    mode "batch" (default): the cells share one batched device context per group -- every kernel of the step is launched once
+    with gridDim.y = number of cells (wcfe_create_batch), so that thousands of config-1-size problems fill the GPU instead of
+    queueing as tiny launches.  With the counter-based generator each cell keeps its own seed inside one group; with the glibc
+    replay tape the cells are grouped by seed (one tape per context).
+    mode "streams": one context and CUDA stream per cell, stepped asynchronously (the pre-batching path, kept for comparison)."""
+
+    def __init__(self, cells, cell_mesh, subs_mesh, device=0, rng_mode=1, mode="batch"):
         from . import ulstep
-        from ._lib import CELL, SUBS
+        from ._lib import CELL, SUBS, RNG_PHILOX
         self.cells = list(cells)
-        self.sims = []
+        self.mode = mode
+        self.sims = []          # contexts
+        self.where = []         # cell -> (context index, replica index)
         xc, tc = cell_mesh
         xs, ts = subs_mesh
-        for c in self.cells:
+
+        def params_of(c):
             p = ulstep.default_params(c["variant"])
             p.rho_i_max = c["rho_i_max"]                      # ligand density (UL:1231)
-            sim = ulstep.ULSim(c["variant"], device=device, params=p)
-            sim.upload_mesh(CELL, xc, tc)
-            sim.upload_mesh(SUBS, xs, ts)
-            sim.set_rng(rng_mode, c["seed"])
-            self.sims.append(sim)
+            return p
+
+        if mode == "streams":
+            for c in self.cells:
+                sim = ulstep.ULSim(c["variant"], device=device, params=params_of(c))
+                sim.upload_mesh(CELL, xc, tc)
+                sim.upload_mesh(SUBS, xs, ts)
+                sim.set_rng(rng_mode, c["seed"])
+                self.where.append((len(self.sims), 0))
+                self.sims.append(sim)
+        elif mode == "batch":
+            groups = {}
+            for i, c in enumerate(self.cells):
+                groups.setdefault(0 if rng_mode == RNG_PHILOX else c["seed"], []).append(i)
+            self.where = [None] * len(self.cells)
+            for key in sorted(groups):
+                ids = groups[key]
+                sim = ulstep.ULSim(self.cells[ids[0]]["variant"], device=device, batch=[params_of(self.cells[i]) for i in ids])
+                sim.upload_mesh(CELL, xc, tc)
+                sim.upload_mesh(SUBS, xs, ts)
+                sim.set_rng(rng_mode, self.cells[ids[0]]["seed"])
+                if rng_mode == RNG_PHILOX and len(ids) > 1:
+                    for r, i in enumerate(ids):
+                        sim.set_replica_seed(r, self.cells[i]["seed"])
+                for r, i in enumerate(ids):
+                    self.where[i] = (len(self.sims), r)
+                self.sims.append(sim)
+        else:
+            raise ValueError("mode must be 'batch' or 'streams'")
         self.t = [0.0] * len(self.sims)
         self.elements_per_cell = len(tc) + len(ts)
 
@@ -89,6 +121,21 @@ class EnsembleRunner:
             done += m
         for sim in self.sims:
             sim.sync()
+
+    def get(self, cell_index, surface, field):
+        """State of one cell of the shard."""
+        k, r = self.where[cell_index]
+        sim = self.sims[k]
+        if sim.replicas > 1:
+            sim.select(r)
+        return sim.get(surface, field)
+
+    def diagnostics(self, cell_index):
+        k, r = self.where[cell_index]
+        sim = self.sims[k]
+        if sim.replicas > 1:
+            sim.select(r)
+        return sim.diagnostics()
 
     def close(self):
         for sim in self.sims:

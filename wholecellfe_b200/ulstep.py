@@ -30,12 +30,20 @@ def _d(a):
 
 
 class ULSim:
-    def __init__(self, variant="k1", device=0, params=None, stream=None):
+    def __init__(self, variant="k1", device=0, params=None, stream=None, batch=None):
+        """batch: a list of Params -> one batched context holding len(batch) independent replicas (wcfe_create_batch)."""
         self.L = B.load()
         self.variant = variant
-        self.params = params if params is not None else default_params(variant)
         self.h = C.c_void_p()
-        rc = self.L.wcfe_create(C.byref(self.h), device, C.byref(self.params))
+        if batch is not None:
+            arr = (B.Params * len(batch))(*batch)
+            self.params = arr[0]
+            self.replicas = len(batch)
+            rc = self.L.wcfe_create_batch(C.byref(self.h), device, arr, len(batch))
+        else:
+            self.params = params if params is not None else default_params(variant)
+            self.replicas = 1
+            rc = self.L.wcfe_create(C.byref(self.h), device, C.byref(self.params))
         if rc:
             self.h = None
             why = self.L.wcfe_last_error(None).decode()
@@ -58,6 +66,13 @@ class ULSim:
     def _ck(self, rc):
         if rc:
             raise WcfeError(rc, self.L.wcfe_last_error(self.h).decode())
+
+    def select(self, replica):
+        """Batched context: the replica that set/get/params/discrete/diagnostics address from now on."""
+        self._ck(self.L.wcfe_select_replica(self.h, int(replica)))
+
+    def set_replica_seed(self, replica, seed):
+        self._ck(self.L.wcfe_set_replica_seed(self.h, int(replica), int(seed)))
 
     def set_params(self, params):
         self._ck(self.L.wcfe_set_params(self.h, C.byref(params)))
