@@ -257,7 +257,7 @@ def main():
     kms, kcnt = sim.kernel_ms()
     sim.set_profile(False)
     info = sim.path_info()
-    names = (["k_predict_cell", "k_bond", "k_cell_patch", "k_boundary_finish", info["subs_kernel"]] if info["planar"]
+    names = (["k_predict_cell", "k_bond", "k_cell_patch", "k_boundary_finish", info["subs_kernel"], "k_bucket_reduce"] if info["planar"]
              else ["k_predict_cell", "k_bond", "k_cell_node", "k_boundary_finish", "k_subs_node"])
     per_kernel = {n: kms[i] / kcnt[i] for i, n in enumerate(names) if kcnt[i]}
     peaks = {}

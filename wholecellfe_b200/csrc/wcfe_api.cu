@@ -63,6 +63,7 @@ struct Surface {
     std::vector<unsigned char> is_bnd;
     std::vector<int> ring_ptr, ring;      // host CSR
     DevBuf<int> d_tri, d_ring_ptr, d_ring;
+    DevBuf<double> anc;                   // cell, planar path: anchor records (p.x, p.y, H.x, H.y) per node, k_cell_patch -> substrate kernels
     DevBuf<double> x, X, V, A, V2, A2, ea[2], cA, cB, cC, fa, asum;   // V2/A2: write buffers of the planar cell kernel
     int ea_cur = 0;
     // boundary (cell)
@@ -107,6 +108,9 @@ struct wcfe_ctx {
     DevBuf<unsigned long long> b_head;
     DevBuf<int> b_items;
     int b_cap = 0;
+    // big buckets (coarse substrate): list + one-warp-per-triangle reduction, see k_bucket_reduce
+    DevBuf<unsigned int> big_count; DevBuf<int> big_list;
+    int big_cap = 0, big_T = 0x7fffffff;
     unsigned int epoch = 0;
     double box[4] = {0, 0, 0, 0};         // padded anchor region, substrate nodes outside cannot receive force
     double ibox[4] = {0, 0, 0, 0};        // region the anchors themselves must stay in (box shrunk by the longest substrate edge)
@@ -243,7 +247,7 @@ SurfView view(Surface &s) {
     v.tri = s.d_tri.p; v.ring_ptr = s.d_ring_ptr.p; v.ring = s.d_ring.p;
     v.x = s.x.p; v.X = s.X.p ? s.X.p : s.x.p; v.V = s.V.p; v.A = s.A.p;
     v.ea_in = s.ea[s.ea_cur].p; v.ea_out = s.ea[s.ea_cur ^ 1].p;
-    v.cC = s.cC.p; v.fa = s.fa.p; v.asum = s.asum.p;
+    v.cC = s.cC.p; v.fa = s.fa.p; v.asum = s.asum.p; v.anc = s.anc.p;
     return v;
 }
 BoundaryView bview(Surface &s) {
@@ -510,6 +514,16 @@ int build_buckets(wcfe_ctx *c) {
     CK(c->b_head.alloc((size_t)ss.nep * c->nrep)); CK(c->b_items.alloc((size_t)ss.ne * cap * c->nrep));
     CK(cudaMemset(c->b_head.p, 0, sizeof(unsigned long long) * ss.nep * c->nrep));
     c->epoch = 0;
+    // many anchors per substrate triangle expected -> reduce big buckets with one warp each (k_subs_ring only)
+    c->big_T = 0x7fffffff; c->big_cap = 0; c->big_count.release(); c->big_list.release();
+    int T = dens >= 3.0 ? 4 : 0;
+    if (const char *e = std::getenv("WCFE_BIG_T")) T = std::atoi(e);
+    if (T > 0 && c->subs_kernel == 2) {
+        c->big_T = T;
+        c->big_cap = std::max(64, 2 * cs.nn);
+        CK(c->big_count.alloc((size_t)c->nrep)); CK(c->big_list.alloc((size_t)c->big_cap * c->nrep));
+        CK(cudaMemset(c->big_count.p, 0, sizeof(unsigned int) * c->nrep));
+    }
     return WCFE_OK;
 }
 
@@ -556,7 +570,7 @@ void harvest_profile(wcfe_ctx *c) {
     }
     c->pev_kernel.clear();
 }
-enum { K_PREDICT = 0, K_BOND = 1, K_CELL = 2, K_FINISH = 3, K_SUBS = 4 };
+enum { K_PREDICT = 0, K_BOND = 1, K_CELL = 2, K_FINISH = 3, K_SUBS = 4, K_REDUCE = 5 };
 
 // ---- one UL update on the device: k_bond, k_cell_node, k_boundary_finish, k_subs_node ---------------------------
 int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const unsigned int *tape_dev, bool fuse_predict, int which = 3) {
@@ -564,13 +578,15 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     SurfView cv = view(cs), sv = view(ss);
     sv.X = sv.x;
     if (which & 1) c->epoch++;            // the cell half fills the triangle buckets of this epoch, the substrate half reads them
-    BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch};
+    BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch, nullptr, nullptr, 0, 0x7fffffff};
     const int gc = (cs.nn + kBlock - 1) / kBlock, gs = (ss.nn + kBlock - 1) / kBlock;
     // Pr < APrate*dt*exp(-APrate*dt) (UL:1531): the threshold is evaluated on the host with the host libm, as the reference does
     const double thr = c->prm.ap_rate * dt_real * std::exp(-c->prm.ap_rate * dt_real);
     BoundaryView bv = bview(cs);
     const bool planar = use_planar(c);
     int npart = gc;
+    const bool reduce = planar && c->subs_kernel == 2 && c->big_count.p != nullptr;
+    if (reduce) { bk.big_count = c->big_count.p; bk.big_list = c->big_list.p; bk.big_cap = c->big_cap; bk.big_T = c->big_T; }
     const bool batch = c->nrep > 1;
     BatchView bt{};
     if (batch) {
@@ -627,11 +643,18 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
             k_cell_node<false><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, DebugView{}); }
         c->launches += 2;
     }
+    if (reduce) {
+        ProfScope pr(c, K_REDUCE);
+        const int gr = std::max(1, std::min(4 * c->num_sms, (cs.nn / 64 + kReduceWarps - 1) / kReduceWarps));
+        if (batch) k_bucket_reduce<true><<<dim3(gr, R), kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
+        else k_bucket_reduce<false><<<gr, kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
+        c->launches += 1;
+    }
     { ProfScope ps(c, K_FINISH);
     const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few blocks: the kernel is latency-, not throughput-bound
-    if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt);
-    else if (c->debug) k_boundary_finish<true><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt);
-    else k_boundary_finish<false><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt); }
+    if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, bk.big_count);
+    else if (c->debug) k_boundary_finish<true><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt, bk.big_count);
+    else k_boundary_finish<false><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, bk.big_count); }
     c->launches += 1;
     cs.ea_cur ^= 1;
 subs_half:
@@ -812,14 +835,14 @@ int wcfe_destroy(wcfe_ctx *c) {
         Surface &s = c->s[q];
         s.d_tri.release(); s.d_ring_ptr.release(); s.d_ring.release();
         s.x.release(); s.X.release(); s.V.release(); s.A.release(); s.V2.release(); s.A2.release(); s.ea[0].release(); s.ea[1].release();
-        s.cA.release(); s.cB.release(); s.cC.release(); s.fa.release(); s.asum.release();
+        s.cA.release(); s.cB.release(); s.cC.release(); s.fa.release(); s.asum.release(); s.anc.release();
         s.d_bnd_node.release(); s.d_bnd_index.release(); s.d_cand_ptr.release(); s.d_cand.release(); s.d_bnd_buf.release();
         s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
         s.p_blob.release(); s.p_ring_blob.release(); s.p_ring_cyc.release(); s.p_elem_ptr.release(); s.p_elem_gid.release(); s.p_cand_l.release();
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();
-    c->d_kb.release(); c->d_seeds.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
+    c->d_kb.release(); c->d_seeds.release(); c->big_count.release(); c->big_list.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
@@ -925,6 +948,7 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
         CK(s.X.alloc(3 * np * R)); CK(cudaMemcpy(s.X.p, s.x.p, sizeof(double) * 3 * np, cudaMemcpyDeviceToDevice));
         CK(s.V2.alloc(3 * np * R)); CK(s.A2.alloc(3 * np * R));
         CK(cudaMemset(s.V2.p, 0, sizeof(double) * 3 * np)); CK(cudaMemset(s.A2.p, 0, sizeof(double) * 3 * np));
+        CK(s.anc.alloc(4 * np * R)); CK(cudaMemset(s.anc.p, 0, sizeof(double) * 4 * np * R));
         CK(s.cA.alloc(np * R)); CK(s.cB.alloc(np * R)); CK(s.cC.alloc(np * R)); CK(s.fa.alloc(3 * np * R)); CK(s.asum.alloc(np * R));
         if ((rc = fill_field(c, s.cA.p, nn, s.np, 1, c->prm.c_A_init))) return rc;        // main.cpp:672
         CK(cudaMemset(s.cB.p, 0, sizeof(double) * np)); CK(cudaMemset(s.cC.p, 0, sizeof(double) * np));

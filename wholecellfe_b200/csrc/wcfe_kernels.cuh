@@ -27,6 +27,8 @@ struct SurfView {            // device pointers of one surface
     const double *ea_in;     // [6*np]
     double *ea_out;          // [6*np]
     double *cC, *fa, *asum;  // cell only: [np], [3*np], [np]
+    double *anc;             // cell only, planar path: [4*np] anchor records (p.x, p.y, H.x, H.y) written by k_cell_patch:
+                             //   p = x - fa_u (UL:1303), H = c_C f(fa_u) Asum rho = minus the cell node's own F_FA (UL:1259, :1414)
 };
 
 struct GridView {            // uniform grid over substrate triangles (candidate filter for point location)
@@ -40,6 +42,11 @@ struct BucketView {          // triangle -> anchored cell nodes, rebuilt every s
     int *items;                 // [ne_subs*cap]
     int cap;
     unsigned int epoch;
+    // coarse substrates (many anchors per triangle): buckets that grow beyond big_T are listed here by the inserting thread and
+    // reduced by one warp each (k_bucket_reduce) instead of by every node of the triangle; big_T = INT_MAX switches it off
+    unsigned int *big_count;        // entries of big_list; zeroed by k_boundary_finish after k_bucket_reduce has run
+    int *big_list;                  // [big_cap] triangle ids
+    int big_cap, big_T;
 };
 
 struct BoundaryView {        // cell boundary vertices in ascending vertex order (the RNG draw order, UL:1463-1465)
@@ -68,8 +75,12 @@ __device__ __forceinline__ void batch_shift(SurfView &s, size_t r) {
     const size_t n = (size_t)s.np * r;
     s.x += 3 * n; s.X += 3 * n; s.V += 3 * n; s.A += 3 * n; s.ea_in += 6 * n; s.ea_out += 6 * n;
     if (s.cC) { s.cC += n; s.fa += 3 * n; s.asum += n; }
+    if (s.anc) s.anc += 4 * n;
 }
-__device__ __forceinline__ void batch_shift(BucketView &bk, const BatchView &bt, size_t r) { bk.head += bt.head * r; bk.items += bt.items * r; }
+__device__ __forceinline__ void batch_shift(BucketView &bk, const BatchView &bt, size_t r) {
+    bk.head += bt.head * r; bk.items += bt.items * r;
+    if (bk.big_count) { bk.big_count += r; bk.big_list += (size_t)bk.big_cap * r; }
+}
 
 enum : int { ERR_BUCKET_OVERFLOW = 1, ERR_LOC_OVERFLOW = 2, ERR_NAN = 4, ERR_REGION = 8 };
 
@@ -341,7 +352,7 @@ template <bool DBG, bool BATCH = false>
 __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k_, int npart, const double *__restrict__ partials,
                                                           const double *__restrict__ V_in, const double *__restrict__ A_in,
                                                           double dt, double dt_real, double *__restrict__ diag, int *__restrict__ err, DebugView dbg,
-                                                          BatchView bt) {
+                                                          BatchView bt, unsigned int *big_count) {
     __shared__ double sh[4 * 32];
     __shared__ double tot[4];
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
@@ -349,7 +360,9 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
         const size_t r = blockIdx.y;
         batch_shift(s, r);
         b.buf += bt.bnd * r; partials += bt.partials * r; V_in += 3 * (size_t)s.np * r; A_in += 3 * (size_t)s.np * r; diag += 8 * r; err += r;
+        if (big_count) big_count += r;
     }
+    if (big_count && blockIdx.x == 0 && threadIdx.x == 0) *big_count = 0;     // the list of this step has been consumed (stream order)
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     // strided accumulation in a fixed order, then a fixed tree
     for (int p = threadIdx.x; p < npart; p += blockDim.x)

@@ -371,20 +371,23 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
             const int lid[3] = {tid, (int)jk.x, (int)jk.y};
             const double2 p1 = sxy[lid[(3 - slot) % 3]], p2 = sxy[lid[(4 - slot) % 3]], p3 = sxy[lid[(5 - slot) % 3]];
             const double n1[3] = {p1.x, p1.y, 0.0}, n2[3] = {p2.x, p2.y, 0.0}, n3[3] = {p3.x, p3.y, 0.0};
+            if (cnt > bk.big_T) {            // reduced by k_bucket_reduce: six sums parked in the bucket's own item storage
+                const double2 f = reinterpret_cast<const double2 *>(bk.items + (size_t)e * bk.cap)[slot];
+                Fx += f.x; Fy += f.y;
+                continue;
+            }
             int prev = -1;
             for (int m = 0; m < cnt; m++) {
                 int ni = 0x7fffffff;
                 for (int q = 0; q < cnt; q++) { const int v = bk.items[(size_t)e * bk.cap + q]; if (v > prev && v < ni) ni = v; }
                 prev = ni;
-                const double u[3] = {c.fa[ni], c.fa[c.np + ni], 0.0};
-                const double pt[3] = {c.x[ni] - u[0], c.x[c.np + ni] - u[1], 0.0};     // UL:1303
+                const double2 ap = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)ni], ah = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)ni + 1];
+                const double pt[3] = {ap.x, ap.y, 0.0};                                  // UL:1303
                 double Ar[3], At;
                 point_in_triangle(n1, n2, n3, pt, Ar, At);
-                double fi[3];
-                integrin_force(k, u, fi);
-                const double w = Ar[slot] / At, cC = c.cC[ni], As = c.asum[ni];
-                Fx += cC * fi[0] * w * As * k.rho_i_max;                                 // UL:1414-1422
-                Fy += cC * fi[1] * w * As * k.rho_i_max;
+                const double w = Ar[slot] / At;
+                Fx += ah.x * w;                                                          // UL:1414-1422
+                Fy += ah.y * w;
             }
         }
     }
@@ -401,6 +404,55 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     if (DBG) {
         dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
         dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
+    }
+}
+
+// ---- big buckets: one warp per listed triangle ------------------------------------------------------------------------------------
+// calculateForce_FA_subs (UL:1297-1454) adds, for every anchor inside a substrate triangle, H * A_j/A_tri to the triangle's three
+// nodes, anchors in ascending cell-node order.  When a triangle holds many anchors (coarse substrate under a fine cell: 88 in one
+// triangle of the example meshes) the per-node gather of k_subs_ring would sort and evaluate the same bucket three times, serially.
+// Here the lanes of a warp rank the items (all pairs, 1/32 each), evaluate them in parallel, park the terms in shared memory by
+// rank, and six lanes form the six sums in the reference's order.  The result overwrites the head of the bucket's own item
+// storage (6 doubles = 12 ints <= cap), where k_subs_ring picks it up.
+constexpr int kReduceWarps = 8, kReduceWindow = 128;
+template <bool BATCH>
+__global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s, SurfView c, BucketView bk, BatchView bt) {
+    __shared__ double term[kReduceWarps][kReduceWindow][6];
+    if (BATCH) { const size_t r = blockIdx.y; batch_shift(s, r); batch_shift(c, r); batch_shift(bk, bt, r); }
+    int nbig = (int)min(*bk.big_count, (unsigned int)bk.big_cap);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double (*tw)[6] = term[warp];
+    for (int b = blockIdx.x * kReduceWarps + warp; b < nbig; b += gridDim.x * kReduceWarps) {
+        const int e = bk.big_list[b];
+        int cnt = (int)(unsigned int)bk.head[e];
+        if (cnt > bk.cap) cnt = bk.cap;
+        int *items = bk.items + (size_t)e * bk.cap;
+        const int i0 = s.tri[e], i1 = s.tri[s.nep + e], i2 = s.tri[2 * s.nep + e];
+        const double n1[3] = {s.x[i0], s.x[s.np + i0], 0.0}, n2[3] = {s.x[i1], s.x[s.np + i1], 0.0}, n3[3] = {s.x[i2], s.x[s.np + i2], 0.0};
+        double acc = 0.0;                                   // lanes 0..5: (vertex, component) = (lane >> 1, lane & 1)
+        for (int w0 = 0; w0 < cnt; w0 += kReduceWindow) {   // one window unless a bucket holds more than 128 anchors
+            for (int m = lane; m < cnt; m += 32) {
+                const int v = items[m];
+                int rank = 0;
+                for (int q = 0; q < cnt; q++) rank += items[q] < v;      // node ids inside a bucket are distinct
+                if (rank < w0 || rank >= w0 + kReduceWindow) continue;
+                const double2 ap = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)v], ah = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)v + 1];
+                const double pt[3] = {ap.x, ap.y, 0.0};
+                double Ar[3], At;
+                point_in_triangle(n1, n2, n3, pt, Ar, At);
+                double *t6 = tw[rank - w0];
+#pragma unroll
+                for (int j = 0; j < 3; j++) { const double w = Ar[j] / At; t6[2 * j] = ah.x * w; t6[2 * j + 1] = ah.y * w; }
+            }
+            __syncwarp();
+            if (lane < 6) {
+                const int n = min(kReduceWindow, cnt - w0);
+#pragma unroll 8
+                for (int r = 0; r < n; r++) acc += tw[r][lane];      // the loads are independent of the running sum: unrolled, they pipeline
+            }
+            __syncwarp();
+        }
+        if (lane < 6) reinterpret_cast<double *>(items)[lane] = acc;     // every lane has finished reading the items (syncwarp above)
     }
 }
 
@@ -603,6 +655,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
                                                        double *__restrict__ V_out, double *__restrict__ A_out, DebugView dbg, BatchView bt) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ double shred[4 * 32];
+    __shared__ int s_big[2 * kThreads];           // big-bucket appends of this CTA, published with one global atomic
+    __shared__ int s_nbig, s_bigbase;
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
     if (BATCH) {
         const size_t r = blockIdx.y, n3 = 3 * (size_t)s.np * r;
@@ -625,6 +679,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     const int np = s.np;
     // ---- stage: TMA bulk copies of the patch descriptor and of the owned nodes' state
     if (tid == 0) {
+        s_nbig = 0;
         mbar_init(bar, 1);
         const unsigned int nb = (unsigned int)ncopy * 8u;
         mbar_expect_tx(bar, (unsigned int)pv.stride + (PREDICT ? 5u : 7u) * nb);
@@ -668,6 +723,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         se0[d] = s.ea_in[gi]; se1[d] = s.ea_in[np + gi]; se3[d] = s.ea_in[3 * (size_t)np + gi];
     }
     // ---- bond kinetics + anchor location for the own node (needs only its own X, x)
+    double anc_px = 0.0, anc_py = 0.0;
     if (own) {
         const double Xi[3] = {sX0[tid], sX1[tid], 0.0}, xi[3] = {sx0[tid], sx1[tid], 0.0};
         double fa[3] = {fa0, fa1, 0.0};
@@ -682,6 +738,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         fa0 = fa[0]; fa1 = fa[1];
         s.fa[i] = fa0; s.fa[np + i] = fa1; s.cC[i] = cC;
         const double pt[3] = {xi[0] - fa0, xi[1] - fa1, 0.0};                           // UL:1303
+        anc_px = pt[0]; anc_py = pt[1];
         if (!(pt[0] >= a.ix0 && pt[0] <= a.ix1 && pt[1] >= a.iy0 && pt[1] <= a.iy1)) atomicOr(a.err, ERR_REGION);
         int cnt = 0, first = -1;
         auto insert = [&](int t, const double *, double) {
@@ -698,6 +755,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
                 if (old == seen) break;
             } while (true);
             if (slot < bk.cap) bk.items[(size_t)t * bk.cap + slot] = i; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
+            if (slot == bk.big_T) {          // this insert makes the bucket "big": list it once for k_bucket_reduce
+                const int q = atomicAdd(&s_nbig, 1);
+                if (q < 2 * kThreads) s_big[q] = t;
+                else { const unsigned int idx = atomicAdd(bk.big_count, 1u); if (idx < (unsigned int)bk.big_cap) bk.big_list[idx] = t; else atomicOr(a.err, ERR_BUCKET_OVERFLOW); }
+            }
         };
         // Anchors rarely change triangle between steps: try the triangle of the previous step first.  A point STRICTLY inside
         // it (all three sub-areas > 0) lies in no other triangle of a conforming substrate mesh, so the grid search -- which
@@ -716,6 +778,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         a.d_loc_cnt[i] = cnt; a.d_loc_first[i] = first;
     }
     __syncthreads();
+    if (bk.big_count) {                       // uniform: publish this CTA's share of the big-bucket list
+        const int nbig = min(s_nbig, 2 * kThreads);
+        if (tid == 0 && nbig) s_bigbase = (int)atomicAdd(bk.big_count, (unsigned int)nbig);
+        __syncthreads();
+        for (int q = tid; q < nbig; q += kThreads) {
+            const int idx = s_bigbase + q;
+            if (idx < bk.big_cap) bk.big_list[idx] = s_big[q]; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
+        }
+    }
     // ---- elements
     const double tk = t_act_of(k, a.t_tot) * k.kappa;
     for (int el = tid; el < nel; el += kThreads) {
@@ -763,6 +834,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         const double Ffx = -cC * fi[0] * asum * k.rho_i_max, Ffy = -cC * fi[1] * asum * k.rho_i_max;   // UL:1259
         const double Fvx = -k.drag * Vh0, Fvy = -k.drag * Vh1;                       // UL:571
         s.asum[i] = asum;
+        reinterpret_cast<double2 *>(s.anc)[2 * (size_t)i] = make_double2(anc_px, anc_py);
+        reinterpret_cast<double2 *>(s.anc)[2 * (size_t)i + 1] = make_double2(-Ffx, -Ffy);
         s.ea_out[i] = ea0 + q0 / mm; s.ea_out[np + i] = ea1 + q1 / mm; s.ea_out[3 * np + i] = ea3 + q3 / mm;   // UL:607-612
         if (DBG) {
             dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Ffx; dbg.f_fa[np + i] = Ffy; dbg.mm[i] = mm;
