@@ -51,6 +51,7 @@ def parse():
                          "per-step NCCL halo exchange (strong scaling)")
     ap.add_argument("--order", default="morton", choices=["morton", "morton_rows"], help="node numbering of the synthetic meshes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the small side measurements (configs 1/2 latency, config 5 batch)")
     ap.add_argument("--cpu-sample-div", type=int, default=16, help="CPU baseline sample = workload / this (both meshes)")
     return ap.parse_args()
 
@@ -199,6 +200,34 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
     dist.destroy_process_group()
 
 
+def other_configs(W):
+    """Side measurements on the reference's shipped example meshes (BASELINE configs 0-1: 296/542 cell, 320/578 substrate, dt 0.005)
+    and on a batch of 512 of them (configs[4] per GPU).  Wall clock around synchronous calls, a few hundred ms in total."""
+    from wholecellfe_b200.ensemble import sweep_grid, EnsembleRunner
+    path = os.path.join(ROOT, "tests", "golden", "example_meshes.npz")
+    if not os.path.exists(path):
+        return None
+    d = np.load(path)
+    xc, tc, xs, ts = d["cell_xyz"], d["cell_tri"], d["subs_xyz"], d["subs_tri"]
+    out = {"mesh": "shipped example: %d-triangle cell on %d-triangle substrate, dt 0.005, glibc replay RNG" % (len(tc), len(ts))}
+    for var in ("k1", "k31", "kMD"):
+        g = W.ULSim(var); g.upload_mesh(W.CELL, xc, tc); g.upload_mesh(W.SUBS, xs, ts); g.srand(1)
+        t = g.step_n(80, 0.005, 0.0)
+        g.step_n(800, 0.005, t)
+        out["config1_%s_us_per_step" % var] = g.last_step_ms() / 800 * 1e3
+        out["config1_%s_element_steps_per_sec" % var] = (len(tc) + len(ts)) * 800 / (g.last_step_ms() * 1e-3)
+        g.close()
+    n = 512
+    run = EnsembleRunner(sweep_grid(n), (xc, tc), (xs, ts))
+    run.advance(40, 0.005)
+    w0 = time.perf_counter(); run.advance(400, 0.005); w1 = time.perf_counter()
+    out["config5_batch_cells_per_gpu"] = n
+    out["config5_batch_element_steps_per_sec"] = n * run.elements_per_cell * 400 / (w1 - w0)
+    out["config5_us_per_cell_step"] = (w1 - w0) / (400 * n) * 1e6
+    run.close()
+    return out
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -310,6 +339,9 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "2 steps of a 1/%d-size copy of the workload (%d-triangle cell on %d-node substrate), oracle C restatement with grid point location, 1 thread"
                          % (div, len(ctc), len(cxs))}
+    other = None
+    if rank == 0 and world == 1 and not a.no_other_configs:
+        other = other_configs(W)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -319,6 +351,8 @@ def main():
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
         if cpu:
             line["cpu_baseline"] = cpu
+        if other:
+            line["other_configs"] = other
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

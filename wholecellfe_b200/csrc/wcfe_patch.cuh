@@ -71,6 +71,17 @@ __host__ __device__ inline size_t patch_smem_bytes(int n_node_arrays, int n_rec,
     return 16 + (size_t)stride + sizeof(double) * n_node_arrays * NL + recs + 64;
 }
 
+// 1/x for a normal, well-scaled x (the determinant of I - 2e, close to 1): MUFU.RCP64H seed plus two Newton steps, four DFMAs,
+// error about one ulp -- the compiler's IEEE division costs twice as many FP64 issue slots plus a range-check branch
+__device__ __forceinline__ double rcp_newton(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ----------------------------------------------------------------------
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count) {
@@ -299,41 +310,51 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     const ushort2 *rjk = (const ushort2 *)(sblob + pv.roff_jk);          // [step][node]: conflict-free across a warp
     const double2 myxy = make_double2(stage[tid], stage[kPatch + tid]), mye01 = make_double2(stage[2 * kPatch + tid], stage[3 * kPatch + tid]);
     const double mye3 = stage[4 * kPatch + tid];
-    sxy[tid] = myxy; se01[tid] = mye01; se3[tid] = mye3;
+    // shared memory holds t = (2/3) e per node: the element's I - 2 e_avg is then 1 - (t_i + t_j + t_k), two additions per
+    // component instead of the average plus a multiply-add (the FP64 pipe, not HBM, is what this kernel saturates first)
+    const double two3 = 2.0 / 3.0;
+    sxy[tid] = myxy; se01[tid] = make_double2(two3 * mye01.x, two3 * mye01.y); se3[tid] = two3 * mye3;
     for (int l = tid; l < nh; l += kPatch) {
         const int g = halo_ids[l];
         sxy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
-        se01[kPatch + l] = make_double2(s.ea_in[g], s.ea_in[np + g]);
-        se3[kPatch + l] = s.ea_in[3 * (size_t)np + g];
+        se01[kPatch + l] = make_double2(two3 * s.ea_in[g], two3 * s.ea_in[np + g]);
+        se3[kPatch + l] = two3 * s.ea_in[3 * (size_t)np + g];
     }
     __syncthreads();
     if (!own) return;
     const double ea0 = mye01.x, ea1 = mye01.y, ea3 = mye3;
     double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
     const int nring = valence[tid];
-    // one incident element, with this node as local vertex 0 and (j, k) the other two in cyclic order
-    struct Nb { double2 p, e; double e3; };
-    auto load_nb = [&](int l) { Nb n; n.p = sxy[l]; n.e = se01[l]; n.e3 = se3[l]; return n; };
-    struct Contrib { double fx, fy, d0, d1, d3, w; };
+    // one incident element, with this node as local vertex 0 and (j, k) the other two in cyclic order.
+    // Frozen substrate, F == I (UL:988-1174 specialised, wcfe_math.cuh elem_eval_frozen), with a = I - 2 e_avg, b01 = -a01:
+    //   S = mu (a^-1 - det(a) I),  Re_0 = -(t/2) sign(W) S (d x, d y),  Re_ea = (e_avg - ea_0) A0 t / 3,  MM = A0 t / 3
+    // written so that every scale factor rides on the accumulating multiply-add.
+    struct Nb { double2 p, t; double t3; };
+    auto load_nb = [&](int l) { Nb n; n.p = sxy[l]; n.t = se01[l]; n.t3 = se3[l]; return n; };
+    const double c0 = 1.0 - two3 * ea0, c1 = 1.0 - two3 * ea1, c3 = two3 * ea3;            // own node's share of a00, a11, b01
+    const double A0c = 1.0 - 2.0 * ea0, A1c = 1.0 - 2.0 * ea1, B3c = 2.0 * ea3;            // a at e_avg == ea_own: Re_ea vanishes there
+    const double mh = 0.5 * k.mu_subs * k.thick, cw = k.thick / 6.0, cwh = k.thick / 12.0;
+    struct Contrib { double f1, f2, m, a00, a11, b01, aw; };
     auto entry = [&](const Nb &J, const Nb &K) {
-        const double third = 1.0 / 3.0;
-        // averaged strain in the element's own vertex order is a sum of three equal-weight terms: order-independent up to rounding
-        const double e0 = third * ea0 + third * J.e.x + third * K.e.x, e1 = third * ea1 + third * J.e.y + third * K.e.y, e3 = third * ea3 + third * J.e3 + third * K.e3;
+        Contrib c;
+        c.a00 = c0 - (J.t.x + K.t.x); c.a11 = c1 - (J.t.y + K.t.y); c.b01 = c3 + (J.t3 + K.t3);
         const double G1x = J.p.x - myxy.x, G1y = J.p.y - myxy.y, G2x = K.p.x - myxy.x, G2y = K.p.y - myxy.y;
         const double Wz = G1x * G2y - G1y * G2x;
-        const double a00 = 1.0 - 2.0 * e0, a11 = 1.0 - 2.0 * e1, a01 = -2.0 * e3;
-        const double det2 = a00 * a11 - a01 * a01;
-        const double idet = 1.0 / det2;
-        const double S00 = k.mu_subs * (a11 * idet - det2), S11 = k.mu_subs * (a00 * idet - det2), S01 = -k.mu_subs * a01 * idet;
+        const double det2 = c.a00 * c.a11 - c.b01 * c.b01;
+        const double idet = rcp_newton(det2);
         const double dx = G2y - G1y, dy = G1x - G2x;
-        const double hs = Wz > 0 ? -0.5 * k.thick : 0.5 * k.thick;       // -(t/2) sign(W)
-        Contrib c;
-        c.fx = hs * (S00 * dx + S01 * dy); c.fy = hs * (S01 * dx + S11 * dy);
-        c.w = third * (0.5 * fabs(Wz)) * k.thick;                        // UL:1172
-        c.d0 = (e0 - ea0) * c.w; c.d1 = (e1 - ea1) * c.w; c.d3 = (e3 - ea3) * c.w;   // UL:1170 with e_s == e for F == I
+        c.f1 = idet * (c.a11 * dx + c.b01 * dy) - det2 * dx;                // (S / mu) (dx, dy)
+        c.f2 = idet * (c.b01 * dx + c.a00 * dy) - det2 * dy;
+        c.m = Wz > 0 ? -mh : mh;                                           // -(t/2) mu sign(W)
+        c.aw = fabs(Wz);                                                   // 2 A0
         return c;
     };
-    auto add = [&](const Contrib &c) { rx += c.fx; ry += c.fy; q0 += c.d0; q1 += c.d1; q3 += c.d3; mm += c.w; };
+    auto add = [&](const Contrib &c) {
+        rx = fma(c.m, c.f1, rx); ry = fma(c.m, c.f2, ry);
+        mm = fma(c.aw, cw, mm);                                            // UL:1172
+        const double wh = c.aw * cwh;                                      // A0 t / 6: (e_avg - ea) = (a_own - a) / 2
+        q0 = fma(A0c - c.a00, wh, q0); q1 = fma(A1c - c.a11, wh, q1); q3 = fma(c.b01 - B3c, wh, q3);   // UL:1170 with e_s == e for F == I
+    };
     // The fan is walked two elements at a time: their dependency chains (loads -> strain -> determinant -> reciprocal -> stress)
     // are independent, which doubles the instruction-level parallelism of a loop that is otherwise latency bound.
     int lastk = -1;
