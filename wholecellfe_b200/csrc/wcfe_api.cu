@@ -101,6 +101,10 @@ struct wcfe_ctx {
     std::vector<unsigned int> rseed;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // k_boundary_finish touches only the cell's boundary vertices and the diagnostics, the substrate kernel neither: it runs on
+    // a high-priority side stream, forked after the cell kernel and joined at the end of the step, hidden behind the substrate kernel
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Surface s[2];
     // point location grid over the substrate + triangle buckets
     GridView grid{};
@@ -552,14 +556,15 @@ int check_device_errors_bits(wcfe_ctx *c, int e) {
 // per-kernel timing: an event pair around a launch, harvested after the stream has drained
 struct ProfScope {
     wcfe_ctx *c; int idx = -1;
-    ProfScope(wcfe_ctx *c_, int kernel_id) : c(c_) {
+    cudaStream_t st;
+    ProfScope(wcfe_ctx *c_, int kernel_id, cudaStream_t on = nullptr) : c(c_), st(on ? on : c_->stream) {
         if (!c->profile) return;
         idx = (int)c->pev_kernel.size();
         if (c->pev.size() < (size_t)2 * (idx + 1)) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); c->pev.push_back(a); c->pev.push_back(b); }
         c->pev_kernel.push_back(kernel_id);
-        cudaEventRecord(c->pev[2 * idx], c->stream);
+        cudaEventRecord(c->pev[2 * idx], st);
     }
-    ~ProfScope() { if (idx >= 0) cudaEventRecord(c->pev[2 * idx + 1], c->stream); }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(c->pev[2 * idx + 1], st); }
 };
 void harvest_profile(wcfe_ctx *c) {
     if (!c->profile) return;
@@ -588,6 +593,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     const bool reduce = planar && c->subs_kernel == 2 && c->big_count.p != nullptr;
     if (reduce) { bk.big_count = c->big_count.p; bk.big_list = c->big_list.p; bk.big_cap = c->big_cap; bk.big_T = c->big_T; }
     const bool batch = c->nrep > 1;
+    bool joined = true;
     BatchView bt{};
     if (batch) {
         if (!planar || !fuse_predict || which != 3 || c->debug || c->subs_kernel != 2)
@@ -600,6 +606,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     const double *v_old = cs.V.p, *a_old = cs.A.p;      // general path: V, A are updated in place
     if (!(which & 1)) goto subs_half;
     if (planar) {
+        if (reduce) CK(cudaMemsetAsync(c->big_count.p, 0, sizeof(unsigned int) * c->nrep, c->stream));     // this step's list of big buckets
         // fused cell kernel: (predict) + updateFA + anchor location + forces + update, one CTA per patch
         ProfScope ps(c, K_CELL);
         PatchView pvc = pview(cs);
@@ -643,6 +650,18 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
             k_cell_node<false><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, DebugView{}); }
         c->launches += 2;
     }
+    {
+    // fork: the finish kernel goes to the side stream first (so that its few blocks are placed as soon as the cell kernel drains)
+    cudaStream_t fs = c->stream;
+    const bool forked = planar && !c->debug && (which & 2);
+    if (forked) { CK(cudaEventRecord(c->ev_fork, c->stream)); CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0)); fs = c->side; }
+    { ProfScope ps(c, K_FINISH, fs);
+    const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few small blocks: latency-, not throughput-bound
+    if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt);
+    else if (c->debug) k_boundary_finish<true><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt);
+    else k_boundary_finish<false><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt); }
+    if (forked) { CK(cudaEventRecord(c->ev_join, c->side)); joined = false; }
+    }
     if (reduce) {
         ProfScope pr(c, K_REDUCE);
         const int gr = std::max(1, std::min(4 * c->num_sms, (cs.nn / 64 + kReduceWarps - 1) / kReduceWarps));
@@ -650,11 +669,6 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         else k_bucket_reduce<false><<<gr, kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
         c->launches += 1;
     }
-    { ProfScope ps(c, K_FINISH);
-    const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few blocks: the kernel is latency-, not throughput-bound
-    if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, bk.big_count);
-    else if (c->debug) k_boundary_finish<true><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt, bk.big_count);
-    else k_boundary_finish<false><<<fb, 1024, 0, c->stream>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, bk.big_count); }
     c->launches += 1;
     cs.ea_cur ^= 1;
 subs_half:
@@ -690,6 +704,7 @@ subs_half:
     c->launches += 1;
     ss.ea_cur ^= 1;
     c->step++;
+    if (!joined) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));      // join: later work on the main stream sees the finished boundary
     CK(cudaGetLastError());
     return WCFE_OK;
 }
@@ -742,6 +757,32 @@ int ready(wcfe_ctx *c) {
 
 }   // namespace
 
+// debugging aid: WCFE_BACKTRACE=1 prints a native backtrace on SIGSEGV / SIGABRT (the host callers are often Python or the reference app)
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+namespace {
+void wcfe_bt_handler(int sig) {
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "wcfe: fatal signal, native backtrace:\n";
+    if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+struct BtInstaller {
+    BtInstaller() {
+        if (!std::getenv("WCFE_BACKTRACE")) return;
+        void *warm[4]; backtrace(warm, 4);              // loads libgcc_s now, not inside the handler
+        static char altstack[1 << 16];
+        stack_t ss; ss.ss_sp = altstack; ss.ss_size = sizeof(altstack); ss.ss_flags = 0; sigaltstack(&ss, nullptr);
+        struct sigaction sa; memset(&sa, 0, sizeof(sa)); sa.sa_handler = wcfe_bt_handler; sa.sa_flags = SA_ONSTACK;
+        sigaction(SIGSEGV, &sa, nullptr); sigaction(SIGABRT, &sa, nullptr); sigaction(SIGBUS, &sa, nullptr);
+    }
+} g_bt_installer;
+}
+
 extern "C" {
 
 int wcfe_default_params(wcfe_params *p, int variant) {
@@ -790,6 +831,12 @@ static int create_impl(wcfe_ctx **out, int device, const wcfe_params *p, int rep
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     c->stream = c->own_stream;
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreateWithPriority", e);
+        if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess || (e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
     c->rng.seed(1);
     {
         cudaDeviceProp prop;
@@ -846,6 +893,9 @@ int wcfe_destroy(wcfe_ctx *c) {
     if (c->h_tape) cudaFreeHost(c->h_tape);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);

@@ -44,7 +44,7 @@ struct BucketView {          // triangle -> anchored cell nodes, rebuilt every s
     unsigned int epoch;
     // coarse substrates (many anchors per triangle): buckets that grow beyond big_T are listed here by the inserting thread and
     // reduced by one warp each (k_bucket_reduce) instead of by every node of the triangle; big_T = INT_MAX switches it off
-    unsigned int *big_count;        // entries of big_list; zeroed by k_boundary_finish after k_bucket_reduce has run
+    unsigned int *big_count;        // entries of big_list; zeroed on the stream before every cell kernel
     int *big_list;                  // [big_cap] triangle ids
     int big_cap, big_T;
 };
@@ -352,7 +352,7 @@ template <bool DBG, bool BATCH = false>
 __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k_, int npart, const double *__restrict__ partials,
                                                           const double *__restrict__ V_in, const double *__restrict__ A_in,
                                                           double dt, double dt_real, double *__restrict__ diag, int *__restrict__ err, DebugView dbg,
-                                                          BatchView bt, unsigned int *big_count) {
+                                                          BatchView bt) {
     __shared__ double sh[4 * 32];
     __shared__ double tot[4];
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
@@ -360,9 +360,7 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
         const size_t r = blockIdx.y;
         batch_shift(s, r);
         b.buf += bt.bnd * r; partials += bt.partials * r; V_in += 3 * (size_t)s.np * r; A_in += 3 * (size_t)s.np * r; diag += 8 * r; err += r;
-        if (big_count) big_count += r;
     }
-    if (big_count && blockIdx.x == 0 && threadIdx.x == 0) *big_count = 0;     // the list of this step has been consumed (stream order)
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     // strided accumulation in a fixed order, then a fixed tree
     for (int p = threadIdx.x; p < npart; p += blockDim.x)
