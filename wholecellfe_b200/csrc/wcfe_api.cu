@@ -104,6 +104,7 @@ struct wcfe_ctx {
     // k_boundary_finish touches only the cell's boundary vertices and the diagnostics, the substrate kernel neither: it runs on
     // a high-priority side stream, forked after the cell kernel and joined at the end of the step, hidden behind the substrate kernel
     cudaStream_t side = nullptr;
+    int use_pdl = 1;                      // chain cell -> finish -> substrate with programmatic dependent launch instead (WCFE_PDL=0: fork/join)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Surface s[2];
     // point location grid over the substrate + triangle buckets
@@ -553,6 +554,18 @@ int check_device_errors_bits(wcfe_ctx *c, int e) {
     return WCFE_OK;
 }
 
+// launch with the programmatic-stream-serialization attribute (the kernel may start before its predecessor in the stream has
+// finished; it synchronises itself with griddepcontrol.wait)
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // per-kernel timing: an event pair around a launch, harvested after the stream has drained
 struct ProfScope {
     wcfe_ctx *c; int idx = -1;
@@ -593,7 +606,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     const bool reduce = planar && c->subs_kernel == 2 && c->big_count.p != nullptr;
     if (reduce) { bk.big_count = c->big_count.p; bk.big_list = c->big_list.p; bk.big_cap = c->big_cap; bk.big_T = c->big_T; }
     const bool batch = c->nrep > 1;
-    bool joined = true;
+    bool joined = true, pdl = false;
     BatchView bt{};
     if (batch) {
         if (!planar || !fuse_predict || which != 3 || c->debug || c->subs_kernel != 2)
@@ -653,11 +666,15 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     {
     // fork: the finish kernel goes to the side stream first (so that its few blocks are placed as soon as the cell kernel drains)
     cudaStream_t fs = c->stream;
-    const bool forked = planar && !c->debug && (which & 2);
+    const bool overlap = planar && !c->debug && which == 3;
+    pdl = overlap && c->use_pdl && !c->profile && !reduce && c->subs_kernel == 2;   // event records or a kernel in between would serialise the chain
+    const bool forked = overlap && !pdl;
     if (forked) { CK(cudaEventRecord(c->ev_fork, c->stream)); CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0)); fs = c->side; }
     { ProfScope ps(c, K_FINISH, fs);
     const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few small blocks: latency-, not throughput-bound
-    if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt);
+    if (pdl && batch) CK(launch_pdl(k_boundary_finish<false, true>, dim3(fb, R), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt));
+    else if (pdl) CK(launch_pdl(k_boundary_finish<false, false>, dim3(fb), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt));
+    else if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt);
     else if (c->debug) k_boundary_finish<true><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt);
     else k_boundary_finish<false><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt); }
     if (forked) { CK(cudaEventRecord(c->ev_join, c->side)); joined = false; }
@@ -679,7 +696,9 @@ subs_half:
         ProfScope ps(c, K_SUBS);
         const size_t smem = ring_smem_bytes(ss.max_halo, ss.ring_stride);
         PatchView pvs = pview(ss);
-        if (batch) k_subs_ring<false, true><<<dim3(ss.npatch, R), kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt);
+        if (pdl && batch) CK(launch_pdl(k_subs_ring<false, true>, dim3(ss.npatch, R), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt));
+        else if (pdl) CK(launch_pdl(k_subs_ring<false, false>, dim3(ss.npatch), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt));
+        else if (batch) k_subs_ring<false, true><<<dim3(ss.npatch, R), kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt);
         else if (c->debug) k_subs_ring<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss), bt);
         else k_subs_ring<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt);
     } else if (planar && c->use_pipe) {
@@ -843,6 +862,7 @@ static int create_impl(wcfe_ctx **out, int device, const wcfe_params *p, int rep
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
         if (const char *e = std::getenv("WCFE_SUBS_PIPE")) { c->use_pipe = std::atoi(e); if (c->use_pipe) c->subs_kernel = 1; }
         if (const char *e = std::getenv("WCFE_SUBS_KERNEL")) c->subs_kernel = std::atoi(e);
+        if (const char *e = std::getenv("WCFE_PDL")) c->use_pdl = std::atoi(e);
         const void *pk[] = {(const void *)k_subs_ring<false>, (const void *)k_subs_ring<true>, (const void *)k_subs_pipe<false>, (const void *)k_subs_pipe<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
                             (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>,
                             (const void *)k_cell_patch<true, false, true>, (const void *)k_subs_ring<false, true>};

@@ -66,6 +66,13 @@ struct DebugView {           // optional force-field capture (parity gate on nod
 // (gridDim.y = R).  Connectivity, patch descriptors and boundary tables are shared; every state array holds R consecutive
 // images, and a CTA shifts its views to replica blockIdx.y before it starts.  Per-replica constants (spring law, ligand
 // density, ...) come from BatchView::k instead of the by-value kernel parameter.
+// Programmatic dependent launch (griddepcontrol, sm_90+): the step's three kernels are chained cell -> finish -> substrate.  A
+// kernel lets its dependent start as soon as all of its own CTAs have been dispatched (pdl_launch_dependents, first instruction),
+// and the dependent blocks (pdl_wait) only where it first touches what the predecessor produced.  Both are no-ops in a launch
+// without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct BatchView {
     const Consts *k;             // [R]
     const unsigned int *seed;    // [R] Philox keys, or nullptr: every replica draws the same numbers (common random numbers)
@@ -355,6 +362,8 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
                                                           BatchView bt) {
     __shared__ double sh[4 * 32];
     __shared__ double tot[4];
+    pdl_launch_dependents();      // the substrate kernel may start its cell-independent part now
+    pdl_wait();                   // everything below reads what the cell kernel wrote
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
     if (BATCH) {
         const size_t r = blockIdx.y;

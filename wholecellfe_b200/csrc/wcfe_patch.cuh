@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     const double Xi0 = myxy.x, Xi1 = myxy.y;
     double Fx = 0.0, Fy = 0.0;
     if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
+        pdl_wait();               // first touch of what the cell kernel produced (buckets, anchor records); all above overlaps its tail
         const int gb = s.ring_ptr[i];
         for (int r = 0; r < nring; r++) {
             const int code = pv.ring_cyc[gb + r];
@@ -678,6 +679,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     __shared__ double shred[4 * 32];
     __shared__ int s_big[2 * kThreads];           // big-bucket appends of this CTA, published with one global atomic
     __shared__ int s_nbig, s_bigbase;
+    pdl_launch_dependents();
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
     if (BATCH) {
         const size_t r = blockIdx.y, n3 = 3 * (size_t)s.np * r;
