@@ -606,7 +606,9 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     const bool reduce = planar && c->subs_kernel == 2 && c->big_count.p != nullptr;
     if (reduce) { bk.big_count = c->big_count.p; bk.big_list = c->big_list.p; bk.big_cap = c->big_cap; bk.big_T = c->big_T; }
     const bool batch = c->nrep > 1;
-    bool joined = true, pdl = false;
+    bool joined = true;
+    const bool overlap = planar && !c->debug && which == 3;
+    const bool pdl = overlap && c->use_pdl && !c->profile && !reduce && c->subs_kernel == 2;   // event records or a kernel in between would serialise the chain
     BatchView bt{};
     if (batch) {
         if (!planar || !fuse_predict || which != 3 || c->debug || c->subs_kernel != 2)
@@ -632,8 +634,14 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         const size_t smem = patch_smem_bytes(7, 9, cs.max_halo, cs.max_elem, cs.stride);
         npart = cs.npatch;
         if (batch) {
-            k_cell_patch<true, false, true><<<dim3(cs.npatch, R), kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt);
+            if (pdl) CK(launch_pdl(k_cell_patch<true, false, true>, dim3(cs.npatch, R), dim3(kThreads), smem, c->stream, cv, pvc, sv, c->grid, bk, bv, c->k, a, (const double *)cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt));
+            else k_cell_patch<true, false, true><<<dim3(cs.npatch, R), kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt);
             std::swap(cs.x.p, cs.X.p);
+        } else if (pdl && fuse_predict) {
+            CK(launch_pdl(k_cell_patch<true, false, false>, dim3(cs.npatch), dim3(kThreads), smem, c->stream, cv, pvc, sv, c->grid, bk, bv, c->k, a, (const double *)cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt));
+            std::swap(cs.x.p, cs.X.p);
+        } else if (pdl) {
+            CK(launch_pdl(k_cell_patch<false, false, false>, dim3(cs.npatch), dim3(kThreads), smem, c->stream, cv, pvc, sv, c->grid, bk, bv, c->k, a, (const double *)nullptr, (double *)nullptr, cs.V2.p, cs.A2.p, DebugView{}, bt));
         } else if (fuse_predict) {
             if (c->debug) k_cell_patch<true, true><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, dview(cs), bt);
             else k_cell_patch<true, false><<<cs.npatch, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt);
@@ -666,8 +674,6 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     {
     // fork: the finish kernel goes to the side stream first (so that its few blocks are placed as soon as the cell kernel drains)
     cudaStream_t fs = c->stream;
-    const bool overlap = planar && !c->debug && which == 3;
-    pdl = overlap && c->use_pdl && !c->profile && !reduce && c->subs_kernel == 2;   // event records or a kernel in between would serialise the chain
     const bool forked = overlap && !pdl;
     if (forked) { CK(cudaEventRecord(c->ev_fork, c->stream)); CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0)); fs = c->side; }
     { ProfScope ps(c, K_FINISH, fs);

@@ -275,6 +275,7 @@ template <bool DBG, bool BATCH = false>
 __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k_, double dt, double dt_real,
                                                          double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg, BatchView bt) {
     extern __shared__ __align__(128) unsigned char smraw[];
+    pdl_launch_dependents();      // the next step's cell kernel may stage its patches behind this kernel's last wave
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
     if (BATCH) { const size_t r = blockIdx.y; batch_shift(s, r); batch_shift(c, r); batch_shift(bk, bt, r); }
     const int NL = kPatch + pv.max_halo;
@@ -715,6 +716,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     const int i = n0 + tid;
     double V0 = 0, V1 = 0, Av0 = 0, Av1 = 0;      // own node's V, A (kept for the update)
     double fa0 = 0, fa1 = 0, cC = 0;
+    // Chained behind the previous step's substrate kernel (programmatic dependent launch): the bulk copies above touch nothing
+    // that kernel or the boundary finish write; from here on this kernel reads the finished V, A of boundary vertices and,
+    // further down, overwrites the buckets and anchor records the substrate kernel was reading.
+    pdl_wait();
     if (own) { V0 = s.V[i]; V1 = s.V[np + i]; Av0 = s.A[i]; Av1 = s.A[np + i]; fa0 = s.fa[i]; fa1 = s.fa[np + i]; cC = s.cC[i]; }
     __syncthreads();
     mbar_wait(bar, 0);
