@@ -116,6 +116,7 @@ struct wcfe_ctx {
     // big buckets (coarse substrate): list + one-warp-per-triangle reduction, see k_bucket_reduce
     DevBuf<unsigned int> big_count; DevBuf<int> big_list;
     int big_cap = 0, big_T = 0x7fffffff;
+    bool big_clean = true;                // the list counter is zero (k_subs_ring re-zeroes it at the end of every full step)
     unsigned int epoch = 0;
     double box[4] = {0, 0, 0, 0};         // padded anchor region, substrate nodes outside cannot receive force
     double ibox[4] = {0, 0, 0, 0};        // region the anchors themselves must stay in (box shrunk by the longest substrate edge)
@@ -518,7 +519,7 @@ int build_buckets(wcfe_ctx *c) {
     c->b_cap = (int)cap;
     CK(c->b_head.alloc((size_t)ss.nep * c->nrep)); CK(c->b_items.alloc((size_t)ss.ne * cap * c->nrep));
     CK(cudaMemset(c->b_head.p, 0, sizeof(unsigned long long) * ss.nep * c->nrep));
-    c->epoch = 0;
+    c->epoch = 0; c->big_clean = true;
     // many anchors per substrate triangle expected -> reduce big buckets with one warp each (k_subs_ring only)
     c->big_T = 0x7fffffff; c->big_cap = 0; c->big_count.release(); c->big_list.release();
     int T = dens >= 3.0 ? 4 : 0;
@@ -608,7 +609,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     const bool batch = c->nrep > 1;
     bool joined = true;
     const bool overlap = planar && !c->debug && which == 3;
-    const bool pdl = overlap && c->use_pdl && !c->profile && !reduce && c->subs_kernel == 2;   // event records or a kernel in between would serialise the chain
+    const bool pdl = overlap && c->use_pdl && !c->profile && c->subs_kernel == 2;   // event records or a kernel in between would serialise the chain
     BatchView bt{};
     if (batch) {
         if (!planar || !fuse_predict || which != 3 || c->debug || c->subs_kernel != 2)
@@ -621,7 +622,8 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     const double *v_old = cs.V.p, *a_old = cs.A.p;      // general path: V, A are updated in place
     if (!(which & 1)) goto subs_half;
     if (planar) {
-        if (reduce) CK(cudaMemsetAsync(c->big_count.p, 0, sizeof(unsigned int) * c->nrep, c->stream));     // this step's list of big buckets
+        if (reduce && !c->big_clean) CK(cudaMemsetAsync(c->big_count.p, 0, sizeof(unsigned int) * c->nrep, c->stream));   // a cell half without its substrate half left a list behind
+        if (reduce) c->big_clean = false;
         // fused cell kernel: (predict) + updateFA + anchor location + forces + update, one CTA per patch
         ProfScope ps(c, K_CELL);
         PatchView pvc = pview(cs);
@@ -688,7 +690,9 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     if (reduce) {
         ProfScope pr(c, K_REDUCE);
         const int gr = std::max(1, std::min(4 * c->num_sms, (cs.nn / 64 + kReduceWarps - 1) / kReduceWarps));
-        if (batch) k_bucket_reduce<true><<<dim3(gr, R), kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
+        if (pdl && batch) CK(launch_pdl(k_bucket_reduce<true>, dim3(gr, R), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
+        else if (pdl) CK(launch_pdl(k_bucket_reduce<false>, dim3(gr), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
+        else if (batch) k_bucket_reduce<true><<<dim3(gr, R), kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
         else k_bucket_reduce<false><<<gr, kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
         c->launches += 1;
     }
@@ -727,6 +731,7 @@ subs_half:
         else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
     }
     c->launches += 1;
+    if (reduce) c->big_clean = true;       // k_subs_ring zeroed the counter
     ss.ea_cur ^= 1;
     c->step++;
     if (!joined) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));      // join: later work on the main stream sees the finished boundary

@@ -379,6 +379,9 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     }
     const double Xi0 = myxy.x, Xi1 = myxy.y;
     double Fx = 0.0, Fy = 0.0;
+    // one thread always waits: this kernel's completion then implies that of the boundary finish, which the next cell kernel
+    // (chained behind this kernel only) depends on; it also re-zeroes the big-bucket list k_bucket_reduce has consumed
+    if (blockIdx.x == 0 && tid == 0) { pdl_wait(); if (bk.big_count) *bk.big_count = 0; }
     if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
         pdl_wait();               // first touch of what the cell kernel produced (buckets, anchor records); all above overlaps its tail
         const int gb = s.ring_ptr[i];
@@ -441,6 +444,8 @@ constexpr int kReduceWarps = 8, kReduceWindow = 128;
 template <bool BATCH>
 __global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s, SurfView c, BucketView bk, BatchView bt) {
     __shared__ double term[kReduceWarps][kReduceWindow][6];
+    pdl_launch_dependents();
+    pdl_wait();                   // the list and the buckets are the cell kernel's output
     if (BATCH) { const size_t r = blockIdx.y; batch_shift(s, r); batch_shift(c, r); batch_shift(bk, bt, r); }
     int nbig = (int)min(*bk.big_count, (unsigned int)bk.big_cap);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -680,7 +685,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     __shared__ double shred[4 * 32];
     __shared__ int s_big[2 * kThreads];           // big-bucket appends of this CTA, published with one global atomic
     __shared__ int s_nbig, s_bigbase;
-    pdl_launch_dependents();
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
     if (BATCH) {
         const size_t r = blockIdx.y, n3 = 3 * (size_t)s.np * r;
@@ -707,7 +711,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         mbar_init(bar, 1);
         const unsigned int nb = (unsigned int)ncopy * 8u;
         mbar_expect_tx(bar, (unsigned int)pv.stride + (PREDICT ? 5u : 7u) * nb);
-        bulk_g2s(sblob, pv.blob + (size_t)p * pv.stride, (unsigned int)pv.stride, bar);
+        bulk_g2s(sblob, pv.blob + (size_t)p * pv.stride, (unsigned int)pv.stride, bar);      // static descriptor: no kernel writes it
+    }
+    // Programmatic dependent launch, the rule that keeps the chain sound: before its wait a kernel touches only data that no
+    // kernel of the chain writes, and it releases its own dependents only AFTER its wait.  By induction, once all CTAs of this
+    // kernel have been released, the previous step's substrate kernel (our prerequisite) and everything before it are complete
+    // -- which is what the substrate kernel of THIS step relies on when it reads its own previous output before waiting.
+    pdl_wait();
+    pdl_launch_dependents();
+    if (tid == 0) {
+        const unsigned int nb = (unsigned int)ncopy * 8u;
         if (PREDICT) { bulk_g2s(sX0, x_in + n0, nb, bar); bulk_g2s(sX1, x_in + np + n0, nb, bar); }
         else { bulk_g2s(sX0, s.X + n0, nb, bar); bulk_g2s(sX1, s.X + np + n0, nb, bar); bulk_g2s(sx0, s.x + n0, nb, bar); bulk_g2s(sx1, s.x + np + n0, nb, bar); }
         bulk_g2s(se0, s.ea_in + n0, nb, bar); bulk_g2s(se1, s.ea_in + np + n0, nb, bar); bulk_g2s(se3, s.ea_in + 3 * (size_t)np + n0, nb, bar);
@@ -716,10 +729,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     const int i = n0 + tid;
     double V0 = 0, V1 = 0, Av0 = 0, Av1 = 0;      // own node's V, A (kept for the update)
     double fa0 = 0, fa1 = 0, cC = 0;
-    // Chained behind the previous step's substrate kernel (programmatic dependent launch): the bulk copies above touch nothing
-    // that kernel or the boundary finish write; from here on this kernel reads the finished V, A of boundary vertices and,
-    // further down, overwrites the buckets and anchor records the substrate kernel was reading.
-    pdl_wait();
     if (own) { V0 = s.V[i]; V1 = s.V[np + i]; Av0 = s.A[i]; Av1 = s.A[np + i]; fa0 = s.fa[i]; fa1 = s.fa[np + i]; cC = s.cC[i]; }
     __syncthreads();
     mbar_wait(bar, 0);
