@@ -217,6 +217,11 @@ def other_configs(W):
         out["config1_%s_us_per_step" % var] = g.last_step_ms() / 800 * 1e3
         out["config1_%s_element_steps_per_sec" % var] = (len(tc) + len(ts)) * 800 / (g.last_step_ms() * 1e-3)
         g.close()
+    # the whole application (reference main.cpp + El Topo + VTK frames every step), with the reference's own step and with ours
+    try:
+        out.update(whole_application(xc, tc, xs, ts))
+    except Exception as e:                                   # side measurement: never fatal
+        out["whole_application"] = "skipped: %s" % e
     n = 512
     run = EnsembleRunner(sweep_grid(n), (xc, tc), (xs, ts))
     run.advance(40, 0.005)
@@ -226,6 +231,35 @@ def other_configs(W):
     out["config5_us_per_cell_step"] = (w1 - w0) / (400 * n) * 1e6
     run.close()
     return out
+
+
+def whole_application(xc, tc, xs, ts, end_t=0.32):
+    """oracle/_ref/cellBP_{ref,gpu}_k1 (oracle/build_app.sh): the unmodified reference application on config 1, El Topo on; wall
+    time of the whole process divided by its steps.  Startup (CUDA context ~1 s) is inside the GPU number: measured twice."""
+    import subprocess
+    import tempfile
+    from wholecellfe_b200.meshio import write_ecomsol
+    exe = {k: os.path.join(ROOT, "oracle", "_ref", "cellBP_%s_k1" % k) for k in ("ref", "gpu")}
+    if not all(os.path.exists(v) for v in exe.values()):
+        return {"whole_application": "skipped: oracle/_ref/cellBP_{ref,gpu}_k1 not built"}
+    tpl = open(os.path.join(ROOT, "tests", "golden", "reference_script_template.txt")).read()
+    res = {}
+    with tempfile.TemporaryDirectory() as w:
+        os.makedirs(os.path.join(w, "scripts"))
+        write_ecomsol(os.path.join(w, "scripts", "disk.txt"), xc, tc); write_ecomsol(os.path.join(w, "scripts", "subs.txt"), xs, ts)
+        for k in ("ref", "gpu"):
+            t = {}
+            for e in (end_t, 2 * end_t):
+                open(os.path.join(w, "cell.txt"), "w").write(tpl.format(end_t=e, max_edge=2, improve=1, topo=1, collide=1, mesh="scripts/disk.txt"))
+                open(os.path.join(w, "subs.txt"), "w").write(tpl.format(end_t=e, max_edge=8, improve=1, topo=1, collide=1, mesh="scripts/subs.txt"))
+                out = os.path.join(w, "out_%s_%g" % (k, e)); os.makedirs(out)
+                w0 = time.perf_counter()
+                subprocess.run([exe[k], "cell.txt", "subs.txt", out], cwd=w, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True, timeout=600)
+                t[e] = time.perf_counter() - w0
+            steps = round(end_t / 0.005)
+            res["config1_whole_app_%s_ms_per_step" % k] = (t[2 * end_t] - t[end_t]) / steps * 1e3     # startup cancels
+    res["whole_app_what"] = "unmodified reference application (main.cpp, El Topo integrate + improve_mesh, two .vtk files per step) on the shipped example, k1; ref = its own UL_growth_explicit.o on one host core, gpu = ul_adapter.cpp + libwcfe (state up/downloaded every step)"
+    return res
 
 
 def main():
