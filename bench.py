@@ -348,19 +348,28 @@ def main():
     except Exception:
         pass
 
-    # end to end: the adapter-mode call sequence with host round trips every step (pinned buffers)
-    e2e_steps = max(2, min(a.steps, 20))
-    t, _, _ = sim.step_n_roundtrip(2, a.dt, t)      # warm-up: pins the host staging buffer, first-touches it
-    barrier()
-    w0 = time.perf_counter()
-    t, h2d, d2h = sim.step_n_roundtrip(e2e_steps, a.dt, t)
-    torch.cuda.synchronize()
-    w1 = time.perf_counter()
-    te = torch.tensor([w1 - w0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = {"value": (ne_c + ne_s) * e2e_steps * world / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": e2e_steps, "what": "wcfe_step_n_roundtrip, every step: predict -> D2H of the predicted positions (cell + substrate, arrays of Vec3d as the reference holds them, pinned) -> H2D of the accepted positions -> update -> D2H of the diagnostics"}
+    # end to end: a host integrator in the loop -- positions to pinned host memory and back EVERY step (wall clock, max over ranks)
+    def time_roundtrip(both):
+        nonlocal t
+        steps = max(2, min(a.steps, 20 if both else 100))
+        t, _, _ = sim.step_n_roundtrip(2, a.dt, t, both_surfaces=both)      # warm-up: pins the host staging buffer, first-touches it
+        barrier()
+        w0 = time.perf_counter()
+        t, h2d, d2h = sim.step_n_roundtrip(steps, a.dt, t, both_surfaces=both)
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        te = torch.tensor([w1 - w0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return (ne_c + ne_s) * steps * world / float(te.item()), h2d, d2h, steps
+    v0, h2d, d2h, e2e_steps = time_roundtrip(False)
+    v1, h2d1, d2h1, steps1 = time_roundtrip(True)
+    e2e = {"value": v0, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "what": "wcfe_step_n_roundtrip, every step: predict -> D2H of the cell's predicted positions (array of Vec3d as the reference holds it, pinned) -> "
+                   "(host integrator) -> H2D of the accepted positions -> update -> D2H of the diagnostics; the frozen substrate's positions (main.cpp:299) "
+                   "do not travel, and the hand-over of step q+1 overlaps the substrate half of step q",
+           "both_surfaces_serial": {"value": v1, "h2d_bytes_per_step": h2d1, "d2h_bytes_per_step": d2h1, "steps": steps1,
+                                    "what": "the same with the substrate's 4M positions also crossing the bus both ways and no overlap (ul_adapter.cpp's traffic pattern)"}}
     x = sim.get(W.CELL, "x")
     if not np.isfinite(x).all():
         raise SystemExit("bench.py: non-finite positions after the run")

@@ -164,9 +164,14 @@ int wcfe_step_n(wcfe_ctx *c, int n, double dt, double *t_io);
  * independent cells per GPU: one host thread keeps every context busy).  wcfe_sync() waits and reports device errors. */
 int wcfe_step_n_async(wcfe_ctx *c, int n, double dt, double *t_io);
 
-/* host round trip per step, as the adapter drives it with El Topo in the loop: predict -> D2H predicted
- * positions of both surfaces into pinned buffers -> H2D of the same buffers as "accepted" positions ->
- * update -> D2H diagnostics.  Used for the end-to-end measurement; returns bytes moved per step. */
+/* host round trip per step, as a host integrator in the loop needs it (El Topo integrate(), main.cpp:248,:316): predict -> D2H of
+ * the predicted positions into pinned buffers (arrays of Vec3d) -> H2D of the same buffers as "accepted" positions -> update ->
+ * D2H of the diagnostics.  Used for the end-to-end measurement; returns the bytes moved per step.
+ * Mode 0 (default): only the CELL's positions travel -- the substrate is frozen (main.cpp:299), its predicted positions are bit
+ * for bit the ones the host holds and wcfe_commit ignores what comes back for it -- and the hand-over of step q+1 overlaps the
+ * substrate half of step q on a second stream.  Mode 1: both surfaces travel, everything serial (what ul_adapter.cpp does, where
+ * the reference application owns every array).  Both give the same state as wcfe_step_n, bit for bit. */
+int wcfe_set_roundtrip_mode(wcfe_ctx *c, int mode);
 int wcfe_step_n_roundtrip(wcfe_ctx *c, int n, double dt, double *t_io, long long *h2d_bytes_per_step, long long *d2h_bytes_per_step);
 
 /* out8: total area, centroid x,y,z (UL:531-535), |Res_cell|, |Res_subs| (UL:593,:472), step counter, time */

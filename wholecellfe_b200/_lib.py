@@ -23,7 +23,7 @@ SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_param
            "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities",
            "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
            "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync",
-           "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed"]
+           "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed", "wcfe_set_roundtrip_mode"]
 
 
 class Params(C.Structure):
@@ -84,6 +84,7 @@ def load():
     L.wcfe_step_n.argtypes = [vp, C.c_int, C.c_double, _dp]
     L.wcfe_step_n_async.argtypes = [vp, C.c_int, C.c_double, _dp]
     L.wcfe_step_n_roundtrip.argtypes = [vp, C.c_int, C.c_double, _dp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.wcfe_set_roundtrip_mode.argtypes = [vp, C.c_int]
     L.wcfe_get_diagnostics.argtypes = [vp, _dp]
     L.wcfe_get_discrete.argtypes = [vp, C.c_int, _ip]
     L.wcfe_get_boundary_flags.argtypes = [vp, C.c_int, _ip]

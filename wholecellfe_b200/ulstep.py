@@ -161,7 +161,9 @@ class ULSim:
         self._ck(self.L.wcfe_step_n_async(self.h, n, dt, C.byref(t)))
         return t.value
 
-    def step_n_roundtrip(self, n, dt, t0):
+    def step_n_roundtrip(self, n, dt, t0, both_surfaces=False):
+        """n steps with the positions handed to the host and back every step; both_surfaces: also the (frozen) substrate's, serial."""
+        self._ck(self.L.wcfe_set_roundtrip_mode(self.h, 1 if both_surfaces else 0))
         t = C.c_double(t0)
         a = C.c_longlong()
         b = C.c_longlong()
