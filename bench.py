@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--mode", default="ensemble", choices=["ensemble", "partition"],
                     help="N > 1: independent replicas (weak scaling, default) or ONE workload with the substrate cut into strips and a "
                          "per-step NCCL halo exchange (strong scaling)")
+    ap.add_argument("--halo", default="peer", choices=["peer", "dist"],
+                    help="--mode partition: border strains pushed into the neighbours' ghost rows by the substrate kernel itself over NVLink peer "
+                         "memory (default), or a host-driven torch.distributed exchange after every step (the baseline)")
     ap.add_argument("--order", default="morton", choices=["morton", "morton_rows"], help="node numbering of the synthetic meshes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the small side measurements (configs 1/2 latency, config 5 batch)")
@@ -176,7 +179,7 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
     elements), every step ends with the NCCL exchange of the strip-border strains.  value counts every element once."""
     import torch
     from wholecellfe_b200.partition import PartitionedSim
-    sim = PartitionedSim(a.variant, cell_mesh, subs_mesh, dist, local, rng=(1, 1))
+    sim = PartitionedSim(a.variant, cell_mesh, subs_mesh, dist, local, rng=(1, 1), halo=a.halo)
     ne = len(cell_mesh[1]) + len(subs_mesh[1])
     sim.step_n(a.warmup, a.dt)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -195,7 +198,8 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
                           "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": "ONE synthetic %d-triangle cell on %d-node substrate, substrate in %d strips, cell replicated"
                                                  % (len(cell_mesh[1]), len(subs_mesh[0]), world), "variant": a.variant, "dt": a.dt,
-                                     "parallelism": "substrate strip partition x%d + per-step NCCL halo exchange (%d border nodes x 24 B per neighbour)" % (world, halo)},
+                                     "parallelism": ("substrate strip partition x%d, halo exchange fused into k_subs_ring over NVLink peer memory (%d border nodes x 24 B per step)" if a.halo == "peer"
+                                                     else "substrate strip partition x%d + per-step torch.distributed (NCCL) halo exchange (%d border nodes x 24 B per step)") % (world, halo)},
                           "gpu_launches": sim.sim.kernel_launches() - l0}), flush=True)
     dist.destroy_process_group()
 

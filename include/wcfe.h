@@ -30,6 +30,7 @@ extern "C" {
 #define WCFE_ERR_UNSUPPORTED (-3)  /* a parameter combination the GPU path does not implement */
 #define WCFE_ERR_CAPACITY (-4)     /* a device-side table overflowed (see wcfe_last_error) */
 #define WCFE_ERR_NUMERIC (-5)      /* NaN/Inf sentinel tripped */
+#define WCFE_ERR_PEER (-6)         /* partitioned run: a neighbouring rank's halo rows did not arrive */
 
 #define WCFE_CELL 0
 #define WCFE_SUBS 1
@@ -190,6 +191,33 @@ int wcfe_force_field(wcfe_ctx *c, int which, double dt, double t_curr, double *o
  * ask again after every step.  Zero-copy interop with torch.distributed for the halo exchange of partitioned meshes. */
 int wcfe_device_ptr(wcfe_ctx *c, int surface, int field, void **ptr, long long *pitch);
 int wcfe_sync(wcfe_ctx *c);
+
+/* ---- one mesh over several GPUs (BASELINE configs[3]: "element-partitioned over 2/4/8 B200 with ... halo exchange"; the reference
+ * itself has no such mode).  Each rank's context holds ONE STRIP of the substrate -- its owned nodes plus a one-ring of
+ * ghost nodes owned by neighbouring ranks, uploaded as an ordinary mesh -- and the whole cell.  The substrate is frozen
+ * (main.cpp:299), so the only per-step data a neighbour needs is the new strain ea of the strip's border nodes.  After
+ * wcfe_halo_connect the substrate kernel itself stores those rows into the neighbours' ghost rows through peer memory (NVLink)
+ * and waits, in-kernel, for its own ghost rows: wcfe_step_n / _async then advance all strips with no host-side exchange, and the
+ * owned nodes of all ranks equal the single-GPU run bit for bit.  All ranks must execute the same number of steps.
+ *   wcfe_halo_info_get   what a neighbour needs to reach this context's strain buffers and arrival counters: raw device addresses
+ *                        (same process) and CUDA IPC handles (other processes of the same node).  Ship the struct as bytes.
+ *   wcfe_halo_connect    peers[q]: the info of neighbour q; my_slot_at_peer[q]: this rank's index in q's own peer list;
+ *                        rows_from_peer[q]: ghost rows q sends here per step; export_*: for every (border node, neighbour) pair the
+ *                        local node, the peer slot and the node's local index AT the peer; ghost_node: local ids of the ghosts.
+ * No step may run between info_get and connect; a host barrier across ranks must follow connect before the first step. */
+#define WCFE_HALO_MAX_PEERS 8
+typedef struct wcfe_halo_info {
+    long long pid;                     /* owner process */
+    int device, ea_cur;                /* CUDA ordinal; which of the two strain buffers is current */
+    long long np;                      /* pitch (doubles) of the strain table: component q of node i at [q*np + i] */
+    unsigned long long ptr[3];         /* device addresses in the owner: ea buffer 0, ea buffer 1, arrival counters */
+    unsigned long long offset[3];      /* of each inside its cudaMalloc allocation (an IPC handle names the allocation) */
+    unsigned char ipc[3][64];          /* cudaIpcMemHandle_t of the three allocations */
+} wcfe_halo_info;
+int wcfe_halo_info_get(wcfe_ctx *c, wcfe_halo_info *out);
+int wcfe_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_halo_info *peers, const int *my_slot_at_peer, const int *rows_from_peer,
+                      int n_export, const int *export_node, const int *export_peer, const int *export_row, int n_ghost, const int *ghost_node);
+int wcfe_halo_disconnect(wcfe_ctx *c);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 from wholecellfe_b200.meshgen import square_mesh, disk_mesh
-from wholecellfe_b200.partition import strip_partition, exchange_rows
+from wholecellfe_b200.partition import strip_partition, exchange_rows, connect_plan, neighbours
 
 
 def _free_port():
@@ -41,6 +41,28 @@ def test_partition_invariants(world):
         have = set(p.elem_gid.tolist())
         for v in p.owned[:: max(1, len(p.owned) // 50)]:
             assert inc[v] <= have
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_connect_plan_is_consistent_across_ranks(world):
+    """what wcfe_halo_connect is told on one rank agrees with what its neighbours are told: every exported (node, row at the
+    peer) names the same global node on both sides, the row counts match, the slots are each other's inverse"""
+    xs, ts = square_mesh(40)
+    parts = strip_partition(xs, ts, world)
+    plans = [connect_plan(parts, r) for r in range(world)]
+    for r, (nb, slot, rows, en, ep, er, gh) in enumerate(plans):
+        assert nb == neighbours(parts[r]) and len(nb) <= 8
+        assert np.array_equal(parts[r].local_nodes[gh], parts[r].ghosts)
+        assert not np.intersect1d(en, gh).size                               # a ghost is never exported
+        for k, q in enumerate(nb):
+            assert plans[q][0][slot[k]] == r                                 # my slot at q really is me
+            sel = ep == k
+            assert np.array_equal(parts[r].local_nodes[en[sel]], parts[q].local_nodes[er[sel]])
+            back = plans[q][0].index(r)
+            assert plans[q][2][back] == int(sel.sum())                       # q expects exactly the rows I push
+        # every ghost row is pushed by exactly one neighbour
+        got = np.concatenate([plans[q][5][plans[q][4] == plans[q][0].index(r)] for q in nb]) if nb else np.zeros(0, int)
+        assert np.array_equal(np.sort(got), np.sort(gh))
 
 
 def _gloo_worker(rank, world, port, q):
@@ -84,14 +106,14 @@ def _initial_strain(nn):
     return ea
 
 
-def _gpu_worker(rank, world, port, backend, q):
+def _gpu_worker(rank, world, port, backend, halo, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dev = rank if backend == "nccl" else 0
     torch.cuda.set_device(dev)
     dist.init_process_group(backend, rank=rank, world_size=world)
     from wholecellfe_b200.partition import PartitionedSim
     xc, tc = disk_mesh(6000); xs, ts = square_mesh(120)
-    sim = PartitionedSim("k31", (xc, tc), (xs, ts), dist, dev, rng=(1, 5))
+    sim = PartitionedSim("k31", (xc, tc), (xs, ts), dist, dev, rng=(1, 5), halo=halo)
     sim.set_subs_field("ea", _initial_strain(len(xs)))
     sim.step_n(12, 2e-4)
     out = {}
@@ -103,13 +125,49 @@ def _gpu_worker(rank, world, port, backend, q):
     dist.barrier(); dist.destroy_process_group()
 
 
+def _single_gpu_reference(steps=12):
+    import wholecellfe_b200 as W
+    xc, tc = disk_mesh(6000); xs, ts = square_mesh(120)
+    g = W.ULSim("k31"); g.upload_mesh(W.CELL, xc, tc); g.upload_mesh(W.SUBS, xs, ts); g.set_rng(1, 5)
+    g.set(W.SUBS, "ea", _initial_strain(len(xs)))
+    g.step_n(steps, 2e-4, 0.0)
+    return g
+
+
 @pytest.mark.gpu
-def test_two_rank_partition_equals_single_gpu_bitwise():
+@pytest.mark.parametrize("world", [2, 3])
+def test_in_process_strips_with_fused_peer_halo_equal_single_gpu_bitwise(world):
+    """the fused halo exchange (border strains stored into the neighbours' ghost rows by k_subs_ring itself, arrival counters
+    awaited in-kernel) on strips that live in one process: the owned nodes of all strips tile the single-GPU result bit for bit"""
+    import wholecellfe_b200 as W
+    from wholecellfe_b200.partition import InProcessStrips
+    xc, tc = disk_mesh(6000); xs, ts = square_mesh(120)
+    ndev = torch.cuda.device_count()
+    run = InProcessStrips("k31", (xc, tc), (xs, ts), [r % ndev for r in range(world)], rng=(1, 5))
+    run.set_subs_field("ea", _initial_strain(len(xs)))
+    run.step_n(5, 2e-4); run.step_n(7, 2e-4)
+    g = _single_gpu_reference()
+    for f in ("V", "A", "ea"):
+        ref = g.get(W.SUBS, f)
+        got = np.full_like(ref, np.nan)
+        for r in range(world):
+            ids, vals = run.owned_field(r, f)
+            got[ids] = vals
+        assert np.array_equal(got, ref), f
+    for sim in run.sims:
+        assert np.array_equal(sim.get(W.CELL, "x"), g.get(W.CELL, "x"))
+    assert np.abs(g.get(W.SUBS, "ea")).max() > 1e-5 and np.abs(g.get(W.SUBS, "A")).max() > 0
+    run.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("halo", ["peer", "dist"])
+def test_two_rank_partition_equals_single_gpu_bitwise(halo):
     import wholecellfe_b200 as W
     world = 2
     backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
     ctx = mp.get_context("spawn"); q = ctx.Queue(); port = _free_port()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, backend, q)) for r in range(world)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, backend, halo, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=600) for _ in procs)

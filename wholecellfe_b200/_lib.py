@@ -7,7 +7,8 @@ LIB_PATH = os.environ.get("WCFE_LIB") or os.path.join(HERE, "libwcfe.so")   # WC
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
-OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_NUMERIC = 0, -1, -2, -3, -4, -5
+OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_NUMERIC, ERR_PEER = 0, -1, -2, -3, -4, -5, -6
+HALO_MAX_PEERS = 8
 CELL, SUBS = 0, 1
 VARIANTS = {"k1": 0, "k31": 1, "kMD": 2}
 FIELDS = {"x": 0, "V": 1, "A": 2, "ea": 3, "cA": 4, "cB": 5, "cC": 6, "fa_u": 7, "X_prev": 8}
@@ -23,7 +24,8 @@ SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_param
            "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities",
            "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
            "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync",
-           "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed", "wcfe_set_roundtrip_mode"]
+           "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed", "wcfe_set_roundtrip_mode",
+           "wcfe_halo_info_get", "wcfe_halo_connect", "wcfe_halo_disconnect"]
 
 
 class Params(C.Structure):
@@ -38,6 +40,12 @@ class Params(C.Structure):
                 ("pin_limit", C.c_double), ("t_i", C.c_double), ("t_f", C.c_double),
                 ("md_px", C.c_double * 6), ("md_py", C.c_double * 6), ("md_k", C.c_double * 6),
                 ("c_A_init", C.c_double)]
+
+
+class HaloInfo(C.Structure):
+    """wcfe_halo_info: what a neighbouring rank needs to reach this context's strain buffers (ship it as bytes)"""
+    _fields_ = [("pid", C.c_longlong), ("device", C.c_int), ("ea_cur", C.c_int), ("np", C.c_longlong),
+                ("ptr", C.c_ulonglong * 3), ("offset", C.c_ulonglong * 3), ("ipc", (C.c_ubyte * 64) * 3)]
 
 
 _lib = None
@@ -93,5 +101,8 @@ def load():
     L.wcfe_force_field.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp]
     L.wcfe_device_ptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
     L.wcfe_sync.argtypes = [vp]
+    L.wcfe_halo_info_get.argtypes = [vp, C.POINTER(HaloInfo)]
+    L.wcfe_halo_connect.argtypes = [vp, C.c_int, C.POINTER(HaloInfo), _ip, _ip, C.c_int, _ip, _ip, _ip, C.c_int, _ip]
+    L.wcfe_halo_disconnect.argtypes = [vp]
     _lib = L
     return L

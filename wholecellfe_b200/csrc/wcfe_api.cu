@@ -11,11 +11,13 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 using namespace wcfe;
 
@@ -146,6 +148,17 @@ struct wcfe_ctx {
     double last_ms = 0, t_last = 0;
     bool have_predict[2] = {false, false};
     bool tape_busy = false;               // an async step_n may still be reading the pinned RNG tape
+    // partitioned substrate: fused peer-memory halo exchange (HaloView, wcfe_patch.cuh)
+    struct {
+        bool have_info = false, active = false;
+        int info_ea_cur = 0, npeer = 0;
+        unsigned int step = 0;                           // steps since the connect
+        DevBuf<unsigned long long> flags;                // arrival counters, one per peer slot, bumped by the peers
+        DevBuf<unsigned char> patch_role, node_role;
+        DevBuf<int> exp_ptr, exp_ent;
+        DevBuf<HaloPeer> peers;
+        std::vector<void *> opened;                      // IPC mappings to close
+    } halo;
     int roundtrip_mode = 0;               // wcfe_step_n_roundtrip: 0 cell only + overlapped, 1 both surfaces serial
     std::string err;
 };
@@ -553,6 +566,7 @@ int check_device_errors_bits(wcfe_ctx *c, int e) {
     if (e & ERR_NAN) return fail(c, WCFE_ERR_NUMERIC, "non-finite cell area / centroid: the explicit step went unstable (dt above the stability limit of the stiffest spring?)");
     if (e & ERR_BUCKET_OVERFLOW) return fail(c, WCFE_ERR_CAPACITY, "triangle bucket overflow: more anchors in one substrate triangle than the capacity sized at upload");
     if (e & ERR_REGION) return fail(c, WCFE_ERR_CAPACITY, "an integrin anchor left the padded cell region; re-commit positions to refresh it");
+    if (e & ERR_HALO_TIMEOUT) return fail(c, WCFE_ERR_PEER, "halo exchange: a neighbouring rank's strain rows did not arrive within 10 s (the peer stopped stepping, or the ranks ran different step counts)");
     return WCFE_OK;
 }
 
@@ -620,6 +634,8 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         bt.head = (long long)(c->b_head.n / R); bt.items = (long long)(c->b_items.n / R);
     }
     const unsigned int R = (unsigned int)c->nrep;
+    if (c->halo.active && (which & 2) && (!planar || c->subs_kernel != 2 || batch || c->debug))
+        return fail(c, WCFE_ERR_UNSUPPORTED, "a halo-connected substrate strip runs the planar k_subs_ring path only (flat meshes, one replica, no debug capture)");
     const double *v_old = cs.V.p, *a_old = cs.A.p;      // general path: V, A are updated in place
     if (!(which & 1)) goto subs_half;
     if (planar) {
@@ -707,11 +723,19 @@ subs_half:
         ProfScope ps(c, K_SUBS);
         const size_t smem = ring_smem_bytes(ss.max_halo, ss.ring_stride);
         PatchView pvs = pview(ss);
-        if (pdl && batch) CK(launch_pdl(k_subs_ring<false, true>, dim3(ss.npatch, R), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt));
-        else if (pdl) CK(launch_pdl(k_subs_ring<false, false>, dim3(ss.npatch), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt));
-        else if (batch) k_subs_ring<false, true><<<dim3(ss.npatch, R), kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt);
-        else if (c->debug) k_subs_ring<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss), bt);
-        else k_subs_ring<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt);
+        const HaloView nohalo{};
+        if (c->halo.active) {
+            // partitioned substrate: border strains go straight into the neighbours' ghost rows, ghost rows are awaited in-kernel
+            HaloView hv{c->halo.patch_role.p, c->halo.node_role.p, c->halo.exp_ptr.p, c->halo.exp_ent.p, c->halo.peers.p, c->halo.flags.p, c->halo.npeer, c->halo.step, c->d_err.p};
+            if (pdl) CK(launch_pdl(k_subs_ring<false, false, true>, dim3(ss.npatch), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, hv));
+            else k_subs_ring<false, false, true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, hv);
+            c->halo.step++;
+        }
+        else if (pdl && batch) CK(launch_pdl(k_subs_ring<false, true>, dim3(ss.npatch, R), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo));
+        else if (pdl) CK(launch_pdl(k_subs_ring<false, false>, dim3(ss.npatch), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo));
+        else if (batch) k_subs_ring<false, true><<<dim3(ss.npatch, R), kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo);
+        else if (c->debug) k_subs_ring<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss), bt, nohalo);
+        else k_subs_ring<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo);
     } else if (planar && c->use_pipe) {
         // persistent, software-pipelined substrate kernel: grid = SMs x 3 resident CTAs
         ProfScope ps(c, K_SUBS);
@@ -778,6 +802,30 @@ int replicate_state(wcfe_ctx *c, int surface) {
     }
     CK(cudaStreamSynchronize(c->stream));
     return WCFE_OK;
+}
+
+typedef int (*cuMemGetAddressRange_t)(unsigned long long *, size_t *, unsigned long long);
+// base address of the cudaMalloc allocation a pointer lives in (an IPC handle names the allocation, and the runtime may carve
+// several small cudaMallocs out of one); the driver entry point is fetched through the runtime so that libwcfe.so does not
+// link libcuda (it must load on a machine without a driver for the symbol check)
+int alloc_base(wcfe_ctx *c, const void *ptr, unsigned long long *base) {
+    static cuMemGetAddressRange_t fn = nullptr;
+    if (!fn) {
+        void *f = nullptr; cudaDriverEntryPointQueryResult qr;
+        CK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &qr));
+        if (!f || qr != cudaDriverEntryPointSuccess) return fail(c, WCFE_ERR_CUDA, "cuMemGetAddressRange not available from this driver");
+        fn = (cuMemGetAddressRange_t)f;
+    }
+    size_t size = 0;
+    if (fn(base, &size, (unsigned long long)(uintptr_t)ptr) != 0) return fail(c, WCFE_ERR_CUDA, "cuMemGetAddressRange failed");
+    return WCFE_OK;
+}
+void halo_release(wcfe_ctx *c) {
+    if (c->halo.active || !c->halo.opened.empty()) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    for (void *m : c->halo.opened) cudaIpcCloseMemHandle(m);
+    c->halo.opened.clear();
+    c->halo.active = false; c->halo.have_info = false; c->halo.npeer = 0; c->halo.step = 0;
+    c->halo.flags.release(); c->halo.patch_role.release(); c->halo.node_role.release(); c->halo.exp_ptr.release(); c->halo.exp_ent.release(); c->halo.peers.release();
 }
 
 int ready(wcfe_ctx *c) {
@@ -877,7 +925,7 @@ static int create_impl(wcfe_ctx **out, int device, const wcfe_params *p, int rep
         if (const char *e = std::getenv("WCFE_PDL")) c->use_pdl = std::atoi(e);
         const void *pk[] = {(const void *)k_subs_ring<false>, (const void *)k_subs_ring<true>, (const void *)k_subs_pipe<false>, (const void *)k_subs_pipe<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
                             (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>,
-                            (const void *)k_cell_patch<true, false, true>, (const void *)k_subs_ring<false, true>};
+                            (const void *)k_cell_patch<true, false, true>, (const void *)k_subs_ring<false, true>, (const void *)k_subs_ring<false, false, true>};
         for (const void *f : pk) {
             // 227 KB is the per-CTA limit including the kernels' small static arrays
             if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kPatchSmemMax)) != cudaSuccess) return bail("cudaFuncSetAttribute(max dynamic smem)", e);
@@ -910,6 +958,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     if (!c) return WCFE_ERR_ARG;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    halo_release(c);
     for (int q = 0; q < 2; q++) {
         Surface &s = c->s[q];
         s.d_tri.release(); s.d_ring_ptr.release(); s.d_ring.release();
@@ -966,6 +1015,7 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
     if (!c || surface < 0 || surface > 1 || nn <= 0 || ne <= 0 || !xyz || !tri) return fail(c, WCFE_ERR_ARG, "upload_mesh: bad arguments (empty meshes are not simulated)");
     for (int q = 0; q < 3 * ne; q++) if (tri[q] < 0 || tri[q] >= nn) return fail(c, WCFE_ERR_ARG, "upload_mesh: triangle refers to a vertex outside [0, nn)");
     CK(cudaSetDevice(c->device));
+    if (surface == WCFE_SUBS) halo_release(c);       // a new strip: the neighbours' tables no longer describe it
     Surface &s = c->s[surface];
     s.nn = nn; s.ne = ne; s.np = (nn + 31) / 32 * 32; s.nep = (ne + 31) / 32 * 32;
     s.tri.assign(tri, tri + 3 * (size_t)ne);
@@ -1493,6 +1543,122 @@ int wcfe_device_ptr(wcfe_ctx *c, int surface, int field, void **ptr, long long *
     double *d = field_dev(c, surface, field);
     if (!d || !c->s[surface].nn) return fail(c, WCFE_ERR_ARG, "device_ptr: no such field on this surface (or no mesh)");
     *ptr = d; *pitch = c->s[surface].np;
+    return WCFE_OK;
+}
+
+/* ---- partitioned substrate: peer-memory halo exchange fused into k_subs_ring (HaloView, wcfe_patch.cuh) ------------------- */
+int wcfe_halo_info_get(wcfe_ctx *c, wcfe_halo_info *out) {
+    int rc = ready(c);
+    if (rc) return rc;
+    if (!out) return WCFE_ERR_ARG;
+    NO_BATCH(c, "halo_info_get");
+    CK(cudaSetDevice(c->device));
+    Surface &ss = c->s[WCFE_SUBS];
+    if (!use_planar(c) || c->subs_kernel != 2) return fail(c, WCFE_ERR_UNSUPPORTED, "halo exchange needs the planar k_subs_ring path (flat meshes)");
+    halo_release(c);
+    CK(c->halo.flags.alloc(WCFE_HALO_MAX_PEERS));
+    CK(cudaMemset(c->halo.flags.p, 0, sizeof(unsigned long long) * WCFE_HALO_MAX_PEERS));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaDeviceSynchronize());
+    memset(out, 0, sizeof(*out));
+    out->pid = (long long)getpid(); out->device = c->device; out->ea_cur = ss.ea_cur; out->np = ss.np;
+    const void *ptrs[3] = {ss.ea[0].p, ss.ea[1].p, c->halo.flags.p};
+    for (int q = 0; q < 3; q++) {
+        unsigned long long base = 0;
+        if ((rc = alloc_base(c, ptrs[q], &base))) return rc;
+        out->ptr[q] = (unsigned long long)(uintptr_t)ptrs[q];
+        out->offset[q] = out->ptr[q] - base;
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, (void *)(uintptr_t)base));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(out->ipc[q], &h, 64);
+    }
+    c->halo.have_info = true; c->halo.info_ea_cur = ss.ea_cur;
+    return WCFE_OK;
+}
+
+int wcfe_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_halo_info *peers, const int *my_slot_at_peer, const int *rows_from_peer,
+                      int n_export, const int *export_node, const int *export_peer, const int *export_row, int n_ghost, const int *ghost_node) {
+    int rc = ready(c);
+    if (rc) return rc;
+    NO_BATCH(c, "halo_connect");
+    if (n_peers < 0 || n_peers > WCFE_HALO_MAX_PEERS || n_export < 0 || n_ghost < 0 || (n_peers && (!peers || !my_slot_at_peer || !rows_from_peer)) ||
+        (n_export && (!export_node || !export_peer || !export_row)) || (n_ghost && !ghost_node))
+        return fail(c, WCFE_ERR_ARG, "halo_connect: bad arguments (at most WCFE_HALO_MAX_PEERS neighbours)");
+    Surface &ss = c->s[WCFE_SUBS];
+    if (!c->halo.have_info || c->halo.info_ea_cur != ss.ea_cur) return fail(c, WCFE_ERR_ARG, "halo_connect: call wcfe_halo_info_get first, and do not step in between");
+    CK(cudaSetDevice(c->device));
+    const long long mypid = (long long)getpid();
+    std::vector<HaloPeer> hp((size_t)std::max(1, n_peers));
+    std::vector<std::pair<std::vector<unsigned char>, void *>> maps;      // IPC handle bytes -> mapped base (a handle is opened once)
+    for (int q = 0; q < n_peers; q++) {
+        const wcfe_halo_info &pi = peers[q];
+        if (my_slot_at_peer[q] < 0 || my_slot_at_peer[q] >= WCFE_HALO_MAX_PEERS || rows_from_peer[q] < 0) return fail(c, WCFE_ERR_ARG, "halo_connect: bad peer slot / row count");
+        void *mapped[3];
+        for (int w = 0; w < 3; w++) {
+            if (pi.pid == mypid) {      // the neighbour strip lives in this process: plain pointers (peer access if it is on another GPU)
+                if (pi.device != c->device) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(pi.device, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    else if (e != cudaSuccess) return fail(c, WCFE_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                }
+                mapped[w] = (void *)(uintptr_t)pi.ptr[w];
+                continue;
+            }
+            std::vector<unsigned char> key(pi.ipc[w], pi.ipc[w] + 64);
+            void *base = nullptr;
+            for (auto &m : maps) if (m.first == key) base = m.second;
+            if (!base) {
+                cudaIpcMemHandle_t h; memcpy(&h, pi.ipc[w], 64);
+                cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) { cudaGetLastError(); return fail(c, WCFE_ERR_CUDA, std::string("cudaIpcOpenMemHandle (peer GPU memory): ") + cudaGetErrorString(e)); }
+                maps.emplace_back(key, base); c->halo.opened.push_back(base);
+            }
+            mapped[w] = (char *)base + pi.offset[w];
+        }
+        // the peer writes ea[ea_cur ^ 1] in its first step after the connect, ea[ea_cur] in the second, ...
+        hp[q].ea[0] = (double *)mapped[pi.ea_cur ^ 1]; hp[q].ea[1] = (double *)mapped[pi.ea_cur];
+        hp[q].np = pi.np;
+        hp[q].flag = (unsigned long long *)mapped[2] + my_slot_at_peer[q];
+        hp[q].nrecv = (unsigned long long)rows_from_peer[q];
+    }
+    // roles and the per-patch export lists
+    std::vector<unsigned char> nrole((size_t)ss.np, 0), prole((size_t)ss.npatch, 0);
+    for (int q = 0; q < n_ghost; q++) {
+        const int g = ghost_node[q];
+        if (g < 0 || g >= ss.nn) return fail(c, WCFE_ERR_ARG, "halo_connect: ghost node outside the strip");
+        nrole[g] = 1;
+        prole[g / kPatch] |= 3;
+        for (int r = ss.ring_ptr[g]; r < ss.ring_ptr[g + 1]; r++) {       // every patch that has the ghost in its node table reads its row
+            const int *tr = &ss.tri[3 * (size_t)(ss.ring[r] >> 2)];
+            for (int j = 0; j < 3; j++) prole[tr[j] / kPatch] |= 1;
+        }
+    }
+    std::vector<std::vector<int>> per_patch((size_t)ss.npatch);
+    for (int q = 0; q < n_export; q++) {
+        const int v = export_node[q], pq = export_peer[q];
+        if (v < 0 || v >= ss.nn || pq < 0 || pq >= n_peers || export_row[q] < 0 || export_row[q] >= peers[pq].np || nrole[v] == 1)
+            return fail(c, WCFE_ERR_ARG, "halo_connect: export entry out of range (node, peer slot, or row at the peer), or a ghost exported");
+        nrole[v] = 2;
+        prole[v / kPatch] |= 2;
+        per_patch[v / kPatch].push_back(v % kPatch); per_patch[v / kPatch].push_back(pq); per_patch[v / kPatch].push_back(export_row[q]);
+    }
+    std::vector<int> eptr((size_t)ss.npatch + 1, 0), eent;
+    for (int p = 0; p < ss.npatch; p++) { eent.insert(eent.end(), per_patch[p].begin(), per_patch[p].end()); eptr[p + 1] = (int)(eent.size() / 3); }
+    if (eent.empty()) eent.assign(3, 0);
+    CK(c->halo.node_role.alloc(nrole.size())); CK(c->halo.patch_role.alloc(prole.size())); CK(c->halo.exp_ptr.alloc(eptr.size())); CK(c->halo.exp_ent.alloc(eent.size())); CK(c->halo.peers.alloc(hp.size()));
+    CK(cudaMemcpy(c->halo.node_role.p, nrole.data(), nrole.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->halo.patch_role.p, prole.data(), prole.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->halo.exp_ptr.p, eptr.data(), sizeof(int) * eptr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->halo.exp_ent.p, eent.data(), sizeof(int) * eent.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->halo.peers.p, hp.data(), sizeof(HaloPeer) * hp.size(), cudaMemcpyHostToDevice));
+    c->halo.npeer = n_peers; c->halo.step = 0; c->halo.active = true;
+    return WCFE_OK;
+}
+
+int wcfe_halo_disconnect(wcfe_ctx *c) {
+    if (!c) return WCFE_ERR_ARG;
+    halo_release(c);
     return WCFE_OK;
 }
 

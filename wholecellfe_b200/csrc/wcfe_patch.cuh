@@ -271,9 +271,66 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
 #ifndef WCFE_RING_MINBLK
 #define WCFE_RING_MINBLK 5
 #endif
-template <bool DBG, bool BATCH = false>
+
+// ---- partitioned substrate (BASELINE configs[3], SURVEY 8e second mode): halo exchange fused into the kernel -------------------
+// A rank holds one strip of the substrate plus a one-ring of GHOST nodes owned by its neighbours.  The only per-step data a
+// neighbour needs is the new strain of the strip's border nodes (positions are frozen, V and A are read by their owner alone).
+// HALO = true: the thread that owns a border node stores the node's new strain into its own ea_out AND, through peer memory
+// (NVLink: the peer's buffer mapped with cudaIpcOpenMemHandle, or a plain pointer when both strips live in one process),
+// straight into the ghost row of every neighbour that mirrors the node -- then bumps that neighbour's arrival counter with a
+// system-scope release.  A CTA of the NEXT step whose node table contains ghost rows spins (acquire, system scope) until every
+// neighbour's counter has reached steps x rows before it reads them.  No host involvement, no separate exchange kernel, no
+// staging buffer: the transfer rides on the stores the kernel performs anyway.
+//   Safety of writing into the buffer the peer may still be reading (ea is double-buffered, out(s) == in(s-1)): a CTA pushes at
+// its very end, after all of its ghost reads; every CTA that reads a ghost row owns a border node (an owned node next to a
+// ghost is mirrored on that ghost's owner), so the peer's border CTAs of step s -- the only ones that push -- start after ALL
+// border CTAs of my step s-1 have pushed, i.e. after every one of my step s-1 ghost reads.
+struct HaloPeer {
+    double *ea[2];                   // the peer's strain buffer this rank writes at even / odd steps since the connect
+    long long np;                    // its pitch
+    unsigned long long *flag;        // this rank's arrival counter in the peer's memory
+    unsigned long long nrecv;        // rows the peer pushes to this rank per step
+};
+struct HaloView {
+    const unsigned char *patch_role; // [npatch] bit 0: reads ghost rows (wait first), bit 1: holds ghost or border nodes
+    const unsigned char *node_role;  // [np] 1 ghost (computed by its owner: no stores here), 2 border (mirrored on a peer)
+    const int *exp_ptr;              // [npatch+1] into exp_ent
+    const int *exp_ent;              // triples (local thread, peer slot, row at the peer), grouped by patch
+    const HaloPeer *peer;            // [npeer]
+    const unsigned long long *flags; // [npeer] arrival counters in MY memory, bumped by the peers
+    int npeer;
+    unsigned int step;               // steps since the connect
+    int *err;
+};
+enum : int { ERR_HALO_TIMEOUT = 16 };
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_inc(unsigned long long *p) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(1ull) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// one thread: wait until every neighbour's rows of the previous step have arrived.  Bounded: after 10 s (a peer died) the error
+// flag is raised and this and every later wait returns at once -- a wrong answer that is reported, never a hung GPU.
+__device__ __noinline__ void halo_wait(const HaloView &hv) {
+    if (hv.step == 0) return;
+    const unsigned long long t0 = global_ns();
+    for (int q = 0; q < hv.npeer; q++) {
+        const unsigned long long want = (unsigned long long)hv.step * hv.peer[q].nrecv;
+        while (ld_acquire_sys(hv.flags + q) < want) {
+            if (*(volatile int *)hv.err & ERR_HALO_TIMEOUT) return;
+            if (global_ns() - t0 > 10000000000ull) { atomicOr(hv.err, ERR_HALO_TIMEOUT); return; }
+            __nanosleep(64);
+        }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copies below read the rows through the async proxy
+}
+
+template <bool DBG, bool BATCH = false, bool HALO = false>
 __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k_, double dt, double dt_real,
-                                                         double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg, BatchView bt) {
+                                                         double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg, BatchView bt, HaloView hv) {
     extern __shared__ __align__(128) unsigned char smraw[];
     pdl_launch_dependents();      // the next step's cell kernel may stage its patches behind this kernel's last wave
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
@@ -290,7 +347,9 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     const int nown = min(kPatch, s.nn - n0);
     const int ncopy = min(kPatch, s.np - n0);
     const int np = s.np;
+    const int prole = HALO ? (int)hv.patch_role[p] : 0;
     if (tid == 0) {
+        if (HALO && (prole & 1)) halo_wait(hv);              // the neighbours' strain rows of the previous step have landed
         mbar_init(bar, 1);
         const unsigned int nb = (unsigned int)ncopy * 8u;
         mbar_expect_tx(bar, (unsigned int)pv.ring_stride + 5u * nb);
@@ -303,6 +362,7 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     const bool own = tid < nown;
     double V0 = 0, V1 = 0, A0v = 0, A1v = 0;
     if (own) { V0 = s.V[i]; V1 = s.V[np + i]; A0v = s.A[i]; A1v = s.A[np + i]; }
+    const int nrole = (HALO && (prole & 2) && own) ? (int)hv.node_role[i] : 0;
     __syncthreads();
     mbar_wait(bar, 0);
     const int nh = ((const int *)sblob)[0];
@@ -315,11 +375,21 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     // component instead of the average plus a multiply-add (the FP64 pipe, not HBM, is what this kernel saturates first)
     const double two3 = 2.0 / 3.0;
     sxy[tid] = myxy; se01[tid] = make_double2(two3 * mye01.x, two3 * mye01.y); se3[tid] = two3 * mye3;
-    for (int l = tid; l < nh; l += kPatch) {
-        const int g = halo_ids[l];
-        sxy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
-        se01[kPatch + l] = make_double2(two3 * s.ea_in[g], two3 * s.ea_in[np + g]);
-        se3[kPatch + l] = two3 * s.ea_in[3 * (size_t)np + g];
+    if (HALO && (prole & 1)) {
+        // ghost rows were written by a peer GPU into L2 while this kernel was already running: read them past the (incoherent) L1
+        for (int l = tid; l < nh; l += kPatch) {
+            const int g = halo_ids[l];
+            sxy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
+            se01[kPatch + l] = make_double2(two3 * __ldcg(s.ea_in + g), two3 * __ldcg(s.ea_in + np + g));
+            se3[kPatch + l] = two3 * __ldcg(s.ea_in + 3 * (size_t)np + g);
+        }
+    } else {
+        for (int l = tid; l < nh; l += kPatch) {
+            const int g = halo_ids[l];
+            sxy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
+            se01[kPatch + l] = make_double2(two3 * s.ea_in[g], two3 * s.ea_in[np + g]);
+            se3[kPatch + l] = two3 * s.ea_in[3 * (size_t)np + g];
+        }
     }
     __syncthreads();
     if (!own) return;
@@ -382,6 +452,7 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     // one thread always waits: this kernel's completion then implies that of the boundary finish, which the next cell kernel
     // (chained behind this kernel only) depends on; it also re-zeroes the big-bucket list k_bucket_reduce has consumed
     if (blockIdx.x == 0 && tid == 0) { pdl_wait(); if (bk.big_count) *bk.big_count = 0; }
+    if (HALO && nrole == 1) return;          // ghost node (incomplete fan): its owner computes it and stores the result here
     if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
         pdl_wait();               // first touch of what the cell kernel produced (buckets, anchor records); all above overlaps its tail
         const int gb = s.ring_ptr[i];
@@ -426,7 +497,20 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     node_update_r(Fx - rx, mm, imm, k.damp, k.rho, dt, dt_real, Vh0, V0, A0v);            // UL:471-503
     node_update_r(Fy - ry, mm, imm, k.damp, k.rho, dt, dt_real, Vh1, V1, A1v);
     s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
-    s.ea_out[i] = ea0 + q0 * imm; s.ea_out[np + i] = ea1 + q1 * imm; s.ea_out[3 * np + i] = ea3 + q3 * imm;
+    const double en0 = ea0 + q0 * imm, en1 = ea1 + q1 * imm, en3 = ea3 + q3 * imm;
+    s.ea_out[i] = en0; s.ea_out[np + i] = en1; s.ea_out[3 * np + i] = en3;
+    if (HALO && nrole == 2) {
+        // border node: the same three words go straight into the ghost row of every neighbour that mirrors it, then the
+        // neighbour's arrival counter is bumped (release: the row is visible before the count)
+        for (int q = hv.exp_ptr[p]; q < hv.exp_ptr[p + 1]; q++) {
+            if (hv.exp_ent[3 * q] != tid) continue;
+            const HaloPeer pr = hv.peer[hv.exp_ent[3 * q + 1]];
+            const long long row = hv.exp_ent[3 * q + 2];
+            double *dst = pr.ea[hv.step & 1];
+            dst[row] = en0; dst[pr.np + row] = en1; dst[3 * pr.np + row] = en3;
+            red_release_sys_inc(pr.flag);
+        }
+    }
     if (DBG) {
         dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
         dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;

@@ -6,8 +6,15 @@ because every kernel is deterministic -- so the only data that has to cross betw
 substrate nodes on the strip borders (3 doubles per node; positions never change, V and A are only read by their owner).
 Ghost nodes are recomputed with incomplete one-rings and overwritten by the exchange before anything reads them.
 
-Host logic only: strip partition, local meshes, send/receive index lists, and the exchange itself through torch.distributed
-(NCCL on device tensors that alias libwcfe's own buffers; gloo on CPU tensors in the tests).
+Two ways to move the border strains:
+  halo="peer" (default)  fused into the substrate kernel: the thread that owns a border node stores its new strain straight into
+                         the neighbours' ghost rows through peer memory (NVLink; CUDA IPC mappings between the ranks' processes)
+                         and bumps an arrival counter; the next step's border CTAs wait for the counters in-kernel.  No host work
+                         per step, the programmatic-dependent-launch chain of the step stays intact (wcfe_halo_connect).
+  halo="dist"            a host-driven exchange after every step through torch.distributed (NCCL on device tensors that alias
+                         libwcfe's own buffers; gloo on CPU tensors in the tests).  Kept as the baseline the fused path is measured
+                         against, and as the only path between nodes.
+Host logic here: strip partition, local meshes, send/receive index lists, the connect plan.
 """
 import numpy as np
 
@@ -71,6 +78,83 @@ def strip_partition(xyz, tri, world):
     return out
 
 
+def neighbours(part):
+    """ranks this strip exchanges rows with, ascending: the peer-slot order of wcfe_halo_connect"""
+    return sorted(set(part.send) | set(part.recv))
+
+
+def connect_plan(parts, rank):
+    """Arguments of wcfe_halo_connect for `rank`, from the partition every rank computes identically: (neighbour ranks,
+    my_slot_at_peer, rows_from_peer, export_node, export_peer, export_row, ghost_node)."""
+    me = parts[rank]
+    nb = neighbours(me)
+    my_slot = [neighbours(parts[q]).index(rank) for q in nb]
+    rows_from = [len(me.recv.get(q, ())) for q in nb]
+    en, ep, er = [], [], []
+    for slot, q in enumerate(nb):
+        mine = me.send.get(q)
+        if mine is None:
+            continue
+        theirs = parts[q].recv[rank]                        # the same nodes, as q numbers them (same order: test_partition_invariants)
+        en.append(mine); ep.append(np.full(len(mine), slot)); er.append(theirs)
+    cat = lambda v: np.concatenate(v).astype(np.int32) if v else np.zeros(0, np.int32)
+    ghost_local = np.searchsorted(me.local_nodes, me.ghosts).astype(np.int32)
+    return nb, my_slot, rows_from, cat(en), cat(ep), cat(er), ghost_local
+
+
+class InProcessStrips:
+    """All strips of a partitioned run driven by ONE process: one context per strip on the given devices (several strips may share
+    a GPU), connected through plain device pointers (peer access between GPUs).  Strips advance in lockstep, one step queued on
+    every strip before the next: a strip's step s+1 waits in-kernel for its neighbours' step s, which is already in flight."""
+
+    def __init__(self, variant, cell_mesh, subs_mesh, devices, rng=(1, 1), params=None):
+        from . import ulstep
+        from ._lib import CELL, SUBS
+        xs, ts = subs_mesh
+        self.parts = strip_partition(xs, ts, len(devices))
+        self.sims = []
+        for part, dev in zip(self.parts, devices):
+            sim = ulstep.ULSim(variant, device=dev, params=params)
+            sim.upload_mesh(CELL, cell_mesh[0], cell_mesh[1])
+            sim.upload_mesh(SUBS, xs[part.local_nodes], part.tri_local)
+            sim.set_rng(*rng)
+            self.sims.append(sim)
+        self.SUBS = SUBS
+        self.t = 0.0
+        self.connected = False
+
+    def set_subs_field(self, field, global_values):
+        for part, sim in zip(self.parts, self.sims):
+            sim.set(self.SUBS, field, np.asarray(global_values)[part.local_nodes])
+
+    def connect(self):
+        infos = [sim.halo_info() for sim in self.sims]
+        for r, sim in enumerate(self.sims):
+            nb, slot, rows, en, ep, er, gh = connect_plan(self.parts, r)
+            sim.halo_connect([infos[q] for q in nb], slot, rows, en, ep, er, gh)
+        self.connected = True
+
+    def step_n(self, n, dt):
+        if not self.connected:
+            self.connect()
+        t = self.t
+        for _ in range(n):
+            for sim in self.sims:
+                t1 = sim.step_n_async(1, dt, t)
+            t = t1
+        for sim in self.sims:
+            sim.sync()
+        self.t = t
+
+    def owned_field(self, r, field):
+        part = self.parts[r]
+        return part.owned, self.sims[r].get(self.SUBS, field)[part.owned_local]
+
+    def close(self):
+        for sim in self.sims:
+            sim.close()
+
+
 class _CudaView:
     """__cuda_array_interface__ holder: lets torch alias a libwcfe device buffer without copying."""
 
@@ -115,15 +199,18 @@ def exchange_rows(dist, table, part, comps, device):
 class PartitionedSim:
     """One rank of a substrate-partitioned run: full cell + this rank's substrate strip on one GPU."""
 
-    def __init__(self, variant, cell_mesh, subs_mesh, dist, device_index, rng=(1, 1), params=None):
+    def __init__(self, variant, cell_mesh, subs_mesh, dist, device_index, rng=(1, 1), params=None, halo="peer"):
         import torch
         from . import ulstep
         from ._lib import CELL, SUBS
         self.torch, self.dist = torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = torch.device("cuda", device_index)
+        self.halo = halo
+        self.connected = False
         xs, ts = subs_mesh
-        self.part = strip_partition(xs, ts, self.world)[self.rank]
+        self.parts = strip_partition(xs, ts, self.world)
+        self.part = self.parts[self.rank]
         self.sim = ulstep.ULSim(variant, device=device_index, params=params, stream=torch.cuda.current_stream().cuda_stream)
         self.sim.upload_mesh(CELL, cell_mesh[0], cell_mesh[1])
         self.sim.upload_mesh(SUBS, xs[self.part.local_nodes], self.part.tri_local)
@@ -136,14 +223,29 @@ class PartitionedSim:
         ptr, pitch = self.sim.device_ptr(self.SUBS, "ea")
         return self.torch.as_tensor(_CudaView(ptr, (6, pitch)), device=self.device)
 
+    def connect(self):
+        """halo="peer": exchange the wcfe_halo_info of every rank (addresses + CUDA IPC handles) and wire this strip to its
+        neighbours.  Collective; called by the first step_n, after the last state upload."""
+        infos = [None] * self.world
+        self.dist.all_gather_object(infos, self.sim.halo_info())
+        nb, slot, rows, en, ep, er, gh = connect_plan(self.parts, self.rank)
+        self.sim.halo_connect([infos[q] for q in nb], slot, rows, en, ep, er, gh)
+        self.dist.barrier()                 # nobody pushes before everybody has zeroed counters and mapped buffers
+        self.connected = True
+
     def step(self, dt):
         """one UL step on every rank, then the halo exchange of the substrate strain (xx, yy, xy: the planar components)"""
         self.t = self.sim.step_n_async(1, dt, self.t)
         exchange_rows(self.dist, self._ea_table(), self.part, [0, 1, 3], self.device)
 
     def step_n(self, n, dt):
-        for _ in range(n):
-            self.step(dt)
+        if self.halo == "peer":
+            if not self.connected:
+                self.connect()
+            self.t = self.sim.step_n_async(n, dt, self.t)      # the exchange is inside the substrate kernel
+        else:
+            for _ in range(n):
+                self.step(dt)
         self.sim.sync()
 
     def set_subs_field(self, field, global_values):

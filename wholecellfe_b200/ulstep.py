@@ -202,6 +202,26 @@ class ULSim:
         self._ck(self.L.wcfe_device_ptr(self.h, surface, B.FIELDS[field], C.byref(ptr), C.byref(pitch)))
         return ptr.value, pitch.value
 
+    # ---- partitioned substrate: peer-memory halo exchange fused into the substrate kernel (include/wcfe.h) ----
+    def halo_info(self):
+        """bytes of this context's wcfe_halo_info (addresses + CUDA IPC handles of its strain buffers and arrival counters)"""
+        info = B.HaloInfo()
+        self._ck(self.L.wcfe_halo_info_get(self.h, C.byref(info)))
+        return bytes(info)
+
+    def halo_connect(self, peer_infos, my_slot_at_peer, rows_from_peer, export_node, export_peer, export_row, ghost_node):
+        n = len(peer_infos)
+        arr = (B.HaloInfo * max(1, n))()
+        for q, b in enumerate(peer_infos):
+            C.memmove(C.byref(arr[q]), b, C.sizeof(B.HaloInfo))
+        ia = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        slot, rows, en, ep, er, gn = ia(my_slot_at_peer), ia(rows_from_peer), ia(export_node), ia(export_peer), ia(export_row), ia(ghost_node)
+        ip = lambda a: a.ctypes.data_as(B._ip)
+        self._ck(self.L.wcfe_halo_connect(self.h, n, arr, ip(slot), ip(rows), len(en), ip(en), ip(ep), ip(er), len(gn), ip(gn)))
+
+    def halo_disconnect(self):
+        self._ck(self.L.wcfe_halo_disconnect(self.h))
+
     def kernel_launches(self):
         return int(self.L.wcfe_kernel_launches(self.h))
 
