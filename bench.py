@@ -189,10 +189,31 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
     sim.step_n(a.steps, a.dt)
     e1.record()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    l1 = sim.sim.kernel_launches()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     halo = sum(len(v) for v in sim.part.send.values())
+    # per-kernel durations of this rank's strip (event pairs around every launch: the PDL chain is off in this pass)
+    sim.sim.set_profile(True)
+    sim.step_n(10, a.dt)
+    kms, kcnt = sim.sim.kernel_ms()
+    sim.sim.set_profile(False)
+    names = ["k_predict_cell", "k_bond", "k_cell_patch", "k_boundary_finish", "k_subs_ring", "k_bucket_reduce"]
+    per_kernel = {n: kms[i] / kcnt[i] for i, n in enumerate(names) if kcnt[i]}
+    # parity at full size: every rank repeats the same steps on the WHOLE mesh on its own GPU and compares its owned rows bit for bit
+    import wholecellfe_b200 as W
+    total_steps = a.warmup + a.steps + 10
+    ids, ea_part = sim.owned_field("ea"); _, v_part = sim.owned_field("V")
+    xc_part = sim.sim.get(W.CELL, "x")
+    sim.sim.close()
+    one = W.ULSim(a.variant, device=local)
+    one.upload_mesh(W.CELL, cell_mesh[0], cell_mesh[1]); one.upload_mesh(W.SUBS, subs_mesh[0], subs_mesh[1]); one.set_rng(1, 1)
+    one.step_n(total_steps, a.dt, 0.0)
+    ok = bool(np.array_equal(one.get(W.SUBS, "ea")[ids], ea_part) and np.array_equal(one.get(W.SUBS, "V")[ids], v_part) and np.array_equal(one.get(W.CELL, "x"), xc_part))
+    one.close()
+    okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": ne * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -200,7 +221,9 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
                                                  % (len(cell_mesh[1]), len(subs_mesh[0]), world), "variant": a.variant, "dt": a.dt,
                                      "parallelism": ("substrate strip partition x%d, halo exchange fused into k_subs_ring over NVLink peer memory (%d border nodes x 24 B per step)" if a.halo == "peer"
                                                      else "substrate strip partition x%d + per-step torch.distributed (NCCL) halo exchange (%d border nodes x 24 B per step)") % (world, halo)},
-                          "gpu_launches": sim.sim.kernel_launches() - l0}), flush=True)
+                          "gpu_launches": l1 - l0, "rank0_per_kernel_ms": per_kernel,
+                          "bitwise_equal_to_single_gpu": {"value": bool(int(okt.item())), "steps": total_steps, "what": "owned substrate rows (ea, V) of every rank and the replicated cell's positions against the same steps of the whole mesh on one GPU"},
+                          "rank0_strip": {"substrate_nodes_local": int(len(sim.part.local_nodes)), "owned": int(len(sim.part.owned)), "ghosts": int(len(sim.part.ghosts))}}), flush=True)
     dist.destroy_process_group()
 
 

@@ -154,11 +154,12 @@ struct wcfe_ctx {
         int info_ea_cur = 0, npeer = 0;
         unsigned int step = 0;                           // steps since the connect
         DevBuf<unsigned long long> flags;                // arrival counters, one per peer slot, bumped by the peers
-        DevBuf<unsigned char> patch_role, node_role;
+        DevBuf<unsigned char> node_role;
         DevBuf<int> exp_ptr, exp_ent;
         DevBuf<HaloPeer> peers;
         std::vector<void *> opened;                      // IPC mappings to close
     } halo;
+    int halo_nowait = 0;
     int roundtrip_mode = 0;               // wcfe_step_n_roundtrip: 0 cell only + overlapped, 1 both surfaces serial
     std::string err;
 };
@@ -650,6 +651,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         a.rng_mode = c->rng_mode; a.seed = c->seed; a.step = c->step; a.tape = tape_dev; a.partials = c->d_partials.p;
         a.d_flags = c->d_flags.p; a.d_loc_bond = c->d_loc_bond.p; a.d_loc_cnt = c->d_loc_cnt.p; a.d_loc_first = c->d_loc_first.p;
         a.d_ap_fire = c->d_ap_fire.p; a.err = c->d_err.p; a.debug = c->debug;
+        if (c->halo.active && c->halo.step > 0) { a.halo_peer = c->halo.peers.p; a.halo_npeer = c->halo.npeer; }   // signal the previous step's halo rows
         const size_t smem = patch_smem_bytes(7, 9, cs.max_halo, cs.max_elem, cs.stride);
         npart = cs.npatch;
         if (batch) {
@@ -726,7 +728,8 @@ subs_half:
         const HaloView nohalo{};
         if (c->halo.active) {
             // partitioned substrate: border strains go straight into the neighbours' ghost rows, ghost rows are awaited in-kernel
-            HaloView hv{c->halo.patch_role.p, c->halo.node_role.p, c->halo.exp_ptr.p, c->halo.exp_ent.p, c->halo.peers.p, c->halo.flags.p, c->halo.npeer, c->halo.step, c->d_err.p};
+            HaloView hv{c->halo.node_role.p, c->halo.exp_ptr.p, c->halo.exp_ent.p, c->halo.peers.p, c->halo.flags.p, c->halo.npeer, c->halo.step, c->d_err.p};
+            if (c->halo_nowait) hv.step = 0;    // WCFE_HALO_NOWAIT=1: timing experiment only (no waits, pushes land in the wrong buffer every other step)
             if (pdl) CK(launch_pdl(k_subs_ring<false, false, true>, dim3(ss.npatch), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, hv));
             else k_subs_ring<false, false, true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, hv);
             c->halo.step++;
@@ -825,7 +828,9 @@ void halo_release(wcfe_ctx *c) {
     for (void *m : c->halo.opened) cudaIpcCloseMemHandle(m);
     c->halo.opened.clear();
     c->halo.active = false; c->halo.have_info = false; c->halo.npeer = 0; c->halo.step = 0;
-    c->halo.flags.release(); c->halo.patch_role.release(); c->halo.node_role.release(); c->halo.exp_ptr.release(); c->halo.exp_ent.release(); c->halo.peers.release();
+    if (c->halo.node_role.p && c->s[WCFE_SUBS].p_ring_blob.p)     // clear the role bits in the descriptors' headers
+        cudaMemset2D(c->s[WCFE_SUBS].p_ring_blob.p + 8, (size_t)c->s[WCFE_SUBS].ring_stride, 0, sizeof(int), (size_t)c->s[WCFE_SUBS].npatch);
+    c->halo.flags.release(); c->halo.node_role.release(); c->halo.exp_ptr.release(); c->halo.exp_ent.release(); c->halo.peers.release();
 }
 
 int ready(wcfe_ctx *c) {
@@ -923,6 +928,7 @@ static int create_impl(wcfe_ctx **out, int device, const wcfe_params *p, int rep
         if (const char *e = std::getenv("WCFE_SUBS_PIPE")) { c->use_pipe = std::atoi(e); if (c->use_pipe) c->subs_kernel = 1; }
         if (const char *e = std::getenv("WCFE_SUBS_KERNEL")) c->subs_kernel = std::atoi(e);
         if (const char *e = std::getenv("WCFE_PDL")) c->use_pdl = std::atoi(e);
+        if (const char *e = std::getenv("WCFE_HALO_NOWAIT")) c->halo_nowait = std::atoi(e);
         const void *pk[] = {(const void *)k_subs_ring<false>, (const void *)k_subs_ring<true>, (const void *)k_subs_pipe<false>, (const void *)k_subs_pipe<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
                             (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>,
                             (const void *)k_cell_patch<true, false, true>, (const void *)k_subs_ring<false, true>, (const void *)k_subs_ring<false, false, true>};
@@ -1621,6 +1627,7 @@ int wcfe_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_halo_info *peers, con
         hp[q].np = pi.np;
         hp[q].flag = (unsigned long long *)mapped[2] + my_slot_at_peer[q];
         hp[q].nrecv = (unsigned long long)rows_from_peer[q];
+        hp[q].nsend = 0;
     }
     // roles and the per-patch export lists
     std::vector<unsigned char> nrole((size_t)ss.np, 0), prole((size_t)ss.npatch, 0);
@@ -1640,15 +1647,19 @@ int wcfe_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_halo_info *peers, con
         if (v < 0 || v >= ss.nn || pq < 0 || pq >= n_peers || export_row[q] < 0 || export_row[q] >= peers[pq].np || nrole[v] == 1)
             return fail(c, WCFE_ERR_ARG, "halo_connect: export entry out of range (node, peer slot, or row at the peer), or a ghost exported");
         nrole[v] = 2;
+        hp[pq].nsend++;
         prole[v / kPatch] |= 2;
         per_patch[v / kPatch].push_back(v % kPatch); per_patch[v / kPatch].push_back(pq); per_patch[v / kPatch].push_back(export_row[q]);
     }
     std::vector<int> eptr((size_t)ss.npatch + 1, 0), eent;
     for (int p = 0; p < ss.npatch; p++) { eent.insert(eent.end(), per_patch[p].begin(), per_patch[p].end()); eptr[p + 1] = (int)(eent.size() / 3); }
     if (eent.empty()) eent.assign(3, 0);
-    CK(c->halo.node_role.alloc(nrole.size())); CK(c->halo.patch_role.alloc(prole.size())); CK(c->halo.exp_ptr.alloc(eptr.size())); CK(c->halo.exp_ent.alloc(eent.size())); CK(c->halo.peers.alloc(hp.size()));
+    CK(c->halo.node_role.alloc(nrole.size())); CK(c->halo.exp_ptr.alloc(eptr.size())); CK(c->halo.exp_ent.alloc(eent.size())); CK(c->halo.peers.alloc(hp.size()));
     CK(cudaMemcpy(c->halo.node_role.p, nrole.data(), nrole.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->halo.patch_role.p, prole.data(), prole.size(), cudaMemcpyHostToDevice));
+    {   // role bits into header word 2 of every patch's ring descriptor (the kernel gets them with the descriptor's bulk copy)
+        std::vector<int> w(prole.begin(), prole.end());
+        CK(cudaMemcpy2D(ss.p_ring_blob.p + 8, (size_t)ss.ring_stride, w.data(), sizeof(int), sizeof(int), (size_t)ss.npatch, cudaMemcpyHostToDevice));
+    }
     CK(cudaMemcpy(c->halo.exp_ptr.p, eptr.data(), sizeof(int) * eptr.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->halo.exp_ent.p, eent.data(), sizeof(int) * eent.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->halo.peers.p, hp.data(), sizeof(HaloPeer) * hp.size(), cudaMemcpyHostToDevice));
@@ -1667,6 +1678,7 @@ int wcfe_sync(wcfe_ctx *c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     c->tape_busy = false;
+    harvest_profile(c);
     return (c->s[0].nn && c->s[1].nn) ? check_device_errors(c) : WCFE_OK;
 }
 

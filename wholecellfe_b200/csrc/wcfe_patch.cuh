@@ -277,22 +277,28 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
 // neighbour needs is the new strain of the strip's border nodes (positions are frozen, V and A are read by their owner alone).
 // HALO = true: the thread that owns a border node stores the node's new strain into its own ea_out AND, through peer memory
 // (NVLink: the peer's buffer mapped with cudaIpcOpenMemHandle, or a plain pointer when both strips live in one process),
-// straight into the ghost row of every neighbour that mirrors the node -- then bumps that neighbour's arrival counter with a
-// system-scope release.  A CTA of the NEXT step whose node table contains ghost rows spins (acquire, system scope) until every
-// neighbour's counter has reached steps x rows before it reads them.  No host involvement, no separate exchange kernel, no
-// staging buffer: the transfer rides on the stores the kernel performs anyway.
-//   Safety of writing into the buffer the peer may still be reading (ea is double-buffered, out(s) == in(s-1)): a CTA pushes at
-// its very end, after all of its ghost reads; every CTA that reads a ghost row owns a border node (an owned node next to a
-// ghost is mirrored on that ghost's owner), so the peer's border CTAs of step s -- the only ones that push -- start after ALL
-// border CTAs of my step s-1 have pushed, i.e. after every one of my step s-1 ghost reads.
+// straight into the ghost row of every neighbour that mirrors the node: plain stores, no fence (a system-scope release per
+// border thread was measured at +0.03 ms per step: MEMBAR.SYS waits for the SM's whole store backlog).  The arrival is
+// signalled once per neighbour by ONE thread of the next kernel in the stream, the following step's cell kernel: the kernel
+// boundary (griddepcontrol.wait / stream order) makes all of this kernel's stores visible to that thread, which then bumps the
+// neighbour's arrival counter by the number of rows with a system-scope release.  A CTA of the next step's substrate kernel
+// whose node table contains ghost rows spins (acquire, system scope) until every neighbour's counter has reached steps x rows
+// before it reads them.  No host involvement, no separate exchange kernel, no staging buffer: the transfer rides on the stores
+// the kernel performs anyway, the signal on a kernel that runs anyway.
+//   Safety of writing into the buffer the peer may still be reading (ea is double-buffered, out(s) == in(s-1)): every CTA that
+// pushes owns a border node, i.e. a node next to a ghost, so its own node table holds ghost rows and it WAITS first -- for the
+// neighbours' signal of step s-1, which they send only after their substrate kernel of step s-1 has completed, all of its ghost
+// reads included.  Deadlock-free: substrate(s) waits for the neighbour's cell(s), which waits for nobody.
 struct HaloPeer {
     double *ea[2];                   // the peer's strain buffer this rank writes at even / odd steps since the connect
     long long np;                    // its pitch
     unsigned long long *flag;        // this rank's arrival counter in the peer's memory
     unsigned long long nrecv;        // rows the peer pushes to this rank per step
+    unsigned long long nsend;        // rows this rank pushes to the peer per step
 };
 struct HaloView {
-    const unsigned char *patch_role; // [npatch] bit 0: reads ghost rows (wait first), bit 1: holds ghost or border nodes
+                                     // (per-patch role bits live in the ring descriptor's header word 2: bit 0 the patch's node table
+                                     //  holds ghost rows -- wait first --, bit 1 the patch owns ghost or border nodes)
     const unsigned char *node_role;  // [np] 1 ghost (computed by its owner: no stores here), 2 border (mirrored on a peer)
     const int *exp_ptr;              // [npatch+1] into exp_ent
     const int *exp_ent;              // triples (local thread, peer slot, row at the peer), grouped by patch
@@ -308,24 +314,30 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_sys_inc(unsigned long long *p) {
-    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(1ull) : "memory");
+__device__ __forceinline__ void red_release_sys_add(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// one thread of the kernel that FOLLOWS a halo substrate kernel in the stream, after its griddepcontrol.wait: tell every
+// neighbour that the rows of the step just finished are in its ghost rows
+__device__ __noinline__ void halo_signal(const HaloPeer *peer, int npeer) {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    for (int q = 0; q < npeer; q++) if (peer[q].nsend) red_release_sys_add(peer[q].flag, peer[q].nsend);
 }
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 // one thread: wait until every neighbour's rows of the previous step have arrived.  Bounded: after 10 s (a peer died) the error
 // flag is raised and this and every later wait returns at once -- a wrong answer that is reported, never a hung GPU.
-__device__ __noinline__ void halo_wait(const HaloView &hv) {
-    if (hv.step == 0) return;
+// (scalars by value: a reference to the kernel parameter would make every thread copy the struct to its local stack)
+__device__ __noinline__ void halo_wait(const unsigned long long *flags, const HaloPeer *peer, int npeer, unsigned int step, int *err) {
+    if (step == 0) return;
     const unsigned long long t0 = global_ns();
-    for (int q = 0; q < hv.npeer; q++) {
-        const unsigned long long want = (unsigned long long)hv.step * hv.peer[q].nrecv;
-        while (ld_acquire_sys(hv.flags + q) < want) {
-            if (*(volatile int *)hv.err & ERR_HALO_TIMEOUT) return;
-            if (global_ns() - t0 > 10000000000ull) { atomicOr(hv.err, ERR_HALO_TIMEOUT); return; }
+    for (int q = 0; q < npeer; q++) {
+        const unsigned long long want = (unsigned long long)step * peer[q].nrecv;
+        while (ld_acquire_sys(flags + q) < want) {
+            if (*(volatile int *)err & ERR_HALO_TIMEOUT) return;
+            if (global_ns() - t0 > 10000000000ull) { atomicOr(err, ERR_HALO_TIMEOUT); return; }
             __nanosleep(64);
         }
     }
-    asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copies below read the rows through the async proxy
 }
 
 template <bool DBG, bool BATCH = false, bool HALO = false>
@@ -347,9 +359,7 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     const int nown = min(kPatch, s.nn - n0);
     const int ncopy = min(kPatch, s.np - n0);
     const int np = s.np;
-    const int prole = HALO ? (int)hv.patch_role[p] : 0;
     if (tid == 0) {
-        if (HALO && (prole & 1)) halo_wait(hv);              // the neighbours' strain rows of the previous step have landed
         mbar_init(bar, 1);
         const unsigned int nb = (unsigned int)ncopy * 8u;
         mbar_expect_tx(bar, (unsigned int)pv.ring_stride + 5u * nb);
@@ -362,10 +372,24 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     const bool own = tid < nown;
     double V0 = 0, V1 = 0, A0v = 0, A1v = 0;
     if (own) { V0 = s.V[i]; V1 = s.V[np + i]; A0v = s.A[i]; A1v = s.A[np + i]; }
-    const int nrole = (HALO && (prole & 2) && own) ? (int)hv.node_role[i] : 0;
     __syncthreads();
     mbar_wait(bar, 0);
     const int nh = ((const int *)sblob)[0];
+    // partitioned run: the patch's role rides in the descriptor's header (bit 0: its node table holds ghost rows, bit 1: it owns
+    // ghost or border nodes), so the staging above is issued without any dependent load and interior patches pay nothing
+    const int prole = HALO ? ((const int *)sblob)[2] : 0;
+    int nrole = 0;
+    if (HALO && prole) {
+        if (own && (prole & 2)) nrole = (int)hv.node_role[i];
+        if (prole & 1) {
+#ifndef WCFE_HALO_NOWAITCODE
+            if (tid == 0) halo_wait(hv.flags, hv.peer, hv.npeer, hv.step, hv.err);   // the neighbours' rows of the previous step have landed
+#endif
+            __syncthreads();
+            // ghost nodes inside the patch's own range were staged before the wait: read them again, past the (incoherent) L1
+            if (nrole == 1) { stage[2 * kPatch + tid] = __ldcg(s.ea_in + i); stage[3 * kPatch + tid] = __ldcg(s.ea_in + np + i); stage[4 * kPatch + tid] = __ldcg(s.ea_in + 3 * (size_t)np + i); }
+        }
+    }
     const int *halo_ids = (const int *)(sblob + pv.roff_halo);
     const unsigned char *valence = sblob + pv.roff_rptr;
     const ushort2 *rjk = (const ushort2 *)(sblob + pv.roff_jk);          // [step][node]: conflict-free across a warp
@@ -499,18 +523,19 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
     const double en0 = ea0 + q0 * imm, en1 = ea1 + q1 * imm, en3 = ea3 + q3 * imm;
     s.ea_out[i] = en0; s.ea_out[np + i] = en1; s.ea_out[3 * np + i] = en3;
+#ifndef WCFE_HALO_NOPUSH
     if (HALO && nrole == 2) {
-        // border node: the same three words go straight into the ghost row of every neighbour that mirrors it, then the
-        // neighbour's arrival counter is bumped (release: the row is visible before the count)
+        // border node: the same three words go straight into the ghost row of every neighbour that mirrors it (signalled by the
+        // next kernel in the stream, halo_signal)
         for (int q = hv.exp_ptr[p]; q < hv.exp_ptr[p + 1]; q++) {
             if (hv.exp_ent[3 * q] != tid) continue;
-            const HaloPeer pr = hv.peer[hv.exp_ent[3 * q + 1]];
-            const long long row = hv.exp_ent[3 * q + 2];
-            double *dst = pr.ea[hv.step & 1];
-            dst[row] = en0; dst[pr.np + row] = en1; dst[3 * pr.np + row] = en3;
-            red_release_sys_inc(pr.flag);
+            const HaloPeer *pr = hv.peer + hv.exp_ent[3 * q + 1];
+            const long long row = hv.exp_ent[3 * q + 2], rnp = pr->np;
+            double *dst = pr->ea[hv.step & 1];
+            dst[row] = en0; dst[rnp + row] = en1; dst[3 * rnp + row] = en3;
         }
     }
+#endif
     if (DBG) {
         dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
         dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
@@ -759,6 +784,8 @@ struct CellStepArgs {
     double *partials;
     int *d_flags, *d_loc_bond, *d_loc_cnt, *d_loc_first, *d_ap_fire, *err;
     int debug;
+    const HaloPeer *halo_peer;      // partitioned run, not the first step: signal the previous step's halo rows (halo_signal)
+    int halo_npeer;
 };
 
 template <bool PREDICT, bool DBG, bool BATCH = false>
@@ -803,6 +830,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     // -- which is what the substrate kernel of THIS step relies on when it reads its own previous output before waiting.
     pdl_wait();
     pdl_launch_dependents();
+    if (!BATCH && a.halo_peer && blockIdx.x == 0 && tid == kThreads - 1) halo_signal(a.halo_peer, a.halo_npeer);   // the previous substrate kernel is complete
     if (tid == 0) {
         const unsigned int nb = (unsigned int)ncopy * 8u;
         if (PREDICT) { bulk_g2s(sX0, x_in + n0, nb, bar); bulk_g2s(sX1, x_in + np + n0, nb, bar); }
