@@ -276,15 +276,17 @@ def whole_application(xc, tc, xs, ts, end_t=0.32):
         write_ecomsol(os.path.join(w, "scripts", "disk.txt"), xc, tc); write_ecomsol(os.path.join(w, "scripts", "subs.txt"), xs, ts)
         for k in ("ref", "gpu"):
             t = {}
-            for e in (end_t, 2 * end_t):
-                open(os.path.join(w, "cell.txt"), "w").write(tpl.format(end_t=e, max_edge=2, improve=1, topo=1, collide=1, mesh="scripts/disk.txt"))
-                open(os.path.join(w, "subs.txt"), "w").write(tpl.format(end_t=e, max_edge=8, improve=1, topo=1, collide=1, mesh="scripts/subs.txt"))
-                out = os.path.join(w, "out_%s_%g" % (k, e)); os.makedirs(out)
-                w0 = time.perf_counter()
-                subprocess.run([exe[k], "cell.txt", "subs.txt", out], cwd=w, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True, timeout=600)
-                t[e] = time.perf_counter() - w0
-            steps = round(end_t / 0.005)
-            res["config1_whole_app_%s_ms_per_step" % k] = (t[2 * end_t] - t[end_t]) / steps * 1e3     # startup cancels
+            for e in (end_t, 3 * end_t):
+                t[e] = 1e30
+                for rep in range(2):          # best of two: process start-up (CUDA context, page-in) varies by hundreds of ms
+                    open(os.path.join(w, "cell.txt"), "w").write(tpl.format(end_t=e, max_edge=2, improve=1, topo=1, collide=1, mesh="scripts/disk.txt"))
+                    open(os.path.join(w, "subs.txt"), "w").write(tpl.format(end_t=e, max_edge=8, improve=1, topo=1, collide=1, mesh="scripts/subs.txt"))
+                    out = os.path.join(w, "out_%s_%g_%d" % (k, e, rep)); os.makedirs(out)
+                    w0 = time.perf_counter()
+                    subprocess.run([exe[k], "cell.txt", "subs.txt", out], cwd=w, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True, timeout=600)
+                    t[e] = min(t[e], time.perf_counter() - w0)
+            steps = round(2 * end_t / 0.005)
+            res["config1_whole_app_%s_ms_per_step" % k] = (t[3 * end_t] - t[end_t]) / steps * 1e3     # startup cancels
     res["whole_app_what"] = "unmodified reference application (main.cpp, El Topo integrate + improve_mesh, two .vtk files per step) on the shipped example, k1; ref = its own UL_growth_explicit.o on one host core, gpu = ul_adapter.cpp + libwcfe (state up/downloaded every step)"
     return res
 

@@ -15,6 +15,9 @@ void hm_elem_eval(const double *X9, const double *x9, const double *e6, double m
 int hm_point_in_triangle(const double *n1, const double *n2, const double *n3, const double *pt, double *A, double *Atri) {
     return point_in_triangle(n1, n2, n3, pt, A, *Atri) ? 1 : 0;
 }
+int hm_point_in_triangle_2d(const double *n1, const double *n2, const double *n3, const double *pt, double *A, double *Atri) {
+    return point_in_triangle_2d(n1[0], n1[1], n2[0], n2[1], n3[0], n3[1], pt[0], pt[1], A, *Atri) ? 1 : 0;
+}
 unsigned int hm_philox(unsigned int seed, unsigned int step, unsigned int ord) { return philox_u32(seed, step, ord); }
 }
 extern "C" {

@@ -75,6 +75,33 @@ def test_point_in_triangle_bit_exact_with_oracle(hm):
         assert np.array_equal(A, Aw) and At.value == Atw
 
 
+def test_planar_point_in_triangle_is_bit_identical_to_the_3d_form(hm):
+    """point_in_triangle_2d (no square roots: |z| instead of sqrt(0 + (0 + z*z))) against the reference-order 3-D predicate on
+    planar inputs: same decision, same sub-areas to the last bit -- random triangles of both orientations and very different
+    scales, interior, exterior, on-edge and on-vertex points, exact zeros."""
+    rng = np.random.default_rng(17)
+    n_checked = 0
+    for trial in range(400):
+        scale = 10.0 ** rng.uniform(-3, 2)
+        n = np.zeros((3, 3)); n[:, :2] = rng.uniform(-1, 1, size=(3, 2)) * scale + rng.uniform(-50, 50, size=2)
+        if trial % 7 == 0:
+            n[:, :2] = np.round(n[:, :2], 1)                              # grid-aligned vertices: exact zeros and ties
+        pts = [n[0].copy(), n[1].copy(), n[2].copy(), 0.5 * (n[0] + n[1]), 0.5 * (n[1] + n[2]), 0.5 * (n[0] + n[2]), n.mean(axis=0)]
+        for _ in range(20):
+            w = rng.dirichlet([1, 1, 1]) if rng.random() < 0.6 else rng.uniform(-0.5, 1.5, size=3)
+            pts.append(w @ n / w.sum())
+        pts += [n[0] + s * (n[1] - n[0]) for s in rng.uniform(0, 1, 5)]
+        for pt in pts:
+            pt = np.ascontiguousarray(pt); pt[2] = 0.0
+            A3d = np.zeros(3); At3d = C.c_double(); A2d = np.zeros(3); At2d = C.c_double()
+            a = hm.hm_point_in_triangle(d(n[0].copy()), d(n[1].copy()), d(n[2].copy()), d(pt), d(A3d), C.byref(At3d))
+            b = hm.hm_point_in_triangle_2d(d(n[0].copy()), d(n[1].copy()), d(n[2].copy()), d(pt), d(A2d), C.byref(At2d))
+            assert a == b
+            assert A3d.tobytes() == A2d.tobytes() and At3d.value == At2d.value
+            n_checked += 1
+    assert n_checked > 10000
+
+
 def test_philox_counter_rng_is_a_pure_function(hm):
     a = [hm.hm_philox(1, s, o) for s in range(4) for o in range(8)]
     b = [hm.hm_philox(1, s, o) for s in range(4) for o in range(8)]

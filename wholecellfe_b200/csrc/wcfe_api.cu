@@ -113,6 +113,7 @@ struct wcfe_ctx {
     GridView grid{};
     DevBuf<int> g_ptr, g_items;
     DevBuf<unsigned long long> b_head;
+    DevBuf<unsigned int> b_node_epoch;    // per substrate node: epoch of the last step in which an incident triangle received an anchor
     DevBuf<int> b_items;
     int b_cap = 0;
     // big buckets (coarse substrate): list + one-warp-per-triangle reduction, see k_bucket_reduce
@@ -534,6 +535,8 @@ int build_buckets(wcfe_ctx *c) {
     c->b_cap = (int)cap;
     CK(c->b_head.alloc((size_t)ss.nep * c->nrep)); CK(c->b_items.alloc((size_t)ss.ne * cap * c->nrep));
     CK(cudaMemset(c->b_head.p, 0, sizeof(unsigned long long) * ss.nep * c->nrep));
+    CK(c->b_node_epoch.alloc((size_t)ss.np * c->nrep));
+    CK(cudaMemset(c->b_node_epoch.p, 0, sizeof(unsigned int) * ss.np * c->nrep));
     c->epoch = 0; c->big_clean = true;
     // many anchors per substrate triangle expected -> reduce big buckets with one warp each (k_subs_ring only)
     c->big_T = 0x7fffffff; c->big_cap = 0; c->big_count.release(); c->big_list.release();
@@ -613,7 +616,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     SurfView cv = view(cs), sv = view(ss);
     sv.X = sv.x;
     if (which & 1) c->epoch++;            // the cell half fills the triangle buckets of this epoch, the substrate half reads them
-    BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch, nullptr, nullptr, 0, 0x7fffffff};
+    BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch, nullptr, nullptr, 0, 0x7fffffff, c->b_node_epoch.p};
     const int gc = (cs.nn + kBlock - 1) / kBlock, gs = (ss.nn + kBlock - 1) / kBlock;
     // Pr < APrate*dt*exp(-APrate*dt) (UL:1531): the threshold is evaluated on the host with the host libm, as the reference does
     const double thr = c->prm.ap_rate * dt_real * std::exp(-c->prm.ap_rate * dt_real);
@@ -632,7 +635,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
             return fail(c, WCFE_ERR_UNSUPPORTED, "batched contexts run the fused planar step only (flat meshes, wcfe_step_n, no debug capture)");
         const size_t R = (size_t)c->nrep;
         bt.k = c->d_kb.p; bt.seed = (c->own_seeds && c->rng_mode == WCFE_RNG_PHILOX) ? c->d_seeds.p : nullptr; bt.flags = (long long)(c->d_flags.n / R); bt.partials = (long long)(c->d_partials.n / R); bt.bnd = (long long)(cs.d_bnd_buf.n / R);
-        bt.head = (long long)(c->b_head.n / R); bt.items = (long long)(c->b_items.n / R);
+        bt.head = (long long)(c->b_head.n / R); bt.items = (long long)(c->b_items.n / R); bt.snodes = (long long)(c->b_node_epoch.n / R);
     }
     const unsigned int R = (unsigned int)c->nrep;
     if (c->halo.active && (which & 2) && (!planar || c->subs_kernel != 2 || batch || c->debug))
@@ -974,7 +977,7 @@ int wcfe_destroy(wcfe_ctx *c) {
         s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
         s.p_blob.release(); s.p_ring_blob.release(); s.p_ring_cyc.release(); s.p_elem_ptr.release(); s.p_elem_gid.release(); s.p_cand_l.release();
     }
-    c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release();
+    c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release(); c->b_node_epoch.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();
     c->d_kb.release(); c->d_seeds.release(); c->big_count.release(); c->big_list.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);

@@ -47,6 +47,10 @@ struct BucketView {          // triangle -> anchored cell nodes, rebuilt every s
     unsigned int *big_count;        // entries of big_list; zeroed on the stream before every cell kernel
     int *big_list;                  // [big_cap] triangle ids
     int big_cap, big_T;
+    // planar path: epoch stamp per SUBSTRATE NODE, written by the cell kernel on the three vertices of every triangle it drops an
+    // anchor into.  A substrate node under the cell whose stamp is stale has nothing to gather and skips the bucket walk (two
+    // thirds of the nodes inside the padded bounding box of a round cell).
+    unsigned int *node_epoch;       // [np_subs], or nullptr
 };
 
 struct BoundaryView {        // cell boundary vertices in ascending vertex order (the RNG draw order, UL:1463-1465)
@@ -76,7 +80,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 struct BatchView {
     const Consts *k;             // [R]
     const unsigned int *seed;    // [R] Philox keys, or nullptr: every replica draws the same numbers (common random numbers)
-    long long flags, partials, bnd, head, items;   // per-replica element counts: int flag arrays, area partials, boundary buffer, bucket heads / items
+    long long flags, partials, bnd, head, items, snodes;   // per-replica element counts: int flag arrays, area partials, boundary buffer, bucket heads / items, substrate node stamps
 };
 __device__ __forceinline__ void batch_shift(SurfView &s, size_t r) {
     const size_t n = (size_t)s.np * r;
@@ -87,6 +91,7 @@ __device__ __forceinline__ void batch_shift(SurfView &s, size_t r) {
 __device__ __forceinline__ void batch_shift(BucketView &bk, const BatchView &bt, size_t r) {
     bk.head += bt.head * r; bk.items += bt.items * r;
     if (bk.big_count) { bk.big_count += r; bk.big_list += (size_t)bk.big_cap * r; }
+    if (bk.node_epoch) bk.node_epoch += bt.snodes * r;
 }
 
 enum : int { ERR_BUCKET_OVERFLOW = 1, ERR_LOC_OVERFLOW = 2, ERR_NAN = 4, ERR_REGION = 8 };

@@ -477,21 +477,35 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     // (chained behind this kernel only) depends on; it also re-zeroes the big-bucket list k_bucket_reduce has consumed
     if (blockIdx.x == 0 && tid == 0) { pdl_wait(); if (bk.big_count) *bk.big_count = 0; }
     if (HALO && nrole == 1) return;          // ghost node (incomplete fan): its owner computes it and stores the result here
+    unsigned int stamp = bk.epoch - 1u;
     if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
-        pdl_wait();               // first touch of what the cell kernel produced (buckets, anchor records); all above overlaps its tail
+        pdl_wait();               // first touch of what the cell kernel produced (stamps, buckets, anchor records); all above overlaps its tail
+        stamp = bk.node_epoch[i];
+    }
+    if (stamp == bk.epoch) {      // an incident triangle received an anchor in this step (two thirds of the nodes in the box skip the walk)
+        // element id -> bucket head -> items -> anchor record are dependent global loads; the first two are fetched for four
+        // incident triangles at a time, so a valence-6 node pays 2 x 2 instead of 6 x 2 of those round trips
         const int gb = s.ring_ptr[i];
-        for (int r = 0; r < nring; r++) {
-            const int code = pv.ring_cyc[gb + r];
+        for (int r0 = 0; r0 < nring; r0 += 4) {
+        int code4[4]; unsigned long long h4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) code4[u] = r0 + u < nring ? pv.ring_cyc[gb + r0 + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; u++) h4[u] = code4[u] >= 0 ? bk.head[code4[u] >> 2] : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int code = code4[u], r = r0 + u;
+            const unsigned long long h = h4[u];
+            if (code < 0 || (unsigned int)(h >> 32) != bk.epoch) continue;
             const int e = code >> 2, slot = code & 3;
-            const unsigned long long h = bk.head[e];
-            if ((unsigned int)(h >> 32) != bk.epoch) continue;
             int cnt = (int)(unsigned int)h;
             if (cnt > bk.cap) cnt = bk.cap;
             // the element's vertices in their ORIGINAL order (the sub-areas of the predicate are order dependent)
             const ushort2 jk = rjk[r * kPatch + tid];
-            const int lid[3] = {tid, (int)jk.x, (int)jk.y};
-            const double2 p1 = sxy[lid[(3 - slot) % 3]], p2 = sxy[lid[(4 - slot) % 3]], p3 = sxy[lid[(5 - slot) % 3]];
-            const double n1[3] = {p1.x, p1.y, 0.0}, n2[3] = {p2.x, p2.y, 0.0}, n3[3] = {p3.x, p3.y, 0.0};
+            const int l1 = slot == 0 ? tid : (slot == 1 ? (int)jk.y : (int)jk.x);        // lid[(3 - slot) % 3] with lid = {tid, j, k}
+            const int l2 = slot == 0 ? (int)jk.x : (slot == 1 ? tid : (int)jk.y);        // lid[(4 - slot) % 3]
+            const int l3 = slot == 0 ? (int)jk.y : (slot == 1 ? (int)jk.x : tid);        // lid[(5 - slot) % 3]
+            const double2 p1 = sxy[l1], p2 = sxy[l2], p3 = sxy[l3];
             if (cnt > bk.big_T) {            // reduced by k_bucket_reduce: six sums parked in the bucket's own item storage
                 const double2 f = reinterpret_cast<const double2 *>(bk.items + (size_t)e * bk.cap)[slot];
                 Fx += f.x; Fy += f.y;
@@ -503,13 +517,13 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
                 for (int q = 0; q < cnt; q++) { const int v = bk.items[(size_t)e * bk.cap + q]; if (v > prev && v < ni) ni = v; }
                 prev = ni;
                 const double2 ap = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)ni], ah = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)ni + 1];
-                const double pt[3] = {ap.x, ap.y, 0.0};                                  // UL:1303
-                double Ar[3], At;
-                point_in_triangle(n1, n2, n3, pt, Ar, At);
-                const double w = Ar[slot] / At;
+                double Ar[3], At;                                                        // UL:1303; planar form, bit-identical
+                point_in_triangle_2d(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, ap.x, ap.y, Ar, At);
+                const double w = (slot == 0 ? Ar[0] : (slot == 1 ? Ar[1] : Ar[2])) / At;
                 Fx += ah.x * w;                                                          // UL:1414-1422
                 Fy += ah.y * w;
             }
+        }
         }
     }
     double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt / 2.0, A1v));   // UL:295
@@ -574,9 +588,8 @@ __global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s,
                 for (int q = 0; q < cnt; q++) rank += items[q] < v;      // node ids inside a bucket are distinct
                 if (rank < w0 || rank >= w0 + kReduceWindow) continue;
                 const double2 ap = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)v], ah = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)v + 1];
-                const double pt[3] = {ap.x, ap.y, 0.0};
                 double Ar[3], At;
-                point_in_triangle(n1, n2, n3, pt, Ar, At);
+                point_in_triangle_2d(n1[0], n1[1], n2[0], n2[1], n3[0], n3[1], ap.x, ap.y, Ar, At);     // planar form, bit-identical
                 double *t6 = tw[rank - w0];
 #pragma unroll
                 for (int j = 0; j < 3; j++) { const double w = Ar[j] / At; t6[2 * j] = ah.x * w; t6[2 * j + 1] = ah.y * w; }
@@ -904,6 +917,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
                 if (old == seen) break;
             } while (true);
             if (slot < bk.cap) bk.items[(size_t)t * bk.cap + slot] = i; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
+            if (slot == 0) {                 // first anchor of the step in this triangle: its three nodes have something to gather
+                bk.node_epoch[sub.tri[t]] = bk.epoch; bk.node_epoch[sub.tri[sub.nep + t]] = bk.epoch; bk.node_epoch[sub.tri[2 * sub.nep + t]] = bk.epoch;
+            }
             if (slot == bk.big_T) {          // this insert makes the bucket "big": list it once for k_bucket_reduce
                 const int q = atomicAdd(&s_nbig, 1);
                 if (q < 2 * kThreads) s_big[q] = t;
@@ -917,11 +933,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         const int tprev = a.d_loc_first[i];
         if (tprev >= 0 && tprev < sub.ne) {
             const int i0 = sub.tri[tprev], i1 = sub.tri[sub.nep + tprev], i2 = sub.tri[2 * sub.nep + tprev];
-            const double n1[3] = {sub.x[i0], sub.x[sub.np + i0], sub.x[2 * sub.np + i0]};
-            const double n2[3] = {sub.x[i1], sub.x[sub.np + i1], sub.x[2 * sub.np + i1]};
-            const double n3[3] = {sub.x[i2], sub.x[sub.np + i2], sub.x[2 * sub.np + i2]};
-            double Ar[3], At;
-            if (point_in_triangle(n1, n2, n3, pt, Ar, At) && Ar[0] > 0 && Ar[1] > 0 && Ar[2] > 0) { insert(tprev, Ar, At); done = true; }
+            double Ar[3], At;      // planar path: z == 0 everywhere (checked at upload), the 2-D predicate is bit-identical to the 3-D one
+            if (point_in_triangle_2d(sub.x[i0], sub.x[sub.np + i0], sub.x[i1], sub.x[sub.np + i1], sub.x[i2], sub.x[sub.np + i2], pt[0], pt[1], Ar, At) &&
+                Ar[0] > 0 && Ar[1] > 0 && Ar[2] > 0) { insert(tprev, Ar, At); done = true; }
         }
         if (!done) locate(g, sub, pt, insert);
         a.d_loc_cnt[i] = cnt; a.d_loc_first[i] = first;
