@@ -9,17 +9,26 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 from wholecellfe_b200.meshgen import square_mesh, disk_mesh
-from wholecellfe_b200.partition import strip_partition, exchange_rows, connect_plan, neighbours
+from wholecellfe_b200.partition import strip_partition, exchange_rows, connect_plan, neighbours, cell_weights
 
 
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+@pytest.mark.parametrize("balanced", [False, True])
 @pytest.mark.parametrize("world", [1, 2, 3, 5])
-def test_partition_invariants(world):
+def test_partition_invariants(world, balanced):
     xs, ts = square_mesh(48)
-    parts = strip_partition(xs, ts, world)
+    w = None
+    if balanced:                                                            # cost weights: nodes under a (small, off-centre) cell count 7x
+        xc = np.array([[-20.0, -5.0, 0.0], [0.0, 12.0, 0.0], [5.0, -8.0, 0.0]])
+        w = cell_weights(xs, xc)
+        assert w.min() == 1.0 and w.max() == 7.0
+    parts = strip_partition(xs, ts, world, w)
+    if balanced and world > 1:
+        tot = [w[p.owned].sum() for p in parts]
+        assert max(tot) - min(tot) <= 0.1 * np.mean(tot) + 7 * 48          # equal weight up to one column of nodes
     owned = np.sort(np.concatenate([p.owned for p in parts]))
     assert np.array_equal(owned, np.arange(len(xs)))                       # every node owned exactly once
     covered = np.zeros(len(ts), dtype=int)

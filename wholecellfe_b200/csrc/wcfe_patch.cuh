@@ -32,6 +32,9 @@ constexpr int kPatch = WCFE_PATCH;     // owned nodes per patch
 constexpr int kThreads = WCFE_THREADS; // threads per CTA: a patch has ~2.35 elements per owned node, so 1.25 x kPatch threads
                                        // finish the element phase in two full rounds instead of two and a tail
 constexpr int kMinBlk = WCFE_MINBLK;   // resident CTAs per SM the register allocation is tuned for
+#ifndef WCFE_CELL_PREFETCH
+#define WCFE_CELL_PREFETCH 1
+#endif
 #ifndef WCFE_RING_CHUNK
 #define WCFE_RING_CHUNK 3
 #endif
@@ -511,17 +514,20 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
                 Fx += f.x; Fy += f.y;
                 continue;
             }
-            int prev = -1;
-            for (int m = 0; m < cnt; m++) {
-                int ni = 0x7fffffff;
-                for (int q = 0; q < cnt; q++) { const int v = bk.items[(size_t)e * bk.cap + q]; if (v > prev && v < ni) ni = v; }
-                prev = ni;
-                const double2 ap = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)ni], ah = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)ni + 1];
+            const double2 *anc2 = reinterpret_cast<const double2 *>(c.anc);
+            auto add_anchor = [&](const double2 ap, const double2 ah) {
                 double Ar[3], At;                                                        // UL:1303; planar form, bit-identical
                 point_in_triangle_2d(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, ap.x, ap.y, Ar, At);
                 const double w = (slot == 0 ? Ar[0] : (slot == 1 ? Ar[1] : Ar[2])) / At;
                 Fx += ah.x * w;                                                          // UL:1414-1422
                 Fy += ah.y * w;
+            };
+            int prev = -1;
+            for (int m = 0; m < cnt; m++) {
+                int ni = 0x7fffffff;
+                for (int q = 0; q < cnt; q++) { const int v = bk.items[(size_t)e * bk.cap + q]; if (v > prev && v < ni) ni = v; }
+                prev = ni;
+                add_anchor(anc2[2 * (size_t)ni], anc2[2 * (size_t)ni + 1]);
             }
         }
         }
@@ -855,6 +861,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     double V0 = 0, V1 = 0, Av0 = 0, Av1 = 0;      // own node's V, A (kept for the update)
     double fa0 = 0, fa1 = 0, cC = 0;
     if (own) { V0 = s.V[i]; V1 = s.V[np + i]; Av0 = s.A[i]; Av1 = s.A[np + i]; fa0 = s.fa[i]; fa1 = s.fa[np + i]; cC = s.cC[i]; }
+#if WCFE_CELL_PREFETCH
+    // the triangle the anchor was in at the previous step and its (frozen) vertices: loc_first -> tri -> x are three dependent
+    // global loads; issued here they complete behind the staging wait instead of after the bond update
+    int tprev = -1;
+    double t1x = 0, t1y = 0, t2x = 0, t2y = 0, t3x = 0, t3y = 0;
+    if (own) {
+        tprev = a.d_loc_first[i];
+        if (tprev >= 0 && tprev < sub.ne) {
+            const int i0 = sub.tri[tprev], i1 = sub.tri[sub.nep + tprev], i2 = sub.tri[2 * sub.nep + tprev];
+            t1x = sub.x[i0]; t1y = sub.x[sub.np + i0]; t2x = sub.x[i1]; t2y = sub.x[sub.np + i1]; t3x = sub.x[i2]; t3y = sub.x[sub.np + i2];
+        } else tprev = -1;
+    }
+#endif
     __syncthreads();
     mbar_wait(bar, 0);
     const int *hdr = (const int *)sblob;
@@ -930,6 +949,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         // it (all three sub-areas > 0) lies in no other triangle of a conforming substrate mesh, so the grid search -- which
         // finds every containing triangle, as the reference's exhaustive loop does (UL:1309-1452) -- is only needed otherwise.
         bool done = false;
+#if WCFE_CELL_PREFETCH
+        if (tprev >= 0) {
+            double Ar[3], At;      // planar path: z == 0 everywhere (checked at upload), the 2-D predicate is bit-identical to the 3-D one
+            if (point_in_triangle_2d(t1x, t1y, t2x, t2y, t3x, t3y, pt[0], pt[1], Ar, At) && Ar[0] > 0 && Ar[1] > 0 && Ar[2] > 0) { insert(tprev, Ar, At); done = true; }
+        }
+#else
         const int tprev = a.d_loc_first[i];
         if (tprev >= 0 && tprev < sub.ne) {
             const int i0 = sub.tri[tprev], i1 = sub.tri[sub.nep + tprev], i2 = sub.tri[2 * sub.nep + tprev];
@@ -937,6 +962,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
             if (point_in_triangle_2d(sub.x[i0], sub.x[sub.np + i0], sub.x[i1], sub.x[sub.np + i1], sub.x[i2], sub.x[sub.np + i2], pt[0], pt[1], Ar, At) &&
                 Ar[0] > 0 && Ar[1] > 0 && Ar[2] > 0) { insert(tprev, Ar, At); done = true; }
         }
+#endif
         if (!done) locate(g, sub, pt, insert);
         a.d_loc_cnt[i] = cnt; a.d_loc_first[i] = first;
     }

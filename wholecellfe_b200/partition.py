@@ -34,8 +34,19 @@ class StripPart:
         self.owned_local = np.searchsorted(local_nodes, owned)
 
 
-def strip_partition(xyz, tri, world):
-    """Cut the mesh into `world` vertical strips of (almost) equal node count.  Returns the list of StripPart.
+def cell_weights(subs_xyz, cell_xyz, under_cell=6.0):
+    """Per-node cost weights for strip_partition: a substrate node inside the cell's bounding box (padded like libwcfe's anchor
+    region) also walks the anchor buckets of its triangles; measured on B200 it costs ~7x a plain node (tools/strip_probe.py)."""
+    xs = np.asarray(subs_xyz); xc = np.asarray(cell_xyz)
+    lo, hi = xc[:, :2].min(axis=0), xc[:, :2].max(axis=0)
+    pad = max(2.0, 0.25 * float((hi - lo).max()))
+    inside = np.all((xs[:, :2] >= lo - pad) & (xs[:, :2] <= hi + pad), axis=1)
+    return 1.0 + under_cell * inside
+
+
+def strip_partition(xyz, tri, world, weights=None):
+    """Cut the mesh into `world` vertical strips of (almost) equal node count -- or, with `weights` (one per node), of equal
+    total weight, so that the strips under the cell hold fewer nodes.  Returns the list of StripPart.
 
     A node belongs to the strip its x coordinate falls in (ties by node id); a rank holds every element with at least one
     owned vertex, hence a one-ring of ghost nodes.  Local numbering keeps the global (space-filling-curve) order, and local
@@ -44,7 +55,11 @@ def strip_partition(xyz, tri, world):
     nn = len(xyz)
     order = np.lexsort((np.arange(nn), xyz[:, 0]))
     owner = np.empty(nn, dtype=np.int32)
-    bounds = [(nn * r) // world for r in range(world + 1)]
+    if weights is None:
+        bounds = [(nn * r) // world for r in range(world + 1)]
+    else:
+        cw = np.cumsum(np.asarray(weights, dtype=np.float64)[order])
+        bounds = [0] + [int(np.searchsorted(cw, cw[-1] * r / world)) for r in range(1, world)] + [nn]
     for r in range(world):
         owner[order[bounds[r]:bounds[r + 1]]] = r
     tri_owner = owner[tri]                                   # [m,3]
@@ -107,11 +122,11 @@ class InProcessStrips:
     a GPU), connected through plain device pointers (peer access between GPUs).  Strips advance in lockstep, one step queued on
     every strip before the next: a strip's step s+1 waits in-kernel for its neighbours' step s, which is already in flight."""
 
-    def __init__(self, variant, cell_mesh, subs_mesh, devices, rng=(1, 1), params=None):
+    def __init__(self, variant, cell_mesh, subs_mesh, devices, rng=(1, 1), params=None, balance=True):
         from . import ulstep
         from ._lib import CELL, SUBS
         xs, ts = subs_mesh
-        self.parts = strip_partition(xs, ts, len(devices))
+        self.parts = strip_partition(xs, ts, len(devices), cell_weights(xs, cell_mesh[0]) if balance else None)
         self.sims = []
         for part, dev in zip(self.parts, devices):
             sim = ulstep.ULSim(variant, device=dev, params=params)
@@ -199,7 +214,7 @@ def exchange_rows(dist, table, part, comps, device):
 class PartitionedSim:
     """One rank of a substrate-partitioned run: full cell + this rank's substrate strip on one GPU."""
 
-    def __init__(self, variant, cell_mesh, subs_mesh, dist, device_index, rng=(1, 1), params=None, halo="peer"):
+    def __init__(self, variant, cell_mesh, subs_mesh, dist, device_index, rng=(1, 1), params=None, halo="peer", balance=True):
         import torch
         from . import ulstep
         from ._lib import CELL, SUBS
@@ -209,7 +224,8 @@ class PartitionedSim:
         self.halo = halo
         self.connected = False
         xs, ts = subs_mesh
-        self.parts = strip_partition(xs, ts, self.world)
+        # strips of equal COST: nodes under the cell also gather integrin forces (balance=False: equal node counts)
+        self.parts = strip_partition(xs, ts, self.world, cell_weights(xs, cell_mesh[0]) if balance else None)
         self.part = self.parts[self.rank]
         self.sim = ulstep.ULSim(variant, device=device_index, params=params, stream=torch.cuda.current_stream().cuda_stream)
         self.sim.upload_mesh(CELL, cell_mesh[0], cell_mesh[1])
