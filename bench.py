@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--halo", default="peer", choices=["peer", "dist"],
                     help="--mode partition: border strains pushed into the neighbours' ghost rows by the substrate kernel itself over NVLink peer "
                          "memory (default), or a host-driven torch.distributed exchange after every step (the baseline)")
-    ap.add_argument("--balance", type=int, default=1, help="--mode partition: strips of equal cost (nodes under the cell weigh 7x) instead of equal node count")
+    ap.add_argument("--balance", type=int, default=1, help="--mode partition: strips of equal cost (nodes under the cell weigh 3x) instead of equal node count")
     ap.add_argument("--order", default="morton", choices=["morton", "morton_rows"], help="node numbering of the synthetic meshes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the small side measurements (configs 1/2 latency, config 5 batch)")
@@ -224,7 +224,7 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
                                                      else "substrate strip partition x%d + per-step torch.distributed (NCCL) halo exchange (%d border nodes x 24 B per step)") % (world, halo)},
                           "gpu_launches": l1 - l0, "rank0_per_kernel_ms": per_kernel,
                           "bitwise_equal_to_single_gpu": {"value": bool(int(okt.item())), "steps": total_steps, "what": "owned substrate rows (ea, V) of every rank and the replicated cell's positions against the same steps of the whole mesh on one GPU"},
-                          "strips": "equal cost (nodes under the cell x7)" if a.balance else "equal node count", "rank0_strip": {"substrate_nodes_local": int(len(sim.part.local_nodes)), "owned": int(len(sim.part.owned)), "ghosts": int(len(sim.part.ghosts))}}), flush=True)
+                          "strips": "equal cost (nodes under the cell x3)" if a.balance else "equal node count", "rank0_strip": {"substrate_nodes_local": int(len(sim.part.local_nodes)), "owned": int(len(sim.part.owned)), "ghosts": int(len(sim.part.ghosts))}}), flush=True)
     dist.destroy_process_group()
 
 

@@ -21,10 +21,10 @@ def _free_port():
 def test_partition_invariants(world, balanced):
     xs, ts = square_mesh(48)
     w = None
-    if balanced:                                                            # cost weights: nodes under a (small, off-centre) cell count 7x
+    if balanced:                                                            # cost weights: nodes under a (small, off-centre) cell count 3x
         xc = np.array([[-20.0, -5.0, 0.0], [0.0, 12.0, 0.0], [5.0, -8.0, 0.0]])
         w = cell_weights(xs, xc)
-        assert w.min() == 1.0 and w.max() == 7.0
+        assert w.min() == 1.0 and w.max() == 3.0
     parts = strip_partition(xs, ts, world, w)
     if balanced and world > 1:
         tot = [w[p.owned].sum() for p in parts]

@@ -34,9 +34,10 @@ class StripPart:
         self.owned_local = np.searchsorted(local_nodes, owned)
 
 
-def cell_weights(subs_xyz, cell_xyz, under_cell=6.0):
+def cell_weights(subs_xyz, cell_xyz, under_cell=2.0):
     """Per-node cost weights for strip_partition: a substrate node inside the cell's bounding box (padded like libwcfe's anchor
-    region) also walks the anchor buckets of its triangles; measured on B200 it costs ~7x a plain node (tools/strip_probe.py)."""
+    region) also reads its epoch stamp and, if an incident triangle holds anchors, walks their buckets; measured on B200 the nodes
+    under the cell cost ~3x a plain node on average (profiles/r01f_ncu_summary.txt, tools/strip_probe.py)."""
     xs = np.asarray(subs_xyz); xc = np.asarray(cell_xyz)
     lo, hi = xc[:, :2].min(axis=0), xc[:, :2].max(axis=0)
     pad = max(2.0, 0.25 * float((hi - lo).max()))
