@@ -54,16 +54,17 @@ def parse():
                          "memory (default), or a host-driven torch.distributed exchange after every step (the baseline)")
     ap.add_argument("--balance", type=int, default=1, help="--mode partition: strips of equal cost (nodes under the cell weigh 3x) instead of equal node count")
     ap.add_argument("--order", default="morton", choices=["morton", "morton_rows"], help="node numbering of the synthetic meshes")
+    ap.add_argument("--diagonals", default="alternate", choices=["alternate", "same"], help="substrate triangulation: union jack (valence 4/8, default) or uniform valence 6 (diagnostic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the small side measurements (configs 1/2 latency, config 5 batch)")
     ap.add_argument("--cpu-sample-div", type=int, default=16, help="CPU baseline sample = workload / this (both meshes)")
     return ap.parse_args()
 
 
-def workload_meshes(cell_tris, subs_side, order="morton"):
+def workload_meshes(cell_tris, subs_side, order="morton", diagonals="alternate"):
     from wholecellfe_b200.meshgen import disk_mesh, square_mesh
     xc, tc = disk_mesh(cell_tris, order=order)
-    xs, ts = square_mesh(subs_side, order=order)
+    xs, ts = square_mesh(subs_side, order=order, diagonals=diagonals)
     return xc, tc, xs, ts
 
 
@@ -309,7 +310,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.current_stream()
 
-    xc, tc, xs, ts = workload_meshes(a.cell_tris, a.subs_side, a.order)
+    xc, tc, xs, ts = workload_meshes(a.cell_tris, a.subs_side, a.order, a.diagonals)
     nn_c, ne_c, nn_s, ne_s = len(xc), len(tc), len(xs), len(ts)
     if a.mode == "partition" and world > 1:
         run_partition_mode(a, dist, rank, world, local, (xc, tc), (xs, ts))

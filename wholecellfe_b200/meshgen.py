@@ -47,8 +47,10 @@ def _renumber(xyz, tri, order="morton"):
     return xyz, np.ascontiguousarray(tri)
 
 
-def square_mesh(n_side, half=50.0, order="morton", jitter=0.0, seed=1234):
-    """Structured right-triangle mesh of [-half, half]^2 with n_side x n_side nodes (2 (n_side-1)^2 triangles)."""
+def square_mesh(n_side, half=50.0, order="morton", jitter=0.0, seed=1234, diagonals="alternate"):
+    """Structured right-triangle mesh of [-half, half]^2 with n_side x n_side nodes (2 (n_side-1)^2 triangles).
+    diagonals="alternate" (default): union-jack pattern, interior valences 4 and 8; "same": every diagonal the same way,
+    interior valence 6 everywhere (a diagnostic: what the node-centric kernels do without valence divergence inside a warp)."""
     g = np.linspace(-half, half, n_side)
     X, Y = np.meshgrid(g, g, indexing="xy")
     xyz = np.stack([X.ravel(), Y.ravel(), np.zeros(n_side * n_side)], axis=1)
@@ -59,7 +61,7 @@ def square_mesh(n_side, half=50.0, order="morton", jitter=0.0, seed=1234):
         xyz[inner, :2] += jitter * h * rng.uniform(-1, 1, size=(int(inner.sum()), 2))
     i, j = np.meshgrid(np.arange(n_side - 1), np.arange(n_side - 1), indexing="xy")
     a = (j * n_side + i).ravel(); b = a + 1; c = a + n_side; d = c + 1
-    flip = ((i + j) % 2 == 0).ravel()        # alternate the diagonal
+    flip = ((i + j) % 2 == 0).ravel() if diagonals == "alternate" else np.zeros(i.size, dtype=bool)   # alternate the diagonal
     t1 = np.where(flip[:, None], np.stack([a, b, d], 1), np.stack([a, b, c], 1))
     t2 = np.where(flip[:, None], np.stack([a, d, c], 1), np.stack([b, d, c], 1))
     tri = np.concatenate([t1, t2]).astype(np.int32)
