@@ -196,3 +196,40 @@ def test_two_rank_partition_equals_single_gpu_bitwise(halo):
     for r in range(world):                                    # the replicated cell evolves identically everywhere
         assert np.array_equal(res[r]["cell_x"], g.get(W.CELL, "x")) and np.array_equal(res[r]["cell_cC"], g.get(W.CELL, "cC"))
     assert np.abs(g.get(W.SUBS, "ea")).max() > 1e-5 and np.abs(g.get(W.SUBS, "A")).max() > 0
+
+
+@pytest.mark.gpu
+def test_halo_connect_argument_checks_and_bounded_wait():
+    """wcfe_halo_connect refuses inconsistent tables, and a neighbour that never delivers makes the step fail with WCFE_ERR_PEER
+    after the bounded in-kernel wait (10 s) instead of hanging the GPU."""
+    import time
+    import wholecellfe_b200 as W
+    from wholecellfe_b200 import _lib as B
+    from wholecellfe_b200.ulstep import WcfeError
+    xc, tc = disk_mesh(600); xs, ts = square_mesh(40)
+    parts = strip_partition(xs, ts, 2)
+    part = parts[0]
+    g = W.ULSim("k1"); g.upload_mesh(W.CELL, xc, tc); g.upload_mesh(W.SUBS, xs[part.local_nodes], part.tri_local); g.set_rng(1, 3)
+    nb, slot, rows, en, ep, er, gh = connect_plan(parts, 0)
+    with pytest.raises(WcfeError) as e:                       # no wcfe_halo_info_get before
+        g.halo_connect([bytes(B.HaloInfo())], [0], [1], en, ep, er, gh)
+    assert e.value.code == B.ERR_ARG
+    info = g.halo_info()
+    with pytest.raises(WcfeError) as e:                       # a ghost cannot be exported
+        g.halo_connect([info], [0], rows, gh[:1], [0], [0], gh)
+    assert e.value.code == B.ERR_ARG
+    info = g.halo_info()
+    with pytest.raises(WcfeError) as e:                       # more neighbours than WCFE_HALO_MAX_PEERS
+        g.halo_connect([info] * 9, [0] * 9, [1] * 9, en, ep, er, gh)
+    assert e.value.code == B.ERR_ARG
+    # the strip wired to ITSELF as its neighbour, but told to expect one row more than is ever pushed
+    info = g.halo_info()
+    er_self = np.minimum(er, len(part.local_nodes) - 1)
+    g.halo_connect([info], [0], [len(en) + 1], en, ep, er_self, gh)
+    t = g.step_n(1, 1e-4, 0.0)                                # first step after the connect waits for nothing
+    t0 = time.time()
+    with pytest.raises(WcfeError) as e:
+        g.step_n(2, 1e-4, t)
+    assert e.value.code == B.ERR_PEER and "halo" in str(e.value)
+    assert 5.0 < time.time() - t0 < 60.0                      # the bounded wait, once: later waits return at once
+    g.close()
