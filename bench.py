@@ -68,6 +68,15 @@ def workload_meshes(cell_tris, subs_side, order="morton", diagonals="alternate")
     return xc, tc, xs, ts
 
 
+def workload_name(a, sizes=None):
+    """config.workload, the same string on both arms: the sizes follow from the generators (rings of 6k nodes for the disk, a
+    structured square), so the reference arm does not have to build the full meshes to name them."""
+    if sizes is None:
+        nr = max(2, int(round(math.sqrt(a.cell_tris / 6.0))))
+        sizes = (6 * nr * nr, 1 + 3 * nr * (nr + 1), a.subs_side ** 2, 2 * (a.subs_side - 1) ** 2)
+    return ("synthetic %d-triangle cell (%d nodes) on %d-node substrate (%d triangles), BASELINE configs[3]; one independent replica per GPU" % sizes)
+
+
 def algorithmic_bytes(nn_c, ne_c, nn_s, ne_s):
     """SURVEY.md 8d / BASELINE.md 3.4: every live state word read once + written once, int32 connectivity read once."""
     return 304 * nn_c + 216 * nn_s + 12 * (ne_c + ne_s)
@@ -169,8 +178,7 @@ def run_reference_arm(a):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "gpu_launches": 0,
-            "config": {"workload": "synthetic %d-triangle cell on %d-node substrate (BASELINE configs[3]); CPU arm runs a bounded sample"
-                                   % (a.cell_tris, a.subs_side ** 2), "variant": a.variant, "dt": a.dt},
+            "config": {"workload": workload_name(a), "variant": a.variant, "dt": a.dt, "note": "the CPU arm runs a bounded sample of this workload (cpu_baseline.sample)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -419,8 +427,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "synthetic %d-triangle cell (%d nodes) on %d-node substrate (%d triangles), BASELINE configs[3]; one independent replica per GPU"
-                                       % (ne_c, nn_c, nn_s, ne_s), "variant": a.variant, "dt": a.dt, "rng": "philox", "parallelism": "ensemble x%d (no comms)" % world,
+                "config": {"workload": workload_name(a, (ne_c, nn_c, nn_s, ne_s)), "variant": a.variant, "dt": a.dt, "rng": "philox", "parallelism": "ensemble x%d (no comms)" % world,
                            "l2": "state %.2f GB >> 126 MB L2, no flush" % (step_bytes / 2 / 1e9)},
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
         if cpu:
