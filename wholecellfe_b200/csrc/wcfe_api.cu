@@ -160,7 +160,6 @@ struct wcfe_ctx {
         DevBuf<HaloPeer> peers;
         std::vector<void *> opened;                      // IPC mappings to close
     } halo;
-    int halo_nowait = 0;
     int roundtrip_mode = 0;               // wcfe_step_n_roundtrip: 0 cell only + overlapped, 1 both surfaces serial
     std::string err;
 };
@@ -732,7 +731,6 @@ subs_half:
         if (c->halo.active) {
             // partitioned substrate: border strains go straight into the neighbours' ghost rows, ghost rows are awaited in-kernel
             HaloView hv{c->halo.node_role.p, c->halo.exp_ptr.p, c->halo.exp_ent.p, c->halo.peers.p, c->halo.flags.p, c->halo.npeer, c->halo.step, c->d_err.p};
-            if (c->halo_nowait) hv.step = 0;    // WCFE_HALO_NOWAIT=1: timing experiment only (no waits, pushes land in the wrong buffer every other step)
             if (pdl) CK(launch_pdl(k_subs_ring<false, false, true>, dim3(ss.npatch), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, hv));
             else k_subs_ring<false, false, true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, hv);
             c->halo.step++;
@@ -931,7 +929,6 @@ static int create_impl(wcfe_ctx **out, int device, const wcfe_params *p, int rep
         if (const char *e = std::getenv("WCFE_SUBS_PIPE")) { c->use_pipe = std::atoi(e); if (c->use_pipe) c->subs_kernel = 1; }
         if (const char *e = std::getenv("WCFE_SUBS_KERNEL")) c->subs_kernel = std::atoi(e);
         if (const char *e = std::getenv("WCFE_PDL")) c->use_pdl = std::atoi(e);
-        if (const char *e = std::getenv("WCFE_HALO_NOWAIT")) c->halo_nowait = std::atoi(e);
         const void *pk[] = {(const void *)k_subs_ring<false>, (const void *)k_subs_ring<true>, (const void *)k_subs_pipe<false>, (const void *)k_subs_pipe<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
                             (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>,
                             (const void *)k_cell_patch<true, false, true>, (const void *)k_subs_ring<false, true>, (const void *)k_subs_ring<false, false, true>};

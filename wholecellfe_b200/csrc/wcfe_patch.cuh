@@ -385,9 +385,7 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     if (HALO && prole) {
         if (own && (prole & 2)) nrole = (int)hv.node_role[i];
         if (prole & 1) {
-#ifndef WCFE_HALO_NOWAITCODE
             if (tid == 0) halo_wait(hv.flags, hv.peer, hv.npeer, hv.step, hv.err);   // the neighbours' rows of the previous step have landed
-#endif
             __syncthreads();
             // ghost nodes inside the patch's own range were staged before the wait: read them again, past the (incoherent) L1
             if (nrole == 1) { stage[2 * kPatch + tid] = __ldcg(s.ea_in + i); stage[3 * kPatch + tid] = __ldcg(s.ea_in + np + i); stage[4 * kPatch + tid] = __ldcg(s.ea_in + 3 * (size_t)np + i); }
@@ -543,7 +541,6 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
     const double en0 = ea0 + q0 * imm, en1 = ea1 + q1 * imm, en3 = ea3 + q3 * imm;
     s.ea_out[i] = en0; s.ea_out[np + i] = en1; s.ea_out[3 * np + i] = en3;
-#ifndef WCFE_HALO_NOPUSH
     if (HALO && nrole == 2) {
         // border node: the same three words go straight into the ghost row of every neighbour that mirrors it (signalled by the
         // next kernel in the stream, halo_signal)
@@ -555,7 +552,6 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
             dst[row] = en0; dst[rnp + row] = en1; dst[3 * rnp + row] = en3;
         }
     }
-#endif
     if (DBG) {
         dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
         dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
