@@ -106,6 +106,7 @@ struct wcfe_ctx {
     // k_boundary_finish touches only the cell's boundary vertices and the diagnostics, the substrate kernel neither: it runs on
     // a high-priority side stream, forked after the cell kernel and joined at the end of the step, hidden behind the substrate kernel
     cudaStream_t side = nullptr;
+    int use_cell_counter = 1;             // substrate kernel waits for the cell kernel's completion counter, not for the chain (WCFE_CELL_COUNTER=0)
     int use_pdl = 1;                      // chain cell -> finish -> substrate with programmatic dependent launch instead (WCFE_PDL=0: fork/join)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Surface s[2];
@@ -113,6 +114,7 @@ struct wcfe_ctx {
     GridView grid{};
     DevBuf<int> g_ptr, g_items;
     DevBuf<unsigned long long> b_head;
+    DevBuf<unsigned long long> cell_done; unsigned long long cell_target = 0;   // completion counter of k_cell_patch (BucketView::cell_done) and its running target
     DevBuf<unsigned int> b_node_epoch;    // per substrate node: epoch of the last step in which an incident triangle received an anchor
     DevBuf<int> b_items;
     int b_cap = 0;
@@ -569,6 +571,7 @@ int check_device_errors_bits(wcfe_ctx *c, int e) {
     if (e & ERR_NAN) return fail(c, WCFE_ERR_NUMERIC, "non-finite cell area / centroid: the explicit step went unstable (dt above the stability limit of the stiffest spring?)");
     if (e & ERR_BUCKET_OVERFLOW) return fail(c, WCFE_ERR_CAPACITY, "triangle bucket overflow: more anchors in one substrate triangle than the capacity sized at upload");
     if (e & ERR_REGION) return fail(c, WCFE_ERR_CAPACITY, "an integrin anchor left the padded cell region; re-commit positions to refresh it");
+    if (e & ERR_CHAIN) return fail(c, WCFE_ERR_CUDA, "internal: the substrate kernel did not see the cell kernel complete within 2 s");
     if (e & ERR_HALO_TIMEOUT) return fail(c, WCFE_ERR_PEER, "halo exchange: a neighbouring rank's strain rows did not arrive within 10 s (the peer stopped stepping, or the ranks ran different step counts)");
     return WCFE_OK;
 }
@@ -615,7 +618,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     SurfView cv = view(cs), sv = view(ss);
     sv.X = sv.x;
     if (which & 1) c->epoch++;            // the cell half fills the triangle buckets of this epoch, the substrate half reads them
-    BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch, nullptr, nullptr, 0, 0x7fffffff, c->b_node_epoch.p};
+    BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch, nullptr, nullptr, 0, 0x7fffffff, c->b_node_epoch.p, c->halo.active ? c->cell_done.p : nullptr, c->cell_target, 0, c->d_err.p};      // the completion counter is a partitioned-run device (the increment costs the cell kernel 3 %)
     const int gc = (cs.nn + kBlock - 1) / kBlock, gs = (ss.nn + kBlock - 1) / kBlock;
     // Pr < APrate*dt*exp(-APrate*dt) (UL:1531): the threshold is evaluated on the host with the host libm, as the reference does
     const double thr = c->prm.ap_rate * dt_real * std::exp(-c->prm.ap_rate * dt_real);
@@ -656,6 +659,8 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         if (c->halo.active && c->halo.step > 0) { a.halo_peer = c->halo.peers.p; a.halo_npeer = c->halo.npeer; }   // signal the previous step's halo rows
         const size_t smem = patch_smem_bytes(7, 9, cs.max_halo, cs.max_elem, cs.stride);
         npart = cs.npatch;
+        if (bk.cell_done) c->cell_target += (unsigned long long)cs.npatch * R;      // every CTA of the launch below adds one to cell_done
+        bk.cell_target = c->cell_target;
         if (batch) {
             if (pdl) CK(launch_pdl(k_cell_patch<true, false, true>, dim3(cs.npatch, R), dim3(kThreads), smem, c->stream, cv, pvc, sv, c->grid, bk, bv, c->k, a, (const double *)cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt));
             else k_cell_patch<true, false, true><<<dim3(cs.npatch, R), kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt);
@@ -724,6 +729,8 @@ subs_half:
     cv = view(cs);
     if (planar && c->subs_kernel == 2) {
         // node-centric frozen-substrate kernel
+        bk.cell_target = c->cell_target;
+        bk.wait_cell = (bk.cell_done != nullptr && !reduce && c->use_cell_counter) ? 1 : 0;      // with k_bucket_reduce in between, wait for the chain instead
         ProfScope ps(c, K_SUBS);
         const size_t smem = ring_smem_bytes(ss.max_halo, ss.ring_stride);
         PatchView pvs = pview(ss);
@@ -929,6 +936,7 @@ static int create_impl(wcfe_ctx **out, int device, const wcfe_params *p, int rep
         if (const char *e = std::getenv("WCFE_SUBS_PIPE")) { c->use_pipe = std::atoi(e); if (c->use_pipe) c->subs_kernel = 1; }
         if (const char *e = std::getenv("WCFE_SUBS_KERNEL")) c->subs_kernel = std::atoi(e);
         if (const char *e = std::getenv("WCFE_PDL")) c->use_pdl = std::atoi(e);
+        if (const char *e = std::getenv("WCFE_CELL_COUNTER")) c->use_cell_counter = std::atoi(e);
         const void *pk[] = {(const void *)k_subs_ring<false>, (const void *)k_subs_ring<true>, (const void *)k_subs_pipe<false>, (const void *)k_subs_pipe<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
                             (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>,
                             (const void *)k_cell_patch<true, false, true>, (const void *)k_subs_ring<false, true>, (const void *)k_subs_ring<false, false, true>};
@@ -938,8 +946,8 @@ static int create_impl(wcfe_ctx **out, int device, const wcfe_params *p, int rep
             if ((e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return bail("cudaFuncSetAttribute(carveout)", e);
         }
     }
-    if ((e = c->d_err.alloc((size_t)replicas)) != cudaSuccess || (e = c->d_diag.alloc((size_t)8 * replicas)) != cudaSuccess) return bail("cudaMalloc", e);
-    cudaMemset(c->d_err.p, 0, sizeof(int) * replicas); cudaMemset(c->d_diag.p, 0, 8 * sizeof(double) * replicas);
+    if ((e = c->d_err.alloc((size_t)replicas)) != cudaSuccess || (e = c->d_diag.alloc((size_t)8 * replicas)) != cudaSuccess || (e = c->cell_done.alloc(1)) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(c->d_err.p, 0, sizeof(int) * replicas); cudaMemset(c->d_diag.p, 0, 8 * sizeof(double) * replicas); cudaMemset(c->cell_done.p, 0, sizeof(unsigned long long));
     if (replicas > 1) {
         c->rprm.assign(p, p + replicas);
         std::vector<Consts> kb((size_t)replicas);
@@ -974,7 +982,7 @@ int wcfe_destroy(wcfe_ctx *c) {
         s.g_res.release(); s.g_ffa.release(); s.g_fap.release(); s.g_fbend.release(); s.g_farea.release(); s.g_mm.release(); s.g_rea.release();
         s.p_blob.release(); s.p_ring_blob.release(); s.p_ring_cyc.release(); s.p_elem_ptr.release(); s.p_elem_gid.release(); s.p_cand_l.release();
     }
-    c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release(); c->b_node_epoch.release();
+    c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release(); c->b_node_epoch.release(); c->cell_done.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();
     c->d_kb.release(); c->d_seeds.release(); c->big_count.release(); c->big_list.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);
@@ -1663,6 +1671,8 @@ int wcfe_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_halo_info *peers, con
     CK(cudaMemcpy(c->halo.exp_ptr.p, eptr.data(), sizeof(int) * eptr.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->halo.exp_ent.p, eent.data(), sizeof(int) * eent.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->halo.peers.p, hp.data(), sizeof(HaloPeer) * hp.size(), cudaMemcpyHostToDevice));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemset(c->cell_done.p, 0, sizeof(unsigned long long))); c->cell_target = 0;      // the cell kernel's completion counter starts with the connect
     c->halo.npeer = n_peers; c->halo.step = 0; c->halo.active = true;
     return WCFE_OK;
 }

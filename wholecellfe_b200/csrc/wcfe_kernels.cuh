@@ -51,6 +51,14 @@ struct BucketView {          // triangle -> anchored cell nodes, rebuilt every s
     // anchor into.  A substrate node under the cell whose stamp is stale has nothing to gather and skips the bucket walk (two
     // thirds of the nodes inside the padded bounding box of a round cell).
     unsigned int *node_epoch;       // [np_subs], or nullptr
+    // completion counter of the planar cell kernel: every CTA of k_cell_patch adds one when all of its global writes are out (it
+    // never resets; the host keeps the running target).  The substrate kernel's under-the-cell threads wait for THIS instead of
+    // griddepcontrol.wait, whose prerequisite is the boundary-finish kernel they have no use for (it sits between the two in the
+    // stream): 20-30 us that only show once a strip's substrate kernel is as short as the finish kernel (partitioned runs).
+    unsigned long long *cell_done;  // or nullptr
+    unsigned long long cell_target;
+    int wait_cell;                  // substrate side: 1 = spin on the counter, 0 = griddepcontrol.wait (k_bucket_reduce sits in between)
+    int *chain_err;
 };
 
 struct BoundaryView {        // cell boundary vertices in ascending vertex order (the RNG draw order, UL:1463-1465)
@@ -94,7 +102,7 @@ __device__ __forceinline__ void batch_shift(BucketView &bk, const BatchView &bt,
     if (bk.node_epoch) bk.node_epoch += bt.snodes * r;
 }
 
-enum : int { ERR_BUCKET_OVERFLOW = 1, ERR_LOC_OVERFLOW = 2, ERR_NAN = 4, ERR_REGION = 8 };
+enum : int { ERR_BUCKET_OVERFLOW = 1, ERR_LOC_OVERFLOW = 2, ERR_NAN = 4, ERR_REGION = 8, ERR_CHAIN = 32 };   // 16: ERR_HALO_TIMEOUT (wcfe_patch.cuh)
 
 // ---- predictor: driverVelocities_Explicit + inline predictor (UL:103-124, main.cpp:224-242) ---------------
 __global__ void __launch_bounds__(kBlock) k_predict_cell(int nn, int np, double *__restrict__ x, double *__restrict__ X,

@@ -326,6 +326,11 @@ __device__ __noinline__ void halo_signal(const HaloPeer *peer, int npeer) {
     asm volatile("fence.acq_rel.sys;" ::: "memory");
     for (int q = 0; q < npeer; q++) if (peer[q].nsend) red_release_sys_add(peer[q].flag, peer[q].nsend);
 }
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 // one thread: wait until every neighbour's rows of the previous step have arrived.  Bounded: after 10 s (a peer died) the error
 // flag is raised and this and every later wait returns at once -- a wrong answer that is reported, never a hung GPU.
@@ -427,7 +432,9 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     // written so that every scale factor rides on the accumulating multiply-add.
     struct Nb { double2 p, t; double t3; };
     auto load_nb = [&](int l) { Nb n; n.p = sxy[l]; n.t = se01[l]; n.t3 = se3[l]; return n; };
-    const double c0 = 1.0 - two3 * ea0, c1 = 1.0 - two3 * ea1, c3 = two3 * ea3;            // own node's share of a00, a11, b01
+    // rounded products, as stored in the table for the neighbours (left to the compiler, 1 - two3*ea was fused in one template
+    // instantiation and built from the table's rounded product in another: a last-bit difference between a strip and the whole mesh)
+    const double c0 = __dsub_rn(1.0, __dmul_rn(two3, ea0)), c1 = __dsub_rn(1.0, __dmul_rn(two3, ea1)), c3 = __dmul_rn(two3, ea3);   // own node's share of a00, a11, b01
     const double A0c = 1.0 - 2.0 * ea0, A1c = 1.0 - 2.0 * ea1, B3c = 2.0 * ea3;            // a at e_avg == ea_own: Re_ea vanishes there
     const double mh = 0.5 * k.mu_subs * k.thick, cw = k.thick / 6.0, cwh = k.thick / 12.0;
     struct Contrib { double f1, f2, m, a00, a11, b01, aw; };
@@ -435,12 +442,15 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
         Contrib c;
         c.a00 = c0 - (J.t.x + K.t.x); c.a11 = c1 - (J.t.y + K.t.y); c.b01 = c3 + (J.t3 + K.t3);
         const double G1x = J.p.x - myxy.x, G1y = J.p.y - myxy.y, G2x = K.p.x - myxy.x, G2y = K.p.y - myxy.y;
-        const double Wz = G1x * G2y - G1y * G2x;
-        const double det2 = c.a00 * c.a11 - c.b01 * c.b01;
+        // every two-product expression is contracted BY HAND (one rounded product, one fused multiply-add): left to the compiler the
+        // choice of which product to fuse differed between template instantiations of this kernel, and a strip of a partitioned run
+        // (HALO instantiation) stopped matching the single-GPU run in the last bit
+        const double Wz = fma(G1x, G2y, -__dmul_rn(G1y, G2x));
+        const double det2 = fma(c.a00, c.a11, -__dmul_rn(c.b01, c.b01));
         const double idet = rcp_newton(det2);
         const double dx = G2y - G1y, dy = G1x - G2x;
-        c.f1 = idet * (c.a11 * dx + c.b01 * dy) - det2 * dx;                // (S / mu) (dx, dy)
-        c.f2 = idet * (c.b01 * dx + c.a00 * dy) - det2 * dy;
+        c.f1 = fma(idet, fma(c.a11, dx, __dmul_rn(c.b01, dy)), -__dmul_rn(det2, dx));                // (S / mu) (dx, dy)
+        c.f2 = fma(idet, fma(c.b01, dx, __dmul_rn(c.a00, dy)), -__dmul_rn(det2, dy));
         c.m = Wz > 0 ? -mh : mh;                                           // -(t/2) mu sign(W)
         c.aw = fabs(Wz);                                                   // 2 A0
         return c;
@@ -480,7 +490,16 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     if (HALO && nrole == 1) return;          // ghost node (incomplete fan): its owner computes it and stores the result here
     unsigned int stamp = bk.epoch - 1u;
     if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
-        pdl_wait();               // first touch of what the cell kernel produced (stamps, buckets, anchor records); all above overlaps its tail
+        // first touch of what the cell kernel produced (stamps, buckets, anchor records); all above overlaps its tail
+        if (bk.wait_cell) {
+            if (ld_acquire_gpu(bk.cell_done) < bk.cell_target) {        // all CTAs of this step's cell kernel are resident or done: bounded anyway
+                const unsigned long long t0 = global_ns();
+                while (ld_acquire_gpu(bk.cell_done) < bk.cell_target) {
+                    if (global_ns() - t0 > 2000000000ull) { atomicOr(bk.chain_err, ERR_CHAIN); break; }
+                    __nanosleep(32);
+                }
+            }
+        } else pdl_wait();
         stamp = bk.node_epoch[i];
     }
     if (stamp == bk.epoch) {      // an incident triangle received an anchor in this step (two thirds of the nodes in the box skip the walk)
@@ -1058,7 +1077,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         }
     }
     block_reduce4(red, shred);
-    if (tid == 0) { for (int q = 0; q < 4; q++) a.partials[(size_t)4 * blockIdx.x + q] = red[q]; }
+    if (tid == 0) {
+        for (int q = 0; q < 4; q++) a.partials[(size_t)4 * blockIdx.x + q] = red[q];
+        // every thread's global writes (state, buckets, stamps, anchor records) precede the barriers of the reduction above: one
+        // release by this thread publishes them all to whoever acquires the counter (k_subs_ring)
+        if (bk.cell_done) { __threadfence(); atomicAdd(bk.cell_done, 1ull); }
+    }
 }
 
 }   // namespace wcfe
