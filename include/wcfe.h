@@ -219,6 +219,22 @@ int wcfe_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_halo_info *peers, con
                       int n_export, const int *export_node, const int *export_peer, const int *export_row, int n_ghost, const int *ghost_node);
 int wcfe_halo_disconnect(wcfe_ctx *c);
 
+/* Host-side helper (no GPU work, usable from any host language): cut ONE mesh into `world` vertical strips and produce, for
+ * `rank`, the local strip to upload and the tables wcfe_halo_connect takes.  Nodes are sorted by x (ties by id) and cut into runs
+ * of equal node count, or -- with one weight per node -- of equal total weight (nodes under the cell cost more: see
+ * wholecellfe_b200/partition.py cell_weights).  A rank holds every element with at least one owned vertex; local nodes and
+ * elements keep ascending global ids, so nodal sums are formed in the single-GPU order.  Call it with the same arguments on every
+ * rank.  Sizes first, then fetch the arrays into caller-owned buffers (any pointer may be NULL):
+ *   mesh: local_nodes[n_local] global id of every local node; tri_local[3*n_elem]; elem_gid[n_elem]; owned_local[n_owned];
+ *         ghost_local[n_ghost] (= ghost_node of wcfe_halo_connect)
+ *   halo: peer_rank[n_peers] ascending = the peer-slot order; my_slot_at_peer, rows_from_peer [n_peers]; export_* [n_export] */
+typedef struct wcfe_strip wcfe_strip;
+int wcfe_strip_partition(int nn, const double *xyz, int ne, const int *tri, const double *weights, int world, int rank, wcfe_strip **out);
+int wcfe_strip_sizes(const wcfe_strip *s, int *n_local, int *n_elem, int *n_owned, int *n_ghost, int *n_peers, int *n_export);
+int wcfe_strip_mesh(const wcfe_strip *s, int *local_nodes, int *tri_local, int *elem_gid, int *owned_local, int *ghost_local);
+int wcfe_strip_halo(const wcfe_strip *s, int *peer_rank, int *my_slot_at_peer, int *rows_from_peer, int *export_node, int *export_peer, int *export_row);
+int wcfe_strip_free(wcfe_strip *s);
+
 #ifdef __cplusplus
 }
 #endif

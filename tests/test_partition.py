@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 from wholecellfe_b200.meshgen import square_mesh, disk_mesh
-from wholecellfe_b200.partition import strip_partition, exchange_rows, connect_plan, neighbours, cell_weights
+from wholecellfe_b200.partition import strip_partition, exchange_rows, connect_plan, neighbours, cell_weights, native_strip
 
 
 def _free_port():
@@ -72,6 +72,43 @@ def test_connect_plan_is_consistent_across_ranks(world):
         # every ghost row is pushed by exactly one neighbour
         got = np.concatenate([plans[q][5][plans[q][4] == plans[q][0].index(r)] for q in nb]) if nb else np.zeros(0, int)
         assert np.array_equal(np.sort(got), np.sort(gh))
+
+
+@pytest.mark.parametrize("balanced", [False, True])
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+def test_c_abi_strip_partition_equals_python(world, balanced):
+    """wcfe_strip_partition (host-only C++ in libwcfe.so: what a C++ / MPI host calls) produces the same strips and the same
+    wcfe_halo_connect tables as partition.py, on a structured and on an unstructured-numbered mesh."""
+    from wholecellfe_b200.build import build
+    build()
+    for xs, ts in (square_mesh(37), disk_mesh(1500)):
+        w = cell_weights(xs, np.array([[-20.0, -5.0, 0.0], [0.0, 12.0, 0.0], [5.0, -8.0, 0.0]])) if balanced else None
+        parts = strip_partition(xs, ts, world, w)
+        for r in range(world):
+            nat = native_strip(xs, ts, world, r, w)
+            p = parts[r]
+            assert np.array_equal(nat["local_nodes"], p.local_nodes) and np.array_equal(nat["elem_gid"], p.elem_gid)
+            assert np.array_equal(nat["tri_local"], p.tri_local)
+            assert np.array_equal(nat["owned_local"], p.owned_local)
+            nb, slot, rows, en, ep, er, gh = connect_plan(parts, r)
+            assert np.array_equal(nat["ghost_local"], gh)
+            assert list(nat["peer_rank"]) == nb and list(nat["my_slot_at_peer"]) == slot and list(nat["rows_from_peer"]) == rows
+            assert np.array_equal(nat["export_node"], en) and np.array_equal(nat["export_peer"], ep) and np.array_equal(nat["export_row"], er)
+
+
+def test_c_abi_strip_partition_rejects_bad_arguments():
+    import ctypes as C
+    from wholecellfe_b200 import _lib as B
+    L = B.load()
+    xs, ts = square_mesh(5)
+    xs = np.ascontiguousarray(xs); ts = np.ascontiguousarray(ts, dtype=np.int32)
+    h = C.c_void_p()
+    args = (len(xs), xs.ctypes.data_as(B._dp), len(ts), ts.ctypes.data_as(B._ip), None)
+    assert L.wcfe_strip_partition(*args, 2, 2, C.byref(h)) == B.ERR_ARG            # rank outside [0, world)
+    assert L.wcfe_strip_partition(*args, 0, 0, C.byref(h)) == B.ERR_ARG
+    bad = ts.copy(); bad[0, 0] = len(xs)
+    assert L.wcfe_strip_partition(len(xs), xs.ctypes.data_as(B._dp), len(bad), bad.ctypes.data_as(B._ip), None, 2, 0, C.byref(h)) == B.ERR_ARG
+    assert L.wcfe_strip_sizes(None, None, None, None, None, None, None) == B.ERR_ARG and L.wcfe_strip_free(None) == B.ERR_ARG
 
 
 def _gloo_worker(rank, world, port, q):

@@ -25,7 +25,8 @@ SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_param
            "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
            "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync",
            "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed", "wcfe_set_roundtrip_mode",
-           "wcfe_halo_info_get", "wcfe_halo_connect", "wcfe_halo_disconnect"]
+           "wcfe_halo_info_get", "wcfe_halo_connect", "wcfe_halo_disconnect",
+           "wcfe_strip_partition", "wcfe_strip_sizes", "wcfe_strip_mesh", "wcfe_strip_halo", "wcfe_strip_free"]
 
 
 class Params(C.Structure):
@@ -104,5 +105,10 @@ def load():
     L.wcfe_halo_info_get.argtypes = [vp, C.POINTER(HaloInfo)]
     L.wcfe_halo_connect.argtypes = [vp, C.c_int, C.POINTER(HaloInfo), _ip, _ip, C.c_int, _ip, _ip, _ip, C.c_int, _ip]
     L.wcfe_halo_disconnect.argtypes = [vp]
+    L.wcfe_strip_partition.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.wcfe_strip_sizes.argtypes = [vp] + [_ip] * 6
+    L.wcfe_strip_mesh.argtypes = [vp] + [_ip] * 5
+    L.wcfe_strip_halo.argtypes = [vp] + [_ip] * 6
+    L.wcfe_strip_free.argtypes = [vp]
     _lib = L
     return L

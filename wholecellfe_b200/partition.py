@@ -118,6 +118,34 @@ def connect_plan(parts, rank):
     return nb, my_slot, rows_from, cat(en), cat(ep), cat(er), ghost_local
 
 
+def native_strip(xyz, tri, world, rank, weights=None):
+    """The same partition and connect plan from the C ABI's host-side helper (wcfe_strip_partition, csrc/wcfe_partition.cu):
+    what a C++ / MPI host would call.  Returns a dict of numpy arrays named like the C arguments."""
+    import ctypes as C
+    from . import _lib as B
+    L = B.load()
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64); tri = np.ascontiguousarray(tri, dtype=np.int32)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    h = C.c_void_p()
+    rc = L.wcfe_strip_partition(len(xyz), xyz.ctypes.data_as(B._dp), len(tri), tri.ctypes.data_as(B._ip),
+                                None if w is None else w.ctypes.data_as(B._dp), world, rank, C.byref(h))
+    if rc:
+        raise ValueError("wcfe_strip_partition failed (%d)" % rc)
+    n = [C.c_int() for _ in range(6)]
+    L.wcfe_strip_sizes(h, *[C.byref(v) for v in n])
+    n_local, n_elem, n_owned, n_ghost, n_peers, n_export = [v.value for v in n]
+    ia = lambda k: np.zeros(k, dtype=np.int32)
+    ip = lambda a: a.ctypes.data_as(B._ip)
+    out = {"local_nodes": ia(n_local), "tri_local": ia(3 * n_elem), "elem_gid": ia(n_elem), "owned_local": ia(n_owned), "ghost_local": ia(n_ghost),
+           "peer_rank": ia(n_peers), "my_slot_at_peer": ia(n_peers), "rows_from_peer": ia(n_peers),
+           "export_node": ia(n_export), "export_peer": ia(n_export), "export_row": ia(n_export)}
+    L.wcfe_strip_mesh(h, ip(out["local_nodes"]), ip(out["tri_local"]), ip(out["elem_gid"]), ip(out["owned_local"]), ip(out["ghost_local"]))
+    L.wcfe_strip_halo(h, ip(out["peer_rank"]), ip(out["my_slot_at_peer"]), ip(out["rows_from_peer"]), ip(out["export_node"]), ip(out["export_peer"]), ip(out["export_row"]))
+    L.wcfe_strip_free(h)
+    out["tri_local"] = out["tri_local"].reshape(-1, 3)
+    return out
+
+
 class InProcessStrips:
     """All strips of a partitioned run driven by ONE process: one context per strip on the given devices (several strips may share
     a GPU), connected through plain device pointers (peer access between GPUs).  Strips advance in lockstep, one step queued on
