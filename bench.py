@@ -254,6 +254,20 @@ def other_configs(W):
         out["config1_%s_us_per_step" % var] = g.last_step_ms() / 800 * 1e3
         out["config1_%s_element_steps_per_sec" % var] = (len(tc) + len(ts)) * 800 / (g.last_step_ms() * 1e-3)
         g.close()
+    # BASELINE configs[2]: kMD law on a ~100k-triangle synthetic disk over a refined substrate (node spacing 0.25 um <= 4 x the cell's),
+    # dt 5e-5 as in the reference's JAP scripts (scripts/cell_JAP.txt:5), counter-based RNG
+    try:
+        from wholecellfe_b200.meshgen import disk_mesh, square_mesh
+        xc3, tc3 = disk_mesh(100000); xs3, ts3 = square_mesh(400)
+        g = W.ULSim("kMD"); g.upload_mesh(W.CELL, xc3, tc3); g.upload_mesh(W.SUBS, xs3, ts3); g.set_rng(1, 1)
+        t3 = g.step_n(50, 5e-5, 0.0)
+        g.step_n(500, 5e-5, t3)
+        out["config3_kMD_mesh"] = "%d-triangle cell on %d-triangle substrate" % (len(tc3), len(ts3))
+        out["config3_kMD_ms_per_step"] = g.last_step_ms() / 500
+        out["config3_kMD_element_steps_per_sec"] = (len(tc3) + len(ts3)) * 500 / (g.last_step_ms() * 1e-3)
+        g.close()
+    except Exception as e:                                   # side measurement: never fatal
+        out["config3_kMD"] = "skipped: %s" % e
     # the whole application (reference main.cpp + El Topo + VTK frames every step), with the reference's own step and with ours
     try:
         out.update(whole_application(xc, tc, xs, ts))
