@@ -24,6 +24,7 @@ def test_refined_kmd_mesh_step_by_step_against_grid_oracle():
             g.set(W.CELL, f, o.get(0, f))
         for f in ["V", "A", "ea"]:
             g.set(W.SUBS, f, o.get(1, f))
+        assert g.path_info()["planar"]             # the oracle's state (1e-16 noise in e_zz) stays on the production kernels
         g.step(dt, t); o.step(dt, t); t += dt
         for f in ["x", "V", "A", "ea", "cC", "fa_u"]:
             ref = o.get(0, f)

@@ -109,3 +109,34 @@ def test_philox_counter_rng_is_a_pure_function(hm):
     assert hm.hm_philox(2, 0, 0) != hm.hm_philox(1, 0, 0)
     u = np.array([hm.hm_philox(5, s, o) for s in range(64) for o in range(64)], dtype=np.float64) / 2**32
     assert abs(u.mean() - 0.5) < 0.02 and abs(u.var() - 1 / 12) < 0.01
+
+
+def test_frozen_substrate_element_matches_reference_at_nonzero_strain(hm):
+    """elem_eval_frozen (S = mu (a^-1 - det a I), the arithmetic of k_subs_ring / k_subs_patch) against the reference's own
+    substrate overload of evalElementRe (UL:988-1174) on golden vectors with x == X and planar strain 1e-6 .. 5e-2, both
+    orientations; also the C restatement.  Error scale: the element's own |Re| plus the reference's cancellation floor
+    (~1e-15 mu L: its long route leaves |Res_subs| ~ 1e-7 on a strain-free substrate)."""
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "elements_frozen.npz"))
+    mu = 1e6
+    worst = worst_o = worst_ea = 0.0
+    for i in range(len(g["X"])):
+        X = g["X"][i]; ea = g["ea"][i]
+        X6 = np.ascontiguousarray(X[:, :2]); e6 = 1 / 3 * ea[0] + 1 / 3 * ea[1] + 1 / 3 * ea[2]
+        e3 = np.ascontiguousarray(e6[[0, 1, 3]])
+        r1 = np.zeros(2); r2 = np.zeros(2); A0 = C.c_double()
+        hm.hm_elem_eval_frozen(d(X6), d(e3), C.c_double(mu), C.c_double(1.0), d(r1), d(r2), C.byref(A0))
+        Re = g["Re"][i].reshape(3, 3)
+        L = np.abs(X[1:] - X[0]).max()
+        sc = np.abs(Re).max() + 1e-15 * mu * L / 1e-11                      # |Re| + the cancellation floor, expressed at the 1e-11 gate
+        worst = max(worst, np.abs(Re[1, :2] - r1).max() / sc, np.abs(Re[2, :2] - r2).max() / sc, np.abs(Re[0, :2] + r1 + r2).max() / sc)
+        assert np.abs(Re[:, 2]).max() == 0.0                                # the reference's out-of-plane residual is exactly 0 for a planar state
+        # e_s == averaged e for F == I: Re_ea = (e_avg - ea_i) A0 / 3 (UL:1170), MM = A0 / 3
+        mine = np.array([(1 / 3) * (e6 - ea[k]) * A0.value for k in range(3)])
+        # (the reference forms e_s = (I - b^-1)/2 as a difference from 1: an ABSOLUTE rounding error of ~2e-16 whatever the strain)
+        sc_ea = (np.abs(ea).max() + 1e-4) * A0.value
+        worst_ea = max(worst_ea, np.abs(g["Re_ea"][i].reshape(3, 6) - mine).max() / sc_ea)
+        assert abs(g["MMe"][i][0] - A0.value / 3) <= 1e-14 * A0.value
+        Ro, Reao, MMo = eval_element("k1", 2, X, X, ea, 0.005, np.zeros(3), float(g["time"][i]))
+        worst_o = max(worst_o, np.abs(Ro - g["Re"][i]).max() / sc, np.abs(Reao - g["Re_ea"][i]).max() / sc_ea)
+    assert worst < 1e-11 and worst_ea < 1e-11 and worst_o < 1e-11, (worst, worst_ea, worst_o)
