@@ -186,6 +186,45 @@ void ulref_step(ulref *h, double dt, double t_curr, double kint, double subs_sca
     updateForces_Explicit(h->Xs_prev, s.x, s.V, h->Vh_s, s.A, s.ea, dt, dt, s.mesh, t_curr, c.fa_u, c.cC, c.x, c.mesh);   // :361
 }
 
+// The same step when the host integrator accepts LESS than the requested dt (El Topo's integrate() with collision_safety on,
+// dynamicsurface.cpp:462-637, returns actual_dt <= dt and leaves the vertices part of the way): main.cpp:244-335 literally, with
+// integrate() modelled as "move the fraction frac of the way, actual_dt = frac * dt".  frac_subs < 1 also takes the redo branch
+// of main.cpp:322-335 (the cell is advanced a second time with the substrate's smaller dt -- as the reference does).
+void ulref_step_short(ulref *h, double dt, double t_curr, double kint, double frac_cell, double frac_subs) {
+    Quiet q;
+    Surface &c = h->cell, &s = h->subs;
+    const int nc = (int)c.x.size(), ns = (int)s.x.size();
+    auto integrate = [](std::vector<Vec3d> &pos, const std::vector<Vec3d> &newpos, double frac, double dt_in, double &actual) {
+        for (size_t i = 0; i < pos.size(); i++) pos[i] = frac == 1.0 ? newpos[i] : pos[i] + frac * (newpos[i] - pos[i]);
+        actual = frac * dt_in;
+    };
+    double curr_dt = dt, actual_dt;
+    h->Vh_c.assign(nc, Vec3d(0, 0, 0)); h->Vh_s.assign(ns, Vec3d(0, 0, 0));
+    driverVelocities_Explicit(c.x, c.V, h->Vh_c, c.A, curr_dt);                  // main.cpp:224
+    std::vector<Vec3d> newp(nc);
+    for (int i = 0; i < nc; i++) newp[i] = c.x[i] + curr_dt * h->Vh_c[i];      // main.cpp:227-231
+    h->Xc_prev = c.x;                                                            // initial_positions, main.cpp:242
+    integrate(c.x, newp, frac_cell, curr_dt, actual_dt);                         // main.cpp:248
+    const double ori_dt = curr_dt;                                               // main.cpp:251
+    curr_dt = actual_dt;
+    driverVelocities_Biaxial(s.x, s.V, h->Vh_s, s.A, curr_dt, t_curr);           // main.cpp:293
+    std::vector<Vec3d> newps(ns);
+    for (int i = 0; i < ns; i++) newps[i] = s.x[i] + 0 * curr_dt * h->Vh_s[i];  // main.cpp:298-302
+    h->Xs_prev = s.x;                                                            // main.cpp:311
+    integrate(s.x, newps, frac_subs, curr_dt, actual_dt);                        // main.cpp:316
+    const double ori_dt2 = curr_dt;
+    curr_dt = actual_dt;
+    if (actual_dt < ori_dt2) {                                                   // main.cpp:322-335
+        driverVelocities_Explicit(c.x, c.V, h->Vh_c, c.A, curr_dt);
+        for (int i = 0; i < nc; i++) newp[i] = c.x[i] + curr_dt * h->Vh_c[i];
+        integrate(c.x, newp, 1.0, curr_dt, actual_dt);
+        curr_dt = actual_dt;
+    }
+    updateFA(c.cA, c.cC, c.fa_u, actual_dt, h->Xc_prev, c.x, c.mesh, h->Xs_prev, s.x, s.mesh, kint);   // main.cpp:354
+    updateForces_Explicit(h->Xc_prev, c.x, c.V, h->Vh_c, c.A, c.ea, c.cA, c.cB, c.cC, c.fa_u, ori_dt, actual_dt, c.mesh, t_curr);   // :360
+    updateForces_Explicit(h->Xs_prev, s.x, s.V, h->Vh_s, s.A, s.ea, ori_dt, actual_dt, s.mesh, t_curr, c.fa_u, c.cC, c.x, c.mesh);   // :361
+}
+
 #ifndef ULREF_ADAPTER_ONLY
 // ---- fine-grained entry points for known-answer tests -------------------------------------------
 

@@ -36,6 +36,7 @@ def _load(variant, kind="ref"):
         lib.ulref_set.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
         lib.ulref_boundary_flags.argtypes = [C.c_void_p, C.c_int, _ip]
         lib.ulref_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+        lib.ulref_step_short.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
         return lib
     lib.ulref_create.restype = C.c_void_p
     lib.ulref_create.argtypes = [C.c_int, _dp, C.c_int, _ip, C.c_int, _dp, C.c_int, _ip]
@@ -48,6 +49,7 @@ def _load(variant, kind="ref"):
     lib.ulref_onering.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, C.c_int]
     lib.ulref_boundary_flags.argtypes = [C.c_void_p, C.c_int, _ip]
     lib.ulref_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.ulref_step_short.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.ulref_eval_element.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, C.c_double, _dp, _dp, _dp]
     lib.ulref_force_field.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp, _dp]
     lib.ulref_write_vtk_cell.argtypes = [C.c_void_p, C.c_double, C.c_char_p]
@@ -92,6 +94,10 @@ class RefSim:
 
     def step(self, dt, t_curr, subs_scale=0.0):
         self.lib.ulref_step(self.h, dt, t_curr, self.kint, subs_scale)
+
+    def step_short(self, dt, t_curr, frac_cell, frac_subs=1.0):
+        """one step in which the host integrator accepts only a fraction of the requested dt (main.cpp:244-335)"""
+        self.lib.ulref_step_short(self.h, dt, t_curr, self.kint, frac_cell, frac_subs)
 
     def write_vtk(self, surface, time, path, fa_source=0):
         """the reference's own writer (cellBP/iomesh.cpp)"""

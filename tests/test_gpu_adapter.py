@@ -45,3 +45,31 @@ def test_adapter_kmd_single_steps_from_oracle_state(meshes):
         for f in ["x", "V", "A", "ea", "cC", "fa_u"]:
             ref = o.get(0, f)
             assert rel_err(a.get(0, f), ref, max(np.abs(ref).max(), FLOOR[f])) < 1e-10, (k, f)
+
+
+@pytest.mark.parametrize("frac_cell,frac_subs", [(0.8, 1.0), (0.4, 1.0), (1.0, 0.5), (0.7, 0.6)])
+def test_adapter_when_the_host_integrator_shortens_the_step(meshes, frac_cell, frac_subs):
+    """El Topo's integrate() may accept less than the requested dt (collision_safety on): main.cpp then forms the substrate's --
+    and, in the redo branch, the cell's -- V_hlf with the SHORTENED dt while updateForces_Explicit still receives ori_dt
+    (main.cpp:244-361).  The same driver sequence, once against the reference's own UL_growth_explicit.o and once against the
+    adapter + libwcfe.so, k1, 12 steps with every third one shortened: the velocity update V = V_hlf + (dt_real - dt/2) A
+    (UL:497, :622) must use the caller's V_hlf, not one rebuilt from ori_dt."""
+    from oracle.refrun import ref_available
+    if not ref_available("k1"):
+        pytest.skip("oracle/_ref/libulref_k1.so not built here")
+    xc, tc, xs, ts = meshes
+    a = RefSim("k1", xc, tc, xs, ts, kind="adapter"); a.srand(1)
+    r = RefSim("k1", xc, tc, xs, ts, kind="ref"); r.srand(1)
+    t = 0.0
+    for k in range(12):
+        if k % 3 == 2:
+            a.step_short(0.005, t, frac_cell, frac_subs); r.step_short(0.005, t, frac_cell, frac_subs)
+            t += 0.005 * frac_cell * frac_subs
+        else:
+            a.step(0.005, t); r.step(0.005, t); t += 0.005
+        for f in ["x", "V", "A", "ea", "cC", "fa_u"]:
+            ref = r.get(0, f)
+            assert rel_err(a.get(0, f), ref, max(np.abs(ref).max(), FLOOR[f])) < 1e-10, (k, f)
+        for f in ["V", "A", "ea"]:
+            ref = r.get(1, f)
+            assert rel_err(a.get(1, f), ref, max(np.abs(ref).max(), SUBS_FLOOR[f])) < 1e-9, (k, f)

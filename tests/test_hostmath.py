@@ -140,3 +140,32 @@ def test_frozen_substrate_element_matches_reference_at_nonzero_strain(hm):
         Ro, Reao, MMo = eval_element("k1", 2, X, X, ea, 0.005, np.zeros(3), float(g["time"][i]))
         worst_o = max(worst_o, np.abs(Ro - g["Re"][i]).max() / sc, np.abs(Reao - g["Re_ea"][i]).max() / sc_ea)
     assert worst < 1e-11 and worst_ea < 1e-11 and worst_o < 1e-11, (worst, worst_ea, worst_o)
+
+
+def test_planar_element_matches_reference_vectors(hm, elements):
+    """elem_eval_planar (what k_cell_patch evaluates; sqrt-free pressure, metric inverse from the current area) against the
+    reference's own evalElementRe on the planar half of the golden element vectors (both materials)."""
+    e = elements
+    worst = 0.0; n = 0
+    for i in range(len(e["X"])):
+        if np.abs(e["X"][i][:, 2]).max() != 0 or np.abs(e["x"][i][:, 2]).max() != 0 or np.abs(e["ea"][i][:, [2, 4, 5]]).max() != 0:
+            continue
+        n += 1
+        mat = int(e["mat"][i]); time = float(e["time"][i])
+        mu = 1000.0 if mat == 1 else 1e6
+        tact = (time * 200 if time < 2 else 400) if mat == 1 else 0.0
+        ea = e["ea"][i]
+        e6 = 1 / 3 * ea[0] + 1 / 3 * ea[1] + 1 / 3 * ea[2]
+        e3 = np.ascontiguousarray(e6[[0, 1, 3]])
+        X6 = np.ascontiguousarray(e["X"][i][:, :2]); x6 = np.ascontiguousarray(e["x"][i][:, :2])
+        r1 = np.zeros(2); r2 = np.zeros(2); eas = np.zeros(3); A0 = C.c_double(); ac = C.c_double()
+        hm.hm_elem_eval_planar(d(X6), d(x6), d(e3), C.c_double(mu), C.c_double(tact * 0.5), C.c_double(1.0), d(r1), d(r2), d(eas), C.byref(A0), C.byref(ac))
+        Re = e["Re"][i].reshape(3, 3)
+        sc = np.abs(Re).max()
+        worst = max(worst, np.abs(Re[1, :2] - r1).max() / sc, np.abs(Re[2, :2] - r2).max() / sc, np.abs(Re[0, :2] + r1 + r2).max() / sc)
+        eas6 = np.zeros(6); eas6[[0, 1, 3]] = eas
+        mine = np.array([(1 / 3) * (eas6 - ea[k]) * A0.value for k in range(3)])
+        ref = e["Re_ea"][i].reshape(3, 6)
+        worst = max(worst, np.abs(ref[:, [0, 1, 3]] - mine[:, [0, 1, 3]]).max() / (np.abs(eas).max() * A0.value))
+        assert abs(e["MMe"][i][0] - A0.value / 3) <= 1e-14 * A0.value
+    assert n >= 40 and worst < 1e-11, (n, worst)

@@ -58,14 +58,23 @@ void ensure_context() {
 const double *flat(const std::vector<Vec3d> &v) { return v.empty() ? nullptr : &v[0][0]; }   // Vec3d == 3 contiguous doubles
 double *flat(std::vector<Vec3d> &v) { return v.empty() ? nullptr : &v[0][0]; }
 
-// (re)upload connectivity when the mesh changed (remeshing: SurfTrack::improve_mesh / defrag_mesh)
-void sync_mesh(int surface, const std::vector<Vec3d> &x, const NonDestructiveTriMesh &mesh) {
+// (re)upload connectivity when the mesh changed (remeshing: SurfTrack::improve_mesh / defrag_mesh).  with_coords: the signature
+// also covers the coordinates -- the SUBSTRATE's device copy (positions, point-location grid, patch tables) is refreshed only
+// here, and El Topo's smoothing / collision resolution may move its vertices without touching the connectivity; the cell's
+// positions travel every step anyway.
+void sync_mesh(int surface, const std::vector<Vec3d> &x, const NonDestructiveTriMesh &mesh, bool with_coords) {
     MeshSig s;
     s.nv = x.size(); s.nt = mesh.num_triangles();
     unsigned long long h = 1469598103934665603ull;
     for (size_t t = 0; t < s.nt; t++) {
         const Vec3st &tri = mesh.get_triangle(t);
         for (int j = 0; j < 3; j++) { h ^= (unsigned long long)tri[j]; h *= 1099511628211ull; }
+    }
+    if (with_coords) {
+        for (size_t v = 0; v < s.nv; v++) for (int j = 0; j < 3; j++) {
+            unsigned long long bits; const double d = x[v][j]; std::memcpy(&bits, &d, 8);
+            h ^= bits; h *= 1099511628211ull;
+        }
     }
     s.hash = h;
     MeshSig &old = g.sig[surface];
@@ -107,10 +116,19 @@ void driverVelocities_Biaxial(const std::vector<Vec3d> &X_t, std::vector<Vec3d> 
 void updateFA(std::vector<double> &c_A, std::vector<double> &c_C, std::vector<Vec3d> &fa_u, double dt_real,
               const std::vector<Vec3d> &X_t_cell, const std::vector<Vec3d> &x_t_cell, const NonDestructiveTriMesh &mesh_cell,
               const std::vector<Vec3d> &X_t_subs, const std::vector<Vec3d> &x_t_subs, const NonDestructiveTriMesh &mesh_subs, double kint) {
-    (void)kint; (void)x_t_subs;       // kint is fixed by the variant (main.cpp:350-354); the substrate is frozen (main.cpp:299)
+    (void)kint;                       // kint is fixed by the variant (main.cpp:350-354)
     ensure_context();
-    sync_mesh(WCFE_SUBS, X_t_subs, mesh_subs);
-    sync_mesh(WCFE_CELL, X_t_cell, mesh_cell);
+    // the device step assumes a FROZEN substrate (the literal 0* of main.cpp:299: x_t_subs == X_t_subs, F == I, subs_u == 0).  A
+    // host integrator that moved a substrate vertex within this step (collision resolution) has left that regime: say so instead
+    // of silently computing with stale positions
+    if (x_t_subs.size() != X_t_subs.size()) { std::fprintf(stderr, "wcfe adapter: substrate changed size inside a step\n"); std::abort(); }
+    for (size_t v = 0; v < x_t_subs.size(); v++)
+        if (x_t_subs[v][0] != X_t_subs[v][0] || x_t_subs[v][1] != X_t_subs[v][1] || x_t_subs[v][2] != X_t_subs[v][2]) {
+            std::fprintf(stderr, "wcfe adapter: substrate vertex %zu moved within the step (x_t != X_t): a moving substrate is not supported by the frozen-substrate device path (WCFE_ERR_UNSUPPORTED)\n", v);
+            std::abort();
+        }
+    sync_mesh(WCFE_SUBS, X_t_subs, mesh_subs, true);     // vertices moved BETWEEN steps (smoothing): fresh positions, grid and tables
+    sync_mesh(WCFE_CELL, X_t_cell, mesh_cell, false);
     OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_X, flat(x_t_cell)));
     OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_XPREV, flat(X_t_cell)));
     OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_CA, c_A.data()));
@@ -125,6 +143,9 @@ void updateFA(std::vector<double> &c_A, std::vector<double> &c_C, std::vector<Ve
 void updateForces_Explicit(const std::vector<Vec3d> &X_t, const std::vector<Vec3d> &x_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf,
                            std::vector<Vec3d> &A_t, std::vector<Eigen::VectorXd> &ea_t, std::vector<double> &c_A, std::vector<double> &c_B,
                            std::vector<double> &c_C, std::vector<Vec3d> &fa_u, double dt, double dt_real, const NonDestructiveTriMesh &mesh, double t_tot) {
+    // V_t_hlf is not uploaded: the device forms it from V_t, A_t and the dt of the LAST driverVelocities_Explicit call, which
+    // wcfe_driver_velocities recorded -- the caller's vector bit for bit, also when El Topo shortened the step and main.cpp
+    // re-ran the driver with the smaller dt (main.cpp:329) while `dt` here is still ori_dt (main.cpp:360)
     (void)X_t; (void)x_t; (void)V_t_hlf; (void)c_B; (void)mesh;
     if (!g.cell_pending) { std::fprintf(stderr, "wcfe adapter: updateForces_Explicit(cell) without a preceding updateFA\n"); std::abort(); }
     OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_V, flat(V_t)));

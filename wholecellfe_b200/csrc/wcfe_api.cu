@@ -121,9 +121,9 @@ struct wcfe_ctx {
     DevBuf<unsigned int> b_node_epoch;    // per substrate node: epoch of the last step in which an incident triangle received an anchor
     DevBuf<int> b_items;
     int b_cap = 0;
-    // big buckets (coarse substrate): list + one-warp-per-triangle reduction, see k_bucket_reduce
+    // list of the triangles that hold anchors + their per-triangle reduction, see k_bucket_reduce
     DevBuf<unsigned int> big_count; DevBuf<int> big_list;
-    int big_cap = 0, big_T = 0x7fffffff;
+    int big_cap = 0, reduce_warp = 0;     // reduce_warp: one warp per listed triangle (coarse substrate) instead of one thread
     bool big_clean = true;                // the list counter is zero (k_subs_ring re-zeroes it at the end of every full step)
     unsigned int epoch = 0;
     double box[4] = {0, 0, 0, 0};         // padded anchor region, substrate nodes outside cannot receive force
@@ -141,8 +141,6 @@ struct wcfe_ctx {
     unsigned int step = 0;
     int debug = 0;
     int force_general = 0;                // test hook: run the general 3-D kernels even on planar states
-    int use_pipe = 0;                     // substrate: persistent software-pipelined kernel (k_subs_pipe) instead of k_subs_patch;
-                                          // measured slower on B200 (0.43 vs 0.355 ms: its 73 KB of stages leave 12 consumer warps per SM)
     int num_sms = 148;
     int subs_kernel = 2;                  // planar substrate kernel: 2 = k_subs_ring (node-centric, default), 0 = k_subs_patch (element-once)
     int profile = 0;                      // per-kernel CUDA-event timing (bench roofline leg)
@@ -153,6 +151,7 @@ struct wcfe_ctx {
     long long launches = 0;
     double last_ms = 0, t_last = 0;
     bool have_predict[2] = {false, false};
+    double drv_dt[2] = {-1.0, -1.0};      // dt of the last driver call per surface (wcfe_predict / wcfe_driver_velocities): V_hlf = V + drv_dt/2 A (UL:118, :295); < 0: the step's dt
     bool tape_busy = false;               // an async step_n may still be reading the pinned RNG tape
     // partitioned substrate: fused peer-memory halo exchange (HaloView, wcfe_patch.cuh)
     struct {
@@ -535,8 +534,7 @@ constexpr int kPatchSmemMax = 224 * 1024;
 bool use_planar(wcfe_ctx *c) {
     if (!(c->s[0].planar() && c->s[1].planar() && c->prm.thetag_dot == 0.0 && !c->force_general)) return false;
     // a mesh numbered without locality can blow the per-patch tables past shared memory: use the general kernels then
-    if (c->use_pipe && pipe_layout(c->s[1].stride, c->s[1].max_halo, c->s[1].max_elem).total > kPatchSmemMax) return false;
-    return patch_smem_bytes(7, 9, c->s[0].max_halo, c->s[0].max_elem, c->s[0].stride) <= (size_t)kPatchSmemMax &&
+    return cell_smem_bytes(c->s[0].max_halo, c->s[0].max_elem, c->s[0].stride) <= (size_t)kPatchSmemMax &&
            patch_smem_bytes(5, 10, c->s[1].max_halo, c->s[1].max_elem, c->s[1].stride) <= (size_t)kPatchSmemMax;
 }
 
@@ -554,12 +552,12 @@ int build_buckets(wcfe_ctx *c) {
     CK(c->b_node_epoch.alloc((size_t)ss.np * c->nrep));
     CK(cudaMemset(c->b_node_epoch.p, 0, sizeof(unsigned int) * ss.np * c->nrep));
     c->epoch = 0; c->big_clean = true;
-    // many anchors per substrate triangle expected -> reduce big buckets with one warp each (k_subs_ring only)
-    c->big_T = 0x7fffffff; c->big_cap = 0; c->big_count.release(); c->big_list.release();
-    int T = dens >= 3.0 ? 4 : 0;
-    if (const char *e = std::getenv("WCFE_BIG_T")) T = std::atoi(e);
-    if (T > 0 && c->subs_kernel == 2) {
-        c->big_T = T;
+    // k_subs_ring path: every triangle that holds anchors is reduced by k_bucket_reduce -- by one thread, or by one warp where many
+    // anchors per substrate triangle are expected
+    c->big_cap = 0; c->big_count.release(); c->big_list.release();
+    c->reduce_warp = dens >= 3.0 ? 1 : 0;
+    if (const char *e = std::getenv("WCFE_REDUCE_WARP")) c->reduce_warp = std::atoi(e) ? 1 : 0;
+    if (c->subs_kernel == 2) {
         c->big_cap = std::max(64, 2 * cs.nn);
         CK(c->big_count.alloc((size_t)c->nrep)); CK(c->big_list.alloc((size_t)c->big_cap * c->nrep));
         CK(cudaMemset(c->big_count.p, 0, sizeof(unsigned int) * c->nrep));
@@ -632,8 +630,11 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     Surface &cs = c->s[WCFE_CELL], &ss = c->s[WCFE_SUBS];
     SurfView cv = view(cs), sv = view(ss);
     sv.X = sv.x;
+    // El Topo may accept less than the requested step: the caller's V_hlf was formed by the LAST driver call, whose dt (curr_dt,
+    // main.cpp:224/:293/:329) then differs from the dt updateForces_Explicit receives (ori_dt, main.cpp:360-361)
+    const double dtd_c = (!fuse_predict && c->drv_dt[0] >= 0) ? c->drv_dt[0] : dt, dtd_s = (!fuse_predict && c->drv_dt[1] >= 0) ? c->drv_dt[1] : dt;
     if (which & 1) c->epoch++;            // the cell half fills the triangle buckets of this epoch, the substrate half reads them
-    BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch, nullptr, nullptr, 0, 0x7fffffff, c->b_node_epoch.p, c->halo.active ? c->cell_done.p : nullptr, c->cell_target, 0, c->d_err.p};      // the completion counter is a partitioned-run device (the increment costs the cell kernel 3 %)
+    BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch, nullptr, nullptr, 0, c->b_node_epoch.p, c->halo.active ? c->cell_done.p : nullptr, c->cell_target, 0, c->d_err.p};      // the completion counter is a partitioned-run device (the increment costs the cell kernel 3 %)
     const int gc = (cs.nn + kBlock - 1) / kBlock, gs = (ss.nn + kBlock - 1) / kBlock;
     // Pr < APrate*dt*exp(-APrate*dt) (UL:1531): the threshold is evaluated on the host with the host libm, as the reference does
     const double thr = c->prm.ap_rate * dt_real * std::exp(-c->prm.ap_rate * dt_real);
@@ -641,7 +642,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     const bool planar = use_planar(c);
     int npart = gc;
     const bool reduce = planar && c->subs_kernel == 2 && c->big_count.p != nullptr;
-    if (reduce) { bk.big_count = c->big_count.p; bk.big_list = c->big_list.p; bk.big_cap = c->big_cap; bk.big_T = c->big_T; }
+    if (reduce) { bk.big_count = c->big_count.p; bk.big_list = c->big_list.p; bk.big_cap = c->big_cap; }
     const bool batch = c->nrep > 1;
     bool joined = true;
     const bool overlap = planar && !c->debug && which == 3;
@@ -666,13 +667,13 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         ProfScope ps(c, K_CELL);
         PatchView pvc = pview(cs);
         CellStepArgs a{};
-        a.dt = dt; a.dt_real = dt_real; a.t_tot = t_tot; a.ap_threshold = thr;
+        a.dt = dt; a.dt_real = dt_real; a.t_tot = t_tot; a.ap_threshold = thr; a.dt_drv = dtd_c;
         a.ix0 = c->ibox[0]; a.ix1 = c->ibox[1]; a.iy0 = c->ibox[2]; a.iy1 = c->ibox[3];
         a.rng_mode = c->rng_mode; a.seed = c->seed; a.step = c->step; a.tape = tape_dev; a.partials = c->d_partials.p;
         a.d_flags = c->d_flags.p; a.d_loc_bond = c->d_loc_bond.p; a.d_loc_cnt = c->d_loc_cnt.p; a.d_loc_first = c->d_loc_first.p;
         a.d_ap_fire = c->d_ap_fire.p; a.err = c->d_err.p; a.debug = c->debug;
         if (c->halo.active && c->halo.step > 0) { a.halo_peer = c->halo.peers.p; a.halo_npeer = c->halo.npeer; }   // signal the previous step's halo rows
-        const size_t smem = patch_smem_bytes(7, 9, cs.max_halo, cs.max_elem, cs.stride);
+        const size_t smem = cell_smem_bytes(cs.max_halo, cs.max_elem, cs.stride);
         npart = cs.npatch;
         if (bk.cell_done) c->cell_target += (unsigned long long)cs.npatch * R;      // every CTA of the launch below adds one to cell_done
         bk.cell_target = c->cell_target;
@@ -709,9 +710,9 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         k_bond<<<gc, kBlock, 0, c->stream>>>(cv, sv, c->grid, bk, c->k, dt_real, c->ibox[0], c->ibox[1], c->ibox[2], c->ibox[3], c->d_flags.p, c->d_loc_bond.p, c->d_loc_cnt.p, c->d_loc_first.p, c->debug, c->d_err.p); }
         { ProfScope ps(c, K_CELL);
         if (c->debug)
-            k_cell_node<true><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, dview(cs));
+            k_cell_node<true><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, dview(cs), dtd_c);
         else
-            k_cell_node<false><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, DebugView{}); }
+            k_cell_node<false><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, DebugView{}, dtd_c); }
         c->launches += 2;
     }
     {
@@ -721,20 +722,29 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     if (forked) { CK(cudaEventRecord(c->ev_fork, c->stream)); CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0)); fs = c->side; }
     { ProfScope ps(c, K_FINISH, fs);
     const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few small blocks: latency-, not throughput-bound
-    if (pdl && batch) CK(launch_pdl(k_boundary_finish<false, true>, dim3(fb, R), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt));
-    else if (pdl) CK(launch_pdl(k_boundary_finish<false, false>, dim3(fb), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt));
-    else if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt);
-    else if (c->debug) k_boundary_finish<true><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt);
-    else k_boundary_finish<false><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt); }
+    if (pdl && batch) CK(launch_pdl(k_boundary_finish<false, true>, dim3(fb, R), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c));
+    else if (pdl) CK(launch_pdl(k_boundary_finish<false, false>, dim3(fb), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c));
+    else if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c);
+    else if (c->debug) k_boundary_finish<true><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt, dtd_c);
+    else k_boundary_finish<false><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c); }
     if (forked) { CK(cudaEventRecord(c->ev_join, c->side)); joined = false; }
     }
     if (reduce) {
         ProfScope pr(c, K_REDUCE);
-        const int gr = std::max(1, std::min(4 * c->num_sms, (cs.nn / 64 + kReduceWarps - 1) / kReduceWarps));
-        if (pdl && batch) CK(launch_pdl(k_bucket_reduce<true>, dim3(gr, R), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
-        else if (pdl) CK(launch_pdl(k_bucket_reduce<false>, dim3(gr), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
-        else if (batch) k_bucket_reduce<true><<<dim3(gr, R), kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
-        else k_bucket_reduce<false><<<gr, kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
+        if (c->reduce_warp) {
+            const int gr = std::max(1, std::min(4 * c->num_sms, (cs.nn / 64 + kReduceWarps - 1) / kReduceWarps));
+            if (pdl && batch) CK(launch_pdl(k_bucket_reduce<true, true>, dim3(gr, R), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
+            else if (pdl) CK(launch_pdl(k_bucket_reduce<false, true>, dim3(gr), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
+            else if (batch) k_bucket_reduce<true, true><<<dim3(gr, R), kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
+            else k_bucket_reduce<false, true><<<gr, kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
+        } else {
+            // one thread per listed triangle; about one triangle in two cell nodes is listed on a substrate finer than the cell
+            const int gr = std::max(1, std::min(8 * c->num_sms, (cs.nn + kReduceWarps * 32 - 1) / (kReduceWarps * 32)));
+            if (pdl && batch) CK(launch_pdl(k_bucket_reduce<true, false>, dim3(gr, R), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
+            else if (pdl) CK(launch_pdl(k_bucket_reduce<false, false>, dim3(gr), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
+            else if (batch) k_bucket_reduce<true, false><<<dim3(gr, R), kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
+            else k_bucket_reduce<false, false><<<gr, kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
+        }
         c->launches += 1;
     }
     c->launches += 1;
@@ -753,33 +763,25 @@ subs_half:
         if (c->halo.active) {
             // partitioned substrate: border strains go straight into the neighbours' ghost rows, ghost rows are awaited in-kernel
             HaloView hv{c->halo.node_role.p, c->halo.exp_ptr.p, c->halo.exp_ent.p, c->halo.peers.p, c->halo.flags.p, c->halo.npeer, c->halo.step, c->d_err.p};
-            if (pdl) CK(launch_pdl(k_subs_ring<false, false, true>, dim3(ss.npatch), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, hv));
-            else k_subs_ring<false, false, true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, hv);
+            if (pdl) CK(launch_pdl(k_subs_ring<false, false, true>, dim3(ss.npatch), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, hv, dtd_s));
+            else k_subs_ring<false, false, true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, hv, dtd_s);
             c->halo.step++;
         }
-        else if (pdl && batch) CK(launch_pdl(k_subs_ring<false, true>, dim3(ss.npatch, R), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo));
-        else if (pdl) CK(launch_pdl(k_subs_ring<false, false>, dim3(ss.npatch), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo));
-        else if (batch) k_subs_ring<false, true><<<dim3(ss.npatch, R), kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo);
-        else if (c->debug) k_subs_ring<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss), bt, nohalo);
-        else k_subs_ring<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo);
-    } else if (planar && c->use_pipe) {
-        // persistent, software-pipelined substrate kernel: grid = SMs x 3 resident CTAs
-        ProfScope ps(c, K_SUBS);
-        const PipeLayout L = pipe_layout(ss.stride, ss.max_halo, ss.max_elem);
-        PatchView pvs = pview(ss);
-        const int grid = std::min(ss.npatch, c->num_sms * 3);
-        if (c->debug) k_subs_pipe<true><<<grid, kPipeThreads, L.total, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
-        else k_subs_pipe<false><<<grid, kPipeThreads, L.total, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+        else if (pdl && batch) CK(launch_pdl(k_subs_ring<false, true>, dim3(ss.npatch, R), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo, dtd_s));
+        else if (pdl) CK(launch_pdl(k_subs_ring<false, false>, dim3(ss.npatch), dim3(kPatch), smem, c->stream, sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo, dtd_s));
+        else if (batch) k_subs_ring<false, true><<<dim3(ss.npatch, R), kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo, dtd_s);
+        else if (c->debug) k_subs_ring<true><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss), bt, nohalo, dtd_s);
+        else k_subs_ring<false><<<ss.npatch, kPatch, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, bt, nohalo, dtd_s);
     } else if (planar) {
         ProfScope ps(c, K_SUBS);
         const size_t smem = patch_smem_bytes(5, 10, ss.max_halo, ss.max_elem, ss.stride);
         PatchView pvs = pview(ss);
-        if (c->debug) k_subs_patch<true><<<ss.npatch, kThreads, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
-        else k_subs_patch<false><<<ss.npatch, kThreads, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+        if (c->debug) k_subs_patch<true><<<ss.npatch, kThreads, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss), dtd_s);
+        else k_subs_patch<false><<<ss.npatch, kThreads, smem, c->stream>>>(sv, pvs, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, dtd_s);
     } else {
         ProfScope ps(c, K_SUBS);
-        if (c->debug) k_subs_node<true><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss));
-        else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{});
+        if (c->debug) k_subs_node<true><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], dview(ss), dtd_s);
+        else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, dtd_s);
     }
     c->launches += 1;
     if (reduce) c->big_clean = true;       // k_subs_ring zeroed the counter
@@ -948,11 +950,10 @@ static int create_impl(wcfe_ctx **out, int device, const wcfe_params *p, int rep
     {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
-        if (const char *e = std::getenv("WCFE_SUBS_PIPE")) { c->use_pipe = std::atoi(e); if (c->use_pipe) c->subs_kernel = 1; }
         if (const char *e = std::getenv("WCFE_SUBS_KERNEL")) c->subs_kernel = std::atoi(e);
         if (const char *e = std::getenv("WCFE_PDL")) c->use_pdl = std::atoi(e);
         if (const char *e = std::getenv("WCFE_CELL_COUNTER")) c->use_cell_counter = std::atoi(e);
-        const void *pk[] = {(const void *)k_subs_ring<false>, (const void *)k_subs_ring<true>, (const void *)k_subs_pipe<false>, (const void *)k_subs_pipe<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
+        const void *pk[] = {(const void *)k_subs_ring<false>, (const void *)k_subs_ring<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
                             (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>,
                             (const void *)k_cell_patch<true, false, true>, (const void *)k_subs_ring<false, true>, (const void *)k_subs_ring<false, false, true>};
         for (const void *f : pk) {
@@ -1281,7 +1282,7 @@ int wcfe_predict(wcfe_ctx *c, int surface, double dt, double t_curr, double *xyz
         CK(cudaGetLastError());
     }
     // substrate: x_new = x + 0*dt*V_hlf (main.cpp:299) == x; V_hlf itself is formed inside the update kernel
-    c->have_predict[surface] = true;
+    c->have_predict[surface] = true; c->drv_dt[surface] = dt;
     if (xyz_new_out) return get_field(c, s.x.p, xyz_new_out, s.nn, s.np, 3);
     return WCFE_OK;
 }
@@ -1313,8 +1314,8 @@ static int update_impl(wcfe_ctx *c, double dt_req, double dt_real, double t_curr
         if ((rc = stage_tape(c, 1))) return rc;
     }
     if ((rc = launch_update(c, dt_req, dt_real, t_curr, c->d_tape.p, false, which))) return rc;
-    if (which & 1) c->have_predict[0] = false;
-    if (which & 2) { c->have_predict[1] = false; c->t_last = t_curr + dt_real; }
+    if (which & 1) { c->have_predict[0] = false; c->drv_dt[0] = -1.0; }
+    if (which & 2) { c->have_predict[1] = false; c->drv_dt[1] = -1.0; c->t_last = t_curr + dt_real; }
     return check_device_errors(c);
 }
 int wcfe_update(wcfe_ctx *c, double dt_req, double dt_real, double t_curr) { return update_impl(c, dt_req, dt_real, t_curr, 3); }
@@ -1338,6 +1339,7 @@ int wcfe_driver_velocities(wcfe_ctx *c, int surface, int nn, const double *X, co
     CK(cudaMemcpyAsync(h + 3 * bytes, d + 9 * (size_t)nn, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     memcpy(Vh_out, h + 3 * bytes, bytes);
+    c->drv_dt[surface] = dt;      // the update that follows forms the same V_hlf on the device
     return WCFE_OK;
 }
 

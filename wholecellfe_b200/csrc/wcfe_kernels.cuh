@@ -42,11 +42,12 @@ struct BucketView {          // triangle -> anchored cell nodes, rebuilt every s
     int *items;                 // [ne_subs*cap]
     int cap;
     unsigned int epoch;
-    // coarse substrates (many anchors per triangle): buckets that grow beyond big_T are listed here by the inserting thread and
-    // reduced by one warp each (k_bucket_reduce) instead of by every node of the triangle; big_T = INT_MAX switches it off
+    // planar path: every triangle that receives its first anchor of the step is listed here by the inserting thread;
+    // k_bucket_reduce turns each listed bucket into the six nodal sums of calculateForce_FA_subs (nullptr: no list, the
+    // substrate kernel walks the buckets itself -- k_subs_patch, k_subs_node)
     unsigned int *big_count;        // entries of big_list; zeroed on the stream before every cell kernel
     int *big_list;                  // [big_cap] triangle ids
-    int big_cap, big_T;
+    int big_cap;
     // planar path: epoch stamp per SUBSTRATE NODE, written by the cell kernel on the three vertices of every triangle it drops an
     // anchor into.  A substrate node under the cell whose stamp is stale has nothing to gather and skips the bucket walk (two
     // thirds of the nodes inside the padded bounding box of a round cell).
@@ -287,7 +288,7 @@ __device__ __forceinline__ void block_reduce4(double v[4], double *sh /*[4*32]*/
 template <bool DBG>
 __global__ void __launch_bounds__(kBlock) k_cell_node(SurfView s, BoundaryView b, Consts k, double dt, double dt_real, double t_tot,
                                                       int rng_mode, const unsigned int *__restrict__ tape, unsigned int seed, unsigned int step,
-                                                      double ap_threshold, double *__restrict__ partials, int *__restrict__ d_ap_fire, DebugView dbg) {
+                                                      double ap_threshold, double *__restrict__ partials, int *__restrict__ d_ap_fire, DebugView dbg, double dt_drv) {
     __shared__ double sh[4 * 32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[4] = {0.0, 0.0, 0.0, 0.0};
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kBlock) k_cell_node(SurfView s, BoundaryView b
         double A[3] = {s.A[i], s.A[np + i], s.A[2 * np + i]};
         double Vh[3];
 #pragma unroll
-        for (int c = 0; c < 3; c++) Vh[c] = V[c] + (dt / 2.0) * A[c];                     // UL:118
+        for (int c = 0; c < 3; c++) Vh[c] = V[c] + (dt_drv / 2.0) * A[c];                     // UL:118 (dt_drv: what the driver was called with)
         Vh[2] = 0.0;
         // integrin force on the cell node (UL:1258-1261; kMD UL:1246-1269)
         const double u[3] = {s.fa[i], s.fa[np + i], s.fa[2 * np + i]};
@@ -372,7 +373,7 @@ template <bool DBG, bool BATCH = false>
 __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k_, int npart, const double *__restrict__ partials,
                                                           const double *__restrict__ V_in, const double *__restrict__ A_in,
                                                           double dt, double dt_real, double *__restrict__ diag, int *__restrict__ err, DebugView dbg,
-                                                          BatchView bt) {
+                                                          BatchView bt, double dt_drv) {
     __shared__ double sh[4 * 32];
     __shared__ double tot[4];
     pdl_launch_dependents();      // the substrate kernel may start its cell-independent part now
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
             const double F_area = -k.k_area * (area_tot - k.area_0) / 2 * tl * o[8 + c];   // UL:1757
             const double f = (o[c] + F_area) - o[3 + c];
             double V = V_in[c * np + i], A = A_in[c * np + i];       // start-of-step values (the planar path double-buffers V, A)
-            double Vh = V + (dt / 2.0) * A;
+            double Vh = V + (dt_drv / 2.0) * A;
             if (c == 2) Vh = 0.0;
             node_update(f, mm, k.damp, k.rho, dt, dt_real, Vh, V, A);
             s.V[c * np + i] = V; s.A[c * np + i] = A;
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
 //      calculateForce_FA_subs (UL:1297-1454) as a gather over the per-triangle buckets filled by k_bond -----------------
 template <bool DBG>
 __global__ void __launch_bounds__(kBlock) k_subs_node(SurfView s, SurfView c, BucketView bk, Consts k, double dt, double dt_real, double t_tot,
-                                                      double bx0, double bx1, double by0, double by1, DebugView dbg) {
+                                                      double bx0, double bx1, double by0, double by1, DebugView dbg, double dt_drv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.nn) return;
     const double theta_g = 1.0 + k.thetag_dot * dt_real;
@@ -466,7 +467,7 @@ __global__ void __launch_bounds__(kBlock) k_subs_node(SurfView s, SurfView c, Bu
     double A[3] = {s.A[i], s.A[np + i], s.A[2 * np + i]};
     double Vh[3];
 #pragma unroll
-    for (int d = 0; d < 3; d++) Vh[d] = V[d] + (dt / 2.0) * A[d];
+    for (int d = 0; d < 3; d++) Vh[d] = V[d] + (dt_drv / 2.0) * A[d];
     Vh[2] = 0.0;
     // pinned edges, UL:298-341 with Vbiax == 0: all three time windows zero the component; nothing fires at t == t_i, t_f
     if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {

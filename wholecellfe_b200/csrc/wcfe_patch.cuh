@@ -32,9 +32,6 @@ constexpr int kPatch = WCFE_PATCH;     // owned nodes per patch
 constexpr int kThreads = WCFE_THREADS; // threads per CTA: a patch has ~2.35 elements per owned node, so 1.25 x kPatch threads
                                        // finish the element phase in two full rounds instead of two and a tail
 constexpr int kMinBlk = WCFE_MINBLK;   // resident CTAs per SM the register allocation is tuned for
-#ifndef WCFE_CELL_PREFETCH
-#define WCFE_CELL_PREFETCH 1
-#endif
 #ifndef WCFE_RING_CHUNK
 #define WCFE_RING_CHUNK 3
 #endif
@@ -74,17 +71,6 @@ __host__ __device__ inline size_t patch_smem_bytes(int n_node_arrays, int n_rec,
     return 16 + (size_t)stride + sizeof(double) * n_node_arrays * NL + recs + 64;
 }
 
-// 1/x for a normal, well-scaled x (the determinant of I - 2e, close to 1): MUFU.RCP64H seed plus two Newton steps, four DFMAs,
-// error about one ulp -- the compiler's IEEE division costs twice as many FP64 issue slots plus a range-check branch
-__device__ __forceinline__ double rcp_newton(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
-}
-
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ----------------------------------------------------------------------
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count) {
@@ -116,7 +102,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
 // (force on local node 0, 1, 2; (e_s.xx,e_s.yy); (e_s.xy, A0)) so that gathers are 128-bit and branch-free.
 template <bool DBG>
 __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
-                                                                  double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg) {
+                                                                  double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg, double dt_drv) {
     extern __shared__ __align__(128) unsigned char smraw[];
     const int NL = kPatch + pv.max_halo, EM = pv.max_elem;
     unsigned long long *bar = (unsigned long long *)smraw;
@@ -242,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
             }
         }
     }
-    double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt / 2.0, A1v));   // UL:295
+    double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt_drv / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt_drv / 2.0, A1v));   // UL:295, with the dt the driver was called with
     if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {            // UL:298-341, Vbiax == 0
         if (Xi0 < -k.pin_limit || Xi0 > k.pin_limit) Vh0 = 0.0;
         if (Xi1 > k.pin_limit || Xi1 < -k.pin_limit) Vh1 = 0.0;
@@ -350,7 +336,7 @@ __device__ __noinline__ void halo_wait(const unsigned long long *flags, const Ha
 
 template <bool DBG, bool BATCH = false, bool HALO = false>
 __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k_, double dt, double dt_real,
-                                                         double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg, BatchView bt, HaloView hv) {
+                                                         double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg, BatchView bt, HaloView hv, double dt_drv) {
     extern __shared__ __align__(128) unsigned char smraw[];
     pdl_launch_dependents();      // the next step's cell kernel may stage its patches behind this kernel's last wave
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
@@ -502,54 +488,29 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
         } else pdl_wait();
         stamp = bk.node_epoch[i];
     }
-    if (stamp == bk.epoch) {      // an incident triangle received an anchor in this step (two thirds of the nodes in the box skip the walk)
-        // element id -> bucket head -> items -> anchor record are dependent global loads; the first two are fetched for four
-        // incident triangles at a time, so a valence-6 node pays 2 x 2 instead of 6 x 2 of those round trips
+    if (stamp == bk.epoch) {      // an incident triangle received an anchor in this step (two thirds of the nodes in the box skip this)
+        // calculateForce_FA_subs (UL:1297-1454) as a gather: k_bucket_reduce has formed, for every triangle that holds anchors, the
+        // six sums  sum_anchors H (A_j / A_tri)  (anchors in ascending cell-node order) and parked them in the triangle's own item
+        // storage; this node adds the one of its slot, triangles in fan order.  element id -> bucket head -> sums are dependent
+        // global loads: fetched for four incident triangles at a time.
         const int gb = s.ring_ptr[i];
         for (int r0 = 0; r0 < nring; r0 += 4) {
-        int code4[4]; unsigned long long h4[4];
+            int code4[4]; unsigned long long h4[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) code4[u] = r0 + u < nring ? pv.ring_cyc[gb + r0 + u] : -1;
+            for (int u = 0; u < 4; u++) code4[u] = r0 + u < nring ? pv.ring_cyc[gb + r0 + u] : -1;
 #pragma unroll
-        for (int u = 0; u < 4; u++) h4[u] = code4[u] >= 0 ? bk.head[code4[u] >> 2] : 0ull;
+            for (int u = 0; u < 4; u++) h4[u] = code4[u] >= 0 ? bk.head[code4[u] >> 2] : 0ull;
+            double2 f4[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int code = code4[u], r = r0 + u;
-            const unsigned long long h = h4[u];
-            if (code < 0 || (unsigned int)(h >> 32) != bk.epoch) continue;
-            const int e = code >> 2, slot = code & 3;
-            int cnt = (int)(unsigned int)h;
-            if (cnt > bk.cap) cnt = bk.cap;
-            // the element's vertices in their ORIGINAL order (the sub-areas of the predicate are order dependent)
-            const ushort2 jk = rjk[r * kPatch + tid];
-            const int l1 = slot == 0 ? tid : (slot == 1 ? (int)jk.y : (int)jk.x);        // lid[(3 - slot) % 3] with lid = {tid, j, k}
-            const int l2 = slot == 0 ? (int)jk.x : (slot == 1 ? tid : (int)jk.y);        // lid[(4 - slot) % 3]
-            const int l3 = slot == 0 ? (int)jk.y : (slot == 1 ? (int)jk.x : tid);        // lid[(5 - slot) % 3]
-            const double2 p1 = sxy[l1], p2 = sxy[l2], p3 = sxy[l3];
-            if (cnt > bk.big_T) {            // reduced by k_bucket_reduce: six sums parked in the bucket's own item storage
-                const double2 f = reinterpret_cast<const double2 *>(bk.items + (size_t)e * bk.cap)[slot];
-                Fx += f.x; Fy += f.y;
-                continue;
+            for (int u = 0; u < 4; u++) {
+                const bool on = code4[u] >= 0 && (unsigned int)(h4[u] >> 32) == bk.epoch;
+                f4[u] = on ? reinterpret_cast<const double2 *>(bk.items + (size_t)(code4[u] >> 2) * bk.cap)[code4[u] & 3] : make_double2(0.0, 0.0);
             }
-            const double2 *anc2 = reinterpret_cast<const double2 *>(c.anc);
-            auto add_anchor = [&](const double2 ap, const double2 ah) {
-                double Ar[3], At;                                                        // UL:1303; planar form, bit-identical
-                point_in_triangle_2d(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, ap.x, ap.y, Ar, At);
-                const double w = (slot == 0 ? Ar[0] : (slot == 1 ? Ar[1] : Ar[2])) / At;
-                Fx += ah.x * w;                                                          // UL:1414-1422
-                Fy += ah.y * w;
-            };
-            int prev = -1;
-            for (int m = 0; m < cnt; m++) {
-                int ni = 0x7fffffff;
-                for (int q = 0; q < cnt; q++) { const int v = bk.items[(size_t)e * bk.cap + q]; if (v > prev && v < ni) ni = v; }
-                prev = ni;
-                add_anchor(anc2[2 * (size_t)ni], anc2[2 * (size_t)ni + 1]);
-            }
-        }
+#pragma unroll
+            for (int u = 0; u < 4; u++) { Fx += f4[u].x; Fy += f4[u].y; }      // (+0 for the triangles without anchors)
         }
     }
-    double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt / 2.0, A1v));   // UL:295
+    double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt_drv / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt_drv / 2.0, A1v));   // UL:295, with the dt the driver was called with
     if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {            // UL:298-341, Vbiax == 0
         if (Xi0 < -k.pin_limit || Xi0 > k.pin_limit) Vh0 = 0.0;
         if (Xi1 > k.pin_limit || Xi1 < -k.pin_limit) Vh1 = 0.0;
@@ -577,23 +538,52 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     }
 }
 
-// ---- big buckets: one warp per listed triangle ------------------------------------------------------------------------------------
+// ---- integrin force on the substrate, per triangle ---------------------------------------------------------------------------------
 // calculateForce_FA_subs (UL:1297-1454) adds, for every anchor inside a substrate triangle, H * A_j/A_tri to the triangle's three
-// nodes, anchors in ascending cell-node order.  When a triangle holds many anchors (coarse substrate under a fine cell: 88 in one
-// triangle of the example meshes) the per-node gather of k_subs_ring would sort and evaluate the same bucket three times, serially.
-// Here the lanes of a warp rank the items (all pairs, 1/32 each), evaluate them in parallel, park the terms in shared memory by
-// rank, and six lanes form the six sums in the reference's order.  The result overwrites the head of the bucket's own item
-// storage (6 doubles = 12 ints <= cap), where k_subs_ring picks it up.
+// nodes, anchors in ascending cell-node order.  The cell kernel lists every triangle that received its first anchor of the step;
+// here each listed triangle evaluates the containment sub-areas of its anchors ONCE (a per-node gather would do it three times,
+// after three dependent lookups) and leaves the six sums in the head of the bucket's own item storage (6 doubles = 12 ints <=
+// cap), where k_subs_ring picks up the one of its slot.
+//   WARP = false  one thread per triangle (fine substrates: a couple of anchors per triangle, ~ne_cell/2 triangles listed)
+//   WARP = true   one warp per triangle (coarse substrate under a fine cell: 88 anchors in one triangle of the example meshes):
+//                 the lanes rank the items (all pairs, 1/32 each), evaluate them in parallel, park the terms in shared memory
+//                 by rank, and six lanes form the six sums in the reference's order.
 constexpr int kReduceWarps = 8, kReduceWindow = 128;
-template <bool BATCH>
+template <bool BATCH, bool WARP>
 __global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s, SurfView c, BucketView bk, BatchView bt) {
-    __shared__ double term[kReduceWarps][kReduceWindow][6];
+    __shared__ double term[WARP ? kReduceWarps : 1][WARP ? kReduceWindow : 1][6];
     pdl_launch_dependents();
     pdl_wait();                   // the list and the buckets are the cell kernel's output
     if (BATCH) { const size_t r = blockIdx.y; batch_shift(s, r); batch_shift(c, r); batch_shift(bk, bt, r); }
-    int nbig = (int)min(*bk.big_count, (unsigned int)bk.big_cap);
+    const int nbig = (int)min(*bk.big_count, (unsigned int)bk.big_cap);
+    const double2 *anc2 = reinterpret_cast<const double2 *>(c.anc);
+    if (!WARP) {
+        for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbig; b += gridDim.x * blockDim.x) {
+            const int e = bk.big_list[b];
+            int cnt = (int)(unsigned int)bk.head[e];
+            if (cnt > bk.cap) cnt = bk.cap;
+            int *items = bk.items + (size_t)e * bk.cap;
+            const int i0 = s.tri[e], i1 = s.tri[s.nep + e], i2 = s.tri[2 * s.nep + e];
+            const double n1x = s.x[i0], n1y = s.x[s.np + i0], n2x = s.x[i1], n2y = s.x[s.np + i1], n3x = s.x[i2], n3y = s.x[s.np + i2];
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+            int prev = -1;
+            for (int m = 0; m < cnt; m++) {          // ascending cell-node order: deterministic whatever the insertion order was
+                int ni = 0x7fffffff;
+                for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v > prev && v < ni) ni = v; }
+                prev = ni;
+                const double2 ap = anc2[2 * (size_t)ni], ah = anc2[2 * (size_t)ni + 1];
+                double Ar[3], At;                                                        // UL:1303-1340; planar form, bit-identical
+                point_in_triangle_2d(n1x, n1y, n2x, n2y, n3x, n3y, ap.x, ap.y, Ar, At);
+                const double w0 = Ar[0] / At, w1 = Ar[1] / At, w2 = Ar[2] / At;
+                a0 += ah.x * w0; a1 += ah.y * w0; a2 += ah.x * w1; a3 += ah.y * w1; a4 += ah.x * w2; a5 += ah.y * w2;   // UL:1414-1422
+            }
+            double2 *o = reinterpret_cast<double2 *>(items);      // this thread alone reads and writes the bucket
+            o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3); o[2] = make_double2(a4, a5);
+        }
+        return;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double (*tw)[6] = term[warp];
+    double (*tw)[6] = term[WARP ? warp : 0];
     for (int b = blockIdx.x * kReduceWarps + warp; b < nbig; b += gridDim.x * kReduceWarps) {
         const int e = bk.big_list[b];
         int cnt = (int)(unsigned int)bk.head[e];
@@ -608,7 +598,7 @@ __global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s,
                 int rank = 0;
                 for (int q = 0; q < cnt; q++) rank += items[q] < v;      // node ids inside a bucket are distinct
                 if (rank < w0 || rank >= w0 + kReduceWindow) continue;
-                const double2 ap = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)v], ah = reinterpret_cast<const double2 *>(c.anc)[2 * (size_t)v + 1];
+                const double2 ap = anc2[2 * (size_t)v], ah = anc2[2 * (size_t)v + 1];
                 double Ar[3], At;
                 point_in_triangle_2d(n1[0], n1[1], n2[0], n2[1], n3[0], n3[1], ap.x, ap.y, Ar, At);     // planar form, bit-identical
                 double *t6 = tw[rank - w0];
@@ -627,181 +617,6 @@ __global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s,
     }
 }
 
-// ---- substrate, software-pipelined persistent version ---------------------------------------------------------------------------
-// Same arithmetic as k_subs_patch, different choreography: a persistent CTA (grid = SMs x resident CTAs) walks over patches with
-// TWO shared-memory stages.  Warp 4 is the producer: for patch k+1 it issues the TMA bulk copies (descriptor + the owned nodes'
-// x, e, V, A), waits for them, packs the node table and gathers the halo nodes -- while warps 0-3 (consumers, one thread per
-// owned node) run the element and node phases of patch k entirely out of shared memory.  full/empty mbarriers hand the stages
-// back and forth; the consumers never wait on global memory except for their coalesced stores.
-constexpr int kPipeConsumers = kPatch;                  // 4 warps at kPatch = 128
-constexpr int kPipeThreads = kPatch + 32;
-struct PipeLayout { int blob, soa, table, stage, rec, total; };
-__host__ __device__ inline PipeLayout pipe_layout(int stride, int max_halo, int max_elem) {
-    PipeLayout L;
-    L.blob = 0;
-    L.soa = (stride + 127) / 128 * 128;                                  // [9][kPatch] doubles: x0 x1 e0 e1 e3 V0 V1 A0 A1
-    L.table = L.soa + 9 * kPatch * 8;                                    // packed node table: (x,y) (e0,e1) e3  -> 40 B per node
-    L.stage = (L.table + 40 * (kPatch + max_halo) + 127) / 128 * 128;
-    L.rec = 128 + 2 * L.stage;                                           // after the barriers and the two stages
-    L.total = L.rec + 64 * max_elem + 128;
-    return L;
-}
-
-template <bool DBG>
-__global__ void __launch_bounds__(kPipeThreads, 3) k_subs_pipe(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k, double dt, double dt_real,
-                                                               double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg) {
-    extern __shared__ __align__(128) unsigned char smraw[];
-    const PipeLayout L = pipe_layout(pv.stride, pv.max_halo, pv.max_elem);
-    unsigned long long *bars = (unsigned long long *)smraw;              // [0..1] tma, [2..3] full, [4..5] empty
-    unsigned char *stage0 = smraw + 128;
-    double2 *rec = (double2 *)(smraw + L.rec);                           // [4][EM]
-    const int NLt = kPatch + pv.max_halo, EM = pv.max_elem;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int np = s.np;
-    if (tid == 0) {
-        for (int q = 0; q < 2; q++) { mbar_init(bars + q, 1); mbar_init(bars + 2 + q, 1); mbar_init(bars + 4 + q, kPipeConsumers); }
-    }
-    __syncthreads();
-    const int first = blockIdx.x, step = gridDim.x;
-    if (warp == kPipeConsumers / 32) {
-        // ================= producer warp =================
-        int it = 0;
-        for (int p = first; p < pv.npatch; p += step, it++) {
-            const int sidx = it & 1; const unsigned int ph = (it >> 1) & 1;
-            unsigned char *st = stage0 + (size_t)sidx * L.stage;
-            double *soa = (double *)(st + L.soa);
-            double2 *txy = (double2 *)(st + L.table); double2 *te01 = txy + NLt; double *te3 = (double *)(te01 + NLt);
-            mbar_wait(bars + 4 + sidx, ph ^ 1);                          // stage free (passes immediately the first time round)
-            const int n0 = p * kPatch;
-            const int ncopy = min(kPatch, s.np - n0);
-            if (lane == 0) {
-                const unsigned int nb = (unsigned int)ncopy * 8u;
-                mbar_expect_tx(bars + sidx, (unsigned int)pv.stride + 9u * nb);
-                bulk_g2s(st + L.blob, pv.blob + (size_t)p * pv.stride, (unsigned int)pv.stride, bars + sidx);
-                bulk_g2s(soa, s.x + n0, nb, bars + sidx); bulk_g2s(soa + kPatch, s.x + np + n0, nb, bars + sidx);
-                bulk_g2s(soa + 2 * kPatch, s.ea_in + n0, nb, bars + sidx); bulk_g2s(soa + 3 * kPatch, s.ea_in + np + n0, nb, bars + sidx);
-                bulk_g2s(soa + 4 * kPatch, s.ea_in + 3 * (size_t)np + n0, nb, bars + sidx);
-                bulk_g2s(soa + 5 * kPatch, s.V + n0, nb, bars + sidx); bulk_g2s(soa + 6 * kPatch, s.V + np + n0, nb, bars + sidx);
-                bulk_g2s(soa + 7 * kPatch, s.A + n0, nb, bars + sidx); bulk_g2s(soa + 8 * kPatch, s.A + np + n0, nb, bars + sidx);
-            }
-            mbar_wait(bars + sidx, ph);
-            const int nh = ((const int *)(st + L.blob))[0];
-            const int *halo_ids = (const int *)(st + L.blob + pv.off_halo);
-            for (int l = lane; l < nh; l += 32) {                        // halo gather first: its loads overlap the repack below
-                const int g = halo_ids[l];
-                txy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
-                te01[kPatch + l] = make_double2(s.ea_in[g], s.ea_in[np + g]);
-                te3[kPatch + l] = s.ea_in[3 * (size_t)np + g];
-            }
-            for (int l = lane; l < kPatch; l += 32) {
-                txy[l] = make_double2(soa[l], soa[kPatch + l]); te01[l] = make_double2(soa[2 * kPatch + l], soa[3 * kPatch + l]); te3[l] = soa[4 * kPatch + l];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 2 + sidx);                 // stage full
-        }
-        return;
-    }
-    // ================= consumer warps =================
-    int it = 0;
-    for (int p = first; p < pv.npatch; p += step, it++) {
-        const int sidx = it & 1; const unsigned int ph = (it >> 1) & 1;
-        unsigned char *st = stage0 + (size_t)sidx * L.stage;
-        const double *soa = (const double *)(st + L.soa);
-        const double2 *txy = (const double2 *)(st + L.table); const double2 *te01 = txy + NLt; const double *te3 = (const double *)(te01 + NLt);
-        const int n0 = p * kPatch;
-        const int nown = min(kPatch, s.nn - n0);
-        const int i = n0 + tid;
-        const bool own = tid < nown;
-        mbar_wait(bars + 2 + sidx, ph);
-        const int nel = ((const int *)(st + L.blob))[1];
-        const unsigned short *elem_lv = (const unsigned short *)(st + L.blob + pv.off_lv);
-        const unsigned short *rptr = (const unsigned short *)(st + L.blob + pv.off_rptr);
-        const unsigned short *ring16 = (const unsigned short *)(st + L.blob + pv.off_ring);
-        // ---- elements
-        for (int el = tid; el < nel; el += kPipeConsumers) {
-            const unsigned short *lv = elem_lv + 3 * el;
-            const int a = lv[0], b = lv[1], d = lv[2];
-            const double2 pa = txy[a], pb = txy[b], pd = txy[d], ea = te01[a], eb = te01[b], ed = te01[d];
-            const double X[3][2] = {{pa.x, pa.y}, {pb.x, pb.y}, {pd.x, pd.y}};
-            const double e3[3] = {1.0 / 3.0 * ea.x + 1.0 / 3.0 * eb.x + 1.0 / 3.0 * ed.x, 1.0 / 3.0 * ea.y + 1.0 / 3.0 * eb.y + 1.0 / 3.0 * ed.y,
-                                  1.0 / 3.0 * te3[a] + 1.0 / 3.0 * te3[b] + 1.0 / 3.0 * te3[d]};      // UL:1055
-            ElemOutFrozen o;
-            elem_eval_frozen(X, e3, k.mu_subs, k.thick, o);
-            rec[el] = make_double2(o.r1[0], o.r1[1]);
-            rec[EM + el] = make_double2(o.r2[0], o.r2[1]);
-            rec[2 * EM + el] = make_double2(e3[0], e3[1]);
-            rec[3 * EM + el] = make_double2(e3[2], o.A0);
-        }
-        named_bar_sync(1, kPipeConsumers);
-        // ---- nodes
-        if (own) {
-            const double2 myxy = txy[tid], mye01 = te01[tid];
-            const double ea0 = mye01.x, ea1 = mye01.y, ea3 = te3[tid];
-            double V0 = soa[5 * kPatch + tid], V1 = soa[6 * kPatch + tid], A0v = soa[7 * kPatch + tid], A1v = soa[8 * kPatch + tid];
-            double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
-            const int rb = rptr[tid], re = rptr[tid + 1];
-            for (int r = rb; r < re; r++) {
-                const int code = ring16[r];
-                const int el = code >> 2, slot = code & 3;
-                const double2 f1 = rec[el], f2 = rec[EM + el], es = rec[2 * EM + el], ez = rec[3 * EM + el];
-                rx += slot == 0 ? -(f1.x + f2.x) : (slot == 1 ? f1.x : f2.x);
-                ry += slot == 0 ? -(f1.y + f2.y) : (slot == 1 ? f1.y : f2.y);
-                const double w = (1. / 3.) * ez.y * k.thick;                 // UL:1172 == the weight of UL:1170
-                q0 += (es.x - ea0) * w; q1 += (es.y - ea1) * w; q3 += (ez.x - ea3) * w;
-                mm += w;
-            }
-            const double Xi0 = myxy.x, Xi1 = myxy.y;
-            double Fx = 0.0, Fy = 0.0;
-            if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
-                const int e0 = pv.elem_ptr[p];
-                for (int r = rb; r < re; r++) {
-                    const int code = ring16[r];
-                    const int el = code >> 2, slot = code & 3;
-                    const int e = pv.elem_gid[e0 + el];
-                    const unsigned long long h = bk.head[e];
-                    if ((unsigned int)(h >> 32) != bk.epoch) continue;
-                    int cnt = (int)(unsigned int)h;
-                    if (cnt > bk.cap) cnt = bk.cap;
-                    const unsigned short *lv = elem_lv + 3 * el;
-                    const double2 p1 = txy[lv[0]], p2 = txy[lv[1]], p3 = txy[lv[2]];
-                    const double n1[3] = {p1.x, p1.y, 0.0}, n2[3] = {p2.x, p2.y, 0.0}, n3[3] = {p3.x, p3.y, 0.0};
-                    int prev = -1;
-                    for (int m = 0; m < cnt; m++) {
-                        int ni = 0x7fffffff;
-                        for (int q = 0; q < cnt; q++) { const int v = bk.items[(size_t)e * bk.cap + q]; if (v > prev && v < ni) ni = v; }
-                        prev = ni;
-                        const double u[3] = {c.fa[ni], c.fa[c.np + ni], 0.0};
-                        const double pt[3] = {c.x[ni] - u[0], c.x[c.np + ni] - u[1], 0.0};     // UL:1303
-                        double Ar[3], At;
-                        point_in_triangle(n1, n2, n3, pt, Ar, At);
-                        double fi[3];
-                        integrin_force(k, u, fi);
-                        const double w = Ar[slot] / At, cC = c.cC[ni], As = c.asum[ni];
-                        Fx += cC * fi[0] * w * As * k.rho_i_max;                                 // UL:1414-1422
-                        Fy += cC * fi[1] * w * As * k.rho_i_max;
-                    }
-                }
-            }
-            double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt / 2.0, A1v));   // UL:295
-            if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {            // UL:298-341, Vbiax == 0
-                if (Xi0 < -k.pin_limit || Xi0 > k.pin_limit) Vh0 = 0.0;
-                if (Xi1 > k.pin_limit || Xi1 < -k.pin_limit) Vh1 = 0.0;
-            }
-            const double imm = 1.0 / mm;
-            node_update_r(Fx - rx, mm, imm, k.damp, k.rho, dt, dt_real, Vh0, V0, A0v);            // UL:471-503
-            node_update_r(Fy - ry, mm, imm, k.damp, k.rho, dt, dt_real, Vh1, V1, A1v);
-            s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
-            s.ea_out[i] = ea0 + q0 * imm; s.ea_out[np + i] = ea1 + q1 * imm; s.ea_out[3 * np + i] = ea3 + q3 * imm;
-            if (DBG) {
-                dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
-                dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
-            }
-        }
-        mbar_arrive(bars + 4 + sidx);                                    // this thread is done with the stage
-        named_bar_sync(1, kPipeConsumers);                               // records may be overwritten by the next patch
-    }
-}
-
 // ---- cell: the whole cell side of one UL step in ONE kernel ---------------------------------------------------------
 //   PREDICT: driverVelocities_Explicit + inline predictor (UL:103-124, main.cpp:224-242) for owned AND halo nodes, read
 //            from the current position buffer and written to the other one (ping-pong: the old buffer becomes X_t).
@@ -812,6 +627,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_subs_pipe(SurfView s, Patch
 // Boundary vertices wait for the total area exactly as in k_cell_node (finished by k_boundary_finish).
 struct CellStepArgs {
     double dt, dt_real, t_tot, ap_threshold;
+    double dt_drv;                  // the dt driverVelocities_Explicit formed V_hlf with (main.cpp:224, :329): differs from dt when El Topo shortened a step
     double ix0, ix1, iy0, iy1;
     int rng_mode; unsigned int seed, step;
     const unsigned int *tape;
@@ -822,13 +638,29 @@ struct CellStepArgs {
     int halo_npeer;
 };
 
+// Shared memory: the seven node arrays in SoA (TMA destinations), element records as array-of-structs, kRec doubles per
+// element at a compile-time stride (one address computation per one-ring entry, immediate offsets for the nine loads).
+constexpr int kRec = 9;           // r1x r1y r2x r2y e_s.xx e_s.yy e_s.xy A0 a_cur
+__host__ __device__ inline size_t cell_smem_bytes(int max_halo, int max_elem, int stride) {
+    const size_t NL = (size_t)kPatch + max_halo;
+    return 16 + (size_t)stride + sizeof(double) * 7 * NL + sizeof(double) * kRec * (size_t)max_elem + 64;
+}
+// append cell node `node` to the bucket of substrate triangle t: one fire-and-forget RED.MAX brings the head to the current epoch
+// (heads are (epoch << 32 | count) and never reset; epochs only grow), one ATOM.ADD takes a slot.  Same-address atomics of one
+// thread are performed in program order, so the value returned carries the current epoch.  No load, no CAS loop: ONE round trip,
+// whose result (the slot) the caller may leave unconsumed for as long as it likes.
+__device__ __forceinline__ unsigned int bucket_take_slot(const BucketView &bk, int t) {
+    atomicMax(bk.head + t, (unsigned long long)bk.epoch << 32);
+    return (unsigned int)atomicAdd(bk.head + t, 1ull);
+}
+
 template <bool PREDICT, bool DBG, bool BATCH = false>
 __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, PatchView pv, SurfView sub, GridView g, BucketView bk, BoundaryView b, Consts k_,
                                                        CellStepArgs a, const double *__restrict__ x_in, double *__restrict__ x_out,
                                                        double *__restrict__ V_out, double *__restrict__ A_out, DebugView dbg, BatchView bt) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    __shared__ double shred[4 * 32];
-    __shared__ int s_big[2 * kThreads];           // big-bucket appends of this CTA, published with one global atomic
+    __shared__ double shred[3 * 8];               // per-warp partial sums of (area, area x, area y)
+    __shared__ int s_big[2 * kThreads];           // triangles that received their first anchor from this CTA, published with one global atomic
     __shared__ int s_nbig, s_bigbase;
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
     if (BATCH) {
@@ -840,11 +672,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         if (PREDICT) { x_in += n3; x_out += n3; }
         V_out += n3; A_out += n3;
     }
-    const int NL = kPatch + pv.max_halo, EM = pv.max_elem;
+    const int NL = kPatch + pv.max_halo;
     unsigned long long *bar = (unsigned long long *)smraw;
     unsigned char *sblob = smraw + 16;
     double *sX0 = (double *)(sblob + pv.stride), *sX1 = sX0 + NL, *sx0 = sX1 + NL, *sx1 = sx0 + NL, *se0 = sx1 + NL, *se1 = se0 + NL, *se3 = se1 + NL;
-    double *rec = se3 + NL;                       // [9][EM]: r1x r1y r2x r2y es0 es1 es3 A0 a_cur
+    double *rec = se3 + NL;                       // [max_elem][kRec]
     const int p = blockIdx.x, tid = threadIdx.x;
     const int n0 = p * kPatch;
     const int nown = min(kPatch, s.nn - n0);
@@ -875,20 +707,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     const int i = n0 + tid;
     double V0 = 0, V1 = 0, Av0 = 0, Av1 = 0;      // own node's V, A (kept for the update)
     double fa0 = 0, fa1 = 0, cC = 0;
-    if (own) { V0 = s.V[i]; V1 = s.V[np + i]; Av0 = s.A[i]; Av1 = s.A[np + i]; fa0 = s.fa[i]; fa1 = s.fa[np + i]; cC = s.cC[i]; }
-#if WCFE_CELL_PREFETCH
+    int bi = -1;                                   // boundary ordinal of the own node
     // the triangle the anchor was in at the previous step and its (frozen) vertices: loc_first -> tri -> x are three dependent
     // global loads; issued here they complete behind the staging wait instead of after the bond update
-    int tprev = -1;
+    int tprev = -1, tv0 = 0, tv1 = 0, tv2 = 0;
     double t1x = 0, t1y = 0, t2x = 0, t2y = 0, t3x = 0, t3y = 0;
     if (own) {
+        V0 = s.V[i]; V1 = s.V[np + i]; Av0 = s.A[i]; Av1 = s.A[np + i]; fa0 = s.fa[i]; fa1 = s.fa[np + i]; cC = s.cC[i];
+        bi = b.index[i];
         tprev = a.d_loc_first[i];
         if (tprev >= 0 && tprev < sub.ne) {
-            const int i0 = sub.tri[tprev], i1 = sub.tri[sub.nep + tprev], i2 = sub.tri[2 * sub.nep + tprev];
-            t1x = sub.x[i0]; t1y = sub.x[sub.np + i0]; t2x = sub.x[i1]; t2y = sub.x[sub.np + i1]; t3x = sub.x[i2]; t3y = sub.x[sub.np + i2];
+            tv0 = sub.tri[tprev]; tv1 = sub.tri[sub.nep + tprev]; tv2 = sub.tri[2 * sub.nep + tprev];
+            t1x = sub.x[tv0]; t1y = sub.x[sub.np + tv0]; t2x = sub.x[tv1]; t2y = sub.x[sub.np + tv1]; t3x = sub.x[tv2]; t3y = sub.x[sub.np + tv2];
         } else tprev = -1;
     }
-#endif
     __syncthreads();
     mbar_wait(bar, 0);
     const int *hdr = (const int *)sblob;
@@ -897,14 +729,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     const unsigned short *elem_lv = (const unsigned short *)(sblob + pv.off_lv);
     const unsigned short *rptr = (const unsigned short *)(sblob + pv.off_rptr);
     const unsigned short *ring16 = (const unsigned short *)(sblob + pv.off_ring);
-    // ---- predictor for the own node (UL:118, main.cpp:228; uncontracted so that x_new is bit-identical to the x86 reference)
-    if (PREDICT && own) {
-        const double vh0 = WCFE_ADD(V0, WCFE_MUL(a.dt / 2.0, Av0)), vh1 = WCFE_ADD(V1, WCFE_MUL(a.dt / 2.0, Av1));
-        const double xn0 = WCFE_ADD(sX0[tid], WCFE_MUL(a.dt, vh0)), xn1 = WCFE_ADD(sX1[tid], WCFE_MUL(a.dt, vh1));
-        sx0[tid] = xn0; sx1[tid] = xn1;
-        x_out[i] = xn0; x_out[np + i] = xn1;
-    }
-    // ---- halo gather (+ the same predictor: every patch that sees a node computes the same x_new)
+    // ---- halo gather first (its global loads fly while the own node's bond kinetics run) + the same predictor: every patch that
+    //      sees a node computes the same x_new
     for (int l = tid; l < nh; l += kThreads) {
         const int gi = halo_ids[l];
         const int d = kPatch + l;
@@ -918,10 +744,32 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         }
         se0[d] = s.ea_in[gi]; se1[d] = s.ea_in[np + gi]; se3[d] = s.ea_in[3 * (size_t)np + gi];
     }
+    // ---- predictor for the own node (UL:118, main.cpp:228; uncontracted so that x_new is bit-identical to the x86 reference)
+    if (PREDICT && own) {
+        const double vh0 = WCFE_ADD(V0, WCFE_MUL(a.dt / 2.0, Av0)), vh1 = WCFE_ADD(V1, WCFE_MUL(a.dt / 2.0, Av1));
+        const double xn0 = WCFE_ADD(sX0[tid], WCFE_MUL(a.dt, vh0)), xn1 = WCFE_ADD(sX1[tid], WCFE_MUL(a.dt, vh1));
+        sx0[tid] = xn0; sx1[tid] = xn1;
+        x_out[i] = xn0; x_out[np + i] = xn1;
+    }
     // ---- bond kinetics + anchor location for the own node (needs only its own X, x)
-    double anc_px = 0.0, anc_py = 0.0;
+    double anc_px = 0.0, anc_py = 0.0, myx0 = 0.0, myx1 = 0.0;
+    unsigned int slot_prev = 0xffffffffu;          // deferred: the slot taken in the previous step's triangle (result of an atomic in flight)
+    int cnt = 0, first = -1;
+    // a triangle received an anchor: record the node, stamp the triangle's three nodes and list the triangle when it was the first
+    auto finish_insert = [&](int t, unsigned int slot, int v0, int v1, int v2) {
+        if (slot < (unsigned int)bk.cap) bk.items[(size_t)t * bk.cap + slot] = i; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
+        if (slot == 0) {                 // first anchor of the step in this triangle: its three nodes have something to gather
+            bk.node_epoch[v0] = bk.epoch; bk.node_epoch[v1] = bk.epoch; bk.node_epoch[v2] = bk.epoch;
+            if (bk.big_count) {          // ... and k_bucket_reduce has a triangle to reduce
+                const int q = atomicAdd(&s_nbig, 1);
+                if (q < 2 * kThreads) s_big[q] = t;
+                else { const unsigned int idx = atomicAdd(bk.big_count, 1u); if (idx < (unsigned int)bk.big_cap) bk.big_list[idx] = t; else atomicOr(a.err, ERR_BUCKET_OVERFLOW); }
+            }
+        }
+    };
     if (own) {
-        const double Xi[3] = {sX0[tid], sX1[tid], 0.0}, xi[3] = {sx0[tid], sx1[tid], 0.0};
+        myx0 = sx0[tid]; myx1 = sx1[tid];
+        const double Xi[3] = {sX0[tid], sX1[tid], 0.0}, xi[3] = {myx0, myx1, 0.0};
         double fa[3] = {fa0, fa1, 0.0};
         if (a.debug) {
             const double pt0[3] = {Xi[0] - fa[0], Xi[1] - fa[1], 0.0};                  // UL:2020
@@ -936,63 +784,31 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         const double pt[3] = {xi[0] - fa0, xi[1] - fa1, 0.0};                           // UL:1303
         anc_px = pt[0]; anc_py = pt[1];
         if (!(pt[0] >= a.ix0 && pt[0] <= a.ix1 && pt[1] >= a.iy0 && pt[1] <= a.iy1)) atomicOr(a.err, ERR_REGION);
-        int cnt = 0, first = -1;
-        auto insert = [&](int t, const double *, double) {
-            if (cnt == 0) first = t;
-            cnt++;
-            unsigned long long *h = bk.head + t;
-            unsigned long long old = *h, want;
-            int slot;
-            do {
-                const unsigned long long seen = old;
-                if ((unsigned int)(seen >> 32) != bk.epoch) { want = ((unsigned long long)bk.epoch << 32) | 1ull; slot = 0; }
-                else { want = seen + 1ull; slot = (int)(unsigned int)seen; }
-                old = atomicCAS(h, seen, want);
-                if (old == seen) break;
-            } while (true);
-            if (slot < bk.cap) bk.items[(size_t)t * bk.cap + slot] = i; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
-            if (slot == 0) {                 // first anchor of the step in this triangle: its three nodes have something to gather
-                bk.node_epoch[sub.tri[t]] = bk.epoch; bk.node_epoch[sub.tri[sub.nep + t]] = bk.epoch; bk.node_epoch[sub.tri[2 * sub.nep + t]] = bk.epoch;
-            }
-            if (slot == bk.big_T) {          // this insert makes the bucket "big": list it once for k_bucket_reduce
-                const int q = atomicAdd(&s_nbig, 1);
-                if (q < 2 * kThreads) s_big[q] = t;
-                else { const unsigned int idx = atomicAdd(bk.big_count, 1u); if (idx < (unsigned int)bk.big_cap) bk.big_list[idx] = t; else atomicOr(a.err, ERR_BUCKET_OVERFLOW); }
-            }
-        };
         // Anchors rarely change triangle between steps: try the triangle of the previous step first.  A point STRICTLY inside
         // it (all three sub-areas > 0) lies in no other triangle of a conforming substrate mesh, so the grid search -- which
         // finds every containing triangle, as the reference's exhaustive loop does (UL:1309-1452) -- is only needed otherwise.
         bool done = false;
-#if WCFE_CELL_PREFETCH
         if (tprev >= 0) {
             double Ar[3], At;      // planar path: z == 0 everywhere (checked at upload), the 2-D predicate is bit-identical to the 3-D one
-            if (point_in_triangle_2d(t1x, t1y, t2x, t2y, t3x, t3y, pt[0], pt[1], Ar, At) && Ar[0] > 0 && Ar[1] > 0 && Ar[2] > 0) { insert(tprev, Ar, At); done = true; }
+            if (point_in_triangle_2d(t1x, t1y, t2x, t2y, t3x, t3y, pt[0], pt[1], Ar, At) && Ar[0] > 0 && Ar[1] > 0 && Ar[2] > 0) {
+                slot_prev = bucket_take_slot(bk, tprev);      // consumed after the element phase: the round trip hides behind it
+                cnt = 1; first = tprev; done = true;
+            }
         }
-#else
-        const int tprev = a.d_loc_first[i];
-        if (tprev >= 0 && tprev < sub.ne) {
-            const int i0 = sub.tri[tprev], i1 = sub.tri[sub.nep + tprev], i2 = sub.tri[2 * sub.nep + tprev];
-            double Ar[3], At;      // planar path: z == 0 everywhere (checked at upload), the 2-D predicate is bit-identical to the 3-D one
-            if (point_in_triangle_2d(sub.x[i0], sub.x[sub.np + i0], sub.x[i1], sub.x[sub.np + i1], sub.x[i2], sub.x[sub.np + i2], pt[0], pt[1], Ar, At) &&
-                Ar[0] > 0 && Ar[1] > 0 && Ar[2] > 0) { insert(tprev, Ar, At); done = true; }
+        if (!done) {
+            locate(g, sub, pt, [&](int t, const double *, double) {
+                if (cnt == 0) first = t;
+                cnt++;
+                finish_insert(t, bucket_take_slot(bk, t), sub.tri[t], sub.tri[sub.nep + t], sub.tri[2 * sub.nep + t]);
+            });
         }
-#endif
-        if (!done) locate(g, sub, pt, insert);
         a.d_loc_cnt[i] = cnt; a.d_loc_first[i] = first;
     }
-    __syncthreads();
-    if (bk.big_count) {                       // uniform: publish this CTA's share of the big-bucket list
-        const int nbig = min(s_nbig, 2 * kThreads);
-        if (tid == 0 && nbig) s_bigbase = (int)atomicAdd(bk.big_count, (unsigned int)nbig);
-        __syncthreads();
-        for (int q = tid; q < nbig; q += kThreads) {
-            const int idx = s_bigbase + q;
-            if (idx < bk.big_cap) bk.big_list[idx] = s_big[q]; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
-        }
-    }
-    // ---- elements
+    __syncthreads();                              // node table complete (halo rows, predicted own rows)
+    // ---- elements: closed-form planar element from shared memory, one record per patch-local element; the thread that
+    //      evaluates an element whose local vertex 0 this patch owns also counts it for calculateAreaTot (UL:1655-1661)
     const double tk = t_act_of(k, a.t_tot) * k.kappa;
+    double red0 = 0.0, red1 = 0.0, red2 = 0.0;
     for (int el = tid; el < nel; el += kThreads) {
         const unsigned short *lv = elem_lv + 3 * el;
         const int n1 = lv[0], n2 = lv[1], n3 = lv[2];
@@ -1002,36 +818,60 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
                               1.0 / 3.0 * se3[n1] + 1.0 / 3.0 * se3[n2] + 1.0 / 3.0 * se3[n3]};
         ElemOut2 o;
         elem_eval_planar(X, x, e3, k.mu_cell, tk, k.thick, o);
-        rec[el] = o.r1[0]; rec[EM + el] = o.r1[1]; rec[2 * EM + el] = o.r2[0]; rec[3 * EM + el] = o.r2[1];
-        rec[4 * EM + el] = o.eas[0]; rec[5 * EM + el] = o.eas[1]; rec[6 * EM + el] = o.eas[2]; rec[7 * EM + el] = o.A0; rec[8 * EM + el] = o.a_cur;
+        double *R = rec + kRec * el;
+        R[0] = o.r1[0]; R[1] = o.r1[1]; R[2] = o.r2[0]; R[3] = o.r2[1]; R[4] = o.eas[0]; R[5] = o.eas[1]; R[6] = o.eas[2]; R[7] = o.A0; R[8] = o.a_cur;
+        if (n1 < kPatch) {
+            red0 += o.a_cur;
+            red1 += (1. / 3.) * ((x[0][0] + x[1][0]) + x[2][0]) * o.a_cur;
+            red2 += (1. / 3.) * ((x[0][1] + x[1][1]) + x[2][1]) * o.a_cur;
+        }
     }
-    __syncthreads();
+    {   // fixed-order partial sums: lanes (shuffle tree), then warps (thread 0, after the barrier below)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { red0 += __shfl_down_sync(0xffffffffu, red0, off); red1 += __shfl_down_sync(0xffffffffu, red1, off); red2 += __shfl_down_sync(0xffffffffu, red2, off); }
+        if ((tid & 31) == 0) { shred[tid >> 5] = red0; shred[8 + (tid >> 5)] = red1; shred[16 + (tid >> 5)] = red2; }
+    }
+    if (own && slot_prev != 0xffffffffu) finish_insert(tprev, slot_prev, tv0, tv1, tv2);      // the deferred insert
+    __syncthreads();                              // records complete; every insert of this CTA listed
+    if (tid == 0) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < kThreads / 32; w++) { t0 += shred[w]; t1 += shred[8 + w]; t2 += shred[16 + w]; }
+        double *o = a.partials + (size_t)4 * blockIdx.x;
+        o[0] = t0; o[1] = t1; o[2] = t2; o[3] = 0.0;
+        const int nbig = min(s_nbig, 2 * kThreads);
+        if (bk.big_count && nbig) s_bigbase = (int)atomicAdd(bk.big_count, (unsigned int)nbig);
+    }
     // ---- nodes
-    double red[4] = {0.0, 0.0, 0.0, 0.0};
     if (own) {
         const double ea0 = se0[tid], ea1 = se1[tid], ea3 = se3[tid];
         double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0, asum = 0.0;
         const int rb = rptr[tid], re = rptr[tid + 1];
-        for (int r = rb; r < re; r++) {
-            const int code = ring16[r];
-            const int el = code >> 2, slot = code & 3;
-            const double r1x = rec[el], r1y = rec[EM + el], r2x = rec[2 * EM + el], r2y = rec[3 * EM + el];
-            rx += slot == 0 ? -(r1x + r2x) : (slot == 1 ? r1x : r2x);
-            ry += slot == 0 ? -(r1y + r2y) : (slot == 1 ? r1y : r2y);
-            const double A0 = rec[7 * EM + el], ac = rec[8 * EM + el];
-            q0 += (1. / 3.) * (rec[4 * EM + el] - ea0) * A0 * k.thick;               // UL:911
-            q1 += (1. / 3.) * (rec[5 * EM + el] - ea1) * A0 * k.thick;
-            q3 += (1. / 3.) * (rec[6 * EM + el] - ea3) * A0 * k.thick;
-            mm += (1. / 3.) * A0 * k.thick;                                          // UL:913
-            asum += ac / 3;                                                          // UL:1251
-            if (slot == 0) {                                                         // UL:1655-1661, each element once
-                const unsigned short *lv = elem_lv + 3 * el;
-                red[0] += ac;
-                red[1] += (1. / 3.) * ((sx0[lv[0]] + sx0[lv[1]]) + sx0[lv[2]]) * ac;
-                red[2] += (1. / 3.) * ((sx1[lv[0]] + sx1[lv[1]]) + sx1[lv[2]]) * ac;
-            }
+        // the one-ring gather is a chain of dependent shared-memory loads (code -> record): two entries per trip, both codes and
+        // both records' loads issued before the first use; a missing second entry adds +0 (the ascending-element summation order
+        // of UL:692-705 and the result are unchanged)
+        for (int r = rb; r < re; r += 2) {
+            const bool two = r + 1 < re;
+            const int cA = ring16[r], cB = two ? (int)ring16[r + 1] : 0;
+            const double *RA = rec + kRec * (cA >> 2), *RB = rec + kRec * (cB >> 2);
+            const int sA = cA & 3, sB = cB & 3;
+            const double a0 = RA[0], a1 = RA[1], a2 = RA[2], a3 = RA[3], a4 = RA[4], a5 = RA[5], a6 = RA[6], a7 = RA[7], a8 = RA[8];
+            const double b0 = RB[0], b1 = RB[1], b2 = RB[2], b3 = RB[3], b4 = RB[4], b5 = RB[5], b6 = RB[6], b7 = two ? RB[7] : 0.0, b8 = two ? RB[8] : 0.0;
+            rx += sA == 0 ? -(a0 + a2) : (sA == 1 ? a0 : a2);
+            ry += sA == 0 ? -(a1 + a3) : (sA == 1 ? a1 : a3);
+            q0 += (1. / 3.) * (a4 - ea0) * a7 * k.thick;               // UL:911
+            q1 += (1. / 3.) * (a5 - ea1) * a7 * k.thick;
+            q3 += (1. / 3.) * (a6 - ea3) * a7 * k.thick;
+            mm += (1. / 3.) * a7 * k.thick;                            // UL:913
+            asum += a8 / 3;                                            // UL:1251
+            const double fxB = sB == 0 ? -(b0 + b2) : (sB == 1 ? b0 : b2), fyB = sB == 0 ? -(b1 + b3) : (sB == 1 ? b1 : b3);
+            rx += two ? fxB : 0.0; ry += two ? fyB : 0.0;
+            q0 += (1. / 3.) * (b4 - ea0) * b7 * k.thick;               // b7 == 0 without a second entry: +0
+            q1 += (1. / 3.) * (b5 - ea1) * b7 * k.thick;
+            q3 += (1. / 3.) * (b6 - ea3) * b7 * k.thick;
+            mm += (1. / 3.) * b7 * k.thick;
+            asum += b8 / 3;
         }
-        double Vh0 = V0 + (a.dt / 2.0) * Av0, Vh1 = V1 + (a.dt / 2.0) * Av1;         // UL:118
+        double Vh0 = V0 + (a.dt_drv / 2.0) * Av0, Vh1 = V1 + (a.dt_drv / 2.0) * Av1;         // UL:118
         const double u[3] = {fa0, fa1, 0.0};
         double fi[3];
         integrin_force(k, u, fi);
@@ -1046,14 +886,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
             dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
             dbg.f_ap[i] = 0.0; dbg.f_ap[np + i] = 0.0; dbg.f_bend[i] = 0.0; dbg.f_bend[np + i] = 0.0; dbg.f_area[i] = 0.0; dbg.f_area[np + i] = 0.0;
         }
-        const int bi = b.index[i];
         if (bi < 0) {
             node_update(Fvx + Ffx - rx, mm, k.damp, k.rho, a.dt, a.dt_real, Vh0, V0, Av0);           // UL:592-628
             node_update(Fvy + Ffy - ry, mm, k.damp, k.rho, a.dt, a.dt_real, Vh1, V1, Av1);
             // V, A go to the OTHER buffer: neighbouring patches still read this node's old V, A for their halo predictor
             V_out[i] = V0; V_out[np + i] = V1; A_out[i] = Av0; A_out[np + i] = Av1;
         } else {
-            const double xi[3] = {sx0[tid], sx1[tid], 0.0};
+            const double xi[3] = {myx0, myx1, 0.0};
             double j1[3] = {0, 0, 0}, j2[3] = {0, 0, 0};
             for (int q = b.cand_ptr[bi]; q < b.cand_ptr[bi + 1]; q++) {                                // UL:1479-1507
                 const int lj = pv.cand_l[2 * q], lint = pv.cand_l[2 * q + 1];
@@ -1076,12 +915,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
             if (DBG) { dbg.f_bend[i] = Fbx; dbg.f_bend[np + i] = Fby; dbg.f_ap[i] = Fax; dbg.f_ap[np + i] = Fay; }
         }
     }
-    block_reduce4(red, shred);
-    if (tid == 0) {
-        for (int q = 0; q < 4; q++) a.partials[(size_t)4 * blockIdx.x + q] = red[q];
-        // every thread's global writes (state, buckets, stamps, anchor records) precede the barriers of the reduction above: one
-        // release by this thread publishes them all to whoever acquires the counter (k_subs_ring)
-        if (bk.cell_done) { __threadfence(); atomicAdd(bk.cell_done, 1ull); }
+    if (bk.big_count) {                       // uniform: publish this CTA's share of the triangle list
+        __syncthreads();                      // s_bigbase
+        const int nbig = min(s_nbig, 2 * kThreads);
+        for (int q = tid; q < nbig; q += kThreads) {
+            const int idx = s_bigbase + q;
+            if (idx < bk.big_cap) bk.big_list[idx] = s_big[q]; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
+        }
+    }
+    if (bk.cell_done) {
+        // every thread's global writes (state, buckets, stamps, anchor records) precede this barrier: one release by thread 0
+        // publishes them all to whoever acquires the counter (k_subs_ring)
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicAdd(bk.cell_done, 1ull); }
     }
 }
 
