@@ -12,7 +12,7 @@ reference's only parallel mode is independent processes, s_sim_031021_1.sub) -- 
 The state (1.1 GB) is ~9x the 126 MB L2, so successive steps stream from HBM: no explicit L2 flush is needed.
 
 The JSON line carries, beside the base contract:
-  roofline      the dominant kernel (k_subs_patch): algorithmic bytes per launch (216 B/substrate node + 12 B/element,
+  roofline      the dominant kernel (k_subs_ring): algorithmic bytes per launch (216 B/substrate node + 12 B/element,
                 SURVEY.md 8d) / its CUDA-event duration measured live, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the oracle's C restatement ("port", grid point location) timed on this box's host on a bounded sample
   e2e           the same metric through the adapter-mode C-ABI call with host round trips every step
@@ -152,8 +152,24 @@ def _replica_worker(args):
     return time.perf_counter() - t0, len(tc) + len(ts)
 
 
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1048576.0
+    except Exception:
+        pass
+    return 8.0
+
+
 def run_reference_arm(a):
-    """The reference's CPU implementation of the path, all host cores as independent replicas (its only parallel mode)."""
+    """The reference's CPU implementation of the path, all host cores as independent replicas (its only parallel mode,
+    s_sim_031021_1.sub).  Two measurements in one line:
+      value / cpu_baseline   the UNMODIFIED reference (oracle/_ref, brute-force point location, UL:1309, :2026) on a 1/256-size
+                             sample -- as large as its O(Nn_cell x Ne_subs) search allows -- exactly `steps` timed steps;
+      same_algorithm         the oracle's C restatement with the GRID point location our kernels use, same workload at the
+                             largest fraction of the full size the host's memory allows (1/1 where it fits), all cores:
+                             the like-for-like CPU number (the reference value flatters nobody: its algorithm is quadratic)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -162,24 +178,41 @@ def run_reference_arm(a):
     cores = os.cpu_count() or 1
     div = a.cpu_sample_div
     use_ref = ref_available(a.variant)
-    # the unmodified reference locates anchors by brute force, O(Nn_cell * Ne_subs) twice per step (UL:1309, :2026): at the
-    # bench workload that is ~8e12 predicate evaluations per step, so it is only runnable on a far smaller sample
     if use_ref:
         kind, cell_tris, subs_side = "reference", max(600, a.cell_tris // 256), max(24, a.subs_side // 16)
     else:
         kind, cell_tris, subs_side = "port", max(600, a.cell_tris // div), max(24, int(a.subs_side / math.sqrt(div)))
-    steps = max(1, min(a.steps, 4))
+    steps = max(1, min(a.steps, 60))            # every reported step is run; above 60 the sample would outlast "a few minutes"
+    warm = max(1, min(a.warmup, 3))
     with mp.get_context("spawn").Pool(cores) as pool:
-        res = pool.map(_replica_worker, [(kind, a.variant, cell_tris, subs_side, a.dt, steps, 1)] * cores)
-    wall = max(r[0] for r in res)
-    value = sum(r[1] for r in res) * steps / wall
-    sample = ("%d independent replicas (one per core) x %d steps of a %d-triangle cell on a %d-node substrate (%s point location)"
-              % (cores, steps, cell_tris, subs_side * subs_side, "brute-force" if use_ref else "grid"))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        res = pool.map(_replica_worker, [(kind, a.variant, cell_tris, subs_side, a.dt, steps, warm)] * cores)
+        wall = max(r[0] for r in res)
+        value = sum(r[1] for r in res) * steps / wall
+        sample = ("%d independent replicas (one per core) x %d steps of a %d-triangle cell on a %d-node substrate (%s point location): 1/%d of the workload's cell"
+                  % (cores, steps, cell_tris, subs_side * subs_side, "brute-force" if use_ref else "grid", max(1, a.cell_tris // max(1, cell_tris))))
+        # the like-for-like arm: same algorithm (grid search), same mesh generator; ~3 GB of host memory per full-size replica
+        same = None
+        try:
+            frac = 1
+            while frac < 64 and cores * 3.0 / frac > 0.6 * _mem_available_gb():
+                frac *= 4
+            ct, ss = max(600, a.cell_tris // frac), max(24, int(a.subs_side / math.sqrt(frac)))
+            psteps = 2 if frac == 1 else 4
+            pres = pool.map(_replica_worker, [("port", a.variant, ct, ss, a.dt, psteps, 1)] * cores)
+            pwall = max(r[0] for r in pres)
+            same = {"value": sum(r[1] for r in pres) * psteps / pwall, "unit": UNIT, "cores": cores, "kind": "port", "fraction_of_workload": "1/%d" % frac,
+                    "ms_per_step_per_replica": 1e3 * pwall / psteps,
+                    "sample": "%d replicas (one per core) x %d steps of a %d-triangle cell on a %d-node substrate, oracle C restatement with grid point location"
+                              % (cores, psteps, ct, ss * ss)}
+        except Exception as e:                  # side measurement: never fatal
+            same = {"skipped": str(e)}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "gpu_launches": 0,
-            "config": {"workload": workload_name(a), "variant": a.variant, "dt": a.dt, "note": "the CPU arm runs a bounded sample of this workload (cpu_baseline.sample)"},
+            "config": {"workload": workload_name(a), "variant": a.variant, "dt": a.dt,
+                       "note": "the CPU arm runs a bounded sample of this workload (cpu_baseline.sample); steps = timed steps actually run (requested %d)" % a.steps},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "same_algorithm": same,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -216,7 +249,8 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
     total_steps = a.warmup + a.steps + 10
     ids, ea_part = sim.owned_field("ea"); _, v_part = sim.owned_field("V")
     xc_part = sim.sim.get(W.CELL, "x")
-    sim.sim.close()
+    part0 = {"substrate_nodes_local": int(len(sim.part.local_nodes)), "owned": int(len(sim.part.owned)), "ghosts": int(len(sim.part.ghosts))}
+    sim.close()                                  # collective: sync + barrier before any rank unmaps its halo buffers
     one = W.ULSim(a.variant, device=local)
     one.upload_mesh(W.CELL, cell_mesh[0], cell_mesh[1]); one.upload_mesh(W.SUBS, subs_mesh[0], subs_mesh[1]); one.set_rng(1, 1)
     one.step_n(total_steps, a.dt, 0.0)
@@ -233,7 +267,7 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
                                                      else "substrate strip partition x%d + per-step torch.distributed (NCCL) halo exchange (%d border nodes x 24 B per step)") % (world, halo)},
                           "gpu_launches": l1 - l0, "rank0_per_kernel_ms": per_kernel,
                           "bitwise_equal_to_single_gpu": {"value": bool(int(okt.item())), "steps": total_steps, "what": "owned substrate rows (ea, V) of every rank and the replicated cell's positions against the same steps of the whole mesh on one GPU"},
-                          "strips": "equal cost (nodes under the cell x3)" if a.balance else "equal node count", "rank0_strip": {"substrate_nodes_local": int(len(sim.part.local_nodes)), "owned": int(len(sim.part.owned)), "ghosts": int(len(sim.part.ghosts))}}), flush=True)
+                          "strips": "equal cost (nodes under the cell x3)" if a.balance else "equal node count", "rank0_strip": part0}), flush=True)
     dist.destroy_process_group()
 
 
@@ -394,12 +428,31 @@ def main():
                 "patch_elements_per_element": {"cell": info["cell_patch_elem_ratio"], "substrate": info["subs_patch_elem_ratio"]},
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_max / a.steps * 1e-3) / 1e9,
                                "frac": step_bytes / (ms_max / a.steps * 1e-3) / 1e9 / peak}}
-    # ncu dram__bytes of the same kernel, if a capture has been summarised under profiles/
+    # ncu dram__bytes per launch (profiles/traffic.json, regenerated from the round's --set full capture): the planar path never
+    # moves the z words the contract bytes count, so the fraction of the HBM peak actually USED is printed beside the contract one
+    tr = {}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        roofline["traffic"] = tr.get(dom)
     except Exception:
         pass
+    roofline["traffic"] = tr.get(dom)
+    if tr.get(dom) and dom_ms > 0:
+        roofline["frac_traffic"] = tr[dom] / (dom_ms * 1e-3) / 1e9 / peak
+    # bytes the planar kernels cannot avoid: in-plane x, V, A + 3 strain words (+ c_C, fa_u in-plane on the cell), read and written
+    # once, 12 B of connectivity per element
+    planar_subs = 128 * nn_s + 12 * ne_s
+    planar_cell = 192 * nn_c + 12 * ne_c
+    roofline["planar_compulsory_bytes_per_launch"] = planar_subs
+    roofline["frac_planar_compulsory"] = planar_subs / (dom_ms * 1e-3) / 1e9 / peak if dom_ms > 0 else None
+    if info["planar"] and per_kernel.get("k_cell_patch"):
+        cms = per_kernel["k_cell_patch"]
+        cell_bytes = 304 * nn_c + 12 * ne_c
+        roofline["cell_kernel"] = {"kernel": "k_cell_patch", "kernel_ms": cms, "algorithmic_bytes_per_launch": cell_bytes,
+                                   "achieved": cell_bytes / (cms * 1e-3) / 1e9, "frac": cell_bytes / (cms * 1e-3) / 1e9 / peak,
+                                   "traffic": tr.get("k_cell_patch"),
+                                   "frac_traffic": (tr["k_cell_patch"] / (cms * 1e-3) / 1e9 / peak) if tr.get("k_cell_patch") else None,
+                                   "planar_compulsory_bytes_per_launch": planar_cell,
+                                   "target": "north_star: >= 0.5 for the fused force+update step on the 1M-triangle cell (SURVEY 8d: 164 MB in <= 50 us)"}
 
     # end to end: a host integrator in the loop -- positions to pinned host memory and back EVERY step (wall clock, max over ranks)
     def time_roundtrip(both):

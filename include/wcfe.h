@@ -117,6 +117,10 @@ const char *wcfe_last_error(wcfe_ctx *c);
 int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne, const int *tri);
 int wcfe_upload_state(wcfe_ctx *c, int surface, int field, const double *host);
 int wcfe_download_state(wcfe_ctx *c, int surface, int field, double *host);
+/* The same for several fields of one surface at once: one pinned transfer and one stream synchronisation per call instead of one
+ * per field (fields[q] is a WCFE_F_* id, host[q] its image laid out as for the single-field calls; processed in order). */
+int wcfe_upload_states(wcfe_ctx *c, int surface, int n_fields, const int *fields, const double *const *host);
+int wcfe_download_states(wcfe_ctx *c, int surface, int n_fields, const int *fields, double *const *host);
 int wcfe_mesh_sizes(wcfe_ctx *c, int surface, int *nn, int *ne);
 
 int wcfe_set_rng(wcfe_ctx *c, int mode, unsigned int seed);
@@ -129,8 +133,8 @@ int wcfe_set_profile(wcfe_ctx *c, int on);
 /* test hook: run the general 3-D (node-centric) kernels even when the state is planar */
 int wcfe_set_force_general(wcfe_ctx *c, int on);
 /* out8: planar fast path active (0/1), patch-local elements / elements for cell and substrate (recompute overhead),
- * max halo nodes / max elements per cell patch, max halo nodes per substrate patch, substrate kernel in use (2 k_subs_ring,
- * 0 k_subs_patch, 1 k_subs_pipe), triangle-bucket capacity */
+ * max halo nodes / max elements per cell patch, max halo nodes per substrate patch, substrate kernel in use (2 k_subs_ring: node-centric,
+ * the default; 0 k_subs_patch: element-once), triangle-bucket capacity */
 int wcfe_get_path_info(wcfe_ctx *c, double *out8);
 int wcfe_get_kernel_ms(wcfe_ctx *c, double *ms8, long long *count8);
 
@@ -191,6 +195,10 @@ int wcfe_force_field(wcfe_ctx *c, int which, double dt, double t_curr, double *o
  * ask again after every step.  Zero-copy interop with torch.distributed for the halo exchange of partitioned meshes. */
 int wcfe_device_ptr(wcfe_ctx *c, int surface, int field, void **ptr, long long *pitch);
 int wcfe_sync(wcfe_ctx *c);
+/* Device self test: n pseudo-random operand pairs (zero numerators, both signs, x / 3 included) through the division-free correctly
+ * rounded quotients the kernels use (wcfe_math.cuh recip_of / quot) and through the compiler's IEEE `/`; *mismatch = results that
+ * differ in any bit (the sign of a zero quotient excepted).  Must be 0. */
+int wcfe_selftest_quotient(int device, long long n, unsigned int seed, long long *mismatch);
 
 /* ---- one mesh over several GPUs (BASELINE configs[3]: "element-partitioned over 2/4/8 B200 with ... halo exchange"; the reference
  * itself has no such mode).  Each rank's context holds ONE STRIP of the substrate -- its owned nodes plus a one-ring of
@@ -204,7 +212,10 @@ int wcfe_sync(wcfe_ctx *c);
  *   wcfe_halo_connect    peers[q]: the info of neighbour q; my_slot_at_peer[q]: this rank's index in q's own peer list;
  *                        rows_from_peer[q]: ghost rows q sends here per step; export_*: for every (border node, neighbour) pair the
  *                        local node, the peer slot and the node's local index AT the peer; ghost_node: local ids of the ghosts.
- * No step may run between info_get and connect; a host barrier across ranks must follow connect before the first step. */
+ * No step may run between info_get and connect; a host barrier across ranks must follow connect before the first step.
+ * Teardown is collective too: the border rows of the last step are peer stores that nobody has awaited, so before ANY rank calls
+ * wcfe_halo_disconnect, wcfe_destroy or wcfe_upload_mesh(WCFE_SUBS) every rank must have returned from wcfe_sync and met the
+ * others at a host barrier (a rank that unmaps its buffers earlier faults a slower neighbour still storing into them). */
 #define WCFE_HALO_MAX_PEERS 8
 typedef struct wcfe_halo_info {
     long long pid;                     /* owner process */

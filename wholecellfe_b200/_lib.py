@@ -19,11 +19,11 @@ RNG_GLIBC_REPLAY, RNG_PHILOX = 0, 1
 
 # every symbol include/wcfe.h declares
 SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_params", "wcfe_set_stream", "wcfe_last_error",
-           "wcfe_upload_mesh", "wcfe_upload_state", "wcfe_download_state", "wcfe_mesh_sizes", "wcfe_set_rng", "wcfe_set_debug",
+           "wcfe_upload_mesh", "wcfe_upload_state", "wcfe_download_state", "wcfe_upload_states", "wcfe_download_states", "wcfe_mesh_sizes", "wcfe_set_rng", "wcfe_set_debug",
            "wcfe_rng_skip", "wcfe_set_profile", "wcfe_get_kernel_ms", "wcfe_set_force_general", "wcfe_get_path_info",
            "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities",
            "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
-           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync",
+           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync", "wcfe_selftest_quotient",
            "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed", "wcfe_set_roundtrip_mode",
            "wcfe_halo_info_get", "wcfe_halo_connect", "wcfe_halo_disconnect",
            "wcfe_strip_partition", "wcfe_strip_sizes", "wcfe_strip_mesh", "wcfe_strip_halo", "wcfe_strip_free"]
@@ -75,6 +75,8 @@ def load():
     L.wcfe_upload_mesh.argtypes = [vp, C.c_int, C.c_int, _dp, C.c_int, _ip]
     L.wcfe_upload_state.argtypes = [vp, C.c_int, C.c_int, _dp]
     L.wcfe_download_state.argtypes = [vp, C.c_int, C.c_int, _dp]
+    L.wcfe_upload_states.argtypes = [vp, C.c_int, C.c_int, _ip, C.POINTER(_dp)]
+    L.wcfe_download_states.argtypes = [vp, C.c_int, C.c_int, _ip, C.POINTER(_dp)]
     L.wcfe_mesh_sizes.argtypes = [vp, C.c_int, _ip, _ip]
     L.wcfe_set_rng.argtypes = [vp, C.c_int, C.c_uint]
     L.wcfe_set_debug.argtypes = [vp, C.c_int]
@@ -102,6 +104,7 @@ def load():
     L.wcfe_force_field.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp]
     L.wcfe_device_ptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
     L.wcfe_sync.argtypes = [vp]
+    L.wcfe_selftest_quotient.argtypes = [C.c_int, C.c_longlong, C.c_uint, C.POINTER(C.c_longlong)]
     L.wcfe_halo_info_get.argtypes = [vp, C.POINTER(HaloInfo)]
     L.wcfe_halo_connect.argtypes = [vp, C.c_int, C.POINTER(HaloInfo), _ip, _ip, C.c_int, _ip, _ip, _ip, C.c_int, _ip]
     L.wcfe_halo_disconnect.argtypes = [vp]

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <Eigen/Dense>
 #include "vec.h"
 #include "nondestructivetrimesh.h"
@@ -35,6 +36,26 @@ struct Adapter {
     double dt_real = 0;
     bool cell_pending = false;        // updateFA seen, device step not yet run
 } g;
+
+// WCFE_ADAPTER_PROFILE=1: wall time spent inside each of the five entry points, printed at exit (where the whole application's
+// step goes: bench.py other_configs.whole_app)
+struct Prof {
+    double t[5] = {0, 0, 0, 0, 0}; long n[5] = {0, 0, 0, 0, 0}; bool on = false;
+    Prof() { on = std::getenv("WCFE_ADAPTER_PROFILE") != nullptr; }
+    ~Prof() {
+        if (!on) return;
+        const char *name[5] = {"driverVelocities_Explicit", "driverVelocities_Biaxial", "updateFA", "updateForces_Explicit(cell)", "updateForces_Explicit(subs)"};
+        double tot = 0;
+        for (int q = 0; q < 5; q++) tot += t[q];
+        std::fprintf(stderr, "wcfe adapter profile: %.3f ms per step inside the adapter (%ld steps)\n", n[2] ? 1e3 * tot / n[2] : 0.0, n[2]);
+        for (int q = 0; q < 5; q++) std::fprintf(stderr, "  %-30s %8ld calls %9.3f ms/call\n", name[q], n[q], n[q] ? 1e3 * t[q] / n[q] : 0.0);
+    }
+} g_prof;
+struct ProfScope {
+    int q; std::chrono::steady_clock::time_point t0;
+    explicit ProfScope(int q_) : q(q_) { if (g_prof.on) t0 = std::chrono::steady_clock::now(); }
+    ~ProfScope() { if (g_prof.on) { g_prof.t[q] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); g_prof.n[q]++; } }
+};
 
 void die(const char *where, int rc) {
     std::fprintf(stderr, "wcfe adapter: %s failed (%d): %s\n", where, rc, wcfe_last_error(g.ctx));
@@ -85,14 +106,13 @@ void sync_mesh(int surface, const std::vector<Vec3d> &x, const NonDestructiveTri
     old = s;
 }
 
-void put_ea(int surface, const std::vector<Eigen::VectorXd> &ea) {
-    g.buf.resize(6 * ea.size());
+// the reference keeps the strain as one heap-allocated Eigen 6-vector per node: flatten / scatter it around the batched transfers
+const double *flat_ea(const std::vector<Eigen::VectorXd> &ea) {
+    g.buf.resize(6 * ea.size() + 1);
     for (size_t i = 0; i < ea.size(); i++) for (int q = 0; q < 6; q++) g.buf[6 * i + q] = ea[i](q);
-    OK(wcfe_upload_state(g.ctx, surface, WCFE_F_EA, g.buf.data()));
+    return g.buf.data();
 }
-void get_ea(int surface, std::vector<Eigen::VectorXd> &ea) {
-    g.buf.resize(6 * ea.size());
-    OK(wcfe_download_state(g.ctx, surface, WCFE_F_EA, g.buf.data()));
+void scatter_ea(std::vector<Eigen::VectorXd> &ea) {
     for (size_t i = 0; i < ea.size(); i++) for (int q = 0; q < 6; q++) ea[i](q) = g.buf[6 * i + q];
 }
 
@@ -100,12 +120,14 @@ void get_ea(int surface, std::vector<Eigen::VectorXd> &ea) {
 
 // main.cpp:224, :329
 void driverVelocities_Explicit(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt) {
+    ProfScope ps(0);
     ensure_context();
     OK(wcfe_driver_velocities(g.ctx, WCFE_CELL, (int)X_t.size(), flat(X_t), flat(V_t), flat(A_t), dt, 0.0, flat(V_t_hlf)));
 }
 
 // main.cpp:293
 void driverVelocities_Biaxial(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot) {
+    ProfScope ps(1);
     ensure_context();
     OK(wcfe_driver_velocities(g.ctx, WCFE_SUBS, (int)X_t.size(), flat(X_t), flat(V_t), flat(A_t), dt, t_tot, flat(V_t_hlf)));
 }
@@ -117,6 +139,7 @@ void updateFA(std::vector<double> &c_A, std::vector<double> &c_C, std::vector<Ve
               const std::vector<Vec3d> &X_t_cell, const std::vector<Vec3d> &x_t_cell, const NonDestructiveTriMesh &mesh_cell,
               const std::vector<Vec3d> &X_t_subs, const std::vector<Vec3d> &x_t_subs, const NonDestructiveTriMesh &mesh_subs, double kint) {
     (void)kint;                       // kint is fixed by the variant (main.cpp:350-354)
+    ProfScope ps(2);
     ensure_context();
     // the device step assumes a FROZEN substrate (the literal 0* of main.cpp:299: x_t_subs == X_t_subs, F == I, subs_u == 0).  A
     // host integrator that moved a substrate vertex within this step (collision resolution) has left that regime: say so instead
@@ -129,11 +152,11 @@ void updateFA(std::vector<double> &c_A, std::vector<double> &c_C, std::vector<Ve
         }
     sync_mesh(WCFE_SUBS, X_t_subs, mesh_subs, true);     // vertices moved BETWEEN steps (smoothing): fresh positions, grid and tables
     sync_mesh(WCFE_CELL, X_t_cell, mesh_cell, false);
-    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_X, flat(x_t_cell)));
-    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_XPREV, flat(X_t_cell)));
-    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_CA, c_A.data()));
-    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_CC, c_C.data()));
-    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_FAU, flat(fa_u)));
+    {   // one pinned transfer for the five fields (X_prev after x: an upload of x alone would also set X_prev := x)
+        const int f[5] = {WCFE_F_X, WCFE_F_XPREV, WCFE_F_CA, WCFE_F_CC, WCFE_F_FAU};
+        const double *h[5] = {flat(x_t_cell), flat(X_t_cell), c_A.data(), c_C.data(), flat(fa_u)};
+        OK(wcfe_upload_states(g.ctx, WCFE_CELL, 5, f, h));
+    }
     OK(wcfe_mark_positions_committed(g.ctx));
     g.dt_real = dt_real;
     g.cell_pending = true;
@@ -147,17 +170,20 @@ void updateForces_Explicit(const std::vector<Vec3d> &X_t, const std::vector<Vec3
     // wcfe_driver_velocities recorded -- the caller's vector bit for bit, also when El Topo shortened the step and main.cpp
     // re-ran the driver with the smaller dt (main.cpp:329) while `dt` here is still ori_dt (main.cpp:360)
     (void)X_t; (void)x_t; (void)V_t_hlf; (void)c_B; (void)mesh;
+    ProfScope ps(3);
     if (!g.cell_pending) { std::fprintf(stderr, "wcfe adapter: updateForces_Explicit(cell) without a preceding updateFA\n"); std::abort(); }
-    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_V, flat(V_t)));
-    OK(wcfe_upload_state(g.ctx, WCFE_CELL, WCFE_F_A, flat(A_t)));
-    put_ea(WCFE_CELL, ea_t);
+    {
+        const int f[3] = {WCFE_F_V, WCFE_F_A, WCFE_F_EA};
+        const double *h[3] = {flat(V_t), flat(A_t), flat_ea(ea_t)};
+        OK(wcfe_upload_states(g.ctx, WCFE_CELL, 3, f, h));
+    }
     OK(wcfe_update_cell(g.ctx, dt, dt_real, t_tot));
-    OK(wcfe_download_state(g.ctx, WCFE_CELL, WCFE_F_V, flat(V_t)));
-    OK(wcfe_download_state(g.ctx, WCFE_CELL, WCFE_F_A, flat(A_t)));
-    get_ea(WCFE_CELL, ea_t);
-    OK(wcfe_download_state(g.ctx, WCFE_CELL, WCFE_F_CA, c_A.data()));
-    OK(wcfe_download_state(g.ctx, WCFE_CELL, WCFE_F_CC, c_C.data()));
-    OK(wcfe_download_state(g.ctx, WCFE_CELL, WCFE_F_FAU, flat(fa_u)));
+    {
+        const int f[6] = {WCFE_F_V, WCFE_F_A, WCFE_F_EA, WCFE_F_CA, WCFE_F_CC, WCFE_F_FAU};
+        double *h[6] = {flat(V_t), flat(A_t), g.buf.data(), c_A.data(), c_C.data(), flat(fa_u)};
+        OK(wcfe_download_states(g.ctx, WCFE_CELL, 6, f, h));
+        scatter_ea(ea_t);
+    }
     g.cell_pending = false;
 }
 
@@ -167,13 +193,19 @@ void updateForces_Explicit(const std::vector<Vec3d> &X_t, const std::vector<Vec3
                            double t_tot, std::vector<Vec3d> &fa_u, const std::vector<double> &c_C, const std::vector<Vec3d> &x_cell,
                            const NonDestructiveTriMesh &mesh_cell) {
     (void)X_t; (void)x_t; (void)V_t_hlf; (void)mesh; (void)fa_u; (void)c_C; (void)x_cell; (void)mesh_cell;   // already on the device
-    OK(wcfe_upload_state(g.ctx, WCFE_SUBS, WCFE_F_V, flat(V_t)));
-    OK(wcfe_upload_state(g.ctx, WCFE_SUBS, WCFE_F_A, flat(A_t)));
-    put_ea(WCFE_SUBS, ea_t);
+    ProfScope ps(4);
+    {
+        const int f[3] = {WCFE_F_V, WCFE_F_A, WCFE_F_EA};
+        const double *h[3] = {flat(V_t), flat(A_t), flat_ea(ea_t)};
+        OK(wcfe_upload_states(g.ctx, WCFE_SUBS, 3, f, h));
+    }
     OK(wcfe_update_subs(g.ctx, dt, dt_real, t_tot));
-    OK(wcfe_download_state(g.ctx, WCFE_SUBS, WCFE_F_V, flat(V_t)));
-    OK(wcfe_download_state(g.ctx, WCFE_SUBS, WCFE_F_A, flat(A_t)));
-    get_ea(WCFE_SUBS, ea_t);
+    {
+        const int f[3] = {WCFE_F_V, WCFE_F_A, WCFE_F_EA};
+        double *h[3] = {flat(V_t), flat(A_t), g.buf.data()};
+        OK(wcfe_download_states(g.ctx, WCFE_SUBS, 3, f, h));
+        scatter_ea(ea_t);
+    }
 }
 
 // test hooks (used by the adapter parity test; harmless in production)

@@ -130,6 +130,7 @@ struct wcfe_ctx {
     double ibox[4] = {0, 0, 0, 0};        // region the anchors themselves must stay in (box shrunk by the longest substrate edge)
     // discrete state + flags
     DevBuf<int> d_flags, d_loc_bond, d_loc_cnt, d_loc_first, d_ap_fire, d_err;
+    DevBuf<double2> d_loc_cache;          // CellStepArgs::loc_cache: [4][np] per replica
     DevBuf<double> d_partials, d_diag;
     DevBuf<unsigned int> d_tape;
     DevBuf<double> d_drv;                 // scratch of wcfe_driver_velocities
@@ -671,7 +672,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         a.ix0 = c->ibox[0]; a.ix1 = c->ibox[1]; a.iy0 = c->ibox[2]; a.iy1 = c->ibox[3];
         a.rng_mode = c->rng_mode; a.seed = c->seed; a.step = c->step; a.tape = tape_dev; a.partials = c->d_partials.p;
         a.d_flags = c->d_flags.p; a.d_loc_bond = c->d_loc_bond.p; a.d_loc_cnt = c->d_loc_cnt.p; a.d_loc_first = c->d_loc_first.p;
-        a.d_ap_fire = c->d_ap_fire.p; a.err = c->d_err.p; a.debug = c->debug;
+        a.d_ap_fire = c->d_ap_fire.p; a.err = c->d_err.p; a.debug = c->debug; a.loc_cache = c->d_loc_cache.p;
         if (c->halo.active && c->halo.step > 0) { a.halo_peer = c->halo.peers.p; a.halo_npeer = c->halo.npeer; }   // signal the previous step's halo rows
         const size_t smem = cell_smem_bytes(cs.max_halo, cs.max_elem, cs.stride);
         npart = cs.npatch;
@@ -999,7 +1000,7 @@ int wcfe_destroy(wcfe_ctx *c) {
         s.p_blob.release(); s.p_ring_blob.release(); s.p_ring_cyc.release(); s.p_elem_ptr.release(); s.p_elem_gid.release(); s.p_cand_l.release();
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release(); c->b_node_epoch.release(); c->cell_done.release();
-    c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release();
+    c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release(); c->d_loc_cache.release();
     c->d_kb.release(); c->d_seeds.release(); c->big_count.release(); c->big_list.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -1147,10 +1148,13 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
         CK(c->d_flags.alloc(nn * R)); CK(c->d_loc_bond.alloc(nn * R)); CK(c->d_loc_cnt.alloc(nn * R)); CK(c->d_loc_first.alloc(nn * R)); CK(c->d_ap_fire.alloc(nn * R));
         CK(cudaMemset(c->d_flags.p, 0, sizeof(int) * nn)); CK(cudaMemset(c->d_loc_bond.p, 0xff, sizeof(int) * nn));
         CK(cudaMemset(c->d_loc_cnt.p, 0, sizeof(int) * nn)); CK(cudaMemset(c->d_loc_first.p, 0xff, sizeof(int) * nn)); CK(cudaMemset(c->d_ap_fire.p, 0, sizeof(int) * nn));
+        CK(c->d_loc_cache.alloc((size_t)4 * s.np * R));
+        CK(cudaMemset(c->d_loc_cache.p, 0xff, sizeof(double2) * c->d_loc_cache.n));      // triangle id -1: nothing cached
         CK(c->d_partials.alloc((size_t)4 * ((nn + kBlock - 1) / kBlock + 1) * R));
         update_box(c, xyz, nn);
     } else {
         s.X.release();
+        if (c->d_loc_cache.p) CK(cudaMemset(c->d_loc_cache.p, 0xff, sizeof(double2) * c->d_loc_cache.n));   // cached triangles describe the old substrate
         if ((rc = build_grid(c, xyz))) return rc;
         if ((rc = build_patches(c, surface, cand))) return rc;
     }
@@ -1168,16 +1172,10 @@ int wcfe_mesh_sizes(wcfe_ctx *c, int surface, int *nn, int *ne) {
     return WCFE_OK;
 }
 
-int wcfe_upload_state(wcfe_ctx *c, int surface, int field, const double *host) {
-    if (!c || surface < 0 || surface > 1 || !host) return WCFE_ERR_ARG;
-    if (field == WCFE_F_XPREV && surface != WCFE_CELL) return fail(c, WCFE_ERR_ARG, "X_prev of the frozen substrate is its position");
+// what an upload of `field` implies beyond the copy itself (shared by wcfe_upload_state and wcfe_upload_states)
+static int after_upload(wcfe_ctx *c, int surface, int field, const double *host) {
     Surface &s = c->s[surface];
-    double *dev = field_dev(c, surface, field);
-    const int w = width_of(field);
-    if (!s.nn || !dev || !w) return fail(c, WCFE_ERR_ARG, "upload_state: no such field on this surface (or no mesh)");
-    CK(cudaSetDevice(c->device));
-    int rc = put_field(c, dev, host, s.nn, s.np, w);
-    if (rc) return rc;
+    int rc;
     // the planar fast path needs every out-of-plane word to be zero (strains: within kPlanarStrainEps, see planar_strain)
     if (c->nrep == 1) {      // (a batched context runs the planar step only and refuses anything else at launch)
         if (field == WCFE_F_X || field == WCFE_F_XPREV || field == WCFE_F_V || field == WCFE_F_A || field == WCFE_F_FAU) {
@@ -1190,8 +1188,88 @@ int wcfe_upload_state(wcfe_ctx *c, int surface, int field, const double *host) {
     if (field == WCFE_F_EA) CK(cudaMemcpyAsync(rsel(c, s.ea[s.ea_cur ^ 1]), rsel(c, s.ea[s.ea_cur]), sizeof(double) * 6 * s.np, cudaMemcpyDeviceToDevice, c->stream));
     if (field == WCFE_F_X) {
         if (surface == WCFE_CELL) { CK(cudaMemcpyAsync(rsel(c, s.X), rsel(c, s.x), sizeof(double) * 3 * s.np, cudaMemcpyDeviceToDevice, c->stream)); update_box(c, host, s.nn); }
-        else { rc = build_grid(c, host); if (rc) return rc; }
+        else {
+            if (c->d_loc_cache.p) CK(cudaMemsetAsync(c->d_loc_cache.p, 0xff, sizeof(double2) * c->d_loc_cache.n, c->stream));   // cached vertex positions are stale
+            rc = build_grid(c, host); if (rc) return rc;
+        }
     }
+    return WCFE_OK;
+}
+
+int wcfe_upload_state(wcfe_ctx *c, int surface, int field, const double *host) {
+    if (!c || surface < 0 || surface > 1 || !host) return WCFE_ERR_ARG;
+    if (field == WCFE_F_XPREV && surface != WCFE_CELL) return fail(c, WCFE_ERR_ARG, "X_prev of the frozen substrate is its position");
+    Surface &s = c->s[surface];
+    double *dev = field_dev(c, surface, field);
+    const int w = width_of(field);
+    if (!s.nn || !dev || !w) return fail(c, WCFE_ERR_ARG, "upload_state: no such field on this surface (or no mesh)");
+    CK(cudaSetDevice(c->device));
+    int rc = put_field(c, dev, host, s.nn, s.np, w);
+    if (rc) return rc;
+    return after_upload(c, surface, field, host);
+}
+
+// several fields of one surface in ONE transfer each way: the host images are packed into the pinned staging buffer, cross the bus
+// in a single cudaMemcpyAsync, are transposed on the device, and the stream is synchronised once (the adapter moves 11 fields up
+// and 9 down per step: 20 round trips of ~25 us each on the example meshes became 6)
+int wcfe_upload_states(wcfe_ctx *c, int surface, int n_fields, const int *fields, const double *const *host) {
+    if (!c || surface < 0 || surface > 1 || n_fields < 0 || (n_fields && (!fields || !host))) return WCFE_ERR_ARG;
+    Surface &s = c->s[surface];
+    if (!s.nn) return fail(c, WCFE_ERR_ARG, "upload_states: no mesh on this surface");
+    CK(cudaSetDevice(c->device));
+    size_t tot_h = 0, tot_d = 0;
+    for (int q = 0; q < n_fields; q++) {
+        const int w = width_of(fields[q]);
+        if (!w || !host[q] || !field_dev(c, surface, fields[q]) || (fields[q] == WCFE_F_XPREV && surface != WCFE_CELL))
+            return fail(c, WCFE_ERR_ARG, "upload_states: no such field on this surface");
+        tot_h += (size_t)w * s.nn; tot_d += (size_t)w * s.np;
+    }
+    if (!n_fields) return WCFE_OK;
+    int rc = ensure_stage(c, sizeof(double) * tot_h);
+    if (rc) return rc;
+    if ((rc = ensure_aos(c, tot_d))) return rc;
+    size_t off = 0;
+    for (int q = 0; q < n_fields; q++) { const size_t cnt = (size_t)width_of(fields[q]) * s.nn; memcpy(c->h_stage + off, host[q], sizeof(double) * cnt); off += cnt; }
+    CK(cudaMemcpyAsync(c->d_aos.p, c->h_stage, sizeof(double) * tot_h, cudaMemcpyHostToDevice, c->stream));
+    off = 0;
+    for (int q = 0; q < n_fields; q++) {
+        const int w = width_of(fields[q]);
+        // (fields are processed in order: an X upload redirects X_prev to x, a later X_prev entry overrides it, as with single uploads)
+        k_aos_to_soa<<<aos_grid((size_t)w * s.np), kBlock, 0, c->stream>>>(s.nn, s.np, w, c->d_aos.p + off, field_dev(c, surface, fields[q]));
+        CK(cudaGetLastError());
+        if ((rc = after_upload(c, surface, fields[q], host[q]))) return rc;
+        off += (size_t)w * s.nn;
+    }
+    CK(cudaStreamSynchronize(c->stream));      // the staging buffer may be refilled by the next call
+    return WCFE_OK;
+}
+
+int wcfe_download_states(wcfe_ctx *c, int surface, int n_fields, const int *fields, double *const *host) {
+    if (!c || surface < 0 || surface > 1 || n_fields < 0 || (n_fields && (!fields || !host))) return WCFE_ERR_ARG;
+    Surface &s = c->s[surface];
+    if (!s.nn) return fail(c, WCFE_ERR_ARG, "download_states: no mesh on this surface");
+    CK(cudaSetDevice(c->device));
+    size_t tot = 0;
+    for (int q = 0; q < n_fields; q++) {
+        const int w = width_of(fields[q]);
+        if (!w || !host[q] || !field_dev(c, surface, fields[q])) return fail(c, WCFE_ERR_ARG, "download_states: no such field on this surface");
+        tot += (size_t)w * s.nn;
+    }
+    if (!n_fields) return WCFE_OK;
+    int rc = ensure_stage(c, sizeof(double) * tot);
+    if (rc) return rc;
+    if ((rc = ensure_aos(c, tot))) return rc;
+    size_t off = 0;
+    for (int q = 0; q < n_fields; q++) {
+        const int w = width_of(fields[q]);
+        k_soa_to_aos<<<aos_grid((size_t)w * s.nn), kBlock, 0, c->stream>>>(s.nn, s.np, w, field_dev(c, surface, fields[q]), c->d_aos.p + off);
+        CK(cudaGetLastError());
+        off += (size_t)w * s.nn;
+    }
+    CK(cudaMemcpyAsync(c->h_stage, c->d_aos.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    off = 0;
+    for (int q = 0; q < n_fields; q++) { const size_t cnt = (size_t)width_of(fields[q]) * s.nn; memcpy(host[q], c->h_stage + off, sizeof(double) * cnt); off += cnt; }
     return WCFE_OK;
 }
 
@@ -1716,3 +1794,48 @@ int wcfe_sync(wcfe_ctx *c) {
 }
 
 }   // extern "C"
+
+// ---- self test: the division-free quotients of wcfe_math.cuh against the compiler's IEEE division, on the device ------------------
+namespace {
+__global__ void k_selftest_quotient(long long n, unsigned int seed, unsigned long long *mismatch) {
+    unsigned long long bad = 0;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        // operands of the ranges the step divides: denominators 1e-12 .. 1e12 (areas, masses, concentrations, lengths), numerators
+        // 0 (one in eight), tiny, ordinary, either sign
+        const unsigned int r0 = philox_u32(seed, (unsigned int)(q >> 32), (unsigned int)q), r1 = philox_u32(seed ^ 0x9E3779B9u, (unsigned int)(q >> 32), (unsigned int)q);
+        const unsigned int r2 = philox_u32(seed + 77u, (unsigned int)(q >> 32), (unsigned int)q), r3 = philox_u32(seed + 1234567u, (unsigned int)(q >> 32), (unsigned int)q);
+        const double mb = 1.0 + (double)r0 * (1.0 / 4294967296.0) + (double)(r1 & 0xFFFFFu) * (1.0 / 4503599627370496.0);
+        const double ma = 1.0 + (double)r2 * (1.0 / 4294967296.0) + (double)(r3 & 0xFFFFFu) * (1.0 / 4503599627370496.0);
+        const int eb = (int)((r1 >> 20) % 81u) - 40, ea = (int)((r3 >> 20) % 121u) - 60;
+        double b = ldexp(mb, eb), a = ldexp(ma, ea);
+        if ((r1 >> 27) & 1u) b = -b;
+        if ((r3 >> 28) & 1u) a = -a;
+        if (((r3 >> 29) & 7u) == 0u) a = ((r3 >> 28) & 1u) ? -0.0 : 0.0;
+        if ((q & 15) == 0) b = 3.0;                                                     // the reference's x / 3 (UL:1251)
+        const double want = a / b, got = div_rn(a, b);
+        // bit for bit, except the sign of a zero quotient (a == -0, b > 0 gives +0: the residual correction adds +0 to -0) -- a
+        // distinction no expression of the step can observe
+        if (__double_as_longlong(want) != __double_as_longlong(got) && !(want == 0.0 && got == 0.0)) bad++;
+        const Recip rb = recip_of(b);
+        const double got2 = quot(a, rb);
+        if (__double_as_longlong(got2) != __double_as_longlong(want) && !(want == 0.0 && got2 == 0.0)) bad++;
+    }
+    if (bad) atomicAdd(mismatch, bad);
+}
+}   // namespace
+
+int wcfe_selftest_quotient(int device, long long n, unsigned int seed, long long *mismatch) {
+    wcfe_ctx *c = nullptr;
+    if (!mismatch || n < 0) return fail(c, WCFE_ERR_ARG, "wcfe_selftest_quotient: bad argument");
+    CK(cudaSetDevice(device));
+    unsigned long long *d = nullptr, h = 0;
+    CK(cudaMalloc((void **)&d, sizeof(unsigned long long)));
+    CK(cudaMemset(d, 0, sizeof(unsigned long long)));
+    k_selftest_quotient<<<592, 256>>>(n, seed, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(c, WCFE_ERR_CUDA, std::string("wcfe_selftest_quotient: ") + cudaGetErrorString(e));
+    *mismatch = (long long)h;
+    return WCFE_OK;
+}

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_subs_patch(SurfView s, Pa
         if (Xi0 < -k.pin_limit || Xi0 > k.pin_limit) Vh0 = 0.0;
         if (Xi1 > k.pin_limit || Xi1 < -k.pin_limit) Vh1 = 0.0;
     }
-    const double imm = 1.0 / mm;                                                          // one reciprocal for the five quotients
+    const double imm = div_rn(1.0, mm);                                                   // one reciprocal for the five quotients
     node_update_r(Fx - rx, mm, imm, k.damp, k.rho, dt, dt_real, Vh0, V0, A0v);            // UL:471-503
     node_update_r(Fy - ry, mm, imm, k.damp, k.rho, dt, dt_real, Vh1, V1, A1v);
     s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
@@ -334,6 +334,159 @@ __device__ __noinline__ void halo_wait(const unsigned long long *flags, const Ha
     }
 }
 
+// ---- what one owned node does once its patch's node table is complete ----------------------------------------------------------
+// The table holds, per local node (owned first, halo after), (x, y), (e_xx, e_yy) and e_xy as stored in global memory.
+struct RingTable { const double2 *sxy, *se01; const double *se3; };
+
+template <bool DBG, bool HALO>
+__device__ __forceinline__ void ring_node(const SurfView &s, const PatchView &pv, const SurfView &c, const BucketView &bk, const Consts &k,
+                                          double dt, double dt_real, double t_tot, double bx0, double bx1, double by0, double by1,
+                                          const DebugView &dbg, const HaloView &hv, double dt_drv, const RingTable T,
+                                          const unsigned char *valence, const ushort2 *rjk, int p, int tid, int i, int nrole, bool zero_list,
+                                          double V0, double V1, double A0v, double A1v) {
+    const int np = s.np;
+    const double2 *sxy = T.sxy, *se01 = T.se01;
+    const double *se3 = T.se3;
+    const double2 myxy = sxy[tid], mye01 = se01[tid];
+    const double ea0 = mye01.x, ea1 = mye01.y, ea3 = se3[tid];
+    double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
+    const int nring = valence[tid];
+    // one incident element, with this node as local vertex 0 and (j, k) the other two in cyclic order.
+    // Frozen substrate, F == I (UL:988-1174 specialised, wcfe_math.cuh elem_eval_frozen), with a = I - 2 e_avg, b01 = -a01:
+    //   S = mu (a^-1 - det(a) I),  Re_0 = -(t/2) sign(W) S (d x, d y),  Re_ea = (e_avg - ea_0) A0 t / 3,  MM = A0 t / 3
+    // written so that every scale factor rides on the accumulating multiply-add.  I - 2 e_avg = 1 - (2/3)(e_i + e_j + e_k): the
+    // own node's share is formed once, the neighbours' enter through one addition and one multiply-add per component.
+    struct Nb { double2 p, t; double t3; };
+    auto load_nb = [&](int l) { Nb n; n.p = sxy[l]; n.t = se01[l]; n.t3 = se3[l]; return n; };
+    const double two3 = 2.0 / 3.0;
+    // every product and sum below is contracted BY HAND (__dmul_rn / fma): this routine is instantiated in several kernels, and
+    // a strip of a partitioned run must equal the whole mesh on one GPU bit for bit whatever each instantiation's compiler pass
+    // would have fused
+    const double c0 = __dsub_rn(1.0, __dmul_rn(two3, ea0)), c1 = __dsub_rn(1.0, __dmul_rn(two3, ea1)), c3 = __dmul_rn(two3, ea3);   // own node's share of a00, a11, b01
+    const double A0c = __dsub_rn(1.0, __dmul_rn(2.0, ea0)), A1c = __dsub_rn(1.0, __dmul_rn(2.0, ea1)), B3c = __dmul_rn(2.0, ea3);   // a at e_avg == ea_own: Re_ea vanishes there
+    const double mh = __dmul_rn(__dmul_rn(0.5, k.mu_subs), k.thick), cw = div_rn(k.thick, 6.0), cwh = div_rn(k.thick, 12.0);
+    struct Contrib { double f1, f2, m, a00, a11, b01, aw; };
+    auto entry = [&](const Nb &J, const Nb &K) {
+        Contrib c;
+        c.a00 = fma(-two3, __dadd_rn(J.t.x, K.t.x), c0); c.a11 = fma(-two3, __dadd_rn(J.t.y, K.t.y), c1); c.b01 = fma(two3, __dadd_rn(J.t3, K.t3), c3);
+        const double G1x = __dsub_rn(J.p.x, myxy.x), G1y = __dsub_rn(J.p.y, myxy.y), G2x = __dsub_rn(K.p.x, myxy.x), G2y = __dsub_rn(K.p.y, myxy.y);
+        const double Wz = fma(G1x, G2y, -__dmul_rn(G1y, G2x));
+        const double det2 = fma(c.a00, c.a11, -__dmul_rn(c.b01, c.b01));
+        const double idet = rcp_newton(det2);
+        const double dx = __dsub_rn(G2y, G1y), dy = __dsub_rn(G1x, G2x);
+        c.f1 = fma(idet, fma(c.a11, dx, __dmul_rn(c.b01, dy)), -__dmul_rn(det2, dx));                // (S / mu) (dx, dy)
+        c.f2 = fma(idet, fma(c.b01, dx, __dmul_rn(c.a00, dy)), -__dmul_rn(det2, dy));
+        c.m = Wz > 0 ? -mh : mh;                                           // -(t/2) mu sign(W)
+        c.aw = fabs(Wz);                                                   // 2 A0
+        return c;
+    };
+    auto add = [&](const Contrib &c) {
+        rx = fma(c.m, c.f1, rx); ry = fma(c.m, c.f2, ry);
+        mm = fma(c.aw, cw, mm);                                            // UL:1172
+        const double wh = __dmul_rn(c.aw, cwh);                            // A0 t / 6: (e_avg - ea) = (a_own - a) / 2
+        q0 = fma(__dsub_rn(A0c, c.a00), wh, q0); q1 = fma(__dsub_rn(A1c, c.a11), wh, q1); q3 = fma(__dsub_rn(c.b01, B3c), wh, q3);   // UL:1170 with e_s == e for F == I
+    };
+    // The fan is walked two elements at a time: their dependency chains (loads -> strain -> determinant -> reciprocal -> stress)
+    // are independent, which doubles the instruction-level parallelism of a loop that is otherwise latency bound.
+    // (keeping a closed fan's first neighbour in registers for its last element was measured: 0.188 -> 0.224 ms, the selects and
+    // the ten extra live registers cost more than the saved table read.)
+    int lastk = -1;
+    Nb prev = {make_double2(0, 0), make_double2(0, 0), 0.0};
+    int r = 0;
+    for (; r + 1 < nring; r += 2) {
+        const ushort2 jkA = rjk[r * kPatch + tid], jkB = rjk[(r + 1) * kPatch + tid];
+        const Nb JA = (int)jkA.x == lastk ? prev : load_nb(jkA.x);
+        const Nb KA = load_nb(jkA.y);
+        const Nb JB = jkB.x == jkA.y ? KA : load_nb(jkB.x);
+        const Nb KB = load_nb(jkB.y);
+        const Contrib cA = entry(JA, KA), cB = entry(JB, KB);
+        add(cA); add(cB);
+        prev = KB; lastk = jkB.y;
+    }
+    if (r < nring) {
+        const ushort2 jk = rjk[r * kPatch + tid];
+        const Nb J = (int)jk.x == lastk ? prev : load_nb(jk.x);
+        const Nb K = load_nb(jk.y);
+        add(entry(J, K));
+    }
+    const double Xi0 = myxy.x, Xi1 = myxy.y;
+    double Fx = 0.0, Fy = 0.0;
+    // one thread always waits: this kernel's completion then implies that of the boundary finish, which the next cell kernel
+    // (chained behind this kernel only) depends on; it also re-zeroes the triangle list k_bucket_reduce has consumed
+    if (zero_list) { pdl_wait(); if (bk.big_count) *bk.big_count = 0; }
+    if (HALO && nrole == 1) return;          // ghost node (incomplete fan): its owner computes it and stores the result here
+    unsigned int stamp = bk.epoch - 1u;
+    if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
+        // first touch of what the cell kernel produced (stamps, buckets, anchor records); all above overlaps its tail
+        if (bk.wait_cell) {
+            if (ld_acquire_gpu(bk.cell_done) < bk.cell_target) {        // all CTAs of this step's cell kernel are resident or done: bounded anyway
+                const unsigned long long t0 = global_ns();
+                while (ld_acquire_gpu(bk.cell_done) < bk.cell_target) {
+                    if (global_ns() - t0 > 2000000000ull) { atomicOr(bk.chain_err, ERR_CHAIN); break; }
+                    __nanosleep(32);
+                }
+            }
+        } else pdl_wait();
+        stamp = bk.node_epoch[i];
+    }
+    if (stamp == bk.epoch) {      // an incident triangle received an anchor in this step (two thirds of the nodes in the box skip this)
+        // calculateForce_FA_subs (UL:1297-1454) as a gather: k_bucket_reduce has formed, for every triangle that holds anchors, the
+        // six sums  sum_anchors H (A_j / A_tri)  (anchors in ascending cell-node order) and parked them in the triangle's own item
+        // storage; this node adds the one of its slot, triangles in fan order.  element id -> bucket head -> sums are dependent
+        // global loads: fetched for four incident triangles at a time.
+        const int gb = s.ring_ptr[i];
+        for (int r0 = 0; r0 < nring; r0 += 4) {
+            int code4[4]; unsigned long long h4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) code4[u] = r0 + u < nring ? pv.ring_cyc[gb + r0 + u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; u++) h4[u] = code4[u] >= 0 ? bk.head[code4[u] >> 2] : 0ull;
+            double2 f4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const bool on = code4[u] >= 0 && (unsigned int)(h4[u] >> 32) == bk.epoch;
+                f4[u] = on ? reinterpret_cast<const double2 *>(bk.items + (size_t)(code4[u] >> 2) * bk.cap)[code4[u] & 3] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) { Fx = __dadd_rn(Fx, f4[u].x); Fy = __dadd_rn(Fy, f4[u].y); }      // (+0 for the triangles without anchors)
+        }
+    }
+    double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt_drv / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt_drv / 2.0, A1v));   // UL:295, with the dt the driver was called with
+    if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {            // UL:298-341, Vbiax == 0
+        if (Xi0 < -k.pin_limit || Xi0 > k.pin_limit) Vh0 = 0.0;
+        if (Xi1 > k.pin_limit || Xi1 < -k.pin_limit) Vh1 = 0.0;
+    }
+    // UL:471-503 with one reciprocal of the lumped mass for the five quotients, hand-contracted like the walk
+    const double imm = div_rn(1.0, mm), ir = div_rn(imm, k.rho), dmr = __dmul_rn(__dmul_rn(k.damp, mm), k.rho);
+    const double hdt = dt / 2.0, ddt = __dsub_rn(dt_real, hdt);
+    A0v = __dmul_rn(fma(-dmr, V0, __dsub_rn(Fx, rx)), ir);
+    A1v = __dmul_rn(fma(-dmr, V1, __dsub_rn(Fy, ry)), ir);
+    V0 = dt_real > hdt ? fma(ddt, A0v, Vh0) : fma(dt_real, A0v, V0);
+    V1 = dt_real > hdt ? fma(ddt, A1v, Vh1) : fma(dt_real, A1v, V1);
+    s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
+    const double en0 = fma(q0, imm, ea0), en1 = fma(q1, imm, ea1), en3 = fma(q3, imm, ea3);
+    s.ea_out[i] = en0; s.ea_out[np + i] = en1; s.ea_out[3 * np + i] = en3;
+    if (HALO && nrole == 2) {
+        // border node: the same three words go straight into the ghost row of every neighbour that mirrors it (signalled by the
+        // next kernel in the stream, halo_signal)
+        for (int q = hv.exp_ptr[p]; q < hv.exp_ptr[p + 1]; q++) {
+            if (hv.exp_ent[3 * q] != tid) continue;
+            const HaloPeer *pr = hv.peer + hv.exp_ent[3 * q + 1];
+            const long long row = hv.exp_ent[3 * q + 2], rnp = pr->np;
+            double *dst = pr->ea[hv.step & 1];
+            dst[row] = en0; dst[rnp + row] = en1; dst[3 * rnp + row] = en3;
+        }
+    }
+    if (DBG) {
+        dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
+        dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
+    }
+}
+
+// ---- one CTA per patch.  (A persistent, software-pipelined form -- every CTA with three patches in flight: descriptor + owned
+//      rows of patch j+2 by cp.async.bulk, halo rows of patch j+1 by cp.async/LDGSTS into a second node table, fans of patch j --
+//      was built and measured in round 2: 0.198 ms against 0.185 ms for this form; the three barriers per patch and the table fill
+//      on every iteration's critical path cost more than the hidden latencies return.  profiles/r02_notes.md.) -----------------
 template <bool DBG, bool BATCH = false, bool HALO = false>
 __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView s, PatchView pv, SurfView c, BucketView bk, Consts k_, double dt, double dt_real,
                                                          double t_tot, double bx0, double bx1, double by0, double by1, DebugView dbg, BatchView bt, HaloView hv, double dt_drv) {
@@ -385,157 +538,27 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     const int *halo_ids = (const int *)(sblob + pv.roff_halo);
     const unsigned char *valence = sblob + pv.roff_rptr;
     const ushort2 *rjk = (const ushort2 *)(sblob + pv.roff_jk);          // [step][node]: conflict-free across a warp
-    const double2 myxy = make_double2(stage[tid], stage[kPatch + tid]), mye01 = make_double2(stage[2 * kPatch + tid], stage[3 * kPatch + tid]);
-    const double mye3 = stage[4 * kPatch + tid];
-    // shared memory holds t = (2/3) e per node: the element's I - 2 e_avg is then 1 - (t_i + t_j + t_k), two additions per
-    // component instead of the average plus a multiply-add (the FP64 pipe, not HBM, is what this kernel saturates first)
-    const double two3 = 2.0 / 3.0;
-    sxy[tid] = myxy; se01[tid] = make_double2(two3 * mye01.x, two3 * mye01.y); se3[tid] = two3 * mye3;
+    sxy[tid] = make_double2(stage[tid], stage[kPatch + tid]); se01[tid] = make_double2(stage[2 * kPatch + tid], stage[3 * kPatch + tid]); se3[tid] = stage[4 * kPatch + tid];
     if (HALO && (prole & 1)) {
         // ghost rows were written by a peer GPU into L2 while this kernel was already running: read them past the (incoherent) L1
         for (int l = tid; l < nh; l += kPatch) {
             const int g = halo_ids[l];
             sxy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
-            se01[kPatch + l] = make_double2(two3 * __ldcg(s.ea_in + g), two3 * __ldcg(s.ea_in + np + g));
-            se3[kPatch + l] = two3 * __ldcg(s.ea_in + 3 * (size_t)np + g);
+            se01[kPatch + l] = make_double2(__ldcg(s.ea_in + g), __ldcg(s.ea_in + np + g));
+            se3[kPatch + l] = __ldcg(s.ea_in + 3 * (size_t)np + g);
         }
     } else {
         for (int l = tid; l < nh; l += kPatch) {
             const int g = halo_ids[l];
             sxy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
-            se01[kPatch + l] = make_double2(two3 * s.ea_in[g], two3 * s.ea_in[np + g]);
-            se3[kPatch + l] = two3 * s.ea_in[3 * (size_t)np + g];
+            se01[kPatch + l] = make_double2(s.ea_in[g], s.ea_in[np + g]);
+            se3[kPatch + l] = s.ea_in[3 * (size_t)np + g];
         }
     }
     __syncthreads();
     if (!own) return;
-    const double ea0 = mye01.x, ea1 = mye01.y, ea3 = mye3;
-    double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
-    const int nring = valence[tid];
-    // one incident element, with this node as local vertex 0 and (j, k) the other two in cyclic order.
-    // Frozen substrate, F == I (UL:988-1174 specialised, wcfe_math.cuh elem_eval_frozen), with a = I - 2 e_avg, b01 = -a01:
-    //   S = mu (a^-1 - det(a) I),  Re_0 = -(t/2) sign(W) S (d x, d y),  Re_ea = (e_avg - ea_0) A0 t / 3,  MM = A0 t / 3
-    // written so that every scale factor rides on the accumulating multiply-add.
-    struct Nb { double2 p, t; double t3; };
-    auto load_nb = [&](int l) { Nb n; n.p = sxy[l]; n.t = se01[l]; n.t3 = se3[l]; return n; };
-    // rounded products, as stored in the table for the neighbours (left to the compiler, 1 - two3*ea was fused in one template
-    // instantiation and built from the table's rounded product in another: a last-bit difference between a strip and the whole mesh)
-    const double c0 = __dsub_rn(1.0, __dmul_rn(two3, ea0)), c1 = __dsub_rn(1.0, __dmul_rn(two3, ea1)), c3 = __dmul_rn(two3, ea3);   // own node's share of a00, a11, b01
-    const double A0c = 1.0 - 2.0 * ea0, A1c = 1.0 - 2.0 * ea1, B3c = 2.0 * ea3;            // a at e_avg == ea_own: Re_ea vanishes there
-    const double mh = 0.5 * k.mu_subs * k.thick, cw = k.thick / 6.0, cwh = k.thick / 12.0;
-    struct Contrib { double f1, f2, m, a00, a11, b01, aw; };
-    auto entry = [&](const Nb &J, const Nb &K) {
-        Contrib c;
-        c.a00 = c0 - (J.t.x + K.t.x); c.a11 = c1 - (J.t.y + K.t.y); c.b01 = c3 + (J.t3 + K.t3);
-        const double G1x = J.p.x - myxy.x, G1y = J.p.y - myxy.y, G2x = K.p.x - myxy.x, G2y = K.p.y - myxy.y;
-        // every two-product expression is contracted BY HAND (one rounded product, one fused multiply-add): left to the compiler the
-        // choice of which product to fuse differed between template instantiations of this kernel, and a strip of a partitioned run
-        // (HALO instantiation) stopped matching the single-GPU run in the last bit
-        const double Wz = fma(G1x, G2y, -__dmul_rn(G1y, G2x));
-        const double det2 = fma(c.a00, c.a11, -__dmul_rn(c.b01, c.b01));
-        const double idet = rcp_newton(det2);
-        const double dx = G2y - G1y, dy = G1x - G2x;
-        c.f1 = fma(idet, fma(c.a11, dx, __dmul_rn(c.b01, dy)), -__dmul_rn(det2, dx));                // (S / mu) (dx, dy)
-        c.f2 = fma(idet, fma(c.b01, dx, __dmul_rn(c.a00, dy)), -__dmul_rn(det2, dy));
-        c.m = Wz > 0 ? -mh : mh;                                           // -(t/2) mu sign(W)
-        c.aw = fabs(Wz);                                                   // 2 A0
-        return c;
-    };
-    auto add = [&](const Contrib &c) {
-        rx = fma(c.m, c.f1, rx); ry = fma(c.m, c.f2, ry);
-        mm = fma(c.aw, cw, mm);                                            // UL:1172
-        const double wh = c.aw * cwh;                                      // A0 t / 6: (e_avg - ea) = (a_own - a) / 2
-        q0 = fma(A0c - c.a00, wh, q0); q1 = fma(A1c - c.a11, wh, q1); q3 = fma(c.b01 - B3c, wh, q3);   // UL:1170 with e_s == e for F == I
-    };
-    // The fan is walked two elements at a time: their dependency chains (loads -> strain -> determinant -> reciprocal -> stress)
-    // are independent, which doubles the instruction-level parallelism of a loop that is otherwise latency bound.
-    int lastk = -1;
-    Nb prev = {make_double2(0, 0), make_double2(0, 0), 0.0};
-    int r = 0;
-    for (; r + 1 < nring; r += 2) {
-        const ushort2 jkA = rjk[r * kPatch + tid], jkB = rjk[(r + 1) * kPatch + tid];
-        const Nb JA = (int)jkA.x == lastk ? prev : load_nb(jkA.x);
-        const Nb KA = load_nb(jkA.y);
-        const Nb JB = jkB.x == jkA.y ? KA : load_nb(jkB.x);
-        const Nb KB = load_nb(jkB.y);
-        const Contrib cA = entry(JA, KA), cB = entry(JB, KB);
-        add(cA); add(cB);
-        prev = KB; lastk = jkB.y;
-    }
-    if (r < nring) {
-        const ushort2 jk = rjk[r * kPatch + tid];
-        const Nb J = (int)jk.x == lastk ? prev : load_nb(jk.x);
-        const Nb K = load_nb(jk.y);
-        add(entry(J, K));
-    }
-    const double Xi0 = myxy.x, Xi1 = myxy.y;
-    double Fx = 0.0, Fy = 0.0;
-    // one thread always waits: this kernel's completion then implies that of the boundary finish, which the next cell kernel
-    // (chained behind this kernel only) depends on; it also re-zeroes the big-bucket list k_bucket_reduce has consumed
-    if (blockIdx.x == 0 && tid == 0) { pdl_wait(); if (bk.big_count) *bk.big_count = 0; }
-    if (HALO && nrole == 1) return;          // ghost node (incomplete fan): its owner computes it and stores the result here
-    unsigned int stamp = bk.epoch - 1u;
-    if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
-        // first touch of what the cell kernel produced (stamps, buckets, anchor records); all above overlaps its tail
-        if (bk.wait_cell) {
-            if (ld_acquire_gpu(bk.cell_done) < bk.cell_target) {        // all CTAs of this step's cell kernel are resident or done: bounded anyway
-                const unsigned long long t0 = global_ns();
-                while (ld_acquire_gpu(bk.cell_done) < bk.cell_target) {
-                    if (global_ns() - t0 > 2000000000ull) { atomicOr(bk.chain_err, ERR_CHAIN); break; }
-                    __nanosleep(32);
-                }
-            }
-        } else pdl_wait();
-        stamp = bk.node_epoch[i];
-    }
-    if (stamp == bk.epoch) {      // an incident triangle received an anchor in this step (two thirds of the nodes in the box skip this)
-        // calculateForce_FA_subs (UL:1297-1454) as a gather: k_bucket_reduce has formed, for every triangle that holds anchors, the
-        // six sums  sum_anchors H (A_j / A_tri)  (anchors in ascending cell-node order) and parked them in the triangle's own item
-        // storage; this node adds the one of its slot, triangles in fan order.  element id -> bucket head -> sums are dependent
-        // global loads: fetched for four incident triangles at a time.
-        const int gb = s.ring_ptr[i];
-        for (int r0 = 0; r0 < nring; r0 += 4) {
-            int code4[4]; unsigned long long h4[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) code4[u] = r0 + u < nring ? pv.ring_cyc[gb + r0 + u] : -1;
-#pragma unroll
-            for (int u = 0; u < 4; u++) h4[u] = code4[u] >= 0 ? bk.head[code4[u] >> 2] : 0ull;
-            double2 f4[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const bool on = code4[u] >= 0 && (unsigned int)(h4[u] >> 32) == bk.epoch;
-                f4[u] = on ? reinterpret_cast<const double2 *>(bk.items + (size_t)(code4[u] >> 2) * bk.cap)[code4[u] & 3] : make_double2(0.0, 0.0);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) { Fx += f4[u].x; Fy += f4[u].y; }      // (+0 for the triangles without anchors)
-        }
-    }
-    double Vh0 = WCFE_ADD(V0, WCFE_MUL(dt_drv / 2.0, A0v)), Vh1 = WCFE_ADD(V1, WCFE_MUL(dt_drv / 2.0, A1v));   // UL:295, with the dt the driver was called with
-    if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {            // UL:298-341, Vbiax == 0
-        if (Xi0 < -k.pin_limit || Xi0 > k.pin_limit) Vh0 = 0.0;
-        if (Xi1 > k.pin_limit || Xi1 < -k.pin_limit) Vh1 = 0.0;
-    }
-    const double imm = 1.0 / mm;
-    node_update_r(Fx - rx, mm, imm, k.damp, k.rho, dt, dt_real, Vh0, V0, A0v);            // UL:471-503
-    node_update_r(Fy - ry, mm, imm, k.damp, k.rho, dt, dt_real, Vh1, V1, A1v);
-    s.V[i] = V0; s.V[np + i] = V1; s.A[i] = A0v; s.A[np + i] = A1v;
-    const double en0 = ea0 + q0 * imm, en1 = ea1 + q1 * imm, en3 = ea3 + q3 * imm;
-    s.ea_out[i] = en0; s.ea_out[np + i] = en1; s.ea_out[3 * np + i] = en3;
-    if (HALO && nrole == 2) {
-        // border node: the same three words go straight into the ghost row of every neighbour that mirrors it (signalled by the
-        // next kernel in the stream, halo_signal)
-        for (int q = hv.exp_ptr[p]; q < hv.exp_ptr[p + 1]; q++) {
-            if (hv.exp_ent[3 * q] != tid) continue;
-            const HaloPeer *pr = hv.peer + hv.exp_ent[3 * q + 1];
-            const long long row = hv.exp_ent[3 * q + 2], rnp = pr->np;
-            double *dst = pr->ea[hv.step & 1];
-            dst[row] = en0; dst[rnp + row] = en1; dst[3 * rnp + row] = en3;
-        }
-    }
-    if (DBG) {
-        dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Fx; dbg.f_fa[np + i] = Fy; dbg.mm[i] = mm;
-        dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
-    }
+    ring_node<DBG, HALO>(s, pv, c, bk, k, dt, dt_real, t_tot, bx0, bx1, by0, by1, dbg, hv, dt_drv, RingTable{sxy, se01, se3}, valence, rjk, p, tid, i, nrole,
+                         blockIdx.x == 0 && tid == 0, V0, V1, A0v, A1v);
 }
 
 // ---- integrin force on the substrate, per triangle ---------------------------------------------------------------------------------
@@ -574,7 +597,8 @@ __global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s,
                 const double2 ap = anc2[2 * (size_t)ni], ah = anc2[2 * (size_t)ni + 1];
                 double Ar[3], At;                                                        // UL:1303-1340; planar form, bit-identical
                 point_in_triangle_2d(n1x, n1y, n2x, n2y, n3x, n3y, ap.x, ap.y, Ar, At);
-                const double w0 = Ar[0] / At, w1 = Ar[1] / At, w2 = Ar[2] / At;
+                const Recip rt = recip_of(At);
+                const double w0 = quot(Ar[0], rt), w1 = quot(Ar[1], rt), w2 = quot(Ar[2], rt);
                 a0 += ah.x * w0; a1 += ah.y * w0; a2 += ah.x * w1; a3 += ah.y * w1; a4 += ah.x * w2; a5 += ah.y * w2;   // UL:1414-1422
             }
             double2 *o = reinterpret_cast<double2 *>(items);      // this thread alone reads and writes the bucket
@@ -602,8 +626,9 @@ __global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s,
                 double Ar[3], At;
                 point_in_triangle_2d(n1[0], n1[1], n2[0], n2[1], n3[0], n3[1], ap.x, ap.y, Ar, At);     // planar form, bit-identical
                 double *t6 = tw[rank - w0];
+                const Recip rt = recip_of(At);
 #pragma unroll
-                for (int j = 0; j < 3; j++) { const double w = Ar[j] / At; t6[2 * j] = ah.x * w; t6[2 * j + 1] = ah.y * w; }
+                for (int j = 0; j < 3; j++) { const double w = quot(Ar[j], rt); t6[2 * j] = ah.x * w; t6[2 * j + 1] = ah.y * w; }
             }
             __syncwarp();
             if (lane < 6) {
@@ -633,6 +658,11 @@ struct CellStepArgs {
     const unsigned int *tape;
     double *partials;
     int *d_flags, *d_loc_bond, *d_loc_cnt, *d_loc_first, *d_ap_fire, *err;
+    // per cell node, the substrate triangle its anchor was found in last: [4][np] double2 = (x1,y1) (x2,y2) (x3,y3) and, as four
+    // ints, (triangle, v1, v2, v3); triangle < 0: nothing cached.  One coalesced read replaces the three dependent gathers
+    // loc_first -> tri -> x at the head of every CTA (16 % of the kernel's stall samples); a HINT only: a stale entry fails the
+    // strict containment test and the grid search takes over.  Valid while the substrate does not move (invalidated at upload).
+    double2 *loc_cache;
     int debug;
     const HaloPeer *halo_peer;      // partitioned run, not the first step: signal the previous step's halo rows (halo_signal)
     int halo_npeer;
@@ -640,7 +670,7 @@ struct CellStepArgs {
 
 // Shared memory: the seven node arrays in SoA (TMA destinations), element records as array-of-structs, kRec doubles per
 // element at a compile-time stride (one address computation per one-ring entry, immediate offsets for the nine loads).
-constexpr int kRec = 9;           // r1x r1y r2x r2y e_s.xx e_s.yy e_s.xy A0 a_cur
+constexpr int kRec = 9;           // r1x r1y r2x r2y e_s.xx e_s.yy e_s.xy w a3:  w = A0 t / 3 (UL:911-913), a3 = a_cur / 3 (UL:1251)
 __host__ __device__ inline size_t cell_smem_bytes(int max_halo, int max_elem, int stride) {
     const size_t NL = (size_t)kPatch + max_halo;
     return 16 + (size_t)stride + sizeof(double) * 7 * NL + sizeof(double) * kRec * (size_t)max_elem + 64;
@@ -668,6 +698,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         batch_shift(s, r); batch_shift(sub, r); batch_shift(bk, bt, r);
         b.buf += bt.bnd * r; a.partials += bt.partials * r;
         a.d_flags += bt.flags * r; a.d_loc_bond += bt.flags * r; a.d_loc_cnt += bt.flags * r; a.d_loc_first += bt.flags * r; a.d_ap_fire += bt.flags * r; a.err += r;
+        a.loc_cache += 4 * (size_t)s.np * r;
         if (bt.seed) a.seed = bt.seed[r];
         if (PREDICT) { x_in += n3; x_out += n3; }
         V_out += n3; A_out += n3;
@@ -708,18 +739,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     double V0 = 0, V1 = 0, Av0 = 0, Av1 = 0;      // own node's V, A (kept for the update)
     double fa0 = 0, fa1 = 0, cC = 0;
     int bi = -1;                                   // boundary ordinal of the own node
-    // the triangle the anchor was in at the previous step and its (frozen) vertices: loc_first -> tri -> x are three dependent
-    // global loads; issued here they complete behind the staging wait instead of after the bond update
+    // the triangle the anchor was in at the previous step and its (frozen) vertices, from the per-node cache: one coalesced load,
+    // in flight behind the staging wait
     int tprev = -1, tv0 = 0, tv1 = 0, tv2 = 0;
     double t1x = 0, t1y = 0, t2x = 0, t2y = 0, t3x = 0, t3y = 0;
     if (own) {
         V0 = s.V[i]; V1 = s.V[np + i]; Av0 = s.A[i]; Av1 = s.A[np + i]; fa0 = s.fa[i]; fa1 = s.fa[np + i]; cC = s.cC[i];
         bi = b.index[i];
-        tprev = a.d_loc_first[i];
-        if (tprev >= 0 && tprev < sub.ne) {
-            tv0 = sub.tri[tprev]; tv1 = sub.tri[sub.nep + tprev]; tv2 = sub.tri[2 * sub.nep + tprev];
-            t1x = sub.x[tv0]; t1y = sub.x[sub.np + tv0]; t2x = sub.x[tv1]; t2y = sub.x[sub.np + tv1]; t3x = sub.x[tv2]; t3y = sub.x[sub.np + tv2];
-        } else tprev = -1;
+        const double2 c0 = a.loc_cache[i], c1 = a.loc_cache[(size_t)np + i], c2 = a.loc_cache[2 * (size_t)np + i];
+        const int4 ci = *reinterpret_cast<const int4 *>(a.loc_cache + 3 * (size_t)np + i);
+        t1x = c0.x; t1y = c0.y; t2x = c1.x; t2y = c1.y; t3x = c2.x; t3y = c2.y;
+        tprev = ci.x; tv0 = ci.y; tv1 = ci.z; tv2 = ci.w;
+        if (tprev >= sub.ne) tprev = -1;
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -790,17 +821,30 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         bool done = false;
         if (tprev >= 0) {
             double Ar[3], At;      // planar path: z == 0 everywhere (checked at upload), the 2-D predicate is bit-identical to the 3-D one
-            if (point_in_triangle_2d(t1x, t1y, t2x, t2y, t3x, t3y, pt[0], pt[1], Ar, At) && Ar[0] > 0 && Ar[1] > 0 && Ar[2] > 0) {
+            // margin: within 1e-9 of an edge (relative sub-area) the reference's rounded predicate may ALSO accept the neighbour
+            // (A1 = A_tri - A2 - A3 is formed in floating point, UL:1338): such anchors take the grid search, which reports every
+            // accepting triangle; the margin is seven orders above the rounding it guards against
+            const bool in = point_in_triangle_2d(t1x, t1y, t2x, t2y, t3x, t3y, pt[0], pt[1], Ar, At);
+            const double mrg = 1e-9 * At;
+            if (in && Ar[0] > mrg && Ar[1] > mrg && Ar[2] > mrg) {
                 slot_prev = bucket_take_slot(bk, tprev);      // consumed after the element phase: the round trip hides behind it
                 cnt = 1; first = tprev; done = true;
             }
         }
         if (!done) {
             locate(g, sub, pt, [&](int t, const double *, double) {
-                if (cnt == 0) first = t;
+                const int v0 = sub.tri[t], v1 = sub.tri[sub.nep + t], v2 = sub.tri[2 * sub.nep + t];
+                if (cnt == 0) {          // the anchor changed triangle (or had none): remember the new one
+                    first = t;
+                    a.loc_cache[i] = make_double2(sub.x[v0], sub.x[sub.np + v0]);
+                    a.loc_cache[(size_t)np + i] = make_double2(sub.x[v1], sub.x[sub.np + v1]);
+                    a.loc_cache[2 * (size_t)np + i] = make_double2(sub.x[v2], sub.x[sub.np + v2]);
+                    *reinterpret_cast<int4 *>(a.loc_cache + 3 * (size_t)np + i) = make_int4(t, v0, v1, v2);
+                }
                 cnt++;
-                finish_insert(t, bucket_take_slot(bk, t), sub.tri[t], sub.tri[sub.nep + t], sub.tri[2 * sub.nep + t]);
+                finish_insert(t, bucket_take_slot(bk, t), v0, v1, v2);
             });
+            if (cnt == 0 && tprev >= 0) *reinterpret_cast<int4 *>(a.loc_cache + 3 * (size_t)np + i) = make_int4(-1, 0, 0, 0);
         }
         a.d_loc_cnt[i] = cnt; a.d_loc_first[i] = first;
     }
@@ -808,6 +852,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     // ---- elements: closed-form planar element from shared memory, one record per patch-local element; the thread that
     //      evaluates an element whose local vertex 0 this patch owns also counts it for calculateAreaTot (UL:1655-1661)
     const double tk = t_act_of(k, a.t_tot) * k.kappa;
+    const Recip r3 = recip_of(3.0);
     double red0 = 0.0, red1 = 0.0, red2 = 0.0;
     for (int el = tid; el < nel; el += kThreads) {
         const unsigned short *lv = elem_lv + 3 * el;
@@ -819,7 +864,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         ElemOut2 o;
         elem_eval_planar(X, x, e3, k.mu_cell, tk, k.thick, o);
         double *R = rec + kRec * el;
-        R[0] = o.r1[0]; R[1] = o.r1[1]; R[2] = o.r2[0]; R[3] = o.r2[1]; R[4] = o.eas[0]; R[5] = o.eas[1]; R[6] = o.eas[2]; R[7] = o.A0; R[8] = o.a_cur;
+        // what every incident node needs of A0 and a_cur is formed here once per element instead of once per (node, element)
+        R[0] = o.r1[0]; R[1] = o.r1[1]; R[2] = o.r2[0]; R[3] = o.r2[1]; R[4] = o.eas[0]; R[5] = o.eas[1]; R[6] = o.eas[2];
+        R[7] = __dmul_rn(__dmul_rn(1. / 3., o.A0), k.thick); R[8] = quot(o.a_cur, r3);
         if (n1 < kPatch) {
             red0 += o.a_cur;
             red1 += (1. / 3.) * ((x[0][0] + x[1][0]) + x[2][0]) * o.a_cur;
@@ -856,20 +903,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
             const int sA = cA & 3, sB = cB & 3;
             const double a0 = RA[0], a1 = RA[1], a2 = RA[2], a3 = RA[3], a4 = RA[4], a5 = RA[5], a6 = RA[6], a7 = RA[7], a8 = RA[8];
             const double b0 = RB[0], b1 = RB[1], b2 = RB[2], b3 = RB[3], b4 = RB[4], b5 = RB[5], b6 = RB[6], b7 = two ? RB[7] : 0.0, b8 = two ? RB[8] : 0.0;
+            // (explicit fma: the contraction must not depend on the template instantiation, batched and single runs compare bitwise)
             rx += sA == 0 ? -(a0 + a2) : (sA == 1 ? a0 : a2);
             ry += sA == 0 ? -(a1 + a3) : (sA == 1 ? a1 : a3);
-            q0 += (1. / 3.) * (a4 - ea0) * a7 * k.thick;               // UL:911
-            q1 += (1. / 3.) * (a5 - ea1) * a7 * k.thick;
-            q3 += (1. / 3.) * (a6 - ea3) * a7 * k.thick;
-            mm += (1. / 3.) * a7 * k.thick;                            // UL:913
-            asum += a8 / 3;                                            // UL:1251
+            q0 = fma(a4 - ea0, a7, q0);                                // UL:911
+            q1 = fma(a5 - ea1, a7, q1);
+            q3 = fma(a6 - ea3, a7, q3);
+            mm += a7;                                                  // UL:913
+            asum += a8;                                                // UL:1251
             const double fxB = sB == 0 ? -(b0 + b2) : (sB == 1 ? b0 : b2), fyB = sB == 0 ? -(b1 + b3) : (sB == 1 ? b1 : b3);
             rx += two ? fxB : 0.0; ry += two ? fyB : 0.0;
-            q0 += (1. / 3.) * (b4 - ea0) * b7 * k.thick;               // b7 == 0 without a second entry: +0
-            q1 += (1. / 3.) * (b5 - ea1) * b7 * k.thick;
-            q3 += (1. / 3.) * (b6 - ea3) * b7 * k.thick;
-            mm += (1. / 3.) * b7 * k.thick;
-            asum += b8 / 3;
+            q0 = fma(b4 - ea0, b7, q0);                                // b7 == 0 without a second entry: +0
+            q1 = fma(b5 - ea1, b7, q1);
+            q3 = fma(b6 - ea3, b7, q3);
+            mm += b7;
+            asum += b8;
         }
         double Vh0 = V0 + (a.dt_drv / 2.0) * Av0, Vh1 = V1 + (a.dt_drv / 2.0) * Av1;         // UL:118
         const double u[3] = {fa0, fa1, 0.0};
@@ -880,15 +928,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         s.asum[i] = asum;
         reinterpret_cast<double2 *>(s.anc)[2 * (size_t)i] = make_double2(anc_px, anc_py);
         reinterpret_cast<double2 *>(s.anc)[2 * (size_t)i + 1] = make_double2(-Ffx, -Ffy);
-        s.ea_out[i] = ea0 + q0 / mm; s.ea_out[np + i] = ea1 + q1 / mm; s.ea_out[3 * np + i] = ea3 + q3 / mm;   // UL:607-612
+        const Recip rmm = recip_of(mm), rmr = recip_of(mm * k.rho);      // shared by the three strain and the two acceleration quotients
+        s.ea_out[i] = ea0 + quot(q0, rmm); s.ea_out[np + i] = ea1 + quot(q1, rmm); s.ea_out[3 * np + i] = ea3 + quot(q3, rmm);   // UL:607-612
         if (DBG) {
             dbg.res[i] = rx; dbg.res[np + i] = ry; dbg.f_fa[i] = Ffx; dbg.f_fa[np + i] = Ffy; dbg.mm[i] = mm;
             dbg.res_ea[i] = q0; dbg.res_ea[np + i] = q1; dbg.res_ea[3 * np + i] = q3;
             dbg.f_ap[i] = 0.0; dbg.f_ap[np + i] = 0.0; dbg.f_bend[i] = 0.0; dbg.f_bend[np + i] = 0.0; dbg.f_area[i] = 0.0; dbg.f_area[np + i] = 0.0;
         }
         if (bi < 0) {
-            node_update(Fvx + Ffx - rx, mm, k.damp, k.rho, a.dt, a.dt_real, Vh0, V0, Av0);           // UL:592-628
-            node_update(Fvy + Ffy - ry, mm, k.damp, k.rho, a.dt, a.dt_real, Vh1, V1, Av1);
+            node_update_q(Fvx + Ffx - rx, mm, rmr, k.damp, k.rho, a.dt, a.dt_real, Vh0, V0, Av0);    // UL:592-628
+            node_update_q(Fvy + Ffy - ry, mm, rmr, k.damp, k.rho, a.dt, a.dt_real, Vh1, V1, Av1);
             // V, A go to the OTHER buffer: neighbouring patches still read this node's old V, A for their halo predictor
             V_out[i] = V0; V_out[np + i] = V1; A_out[i] = Av0; A_out[np + i] = Av1;
         } else {

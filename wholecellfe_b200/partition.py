@@ -300,3 +300,14 @@ class PartitionedSim:
     def owned_field(self, field):
         """(global node ids, values) of this rank's owned substrate nodes"""
         return self.part.owned, self.sim.get(self.SUBS, field)[self.part.owned_local]
+
+    def close(self):
+        """Collective.  The border rows of the LAST step are plain peer stores nobody has awaited yet: a rank that unmapped or
+        freed its strain buffers while a slower neighbour's final substrate kernel was still storing into them would fault the
+        neighbour.  Drain the own stream, meet everybody, only then disconnect and free (include/wcfe.h, wcfe_halo_disconnect)."""
+        if self.sim is None:
+            return
+        self.sim.sync()
+        self.dist.barrier()
+        self.sim.close()
+        self.sim = None

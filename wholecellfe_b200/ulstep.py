@@ -126,7 +126,7 @@ class ULSim:
         self._ck(self.L.wcfe_get_path_info(self.h, _d(out)))
         return {"planar": bool(out[0]), "cell_patch_elem_ratio": out[1], "subs_patch_elem_ratio": out[2], "cell_max_halo": int(out[3]),
                 "cell_max_elem": int(out[4]), "subs_max_halo": int(out[5]),
-                "subs_kernel": {2: "k_subs_ring", 0: "k_subs_patch", 1: "k_subs_pipe"}.get(int(out[6]), "?"), "bucket_cap": int(out[7])}
+                "subs_kernel": {2: "k_subs_ring", 0: "k_subs_patch"}.get(int(out[6]), "?"), "bucket_cap": int(out[7])}
 
     def set_debug(self, on):
         self._ck(self.L.wcfe_set_debug(self.h, 1 if on else 0))
