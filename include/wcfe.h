@@ -230,6 +230,42 @@ int wcfe_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_halo_info *peers, con
                       int n_export, const int *export_node, const int *export_peer, const int *export_row, int n_ghost, const int *ghost_node);
 int wcfe_halo_disconnect(wcfe_ctx *c);
 
+/* ---- the CELL of the same partitioned run.  Every rank uploads the WHOLE cell (same numbering, hence the same 128-node patches as on
+ * one GPU) but computes only a subset of the patches: those that can drop an anchor into its substrate strip; a patch on a cut is
+ * computed by both neighbours, bit-identically.  What a rank does not compute goes stale in its arrays -- except the nodes its own
+ * patches read as halo rows, which the rank that OWNS their patch stores, every step, into the same index of the reader's arrays
+ * through peer memory (from the cell kernel; V and A of boundary vertices from the boundary-finish kernel).  The area / centroid
+ * partial sums of every patch go from its owner into every rank's partials array, so that each rank forms the total area in the
+ * single-GPU order (UL:1641-1667, consumed at UL:589, :1757).  Two epoch counters per ordered pair of ranks pace all of it, in
+ * kernel; no host work per step.  Results equal the single-GPU run bit for bit on every row a rank computes.
+ *   wcfe_cell_halo_info_get   addresses + CUDA IPC handles of this context's cell buffers (ship as bytes to every other rank)
+ *   wcfe_cell_halo_connect    peers[q]: EVERY other rank; my_slot_at_peer[q]: this rank's index in q's peer list;
+ *                             patch_list: ascending patch ids this rank computes (at least one), patch_owned[k]: 1 where this rank
+ *                             publishes the patch's partial sums (every patch has exactly one owner across the ranks);
+ *                             export_node / export_peer: (node, peer slot) pairs -- nodes of OWNED patches the peer reads as halo
+ *                             rows; import_node: nodes this rank receives (halo rows of its patches that it does not compute);
+ *                             anchor_margin: the distance |fa_u| the patch lists allow an anchor to be from its node (an anchor
+ *                             beyond it raises WCFE_ERR_CAPACITY: it may lie under a strip whose rank does not compute the patch).
+ * After the connect the context advances with wcfe_step_n / wcfe_step_n_async only, all ranks by the same number of steps.  The same
+ * barriers as for the substrate apply: one after every rank's connect, one (after wcfe_sync) before any rank disconnects, destroys
+ * or re-uploads. */
+#define WCFE_CELL_HALO_NPTR 11
+typedef struct wcfe_cell_halo_info {
+    long long pid;
+    int device, reserved;
+    long long np;                                      /* pitch (doubles) of the cell's node arrays */
+    unsigned long long ptr[WCFE_CELL_HALO_NPTR];       /* x, V, A, ea as written by the next step and by the one after (8), partials of even /
+                                                          odd steps (2), counters (1) */
+    unsigned long long offset[WCFE_CELL_HALO_NPTR];
+    unsigned char ipc[WCFE_CELL_HALO_NPTR][64];
+} wcfe_cell_halo_info;
+int wcfe_cell_halo_info_get(wcfe_ctx *c, wcfe_cell_halo_info *out);
+int wcfe_cell_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_cell_halo_info *peers, const int *my_slot_at_peer,
+                           int n_patches, const int *patch_list, const int *patch_owned,
+                           int n_export, const int *export_node, const int *export_peer, int n_import, const int *import_node,
+                           double anchor_margin);
+int wcfe_cell_halo_disconnect(wcfe_ctx *c);
+
 /* Host-side helper (no GPU work, usable from any host language): cut ONE mesh into `world` vertical strips and produce, for
  * `rank`, the local strip to upload and the tables wcfe_halo_connect takes.  Nodes are sorted by x (ties by id) and cut into runs
  * of equal node count, or -- with one weight per node -- of equal total weight (nodes under the cell cost more: see

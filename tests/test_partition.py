@@ -207,6 +207,42 @@ def test_in_process_strips_with_fused_peer_halo_equal_single_gpu_bitwise(world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_partitioned_cell_in_process_equals_single_gpu_bitwise(world):
+    """BASELINE configs[3] with the CELL partitioned as well: every strip computes only the cell patches that can reach its
+    substrate strip, the rows its patches read from elsewhere are pushed by their owners through peer memory, every rank adds
+    the same area / centroid partial sums in the single-GPU order.  The cell rows every rank OWNS tile the single-GPU cell bit
+    for bit (positions, velocities, strains, bond state), and so do the substrate rows; 12 steps of k31, Philox."""
+    import wholecellfe_b200 as W
+    from wholecellfe_b200.partition import InProcessStrips
+    xc, tc = disk_mesh(6000); xs, ts = square_mesh(120)
+    ndev = torch.cuda.device_count()
+    run = InProcessStrips("k31", (xc, tc), (xs, ts), [r % ndev for r in range(world)], rng=(1, 5), cell="partitioned")
+    assert sum(len(c.owned_patches) for c in run.cparts) == (len(xc) + 127) // 128
+    assert min(len(c.patch_list) for c in run.cparts) < (len(xc) + 127) // 128          # somebody really computes less than the whole cell
+    run.set_subs_field("ea", _initial_strain(len(xs)))
+    run.step_n(5, 2e-4); run.step_n(7, 2e-4)
+    g = _single_gpu_reference()
+    for f in ("x", "V", "A", "ea", "cC", "fa_u"):
+        ref = g.get(W.CELL, f)
+        got = np.full_like(ref, np.nan)
+        for r in range(world):
+            ids, vals = run.owned_cell_field(r, f)
+            got[ids] = vals
+        assert np.array_equal(got, ref), (f, int((got != ref).sum()))
+    for f in ("V", "A", "ea"):
+        ref = g.get(W.SUBS, f)
+        got = np.full_like(ref, np.nan)
+        for r in range(world):
+            ids, vals = run.owned_field(r, f)
+            got[ids] = vals
+        assert np.array_equal(got, ref), f
+    d0 = run.sims[0].diagnostics()
+    assert np.array_equal(d0[:4], g.diagnostics()[:4])               # total area and centroid: the same sum of the same partials
+    run.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("halo", ["peer", "dist"])
 def test_two_rank_partition_equals_single_gpu_bitwise(halo):
     import wholecellfe_b200 as W

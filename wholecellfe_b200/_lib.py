@@ -25,7 +25,7 @@ SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_param
            "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
            "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync", "wcfe_selftest_quotient",
            "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed", "wcfe_set_roundtrip_mode",
-           "wcfe_halo_info_get", "wcfe_halo_connect", "wcfe_halo_disconnect",
+           "wcfe_halo_info_get", "wcfe_halo_connect", "wcfe_halo_disconnect", "wcfe_cell_halo_info_get", "wcfe_cell_halo_connect", "wcfe_cell_halo_disconnect",
            "wcfe_strip_partition", "wcfe_strip_sizes", "wcfe_strip_mesh", "wcfe_strip_halo", "wcfe_strip_free"]
 
 
@@ -47,6 +47,12 @@ class HaloInfo(C.Structure):
     """wcfe_halo_info: what a neighbouring rank needs to reach this context's strain buffers (ship it as bytes)"""
     _fields_ = [("pid", C.c_longlong), ("device", C.c_int), ("ea_cur", C.c_int), ("np", C.c_longlong),
                 ("ptr", C.c_ulonglong * 3), ("offset", C.c_ulonglong * 3), ("ipc", (C.c_ubyte * 64) * 3)]
+
+
+class CellHaloInfo(C.Structure):
+    """wcfe_cell_halo_info: what another rank needs to reach this context's cell buffers (ship it as bytes)"""
+    _fields_ = [("pid", C.c_longlong), ("device", C.c_int), ("reserved", C.c_int), ("np", C.c_longlong),
+                ("ptr", C.c_ulonglong * 11), ("offset", C.c_ulonglong * 11), ("ipc", (C.c_ubyte * 64) * 11)]
 
 
 _lib = None
@@ -108,6 +114,9 @@ def load():
     L.wcfe_halo_info_get.argtypes = [vp, C.POINTER(HaloInfo)]
     L.wcfe_halo_connect.argtypes = [vp, C.c_int, C.POINTER(HaloInfo), _ip, _ip, C.c_int, _ip, _ip, _ip, C.c_int, _ip]
     L.wcfe_halo_disconnect.argtypes = [vp]
+    L.wcfe_cell_halo_info_get.argtypes = [vp, C.POINTER(CellHaloInfo)]
+    L.wcfe_cell_halo_connect.argtypes = [vp, C.c_int, C.POINTER(CellHaloInfo), _ip, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _ip, C.c_double]
+    L.wcfe_cell_halo_disconnect.argtypes = [vp]
     L.wcfe_strip_partition.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, C.c_int, C.c_int, C.POINTER(vp)]
     L.wcfe_strip_sizes.argtypes = [vp] + [_ip] * 6
     L.wcfe_strip_mesh.argtypes = [vp] + [_ip] * 5

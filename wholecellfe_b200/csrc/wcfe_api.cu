@@ -165,6 +165,20 @@ struct wcfe_ctx {
         DevBuf<HaloPeer> peers;
         std::vector<void *> opened;                      // IPC mappings to close
     } halo;
+    // partitioned cell: patch list, pushes and epoch counters (CellPartView, wcfe_kernels.cuh)
+    struct {
+        bool have_info = false, active = false;
+        int npeer = 0, n_list = 0;
+        unsigned int step = 0;                           // steps since the connect
+        DevBuf<unsigned long long> flags;                // [16]: step counters, partials counters (bumped by the peers)
+        DevBuf<double> partials2;                        // second partials array (odd steps)
+        DevBuf<int> patch_list, exp_ptr, exp_ent, bexp_ptr, bexp_peer;
+        DevBuf<unsigned char> bnd_local;
+        DevBuf<CellPeer> peers;
+        double margin = 0;                               // anchor margin the patch lists were built for
+        void *info_ptr[WCFE_CELL_HALO_NPTR] = {};        // what wcfe_cell_halo_info_get reported (the buffers must not have swapped since)
+        std::vector<void *> opened;
+    } cpart;
     int roundtrip_mode = 0;               // wcfe_step_n_roundtrip: 0 cell only + overlapped, 1 both surfaces serial
     std::string err;
 };
@@ -584,8 +598,10 @@ int check_device_errors(wcfe_ctx *c) {
 int check_device_errors_bits(wcfe_ctx *c, int e) {
     if (e & ERR_NAN) return fail(c, WCFE_ERR_NUMERIC, "non-finite cell area / centroid: the explicit step went unstable (dt above the stability limit of the stiffest spring?)");
     if (e & ERR_BUCKET_OVERFLOW) return fail(c, WCFE_ERR_CAPACITY, "triangle bucket overflow: more anchors in one substrate triangle than the capacity sized at upload");
-    if (e & ERR_REGION) return fail(c, WCFE_ERR_CAPACITY, "an integrin anchor left the padded cell region; re-commit positions to refresh it");
+    if (e & ERR_REGION) return fail(c, WCFE_ERR_CAPACITY, c->cpart.active ? "an integrin anchor left the padded cell region, or moved further from its node than the anchor margin the cell partition was built with"
+                                                                           : "an integrin anchor left the padded cell region; re-commit positions to refresh it");
     if (e & ERR_CHAIN) return fail(c, WCFE_ERR_CUDA, "internal: the substrate kernel did not see the cell kernel complete within 2 s");
+    if (e & ERR_CELL_HALO_TIMEOUT) return fail(c, WCFE_ERR_PEER, "partitioned cell: a peer's step / partial-sum counter did not arrive within 10 s (the peer stopped stepping, or the ranks ran different step counts)");
     if (e & ERR_HALO_TIMEOUT) return fail(c, WCFE_ERR_PEER, "halo exchange: a neighbouring rank's strain rows did not arrive within 10 s (the peer stopped stepping, or the ranks ran different step counts)");
     return WCFE_OK;
 }
@@ -674,11 +690,27 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         a.d_flags = c->d_flags.p; a.d_loc_bond = c->d_loc_bond.p; a.d_loc_cnt = c->d_loc_cnt.p; a.d_loc_first = c->d_loc_first.p;
         a.d_ap_fire = c->d_ap_fire.p; a.err = c->d_err.p; a.debug = c->debug; a.loc_cache = c->d_loc_cache.p;
         if (c->halo.active && c->halo.step > 0) { a.halo_peer = c->halo.peers.p; a.halo_npeer = c->halo.npeer; }   // signal the previous step's halo rows
+        CellPartView cpv{};
+        if (c->cpart.active) {
+            if (!fuse_predict || batch || c->debug || which != 3)
+                return fail(c, WCFE_ERR_UNSUPPORTED, "a partitioned cell advances with wcfe_step_n / _async only (fused planar step, one replica, no debug capture)");
+            cpv.patch_list = c->cpart.patch_list.p; cpv.exp_ptr = c->cpart.exp_ptr.p; cpv.exp_ent = c->cpart.exp_ent.p;
+            cpv.peer = c->cpart.peers.p; cpv.npeer = c->cpart.npeer; cpv.flags = c->cpart.flags.p; cpv.step = c->cpart.step;
+            cpv.bnd_local = c->cpart.bnd_local.p; cpv.bexp_ptr = c->cpart.bexp_ptr.p; cpv.bexp_peer = c->cpart.bexp_peer.p; cpv.err = c->d_err.p; cpv.fa_max2 = c->cpart.margin * c->cpart.margin;
+            a.part = cpv;
+            if (c->cpart.step & 1u) a.partials = c->cpart.partials2.p;
+            bk.cell_peer = c->cpart.peers.p; bk.cell_npeer = c->cpart.npeer;
+        }
         const size_t smem = cell_smem_bytes(cs.max_halo, cs.max_elem, cs.stride);
         npart = cs.npatch;
-        if (bk.cell_done) c->cell_target += (unsigned long long)cs.npatch * R;      // every CTA of the launch below adds one to cell_done
+        const int gcell = c->cpart.active ? c->cpart.n_list : cs.npatch;
+        if (bk.cell_done) c->cell_target += (unsigned long long)gcell * R;      // every CTA of the launch below adds one to cell_done
         bk.cell_target = c->cell_target;
-        if (batch) {
+        if (c->cpart.active) {
+            if (pdl) CK(launch_pdl(k_cell_patch<true, false, false, true>, dim3(gcell), dim3(kThreads), smem, c->stream, cv, pvc, sv, c->grid, bk, bv, c->k, a, (const double *)cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt));
+            else k_cell_patch<true, false, false, true><<<gcell, kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt);
+            std::swap(cs.x.p, cs.X.p);
+        } else if (batch) {
             if (pdl) CK(launch_pdl(k_cell_patch<true, false, true>, dim3(cs.npatch, R), dim3(kThreads), smem, c->stream, cv, pvc, sv, c->grid, bk, bv, c->k, a, (const double *)cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt));
             else k_cell_patch<true, false, true><<<dim3(cs.npatch, R), kThreads, smem, c->stream>>>(cv, pvc, sv, c->grid, bk, bv, c->k, a, cs.x.p, cs.X.p, cs.V2.p, cs.A2.p, DebugView{}, bt);
             std::swap(cs.x.p, cs.X.p);
@@ -719,15 +751,25 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     {
     // fork: the finish kernel goes to the side stream first (so that its few blocks are placed as soon as the cell kernel drains)
     cudaStream_t fs = c->stream;
-    const bool forked = overlap && !pdl;
+    const bool forked = overlap && !pdl && !c->cpart.active;      // (partitioned cell: the substrate kernel's first thread vouches for the finish kernel's completion)
     if (forked) { CK(cudaEventRecord(c->ev_fork, c->stream)); CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0)); fs = c->side; }
     { ProfScope ps(c, K_FINISH, fs);
     const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few small blocks: latency-, not throughput-bound
-    if (pdl && batch) CK(launch_pdl(k_boundary_finish<false, true>, dim3(fb, R), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c));
-    else if (pdl) CK(launch_pdl(k_boundary_finish<false, false>, dim3(fb), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c));
-    else if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c);
-    else if (c->debug) k_boundary_finish<true><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt, dtd_c);
-    else k_boundary_finish<false><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c); }
+    const CellPartView nocp{};
+    if (c->cpart.active && planar && (which & 1)) {
+        CellPartView cpf{};
+        cpf.peer = c->cpart.peers.p; cpf.npeer = c->cpart.npeer; cpf.flags = c->cpart.flags.p; cpf.step = c->cpart.step;
+        cpf.bnd_local = c->cpart.bnd_local.p; cpf.bexp_ptr = c->cpart.bexp_ptr.p; cpf.bexp_peer = c->cpart.bexp_peer.p; cpf.err = c->d_err.p;
+        const double *parts = (c->cpart.step & 1u) ? c->cpart.partials2.p : c->d_partials.p;
+        if (pdl) CK(launch_pdl(k_boundary_finish<false, false, true>, dim3(fb), dim3(256), 0, fs, cv, bv, c->k, npart, parts, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, cpf));
+        else k_boundary_finish<false, false, true><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, parts, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, cpf);
+        c->cpart.step++;
+    }
+    else if (pdl && batch) CK(launch_pdl(k_boundary_finish<false, true>, dim3(fb, R), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, nocp));
+    else if (pdl) CK(launch_pdl(k_boundary_finish<false, false>, dim3(fb), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, nocp));
+    else if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, nocp);
+    else if (c->debug) k_boundary_finish<true><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt, dtd_c, nocp);
+    else k_boundary_finish<false><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, nocp); }
     if (forked) { CK(cudaEventRecord(c->ev_join, c->side)); joined = false; }
     }
     if (reduce) {
@@ -849,6 +891,16 @@ int alloc_base(wcfe_ctx *c, const void *ptr, unsigned long long *base) {
     if (fn(base, &size, (unsigned long long)(uintptr_t)ptr) != 0) return fail(c, WCFE_ERR_CUDA, "cuMemGetAddressRange failed");
     return WCFE_OK;
 }
+void cell_part_release(wcfe_ctx *c) {
+    if (c->cpart.active || !c->cpart.opened.empty()) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    for (void *m : c->cpart.opened) cudaIpcCloseMemHandle(m);
+    c->cpart.opened.clear();
+    if (c->cpart.active && c->s[WCFE_CELL].p_blob.p)      // clear the role words in the descriptors' headers
+        cudaMemset2D(c->s[WCFE_CELL].p_blob.p + 8, (size_t)c->s[WCFE_CELL].stride, 0, sizeof(int), (size_t)c->s[WCFE_CELL].npatch);
+    c->cpart.active = false; c->cpart.have_info = false; c->cpart.npeer = 0; c->cpart.n_list = 0; c->cpart.step = 0;
+    c->cpart.flags.release(); c->cpart.partials2.release(); c->cpart.patch_list.release(); c->cpart.exp_ptr.release(); c->cpart.exp_ent.release();
+    c->cpart.bexp_ptr.release(); c->cpart.bexp_peer.release(); c->cpart.bnd_local.release(); c->cpart.peers.release();
+}
 void halo_release(wcfe_ctx *c) {
     if (c->halo.active || !c->halo.opened.empty()) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
     for (void *m : c->halo.opened) cudaIpcCloseMemHandle(m);
@@ -956,7 +1008,7 @@ static int create_impl(wcfe_ctx **out, int device, const wcfe_params *p, int rep
         if (const char *e = std::getenv("WCFE_CELL_COUNTER")) c->use_cell_counter = std::atoi(e);
         const void *pk[] = {(const void *)k_subs_ring<false>, (const void *)k_subs_ring<true>, (const void *)k_subs_patch<false>, (const void *)k_subs_patch<true>, (const void *)k_cell_patch<true, false>,
                             (const void *)k_cell_patch<true, true>, (const void *)k_cell_patch<false, false>, (const void *)k_cell_patch<false, true>,
-                            (const void *)k_cell_patch<true, false, true>, (const void *)k_subs_ring<false, true>, (const void *)k_subs_ring<false, false, true>};
+                            (const void *)k_cell_patch<true, false, true>, (const void *)k_cell_patch<true, false, false, true>, (const void *)k_subs_ring<false, true>, (const void *)k_subs_ring<false, false, true>};
         for (const void *f : pk) {
             // 227 KB is the per-CTA limit including the kernels' small static arrays
             if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kPatchSmemMax)) != cudaSuccess) return bail("cudaFuncSetAttribute(max dynamic smem)", e);
@@ -990,6 +1042,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     halo_release(c);
+    cell_part_release(c);
     for (int q = 0; q < 2; q++) {
         Surface &s = c->s[q];
         s.d_tri.release(); s.d_ring_ptr.release(); s.d_ring.release();
@@ -1047,6 +1100,7 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
     for (int q = 0; q < 3 * ne; q++) if (tri[q] < 0 || tri[q] >= nn) return fail(c, WCFE_ERR_ARG, "upload_mesh: triangle refers to a vertex outside [0, nn)");
     CK(cudaSetDevice(c->device));
     if (surface == WCFE_SUBS) halo_release(c);       // a new strip: the neighbours' tables no longer describe it
+    cell_part_release(c);                            // patch lists follow both meshes
     Surface &s = c->s[surface];
     s.nn = nn; s.ne = ne; s.np = (nn + 31) / 32 * 32; s.nep = (ne + 31) / 32 * 32;
     s.tri.assign(tri, tri + 3 * (size_t)ne);
@@ -1775,6 +1829,165 @@ int wcfe_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_halo_info *peers, con
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemset(c->cell_done.p, 0, sizeof(unsigned long long))); c->cell_target = 0;      // the cell kernel's completion counter starts with the connect
     c->halo.npeer = n_peers; c->halo.step = 0; c->halo.active = true;
+    return WCFE_OK;
+}
+
+// ---- partitioned cell (CellPartView, wcfe_kernels.cuh) --------------------------------------------------------------------------
+namespace {
+// a peer's buffer as THIS process can address it: a plain pointer when the peer lives in this process (peer access across GPUs),
+// a CUDA IPC mapping otherwise (one mapping per allocation)
+typedef std::vector<std::pair<std::vector<unsigned char>, void *>> IpcMaps;
+int map_peer_ptr(wcfe_ctx *c, long long pid, int device, unsigned long long ptr, unsigned long long offset, const unsigned char *ipc,
+                 IpcMaps &maps, std::vector<void *> &opened, void **out) {
+    if (pid == (long long)getpid()) {
+        if (device != c->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(c, WCFE_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        }
+        *out = (void *)(uintptr_t)ptr;
+        return WCFE_OK;
+    }
+    std::vector<unsigned char> key(ipc, ipc + 64);
+    void *base = nullptr;
+    for (auto &m : maps) if (m.first == key) base = m.second;
+    if (!base) {
+        cudaIpcMemHandle_t h; memcpy(&h, ipc, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, WCFE_ERR_CUDA, std::string("cudaIpcOpenMemHandle (peer GPU memory): ") + cudaGetErrorString(e)); }
+        maps.emplace_back(key, base); opened.push_back(base);
+    }
+    *out = (char *)base + offset;
+    return WCFE_OK;
+}
+}   // namespace
+
+int wcfe_cell_halo_info_get(wcfe_ctx *c, wcfe_cell_halo_info *out) {
+    int rc = ready(c);
+    if (rc) return rc;
+    if (!out) return WCFE_ERR_ARG;
+    NO_BATCH(c, "cell_halo_info_get");
+    CK(cudaSetDevice(c->device));
+    Surface &cs = c->s[WCFE_CELL];
+    if (!use_planar(c) || c->subs_kernel != 2) return fail(c, WCFE_ERR_UNSUPPORTED, "a partitioned cell needs the planar patch kernels (flat meshes)");
+    cell_part_release(c);
+    CK(c->cpart.flags.alloc(2 * WCFE_HALO_MAX_PEERS));
+    CK(cudaMemset(c->cpart.flags.p, 0, sizeof(unsigned long long) * 2 * WCFE_HALO_MAX_PEERS));
+    CK(c->cpart.partials2.alloc(c->d_partials.n));
+    CK(cudaMemset(c->cpart.partials2.p, 0, sizeof(double) * c->d_partials.n));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaDeviceSynchronize());
+    memset(out, 0, sizeof(*out));
+    out->pid = (long long)getpid(); out->device = c->device; out->np = cs.np;
+    // the next fused step writes X (positions ping-pong), V2, A2 and ea[cur ^ 1]; the one after it x, V, A, ea[cur]
+    void *ptrs[WCFE_CELL_HALO_NPTR] = {cs.X.p, cs.x.p, cs.V2.p, cs.V.p, cs.A2.p, cs.A.p, cs.ea[cs.ea_cur ^ 1].p, cs.ea[cs.ea_cur].p,
+                                       c->d_partials.p, c->cpart.partials2.p, c->cpart.flags.p};
+    for (int q = 0; q < WCFE_CELL_HALO_NPTR; q++) {
+        if (!ptrs[q]) return fail(c, WCFE_ERR_ARG, "cell_halo_info_get: cell buffers not allocated");
+        unsigned long long base = 0;
+        if ((rc = alloc_base(c, ptrs[q], &base))) return rc;
+        out->ptr[q] = (unsigned long long)(uintptr_t)ptrs[q];
+        out->offset[q] = out->ptr[q] - base;
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, (void *)(uintptr_t)base));
+        memcpy(out->ipc[q], &h, 64);
+        c->cpart.info_ptr[q] = ptrs[q];
+    }
+    c->cpart.have_info = true;
+    return WCFE_OK;
+}
+
+int wcfe_cell_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_cell_halo_info *peers, const int *my_slot_at_peer,
+                           int n_patches, const int *patch_list, const int *patch_owned,
+                           int n_export, const int *export_node, const int *export_peer, int n_import, const int *import_node, double anchor_margin) {
+    int rc = ready(c);
+    if (rc) return rc;
+    NO_BATCH(c, "cell_halo_connect");
+    Surface &cs = c->s[WCFE_CELL];
+    if (n_peers < 0 || n_peers > WCFE_HALO_MAX_PEERS || n_patches < 1 || n_patches > cs.npatch || !patch_list || !patch_owned || n_export < 0 || n_import < 0 ||
+        (n_peers && (!peers || !my_slot_at_peer)) || (n_export && (!export_node || !export_peer)) || (n_import && !import_node) || !(anchor_margin > 0))
+        return fail(c, WCFE_ERR_ARG, "cell_halo_connect: bad arguments (at least one patch, at most WCFE_HALO_MAX_PEERS peers, a positive anchor margin)");
+    if (!c->cpart.have_info) return fail(c, WCFE_ERR_ARG, "cell_halo_connect: call wcfe_cell_halo_info_get first");
+    {
+        void *now[8] = {cs.X.p, cs.x.p, cs.V2.p, cs.V.p, cs.A2.p, cs.A.p, cs.ea[cs.ea_cur ^ 1].p, cs.ea[cs.ea_cur].p};
+        for (int q = 0; q < 8; q++) if (now[q] != c->cpart.info_ptr[q]) return fail(c, WCFE_ERR_ARG, "cell_halo_connect: the context stepped since wcfe_cell_halo_info_get");
+    }
+    CK(cudaSetDevice(c->device));
+    std::vector<CellPeer> hp((size_t)std::max(1, n_peers));
+    IpcMaps maps;
+    for (int q = 0; q < n_peers; q++) {
+        const wcfe_cell_halo_info &pi = peers[q];
+        if (my_slot_at_peer[q] < 0 || my_slot_at_peer[q] >= WCFE_HALO_MAX_PEERS || pi.np != cs.np) return fail(c, WCFE_ERR_ARG, "cell_halo_connect: bad peer slot, or a peer holds a different cell mesh");
+        void *m[WCFE_CELL_HALO_NPTR];
+        for (int w = 0; w < WCFE_CELL_HALO_NPTR; w++)
+            if ((rc = map_peer_ptr(c, pi.pid, pi.device, pi.ptr[w], pi.offset[w], pi.ipc[w], maps, c->cpart.opened, &m[w]))) return rc;
+        hp[q].x[0] = (double *)m[0]; hp[q].x[1] = (double *)m[1]; hp[q].V[0] = (double *)m[2]; hp[q].V[1] = (double *)m[3];
+        hp[q].A[0] = (double *)m[4]; hp[q].A[1] = (double *)m[5]; hp[q].ea[0] = (double *)m[6]; hp[q].ea[1] = (double *)m[7];
+        hp[q].partials[0] = (double *)m[8]; hp[q].partials[1] = (double *)m[9];
+        hp[q].flag_step = (unsigned long long *)m[10] + my_slot_at_peer[q];
+        hp[q].flag_part = (unsigned long long *)m[10] + WCFE_HALO_MAX_PEERS + my_slot_at_peer[q];
+    }
+    // roles of the listed patches: bit 0 wait for the peers' step counters, bit 1 pushes rows, bit 2 publishes its partial sums
+    std::vector<int> role((size_t)cs.npatch, 0);
+    std::vector<unsigned char> listed((size_t)cs.npatch, 0), imported((size_t)cs.np, 0);
+    for (int k = 0; k < n_patches; k++) {
+        const int p = patch_list[k];
+        if (p < 0 || p >= cs.npatch || (k && p <= patch_list[k - 1])) return fail(c, WCFE_ERR_ARG, "cell_halo_connect: patch list must be ascending patch ids");
+        listed[p] = 1;
+        if (patch_owned[k]) role[p] |= 4;
+    }
+    for (int q = 0; q < n_import; q++) {
+        const int v = import_node[q];
+        if (v < 0 || v >= cs.nn || listed[v / kPatch]) return fail(c, WCFE_ERR_ARG, "cell_halo_connect: an imported node lies in a patch this rank computes itself");
+        imported[v] = 1;
+    }
+    // every listed patch whose node table holds an imported row waits (its halo = the vertices of its elements outside its own range)
+    for (int k = 0; k < n_patches; k++) {
+        const int p = patch_list[k], n0 = p * kPatch, n1 = std::min(cs.nn, n0 + kPatch);
+        bool waits = false;
+        for (int r = cs.ring_ptr[n0]; r < cs.ring_ptr[n1] && !waits; r++) {
+            const int *tr = &cs.tri[3 * (size_t)(cs.ring[r] >> 2)];
+            for (int j = 0; j < 3; j++) if (imported[tr[j]]) waits = true;
+        }
+        if (waits) role[p] |= 1;
+    }
+    std::vector<std::vector<int>> per_patch((size_t)cs.npatch);
+    std::vector<std::vector<int>> per_bnd((size_t)std::max(1, cs.nb));
+    std::vector<int> bindex((size_t)cs.nn, -1);
+    for (int b = 0; b < cs.nb; b++) bindex[cs.bnd_node[b]] = b;
+    for (int q = 0; q < n_export; q++) {
+        const int v = export_node[q], pq = export_peer[q];
+        if (v < 0 || v >= cs.nn || pq < 0 || pq >= n_peers || !(role[v / kPatch] & 4)) return fail(c, WCFE_ERR_ARG, "cell_halo_connect: export entry out of range, or a node of a patch this rank does not own");
+        role[v / kPatch] |= 3;               // a patch that pushes also waits: the buffers it stores into must no longer be read
+        per_patch[v / kPatch].push_back(v % kPatch); per_patch[v / kPatch].push_back(pq);
+        if (bindex[v] >= 0) per_bnd[bindex[v]].push_back(pq);
+    }
+    std::vector<int> eptr((size_t)cs.npatch + 1, 0), eent, bptr((size_t)cs.nb + 1, 0), bent;
+    for (int p = 0; p < cs.npatch; p++) { eent.insert(eent.end(), per_patch[p].begin(), per_patch[p].end()); eptr[p + 1] = (int)(eent.size() / 2); }
+    for (int b = 0; b < cs.nb; b++) { bent.insert(bent.end(), per_bnd[b].begin(), per_bnd[b].end()); bptr[b + 1] = (int)bent.size(); }
+    if (eent.empty()) eent.assign(2, 0);
+    if (bent.empty()) bent.assign(1, 0);
+    std::vector<unsigned char> blocal((size_t)std::max(1, cs.nb), 0);
+    for (int b = 0; b < cs.nb; b++) blocal[b] = listed[cs.bnd_node[b] / kPatch];
+    CK(c->cpart.patch_list.alloc((size_t)n_patches)); CK(c->cpart.exp_ptr.alloc(eptr.size())); CK(c->cpart.exp_ent.alloc(eent.size()));
+    CK(c->cpart.bexp_ptr.alloc(bptr.size())); CK(c->cpart.bexp_peer.alloc(bent.size())); CK(c->cpart.bnd_local.alloc(blocal.size())); CK(c->cpart.peers.alloc(hp.size()));
+    CK(cudaMemcpy(c->cpart.patch_list.p, patch_list, sizeof(int) * n_patches, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->cpart.exp_ptr.p, eptr.data(), sizeof(int) * eptr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->cpart.exp_ent.p, eent.data(), sizeof(int) * eent.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->cpart.bexp_ptr.p, bptr.data(), sizeof(int) * bptr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->cpart.bexp_peer.p, bent.data(), sizeof(int) * bent.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->cpart.bnd_local.p, blocal.data(), blocal.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->cpart.peers.p, hp.data(), sizeof(CellPeer) * hp.size(), cudaMemcpyHostToDevice));
+    // role words into header word 2 of every patch descriptor (they arrive with the descriptor's bulk copy)
+    CK(cudaMemcpy2D(cs.p_blob.p + 8, (size_t)cs.stride, role.data(), sizeof(int), sizeof(int), (size_t)cs.npatch, cudaMemcpyHostToDevice));
+    CK(cudaStreamSynchronize(c->stream));
+    c->cpart.npeer = n_peers; c->cpart.n_list = n_patches; c->cpart.step = 0; c->cpart.margin = anchor_margin; c->cpart.active = true;
+    return WCFE_OK;
+}
+
+int wcfe_cell_halo_disconnect(wcfe_ctx *c) {
+    if (!c) return WCFE_ERR_ARG;
+    cell_part_release(c);
     return WCFE_OK;
 }
 

@@ -37,6 +37,7 @@ struct GridView {            // uniform grid over substrate triangles (candidate
     const int *ptr, *items;  // CSR cell -> triangles, ascending triangle index inside a cell
 };
 
+struct CellPeer;
 struct BucketView {          // triangle -> anchored cell nodes, rebuilt every step, no reset pass:
     unsigned long long *head;   // [ne_subs] (epoch<<32 | count); a stale epoch reads as count 0
     int *items;                 // [ne_subs*cap]
@@ -60,7 +61,39 @@ struct BucketView {          // triangle -> anchored cell nodes, rebuilt every s
     unsigned long long cell_target;
     int wait_cell;                  // substrate side: 1 = spin on the counter, 0 = griddepcontrol.wait (k_bucket_reduce sits in between)
     int *chain_err;
+    const CellPeer *cell_peer;      // partitioned cell: the substrate kernel's first thread bumps every peer's step counter
+    int cell_npeer;
 };
+
+// ---- partitioned CELL (BASELINE configs[3]): every rank keeps the whole cell's arrays, with the single-GPU numbering, but computes
+// only the patches that can put an anchor into its substrate strip (a patch on a cut is computed by both neighbours).  What a rank
+// does not compute goes stale there -- except the nodes its own patches read as halo rows: those are pushed, every step, by the
+// rank that owns their patch, through peer memory, to the same index of the reader's arrays (replicated storage: no row
+// translation).  Two epoch counters per ordered pair of ranks pace the exchange, both bumped by one per step:
+//   step counter     by the substrate kernel's first thread after its griddepcontrol.wait (cell kernel, boundary finish and the
+//                    reduction of this step are complete: every pushed row is out, every halo row has been read).  A patch that
+//                    reads pushed rows OR pushes rows waits until every peer's counter has reached the step it is about to run:
+//                    the rows of the previous step have landed, and the buffers it is about to push into are no longer read.
+//   partials counter by the boundary-finish kernel's first thread after its wait (this rank's cell kernel is complete: the area /
+//                    centroid partial sums of the patches it OWNS have been stored into every peer's partials array).  Every
+//                    rank then adds ALL patches' partials in the single-GPU order (UL:1641-1667): the same total, bit for bit.
+struct CellPeer {
+    double *x[2], *V[2], *A[2], *ea[2];   // the peer's write buffers of the first / second step after the connect (they swap every step)
+    double *partials[2];                  // its partials arrays, by step parity
+    unsigned long long *flag_step, *flag_part;   // this rank's counters in the peer's memory
+};
+struct CellPartView {
+    const int *patch_list;               // [gridDim.x] patches this rank computes, ascending
+    const int *exp_ptr, *exp_ent;        // CSR over ALL patches: pairs (local node, peer slot) of the nodes a patch pushes
+    const CellPeer *peer; int npeer;
+    const unsigned long long *flags;     // mine: [0 .. 7] step counters, [8 .. 15] partials counters, one per peer slot
+    unsigned int step;                   // steps since the connect
+    const unsigned char *bnd_local;      // [nb] the boundary vertex sits in a patch this rank computes
+    const int *bexp_ptr, *bexp_peer;     // CSR over boundary ordinals: peer slots its V, A go to (written by the boundary finish)
+    int *err;
+    double fa_max2;                      // (anchor margin)^2 the patch lists were built for: |fa_u| beyond it is an error
+};
+enum : int { ERR_CELL_HALO_TIMEOUT = 32 };
 
 struct BoundaryView {        // cell boundary vertices in ascending vertex order (the RNG draw order, UL:1463-1465)
     int nb;
@@ -369,15 +402,48 @@ __global__ void __launch_bounds__(kBlock) k_cell_node(SurfView s, BoundaryView b
 // ---- total area / centroid (UL:1641-1667) + area-constraint force and update of the boundary vertices (UL:1670-1763) --
 // every block reduces the partial sums itself, in the same fixed order (bit-reproducible run to run and identical across
 // blocks), then finishes its share of the boundary vertices; block 0 publishes the diagnostics
-template <bool DBG, bool BATCH = false>
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// one thread: bump this rank's counter `which` (0 step, 1 partials) on every peer -- after a fence that orders the pushes of the
+// kernels that completed before this thread's griddepcontrol.wait returned
+__device__ __noinline__ void cell_part_signal(const CellPeer *peer, int npeer, int which) {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    for (int q = 0; q < npeer; q++)
+        asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(which ? peer[q].flag_part : peer[q].flag_step), "l"(1ull) : "memory");
+}
+// one thread: wait until every peer's counter (base 0 step, 8 partials) has reached `want`.  Bounded like halo_wait: 10 s, then the
+// error flag is raised and every later wait returns at once -- a wrong answer that is reported, never a hung GPU.
+__device__ __noinline__ void cell_part_wait(const unsigned long long *flags, int base, int npeer, unsigned long long want, int *err) {
+    if (want == 0) return;
+    const unsigned long long t0 = global_timer_ns();
+    for (int q = 0; q < npeer; q++)
+        while (ld_acquire_sys_u64(flags + base + q) < want) {
+            if (*(volatile int *)err & ERR_CELL_HALO_TIMEOUT) return;
+            if (global_timer_ns() - t0 > 10000000000ull) { atomicOr(err, ERR_CELL_HALO_TIMEOUT); return; }
+            __nanosleep(64);
+        }
+}
+
+template <bool DBG, bool BATCH = false, bool PART = false>
 __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k_, int npart, const double *__restrict__ partials,
                                                           const double *__restrict__ V_in, const double *__restrict__ A_in,
                                                           double dt, double dt_real, double *__restrict__ diag, int *__restrict__ err, DebugView dbg,
-                                                          BatchView bt, double dt_drv) {
+                                                          BatchView bt, double dt_drv, CellPartView cp) {
     __shared__ double sh[4 * 32];
     __shared__ double tot[4];
     pdl_launch_dependents();      // the substrate kernel may start its cell-independent part now
     pdl_wait();                   // everything below reads what the cell kernel wrote
+    if (PART) {
+        // this rank's cell kernel is complete: tell everybody that the partial sums of its patches are in their arrays, then wait
+        // for everybody else's
+        if (blockIdx.x == 0 && threadIdx.x == 0) cell_part_signal(cp.peer, cp.npeer, 1);
+        if (threadIdx.x == 0) cell_part_wait(cp.flags, 8, cp.npeer, (unsigned long long)cp.step + 1ull, cp.err);
+        __syncthreads();
+    }
     const Consts &k = BATCH ? bt.k[blockIdx.y] : k_;
     if (BATCH) {
         const size_t r = blockIdx.y;
@@ -387,7 +453,7 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     // strided accumulation in a fixed order, then a fixed tree
     for (int p = threadIdx.x; p < npart; p += blockDim.x)
-        for (int q = 0; q < 4; q++) v[q] += partials[(size_t)4 * p + q];
+        for (int q = 0; q < 4; q++) v[q] += PART ? __ldcg(partials + (size_t)4 * p + q) : partials[(size_t)4 * p + q];      // (peer-written rows: past the incoherent L1)
     block_reduce4(v, sh);
     if (threadIdx.x == 0) {
         tot[0] = v[0]; tot[1] = v[1] / v[0]; tot[2] = v[2] / v[0]; tot[3] = v[3] / v[0];
@@ -401,6 +467,7 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
     const double area_tot = tot[0];
     const int np = s.np;
     for (int bi = blockIdx.x * blockDim.x + threadIdx.x; bi < b.nb; bi += gridDim.x * blockDim.x) {
+        if (PART && !cp.bnd_local[bi]) continue;      // its patch is another rank's: the record below is stale here
         const int i = b.node[bi];
         const double *o = b.buf + (size_t)16 * bi;
         const double mm = o[6], tl = o[7];
@@ -413,6 +480,11 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
             if (c == 2) Vh = 0.0;
             node_update(f, mm, k.damp, k.rho, dt, dt_real, Vh, V, A);
             s.V[c * np + i] = V; s.A[c * np + i] = A;
+            if (PART && c < 2)      // a boundary vertex other ranks read as a halo row: its V, A are final only here
+                for (int q = cp.bexp_ptr[bi]; q < cp.bexp_ptr[bi + 1]; q++) {
+                    const CellPeer *pr = cp.peer + cp.bexp_peer[q];
+                    pr->V[cp.step & 1][c * np + i] = V; pr->A[cp.step & 1][c * np + i] = A;
+                }
             if (DBG) dbg.f_area[c * np + i] = F_area;
         }
     }

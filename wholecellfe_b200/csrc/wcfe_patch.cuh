@@ -413,7 +413,13 @@ __device__ __forceinline__ void ring_node(const SurfView &s, const PatchView &pv
     double Fx = 0.0, Fy = 0.0;
     // one thread always waits: this kernel's completion then implies that of the boundary finish, which the next cell kernel
     // (chained behind this kernel only) depends on; it also re-zeroes the triangle list k_bucket_reduce has consumed
-    if (zero_list) { pdl_wait(); if (bk.big_count) *bk.big_count = 0; }
+    if (zero_list) {
+        pdl_wait();
+        if (bk.big_count) *bk.big_count = 0;
+        // partitioned cell: this step's cell kernel, boundary finish and reduction are complete on this rank -- every row it pushes is
+        // out, every pushed row it reads has been read
+        if (bk.cell_peer) cell_part_signal(bk.cell_peer, bk.cell_npeer, 0);
+    }
     if (HALO && nrole == 1) return;          // ghost node (incomplete fan): its owner computes it and stores the result here
     unsigned int stamp = bk.epoch - 1u;
     if (Xi0 >= bx0 && Xi0 <= bx1 && Xi1 >= by0 && Xi1 <= by1) {
@@ -666,6 +672,7 @@ struct CellStepArgs {
     int debug;
     const HaloPeer *halo_peer;      // partitioned run, not the first step: signal the previous step's halo rows (halo_signal)
     int halo_npeer;
+    CellPartView part;              // partitioned cell (PART instantiation): patch list, pushes, counters
 };
 
 // Shared memory: the seven node arrays in SoA (TMA destinations), element records as array-of-structs, kRec doubles per
@@ -684,7 +691,7 @@ __device__ __forceinline__ unsigned int bucket_take_slot(const BucketView &bk, i
     return (unsigned int)atomicAdd(bk.head + t, 1ull);
 }
 
-template <bool PREDICT, bool DBG, bool BATCH = false>
+template <bool PREDICT, bool DBG, bool BATCH = false, bool PART = false>
 __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, PatchView pv, SurfView sub, GridView g, BucketView bk, BoundaryView b, Consts k_,
                                                        CellStepArgs a, const double *__restrict__ x_in, double *__restrict__ x_out,
                                                        double *__restrict__ V_out, double *__restrict__ A_out, DebugView dbg, BatchView bt) {
@@ -708,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     unsigned char *sblob = smraw + 16;
     double *sX0 = (double *)(sblob + pv.stride), *sX1 = sX0 + NL, *sx0 = sX1 + NL, *sx1 = sx0 + NL, *se0 = sx1 + NL, *se1 = se0 + NL, *se3 = se1 + NL;
     double *rec = se3 + NL;                       // [max_elem][kRec]
-    const int p = blockIdx.x, tid = threadIdx.x;
+    const int p = PART ? a.part.patch_list[blockIdx.x] : blockIdx.x, tid = threadIdx.x;      // (the list is static: read before the wait)
     const int n0 = p * kPatch;
     const int nown = min(kPatch, s.nn - n0);
     const int ncopy = min(kPatch, s.np - n0);
@@ -760,11 +767,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     const unsigned short *elem_lv = (const unsigned short *)(sblob + pv.off_lv);
     const unsigned short *rptr = (const unsigned short *)(sblob + pv.off_rptr);
     const unsigned short *ring16 = (const unsigned short *)(sblob + pv.off_ring);
+    // partitioned cell: header word 2 of the descriptor carries the patch's role on THIS rank (bit 0: it reads rows other ranks push,
+    // or pushes rows itself -- wait for every peer's step counter first; bit 1: it pushes; bit 2: this rank owns its partial sums)
+    const int prole = PART ? hdr[2] : 0;
+    if (PART && (prole & 1)) {
+        if (tid == 0) cell_part_wait(a.part.flags, 0, a.part.npeer, (unsigned long long)a.part.step, a.part.err);
+        __syncthreads();
+    }
     // ---- halo gather first (its global loads fly while the own node's bond kinetics run) + the same predictor: every patch that
     //      sees a node computes the same x_new
     for (int l = tid; l < nh; l += kThreads) {
         const int gi = halo_ids[l];
         const int d = kPatch + l;
+        if (PART && (prole & 1)) {
+            // rows a peer GPU stored into L2 while this kernel may already have been running: read them past the (incoherent) L1
+            const double xo0 = __ldcg(x_in + gi), xo1 = __ldcg(x_in + np + gi);
+            const double v0 = __ldcg(s.V + gi), v1 = __ldcg(s.V + np + gi), a0 = __ldcg(s.A + gi), a1 = __ldcg(s.A + np + gi);
+            const double vh0 = WCFE_ADD(v0, WCFE_MUL(a.dt / 2.0, a0)), vh1 = WCFE_ADD(v1, WCFE_MUL(a.dt / 2.0, a1));
+            sX0[d] = xo0; sX1[d] = xo1; sx0[d] = WCFE_ADD(xo0, WCFE_MUL(a.dt, vh0)); sx1[d] = WCFE_ADD(xo1, WCFE_MUL(a.dt, vh1));
+            se0[d] = __ldcg(s.ea_in + gi); se1[d] = __ldcg(s.ea_in + np + gi); se3[d] = __ldcg(s.ea_in + 3 * (size_t)np + gi);
+            continue;
+        }
         if (PREDICT) {
             const double xo0 = x_in[gi], xo1 = x_in[np + gi];
             const double v0 = s.V[gi], v1 = s.V[np + gi], a0 = s.A[gi], a1 = s.A[np + gi];
@@ -815,6 +838,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         const double pt[3] = {xi[0] - fa0, xi[1] - fa1, 0.0};                           // UL:1303
         anc_px = pt[0]; anc_py = pt[1];
         if (!(pt[0] >= a.ix0 && pt[0] <= a.ix1 && pt[1] >= a.iy0 && pt[1] <= a.iy1)) atomicOr(a.err, ERR_REGION);
+        if (PART && !(fa0 * fa0 + fa1 * fa1 <= a.part.fa_max2)) atomicOr(a.err, ERR_REGION);      // the anchor may sit under a strip whose rank does not compute this patch
         // Anchors rarely change triangle between steps: try the triangle of the previous step first.  A point STRICTLY inside
         // it (all three sub-areas > 0) lies in no other triangle of a conforming substrate mesh, so the grid search -- which
         // finds every containing triangle, as the reference's exhaustive loop does (UL:1309-1452) -- is only needed otherwise.
@@ -883,8 +907,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     if (tid == 0) {
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
         for (int w = 0; w < kThreads / 32; w++) { t0 += shred[w]; t1 += shred[8 + w]; t2 += shred[16 + w]; }
-        double *o = a.partials + (size_t)4 * blockIdx.x;
+        double *o = a.partials + (size_t)4 * p;
         o[0] = t0; o[1] = t1; o[2] = t2; o[3] = 0.0;
+        if (PART && (prole & 4))             // this rank owns the patch: its sums go into everybody's array (a patch on a cut is computed
+            for (int q = 0; q < a.part.npeer; q++) {      // twice, bit-identically, and published once)
+                double *po = a.part.peer[q].partials[a.part.step & 1] + (size_t)4 * p;
+                po[0] = t0; po[1] = t1; po[2] = t2; po[3] = 0.0;
+            }
         const int nbig = min(s_nbig, 2 * kThreads);
         if (bk.big_count && nbig) s_bigbase = (int)atomicAdd(bk.big_count, (unsigned int)nbig);
     }
@@ -962,6 +991,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
             o[0] = ((Fvx + Fbx) + Fax) + Ffx; o[1] = ((Fvy + Fby) + Fay) + Ffy; o[2] = 0.0;
             o[3] = rx; o[4] = ry; o[5] = 0.0; o[6] = mm; o[7] = tl; o[8] = nrm[0]; o[9] = nrm[1]; o[10] = 0.0;
             if (DBG) { dbg.f_bend[i] = Fbx; dbg.f_bend[np + i] = Fby; dbg.f_ap[i] = Fax; dbg.f_ap[np + i] = Fay; }
+        }
+    }
+    if (PART && PREDICT && (prole & 2) && own) {
+        // rows other ranks read as halo rows of THEIR patches: the new state goes to the same index of their write buffers
+        // (positions and strains from here for every such node, V and A only for interior nodes: a boundary vertex gets them
+        // from the boundary finish)
+        const int par = (int)(a.part.step & 1u);
+        for (int q = a.part.exp_ptr[p]; q < a.part.exp_ptr[p + 1]; q++) {
+            if (a.part.exp_ent[2 * q] != tid) continue;
+            const CellPeer *pr = a.part.peer + a.part.exp_ent[2 * q + 1];
+            pr->x[par][i] = myx0; pr->x[par][np + i] = myx1;
+            pr->ea[par][i] = s.ea_out[i]; pr->ea[par][np + i] = s.ea_out[np + i]; pr->ea[par][3 * (size_t)np + i] = s.ea_out[3 * (size_t)np + i];
+            if (bi < 0) { pr->V[par][i] = V0; pr->V[par][np + i] = V1; pr->A[par][i] = Av0; pr->A[par][np + i] = Av1; }
         }
     }
     if (bk.big_count) {                       // uniform: publish this CTA's share of the triangle list

@@ -94,6 +94,104 @@ def strip_partition(xyz, tri, world, weights=None):
     return out
 
 
+PATCH = 128      # libwcfe's owned nodes per patch (wcfe_patch.cuh kPatch)
+
+
+class CellPart:
+    """What one rank computes of the partitioned cell (replicated storage, partitioned patches: include/wcfe.h)."""
+
+    def __init__(self, rank, world, patch_list, patch_owned, imports, exports):
+        self.rank, self.world = rank, world
+        self.patch_list = patch_list        # ascending patch ids this rank computes
+        self.patch_owned = patch_owned      # 1 where it publishes the patch's partial sums / pushes its rows
+        self.imports = imports              # node ids it receives (halo rows of its patches that it does not compute)
+        self.exports = exports              # {peer rank: node ids of owned patches the peer reads}
+        own = patch_list[patch_owned.astype(bool)]
+        self.owned_patches = own
+
+    def owned_nodes(self, nn):
+        """node ids of the patches this rank owns (its authoritative rows)"""
+        if len(self.owned_patches) == 0:
+            return np.zeros(0, dtype=np.int64)
+        ids = (self.owned_patches[:, None] * PATCH + np.arange(PATCH)[None, :]).ravel()
+        return ids[ids < nn]
+
+
+def cell_partition(parts, cell_xyz, cell_tri, subs_xyz, margin=0.15):
+    """Which cell patches every rank computes, owns, pushes and receives.
+
+    A rank computes every patch that can drop an anchor into its strip: the patch's x range, widened by `margin` (the largest
+    |fa_u| an anchor may be away from its node: libwcfe raises an error when an anchor leaves it; the strip's range covers its ghost
+    triangles as well).  A patch on a cut is therefore computed by both neighbours; the rank whose OWNED x range
+    holds the patch's centre owns it: it alone publishes the patch's area / centroid partial sums and pushes its rows to the ranks
+    that read them as halo rows of their own patches without computing them."""
+    xyz = np.asarray(cell_xyz); tri = np.asarray(cell_tri); xs = np.asarray(subs_xyz)
+    world = len(parts)
+    nn = len(xyz); npatch = (nn + PATCH - 1) // PATCH
+    starts = np.arange(0, nn, PATCH)
+    pxmin = np.minimum.reduceat(xyz[:, 0], starts); pxmax = np.maximum.reduceat(xyz[:, 0], starts)
+    centre = 0.5 * (pxmin + pxmax)
+    lo = np.array([xs[p.local_nodes, 0].min() for p in parts]); hi = np.array([xs[p.local_nodes, 0].max() for p in parts])
+    cuts = np.array([xs[p.owned, 0].max() for p in parts[:-1]])          # owned x ranges are consecutive intervals
+    owner = np.searchsorted(cuts, centre, side="left").astype(np.int32)    # centre <= cuts[r] -> rank r
+    listed = np.zeros((world, npatch), dtype=bool)
+    for r in range(world):
+        listed[r] = (pxmax + margin >= lo[r]) & (pxmin - margin <= hi[r])
+        listed[r, owner == r] = True
+        if not listed[r].any():              # a strip far from the cell still runs the step's kernels: give it the nearest patch
+            listed[r, int(np.argmin(np.minimum(np.abs(centre - lo[r]), np.abs(centre - hi[r]))))] = True
+    pid = np.arange(nn) // PATCH
+    a = tri[:, [0, 0, 1, 1, 2, 2]].ravel(); b = tri[:, [1, 2, 0, 2, 0, 1]].ravel()
+    pa, pb = pid[a], pid[b]
+    cross = pa != pb                                                       # b is a halo row of patch pa
+    pa, b, pb = pa[cross], b[cross], pb[cross]
+    imports = []
+    for r in range(world):
+        sel = listed[r][pa] & ~listed[r][pb]
+        imports.append(np.unique(b[sel]))
+    out = []
+    for r in range(world):
+        exports = {}
+        for q in range(world):
+            if q == r or len(imports[q]) == 0:
+                continue
+            mine = imports[q][owner[pid[imports[q]]] == r]
+            if len(mine):
+                exports[q] = mine
+        pl = np.nonzero(listed[r])[0].astype(np.int32)
+        out.append(CellPart(r, world, pl, (owner[pl] == r).astype(np.int32), imports[r].astype(np.int32), exports))
+    return out
+
+
+def cell_connect_plan(cparts, rank):
+    """Arguments of wcfe_cell_halo_connect for `rank`: (peer ranks, my_slot_at_peer, patch_list, patch_owned, export_node,
+    export_peer, import_node).  Every other rank is a peer (the partial sums go to all of them)."""
+    me = cparts[rank]
+    peers = [q for q in range(me.world) if q != rank]
+    my_slot = [rank if rank < q else rank - 1 for q in peers]
+    en, ep = [], []
+    for slot, q in enumerate(peers):
+        mine = me.exports.get(q)
+        if mine is not None:
+            en.append(mine); ep.append(np.full(len(mine), slot))
+    cat = lambda v: np.concatenate(v).astype(np.int32) if v else np.zeros(0, np.int32)
+    return peers, my_slot, me.patch_list, me.patch_owned, cat(en), cat(ep), me.imports
+
+
+def cell_column_weights(subs_xyz, cell_xyz, cell_cost=4.0):
+    """Extra per-substrate-node weights for strip_partition when the cell is partitioned too: the cost of the cell nodes above a
+    substrate column is charged to the substrate nodes of that column (a cell node costs ~4 substrate nodes: 0.088 ms / 0.5 M
+    against 0.185 ms / 4 M on B200)."""
+    xs = np.asarray(subs_xyz)[:, 0]; xc = np.asarray(cell_xyz)[:, 0]
+    order = np.argsort(xs, kind="stable")
+    edges = xs[order]
+    pos = np.clip(np.searchsorted(edges, xc), 0, len(xs) - 1)
+    w = np.zeros(len(xs))
+    np.add.at(w, order[pos], cell_cost)
+    # spread each column's charge over a window of neighbours in x so that single nodes do not become walls
+    return w
+
+
 def neighbours(part):
     """ranks this strip exchanges rows with, ascending: the peer-slot order of wcfe_halo_connect"""
     return sorted(set(part.send) | set(part.recv))
@@ -151,11 +249,20 @@ class InProcessStrips:
     a GPU), connected through plain device pointers (peer access between GPUs).  Strips advance in lockstep, one step queued on
     every strip before the next: a strip's step s+1 waits in-kernel for its neighbours' step s, which is already in flight."""
 
-    def __init__(self, variant, cell_mesh, subs_mesh, devices, rng=(1, 1), params=None, balance=True):
+    def __init__(self, variant, cell_mesh, subs_mesh, devices, rng=(1, 1), params=None, balance=True, cell="replicated", margin=0.15):
         from . import ulstep
         from ._lib import CELL, SUBS
         xs, ts = subs_mesh
-        self.parts = strip_partition(xs, ts, len(devices), cell_weights(xs, cell_mesh[0]) if balance else None)
+        w = None
+        if balance:
+            w = cell_weights(xs, cell_mesh[0])
+            if cell == "partitioned":
+                w = w + cell_column_weights(xs, cell_mesh[0])
+        self.parts = strip_partition(xs, ts, len(devices), w)
+        self.cparts = cell_partition(self.parts, cell_mesh[0], cell_mesh[1], xs, margin) if cell == "partitioned" else None
+        self.ncell = len(cell_mesh[0])
+        self.margin = margin
+        self.CELL = CELL
         self.sims = []
         for part, dev in zip(self.parts, devices):
             sim = ulstep.ULSim(variant, device=dev, params=params)
@@ -176,7 +283,17 @@ class InProcessStrips:
         for r, sim in enumerate(self.sims):
             nb, slot, rows, en, ep, er, gh = connect_plan(self.parts, r)
             sim.halo_connect([infos[q] for q in nb], slot, rows, en, ep, er, gh)
+        if self.cparts is not None:
+            cinfos = [sim.cell_halo_info() for sim in self.sims]
+            for r, sim in enumerate(self.sims):
+                peers, slot, pl, po, en, ep, im = cell_connect_plan(self.cparts, r)
+                sim.cell_halo_connect([cinfos[q] for q in peers], slot, pl, po, en, ep, im, self.margin)
         self.connected = True
+
+    def owned_cell_field(self, r, field):
+        """(node ids, values) of the cell rows rank r owns (every row when the cell is replicated)"""
+        ids = self.cparts[r].owned_nodes(self.ncell) if self.cparts is not None else np.arange(self.ncell)
+        return ids, self.sims[r].get(self.CELL, field)[ids]
 
     def step_n(self, n, dt):
         if not self.connected:
@@ -243,7 +360,8 @@ def exchange_rows(dist, table, part, comps, device):
 class PartitionedSim:
     """One rank of a substrate-partitioned run: full cell + this rank's substrate strip on one GPU."""
 
-    def __init__(self, variant, cell_mesh, subs_mesh, dist, device_index, rng=(1, 1), params=None, halo="peer", balance=True):
+    def __init__(self, variant, cell_mesh, subs_mesh, dist, device_index, rng=(1, 1), params=None, halo="peer", balance=True,
+                 cell="replicated", margin=0.15):
         import torch
         from . import ulstep
         from ._lib import CELL, SUBS
@@ -253,9 +371,22 @@ class PartitionedSim:
         self.halo = halo
         self.connected = False
         xs, ts = subs_mesh
-        # strips of equal COST: nodes under the cell also gather integrin forces (balance=False: equal node counts)
-        self.parts = strip_partition(xs, ts, self.world, cell_weights(xs, cell_mesh[0]) if balance else None)
+        if cell == "partitioned" and halo != "peer":
+            raise ValueError("a partitioned cell needs the fused peer-memory exchange (halo='peer')")
+        # strips of equal COST: nodes under the cell also gather integrin forces, and -- with the cell partitioned too -- carry the
+        # cost of the cell nodes above them (balance=False: equal node counts)
+        w = None
+        if balance:
+            w = cell_weights(xs, cell_mesh[0])
+            if cell == "partitioned":
+                w = w + cell_column_weights(xs, cell_mesh[0])
+        self.parts = strip_partition(xs, ts, self.world, w)
         self.part = self.parts[self.rank]
+        self.cparts = cell_partition(self.parts, cell_mesh[0], cell_mesh[1], xs, margin) if cell == "partitioned" else None
+        self.cpart = self.cparts[self.rank] if self.cparts is not None else None
+        self.margin = margin
+        self.ncell = len(cell_mesh[0])
+        self.CELL = CELL
         self.sim = ulstep.ULSim(variant, device=device_index, params=params, stream=torch.cuda.current_stream().cuda_stream)
         self.sim.upload_mesh(CELL, cell_mesh[0], cell_mesh[1])
         self.sim.upload_mesh(SUBS, xs[self.part.local_nodes], self.part.tri_local)
@@ -275,6 +406,11 @@ class PartitionedSim:
         self.dist.all_gather_object(infos, self.sim.halo_info())
         nb, slot, rows, en, ep, er, gh = connect_plan(self.parts, self.rank)
         self.sim.halo_connect([infos[q] for q in nb], slot, rows, en, ep, er, gh)
+        if self.cparts is not None:
+            cinfos = [None] * self.world
+            self.dist.all_gather_object(cinfos, self.sim.cell_halo_info())
+            peers, slot, pl, po, en, ep, im = cell_connect_plan(self.cparts, self.rank)
+            self.sim.cell_halo_connect([cinfos[q] for q in peers], slot, pl, po, en, ep, im, self.margin)
         self.dist.barrier()                 # nobody pushes before everybody has zeroed counters and mapped buffers
         self.connected = True
 
@@ -300,6 +436,11 @@ class PartitionedSim:
     def owned_field(self, field):
         """(global node ids, values) of this rank's owned substrate nodes"""
         return self.part.owned, self.sim.get(self.SUBS, field)[self.part.owned_local]
+
+    def owned_cell_field(self, field):
+        """(node ids, values) of the cell rows this rank owns (every row when the cell is replicated)"""
+        ids = self.cpart.owned_nodes(self.ncell) if self.cpart is not None else np.arange(self.ncell)
+        return ids, self.sim.get(self.CELL, field)[ids]
 
     def close(self):
         """Collective.  The border rows of the LAST step are plain peer stores nobody has awaited yet: a rank that unmapped or

@@ -222,6 +222,25 @@ class ULSim:
     def halo_disconnect(self):
         self._ck(self.L.wcfe_halo_disconnect(self.h))
 
+    def cell_halo_info(self):
+        """bytes of this context's wcfe_cell_halo_info (addresses + CUDA IPC handles of its cell buffers and epoch counters)"""
+        info = B.CellHaloInfo()
+        self._ck(self.L.wcfe_cell_halo_info_get(self.h, C.byref(info)))
+        return bytes(info)
+
+    def cell_halo_connect(self, peer_infos, my_slot_at_peer, patch_list, patch_owned, export_node, export_peer, import_node, margin):
+        n = len(peer_infos)
+        arr = (B.CellHaloInfo * max(1, n))()
+        for q, b in enumerate(peer_infos):
+            C.memmove(C.byref(arr[q]), b, C.sizeof(B.CellHaloInfo))
+        ia = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        slot, pl, po, en, ep, im = ia(my_slot_at_peer), ia(patch_list), ia(patch_owned), ia(export_node), ia(export_peer), ia(import_node)
+        ip = lambda a: a.ctypes.data_as(B._ip)
+        self._ck(self.L.wcfe_cell_halo_connect(self.h, n, arr, ip(slot), len(pl), ip(pl), ip(po), len(en), ip(en), ip(ep), len(im), ip(im), float(margin)))
+
+    def cell_halo_disconnect(self):
+        self._ck(self.L.wcfe_cell_halo_disconnect(self.h))
+
     def kernel_launches(self):
         return int(self.L.wcfe_kernel_launches(self.h))
 
