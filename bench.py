@@ -52,6 +52,11 @@ def parse():
     ap.add_argument("--halo", default="peer", choices=["peer", "dist"],
                     help="--mode partition: border strains pushed into the neighbours' ghost rows by the substrate kernel itself over NVLink peer "
                          "memory (default), or a host-driven torch.distributed exchange after every step (the baseline)")
+    ap.add_argument("--cell", default="partitioned", choices=["partitioned", "replicated"],
+                    help="--mode partition: every rank computes only the cell patches that reach its strip (default), or the whole cell")
+    ap.add_argument("--shape", default="sectors", choices=["sectors", "strips"],
+                    help="--mode partition: substrate cut into sectors around the cell's centroid (default: every rank gets its share of the cell) or into vertical strips")
+    ap.add_argument("--no-partition-record", action="store_true", help="N > 1, ensemble mode: skip the strong-scaling sub-record (`partition`)")
     ap.add_argument("--balance", type=int, default=1, help="--mode partition: strips of equal cost (nodes under the cell weigh 3x) instead of equal node count")
     ap.add_argument("--order", default="morton", choices=["morton", "morton_rows"], help="node numbering of the synthetic meshes")
     ap.add_argument("--diagonals", default="alternate", choices=["alternate", "same"], help="substrate triangulation: union jack (valence 4/8, default) or uniform valence 6 (diagnostic)")
@@ -217,19 +222,22 @@ def run_reference_arm(a):
     print(json.dumps(line), flush=True)
 
 
-def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
-    """Strong scaling: ONE cell + substrate; the substrate is cut into `world` strips (cell replicated, it is 1/9 of the
-    elements), every step ends with the NCCL exchange of the strip-border strains.  value counts every element once."""
+def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh, steps=None, one_gpu_ms=None):
+    """Strong scaling (BASELINE configs[3]): ONE cell + substrate over `world` GPUs.  The substrate is cut into strips of equal cost;
+    with --cell partitioned (default) every rank also computes only the cell patches that reach its strip, rows and partial sums
+    travel through peer memory inside the kernels (include/wcfe.h); --cell replicated keeps the whole cell on every rank.
+    value counts every element once.  Returns the record (rank 0) or None."""
     import torch
     from wholecellfe_b200.partition import PartitionedSim
-    sim = PartitionedSim(a.variant, cell_mesh, subs_mesh, dist, local, rng=(1, 1), halo=a.halo, balance=bool(a.balance))
+    steps = steps or a.steps
+    sim = PartitionedSim(a.variant, cell_mesh, subs_mesh, dist, local, rng=(1, 1), halo=a.halo, balance=bool(a.balance), cell=a.cell, shape=a.shape)
     ne = len(cell_mesh[1]) + len(subs_mesh[1])
     sim.step_n(a.warmup, a.dt)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     l0 = sim.sim.kernel_launches()
     e0.record()
-    sim.step_n(a.steps, a.dt)
+    sim.step_n(steps, a.dt)
     e1.record()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     l1 = sim.sim.kernel_launches()
@@ -237,38 +245,55 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     halo = sum(len(v) for v in sim.part.send.values())
-    # per-kernel durations of this rank's strip (event pairs around every launch: the PDL chain is off in this pass)
+    cell_rows = sum(len(v) for v in sim.cpart.exports.values()) if sim.cpart is not None else 0
+    # per-kernel durations of this rank's share (event pairs around every launch: the PDL chain is off in this pass)
     sim.sim.set_profile(True)
     sim.step_n(10, a.dt)
     kms, kcnt = sim.sim.kernel_ms()
     sim.sim.set_profile(False)
     names = ["k_predict_cell", "k_bond", "k_cell_patch", "k_boundary_finish", "k_subs_ring", "k_bucket_reduce"]
     per_kernel = {n: kms[i] / kcnt[i] for i, n in enumerate(names) if kcnt[i]}
+    pk = torch.tensor([per_kernel.get(n, 0.0) for n in names], dtype=torch.float64, device="cuda")
+    pk_all = [torch.zeros_like(pk) for _ in range(world)]
+    dist.all_gather(pk_all, pk)
     # parity at full size: every rank repeats the same steps on the WHOLE mesh on its own GPU and compares its owned rows bit for bit
     import wholecellfe_b200 as W
-    total_steps = a.warmup + a.steps + 10
+    total_steps = a.warmup + steps + 10
     ids, ea_part = sim.owned_field("ea"); _, v_part = sim.owned_field("V")
-    xc_part = sim.sim.get(W.CELL, "x")
-    part0 = {"substrate_nodes_local": int(len(sim.part.local_nodes)), "owned": int(len(sim.part.owned)), "ghosts": int(len(sim.part.ghosts))}
+    cid, xc_part = sim.owned_cell_field("x"); _, cc_part = sim.owned_cell_field("cC"); _, cv_part = sim.owned_cell_field("V")
+    part0 = {"substrate_nodes_local": int(len(sim.part.local_nodes)), "owned": int(len(sim.part.owned)), "ghosts": int(len(sim.part.ghosts)),
+             "cell_patches_computed": int(len(sim.cpart.patch_list)) if sim.cpart is not None else None,
+             "cell_patches_owned": int(len(sim.cpart.owned_patches)) if sim.cpart is not None else None}
+    npl = torch.tensor([len(sim.cpart.patch_list) if sim.cpart is not None else 0], dtype=torch.int64, device="cuda")
+    npl_all = [torch.zeros_like(npl) for _ in range(world)]
+    dist.all_gather(npl_all, npl)
     sim.close()                                  # collective: sync + barrier before any rank unmaps its halo buffers
     one = W.ULSim(a.variant, device=local)
     one.upload_mesh(W.CELL, cell_mesh[0], cell_mesh[1]); one.upload_mesh(W.SUBS, subs_mesh[0], subs_mesh[1]); one.set_rng(1, 1)
     one.step_n(total_steps, a.dt, 0.0)
-    ok = bool(np.array_equal(one.get(W.SUBS, "ea")[ids], ea_part) and np.array_equal(one.get(W.SUBS, "V")[ids], v_part) and np.array_equal(one.get(W.CELL, "x"), xc_part))
+    one_ms = one.last_step_ms() / total_steps
+    ok = bool(np.array_equal(one.get(W.SUBS, "ea")[ids], ea_part) and np.array_equal(one.get(W.SUBS, "V")[ids], v_part) and
+              np.array_equal(one.get(W.CELL, "x")[cid], xc_part) and np.array_equal(one.get(W.CELL, "cC")[cid], cc_part) and np.array_equal(one.get(W.CELL, "V")[cid], cv_part))
     one.close()
     okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
     dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        print(json.dumps({"metric": METRIC, "value": ne * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                          "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "ONE synthetic %d-triangle cell on %d-node substrate, substrate in %d strips, cell replicated"
-                                                 % (len(cell_mesh[1]), len(subs_mesh[0]), world), "variant": a.variant, "dt": a.dt,
-                                     "parallelism": ("substrate strip partition x%d, halo exchange fused into k_subs_ring over NVLink peer memory (%d border nodes x 24 B per step)" if a.halo == "peer"
-                                                     else "substrate strip partition x%d + per-step torch.distributed (NCCL) halo exchange (%d border nodes x 24 B per step)") % (world, halo)},
-                          "gpu_launches": l1 - l0, "rank0_per_kernel_ms": per_kernel,
-                          "bitwise_equal_to_single_gpu": {"value": bool(int(okt.item())), "steps": total_steps, "what": "owned substrate rows (ea, V) of every rank and the replicated cell's positions against the same steps of the whole mesh on one GPU"},
-                          "strips": "equal cost (nodes under the cell x3)" if a.balance else "equal node count", "rank0_strip": part0}), flush=True)
-    dist.destroy_process_group()
+    if rank != 0:
+        return None
+    base_ms = one_gpu_ms if one_gpu_ms else one_ms
+    cellwhat = ("cell partitioned by patches (replicated storage; %d cell rows x 72 B pushed per step by rank 0, patches computed per rank %s of %d)"
+                % (cell_rows, [int(v.item()) for v in npl_all], (len(cell_mesh[0]) + 127) // 128)) if a.cell == "partitioned" else "cell replicated"
+    return {"metric": METRIC, "value": ne * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": a.warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ONE synthetic %d-triangle cell on %d-node substrate, substrate in %d %s, %s"
+                                   % (len(cell_mesh[1]), len(subs_mesh[0]), world, a.shape, cellwhat), "variant": a.variant, "dt": a.dt,
+                       "parallelism": ("substrate partition x%d, halo exchange fused into the kernels over NVLink peer memory (%d border nodes x 24 B per step from rank 0)" if a.halo == "peer"
+                                       else "substrate partition x%d + per-step torch.distributed (NCCL) halo exchange (%d border nodes x 24 B per step from rank 0)") % (world, halo)},
+            "one_gpu_ms_per_step": base_ms, "speedup_vs_one_gpu": base_ms / (ms / steps),
+            "gpu_launches": l1 - l0, "per_kernel_ms_by_rank": {n: [float(v[i].item()) for v in pk_all] for i, n in enumerate(names) if any(float(v[i].item()) > 0 for v in pk_all)},
+            "bitwise_equal_to_single_gpu": {"value": bool(int(okt.item())), "steps": total_steps,
+                                            "what": "owned substrate rows (ea, V) and owned cell rows (x, V, cC) of every rank against the same steps of the whole mesh on one GPU"},
+            "pieces": ("%s of equal cost (nodes under the cell x3%s)" % (a.shape, ", + 4 per cell node above" if a.cell == "partitioned" else "")) if a.balance else "%s of equal node count" % a.shape,
+            "rank0": part0}
 
 
 def other_configs(W):
@@ -315,6 +340,55 @@ def other_configs(W):
     out["config5_batch_element_steps_per_sec"] = n * run.elements_per_cell * 400 / (w1 - w0)
     out["config5_us_per_cell_step"] = (w1 - w0) / (400 * n) * 1e6
     run.close()
+    return out
+
+
+def config5_sweep(W, dist, rank, world, local, per_gpu=512, steps=400):
+    """BASELINE configs[4]: per_gpu x world independent cells of the shipped example size (4 096 at 8 GPUs) over stiffness law x
+    ligand density x seed (ensemble.sweep_grid), each rank's shard as batched contexts (gridDim.y = cells), no communication.
+    Wall clock between barriers, max over ranks."""
+    import torch
+    from wholecellfe_b200.ensemble import sweep_grid, EnsembleRunner, partition
+    path = os.path.join(ROOT, "tests", "golden", "example_meshes.npz")
+    d = np.load(path)
+    xc, tc, xs, ts = d["cell_xyz"], d["cell_tri"], d["subs_xyz"], d["subs_tri"]
+    cells = sweep_grid(per_gpu * world)
+    mine = [cells[i] for i in partition(len(cells), world, rank)]
+    run = EnsembleRunner(mine, (xc, tc), (xs, ts), device=local)
+    run.advance(40, 0.005)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    w0 = time.perf_counter(); run.advance(steps, 0.005); torch.cuda.synchronize(); w = time.perf_counter() - w0
+    tt = torch.tensor([w], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wmax = float(tt.item())
+    finite = bool(np.isfinite(run.get(0, W.CELL, "x")).all() and np.isfinite(run.get(len(mine) - 1, W.CELL, "x")).all())
+    run.close()
+    return {"cells": len(cells), "cells_per_gpu": per_gpu, "n_gpus": world, "steps": steps, "element_steps_per_sec": len(cells) * run.elements_per_cell * steps / wmax,
+            "us_per_cell_step": wmax / (steps * per_gpu) * 1e6, "finite": finite,
+            "what": "laws k1/k31/kMD x log-spaced rho_i_max 1..100 x seeds, %d-triangle cell on %d-triangle substrate each, dt 0.005, Philox, batched (one launch per kernel per step per law group)"
+                    % (len(tc), len(ts))}
+
+
+def pcie_concurrent(torch, dist, world, nbytes, reps=20):
+    """Every rank copies `nbytes` (the cell's Vec3d image) pinned host -> device and back, all ranks at once: GB/s per rank (slowest)."""
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory(); dv = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    out = {}
+    for name, src, dst in (("h2d", h, dv), ("d2h", dv, h)):
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        w0 = time.perf_counter()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        out[name + "_gbs_per_rank"] = nbytes * reps / float(tt.item()) / 1e9
+    out["bytes"] = nbytes; out["ranks_at_once"] = world
     return out
 
 
@@ -369,7 +443,10 @@ def main():
     xc, tc, xs, ts = workload_meshes(a.cell_tris, a.subs_side, a.order, a.diagonals)
     nn_c, ne_c, nn_s, ne_s = len(xc), len(tc), len(xs), len(ts)
     if a.mode == "partition" and world > 1:
-        run_partition_mode(a, dist, rank, world, local, (xc, tc), (xs, ts))
+        rec = run_partition_mode(a, dist, rank, world, local, (xc, tc), (xs, ts))
+        if rank == 0:
+            print(json.dumps(rec), flush=True)
+        dist.destroy_process_group()
         return
     sim = W.ULSim(a.variant, device=local, stream=stream.cuda_stream)
     sim.upload_mesh(W.CELL, xc, tc); sim.upload_mesh(W.SUBS, xs, ts)
@@ -491,6 +568,26 @@ def main():
     other = None
     if rank == 0 and world == 1 and not a.no_other_configs:
         other = other_configs(W)
+    # BASELINE configs[4] as stated: 512 independent config-1 cells per GPU (4 096 over 8 GPUs), stiffness law x ligand density x seed,
+    # batched per GPU, no communication; and what the bus gives every rank when all N move their 12 MB at once (explains e2e scaling)
+    config5 = pcie = None
+    if not a.no_other_configs:
+        try:
+            config5 = config5_sweep(W, dist, rank, world, local)
+        except Exception as e:
+            config5 = {"skipped": str(e)}
+        try:
+            pcie = pcie_concurrent(torch, dist, world, 3 * 8 * nn_c)
+        except Exception as e:
+            pcie = {"skipped": str(e)}
+    # strong scaling of the SAME workload over the N GPUs of this run (BASELINE configs[3]), as a sub-record the driver's scaling run sees
+    partition = None
+    if world > 1 and not a.no_partition_record:
+        sim.close()
+        try:
+            partition = run_partition_mode(a, dist, rank, world, local, (xc, tc), (xs, ts), steps=min(max(a.steps, 100), 200), one_gpu_ms=ms_max / a.steps)
+        except Exception as e:                               # never lose the main line
+            partition = {"failed": str(e)}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -501,6 +598,12 @@ def main():
             line["cpu_baseline"] = cpu
         if other:
             line["other_configs"] = other
+        if config5:
+            line["config5_sweep"] = config5
+        if pcie:
+            line["pcie_concurrent"] = pcie
+        if partition:
+            line["partition"] = partition
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -152,14 +152,14 @@ def _initial_strain(nn):
     return ea
 
 
-def _gpu_worker(rank, world, port, backend, halo, q):
+def _gpu_worker(rank, world, port, backend, halo, q, cell="replicated"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dev = rank if backend == "nccl" else 0
     torch.cuda.set_device(dev)
     dist.init_process_group(backend, rank=rank, world_size=world)
     from wholecellfe_b200.partition import PartitionedSim
     xc, tc = disk_mesh(6000); xs, ts = square_mesh(120)
-    sim = PartitionedSim("k31", (xc, tc), (xs, ts), dist, dev, rng=(1, 5), halo=halo)
+    sim = PartitionedSim("k31", (xc, tc), (xs, ts), dist, dev, rng=(1, 5), halo=halo, cell=cell)
     sim.set_subs_field("ea", _initial_strain(len(xs)))
     sim.step_n(12, 2e-4)
     out = {}
@@ -167,7 +167,10 @@ def _gpu_worker(rank, world, port, backend, halo, q):
         ids, vals = sim.owned_field(f)
         out[f] = (ids, vals)
     out["cell_x"] = sim.sim.get(0, "x"); out["cell_cC"] = sim.sim.get(0, "cC")
+    for f in ("x", "V", "ea", "cC", "fa_u"):
+        out["cell_owned_" + f] = sim.owned_cell_field(f)
     q.put((rank, out))
+    sim.close()
     dist.barrier(); dist.destroy_process_group()
 
 
@@ -207,8 +210,8 @@ def test_in_process_strips_with_fused_peer_halo_equal_single_gpu_bitwise(world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 3, 5])
-def test_partitioned_cell_in_process_equals_single_gpu_bitwise(world):
+@pytest.mark.parametrize("world,shape", [(2, "strips"), (3, "strips"), (5, "strips"), (3, "sectors"), (8, "sectors")])
+def test_partitioned_cell_in_process_equals_single_gpu_bitwise(world, shape):
     """BASELINE configs[3] with the CELL partitioned as well: every strip computes only the cell patches that can reach its
     substrate strip, the rows its patches read from elsewhere are pushed by their owners through peer memory, every rank adds
     the same area / centroid partial sums in the single-GPU order.  The cell rows every rank OWNS tile the single-GPU cell bit
@@ -217,9 +220,10 @@ def test_partitioned_cell_in_process_equals_single_gpu_bitwise(world):
     from wholecellfe_b200.partition import InProcessStrips
     xc, tc = disk_mesh(6000); xs, ts = square_mesh(120)
     ndev = torch.cuda.device_count()
-    run = InProcessStrips("k31", (xc, tc), (xs, ts), [r % ndev for r in range(world)], rng=(1, 5), cell="partitioned")
+    run = InProcessStrips("k31", (xc, tc), (xs, ts), [r % ndev for r in range(world)], rng=(1, 5), cell="partitioned", shape=shape)
     assert sum(len(c.owned_patches) for c in run.cparts) == (len(xc) + 127) // 128
     assert min(len(c.patch_list) for c in run.cparts) < (len(xc) + 127) // 128          # somebody really computes less than the whole cell
+    assert max(len(neighbours(p)) for p in run.parts) <= 8
     run.set_subs_field("ea", _initial_strain(len(xs)))
     run.step_n(5, 2e-4); run.step_n(7, 2e-4)
     g = _single_gpu_reference()
@@ -269,6 +273,37 @@ def test_two_rank_partition_equals_single_gpu_bitwise(halo):
     for r in range(world):                                    # the replicated cell evolves identically everywhere
         assert np.array_equal(res[r]["cell_x"], g.get(W.CELL, "x")) and np.array_equal(res[r]["cell_cC"], g.get(W.CELL, "cC"))
     assert np.abs(g.get(W.SUBS, "ea")).max() > 1e-5 and np.abs(g.get(W.SUBS, "A")).max() > 0
+
+
+@pytest.mark.gpu
+def test_two_rank_partitioned_cell_across_processes_equals_single_gpu_bitwise():
+    """the partitioned cell between two PROCESSES (CUDA IPC mappings of the peer's cell buffers; NVLink where the box has two
+    GPUs, one GPU shared otherwise): owned cell rows and owned substrate rows tile the single-GPU run bit for bit"""
+    import wholecellfe_b200 as W
+    world = 2
+    backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
+    ctx = mp.get_context("spawn"); q = ctx.Queue(); port = _free_port()
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, backend, "peer", q, "partitioned")) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=120); assert p.exitcode == 0
+    g = _single_gpu_reference()
+    for f in ("x", "V", "ea", "cC", "fa_u"):
+        ref = g.get(W.CELL, f)
+        got = np.full_like(ref, np.nan)
+        for r in range(world):
+            ids, vals = res[r]["cell_owned_" + f]
+            got[ids] = vals
+        assert np.array_equal(got, ref), f
+    for f in ("V", "A", "ea"):
+        ref = g.get(W.SUBS, f)
+        got = np.full_like(ref, np.nan)
+        for r in range(world):
+            ids, vals = res[r][f]
+            got[ids] = vals
+        assert np.array_equal(got, ref), f
 
 
 @pytest.mark.gpu

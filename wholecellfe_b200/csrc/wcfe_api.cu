@@ -573,7 +573,9 @@ int build_buckets(wcfe_ctx *c) {
     c->reduce_warp = dens >= 3.0 ? 1 : 0;
     if (const char *e = std::getenv("WCFE_REDUCE_WARP")) c->reduce_warp = std::atoi(e) ? 1 : 0;
     if (c->subs_kernel == 2) {
-        c->big_cap = std::max(64, 2 * cs.nn);
+        // every triangle that holds an anchor is listed once: at most all of them, and an anchor ON a vertex counts for the whole fan
+        // (UL:1309-1452 has no break), so 2 per cell node is not a bound -- 8 covers a cell snapped onto a union-jack substrate's vertices
+        c->big_cap = (int)std::max<long long>(64, std::min<long long>(ss.ne, 8LL * cs.nn));
         CK(c->big_count.alloc((size_t)c->nrep)); CK(c->big_list.alloc((size_t)c->big_cap * c->nrep));
         CK(cudaMemset(c->big_count.p, 0, sizeof(unsigned int) * c->nrep));
     }
@@ -749,46 +751,62 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         c->launches += 2;
     }
     {
+    const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // boundary finish: a few small blocks, latency- not throughput-bound
+    CellPartView cpf{};
+    const bool part = c->cpart.active && planar && (which & 1);
+    if (part) {
+        cpf.peer = c->cpart.peers.p; cpf.npeer = c->cpart.npeer; cpf.flags = c->cpart.flags.p; cpf.step = c->cpart.step;
+        cpf.bnd_local = c->cpart.bnd_local.p; cpf.bexp_ptr = c->cpart.bexp_ptr.p; cpf.bexp_peer = c->cpart.bexp_peer.p; cpf.err = c->d_err.p;
+    }
+    const double *parts = (part && (c->cpart.step & 1u)) ? c->cpart.partials2.p : c->d_partials.p;
+    // bucket reduction: one warp per listed triangle (coarse substrate), or one thread (about one triangle in two cell nodes is
+    // listed on a substrate finer than the cell)
+    const int gr = c->reduce_warp ? std::max(1, std::min(4 * c->num_sms, (cs.nn / 64 + kReduceWarps - 1) / kReduceWarps))
+                                  : std::max(1, std::min(8 * c->num_sms, (cs.nn + kReduceWarps * 32 - 1) / (kReduceWarps * 32)));
+    if (pdl && reduce) {
+        // production chain: boundary finish and bucket reduction as ONE link (k_finish_reduce)
+        const dim3 g2(fb + gr, R), b2(kReduceWarps * 32);
+#define WCFE_FR(B_, P_, W_) CK(launch_pdl(k_finish_reduce<B_, P_, W_>, g2, b2, 0, c->stream, fb, cv, bv, c->k, npart, parts, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, bt, dtd_c, cpf, sv, bk))
+        if (part) { if (c->reduce_warp) WCFE_FR(false, true, true); else WCFE_FR(false, true, false); }
+        else if (batch) { if (c->reduce_warp) WCFE_FR(true, false, true); else WCFE_FR(true, false, false); }
+        else { if (c->reduce_warp) WCFE_FR(false, false, true); else WCFE_FR(false, false, false); }
+#undef WCFE_FR
+        c->launches += 1;
+    } else {
+    {
     // fork: the finish kernel goes to the side stream first (so that its few blocks are placed as soon as the cell kernel drains)
     cudaStream_t fs = c->stream;
     const bool forked = overlap && !pdl && !c->cpart.active;      // (partitioned cell: the substrate kernel's first thread vouches for the finish kernel's completion)
     if (forked) { CK(cudaEventRecord(c->ev_fork, c->stream)); CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0)); fs = c->side; }
     { ProfScope ps(c, K_FINISH, fs);
-    const int fb = std::max(1, std::min(64, (cs.nb + 255) / 256));      // a few small blocks: latency-, not throughput-bound
-    const CellPartView nocp{};
-    if (c->cpart.active && planar && (which & 1)) {
-        CellPartView cpf{};
-        cpf.peer = c->cpart.peers.p; cpf.npeer = c->cpart.npeer; cpf.flags = c->cpart.flags.p; cpf.step = c->cpart.step;
-        cpf.bnd_local = c->cpart.bnd_local.p; cpf.bexp_ptr = c->cpart.bexp_ptr.p; cpf.bexp_peer = c->cpart.bexp_peer.p; cpf.err = c->d_err.p;
-        const double *parts = (c->cpart.step & 1u) ? c->cpart.partials2.p : c->d_partials.p;
+    if (part) {
         if (pdl) CK(launch_pdl(k_boundary_finish<false, false, true>, dim3(fb), dim3(256), 0, fs, cv, bv, c->k, npart, parts, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, cpf));
         else k_boundary_finish<false, false, true><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, parts, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, cpf);
-        c->cpart.step++;
     }
-    else if (pdl && batch) CK(launch_pdl(k_boundary_finish<false, true>, dim3(fb, R), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, nocp));
-    else if (pdl) CK(launch_pdl(k_boundary_finish<false, false>, dim3(fb), dim3(256), 0, fs, cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, nocp));
-    else if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, nocp);
-    else if (c->debug) k_boundary_finish<true><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt, dtd_c, nocp);
-    else k_boundary_finish<false><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, c->d_partials.p, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, nocp); }
+    else if (pdl && batch) CK(launch_pdl(k_boundary_finish<false, true>, dim3(fb, R), dim3(256), 0, fs, cv, bv, c->k, npart, parts, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, cpf));
+    else if (pdl) CK(launch_pdl(k_boundary_finish<false, false>, dim3(fb), dim3(256), 0, fs, cv, bv, c->k, npart, parts, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, cpf));
+    else if (batch) k_boundary_finish<false, true><<<dim3(fb, R), 256, 0, fs>>>(cv, bv, c->k, npart, parts, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, cpf);
+    else if (c->debug) k_boundary_finish<true><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, parts, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, dview(cs), bt, dtd_c, cpf);
+    else k_boundary_finish<false><<<fb, 256, 0, fs>>>(cv, bv, c->k, npart, parts, v_old, a_old, dt, dt_real, c->d_diag.p, c->d_err.p, DebugView{}, bt, dtd_c, cpf); }
     if (forked) { CK(cudaEventRecord(c->ev_join, c->side)); joined = false; }
     }
     if (reduce) {
         ProfScope pr(c, K_REDUCE);
         if (c->reduce_warp) {
-            const int gr = std::max(1, std::min(4 * c->num_sms, (cs.nn / 64 + kReduceWarps - 1) / kReduceWarps));
             if (pdl && batch) CK(launch_pdl(k_bucket_reduce<true, true>, dim3(gr, R), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
             else if (pdl) CK(launch_pdl(k_bucket_reduce<false, true>, dim3(gr), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
             else if (batch) k_bucket_reduce<true, true><<<dim3(gr, R), kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
             else k_bucket_reduce<false, true><<<gr, kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
         } else {
-            // one thread per listed triangle; about one triangle in two cell nodes is listed on a substrate finer than the cell
-            const int gr = std::max(1, std::min(8 * c->num_sms, (cs.nn + kReduceWarps * 32 - 1) / (kReduceWarps * 32)));
             if (pdl && batch) CK(launch_pdl(k_bucket_reduce<true, false>, dim3(gr, R), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
             else if (pdl) CK(launch_pdl(k_bucket_reduce<false, false>, dim3(gr), dim3(kReduceWarps * 32), 0, c->stream, sv, cv, bk, bt));
             else if (batch) k_bucket_reduce<true, false><<<dim3(gr, R), kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
             else k_bucket_reduce<false, false><<<gr, kReduceWarps * 32, 0, c->stream>>>(sv, cv, bk, bt);
         }
         c->launches += 1;
+    }
+    }
+    if (part) c->cpart.step++;
     }
     c->launches += 1;
     cs.ea_cur ^= 1;

@@ -428,19 +428,16 @@ __device__ __noinline__ void cell_part_wait(const unsigned long long *flags, int
         }
 }
 
-template <bool DBG, bool BATCH = false, bool PART = false>
-__global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k_, int npart, const double *__restrict__ partials,
-                                                          const double *__restrict__ V_in, const double *__restrict__ A_in,
-                                                          double dt, double dt_real, double *__restrict__ diag, int *__restrict__ err, DebugView dbg,
-                                                          BatchView bt, double dt_drv, CellPartView cp) {
-    __shared__ double sh[4 * 32];
-    __shared__ double tot[4];
-    pdl_launch_dependents();      // the substrate kernel may start its cell-independent part now
-    pdl_wait();                   // everything below reads what the cell kernel wrote
+// (the work of one block of `nblk`; the caller has passed griddepcontrol.wait.  sh: 4 * 32 doubles, tot: 4 doubles of shared memory)
+template <bool DBG, bool BATCH, bool PART>
+__device__ __forceinline__ void boundary_finish_body(int bid, int nblk, double *sh, double *tot, SurfView s, BoundaryView b, const Consts &k_, int npart,
+                                                     const double *__restrict__ partials, const double *__restrict__ V_in, const double *__restrict__ A_in,
+                                                     double dt, double dt_real, double *__restrict__ diag, int *__restrict__ err, const DebugView &dbg,
+                                                     const BatchView &bt, double dt_drv, const CellPartView &cp) {
     if (PART) {
         // this rank's cell kernel is complete: tell everybody that the partial sums of its patches are in their arrays, then wait
         // for everybody else's
-        if (blockIdx.x == 0 && threadIdx.x == 0) cell_part_signal(cp.peer, cp.npeer, 1);
+        if (bid == 0 && threadIdx.x == 0) cell_part_signal(cp.peer, cp.npeer, 1);
         if (threadIdx.x == 0) cell_part_wait(cp.flags, 8, cp.npeer, (unsigned long long)cp.step + 1ull, cp.err);
         __syncthreads();
     }
@@ -457,7 +454,7 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
     block_reduce4(v, sh);
     if (threadIdx.x == 0) {
         tot[0] = v[0]; tot[1] = v[1] / v[0]; tot[2] = v[2] / v[0]; tot[3] = v[3] / v[0];
-        if (blockIdx.x == 0) {
+        if (bid == 0) {
             for (int q = 0; q < 4; q++) diag[q] = tot[q];
             // NaN/Inf sentinel: the total area and the centroid see every cell node's position once per step
             if (!(isfinite(tot[0]) && isfinite(tot[1]) && isfinite(tot[2]))) atomicOr(err, ERR_NAN);
@@ -466,7 +463,7 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
     __syncthreads();
     const double area_tot = tot[0];
     const int np = s.np;
-    for (int bi = blockIdx.x * blockDim.x + threadIdx.x; bi < b.nb; bi += gridDim.x * blockDim.x) {
+    for (int bi = bid * blockDim.x + threadIdx.x; bi < b.nb; bi += nblk * blockDim.x) {
         if (PART && !cp.bnd_local[bi]) continue;      // its patch is another rank's: the record below is stale here
         const int i = b.node[bi];
         const double *o = b.buf + (size_t)16 * bi;
@@ -488,6 +485,18 @@ __global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryVi
             if (DBG) dbg.f_area[c * np + i] = F_area;
         }
     }
+}
+
+template <bool DBG, bool BATCH = false, bool PART = false>
+__global__ void __launch_bounds__(1024) k_boundary_finish(SurfView s, BoundaryView b, Consts k_, int npart, const double *__restrict__ partials,
+                                                          const double *__restrict__ V_in, const double *__restrict__ A_in,
+                                                          double dt, double dt_real, double *__restrict__ diag, int *__restrict__ err, DebugView dbg,
+                                                          BatchView bt, double dt_drv, CellPartView cp) {
+    __shared__ double sh[4 * 32];
+    __shared__ double tot[4];
+    pdl_launch_dependents();      // the substrate kernel may start its cell-independent part now
+    pdl_wait();                   // everything below reads what the cell kernel wrote
+    boundary_finish_body<DBG, BATCH, PART>(blockIdx.x, gridDim.x, sh, tot, s, b, k_, npart, partials, V_in, A_in, dt, dt_real, diag, err, dbg, bt, dt_drv, cp);
 }
 
 // ---- updateForces_Explicit, substrate overload (UL:429-504) incl. driverVelocities_Biaxial (UL:275-345) and

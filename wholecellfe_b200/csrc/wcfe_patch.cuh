@@ -578,16 +578,15 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
 //                 the lanes rank the items (all pairs, 1/32 each), evaluate them in parallel, park the terms in shared memory
 //                 by rank, and six lanes form the six sums in the reference's order.
 constexpr int kReduceWarps = 8, kReduceWindow = 128;
+// (the work of block `bid` of `nblk`; the caller has passed griddepcontrol.wait.  term: [kReduceWarps][kReduceWindow][6] doubles of shared
+// memory for WARP, unused otherwise)
 template <bool BATCH, bool WARP>
-__global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s, SurfView c, BucketView bk, BatchView bt) {
-    __shared__ double term[WARP ? kReduceWarps : 1][WARP ? kReduceWindow : 1][6];
-    pdl_launch_dependents();
-    pdl_wait();                   // the list and the buckets are the cell kernel's output
+__device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*term)[kReduceWindow][6], SurfView s, SurfView c, BucketView bk, const BatchView &bt) {
     if (BATCH) { const size_t r = blockIdx.y; batch_shift(s, r); batch_shift(c, r); batch_shift(bk, bt, r); }
     const int nbig = (int)min(*bk.big_count, (unsigned int)bk.big_cap);
     const double2 *anc2 = reinterpret_cast<const double2 *>(c.anc);
     if (!WARP) {
-        for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbig; b += gridDim.x * blockDim.x) {
+        for (int b = bid * blockDim.x + threadIdx.x; b < nbig; b += nblk * blockDim.x) {
             const int e = bk.big_list[b];
             int cnt = (int)(unsigned int)bk.head[e];
             if (cnt > bk.cap) cnt = bk.cap;
@@ -614,7 +613,7 @@ __global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s,
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double (*tw)[6] = term[WARP ? warp : 0];
-    for (int b = blockIdx.x * kReduceWarps + warp; b < nbig; b += gridDim.x * kReduceWarps) {
+    for (int b = bid * kReduceWarps + warp; b < nbig; b += nblk * kReduceWarps) {
         const int e = bk.big_list[b];
         int cnt = (int)(unsigned int)bk.head[e];
         if (cnt > bk.cap) cnt = bk.cap;
@@ -646,6 +645,34 @@ __global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s,
         }
         if (lane < 6) reinterpret_cast<double *>(items)[lane] = acc;     // every lane has finished reading the items (syncwarp above)
     }
+}
+
+template <bool BATCH, bool WARP>
+__global__ void __launch_bounds__(kReduceWarps * 32) k_bucket_reduce(SurfView s, SurfView c, BucketView bk, BatchView bt) {
+    __shared__ double term[WARP ? kReduceWarps : 1][WARP ? kReduceWindow : 1][6];
+    pdl_launch_dependents();
+    pdl_wait();                   // the list and the buckets are the cell kernel's output
+    bucket_reduce_body<BATCH, WARP>(blockIdx.x, gridDim.x, reinterpret_cast<double (*)[kReduceWindow][6]>(term), s, c, bk, bt);
+}
+
+// ---- boundary finish and bucket reduction in ONE launch (production chain) ------------------------------------------------------
+// Both follow the cell kernel, neither needs the other, both are a handful of latency-bound blocks: as separate links of the
+// programmatic-dependent-launch chain the reduction could not start before the LAST block of the finish kernel had retired
+// (griddepcontrol.wait waits for the whole prerequisite grid) -- 13-18 us per step in which the GPU idles.  Blocks [0, nfb) finish
+// the boundary, the others reduce; the substrate kernel's wait then covers both.
+template <bool BATCH, bool PART, bool WARP>
+__global__ void __launch_bounds__(kReduceWarps * 32) k_finish_reduce(int nfb, SurfView cs, BoundaryView b, Consts k_, int npart, const double *__restrict__ partials,
+                                                                     const double *__restrict__ V_in, const double *__restrict__ A_in, double dt, double dt_real,
+                                                                     double *__restrict__ diag, int *__restrict__ err, BatchView bt, double dt_drv, CellPartView cp,
+                                                                     SurfView ss, BucketView bk) {
+    __shared__ double smem_d[WARP ? kReduceWarps * kReduceWindow * 6 : 4 * 32 + 4];
+    static_assert(kReduceWarps * kReduceWindow * 6 >= 4 * 32 + 4, "the finish blocks' scratch fits the reduction's");
+    pdl_launch_dependents();
+    pdl_wait();                   // everything below reads what the cell kernel wrote
+    if ((int)blockIdx.x < nfb)
+        boundary_finish_body<false, BATCH, PART>(blockIdx.x, nfb, smem_d, smem_d + 4 * 32, cs, b, k_, npart, partials, V_in, A_in, dt, dt_real, diag, err, DebugView{}, bt, dt_drv, cp);
+    else
+        bucket_reduce_body<BATCH, WARP>((int)blockIdx.x - nfb, (int)gridDim.x - nfb, reinterpret_cast<double (*)[kReduceWindow][6]>(smem_d), ss, cs, bk, bt);
 }
 
 // ---- cell: the whole cell side of one UL step in ONE kernel ---------------------------------------------------------

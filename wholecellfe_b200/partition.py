@@ -45,16 +45,10 @@ def cell_weights(subs_xyz, cell_xyz, under_cell=2.0):
     return 1.0 + under_cell * inside
 
 
-def strip_partition(xyz, tri, world, weights=None):
-    """Cut the mesh into `world` vertical strips of (almost) equal node count -- or, with `weights` (one per node), of equal
-    total weight, so that the strips under the cell hold fewer nodes.  Returns the list of StripPart.
-
-    A node belongs to the strip its x coordinate falls in (ties by node id); a rank holds every element with at least one
-    owned vertex, hence a one-ring of ghost nodes.  Local numbering keeps the global (space-filling-curve) order, and local
-    elements keep ascending global ids, so every nodal sum is formed in the same order as on a single GPU."""
-    xyz = np.asarray(xyz); tri = np.asarray(tri)
-    nn = len(xyz)
-    order = np.lexsort((np.arange(nn), xyz[:, 0]))
+def _cut_by_key(key, world, weights):
+    """owner rank per node: nodes sorted by `key` (ties by id) and cut into `world` runs of equal count / equal total weight"""
+    nn = len(key)
+    order = np.lexsort((np.arange(nn), key))
     owner = np.empty(nn, dtype=np.int32)
     if weights is None:
         bounds = [(nn * r) // world for r in range(world + 1)]
@@ -63,6 +57,14 @@ def strip_partition(xyz, tri, world, weights=None):
         bounds = [0] + [int(np.searchsorted(cw, cw[-1] * r / world)) for r in range(1, world)] + [nn]
     for r in range(world):
         owner[order[bounds[r]:bounds[r + 1]]] = r
+    return owner
+
+
+def partition_from_owner(xyz, tri, owner, world):
+    """The StripPart of every rank from a node -> owner-rank map: a rank holds every element with at least one owned vertex, hence
+    a one-ring of ghost nodes.  Local numbering keeps the global (space-filling-curve) order, and local elements keep ascending
+    global ids, so every nodal sum is formed in the same order as on a single GPU."""
+    tri = np.asarray(tri)
     tri_owner = owner[tri]                                   # [m,3]
     parts = []
     for r in range(world):
@@ -94,6 +96,24 @@ def strip_partition(xyz, tri, world, weights=None):
     return out
 
 
+def strip_partition(xyz, tri, world, weights=None):
+    """Cut the mesh into `world` vertical strips of (almost) equal node count -- or, with `weights` (one per node), of equal
+    total weight, so that the strips under the cell hold fewer nodes.  Returns the list of StripPart.
+    A node belongs to the strip its x coordinate falls in (ties by node id)."""
+    xyz = np.asarray(xyz)
+    return partition_from_owner(xyz, tri, _cut_by_key(xyz[:, 0], world, weights), world)
+
+
+def sector_partition(xyz, tri, world, centre, weights=None):
+    """Cut the mesh into `world` sectors around `centre` (the cell's centroid) of equal node count / equal total weight: every rank
+    then holds a wedge of the substrate AND the wedge of the cell above it, so that a partitioned cell's work spreads over all
+    ranks instead of the few whose vertical strip happens to pass under the cell.  All sectors meet at the centre: a rank may have
+    every other rank as a neighbour (world - 1 <= WCFE_HALO_MAX_PEERS)."""
+    xyz = np.asarray(xyz)
+    ang = np.arctan2(xyz[:, 1] - centre[1], xyz[:, 0] - centre[0])
+    return partition_from_owner(xyz, tri, _cut_by_key(ang, world, weights), world)
+
+
 PATCH = 128      # libwcfe's owned nodes per patch (wcfe_patch.cuh kPatch)
 
 
@@ -117,29 +137,69 @@ class CellPart:
         return ids[ids < nn]
 
 
-def cell_partition(parts, cell_xyz, cell_tri, subs_xyz, margin=0.15):
-    """Which cell patches every rank computes, owns, pushes and receives.
+def _owner_raster(parts, subs_xyz, cell_size):
+    """bit mask of the ranks that OWN a substrate node in every cell of a uniform raster over the substrate, and one node per cell"""
+    xs = np.asarray(subs_xyz)
+    x0, y0 = xs[:, 0].min(), xs[:, 1].min()
+    nx = int((xs[:, 0].max() - x0) / cell_size) + 1; ny = int((xs[:, 1].max() - y0) / cell_size) + 1
+    mask = np.zeros((ny, nx), dtype=np.uint32)
+    rep = np.full((ny, nx), -1, dtype=np.int64)
+    for r, p in enumerate(parts):
+        ix = ((xs[p.owned, 0] - x0) / cell_size).astype(np.int64); iy = ((xs[p.owned, 1] - y0) / cell_size).astype(np.int64)
+        np.bitwise_or.at(mask, (iy, ix), np.uint32(1 << r))
+        rep[iy, ix] = p.owned
+    return mask, rep, (x0, y0, nx, ny)
 
-    A rank computes every patch that can drop an anchor into its strip: the patch's x range, widened by `margin` (the largest
-    |fa_u| an anchor may be away from its node: libwcfe raises an error when an anchor leaves it; the strip's range covers its ghost
-    triangles as well).  A patch on a cut is therefore computed by both neighbours; the rank whose OWNED x range
-    holds the patch's centre owns it: it alone publishes the patch's area / centroid partial sums and pushes its rows to the ranks
-    that read them as halo rows of their own patches without computing them."""
+
+def _dilate(mask):
+    out = mask.copy()
+    ny, nx = mask.shape
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            if dx == 0 and dy == 0:
+                continue
+            ys = slice(max(0, dy), ny + min(0, dy)); yd = slice(max(0, -dy), ny + min(0, -dy))
+            xs_ = slice(max(0, dx), nx + min(0, dx)); xd = slice(max(0, -dx), nx + min(0, -dx))
+            out[yd, xd] |= mask[ys, xs_]
+    return out
+
+
+def cell_partition(parts, cell_xyz, cell_tri, subs_xyz, margin=0.15):
+    """Which cell patches every rank computes, owns, pushes and receives -- for ANY partition of the substrate (strips, sectors).
+
+    A rank computes every patch that can drop an anchor into one of its local substrate triangles.  An anchor lies within `margin`
+    of its node (libwcfe raises an error when one leaves it), a local triangle has an owned vertex, i.e. reaches at most one edge
+    length beyond the owned nodes: the ranks that own a substrate node within margin + 1.5 h of a cell node are found on a raster of
+    that cell size, dilated by one cell (conservative).  A patch on a cut is therefore computed by every rank it touches; the
+    rank that owns the substrate under the patch's centroid owns it: it alone publishes the patch's area / centroid partial sums
+    and pushes its rows to the ranks that read them as halo rows of their own patches without computing them."""
     xyz = np.asarray(cell_xyz); tri = np.asarray(cell_tri); xs = np.asarray(subs_xyz)
     world = len(parts)
+    if world > 32:
+        raise ValueError("cell_partition: at most 32 ranks (rank sets are 32-bit masks)")
     nn = len(xyz); npatch = (nn + PATCH - 1) // PATCH
+    h = np.sqrt((xs[:, 0].max() - xs[:, 0].min()) * (xs[:, 1].max() - xs[:, 1].min()) / max(1, len(xs)))
+    g = margin + 1.5 * h
+    mask, rep, (x0, y0, nx, ny) = _owner_raster(parts, xs, g)
+    dil = _dilate(mask)
+    ix = np.clip(((xyz[:, 0] - x0) / g).astype(np.int64), 0, nx - 1); iy = np.clip(((xyz[:, 1] - y0) / g).astype(np.int64), 0, ny - 1)
     starts = np.arange(0, nn, PATCH)
-    pxmin = np.minimum.reduceat(xyz[:, 0], starts); pxmax = np.maximum.reduceat(xyz[:, 0], starts)
-    centre = 0.5 * (pxmin + pxmax)
-    lo = np.array([xs[p.local_nodes, 0].min() for p in parts]); hi = np.array([xs[p.local_nodes, 0].max() for p in parts])
-    cuts = np.array([xs[p.owned, 0].max() for p in parts[:-1]])          # owned x ranges are consecutive intervals
-    owner = np.searchsorted(cuts, centre, side="left").astype(np.int32)    # centre <= cuts[r] -> rank r
+    pbits = np.bitwise_or.reduceat(dil[iy, ix], starts)
+    cx = np.add.reduceat(xyz[:, 0], starts) / np.diff(np.append(starts, nn)); cy = np.add.reduceat(xyz[:, 1], starts) / np.diff(np.append(starts, nn))
+    cix = np.clip(((cx - x0) / g).astype(np.int64), 0, nx - 1); ciy = np.clip(((cy - y0) / g).astype(np.int64), 0, ny - 1)
+    cbits = mask[ciy, cix]
+    cbits = np.where(cbits != 0, cbits, dil[ciy, cix])
+    cbits = np.where(cbits != 0, cbits, np.uint32(1))
+    owner = np.zeros(npatch, dtype=np.int32)
+    for r in range(world - 1, -1, -1):                                     # lowest rank among the owners of the centroid's raster cell
+        owner[(cbits >> np.uint32(r)) & np.uint32(1) == 1] = r
     listed = np.zeros((world, npatch), dtype=bool)
     for r in range(world):
-        listed[r] = (pxmax + margin >= lo[r]) & (pxmin - margin <= hi[r])
+        listed[r] = ((pbits >> np.uint32(r)) & np.uint32(1)) == 1
         listed[r, owner == r] = True
-        if not listed[r].any():              # a strip far from the cell still runs the step's kernels: give it the nearest patch
-            listed[r, int(np.argmin(np.minimum(np.abs(centre - lo[r]), np.abs(centre - hi[r]))))] = True
+        if not listed[r].any():              # a rank far from the cell still runs the step's kernels: give it the nearest patch
+            px = xs[parts[r].owned, 0].mean(); py = xs[parts[r].owned, 1].mean()
+            listed[r, int(np.argmin((cx - px) ** 2 + (cy - py) ** 2))] = True
     pid = np.arange(nn) // PATCH
     a = tri[:, [0, 0, 1, 1, 2, 2]].ravel(); b = tri[:, [1, 2, 0, 2, 0, 1]].ravel()
     pa, pb = pid[a], pid[b]
@@ -178,17 +238,20 @@ def cell_connect_plan(cparts, rank):
     return peers, my_slot, me.patch_list, me.patch_owned, cat(en), cat(ep), me.imports
 
 
-def cell_column_weights(subs_xyz, cell_xyz, cell_cost=4.0):
-    """Extra per-substrate-node weights for strip_partition when the cell is partitioned too: the cost of the cell nodes above a
-    substrate column is charged to the substrate nodes of that column (a cell node costs ~4 substrate nodes: 0.088 ms / 0.5 M
-    against 0.185 ms / 4 M on B200)."""
-    xs = np.asarray(subs_xyz)[:, 0]; xc = np.asarray(cell_xyz)[:, 0]
-    order = np.argsort(xs, kind="stable")
-    edges = xs[order]
-    pos = np.clip(np.searchsorted(edges, xc), 0, len(xs) - 1)
+def cell_cost_weights(subs_xyz, cell_xyz, cell_cost=4.0):
+    """Extra per-substrate-node weights for a partition whose cell is partitioned too: the cost of every cell node is charged to a
+    substrate node under it (a cell node costs ~4 substrate nodes: 0.088 ms / 0.5 M against 0.185 ms / 4 M on B200)."""
+    xs = np.asarray(subs_xyz); xc = np.asarray(cell_xyz)
+    h = np.sqrt((xs[:, 0].max() - xs[:, 0].min()) * (xs[:, 1].max() - xs[:, 1].min()) / max(1, len(xs)))
+    g = 1.5 * h
+    x0, y0 = xs[:, 0].min(), xs[:, 1].min()
+    nx = int((xs[:, 0].max() - x0) / g) + 1; ny = int((xs[:, 1].max() - y0) / g) + 1
+    rep = np.full((ny, nx), -1, dtype=np.int64)
+    rep[((xs[:, 1] - y0) / g).astype(np.int64), ((xs[:, 0] - x0) / g).astype(np.int64)] = np.arange(len(xs))
+    ix = np.clip(((xc[:, 0] - x0) / g).astype(np.int64), 0, nx - 1); iy = np.clip(((xc[:, 1] - y0) / g).astype(np.int64), 0, ny - 1)
+    tgt = rep[iy, ix]
     w = np.zeros(len(xs))
-    np.add.at(w, order[pos], cell_cost)
-    # spread each column's charge over a window of neighbours in x so that single nodes do not become walls
+    np.add.at(w, tgt[tgt >= 0], cell_cost)
     return w
 
 
@@ -244,21 +307,32 @@ def native_strip(xyz, tri, world, rank, weights=None):
     return out
 
 
+def make_partition(xs, ts, world, cell_xyz, balance=True, cell="replicated", shape="strips"):
+    """The substrate partition of a run: pieces of equal COST -- nodes under the cell also gather integrin forces, and with the cell
+    partitioned too they carry the cost of the cell nodes above them (balance=False: equal node counts) -- as vertical strips, or
+    as sectors around the cell's centroid (every rank then gets its share of the cell as well)."""
+    w = None
+    if balance:
+        w = cell_weights(xs, cell_xyz)
+        if cell == "partitioned":
+            w = w + cell_cost_weights(xs, cell_xyz)
+    if shape == "sectors":
+        return sector_partition(xs, ts, world, np.asarray(cell_xyz)[:, :2].mean(axis=0), w)
+    if shape != "strips":
+        raise ValueError("shape must be 'strips' or 'sectors'")
+    return strip_partition(xs, ts, world, w)
+
+
 class InProcessStrips:
     """All strips of a partitioned run driven by ONE process: one context per strip on the given devices (several strips may share
     a GPU), connected through plain device pointers (peer access between GPUs).  Strips advance in lockstep, one step queued on
     every strip before the next: a strip's step s+1 waits in-kernel for its neighbours' step s, which is already in flight."""
 
-    def __init__(self, variant, cell_mesh, subs_mesh, devices, rng=(1, 1), params=None, balance=True, cell="replicated", margin=0.15):
+    def __init__(self, variant, cell_mesh, subs_mesh, devices, rng=(1, 1), params=None, balance=True, cell="replicated", margin=0.15, shape="strips"):
         from . import ulstep
         from ._lib import CELL, SUBS
         xs, ts = subs_mesh
-        w = None
-        if balance:
-            w = cell_weights(xs, cell_mesh[0])
-            if cell == "partitioned":
-                w = w + cell_column_weights(xs, cell_mesh[0])
-        self.parts = strip_partition(xs, ts, len(devices), w)
+        self.parts = make_partition(xs, ts, len(devices), cell_mesh[0], balance, cell, shape)
         self.cparts = cell_partition(self.parts, cell_mesh[0], cell_mesh[1], xs, margin) if cell == "partitioned" else None
         self.ncell = len(cell_mesh[0])
         self.margin = margin
@@ -361,7 +435,7 @@ class PartitionedSim:
     """One rank of a substrate-partitioned run: full cell + this rank's substrate strip on one GPU."""
 
     def __init__(self, variant, cell_mesh, subs_mesh, dist, device_index, rng=(1, 1), params=None, halo="peer", balance=True,
-                 cell="replicated", margin=0.15):
+                 cell="replicated", margin=0.15, shape="strips"):
         import torch
         from . import ulstep
         from ._lib import CELL, SUBS
@@ -373,14 +447,7 @@ class PartitionedSim:
         xs, ts = subs_mesh
         if cell == "partitioned" and halo != "peer":
             raise ValueError("a partitioned cell needs the fused peer-memory exchange (halo='peer')")
-        # strips of equal COST: nodes under the cell also gather integrin forces, and -- with the cell partitioned too -- carry the
-        # cost of the cell nodes above them (balance=False: equal node counts)
-        w = None
-        if balance:
-            w = cell_weights(xs, cell_mesh[0])
-            if cell == "partitioned":
-                w = w + cell_column_weights(xs, cell_mesh[0])
-        self.parts = strip_partition(xs, ts, self.world, w)
+        self.parts = make_partition(xs, ts, self.world, cell_mesh[0], balance, cell, shape)
         self.part = self.parts[self.rank]
         self.cparts = cell_partition(self.parts, cell_mesh[0], cell_mesh[1], xs, margin) if cell == "partitioned" else None
         self.cpart = self.cparts[self.rank] if self.cparts is not None else None
