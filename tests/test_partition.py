@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 from wholecellfe_b200.meshgen import square_mesh, disk_mesh
-from wholecellfe_b200.partition import strip_partition, exchange_rows, connect_plan, neighbours, cell_weights, native_strip
+from wholecellfe_b200.partition import (strip_partition, sector_partition, make_partition, cell_partition, cell_connect_plan, exchange_rows,
+                                        connect_plan, neighbours, cell_weights, native_strip, PATCH)
 
 
 def _free_port():
@@ -50,6 +51,69 @@ def test_partition_invariants(world, balanced):
         have = set(p.elem_gid.tolist())
         for v in p.owned[:: max(1, len(p.owned) // 50)]:
             assert inc[v] <= have
+
+
+@pytest.mark.parametrize("shape", ["strips", "sectors"])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_cell_partition_invariants(world, shape):
+    """The partitioned cell's plan (host logic, no GPU): every patch has exactly one owner, who computes it; every halo row of a
+    computed patch is either computed locally or imported; every import is exported by the owner of its patch, to the right peer
+    slot; sectors tile the substrate like strips do; anchors within the margin of a computed patch's nodes can only fall into
+    triangles local to that rank (checked on random points)."""
+    xc, tc = disk_mesh(6000); xs, ts = square_mesh(120)
+    parts = make_partition(xs, ts, world, xc, True, "partitioned", shape)
+    owned = np.sort(np.concatenate([p.owned for p in parts]))
+    assert np.array_equal(owned, np.arange(len(xs)))
+    margin = 0.15
+    cps = cell_partition(parts, xc, tc, xs, margin)
+    npatch = (len(xc) + PATCH - 1) // PATCH
+    own = np.zeros(npatch, dtype=int)
+    for c in cps:
+        own[c.owned_patches] += 1
+        assert set(c.owned_patches.tolist()) <= set(c.patch_list.tolist()) and len(c.patch_list) >= 1
+        assert np.all(np.diff(c.patch_list) > 0)
+    assert np.all(own == 1)
+    pid = np.arange(len(xc)) // PATCH
+    owner = np.zeros(npatch, dtype=int)
+    for r, c in enumerate(cps):
+        owner[c.owned_patches] = r
+    for r, c in enumerate(cps):
+        listed = np.zeros(npatch, dtype=bool); listed[c.patch_list] = True
+        halo = set()
+        for t in tc[np.any(listed[pid[tc]], axis=1)]:
+            ps = pid[t]
+            for v, pv in zip(t, ps):
+                if not listed[pv] and np.any(listed[ps]):
+                    halo.add(int(v))
+        assert halo == set(c.imports.tolist())                               # exactly the rows its patches read and it does not compute
+        plan = cell_connect_plan(cps, r)
+        peers, slot = plan[0], plan[1]
+        assert peers == [q for q in range(world) if q != r]
+        for k, q in enumerate(peers):
+            assert cell_connect_plan(cps, q)[0][slot[k]] == r
+        for q in range(world):                                                # what r imports from q's patches, q exports to r
+            if q == r:
+                continue
+            need = c.imports[owner[pid[c.imports]] == q]
+            got = cps[q].exports.get(r, np.zeros(0, int))
+            assert np.array_equal(np.sort(need), np.sort(got))
+    # anchors: a point within the margin of a node of a patch NOT computed by rank r never lies in a triangle local to r
+    rng = np.random.default_rng(3)
+    tri_rank = [set(p.elem_gid.tolist()) for p in parts]
+    cen = xs[ts].mean(axis=1)[:, :2]
+    for _ in range(300):
+        n = int(rng.integers(len(xc)))
+        ang = rng.uniform(0, 2 * np.pi); pt = xc[n, :2] + margin * rng.uniform(0, 1) * np.array([np.cos(ang), np.sin(ang)])
+        near = np.argsort(((cen - pt) ** 2).sum(axis=1))[:12]                 # the containing triangle is among the nearest centroids
+        for e in near:
+            a, b, c3 = xs[ts[e], :2]
+            d = (b[0] - a[0]) * (c3[1] - a[1]) - (b[1] - a[1]) * (c3[0] - a[0])
+            w1 = ((b[0] - pt[0]) * (c3[1] - pt[1]) - (b[1] - pt[1]) * (c3[0] - pt[0])) / d
+            w2 = ((c3[0] - pt[0]) * (a[1] - pt[1]) - (c3[1] - pt[1]) * (a[0] - pt[0])) / d
+            if w1 >= 0 and w2 >= 0 and 1 - w1 - w2 >= 0:
+                for r in range(world):
+                    if int(e) in tri_rank[r]:
+                        assert pid[n] in set(cps[r].patch_list.tolist()), (r, n, e)
 
 
 @pytest.mark.parametrize("world", [2, 3, 5])

@@ -179,6 +179,9 @@ struct wcfe_ctx {
         void *info_ptr[WCFE_CELL_HALO_NPTR] = {};        // what wcfe_cell_halo_info_get reported (the buffers must not have swapped since)
         std::vector<void *> opened;
     } cpart;
+    // mesh (re-)upload: every table goes through two pinned 16-MB chunks with cudaMemcpyAsync on the context's stream -- the CPU fills
+    // one chunk while the DMA engine drains the other, and nothing waits for the device (h2d_staged)
+    struct { char *buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; bool used[2] = {false, false}; int k = 0; } stager;
     int roundtrip_mode = 0;               // wcfe_step_n_roundtrip: 0 cell only + overlapped, 1 both surfaces serial
     std::string err;
 };
@@ -227,6 +230,28 @@ int ensure_stage(wcfe_ctx *c, size_t bytes) {
     return WCFE_OK;
 }
 
+constexpr size_t kStageChunk = 16u << 20;
+// pageable host memory -> device through the pinned double buffer, asynchronous on the context's stream.  `src` may be freed as
+// soon as this returns (it has been copied into pinned memory); later work on the stream sees the data.
+int h2d_staged(wcfe_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return WCFE_OK;
+    auto &st = c->stager;
+    if (!st.buf[0]) {
+        for (int q = 0; q < 2; q++) { CK(cudaMallocHost((void **)&st.buf[q], kStageChunk)); CK(cudaEventCreateWithFlags(&st.ev[q], cudaEventDisableTiming)); st.used[q] = false; }
+    }
+    for (size_t off = 0; off < bytes; off += kStageChunk) {
+        const size_t n = std::min(kStageChunk, bytes - off);
+        const int k = st.k;
+        if (st.used[k]) CK(cudaEventSynchronize(st.ev[k]));      // the chunk's previous transfer has left pinned memory
+        memcpy(st.buf[k], (const char *)src + off, n);
+        CK(cudaMemcpyAsync((char *)dst + off, st.buf[k], n, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(st.ev[k], c->stream));
+        st.used[k] = true; st.k ^= 1;
+    }
+    return WCFE_OK;
+}
+#define H2D(dst, src, bytes) do { int rc_ = h2d_staged(c, (dst), (src), (bytes)); if (rc_) return rc_; } while (0)
+
 // AoS host [n*w] <-> SoA device [w*np]: the copy moves the caller's AoS image as it is, the transposition runs on the device
 int ensure_aos(wcfe_ctx *c, size_t count) {
     if (c->d_aos.n >= count) return WCFE_OK;
@@ -237,7 +262,7 @@ inline unsigned int aos_grid(size_t items) { return (unsigned int)((items + kBlo
 int put_field(wcfe_ctx *c, double *dev, const double *host, int nn, int np, int w) {
     int rc = ensure_aos(c, (size_t)w * np);
     if (rc) return rc;
-    if (nn > 0) CK(cudaMemcpyAsync(c->d_aos.p, host, sizeof(double) * (size_t)w * nn, cudaMemcpyHostToDevice, c->stream));
+    if (nn > 0 && (rc = h2d_staged(c, c->d_aos.p, host, sizeof(double) * (size_t)w * nn))) return rc;      // pinned, asynchronous
     k_aos_to_soa<<<aos_grid((size_t)w * np), kBlock, 0, c->stream>>>(nn, np, w, c->d_aos.p, dev);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
@@ -362,8 +387,8 @@ int build_grid(wcfe_ctx *c, const double *xyz) {
         for (int iy = iy0; iy <= iy1; iy++) for (int ix = ix0; ix <= ix1; ix++) { const size_t q = (size_t)iy * g.nx + ix; items[ptr[q] + fill[q]++] = e; }
     }
     CK(c->g_ptr.alloc(ncell + 1)); CK(c->g_items.alloc(items.size()));
-    CK(cudaMemcpy(c->g_ptr.p, ptr.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->g_items.p, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice));
+    H2D(c->g_ptr.p, ptr.data(), sizeof(int) * (ncell + 1));
+    H2D(c->g_items.p, items.data(), sizeof(int) * items.size());
     g.ptr = c->g_ptr.p; g.items = c->g_items.p;
     return WCFE_OK;
 }
@@ -508,20 +533,20 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
             }
         }
         CK(s.p_ring_blob.alloc(rb.size()));
-        CK(cudaMemcpy(s.p_ring_blob.p, rb.data(), rb.size(), cudaMemcpyHostToDevice));
+        H2D(s.p_ring_blob.p, rb.data(), rb.size());
         // (element << 2 | slot) of every ring entry in the cyclic order, for the bucket lookup of the integrin gather
         std::vector<int> cyc((size_t)s.ring.size());
         size_t pos = 0;
         for (int p = 0; p < s.npatch; p++) { memcpy(cyc.data() + pos, tmp[p].cyc_code.data(), 4 * tmp[p].cyc_code.size()); pos += tmp[p].cyc_code.size(); }
         CK(s.p_ring_cyc.alloc(cyc.size()));
-        CK(cudaMemcpy(s.p_ring_cyc.p, cyc.data(), 4 * cyc.size(), cudaMemcpyHostToDevice));
+        H2D(s.p_ring_cyc.p, cyc.data(), 4 * cyc.size());
     }
     if (cand_l.empty()) cand_l.push_back(0);
     CK(s.p_blob.alloc(blob.size())); CK(s.p_elem_ptr.alloc(elem_ptr.size())); CK(s.p_elem_gid.alloc(elem_gid.size())); CK(s.p_cand_l.alloc(cand_l.size()));
-    CK(cudaMemcpy(s.p_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s.p_elem_ptr.p, elem_ptr.data(), sizeof(int) * elem_ptr.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s.p_elem_gid.p, elem_gid.data(), sizeof(int) * elem_gid.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s.p_cand_l.p, cand_l.data(), sizeof(unsigned short) * cand_l.size(), cudaMemcpyHostToDevice));
+    H2D(s.p_blob.p, blob.data(), blob.size());
+    H2D(s.p_elem_ptr.p, elem_ptr.data(), sizeof(int) * elem_ptr.size());
+    H2D(s.p_elem_gid.p, elem_gid.data(), sizeof(int) * elem_gid.size());
+    H2D(s.p_cand_l.p, cand_l.data(), sizeof(unsigned short) * cand_l.size());
     return WCFE_OK;
 }
 PatchView pview(Surface &s) {
@@ -1061,6 +1086,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     cudaStreamSynchronize(c->stream);
     halo_release(c);
     cell_part_release(c);
+    for (int q = 0; q < 2; q++) { if (c->stager.buf[q]) cudaFreeHost(c->stager.buf[q]); if (c->stager.ev[q]) cudaEventDestroy(c->stager.ev[q]); c->stager.buf[q] = nullptr; c->stager.ev[q] = nullptr; }
     for (int q = 0; q < 2; q++) {
         Surface &s = c->s[q];
         s.d_tri.release(); s.d_ring_ptr.release(); s.d_ring.release();
@@ -1165,9 +1191,9 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
     {
         std::vector<int> soa((size_t)3 * s.nep, 0);
         for (int e = 0; e < ne; e++) for (int j = 0; j < 3; j++) soa[(size_t)j * s.nep + e] = tri[3 * e + j];
-        CK(s.d_tri.alloc(soa.size())); CK(cudaMemcpy(s.d_tri.p, soa.data(), sizeof(int) * soa.size(), cudaMemcpyHostToDevice));
-        CK(s.d_ring_ptr.alloc((size_t)nn + 1)); CK(cudaMemcpy(s.d_ring_ptr.p, s.ring_ptr.data(), sizeof(int) * ((size_t)nn + 1), cudaMemcpyHostToDevice));
-        CK(s.d_ring.alloc(s.ring.size())); CK(cudaMemcpy(s.d_ring.p, s.ring.data(), sizeof(int) * s.ring.size(), cudaMemcpyHostToDevice));
+        CK(s.d_tri.alloc(soa.size())); H2D(s.d_tri.p, soa.data(), sizeof(int) * soa.size());
+        CK(s.d_ring_ptr.alloc((size_t)nn + 1)); H2D(s.d_ring_ptr.p, s.ring_ptr.data(), sizeof(int) * ((size_t)nn + 1));
+        CK(s.d_ring.alloc(s.ring.size())); H2D(s.d_ring.p, s.ring.data(), sizeof(int) * s.ring.size());
     }
     const size_t np = s.np, R = (size_t)c->nrep;     // per-replica arrays hold R images; replica 0 is initialised here and copied below
     CK(s.x.alloc(3 * np * R)); CK(s.V.alloc(3 * np * R)); CK(s.A.alloc(3 * np * R)); CK(s.ea[0].alloc(6 * np * R)); CK(s.ea[1].alloc(6 * np * R));
@@ -1211,10 +1237,10 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
         if ((rc = build_patches(c, surface, cand))) return rc;
         if (cand.empty()) cand.push_back(0);
         CK(s.d_bnd_node.alloc(std::max(1, s.nb))); CK(s.d_bnd_index.alloc(nn)); CK(s.d_cand_ptr.alloc(cand_ptr.size())); CK(s.d_cand.alloc(cand.size()));
-        if (s.nb) CK(cudaMemcpy(s.d_bnd_node.p, s.bnd_node.data(), sizeof(int) * s.nb, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(s.d_bnd_index.p, index.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(s.d_cand_ptr.p, cand_ptr.data(), sizeof(int) * cand_ptr.size(), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(s.d_cand.p, cand.data(), sizeof(int) * cand.size(), cudaMemcpyHostToDevice));
+        if (s.nb) H2D(s.d_bnd_node.p, s.bnd_node.data(), sizeof(int) * s.nb);
+        H2D(s.d_bnd_index.p, index.data(), sizeof(int) * nn);
+        H2D(s.d_cand_ptr.p, cand_ptr.data(), sizeof(int) * cand_ptr.size());
+        H2D(s.d_cand.p, cand.data(), sizeof(int) * cand.size());
         CK(s.d_bnd_buf.alloc((size_t)16 * std::max(1, s.nb) * R));
         CK(cudaMemset(s.d_bnd_buf.p, 0, sizeof(double) * s.d_bnd_buf.n));
         CK(c->d_flags.alloc(nn * R)); CK(c->d_loc_bond.alloc(nn * R)); CK(c->d_loc_cnt.alloc(nn * R)); CK(c->d_loc_first.alloc(nn * R)); CK(c->d_ap_fire.alloc(nn * R));
