@@ -39,11 +39,27 @@ void read_ecomsol(const std::string &path, std::vector<double> &xyz, std::vector
 }
 
 namespace {
-// theta_e = sqrt(det((I - 2 ea)^-1)) per node (iomesh.cpp:789-802, :905-919)
+// theta_e = sqrt(det((I - 2 ea)^-1)) per node (iomesh.cpp:789-802, :905-919), in the reference's own operation order: it goes
+// through Eigen 3.3.4's fixed-size 3x3 inverse (cofactors * 1/det, det = c00 m00 + (c10 m10 + c20 m20):
+// Eigen/src/LU/InverseImpl.h compute_inverse_size3_helper) and then Eigen's 3x3 determinant of that inverse
+// (Eigen/src/LU/Determinant.h bruteforce_det3_helper) -- the printed 6 significant digits then agree in the last place too
 double theta_e_of(const double *e) {
-    const double a00 = 1 - 2 * e[0], a11 = 1 - 2 * e[1], a22 = 1 - 2 * e[2], a01 = -2 * e[3], a02 = -2 * e[4], a12 = -2 * e[5];
-    const double det = a00 * (a11 * a22 - a12 * a12) - a01 * (a01 * a22 - a12 * a02) + a02 * (a01 * a12 - a11 * a02);
-    return std::sqrt(1.0 / det);
+    double m[3][3] = {{1.0 - 2.0 * e[0], 0.0 - 2.0 * e[3], 0.0 - 2.0 * e[4]},
+                      {0.0 - 2.0 * e[3], 1.0 - 2.0 * e[1], 0.0 - 2.0 * e[5]},
+                      {0.0 - 2.0 * e[4], 0.0 - 2.0 * e[5], 1.0 - 2.0 * e[2]}};
+    auto cof = [&](int i, int j) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return m[i1][j1] * m[i2][j2] - m[i1][j2] * m[i2][j1];
+    };
+    const double c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+    const double det = c00 * m[0][0] + (c10 * m[1][0] + c20 * m[2][0]);
+    const double invdet = 1.0 / det;
+    double b[3][3];
+    b[0][0] = c00 * invdet; b[0][1] = c10 * invdet; b[0][2] = c20 * invdet;
+    b[1][0] = cof(0, 1) * invdet; b[1][1] = cof(1, 1) * invdet; b[1][2] = cof(2, 1) * invdet;
+    b[2][0] = cof(0, 2) * invdet; b[2][1] = cof(1, 2) * invdet; b[2][2] = cof(2, 2) * invdet;
+    auto h = [&](int a, int bb, int c) { return b[0][a] * (b[1][bb] * b[2][c] - b[1][c] * b[2][bb]); };
+    return std::sqrt(h(0, 1, 2) - h(1, 0, 2) + h(2, 0, 1));
 }
 void header(std::ofstream &o, double time, size_t nn) {
     o << "# vtk DataFile Version 2.0\nCellBP Time: " << time << "\nASCII\nDATASET UNSTRUCTURED_GRID\n";
