@@ -198,6 +198,9 @@ int wcfe_sync(wcfe_ctx *c);
 /* Device self test: n pseudo-random operand pairs (zero numerators, both signs, x / 3 included) through the division-free correctly
  * rounded quotients the kernels use (wcfe_math.cuh recip_of / quot) and through the compiler's IEEE `/`; *mismatch = results that
  * differ in any bit (the sign of a zero quotient excepted).  Must be 0. */
+/* moving substrate (wcfe_params::subs_scale != 0): how often the point-location grid has been rebuilt because a substrate node had
+ * drifted beyond half the grid's padding from where the grid was built (checked after every step of wcfe_step_n) */
+long long wcfe_grid_refreshes(wcfe_ctx *c);
 int wcfe_selftest_quotient(int device, long long n, unsigned int seed, long long *mismatch);
 
 /* ---- one mesh over several GPUs (BASELINE configs[3]: "element-partitioned over 2/4/8 B200 with ... halo exchange"; the reference

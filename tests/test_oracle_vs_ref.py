@@ -28,6 +28,33 @@ def test_first_steps_all_fields(meshes, variant, nsteps):
         assert rel_err(a["F"], b["F"], scale) < 1e-10, name
 
 
+@pytest.mark.parametrize("variant,scale", [("k1", 1.0), ("k31", 0.5)])
+def test_moving_substrate_restatement_against_the_reference(meshes, variant, scale):
+    """The substrate's predictor without the literal `0*` of main.cpp:299 (x_new = x + scale * dt * V_hlf): the restatement's
+    moving-substrate branch -- displacement interpolation at the anchors in the start-of-step coordinates, last match wins
+    (UL:2026-2065), general substrate element (UL:988-1174) -- against the unmodified reference functions driven through the same
+    sequence, substrate started with velocity and strain so that it moves at once."""
+    xc, tc, xs, ts = meshes
+    r = RefSim(variant, xc, tc, xs, ts); r.srand(1)
+    o = OracleSim(variant, xc, tc, xs, ts); o.srand(1); o.params.subs_scale = scale
+    rng = np.random.default_rng(23)
+    # a smooth shear / stretch field plus a little noise (um/s); dt = 1e-3 keeps the mu = 1e6 substrate's explicit step stable
+    V = np.zeros((len(xs), 3)); V[:, 0] = 2.0 * xs[:, 1] / 50 + 0.02 * rng.normal(size=len(xs)); V[:, 1] = 1.2 * xs[:, 0] / 50 + 0.02 * rng.normal(size=len(xs))
+    ea = np.zeros((len(xs), 6)); ea[:, [0, 1, 3]] = 1e-3 * rng.normal(size=(len(xs), 3))
+    for f, v in (("V", V), ("ea", ea)):
+        r.set(1, f, v); o.set(1, f, v)
+    t = 0.0
+    x0 = r.get(1, "x").copy()
+    for k in range(10):
+        r.step(0.001, t, subs_scale=scale); o.step(0.001, t); t += 0.001
+        for f in ["x", "V", "A", "ea", "cC", "fa_u"]:
+            assert rel_err(o.get(0, f), r.get(0, f)) < 1e-10, (variant, k, f)
+        for f in ["x", "V", "A", "ea"]:
+            b = r.get(1, f)
+            assert rel_err(o.get(1, f), b, np.abs(b).max()) < 1e-10, (variant, k, f)
+    assert np.abs(r.get(1, "x") - x0).max() > 5e-3 and np.isfinite(r.get(1, "A")).all()
+
+
 def test_random_elements_3d_and_planar():
     rng = np.random.default_rng(7)
     base = np.array([[0, 0, 0], [1.0, 0, 0], [0.4, 0.9, 0]])

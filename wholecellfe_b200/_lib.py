@@ -23,7 +23,7 @@ SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_param
            "wcfe_rng_skip", "wcfe_set_profile", "wcfe_get_kernel_ms", "wcfe_set_force_general", "wcfe_get_path_info",
            "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities",
            "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
-           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync", "wcfe_selftest_quotient",
+           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync", "wcfe_selftest_quotient", "wcfe_grid_refreshes",
            "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed", "wcfe_set_roundtrip_mode",
            "wcfe_halo_info_get", "wcfe_halo_connect", "wcfe_halo_disconnect", "wcfe_cell_halo_info_get", "wcfe_cell_halo_connect", "wcfe_cell_halo_disconnect",
            "wcfe_strip_partition", "wcfe_strip_sizes", "wcfe_strip_mesh", "wcfe_strip_halo", "wcfe_strip_free"]
@@ -110,6 +110,7 @@ def load():
     L.wcfe_force_field.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp]
     L.wcfe_device_ptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
     L.wcfe_sync.argtypes = [vp]
+    L.wcfe_grid_refreshes.argtypes = [vp]; L.wcfe_grid_refreshes.restype = C.c_longlong
     L.wcfe_selftest_quotient.argtypes = [C.c_int, C.c_longlong, C.c_uint, C.POINTER(C.c_longlong)]
     L.wcfe_halo_info_get.argtypes = [vp, C.POINTER(HaloInfo)]
     L.wcfe_halo_connect.argtypes = [vp, C.c_int, C.POINTER(HaloInfo), _ip, _ip, C.c_int, _ip, _ip, _ip, C.c_int, _ip]

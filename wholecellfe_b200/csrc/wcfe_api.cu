@@ -182,6 +182,8 @@ struct wcfe_ctx {
     // mesh (re-)upload: every table goes through two pinned 16-MB chunks with cudaMemcpyAsync on the context's stream -- the CPU fills
     // one chunk while the DMA engine drains the other, and nothing waits for the device (h2d_staged)
     struct { char *buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; bool used[2] = {false, false}; int k = 0; } stager;
+    // moving substrate (subs_scale != 0): positions the location grid was built on, its padding, the drift flag k_predict_subs raises
+    DevBuf<double> grid_ref; DevBuf<int> d_grid_flag; double grid_pad = 0.0; long long grid_refreshes = 0;
     int roundtrip_mode = 0;               // wcfe_step_n_roundtrip: 0 cell only + overlapped, 1 both surfaces serial
     std::string err;
 };
@@ -300,7 +302,7 @@ void make_consts(wcfe_ctx *c) { c->k = consts_of(c->prm); }
 template <class T> T *rsel(wcfe_ctx *c, DevBuf<T> &b) { return b.p ? b.p + (b.n / (size_t)c->nrep) * (size_t)c->sel : nullptr; }
 #define NO_BATCH(c, what) do { if ((c)->nrep > 1) return fail((c), WCFE_ERR_UNSUPPORTED, what ": not available on a batched context (wcfe_create_batch); batches advance with wcfe_step_n only"); } while (0)
 int check_params(wcfe_ctx *c, const wcfe_params *p) {
-    if (p->subs_scale != 0.0) return fail(c, WCFE_ERR_UNSUPPORTED, "subs_scale != 0: a moving substrate (main.cpp:299 without the 0*) is not implemented on the GPU path");
+    // subs_scale != 0 (a moving substrate: main.cpp:299 without the literal 0*) runs on the general 3-D kernels, wcfe_step_n only
     if (p->kappa != 0.5) return fail(c, WCFE_ERR_UNSUPPORTED, "kappa != 0.5: the anisotropic active-stress term (UL:877) needs the centroid of the same step and is not implemented");
     if (p->law != 0 && p->law != 1) return fail(c, WCFE_ERR_ARG, "law must be 0 (linear) or 1 (MD table)");
     return WCFE_OK;
@@ -360,7 +362,11 @@ int build_grid(wcfe_ctx *c, const double *xyz) {
     }
     double h = std::sqrt(((xmax - xmin) * (ymax - ymin)) / std::max(1, s.ne)) * 1.5;
     if (!(h > 0)) h = 1;
-    const double eps = 1e-9 * ((xmax - xmin) + (ymax - ymin) + 1.0);
+    // a moving substrate is located in its start-of-step AND its current coordinates while it drifts from the positions the grid
+    // was built on: every triangle is registered in the cells its bounding box reaches when inflated by the padding
+    c->grid_pad = c->prm.subs_scale != 0.0 ? 0.5 * h : 0.0;
+    if (c->grid_pad > 0.0) if (const char *e = std::getenv("WCFE_GRID_PAD")) c->grid_pad = std::max(1e-6, std::atof(e));      // test hook: force frequent rebuilds
+    const double eps = 1e-9 * ((xmax - xmin) + (ymax - ymin) + 1.0) + c->grid_pad;
     GridView &g = c->grid;
     g.x0 = xmin - 2 * eps; g.y0 = ymin - 2 * eps; g.inv_h = 1.0 / h;
     g.nx = (int)((xmax - g.x0 + 2 * eps) * g.inv_h) + 1; g.ny = (int)((ymax - g.y0 + 2 * eps) * g.inv_h) + 1;
@@ -572,7 +578,7 @@ bool planar_strain(const double *ea6, int nn) {
 }
 constexpr int kPatchSmemMax = 224 * 1024;
 bool use_planar(wcfe_ctx *c) {
-    if (!(c->s[0].planar() && c->s[1].planar() && c->prm.thetag_dot == 0.0 && !c->force_general)) return false;
+    if (!(c->s[0].planar() && c->s[1].planar() && c->prm.thetag_dot == 0.0 && c->prm.subs_scale == 0.0 && !c->force_general)) return false;
     // a mesh numbered without locality can blow the per-patch tables past shared memory: use the general kernels then
     return cell_smem_bytes(c->s[0].max_halo, c->s[0].max_elem, c->s[0].stride) <= (size_t)kPatchSmemMax &&
            patch_smem_bytes(5, 10, c->s[1].max_halo, c->s[1].max_elem, c->s[1].stride) <= (size_t)kPatchSmemMax;
@@ -669,11 +675,55 @@ void harvest_profile(wcfe_ctx *c) {
 }
 enum { K_PREDICT = 0, K_BOND = 1, K_CELL = 2, K_FINISH = 3, K_SUBS = 4, K_REDUCE = 5 };
 
+// ---- moving substrate (subs_scale != 0) --------------------------------------------------------------------------------------
+// second position buffer for the substrate (start-of-step positions X_t, main.cpp:311), the positions the location grid was built
+// on, and the drift flag; allocated on first use
+int ensure_moving(wcfe_ctx *c) {
+    Surface &ss = c->s[WCFE_SUBS];
+    if (ss.X.p && c->grid_ref.p && c->d_grid_flag.p && c->grid_pad > 0.0) return WCFE_OK;
+    NO_BATCH(c, "a moving substrate");
+    if (!ss.X.p) { CK(ss.X.alloc(3 * (size_t)ss.np)); CK(cudaMemcpyAsync(ss.X.p, ss.x.p, sizeof(double) * 3 * ss.np, cudaMemcpyDeviceToDevice, c->stream)); }
+    if (!c->d_grid_flag.p) { CK(c->d_grid_flag.alloc(1)); CK(cudaMemsetAsync(c->d_grid_flag.p, 0, sizeof(int), c->stream)); }
+    if (!c->grid_ref.p || c->grid_pad == 0.0) {
+        // the grid on hand was built without padding (parameters set after the mesh upload): rebuild it from the current positions
+        std::vector<double> xyz(3 * (size_t)ss.nn);
+        int rc = get_field(c, ss.x.p, xyz.data(), ss.nn, ss.np, 3);
+        if (rc) return rc;
+        if ((rc = build_grid(c, xyz.data()))) return rc;
+        CK(c->grid_ref.alloc(3 * (size_t)ss.np));
+        CK(cudaMemcpyAsync(c->grid_ref.p, ss.x.p, sizeof(double) * 3 * ss.np, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return WCFE_OK;
+}
+// after a step: did a node drift beyond half the grid's padding from where the grid was built?  Then rebuild it (host-side, as at
+// upload) before the next step looks anything up.  One small synchronous read per step: this path is about correctness, not speed.
+int refresh_grid_if_drifted(wcfe_ctx *c) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, c->d_grid_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (!flag) return WCFE_OK;
+    Surface &ss = c->s[WCFE_SUBS];
+    std::vector<double> xyz(3 * (size_t)ss.nn);
+    int rc = get_field(c, ss.x.p, xyz.data(), ss.nn, ss.np, 3);
+    if (rc) return rc;
+    if ((rc = build_grid(c, xyz.data()))) return rc;
+    CK(cudaMemcpyAsync(c->grid_ref.p, ss.x.p, sizeof(double) * 3 * ss.np, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_grid_flag.p, 0, sizeof(int), c->stream));
+    c->grid_refreshes++;
+    return WCFE_OK;
+}
+
 // ---- one UL update on the device: k_bond, k_cell_node, k_boundary_finish, k_subs_node ---------------------------
 int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const unsigned int *tape_dev, bool fuse_predict, int which = 3) {
     Surface &cs = c->s[WCFE_CELL], &ss = c->s[WCFE_SUBS];
     SurfView cv = view(cs), sv = view(ss);
-    sv.X = sv.x;
+    const bool moving = c->prm.subs_scale != 0.0;
+    if (moving) {
+        if (!fuse_predict || c->nrep > 1 || c->halo.active || c->cpart.active) return fail(c, WCFE_ERR_UNSUPPORTED, "a moving substrate (subs_scale != 0) advances with wcfe_step_n only (one replica, one GPU)");
+        int rcm = ensure_moving(c);
+        if (rcm) return rcm;
+        sv = view(ss);
+    } else sv.X = sv.x;
     // El Topo may accept less than the requested step: the caller's V_hlf was formed by the LAST driver call, whose dt (curr_dt,
     // main.cpp:224/:293/:329) then differs from the dt updateForces_Explicit receives (ori_dt, main.cpp:360-361)
     const double dtd_c = (!fuse_predict && c->drv_dt[0] >= 0) ? c->drv_dt[0] : dt, dtd_s = (!fuse_predict && c->drv_dt[1] >= 0) ? c->drv_dt[1] : dt;
@@ -765,9 +815,14 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
             ProfScope ps(c, K_PREDICT);
             k_predict_cell<<<gc, kBlock, 0, c->stream>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt);
             c->launches += 1;
+            if (moving) {      // driverVelocities_Biaxial + x_new = x + subs_scale * dt * V_hlf (main.cpp:293-311)
+                k_predict_subs<<<gs, kBlock, 0, c->stream>>>(ss.nn, ss.np, ss.x.p, ss.X.p, ss.V.p, ss.A.p, dt, t_tot, c->prm.subs_scale, c->k,
+                                                             c->grid_ref.p, 0.25 * c->grid_pad * c->grid_pad, c->d_grid_flag.p);
+                c->launches += 1;
+            }
         }
         { ProfScope ps(c, K_BOND);
-        k_bond<<<gc, kBlock, 0, c->stream>>>(cv, sv, c->grid, bk, c->k, dt_real, c->ibox[0], c->ibox[1], c->ibox[2], c->ibox[3], c->d_flags.p, c->d_loc_bond.p, c->d_loc_cnt.p, c->d_loc_first.p, c->debug, c->d_err.p); }
+        k_bond<<<gc, kBlock, 0, c->stream>>>(cv, sv, c->grid, bk, c->k, dt_real, c->ibox[0], c->ibox[1], c->ibox[2], c->ibox[3], c->d_flags.p, c->d_loc_bond.p, c->d_loc_cnt.p, c->d_loc_first.p, c->debug, c->d_err.p, moving ? 1 : 0); }
         { ProfScope ps(c, K_CELL);
         if (c->debug)
             k_cell_node<true><<<gc, kBlock, 0, c->stream>>>(cv, bv, c->k, dt, dt_real, t_tot, c->rng_mode, tape_dev, c->seed, c->step, thr, c->d_partials.p, c->d_ap_fire.p, dview(cs), dtd_c);
@@ -1289,6 +1344,7 @@ static int after_upload(wcfe_ctx *c, int surface, int field, const double *host)
         else {
             if (c->d_loc_cache.p) CK(cudaMemsetAsync(c->d_loc_cache.p, 0xff, sizeof(double2) * c->d_loc_cache.n, c->stream));   // cached vertex positions are stale
             rc = build_grid(c, host); if (rc) return rc;
+            if (c->grid_ref.p) CK(cudaMemcpyAsync(c->grid_ref.p, rsel(c, s.x), sizeof(double) * 3 * s.np, cudaMemcpyDeviceToDevice, c->stream));   // the grid now describes these positions
         }
     }
     return WCFE_OK;
@@ -1538,6 +1594,7 @@ int wcfe_step_n(wcfe_ctx *c, int n, double dt, double *t_io) {
     for (int q = 0; q < n; q++) {
         const unsigned int *tape = c->d_tape.p ? c->d_tape.p + (size_t)q * cs.nb : nullptr;
         if ((rc = launch_update(c, dt, dt, t, tape, true))) return rc;
+        if (c->prm.subs_scale != 0.0 && (rc = refresh_grid_if_drifted(c))) return rc;
         t += dt;   // sim->m_curr_t += accum_dt (main.cpp:405)
     }
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -1555,6 +1612,7 @@ int wcfe_step_n_async(wcfe_ctx *c, int n, double dt, double *t_io) {
     if (rc) return rc;
     if (n < 0 || !t_io) return WCFE_ERR_ARG;
     CK(cudaSetDevice(c->device));
+    if (c->prm.subs_scale != 0.0) return fail(c, WCFE_ERR_UNSUPPORTED, "step_n_async: a moving substrate advances with wcfe_step_n only (the location grid is checked after every step)");
     if (c->rng_mode == WCFE_RNG_GLIBC_REPLAY && c->tape_busy) { CK(cudaStreamSynchronize(c->stream)); c->tape_busy = false; }   // pinned tape still in flight
     if ((rc = stage_tape(c, n))) return rc;
     c->tape_busy = true;
@@ -1670,7 +1728,8 @@ int wcfe_step_n_roundtrip(wcfe_ctx *c, int n, double dt, double *t_io, long long
     CK(cudaSetDevice(c->device));
     // a moving substrate (subs_scale != 0) is rejected at parameter check, so the cell-only hand-over is always valid today; the
     // test stays so that lifting that restriction cannot silently drop the substrate's positions
-    if (c->roundtrip_mode == 1 || c->prm.subs_scale != 0.0) return roundtrip_both(c, n, dt, t_io, h2d, d2h);
+    if (c->prm.subs_scale != 0.0) return fail(c, WCFE_ERR_UNSUPPORTED, "step_n_roundtrip: a moving substrate advances with wcfe_step_n only");
+    if (c->roundtrip_mode == 1) return roundtrip_both(c, n, dt, t_io, h2d, d2h);
     return roundtrip_cell(c, n, dt, t_io, h2d, d2h);
 }
 
@@ -2034,6 +2093,8 @@ int wcfe_cell_halo_disconnect(wcfe_ctx *c) {
     cell_part_release(c);
     return WCFE_OK;
 }
+
+long long wcfe_grid_refreshes(wcfe_ctx *c) { return c ? c->grid_refreshes : 0; }
 
 int wcfe_halo_disconnect(wcfe_ctx *c) {
     if (!c) return WCFE_ERR_ARG;

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kBlock) k_driver(int surface, int nn, const do
 // ---- point location of one anchor in the substrate -------------------------------------------------------
 // visits candidates in ascending triangle index; calls f(tri, A[3], A_tri) for every containing triangle
 template <class F>
-__device__ __forceinline__ void locate(const GridView &g, const SurfView &s, const double pt[3], F &&f) {
+__device__ __forceinline__ void locate_at(const GridView &g, const SurfView &s, const double *__restrict__ pos, const double pt[3], F &&f) {
     const double fx = (pt[0] - g.x0) * g.inv_h, fy = (pt[1] - g.y0) * g.inv_h;
     if (!(fx >= 0.0) || !(fy >= 0.0) || fx >= (double)g.nx || fy >= (double)g.ny) return;
     const int cidx = (int)fy * g.nx + (int)fx;
@@ -197,12 +197,44 @@ __device__ __forceinline__ void locate(const GridView &g, const SurfView &s, con
     for (int k = b; k < e; k++) {
         const int t = g.items[k];
         const int i0 = s.tri[t], i1 = s.tri[s.nep + t], i2 = s.tri[2 * s.nep + t];
-        const double n1[3] = {s.x[i0], s.x[s.np + i0], s.x[2 * s.np + i0]};
-        const double n2[3] = {s.x[i1], s.x[s.np + i1], s.x[2 * s.np + i1]};
-        const double n3[3] = {s.x[i2], s.x[s.np + i2], s.x[2 * s.np + i2]};
+        const double n1[3] = {pos[i0], pos[s.np + i0], pos[2 * s.np + i0]};
+        const double n2[3] = {pos[i1], pos[s.np + i1], pos[2 * s.np + i1]};
+        const double n3[3] = {pos[i2], pos[s.np + i2], pos[2 * s.np + i2]};
         double Ar[3], At;
         if (point_in_triangle(n1, n2, n3, pt, Ar, At)) f(t, Ar, At);
     }
+}
+template <class F>
+__device__ __forceinline__ void locate(const GridView &g, const SurfView &s, const double pt[3], F &&f) { locate_at(g, s, s.x, pt, f); }
+
+// ---- moving substrate (the reference's `0*` of main.cpp:299 replaced by wcfe_params::subs_scale): driverVelocities_Biaxial
+//      (UL:275-345) + predictor x_new = x + scale * dt * V_hlf (main.cpp:298-302), general 3-D path only.  Also watches how far the
+//      nodes have drifted from the positions the point-location grid was built on (grid_ref): beyond half the grid's padding the host
+//      rebuilds the grid before the next step (flag).
+__global__ void __launch_bounds__(kBlock) k_predict_subs(int nn, int np, double *__restrict__ x, double *__restrict__ X, const double *__restrict__ V,
+                                                         const double *__restrict__ A, double dt, double t_tot, double scale, Consts k,
+                                                         const double *__restrict__ grid_ref, double half_pad2, int *__restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn) return;
+    const double xo[3] = {x[i], x[np + i], x[2 * np + i]};
+    double vh[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) vh[c] = WCFE_ADD(V[c * np + i], WCFE_MUL(dt / 2.0, A[c * np + i]));
+    vh[2] = 0.0;
+    if (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f) {            // UL:298-341, Vbiax == 0
+        if (xo[0] < -k.pin_limit || xo[0] > k.pin_limit) vh[0] = 0.0;
+        if (xo[1] > k.pin_limit || xo[1] < -k.pin_limit) vh[1] = 0.0;
+    }
+    double d2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double xn = WCFE_ADD(xo[c], WCFE_MUL(WCFE_MUL(scale, dt), vh[c]));         // main.cpp:299: x + scale*dt*V_hlf, uncontracted
+        X[c * np + i] = xo[c];
+        x[c * np + i] = xn;
+        const double d = xn - grid_ref[c * np + i];
+        d2 += d * d;
+    }
+    if (d2 > half_pad2) *flag = 1;
 }
 
 // ---- updateFA (UL:2005-2114) + anchor location for calculateForce_FA_subs (UL:1301-1340) ---------------------
@@ -211,21 +243,34 @@ __device__ __forceinline__ void locate(const GridView &g, const SurfView &s, con
 __global__ void __launch_bounds__(kBlock) k_bond(SurfView c, SurfView s, GridView g, BucketView bk, Consts k, double dt,
                                                  double ix0, double ix1, double iy0, double iy1,
                                                  int *__restrict__ d_flags, int *__restrict__ d_loc_bond,
-                                                 int *__restrict__ d_loc_cnt, int *__restrict__ d_loc_first, int debug, int *__restrict__ err) {
+                                                 int *__restrict__ d_loc_cnt, int *__restrict__ d_loc_first, int debug, int *__restrict__ err, int moving) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.nn) return;
     const double xi[3] = {c.x[i], c.x[c.np + i], c.x[2 * c.np + i]};
     const double Xi[3] = {c.X[i], c.X[c.np + i], c.X[2 * c.np + i]};
     double fa[3] = {c.fa[i], c.fa[c.np + i], c.fa[2 * c.np + i]};
     double cC = c.cC[i];
-    if (debug) {
-        const double pt0[3] = {Xi[0] - fa[0], Xi[1] - fa[1], Xi[2] - fa[2]};     // UL:2020
+    double subs_u[3] = {0.0, 0.0, 0.0};          // (no containing triangle: the reference leaves it uninitialised, UL:2018 -- defined 0)
+    if (debug || moving) {
+        // the anchor in the substrate's coordinates at the START of the step (s.X; == s.x for the frozen substrate), UL:2020-2057; with a
+        // moving substrate its displacement over the step is interpolated there: last match wins (UL:2057-2064)
+        const double pt0[3] = {Xi[0] - fa[0], Xi[1] - fa[1], Xi[2] - fa[2]};
         int last = -1;
-        locate(g, s, pt0, [&](int t, const double *, double) { last = t; });     // last match wins, UL:2057-2064
-        d_loc_bond[i] = last;
+        const int np = s.np;
+        locate_at(g, s, s.X, pt0, [&](int t, const double *Ar, double At) {
+            last = t;
+            if (moving) {
+                const int i0 = s.tri[t], i1 = s.tri[s.nep + t], i2 = s.tri[2 * s.nep + t];
+                const double w1 = Ar[0] / At, w2 = Ar[1] / At, w3 = Ar[2] / At;
+#pragma unroll
+                for (int q = 0; q < 3; q++)      // UL:2061, left to right, uncontracted
+                    subs_u[q] = WCFE_ADD(WCFE_ADD(WCFE_MUL(w1, WCFE_SUB(s.x[q * np + i0], s.X[q * np + i0])), WCFE_MUL(w2, WCFE_SUB(s.x[q * np + i1], s.X[q * np + i1]))),
+                                         WCFE_MUL(w3, WCFE_SUB(s.x[q * np + i2], s.X[q * np + i2])));
+            }
+        });
+        if (debug) d_loc_bond[i] = last;
     }
     const double cell_u[3] = {xi[0] - Xi[0], xi[1] - Xi[1], xi[2] - Xi[2]};      // UL:2016
-    const double subs_u[3] = {0.0, 0.0, 0.0};
     const int fl = bond_update(k, dt, cell_u, subs_u, fa, cC);
     c.fa[i] = fa[0]; c.fa[c.np + i] = fa[1]; c.fa[2 * c.np + i] = fa[2];
     c.cC[i] = cC;

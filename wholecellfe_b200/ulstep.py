@@ -241,6 +241,10 @@ class ULSim:
     def cell_halo_disconnect(self):
         self._ck(self.L.wcfe_cell_halo_disconnect(self.h))
 
+    def grid_refreshes(self):
+        """moving substrate: rebuilds of the point-location grid so far"""
+        return int(self.L.wcfe_grid_refreshes(self.h))
+
     def kernel_launches(self):
         return int(self.L.wcfe_kernel_launches(self.h))
 
