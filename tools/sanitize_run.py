@@ -11,6 +11,9 @@ on meshes small enough for the sanitizer's ~50x slow-down.
   4  two substrate strips in one process (HALO instantiation of k_subs_ring, peer stores + in-kernel waits, cell counter)
   5  a batch of 4 replicas (BATCH instantiations)
   6  a non-planar state (general kernels k_predict_cell, k_bond, k_cell_node, k_subs_node)
+  7  three strips in one process with the CELL partitioned too (PART instantiations of k_cell_patch / k_finish_reduce, pushes into
+     the other contexts' buffers, epoch-counter waits), strips and sectors
+  8  a moving substrate (k_predict_subs, displacement interpolation in k_bond, grid rebuilds forced by a 4-nm padding)
 Nothing is compared here -- tests/ does that; the sanitizer's report is the result."""
 import os
 import sys
@@ -53,3 +56,15 @@ ea = np.zeros((len(xc), 6)); ea[:, 2] = 1e-3
 g.set(W.CELL, "ea", ea)
 g.step_n(n, 0.005, 0.0); g.close()
 print("6 done", flush=True)
+for shape in ("strips", "sectors"):
+    run = InProcessStrips("k31", (xc3, tc3), (xs3, ts3), [0, 0, 0], cell="partitioned", shape=shape)
+    run.step_n(n, 5e-5)
+    run.close()
+print("7 done", flush=True)
+os.environ["WCFE_GRID_PAD"] = "0.004"
+p = W.default_params("k1"); p.subs_scale = 1.0
+g = W.ULSim("k1", params=p); g.upload_mesh(W.CELL, xc, tc); g.upload_mesh(W.SUBS, xs, ts); g.srand(1)
+V = np.zeros((len(xs), 3)); V[:, 0] = 2.0 * xs[:, 1] / 50; V[:, 1] = 1.2 * xs[:, 0] / 50
+g.set(W.SUBS, "V", V)
+g.step_n(12, 1e-3, 0.0)
+print("8 done, grid rebuilt", g.grid_refreshes(), "times", flush=True); g.close()
