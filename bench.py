@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--shape", default="strips", choices=["strips", "sectors"],
                     help="--mode partition: substrate cut into vertical strips (default; measured faster at 8 GPUs: the ranks under the cell do the cell's work while "
                          "the outer ranks carry more substrate) or into sectors around the cell's centroid (every rank gets an equal share of both)")
+    ap.add_argument("--cell-cost", type=float, default=4.0, help="--mode partition, --cell partitioned: weight of a cell node in substrate-node units when the strips are balanced")
     ap.add_argument("--no-partition-record", action="store_true", help="N > 1, ensemble mode: skip the strong-scaling sub-record (`partition`)")
     ap.add_argument("--balance", type=int, default=1, help="--mode partition: strips of equal cost (nodes under the cell weigh 3x) instead of equal node count")
     ap.add_argument("--order", default="morton", choices=["morton", "morton_rows"], help="node numbering of the synthetic meshes")
@@ -231,7 +232,7 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh, steps=
     import torch
     from wholecellfe_b200.partition import PartitionedSim
     steps = steps or a.steps
-    sim = PartitionedSim(a.variant, cell_mesh, subs_mesh, dist, local, rng=(1, 1), halo=a.halo, balance=bool(a.balance), cell=a.cell, shape=a.shape)
+    sim = PartitionedSim(a.variant, cell_mesh, subs_mesh, dist, local, rng=(1, 1), halo=a.halo, balance=bool(a.balance), cell=a.cell, shape=a.shape, cell_cost=a.cell_cost)
     ne = len(cell_mesh[1]) + len(subs_mesh[1])
     sim.step_n(a.warmup, a.dt)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -293,7 +294,7 @@ def run_partition_mode(a, dist, rank, world, local, cell_mesh, subs_mesh, steps=
             "gpu_launches": l1 - l0, "per_kernel_ms_by_rank": {n: [float(v[i].item()) for v in pk_all] for i, n in enumerate(names) if any(float(v[i].item()) > 0 for v in pk_all)},
             "bitwise_equal_to_single_gpu": {"value": bool(int(okt.item())), "steps": total_steps,
                                             "what": "owned substrate rows (ea, V) and owned cell rows (x, V, cC) of every rank against the same steps of the whole mesh on one GPU"},
-            "pieces": ("%s of equal cost (nodes under the cell x3%s)" % (a.shape, ", + 4 per cell node above" if a.cell == "partitioned" else "")) if a.balance else "%s of equal node count" % a.shape,
+            "pieces": ("%s of equal cost (nodes under the cell x3%s)" % (a.shape, ", + %g per cell node above" % a.cell_cost if a.cell == "partitioned" else "")) if a.balance else "%s of equal node count" % a.shape,
             "rank0": part0}
 
 

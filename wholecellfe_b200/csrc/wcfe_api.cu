@@ -125,6 +125,8 @@ struct wcfe_ctx {
     DevBuf<unsigned int> big_count; DevBuf<int> big_list;
     int big_cap = 0, reduce_warp = 0;     // reduce_warp: one warp per listed triangle (coarse substrate) instead of one thread
     bool big_clean = true;                // the list counter is zero (k_subs_ring re-zeroes it at the end of every full step)
+    int head_proto = 0;                   // what the bucket heads hold: 0 zeros, 1 (epoch << 32 | count) never reset (general path, k_subs_patch),
+                                          // 2 counts that the reduction returns to zero (production chain, bucket_take_slot)
     unsigned int epoch = 0;
     double box[4] = {0, 0, 0, 0};         // padded anchor region, substrate nodes outside cannot receive force
     double ibox[4] = {0, 0, 0, 0};        // region the anchors themselves must stay in (box shrunk by the longest substrate edge)
@@ -430,13 +432,62 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
             if (v >= n0 && v < n1) return (unsigned short)(v - n0);
             return (unsigned short)(P + (std::lower_bound(hl.begin(), hl.end(), v) - hl.begin()));
         };
-        for (int e : el) { elem_gid.push_back(e); for (int j = 0; j < 3; j++) t.lv.push_back(local(s.tri[3 * (size_t)e + j])); }
-        t.nel = (int)el.size();
+        // Patch-local element SLOTS.  The kernels treat a slot id as opaque (descriptor rows, record rows, one-ring codes), so the
+        // slot numbering is free -- and it decides the shared-memory bank conflicts of the cell kernel's one-ring gather: at ring
+        // position k the 16 nodes of a half-warp read 16 records, which collide when two DIFFERENT records share slot mod 16 (records
+        // are 9 doubles apart: an odd stride, so the 8-byte bank pair is a bijection of slot mod 16).  Greedy colouring with 16
+        // balanced colours over the sets {element at ring position k of node t : t in a half-warp}, slot = 16 * (rank within the
+        // colour) + colour: measured 2.4 -> 1.4 wavefronts per gather on the bench cell.  The nodal sums keep the reference's
+        // ascending GLOBAL element order (UL:692-705): only where a record lives changes.
+        const int ne_p = (int)el.size();
+        std::vector<int> slot_of((size_t)ne_p);
+        if (surface == WCFE_CELL && ne_p >= 32) {
+            const int G = (ne_p + 15) / 16, rem = ne_p % 16;
+            int cap[16], used[16];
+            for (int q = 0; q < 16; q++) { cap[q] = (rem == 0 || q < rem) ? G : G - 1; used[q] = 0; }
+            std::vector<std::vector<int>> sets, memb((size_t)ne_p);
+            for (int h0 = n0; h0 < n1; h0 += 16) {
+                const int h1 = std::min(n1, h0 + 16);
+                int kmax = 0;
+                for (int v = h0; v < h1; v++) kmax = std::max(kmax, s.ring_ptr[v + 1] - s.ring_ptr[v]);
+                for (int k = 0; k < kmax; k++) {
+                    std::vector<int> S;
+                    for (int v = h0; v < h1; v++)
+                        if (s.ring_ptr[v + 1] - s.ring_ptr[v] > k) S.push_back((int)(std::lower_bound(el.begin(), el.end(), s.ring[s.ring_ptr[v] + k] >> 2) - el.begin()));
+                    std::sort(S.begin(), S.end()); S.erase(std::unique(S.begin(), S.end()), S.end());
+                    for (int e : S) memb[e].push_back((int)sets.size());
+                    sets.push_back(S);
+                }
+            }
+            std::vector<int> order((size_t)ne_p), colour((size_t)ne_p, -1);
+            for (int q = 0; q < ne_p; q++) order[q] = q;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return memb[a].size() > memb[b].size(); });      // most constrained first
+            for (int e : order) {
+                int cost[16] = {0};
+                for (int si : memb[e]) for (int f : sets[si]) if (f != e && colour[f] >= 0) cost[colour[f]]++;
+                int best = -1;
+                for (int q = 0; q < 16; q++)
+                    if (used[q] < cap[q] && (best < 0 || cost[q] < cost[best] || (cost[q] == cost[best] && used[q] < used[best]))) best = q;
+                colour[e] = best; slot_of[e] = 16 * used[best] + best; used[best]++;
+            }
+        } else {
+            for (int q = 0; q < ne_p; q++) slot_of[q] = q;
+        }
+        {
+            std::vector<int> at((size_t)ne_p, -1);                    // slot -> index into el
+            for (int q = 0; q < ne_p; q++) at[slot_of[q]] = q;
+            for (int sl = 0; sl < ne_p; sl++) {
+                const int e = el[at[sl]];
+                elem_gid.push_back(e);
+                for (int j = 0; j < 3; j++) t.lv.push_back(local(s.tri[3 * (size_t)e + j]));
+            }
+        }
+        t.nel = ne_p;
         t.rptr.assign((size_t)P + 1, (unsigned short)nring);
         for (int v = n0; v <= n1; v++) t.rptr[v - n0] = (unsigned short)(s.ring_ptr[v] - s.ring_ptr[n0]);
         for (int r = s.ring_ptr[n0]; r < s.ring_ptr[n1]; r++) {
             const int e = s.ring[r] >> 2, slot = s.ring[r] & 3;
-            t.ring.push_back((unsigned short)(((std::lower_bound(el.begin(), el.end(), e) - el.begin()) << 2) | slot));
+            t.ring.push_back((unsigned short)((slot_of[std::lower_bound(el.begin(), el.end(), e) - el.begin()] << 2) | slot));
         }
         if (surface == WCFE_SUBS) {
             // k_subs_ring walks each node's fan in CYCLIC order (entry r+1 starts at the vertex entry r ended on), so that every
@@ -597,7 +648,7 @@ int build_buckets(wcfe_ctx *c) {
     CK(cudaMemset(c->b_head.p, 0, sizeof(unsigned long long) * ss.nep * c->nrep));
     CK(c->b_node_epoch.alloc((size_t)ss.np * c->nrep));
     CK(cudaMemset(c->b_node_epoch.p, 0, sizeof(unsigned int) * ss.np * c->nrep));
-    c->epoch = 0; c->big_clean = true;
+    c->epoch = 0; c->big_clean = true; c->head_proto = 0;
     // k_subs_ring path: every triangle that holds anchors is reduced by k_bucket_reduce -- by one thread, or by one warp where many
     // anchors per substrate triangle are expected
     c->big_cap = 0; c->big_count.release(); c->big_list.release();
@@ -728,6 +779,12 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     // main.cpp:224/:293/:329) then differs from the dt updateForces_Explicit receives (ori_dt, main.cpp:360-361)
     const double dtd_c = (!fuse_predict && c->drv_dt[0] >= 0) ? c->drv_dt[0] : dt, dtd_s = (!fuse_predict && c->drv_dt[1] >= 0) ? c->drv_dt[1] : dt;
     if (which & 1) c->epoch++;            // the cell half fills the triangle buckets of this epoch, the substrate half reads them
+    if (which & 1) {
+        // the two bucket-head protocols do not mix: zero the heads when the path changes (planar <-> general, k_subs_ring <-> k_subs_patch)
+        const int proto = (use_planar(c) && c->subs_kernel == 2 && c->big_count.p != nullptr) ? 2 : 1;
+        if (c->head_proto != 0 && c->head_proto != proto) CK(cudaMemsetAsync(c->b_head.p, 0, sizeof(unsigned long long) * c->b_head.n, c->stream));
+        c->head_proto = proto;
+    }
     BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch, nullptr, nullptr, 0, c->b_node_epoch.p, c->halo.active ? c->cell_done.p : nullptr, c->cell_target, 0, c->d_err.p};      // the completion counter is a partitioned-run device (the increment costs the cell kernel 3 %)
     const int gc = (cs.nn + kBlock - 1) / kBlock, gs = (ss.nn + kBlock - 1) / kBlock;
     // Pr < APrate*dt*exp(-APrate*dt) (UL:1531): the threshold is evaluated on the host with the host libm, as the reference does
@@ -755,7 +812,10 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     const double *v_old = cs.V.p, *a_old = cs.A.p;      // general path: V, A are updated in place
     if (!(which & 1)) goto subs_half;
     if (planar) {
-        if (reduce && !c->big_clean) CK(cudaMemsetAsync(c->big_count.p, 0, sizeof(unsigned int) * c->nrep, c->stream));   // a cell half without its substrate half left a list behind
+        if (reduce && !c->big_clean) {      // a cell half without its substrate half left a list behind, and counts nobody returned to zero
+            CK(cudaMemsetAsync(c->big_count.p, 0, sizeof(unsigned int) * c->nrep, c->stream));
+            CK(cudaMemsetAsync(c->b_head.p, 0, sizeof(unsigned long long) * c->b_head.n, c->stream));
+        }
         if (reduce) c->big_clean = false;
         // fused cell kernel: (predict) + updateFA + anchor location + forces + update, one CTA per patch
         ProfScope ps(c, K_CELL);

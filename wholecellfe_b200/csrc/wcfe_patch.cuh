@@ -608,6 +608,9 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
             }
             double2 *o = reinterpret_cast<double2 *>(items);      // this thread alone reads and writes the bucket
             o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3); o[2] = make_double2(a4, a5);
+            // the triangle's three nodes have something to gather in this step; its count starts the next step at zero
+            bk.node_epoch[i0] = bk.epoch; bk.node_epoch[i1] = bk.epoch; bk.node_epoch[i2] = bk.epoch;
+            bk.head[e] = (unsigned long long)bk.epoch << 32;
         }
         return;
     }
@@ -644,6 +647,7 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
             __syncwarp();
         }
         if (lane < 6) reinterpret_cast<double *>(items)[lane] = acc;     // every lane has finished reading the items (syncwarp above)
+        if (lane == 6) { bk.node_epoch[i0] = bk.epoch; bk.node_epoch[i1] = bk.epoch; bk.node_epoch[i2] = bk.epoch; bk.head[e] = (unsigned long long)bk.epoch << 32; }
     }
 }
 
@@ -709,12 +713,17 @@ __host__ __device__ inline size_t cell_smem_bytes(int max_halo, int max_elem, in
     const size_t NL = (size_t)kPatch + max_halo;
     return 16 + (size_t)stride + sizeof(double) * 7 * NL + sizeof(double) * kRec * (size_t)max_elem + 64;
 }
-// append cell node `node` to the bucket of substrate triangle t: one fire-and-forget RED.MAX brings the head to the current epoch
-// (heads are (epoch << 32 | count) and never reset; epochs only grow), one ATOM.ADD takes a slot.  Same-address atomics of one
-// thread are performed in program order, so the value returned carries the current epoch.  No load, no CAS loop: ONE round trip,
-// whose result (the slot) the caller may leave unconsumed for as long as it likes.
+// append a cell node to the bucket of substrate triangle t; returns the slot.
+//   With the per-triangle reduction behind this kernel (bk.big_count != nullptr, the production chain): ONE 64-bit ATOM.ADD on the
+//   head word.  Its low half is the anchor count of the step; k_finish_reduce / k_bucket_reduce, which visits every triangle that
+//   received an anchor, leaves it at zero again (and the current epoch in the high half, for the substrate kernel) -- no reset pass,
+//   no epoch test, no second atomic here, and the result (the slot) may stay unconsumed for as long as the caller likes.
+//   Without it (k_subs_patch walks the buckets itself): heads are (epoch << 32 | count) and never reset; a fire-and-forget RED.MAX
+//   brings the head to the current epoch first (same-address atomics of one thread are performed in program order).
+// Measured (timing experiment, bench cell): anchor location + insertion cost 33 of k_cell_patch's 95 us -- 2.5 M scattered atomics
+// and partial-sector stores per launch; this form and the epoch stamps moved into the reduction leave 1 M.
 __device__ __forceinline__ unsigned int bucket_take_slot(const BucketView &bk, int t) {
-    atomicMax(bk.head + t, (unsigned long long)bk.epoch << 32);
+    if (!bk.big_count) atomicMax(bk.head + t, (unsigned long long)bk.epoch << 32);
     return (unsigned int)atomicAdd(bk.head + t, 1ull);
 }
 
@@ -839,9 +848,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     // a triangle received an anchor: record the node, stamp the triangle's three nodes and list the triangle when it was the first
     auto finish_insert = [&](int t, unsigned int slot, int v0, int v1, int v2) {
         if (slot < (unsigned int)bk.cap) bk.items[(size_t)t * bk.cap + slot] = i; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
-        if (slot == 0) {                 // first anchor of the step in this triangle: its three nodes have something to gather
-            bk.node_epoch[v0] = bk.epoch; bk.node_epoch[v1] = bk.epoch; bk.node_epoch[v2] = bk.epoch;
-            if (bk.big_count) {          // ... and k_bucket_reduce has a triangle to reduce
+        if (slot == 0) {                 // first anchor of the step in this triangle
+            if (!bk.big_count) { bk.node_epoch[v0] = bk.epoch; bk.node_epoch[v1] = bk.epoch; bk.node_epoch[v2] = bk.epoch; }   // (else: stamped by the reduction)
+            if (bk.big_count) {          // the reduction has a triangle to reduce
                 const int q = atomicAdd(&s_nbig, 1);
                 if (q < 2 * kThreads) s_big[q] = t;
                 else { const unsigned int idx = atomicAdd(bk.big_count, 1u); if (idx < (unsigned int)bk.big_cap) bk.big_list[idx] = t; else atomicOr(a.err, ERR_BUCKET_OVERFLOW); }

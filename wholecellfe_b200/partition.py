@@ -307,7 +307,7 @@ def native_strip(xyz, tri, world, rank, weights=None):
     return out
 
 
-def make_partition(xs, ts, world, cell_xyz, balance=True, cell="replicated", shape="strips"):
+def make_partition(xs, ts, world, cell_xyz, balance=True, cell="replicated", shape="strips", cell_cost=4.0):
     """The substrate partition of a run: pieces of equal COST -- nodes under the cell also gather integrin forces, and with the cell
     partitioned too they carry the cost of the cell nodes above them (balance=False: equal node counts) -- as vertical strips, or
     as sectors around the cell's centroid (every rank then gets its share of the cell as well)."""
@@ -315,7 +315,7 @@ def make_partition(xs, ts, world, cell_xyz, balance=True, cell="replicated", sha
     if balance:
         w = cell_weights(xs, cell_xyz)
         if cell == "partitioned":
-            w = w + cell_cost_weights(xs, cell_xyz)
+            w = w + cell_cost_weights(xs, cell_xyz, cell_cost)
     if shape == "sectors":
         return sector_partition(xs, ts, world, np.asarray(cell_xyz)[:, :2].mean(axis=0), w)
     if shape != "strips":
@@ -435,7 +435,7 @@ class PartitionedSim:
     """One rank of a substrate-partitioned run: full cell + this rank's substrate strip on one GPU."""
 
     def __init__(self, variant, cell_mesh, subs_mesh, dist, device_index, rng=(1, 1), params=None, halo="peer", balance=True,
-                 cell="replicated", margin=0.15, shape="strips"):
+                 cell="replicated", margin=0.15, shape="strips", cell_cost=4.0):
         import torch
         from . import ulstep
         from ._lib import CELL, SUBS
@@ -447,7 +447,7 @@ class PartitionedSim:
         xs, ts = subs_mesh
         if cell == "partitioned" and halo != "peer":
             raise ValueError("a partitioned cell needs the fused peer-memory exchange (halo='peer')")
-        self.parts = make_partition(xs, ts, self.world, cell_mesh[0], balance, cell, shape)
+        self.parts = make_partition(xs, ts, self.world, cell_mesh[0], balance, cell, shape, cell_cost)
         self.part = self.parts[self.rank]
         self.cparts = cell_partition(self.parts, cell_mesh[0], cell_mesh[1], xs, margin) if cell == "partitioned" else None
         self.cpart = self.cparts[self.rank] if self.cparts is not None else None
