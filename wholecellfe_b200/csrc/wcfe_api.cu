@@ -8,6 +8,7 @@
 #include "../../include/wcfe.h"
 #include "wcfe_kernels.cuh"
 #include "wcfe_patch.cuh"
+#include "wcfe_patch_alt.cuh"
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
