@@ -133,7 +133,7 @@ struct wcfe_ctx {
     double ibox[4] = {0, 0, 0, 0};        // region the anchors themselves must stay in (box shrunk by the longest substrate edge)
     // discrete state + flags
     DevBuf<int> d_flags, d_loc_bond, d_loc_cnt, d_loc_first, d_ap_fire, d_err;
-    DevBuf<double2> d_loc_cache;          // CellStepArgs::loc_cache: [4][np] per replica
+    DevBuf<double2> d_loc_cache;          // CellStepArgs::loc_cache: [2][np] per replica
     DevBuf<double> d_partials, d_diag;
     DevBuf<unsigned int> d_tape;
     DevBuf<double> d_drv;                 // scratch of wcfe_driver_velocities
@@ -1362,7 +1362,7 @@ int wcfe_upload_mesh(wcfe_ctx *c, int surface, int nn, const double *xyz, int ne
         CK(c->d_flags.alloc(nn * R)); CK(c->d_loc_bond.alloc(nn * R)); CK(c->d_loc_cnt.alloc(nn * R)); CK(c->d_loc_first.alloc(nn * R)); CK(c->d_ap_fire.alloc(nn * R));
         CK(cudaMemset(c->d_flags.p, 0, sizeof(int) * nn)); CK(cudaMemset(c->d_loc_bond.p, 0xff, sizeof(int) * nn));
         CK(cudaMemset(c->d_loc_cnt.p, 0, sizeof(int) * nn)); CK(cudaMemset(c->d_loc_first.p, 0xff, sizeof(int) * nn)); CK(cudaMemset(c->d_ap_fire.p, 0, sizeof(int) * nn));
-        CK(c->d_loc_cache.alloc((size_t)4 * s.np * R));
+        CK(c->d_loc_cache.alloc((size_t)2 * s.np * R));
         CK(cudaMemset(c->d_loc_cache.p, 0xff, sizeof(double2) * c->d_loc_cache.n));      // triangle id -1: nothing cached
         CK(c->d_partials.alloc((size_t)4 * ((nn + kBlock - 1) / kBlock + 1) * R));
         update_box(c, xyz, nn);

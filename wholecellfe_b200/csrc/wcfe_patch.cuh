@@ -547,10 +547,12 @@ struct CellStepArgs {
     const unsigned int *tape;
     double *partials;
     int *d_flags, *d_loc_bond, *d_loc_cnt, *d_loc_first, *d_ap_fire, *err;
-    // per cell node, the substrate triangle its anchor was found in last: [4][np] double2 = (x1,y1) (x2,y2) (x3,y3) and, as four
-    // ints, (triangle, v1, v2, v3); triangle < 0: nothing cached.  One coalesced read replaces the three dependent gathers
-    // loc_first -> tri -> x at the head of every CTA (16 % of the kernel's stall samples); a HINT only: a stale entry fails the
-    // strict containment test and the grid search takes over.  Valid while the substrate does not move (invalidated at upload).
+    // per cell node, where its anchor was last LOCATED: [2][np] double2 = (anchor x, anchor y) at that moment and (c^2, triangle as
+    // the bits of a 64-bit integer), c the radius around that point inside which every point lies in the triangle with all three
+    // sub-areas above the margin of the previous-triangle shortcut (anchor_clearance2).  While the anchor stays inside the circle --
+    // thousands of steps at the rates anchors creep -- one coalesced 32-byte read and two multiply-adds replace the containment test
+    // and the gathers loc_first -> tri -> x behind it.  triangle < 0 or c^2 <= 0 (also NaN: the 0xff fill): nothing usable, locate.
+    // A geometric fact about the frozen substrate: invalidated when substrate positions are uploaded, by nothing else.
     double2 *loc_cache;
     int debug;
     const HaloPeer *halo_peer;      // partitioned run, not the first step: signal the previous step's halo rows (halo_signal)
@@ -574,6 +576,18 @@ __host__ __device__ inline size_t cell_smem_bytes(int max_halo, int max_elem, in
 //   brings the head to the current epoch first (same-address atomics of one thread are performed in program order).
 // Measured (timing experiment, bench cell): anchor location + insertion cost 33 of k_cell_patch's 95 us -- 2.5 M scattered atomics
 // and partial-sector stores per launch; this form and the epoch stamps moved into the reduction leave 1 M.
+// margin of the previous-triangle shortcut (relative sub-area) and the squared radius around p inside which it holds: a sub-area is
+// linear in p and changes by at most |edge| |dp| / 2, so |dp| < 2 (min A_k - margin A_tri) / max |edge| keeps all three above the
+// margin; 0.999 absorbs the rounding of this very computation (the margin itself is seven orders above the predicate's).
+constexpr double kAnchorMargin = 1e-9;
+__device__ __forceinline__ double anchor_clearance2(const double *Ar, double At, double n1x, double n1y, double n2x, double n2y, double n3x, double n3y) {
+    const double amin = fmin(Ar[0], fmin(Ar[1], Ar[2])) - kAnchorMargin * At;
+    if (!(amin > 0.0)) return 0.0;
+    const double e1 = (n2x - n1x) * (n2x - n1x) + (n2y - n1y) * (n2y - n1y), e2 = (n3x - n1x) * (n3x - n1x) + (n3y - n1y) * (n3y - n1y),
+                 e3 = (n3x - n2x) * (n3x - n2x) + (n3y - n2y) * (n3y - n2y);
+    const double l2 = fmax(e1, fmax(e2, e3));
+    return 0.999 * (4.0 * amin * amin) / l2;
+}
 __device__ __forceinline__ unsigned int bucket_take_slot(const BucketView &bk, int t) {
     if (!bk.big_count) atomicMax(bk.head + t, (unsigned long long)bk.epoch << 32);
     return (unsigned int)atomicAdd(bk.head + t, 1ull);
@@ -593,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         batch_shift(s, r); batch_shift(sub, r); batch_shift(bk, bt, r);
         b.buf += bt.bnd * r; a.partials += bt.partials * r;
         a.d_flags += bt.flags * r; a.d_loc_bond += bt.flags * r; a.d_loc_cnt += bt.flags * r; a.d_loc_first += bt.flags * r; a.d_ap_fire += bt.flags * r; a.err += r;
-        a.loc_cache += 4 * (size_t)s.np * r;
+        a.loc_cache += 2 * (size_t)s.np * r;
         if (bt.seed) a.seed = bt.seed[r];
         if (PREDICT) { x_in += n3; x_out += n3; }
         V_out += n3; A_out += n3;
@@ -636,16 +650,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     int bi = -1;                                   // boundary ordinal of the own node
     // the triangle the anchor was in at the previous step and its (frozen) vertices, from the per-node cache: one coalesced load,
     // in flight behind the staging wait
-    int tprev = -1, tv0 = 0, tv1 = 0, tv2 = 0;
-    double t1x = 0, t1y = 0, t2x = 0, t2y = 0, t3x = 0, t3y = 0;
+    int tprev = -1;
+    double lc_x = 0, lc_y = 0, lc_c2 = 0;
     if (own) {
         V0 = s.V[i]; V1 = s.V[np + i]; Av0 = s.A[i]; Av1 = s.A[np + i]; fa0 = s.fa[i]; fa1 = s.fa[np + i]; cC = s.cC[i];
         bi = b.index[i];
-        const double2 c0 = a.loc_cache[i], c1 = a.loc_cache[(size_t)np + i], c2 = a.loc_cache[2 * (size_t)np + i];
-        const int4 ci = *reinterpret_cast<const int4 *>(a.loc_cache + 3 * (size_t)np + i);
-        t1x = c0.x; t1y = c0.y; t2x = c1.x; t2y = c1.y; t3x = c2.x; t3y = c2.y;
-        tprev = ci.x; tv0 = ci.y; tv1 = ci.z; tv2 = ci.w;
-        if (tprev >= sub.ne) tprev = -1;
+        const double2 c0 = a.loc_cache[i], c1 = a.loc_cache[(size_t)np + i];
+        lc_x = c0.x; lc_y = c0.y; lc_c2 = c1.x;
+        const long long tl = __double_as_longlong(c1.y);
+        tprev = (tl >= 0 && tl < (long long)sub.ne) ? (int)tl : -1;
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -731,32 +744,43 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         // it (all three sub-areas > 0) lies in no other triangle of a conforming substrate mesh, so the grid search -- which
         // finds every containing triangle, as the reference's exhaustive loop does (UL:1309-1452) -- is only needed otherwise.
         bool done = false;
+        auto remember = [&](int t, const double *Ar, double At, double n1x, double n1y, double n2x, double n2y, double n3x, double n3y) {
+            a.loc_cache[i] = make_double2(pt[0], pt[1]);
+            a.loc_cache[(size_t)np + i] = make_double2(anchor_clearance2(Ar, At, n1x, n1y, n2x, n2y, n3x, n3y), __longlong_as_double((long long)t));
+        };
         if (tprev >= 0) {
-            double Ar[3], At;      // planar path: z == 0 everywhere (checked at upload), the 2-D predicate is bit-identical to the 3-D one
-            // margin: within 1e-9 of an edge (relative sub-area) the reference's rounded predicate may ALSO accept the neighbour
-            // (A1 = A_tri - A2 - A3 is formed in floating point, UL:1338): such anchors take the grid search, which reports every
-            // accepting triangle; the margin is seven orders above the rounding it guards against
-            const bool in = point_in_triangle_2d(t1x, t1y, t2x, t2y, t3x, t3y, pt[0], pt[1], Ar, At);
-            const double mrg = 1e-9 * At;
-            if (in && Ar[0] > mrg && Ar[1] > mrg && Ar[2] > mrg) {
+            const double dx = pt[0] - lc_x, dy = pt[1] - lc_y;
+            if (fma(dx, dx, dy * dy) < lc_c2) {              // still inside the circle that was inside the triangle, margin included
                 slot_prev = bucket_take_slot(bk, tprev);      // consumed after the element phase: the round trip hides behind it
                 cnt = 1; first = tprev; done = true;
+            } else {
+                // out of the circle (or no circle: the anchor sits within the margin of an edge): the containment test itself.
+                // margin: within 1e-9 of an edge (relative sub-area) the reference's rounded predicate may ALSO accept the neighbour
+                // (A1 = A_tri - A2 - A3 is formed in floating point, UL:1338): such anchors take the grid search, which reports every
+                // accepting triangle; the margin is seven orders above the rounding it guards against
+                const int v0 = sub.tri[tprev], v1 = sub.tri[sub.nep + tprev], v2 = sub.tri[2 * sub.nep + tprev];
+                const double n1x = sub.x[v0], n1y = sub.x[sub.np + v0], n2x = sub.x[v1], n2y = sub.x[sub.np + v1], n3x = sub.x[v2], n3y = sub.x[sub.np + v2];
+                double Ar[3], At;      // planar path: z == 0 everywhere (checked at upload), the 2-D predicate is bit-identical to the 3-D one
+                const bool in = point_in_triangle_2d(n1x, n1y, n2x, n2y, n3x, n3y, pt[0], pt[1], Ar, At);
+                const double mrg = kAnchorMargin * At;
+                if (in && Ar[0] > mrg && Ar[1] > mrg && Ar[2] > mrg) {
+                    remember(tprev, Ar, At, n1x, n1y, n2x, n2y, n3x, n3y);
+                    slot_prev = bucket_take_slot(bk, tprev);
+                    cnt = 1; first = tprev; done = true;
+                }
             }
         }
         if (!done) {
-            locate(g, sub, pt, [&](int t, const double *, double) {
+            locate(g, sub, pt, [&](int t, const double *Ar, double At) {
                 const int v0 = sub.tri[t], v1 = sub.tri[sub.nep + t], v2 = sub.tri[2 * sub.nep + t];
                 if (cnt == 0) {          // the anchor changed triangle (or had none): remember the new one
                     first = t;
-                    a.loc_cache[i] = make_double2(sub.x[v0], sub.x[sub.np + v0]);
-                    a.loc_cache[(size_t)np + i] = make_double2(sub.x[v1], sub.x[sub.np + v1]);
-                    a.loc_cache[2 * (size_t)np + i] = make_double2(sub.x[v2], sub.x[sub.np + v2]);
-                    *reinterpret_cast<int4 *>(a.loc_cache + 3 * (size_t)np + i) = make_int4(t, v0, v1, v2);
+                    remember(t, Ar, At, sub.x[v0], sub.x[sub.np + v0], sub.x[v1], sub.x[sub.np + v1], sub.x[v2], sub.x[sub.np + v2]);
                 }
                 cnt++;
                 finish_insert(t, bucket_take_slot(bk, t), v0, v1, v2);
             });
-            if (cnt == 0 && tprev >= 0) *reinterpret_cast<int4 *>(a.loc_cache + 3 * (size_t)np + i) = make_int4(-1, 0, 0, 0);
+            if (cnt == 0 && tprev >= 0) a.loc_cache[(size_t)np + i] = make_double2(0.0, __longlong_as_double(-1ll));
         }
         a.d_loc_cnt[i] = cnt; a.d_loc_first[i] = first;
     }
@@ -790,7 +814,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         for (int off = 16; off > 0; off >>= 1) { red0 += __shfl_down_sync(0xffffffffu, red0, off); red1 += __shfl_down_sync(0xffffffffu, red1, off); red2 += __shfl_down_sync(0xffffffffu, red2, off); }
         if ((tid & 31) == 0) { shred[tid >> 5] = red0; shred[8 + (tid >> 5)] = red1; shred[16 + (tid >> 5)] = red2; }
     }
-    if (own && slot_prev != 0xffffffffu) finish_insert(tprev, slot_prev, tv0, tv1, tv2);      // the deferred insert
+    if (own && slot_prev != 0xffffffffu) {      // the deferred insert
+        int tv0 = 0, tv1 = 0, tv2 = 0;
+        if (!bk.big_count) { tv0 = sub.tri[tprev]; tv1 = sub.tri[sub.nep + tprev]; tv2 = sub.tri[2 * sub.nep + tprev]; }   // (the stamps of the protocol without reduction)
+        finish_insert(tprev, slot_prev, tv0, tv1, tv2);
+    }
     __syncthreads();                              // records complete; every insert of this CTA listed
     if (tid == 0) {
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
