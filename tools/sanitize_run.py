@@ -8,6 +8,8 @@ on meshes small enough for the sanitizer's ~50x slow-down.
      k_bucket_reduce<WARP> (coarse substrate), k_subs_ring, PDL chain (or fork/join with `pdl0`)
   2  the adapter sequence on the same meshes: predict / commit / update (k_cell_patch<!PREDICT>), round trip through the host
   3  a 20k-triangle kMD cell on a finer substrate, Philox: k_bucket_reduce<thread per triangle>
+     (1 and 3: the cell is displaced by most of a substrate triangle once, so that the persistent anchor membership is exercised:
+     entries die, buckets are compacted, triangles listed and unlisted)
   4  two substrate strips in one process (HALO instantiation of k_subs_ring, peer stores + in-kernel waits, cell counter)
   5  a batch of 4 replicas (BATCH instantiations)
   6  a non-planar state (general kernels k_predict_cell, k_bond, k_cell_node, k_subs_node)
@@ -37,12 +39,18 @@ for var in ("k1", "k31", "kMD"):
     t = g.step_n(n, 0.005, 0.0)
     for _ in range(3):
         t = g.step(0.005, t)                      # predict / commit / update
-    g.step_n_roundtrip(3, 0.005, t)
+    t, _, _ = g.step_n_roundtrip(3, 0.005, t)
+    x = g.get(W.CELL, "x"); x[:, 0] += 3.7; x[:, 1] -= 2.9          # every anchor leaves its triangle: dead entries, compaction, (un)listing
+    g.set(W.CELL, "x", x)
+    t = g.step_n(3, 0.005, t)
     g.get(W.CELL, "x"); g.close()
 print("1-2 done", flush=True)
 xc3, tc3 = disk_mesh(20000); xs3, ts3 = square_mesh(160)
 g = W.ULSim("kMD"); g.upload_mesh(W.CELL, xc3, tc3); g.upload_mesh(W.SUBS, xs3, ts3); g.set_rng(1, 1)
-g.step_n(n, 5e-5, 0.0); g.get(W.SUBS, "ea"); g.close()
+t = g.step_n(n, 5e-5, 0.0)
+x = g.get(W.CELL, "x"); x[:, 0] += 0.41; x[:, 1] += 0.33            # the same with one thread per bucket
+g.set(W.CELL, "x", x)
+g.step_n(3, 5e-5, t); g.get(W.SUBS, "ea"); g.close()
 print("3 done", flush=True)
 run = InProcessStrips("k31", (xc3, tc3), (xs3, ts3), [0, 0])
 run.step_n(n, 5e-5)

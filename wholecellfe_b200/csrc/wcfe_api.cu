@@ -124,9 +124,11 @@ struct wcfe_ctx {
     int b_cap = 0;
     // list of the triangles that hold anchors + their per-triangle reduction, see k_bucket_reduce
     DevBuf<unsigned int> big_count; DevBuf<int> big_list;
+    DevBuf<double> b_sums;                // BucketView::sums (persistent membership)
+    int persist = 1;                      // WCFE_PERSIST=0: the per-step bucket protocol on the production chain too
     int big_cap = 0, reduce_warp = 0;     // reduce_warp: one warp per listed triangle (coarse substrate) instead of one thread
     bool big_clean = true;                // the list counter is zero (k_subs_ring re-zeroes it at the end of every full step)
-    int head_proto = 0;                   // what the bucket heads hold: 0 zeros, 1 (epoch << 32 | count) never reset (general path, k_subs_patch),
+    int head_proto = 0;                   // what the bucket heads hold: 0 zeros, 3 persistent membership (BucketView), 1 (epoch << 32 | count) never reset (general path, k_subs_patch),
                                           // 2 counts that the reduction returns to zero (production chain, bucket_take_slot)
     unsigned int epoch = 0;
     double box[4] = {0, 0, 0, 0};         // padded anchor region, substrate nodes outside cannot receive force
@@ -661,7 +663,21 @@ int build_buckets(wcfe_ctx *c) {
         c->big_cap = (int)std::max<long long>(64, std::min<long long>(ss.ne, 8LL * cs.nn));
         CK(c->big_count.alloc((size_t)c->nrep)); CK(c->big_list.alloc((size_t)c->big_cap * c->nrep));
         CK(cudaMemset(c->big_count.p, 0, sizeof(unsigned int) * c->nrep));
+        c->persist = 1;
+        if (const char *e = std::getenv("WCFE_PERSIST")) c->persist = std::atoi(e) ? 1 : 0;
+        if (c->persist) CK(c->b_sums.alloc((size_t)6 * ss.nep * c->nrep)); else c->b_sums.release();
     }
+    if (c->d_loc_cache.p) CK(cudaMemset(c->d_loc_cache.p, 0xff, sizeof(double2) * c->d_loc_cache.n));      // membership and cache rows are valid together
+    return WCFE_OK;
+}
+
+// empty buckets, empty triangle list, no cached triangle: whenever what one of them says about the anchors may no longer be what the
+// others say (BucketView, persistent membership)
+int reset_buckets(wcfe_ctx *c) {
+    if (c->b_head.p) CK(cudaMemsetAsync(c->b_head.p, 0, sizeof(unsigned long long) * c->b_head.n, c->stream));
+    if (c->big_count.p) CK(cudaMemsetAsync(c->big_count.p, 0, sizeof(unsigned int) * c->nrep, c->stream));
+    if (c->d_loc_cache.p) CK(cudaMemsetAsync(c->d_loc_cache.p, 0xff, sizeof(double2) * c->d_loc_cache.n, c->stream));
+    c->big_clean = true;
     return WCFE_OK;
 }
 
@@ -782,8 +798,8 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     if (which & 1) c->epoch++;            // the cell half fills the triangle buckets of this epoch, the substrate half reads them
     if (which & 1) {
         // the two bucket-head protocols do not mix: zero the heads when the path changes (planar <-> general, k_subs_ring <-> k_subs_patch)
-        const int proto = (use_planar(c) && c->subs_kernel == 2 && c->big_count.p != nullptr) ? 2 : 1;
-        if (c->head_proto != 0 && c->head_proto != proto) CK(cudaMemsetAsync(c->b_head.p, 0, sizeof(unsigned long long) * c->b_head.n, c->stream));
+        const int proto = (use_planar(c) && c->subs_kernel == 2 && c->big_count.p != nullptr) ? (c->persist ? 3 : 2) : 1;
+        if (c->head_proto != 0 && c->head_proto != proto) { int rcb = reset_buckets(c); if (rcb) return rcb; }
         c->head_proto = proto;
     }
     BucketView bk{c->b_head.p, c->b_items.p, c->b_cap, c->epoch, nullptr, nullptr, 0, c->b_node_epoch.p, c->halo.active ? c->cell_done.p : nullptr, c->cell_target, 0, c->d_err.p};      // the completion counter is a partitioned-run device (the increment costs the cell kernel 3 %)
@@ -794,7 +810,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     const bool planar = use_planar(c);
     int npart = gc;
     const bool reduce = planar && c->subs_kernel == 2 && c->big_count.p != nullptr;
-    if (reduce) { bk.big_count = c->big_count.p; bk.big_list = c->big_list.p; bk.big_cap = c->big_cap; }
+    if (reduce) { bk.big_count = c->big_count.p; bk.big_list = c->big_list.p; bk.big_cap = c->big_cap; bk.sums = c->persist ? c->b_sums.p : nullptr; bk.persist = c->persist; }
     const bool batch = c->nrep > 1;
     bool joined = true;
     const bool overlap = planar && !c->debug && which == 3;
@@ -813,7 +829,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     const double *v_old = cs.V.p, *a_old = cs.A.p;      // general path: V, A are updated in place
     if (!(which & 1)) goto subs_half;
     if (planar) {
-        if (reduce && !c->big_clean) {      // a cell half without its substrate half left a list behind, and counts nobody returned to zero
+        if (reduce && !c->persist && !c->big_clean) {      // a cell half without its substrate half left a list behind, and counts nobody returned to zero
             CK(cudaMemsetAsync(c->big_count.p, 0, sizeof(unsigned int) * c->nrep, c->stream));
             CK(cudaMemsetAsync(c->b_head.p, 0, sizeof(unsigned long long) * c->b_head.n, c->stream));
         }
@@ -1057,6 +1073,7 @@ void cell_part_release(wcfe_ctx *c) {
     if (c->cpart.active && c->s[WCFE_CELL].p_blob.p)      // clear the role words in the descriptors' headers
         cudaMemset2D(c->s[WCFE_CELL].p_blob.p + 8, (size_t)c->s[WCFE_CELL].stride, 0, sizeof(int), (size_t)c->s[WCFE_CELL].npatch);
     c->cpart.active = false; c->cpart.have_info = false; c->cpart.npeer = 0; c->cpart.n_list = 0; c->cpart.step = 0;
+    c->head_proto = -1;                 // the set of patches this context computes changes: memberships of the others' nodes would go stale (reset at the next step)
     c->cpart.flags.release(); c->cpart.partials2.release(); c->cpart.patch_list.release(); c->cpart.exp_ptr.release(); c->cpart.exp_ent.release();
     c->cpart.bexp_ptr.release(); c->cpart.bexp_peer.release(); c->cpart.bnd_local.release(); c->cpart.peers.release();
 }
@@ -1214,7 +1231,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release(); c->b_node_epoch.release(); c->cell_done.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release(); c->d_loc_cache.release();
-    c->d_kb.release(); c->d_seeds.release(); c->big_count.release(); c->big_list.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
+    c->d_kb.release(); c->d_seeds.release(); c->big_count.release(); c->big_list.release(); c->b_sums.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
@@ -1403,7 +1420,7 @@ static int after_upload(wcfe_ctx *c, int surface, int field, const double *host)
     if (field == WCFE_F_X) {
         if (surface == WCFE_CELL) { CK(cudaMemcpyAsync(rsel(c, s.X), rsel(c, s.x), sizeof(double) * 3 * s.np, cudaMemcpyDeviceToDevice, c->stream)); update_box(c, host, s.nn); }
         else {
-            if (c->d_loc_cache.p) CK(cudaMemsetAsync(c->d_loc_cache.p, 0xff, sizeof(double2) * c->d_loc_cache.n, c->stream));   // cached vertex positions are stale
+            if ((rc = reset_buckets(c))) return rc;       // the circles were drawn inside triangles that have moved
             rc = build_grid(c, host); if (rc) return rc;
             if (c->grid_ref.p) CK(cudaMemcpyAsync(c->grid_ref.p, rsel(c, s.x), sizeof(double) * 3 * s.np, cudaMemcpyDeviceToDevice, c->stream));   // the grid now describes these positions
         }
@@ -2146,6 +2163,7 @@ int wcfe_cell_halo_connect(wcfe_ctx *c, int n_peers, const wcfe_cell_halo_info *
     CK(cudaMemcpy2D(cs.p_blob.p + 8, (size_t)cs.stride, role.data(), sizeof(int), sizeof(int), (size_t)cs.npatch, cudaMemcpyHostToDevice));
     CK(cudaStreamSynchronize(c->stream));
     c->cpart.npeer = n_peers; c->cpart.n_list = n_patches; c->cpart.step = 0; c->cpart.margin = anchor_margin; c->cpart.active = true;
+    c->head_proto = -1;                 // from now on only the listed patches file their anchors here: start from empty buckets
     return WCFE_OK;
 }
 

@@ -63,7 +63,20 @@ struct BucketView {          // triangle -> anchored cell nodes, rebuilt every s
     int *chain_err;
     const CellPeer *cell_peer;      // partitioned cell: the substrate kernel's first thread bumps every peer's step counter
     int cell_npeer;
+    // PERSISTENT membership (production chain with the reduction, persist != 0): an anchor changes triangle about once in a thousand
+    // steps, so buckets and the triangle list are kept from step to step and the cell kernel touches them only on a change --
+    //   head word, low half: bit 31 = the triangle is listed, bits 0..30 = entries in use (live, tombstones, this step's appends);
+    //   items: node id; kItemDead = a member that left (its own thread overwrites its entry); | kItemVolatile = an anchor within
+    //   the margin of an edge, located and inserted anew every step (possibly into several triangles), dropped by the reduction;
+    //   the reduction compacts a bucket when it finds either, unlists a triangle whose last member left (list entry -1), and puts
+    //   the six sums into sums[6 * triangle] instead of the head of the item storage, which now has to survive.
+    // Valid together with CellStepArgs::loc_cache ("the node is a member of the triangle its cache row names"): the host resets both
+    // whenever one of them is (path change, substrate upload, mesh upload, partition connect).
+    double *sums;                   // [6 * ne_subs], or nullptr
+    int persist;
 };
+constexpr int kItemDead = -1, kItemVolatile = 0x40000000, kItemId = 0x3fffffff;
+constexpr unsigned int kHeadListed = 0x80000000u, kHeadCount = 0x7fffffffu;
 
 // ---- partitioned CELL (BASELINE configs[3]): every rank keeps the whole cell's arrays, with the single-GPU numbering, but computes
 // only the patches that can put an anchor into its substrate strip (a patch on a cut is computed by both neighbours).  What a rank
@@ -134,6 +147,7 @@ __device__ __forceinline__ void batch_shift(BucketView &bk, const BatchView &bt,
     bk.head += bt.head * r; bk.items += bt.items * r;
     if (bk.big_count) { bk.big_count += r; bk.big_list += (size_t)bk.big_cap * r; }
     if (bk.node_epoch) bk.node_epoch += bt.snodes * r;
+    if (bk.sums) bk.sums += 6 * bt.head * r;
 }
 
 enum : int { ERR_BUCKET_OVERFLOW = 1, ERR_LOC_OVERFLOW = 2, ERR_NAN = 4, ERR_REGION = 8, ERR_CHAIN = 32 };   // 16: ERR_HALO_TIMEOUT (wcfe_patch.cuh)

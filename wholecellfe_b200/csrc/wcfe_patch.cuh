@@ -267,7 +267,7 @@ __device__ __forceinline__ void ring_node(const SurfView &s, const PatchView &pv
     // (chained behind this kernel only) depends on; it also re-zeroes the triangle list k_bucket_reduce has consumed
     if (zero_list) {
         pdl_wait();
-        if (bk.big_count) *bk.big_count = 0;
+        if (bk.big_count && !bk.persist) *bk.big_count = 0;
         // partitioned cell: this step's cell kernel, boundary finish and reduction are complete on this rank -- every row it pushes is
         // out, every pushed row it reads has been read
         if (bk.cell_peer) cell_part_signal(bk.cell_peer, bk.cell_npeer, 0);
@@ -303,7 +303,9 @@ __device__ __forceinline__ void ring_node(const SurfView &s, const PatchView &pv
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const bool on = code4[u] >= 0 && (unsigned int)(h4[u] >> 32) == bk.epoch;
-                f4[u] = on ? reinterpret_cast<const double2 *>(bk.items + (size_t)(code4[u] >> 2) * bk.cap)[code4[u] & 3] : make_double2(0.0, 0.0);
+                const double2 *sums = bk.persist ? reinterpret_cast<const double2 *>(bk.sums + (size_t)6 * (code4[u] >> 2))
+                                                 : reinterpret_cast<const double2 *>(bk.items + (size_t)(code4[u] >> 2) * bk.cap);
+                f4[u] = on ? sums[code4[u] & 3] : make_double2(0.0, 0.0);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) { Fx = __dadd_rn(Fx, f4[u].x); Fy = __dadd_rn(Fy, f4[u].y); }      // (+0 for the triangles without anchors)
@@ -440,16 +442,19 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
     if (!WARP) {
         for (int b = bid * blockDim.x + threadIdx.x; b < nbig; b += nblk * blockDim.x) {
             const int e = bk.big_list[b];
-            int cnt = (int)(unsigned int)bk.head[e];
+            if (e < 0) continue;                     // (persistent list: a triangle whose last member left)
+            int cnt = (int)((unsigned int)bk.head[e] & (bk.persist ? kHeadCount : 0xffffffffu));
             if (cnt > bk.cap) cnt = bk.cap;
             int *items = bk.items + (size_t)e * bk.cap;
             const int i0 = s.tri[e], i1 = s.tri[s.nep + e], i2 = s.tri[2 * s.nep + e];
             const double n1x = s.x[i0], n1y = s.x[s.np + i0], n2x = s.x[i1], n2y = s.x[s.np + i1], n3x = s.x[i2], n3y = s.x[s.np + i2];
             double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+            int nlive = 0; bool dirty = false;
+            for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v < 0) dirty = true; else { nlive++; dirty |= (v & kItemVolatile) != 0; } }
             int prev = -1;
-            for (int m = 0; m < cnt; m++) {          // ascending cell-node order: deterministic whatever the insertion order was
+            for (int m = 0; m < nlive; m++) {        // ascending cell-node order: deterministic whatever the insertion order was
                 int ni = 0x7fffffff;
-                for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v > prev && v < ni) ni = v; }
+                for (int q = 0; q < cnt; q++) { const int v = items[q]; const int id = v & kItemId; if (v >= 0 && id > prev && id < ni) ni = id; }
                 prev = ni;
                 const double2 ap = anc2[2 * (size_t)ni], ah = anc2[2 * (size_t)ni + 1];
                 double Ar[3], At;                                                        // UL:1303-1340; planar form, bit-identical
@@ -458,11 +463,20 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
                 const double w0 = quot(Ar[0], rt), w1 = quot(Ar[1], rt), w2 = quot(Ar[2], rt);
                 a0 += ah.x * w0; a1 += ah.y * w0; a2 += ah.x * w1; a3 += ah.y * w1; a4 += ah.x * w2; a5 += ah.y * w2;   // UL:1414-1422
             }
-            double2 *o = reinterpret_cast<double2 *>(items);      // this thread alone reads and writes the bucket
-            o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3); o[2] = make_double2(a4, a5);
-            // the triangle's three nodes have something to gather in this step; its count starts the next step at zero
+            // the triangle's three nodes have something to gather in this step
             bk.node_epoch[i0] = bk.epoch; bk.node_epoch[i1] = bk.epoch; bk.node_epoch[i2] = bk.epoch;
-            bk.head[e] = (unsigned long long)bk.epoch << 32;
+            if (bk.persist) {
+                double2 *o = reinterpret_cast<double2 *>(bk.sums + (size_t)6 * e);
+                o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3); o[2] = make_double2(a4, a5);
+                int w = cnt;
+                if (dirty) { w = 0; for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v >= 0 && !(v & kItemVolatile)) items[w++] = v; } }   // this thread alone owns the bucket now
+                if (w) bk.head[e] = ((unsigned long long)bk.epoch << 32) | kHeadListed | (unsigned int)w;
+                else { bk.head[e] = (unsigned long long)bk.epoch << 32; bk.big_list[b] = -1; }       // nobody left: unlisted until an anchor arrives again
+            } else {
+                double2 *o = reinterpret_cast<double2 *>(items);      // this thread alone reads and writes the bucket; its count starts the next step at zero
+                o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3); o[2] = make_double2(a4, a5);
+                bk.head[e] = (unsigned long long)bk.epoch << 32;
+            }
         }
         return;
     }
@@ -470,17 +484,23 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
     double (*tw)[6] = term[WARP ? warp : 0];
     for (int b = bid * kReduceWarps + warp; b < nbig; b += nblk * kReduceWarps) {
         const int e = bk.big_list[b];
-        int cnt = (int)(unsigned int)bk.head[e];
+        if (e < 0) continue;                         // (persistent list: a triangle whose last member left; uniform across the warp)
+        int cnt = (int)((unsigned int)bk.head[e] & (bk.persist ? kHeadCount : 0xffffffffu));
         if (cnt > bk.cap) cnt = bk.cap;
         int *items = bk.items + (size_t)e * bk.cap;
         const int i0 = s.tri[e], i1 = s.tri[s.nep + e], i2 = s.tri[2 * s.nep + e];
         const double n1[3] = {s.x[i0], s.x[s.np + i0], 0.0}, n2[3] = {s.x[i1], s.x[s.np + i1], 0.0}, n3[3] = {s.x[i2], s.x[s.np + i2], 0.0};
+        int nlive = 0, dirty = 0;
+        for (int m = lane; m < cnt; m += 32) { const int v = items[m]; if (v < 0) dirty = 1; else { nlive++; dirty |= (v & kItemVolatile) != 0; } }
+        nlive = __reduce_add_sync(0xffffffffu, nlive); dirty = __any_sync(0xffffffffu, dirty);
         double acc = 0.0;                                   // lanes 0..5: (vertex, component) = (lane >> 1, lane & 1)
-        for (int w0 = 0; w0 < cnt; w0 += kReduceWindow) {   // one window unless a bucket holds more than 128 anchors
+        for (int w0 = 0; w0 < nlive; w0 += kReduceWindow) {   // one window unless a bucket holds more than 128 anchors
             for (int m = lane; m < cnt; m += 32) {
-                const int v = items[m];
+                const int vv = items[m];
+                if (vv < 0) continue;
+                const int v = vv & kItemId;
                 int rank = 0;
-                for (int q = 0; q < cnt; q++) rank += items[q] < v;      // node ids inside a bucket are distinct
+                for (int q = 0; q < cnt; q++) { const int u = items[q]; rank += (u >= 0 && (u & kItemId) < v); }      // node ids inside a bucket are distinct
                 if (rank < w0 || rank >= w0 + kReduceWindow) continue;
                 const double2 ap = anc2[2 * (size_t)v], ah = anc2[2 * (size_t)v + 1];
                 double Ar[3], At;
@@ -492,14 +512,25 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
             }
             __syncwarp();
             if (lane < 6) {
-                const int n = min(kReduceWindow, cnt - w0);
+                const int n = min(kReduceWindow, nlive - w0);
 #pragma unroll 8
                 for (int r = 0; r < n; r++) acc += tw[r][lane];      // the loads are independent of the running sum: unrolled, they pipeline
             }
             __syncwarp();
         }
-        if (lane < 6) reinterpret_cast<double *>(items)[lane] = acc;     // every lane has finished reading the items (syncwarp above)
-        if (lane == 6) { bk.node_epoch[i0] = bk.epoch; bk.node_epoch[i1] = bk.epoch; bk.node_epoch[i2] = bk.epoch; bk.head[e] = (unsigned long long)bk.epoch << 32; }
+        if (bk.persist) {
+            if (lane < 6) bk.sums[(size_t)6 * e + lane] = acc;
+            if (lane == 6) {
+                bk.node_epoch[i0] = bk.epoch; bk.node_epoch[i1] = bk.epoch; bk.node_epoch[i2] = bk.epoch;
+                int w = cnt;
+                if (dirty) { w = 0; for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v >= 0 && !(v & kItemVolatile)) items[w++] = v; } }   // every lane has finished reading the items (syncwarp above)
+                if (w) bk.head[e] = ((unsigned long long)bk.epoch << 32) | kHeadListed | (unsigned int)w;
+                else { bk.head[e] = (unsigned long long)bk.epoch << 32; bk.big_list[b] = -1; }
+            }
+        } else {
+            if (lane < 6) reinterpret_cast<double *>(items)[lane] = acc;     // every lane has finished reading the items (syncwarp above)
+            if (lane == 6) { bk.node_epoch[i0] = bk.epoch; bk.node_epoch[i1] = bk.epoch; bk.node_epoch[i2] = bk.epoch; bk.head[e] = (unsigned long long)bk.epoch << 32; }
+        }
     }
 }
 
@@ -711,11 +742,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     unsigned int slot_prev = 0xffffffffu;          // deferred: the slot taken in the previous step's triangle (result of an atomic in flight)
     int cnt = 0, first = -1;
     // a triangle received an anchor: record the node, stamp the triangle's three nodes and list the triangle when it was the first
-    auto finish_insert = [&](int t, unsigned int slot, int v0, int v1, int v2) {
-        if (slot < (unsigned int)bk.cap) bk.items[(size_t)t * bk.cap + slot] = i; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
-        if (slot == 0) {                 // first anchor of the step in this triangle
+    // (persistent membership, BucketView: the slot word's bit 31 says the triangle is listed already; item = node id | flags)
+    auto finish_insert = [&](int t, unsigned int slot_raw, int v0, int v1, int v2, int item) {
+        const unsigned int slot = bk.persist ? (slot_raw & kHeadCount) : slot_raw;
+        if (slot < (unsigned int)bk.cap) bk.items[(size_t)t * bk.cap + slot] = item; else atomicOr(a.err, ERR_BUCKET_OVERFLOW);
+        if (slot_raw == 0) {             // first anchor of the step in this triangle (persistent: of an empty, unlisted triangle)
             if (!bk.big_count) { bk.node_epoch[v0] = bk.epoch; bk.node_epoch[v1] = bk.epoch; bk.node_epoch[v2] = bk.epoch; }   // (else: stamped by the reduction)
             if (bk.big_count) {          // the reduction has a triangle to reduce
+                if (bk.persist) atomicOr(bk.head + t, (unsigned long long)kHeadListed);
                 const int q = atomicAdd(&s_nbig, 1);
                 if (q < 2 * kThreads) s_big[q] = t;
                 else { const unsigned int idx = atomicAdd(bk.big_count, 1u); if (idx < (unsigned int)bk.big_cap) bk.big_list[idx] = t; else atomicOr(a.err, ERR_BUCKET_OVERFLOW); }
@@ -744,15 +778,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
         // it (all three sub-areas > 0) lies in no other triangle of a conforming substrate mesh, so the grid search -- which
         // finds every containing triangle, as the reference's exhaustive loop does (UL:1309-1452) -- is only needed otherwise.
         bool done = false;
+        // (no circle -- the anchor sits within the margin of an edge --: nothing to remember, the next step locates again)
         auto remember = [&](int t, const double *Ar, double At, double n1x, double n1y, double n2x, double n2y, double n3x, double n3y) {
+            const double c2 = anchor_clearance2(Ar, At, n1x, n1y, n2x, n2y, n3x, n3y);
             a.loc_cache[i] = make_double2(pt[0], pt[1]);
-            a.loc_cache[(size_t)np + i] = make_double2(anchor_clearance2(Ar, At, n1x, n1y, n2x, n2y, n3x, n3y), __longlong_as_double((long long)t));
+            a.loc_cache[(size_t)np + i] = make_double2(c2, __longlong_as_double(c2 > 0.0 ? (long long)t : -1ll));
+            return c2 > 0.0;
         };
         if (tprev >= 0) {
             const double dx = pt[0] - lc_x, dy = pt[1] - lc_y;
             if (fma(dx, dx, dy * dy) < lc_c2) {              // still inside the circle that was inside the triangle, margin included
-                slot_prev = bucket_take_slot(bk, tprev);      // consumed after the element phase: the round trip hides behind it
-                cnt = 1; first = tprev; done = true;
+                if (!bk.persist) slot_prev = bucket_take_slot(bk, tprev);      // consumed after the element phase: the round trip hides behind it
+                cnt = 1; first = tprev; done = true;                           // (persistent membership: nothing to do at all)
             } else {
                 // out of the circle (or no circle: the anchor sits within the margin of an edge): the containment test itself.
                 // margin: within 1e-9 of an edge (relative sub-area) the reference's rounded predicate may ALSO accept the neighbour
@@ -763,22 +800,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
                 double Ar[3], At;      // planar path: z == 0 everywhere (checked at upload), the 2-D predicate is bit-identical to the 3-D one
                 const bool in = point_in_triangle_2d(n1x, n1y, n2x, n2y, n3x, n3y, pt[0], pt[1], Ar, At);
                 const double mrg = kAnchorMargin * At;
-                if (in && Ar[0] > mrg && Ar[1] > mrg && Ar[2] > mrg) {
-                    remember(tprev, Ar, At, n1x, n1y, n2x, n2y, n3x, n3y);
-                    slot_prev = bucket_take_slot(bk, tprev);
+                if (in && Ar[0] > mrg && Ar[1] > mrg && Ar[2] > mrg && remember(tprev, Ar, At, n1x, n1y, n2x, n2y, n3x, n3y)) {
+                    if (!bk.persist) slot_prev = bucket_take_slot(bk, tprev);
                     cnt = 1; first = tprev; done = true;
+                } else if (bk.persist) {
+                    // the anchor leaves the triangle it is a member of (or comes within the margin of its edges): its entry dies
+                    const int n = min((int)((unsigned int)bk.head[tprev] & kHeadCount), bk.cap);
+                    int *it = bk.items + (size_t)tprev * bk.cap;
+                    for (int q = 0; q < n; q++) if (it[q] == i) { it[q] = kItemDead; break; }
                 }
             }
         }
         if (!done) {
+            bool stay = false;           // strictly inside one triangle, margin included: a persistent member
             locate(g, sub, pt, [&](int t, const double *Ar, double At) {
                 const int v0 = sub.tri[t], v1 = sub.tri[sub.nep + t], v2 = sub.tri[2 * sub.nep + t];
                 if (cnt == 0) {          // the anchor changed triangle (or had none): remember the new one
                     first = t;
-                    remember(t, Ar, At, sub.x[v0], sub.x[sub.np + v0], sub.x[v1], sub.x[sub.np + v1], sub.x[v2], sub.x[sub.np + v2]);
+                    stay = remember(t, Ar, At, sub.x[v0], sub.x[sub.np + v0], sub.x[v1], sub.x[sub.np + v1], sub.x[v2], sub.x[sub.np + v2]);
                 }
                 cnt++;
-                finish_insert(t, bucket_take_slot(bk, t), v0, v1, v2);
+                finish_insert(t, bucket_take_slot(bk, t), v0, v1, v2, (bk.persist && (!stay || cnt > 1)) ? (i | kItemVolatile) : i);
             });
             if (cnt == 0 && tprev >= 0) a.loc_cache[(size_t)np + i] = make_double2(0.0, __longlong_as_double(-1ll));
         }
@@ -817,7 +859,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlk) k_cell_patch(SurfView s, Pa
     if (own && slot_prev != 0xffffffffu) {      // the deferred insert
         int tv0 = 0, tv1 = 0, tv2 = 0;
         if (!bk.big_count) { tv0 = sub.tri[tprev]; tv1 = sub.tri[sub.nep + tprev]; tv2 = sub.tri[2 * sub.nep + tprev]; }   // (the stamps of the protocol without reduction)
-        finish_insert(tprev, slot_prev, tv0, tv1, tv2);
+        finish_insert(tprev, slot_prev, tv0, tv1, tv2, i);
     }
     __syncthreads();                              // records complete; every insert of this CTA listed
     if (tid == 0) {
