@@ -1768,24 +1768,19 @@ static int roundtrip_cell(wcfe_ctx *c, int n, double dt, double *t_io, long long
     double *dc = c->d_aos.p;
     double t = *t_io;
     cudaStream_t cp = c->side;
-    const bool zc = std::getenv("WCFE_ZEROCOPY") && std::atoi(std::getenv("WCFE_ZEROCOPY"));
+    // (the transposes reading / writing the pinned host buffer directly -- no DMA copies -- were measured: 1.24e10 against 1.48e10
+    // element-steps/s; the copy engines move the 12 MB faster than SM-issued PCIe traffic does)
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaEventRecord(c->ev_fork, c->stream));                  // the first hand-over follows whatever is queued on the main stream
     for (int q = 0; q < n; q++) {
         CK(cudaStreamWaitEvent(cp, c->ev_fork, 0));              // cell half of step q-1 (finish kernel included) is complete
         if (q) CK(cudaMemcpyAsync(hd, c->d_diag.p, 64, cudaMemcpyDeviceToHost, cp));   // the step's result: area, centroid, ...
         k_predict_cell<<<(cs.nn + kBlock - 1) / kBlock, kBlock, 0, cp>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt);
-        if (zc) {
-            k_soa_to_aos<<<aos_grid(nc3), kBlock, 0, cp>>>(cs.nn, cs.np, 3, cs.x.p, (double *)hx);
-            CK(cudaStreamSynchronize(cp));
-            k_aos_to_soa<<<aos_grid((size_t)3 * cs.np), kBlock, 0, cp>>>(cs.nn, cs.np, 3, (const double *)hx, cs.x.p);
-        } else {
         k_soa_to_aos<<<aos_grid(nc3), kBlock, 0, cp>>>(cs.nn, cs.np, 3, cs.x.p, dc);
         CK(cudaMemcpyAsync(hx, dc, bytes, cudaMemcpyDeviceToHost, cp));
         CK(cudaStreamSynchronize(cp));                           // the host integrator (El Topo integrate(), main.cpp:248) would run here
         CK(cudaMemcpyAsync(dc, hx, bytes, cudaMemcpyHostToDevice, cp));
         k_aos_to_soa<<<aos_grid((size_t)3 * cs.np), kBlock, 0, cp>>>(cs.nn, cs.np, 3, dc, cs.x.p);
-        }
         CK(cudaEventRecord(c->ev_join, cp));
         c->launches += 3;
         CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
