@@ -9,7 +9,7 @@ on meshes small enough for the sanitizer's ~50x slow-down.
   2  the adapter sequence on the same meshes: predict / commit / update (k_cell_patch<!PREDICT>), round trip through the host
   3  a 20k-triangle kMD cell on a finer substrate, Philox: k_bucket_reduce<thread per triangle>
      (1 and 3: the cell is displaced by most of a substrate triangle once, so that the persistent anchor membership is exercised:
-     entries die, buckets are compacted, triangles listed and unlisted)
+     entries die, buckets are compacted, triangles listed)
   4  two substrate strips in one process (HALO instantiation of k_subs_ring, peer stores + in-kernel waits, cell counter)
   5  a batch of 4 replicas (BATCH instantiations)
   6  a non-planar state (general kernels k_predict_cell, k_bond, k_cell_node, k_subs_node)
@@ -40,7 +40,7 @@ for var in ("k1", "k31", "kMD"):
     for _ in range(3):
         t = g.step(0.005, t)                      # predict / commit / update
     t, _, _ = g.step_n_roundtrip(3, 0.005, t)
-    x = g.get(W.CELL, "x"); x[:, 0] += 3.7; x[:, 1] -= 2.9          # every anchor leaves its triangle: dead entries, compaction, (un)listing
+    x = g.get(W.CELL, "x"); x[:, 0] += 3.7; x[:, 1] -= 2.9          # every anchor leaves its triangle: dead entries, compaction, listing
     g.set(W.CELL, "x", x)
     t = g.step_n(3, 0.005, t)
     g.get(W.CELL, "x"); g.close()

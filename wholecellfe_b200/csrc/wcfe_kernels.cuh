@@ -68,8 +68,9 @@ struct BucketView {          // triangle -> anchored cell nodes, rebuilt every s
     //   head word, low half: bit 31 = the triangle is listed, bits 0..30 = entries in use (live, tombstones, this step's appends);
     //   items: node id; kItemDead = a member that left (its own thread overwrites its entry); | kItemVolatile = an anchor within
     //   the margin of an edge, located and inserted anew every step (possibly into several triangles), dropped by the reduction;
-    //   the reduction compacts a bucket when it finds either, unlists a triangle whose last member left (list entry -1), and puts
-    //   the six sums into sums[6 * triangle] instead of the head of the item storage, which now has to survive.
+    //   the reduction compacts a bucket when it finds either and puts the six sums into sums[6 * triangle] instead of the head of the
+    //   item storage, which now has to survive.  A triangle stays listed once it has held an anchor (an empty one costs the reduction
+    //   one load): the list grows with the area the anchors have visited since the last reset, never with the number of crossings.
     // Valid together with CellStepArgs::loc_cache ("the node is a member of the triangle its cache row names"): the host resets both
     // whenever one of them is (path change, substrate upload, mesh upload, partition connect).
     double *sums;                   // [6 * ne_subs], or nullptr

@@ -442,8 +442,9 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
     if (!WARP) {
         for (int b = bid * blockDim.x + threadIdx.x; b < nbig; b += nblk * blockDim.x) {
             const int e = bk.big_list[b];
-            if (e < 0) continue;                     // (persistent list: a triangle whose last member left)
-            int cnt = (int)((unsigned int)bk.head[e] & (bk.persist ? kHeadCount : 0xffffffffu));
+            const unsigned long long hw = bk.head[e];
+            int cnt = (int)((unsigned int)hw & (bk.persist ? kHeadCount : 0xffffffffu));
+            if (bk.persist && cnt == 0) continue;    // a listed triangle nobody is in at the moment (it stays listed: an anchor that comes back does not list it twice)
             if (cnt > bk.cap) cnt = bk.cap;
             int *items = bk.items + (size_t)e * bk.cap;
             const int i0 = s.tri[e], i1 = s.tri[s.nep + e], i2 = s.tri[2 * s.nep + e];
@@ -470,8 +471,7 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
                 o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3); o[2] = make_double2(a4, a5);
                 int w = cnt;
                 if (dirty) { w = 0; for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v >= 0 && !(v & kItemVolatile)) items[w++] = v; } }   // this thread alone owns the bucket now
-                if (w) bk.head[e] = ((unsigned long long)bk.epoch << 32) | kHeadListed | (unsigned int)w;
-                else { bk.head[e] = (unsigned long long)bk.epoch << 32; bk.big_list[b] = -1; }       // nobody left: unlisted until an anchor arrives again
+                bk.head[e] = ((unsigned long long)bk.epoch << 32) | kHeadListed | (unsigned int)w;
             } else {
                 double2 *o = reinterpret_cast<double2 *>(items);      // this thread alone reads and writes the bucket; its count starts the next step at zero
                 o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3); o[2] = make_double2(a4, a5);
@@ -484,8 +484,8 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
     double (*tw)[6] = term[WARP ? warp : 0];
     for (int b = bid * kReduceWarps + warp; b < nbig; b += nblk * kReduceWarps) {
         const int e = bk.big_list[b];
-        if (e < 0) continue;                         // (persistent list: a triangle whose last member left; uniform across the warp)
         int cnt = (int)((unsigned int)bk.head[e] & (bk.persist ? kHeadCount : 0xffffffffu));
+        if (bk.persist && cnt == 0) continue;        // a listed triangle nobody is in at the moment (uniform across the warp)
         if (cnt > bk.cap) cnt = bk.cap;
         int *items = bk.items + (size_t)e * bk.cap;
         const int i0 = s.tri[e], i1 = s.tri[s.nep + e], i2 = s.tri[2 * s.nep + e];
@@ -524,8 +524,7 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
                 bk.node_epoch[i0] = bk.epoch; bk.node_epoch[i1] = bk.epoch; bk.node_epoch[i2] = bk.epoch;
                 int w = cnt;
                 if (dirty) { w = 0; for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v >= 0 && !(v & kItemVolatile)) items[w++] = v; } }   // every lane has finished reading the items (syncwarp above)
-                if (w) bk.head[e] = ((unsigned long long)bk.epoch << 32) | kHeadListed | (unsigned int)w;
-                else { bk.head[e] = (unsigned long long)bk.epoch << 32; bk.big_list[b] = -1; }
+                bk.head[e] = ((unsigned long long)bk.epoch << 32) | kHeadListed | (unsigned int)w;
             }
         } else {
             if (lane < 6) reinterpret_cast<double *>(items)[lane] = acc;     // every lane has finished reading the items (syncwarp above)
