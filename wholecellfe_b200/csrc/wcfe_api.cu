@@ -126,6 +126,7 @@ struct wcfe_ctx {
     DevBuf<unsigned int> big_count; DevBuf<int> big_list;
     DevBuf<double> b_sums;                // BucketView::sums (persistent membership)
     int persist = 1;                      // WCFE_PERSIST=0: the per-step bucket protocol on the production chain too
+    int reduce_bps = 8;                   // reduction blocks per SM (thread-per-triangle form; grid-stride)
     int big_cap = 0, reduce_warp = 0;     // reduce_warp: one warp per listed triangle (coarse substrate) instead of one thread
     bool big_clean = true;                // the list counter is zero (k_subs_ring re-zeroes it at the end of every full step)
     int head_proto = 0;                   // what the bucket heads hold: 0 zeros, 3 persistent membership (BucketView), 1 (epoch << 32 | count) never reset (general path, k_subs_patch),
@@ -665,6 +666,7 @@ int build_buckets(wcfe_ctx *c) {
         CK(cudaMemset(c->big_count.p, 0, sizeof(unsigned int) * c->nrep));
         c->persist = 1;
         if (const char *e = std::getenv("WCFE_PERSIST")) c->persist = std::atoi(e) ? 1 : 0;
+        if (const char *e = std::getenv("WCFE_REDUCE_BPS")) c->reduce_bps = std::max(1, std::atoi(e));
         if (c->persist) CK(c->b_sums.alloc((size_t)6 * ss.nep * c->nrep)); else c->b_sums.release();
     }
     if (c->d_loc_cache.p) CK(cudaMemset(c->d_loc_cache.p, 0xff, sizeof(double2) * c->d_loc_cache.n));      // membership and cache rows are valid together
@@ -919,7 +921,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     // bucket reduction: one warp per listed triangle (coarse substrate), or one thread (about one triangle in two cell nodes is
     // listed on a substrate finer than the cell)
     const int gr = c->reduce_warp ? std::max(1, std::min(4 * c->num_sms, (cs.nn / 64 + kReduceWarps - 1) / kReduceWarps))
-                                  : std::max(1, std::min(8 * c->num_sms, (cs.nn + kReduceWarps * 32 - 1) / (kReduceWarps * 32)));
+                                  : std::max(1, std::min(c->reduce_bps * c->num_sms, (cs.nn + kReduceWarps * 32 - 1) / (kReduceWarps * 32)));
     if (pdl && reduce) {
         // production chain: boundary finish and bucket reduction as ONE link (k_finish_reduce)
         const dim3 g2(fb + gr, R), b2(kReduceWarps * 32);
@@ -1775,14 +1777,13 @@ static int roundtrip_cell(wcfe_ctx *c, int n, double dt, double *t_io, long long
     for (int q = 0; q < n; q++) {
         CK(cudaStreamWaitEvent(cp, c->ev_fork, 0));              // cell half of step q-1 (finish kernel included) is complete
         if (q) CK(cudaMemcpyAsync(hd, c->d_diag.p, 64, cudaMemcpyDeviceToHost, cp));   // the step's result: area, centroid, ...
-        k_predict_cell<<<(cs.nn + kBlock - 1) / kBlock, kBlock, 0, cp>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt);
-        k_soa_to_aos<<<aos_grid(nc3), kBlock, 0, cp>>>(cs.nn, cs.np, 3, cs.x.p, dc);
+        k_predict_cell<<<(cs.nn + kBlock - 1) / kBlock, kBlock, 0, cp>>>(cs.nn, cs.np, cs.x.p, cs.X.p, cs.V.p, cs.A.p, dt, dc);   // SoA state and the AoS hand-over in one pass
         CK(cudaMemcpyAsync(hx, dc, bytes, cudaMemcpyDeviceToHost, cp));
         CK(cudaStreamSynchronize(cp));                           // the host integrator (El Topo integrate(), main.cpp:248) would run here
         CK(cudaMemcpyAsync(dc, hx, bytes, cudaMemcpyHostToDevice, cp));
         k_aos_to_soa<<<aos_grid((size_t)3 * cs.np), kBlock, 0, cp>>>(cs.nn, cs.np, 3, dc, cs.x.p);
         CK(cudaEventRecord(c->ev_join, cp));
-        c->launches += 3;
+        c->launches += 2;
         CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         const unsigned int *tape = c->d_tape.p ? c->d_tape.p + (size_t)q * cs.nb : nullptr;
         if ((rc = launch_update(c, dt, dt, t, tape, false, 1))) return rc;    // cell half: follows the substrate half of step q-1 in stream order

@@ -154,8 +154,10 @@ __device__ __forceinline__ void batch_shift(BucketView &bk, const BatchView &bt,
 enum : int { ERR_BUCKET_OVERFLOW = 1, ERR_LOC_OVERFLOW = 2, ERR_NAN = 4, ERR_REGION = 8, ERR_CHAIN = 32 };   // 16: ERR_HALO_TIMEOUT (wcfe_patch.cuh)
 
 // ---- predictor: driverVelocities_Explicit + inline predictor (UL:103-124, main.cpp:224-242) ---------------
+// (aos != nullptr: the predicted positions also as the array of Vec3d the host integrator receives -- the round trip's hand-over
+// without a transpose pass of its own)
 __global__ void __launch_bounds__(kBlock) k_predict_cell(int nn, int np, double *__restrict__ x, double *__restrict__ X,
-                                                         const double *__restrict__ V, const double *__restrict__ A, double dt) {
+                                                         const double *__restrict__ V, const double *__restrict__ A, double dt, double *__restrict__ aos = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nn) return;
 #pragma unroll
@@ -166,7 +168,9 @@ __global__ void __launch_bounds__(kBlock) k_predict_cell(int nn, int np, double 
         double vh = WCFE_ADD(V[c * np + i], WCFE_MUL(dt / 2.0, A[c * np + i]));
         if (c == 2) vh = 0.0;
         X[c * np + i] = xo;
-        x[c * np + i] = WCFE_ADD(xo, WCFE_MUL(dt, vh));
+        const double xn = WCFE_ADD(xo, WCFE_MUL(dt, vh));
+        x[c * np + i] = xn;
+        if (aos) aos[3 * (size_t)i + c] = xn;
     }
 }
 
