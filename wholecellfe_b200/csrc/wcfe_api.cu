@@ -661,12 +661,13 @@ int build_buckets(wcfe_ctx *c) {
     if (c->subs_kernel == 2) {
         // every triangle that holds an anchor is listed once: at most all of them, and an anchor ON a vertex counts for the whole fan
         // (UL:1309-1452 has no break), so 2 per cell node is not a bound -- 8 covers a cell snapped onto a union-jack substrate's vertices
-        c->big_cap = (int)std::max<long long>(64, std::min<long long>(ss.ne, 8LL * cs.nn));
-        CK(c->big_count.alloc((size_t)c->nrep)); CK(c->big_list.alloc((size_t)c->big_cap * c->nrep));
-        CK(cudaMemset(c->big_count.p, 0, sizeof(unsigned int) * c->nrep));
         c->persist = 1;
         if (const char *e = std::getenv("WCFE_PERSIST")) c->persist = std::atoi(e) ? 1 : 0;
         if (const char *e = std::getenv("WCFE_REDUCE_BPS")) c->reduce_bps = std::max(1, std::atoi(e));
+        // (persistent membership: a triangle is listed at most once between two resets -- the list can hold them all)
+        c->big_cap = c->persist ? std::max(64, ss.ne) : (int)std::max<long long>(64, std::min<long long>(ss.ne, 8LL * cs.nn));
+        CK(c->big_count.alloc((size_t)c->nrep)); CK(c->big_list.alloc((size_t)c->big_cap * c->nrep));
+        CK(cudaMemset(c->big_count.p, 0, sizeof(unsigned int) * c->nrep));
         if (c->persist) CK(c->b_sums.alloc((size_t)6 * ss.nep * c->nrep)); else c->b_sums.release();
     }
     if (c->d_loc_cache.p) CK(cudaMemset(c->d_loc_cache.p, 0xff, sizeof(double2) * c->d_loc_cache.n));      // membership and cache rows are valid together
