@@ -931,8 +931,7 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
         else if (batch) { if (c->reduce_warp) WCFE_FR(true, false, true); else WCFE_FR(true, false, false); }
         else { if (c->reduce_warp) WCFE_FR(false, false, true); else WCFE_FR(false, false, false); }
 #undef WCFE_FR
-        c->launches += 1;
-    } else {
+    } else {       // (the one launch is counted below, where the separate finish kernel's is)
     {
     // fork: the finish kernel goes to the side stream first (so that its few blocks are placed as soon as the cell kernel drains)
     cudaStream_t fs = c->stream;
