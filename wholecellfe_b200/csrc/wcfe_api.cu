@@ -87,7 +87,7 @@ struct Surface {
     int stride = 0, off_halo = 0, off_lv = 0, off_rptr = 0, off_ring = 0;   // blob layout (wcfe_patch.cuh)
     DevBuf<unsigned char> p_blob, p_ring_blob;
     DevBuf<int> p_ring_cyc;
-    int ring_stride = 0, roff_halo = 0, roff_rptr = 0, roff_jk = 0, max_val = 0;
+    int ring_stride = 0, roff_halo = 0, roff_rptr = 0, roff_jk = 0, roff_row = 0, max_val = 0;
     DevBuf<int> p_elem_ptr, p_elem_gid;
     DevBuf<unsigned short> p_cand_l;
 };
@@ -405,6 +405,66 @@ int build_grid(wcfe_ctx *c, const double *xyz) {
     return WCFE_OK;
 }
 
+// Row numbering of a substrate patch's node table (k_subs_ring) against shared-memory bank conflicts.  The table is gathered: at
+// fan position e the lanes of a warp read the rows of THEIR e-th neighbours, 16 bytes per lane, a quarter-warp (8 lanes) per
+// wavefront when the eight rows fall into eight different 16-byte bank groups (row mod 8) -- with rows numbered as the nodes are,
+// the eight behave like random numbers and a gather costs 2.2 wavefronts instead of one (ncu: 11 of 29 M wavefronts per launch, on
+// the unit that bounds the kernel).  The access pattern is static, so the numbering is chosen for it: nodes in order of how often
+// they are read, each into the residue class (mod 8, of limited capacity) in which it meets the fewest rows it is ever read
+// together with; inside the class, the row whose residue mod 16 does the same for the 8-byte reads of a half-warp.
+// jk: (j, k) local ids per fan entry, rptr: CSR over the owned nodes; returns row_of[local id] (a permutation of [0, NL)).
+std::vector<unsigned short> ring_table_rows(const std::vector<unsigned short> &jk, const std::vector<unsigned short> &rptr, int P, int NL) {
+    std::vector<unsigned short> row_of((size_t)NL);
+    for (int l = 0; l < NL; l++) row_of[l] = (unsigned short)l;
+    int maxval = 0;
+    for (int l = 0; l < P; l++) maxval = std::max(maxval, (int)rptr[l + 1] - (int)rptr[l]);
+    if (!maxval) return row_of;
+    // groups of local ids one load instruction of one quarter-warp touches (J only where the walk really loads it)
+    std::vector<std::vector<int>> groups;
+    for (int e = 0; e < maxval; e++)
+        for (int q = 0; q < P / 8; q++)
+            for (int slot = 0; slot < 2; slot++) {
+                std::vector<int> g;
+                for (int t = 8 * q; t < 8 * q + 8; t++) {
+                    const int r0 = rptr[t], n = rptr[t + 1] - r0;
+                    if (e >= n) continue;
+                    if (slot == 0 && e > 0 && jk[2 * (size_t)(r0 + e)] == jk[2 * (size_t)(r0 + e - 1) + 1]) continue;     // J == previous K: kept in registers
+                    g.push_back(jk[2 * (size_t)(r0 + e) + slot]);
+                }
+                if (g.size() > 1) groups.push_back(std::move(g));
+            }
+    // the table fill: eight consecutive threads store their own rows, eight consecutive halo positions theirs
+    for (int q = 0; q < NL / 8; q++) { std::vector<int> g; for (int t = 8 * q; t < 8 * q + 8 && t < NL; t++) g.push_back(t); groups.push_back(std::move(g)); }
+    std::vector<int> freq((size_t)NL, 0);
+    std::vector<std::vector<int>> of_node((size_t)NL);
+    for (size_t gi = 0; gi < groups.size(); gi++) for (int v : groups[gi]) { freq[v]++; of_node[v].push_back((int)gi); }
+    std::vector<int> order;
+    for (int l = 0; l < NL; l++) if (freq[l]) order.push_back(l);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return freq[a] > freq[b]; });
+    std::vector<int> row((size_t)NL, -1);
+    std::vector<char> taken((size_t)NL, 0);
+    std::vector<int> left(8, 0);
+    for (int r = 0; r < NL; r++) left[r % 8]++;
+    for (int v : order) {
+        int cost8[8] = {0}, cost16[16] = {0};
+        for (int gi : of_node[v])
+            for (int u : groups[gi]) if (u != v && row[u] >= 0) { cost8[row[u] % 8]++; cost16[row[u] % 16]++; }
+        int best = -1;
+        for (int c = 0; c < 8; c++) if (left[c] && (best < 0 || cost8[c] < cost8[best] || (cost8[c] == cost8[best] && left[c] > left[best]))) best = c;
+        int pick = -1;
+        for (int r = best; r < NL; r += 8) if (!taken[r] && (pick < 0 || cost16[r % 16] < cost16[pick % 16])) pick = r;
+        row[v] = pick; taken[pick] = 1; left[best]--;
+    }
+    int next = 0;
+    for (int l = 0; l < NL; l++) {          // nodes nobody gathers (none on a closed mesh) take what is left
+        if (row[l] >= 0) continue;
+        while (taken[next]) next++;
+        row[l] = next; taken[next] = 1;
+    }
+    for (int l = 0; l < NL; l++) row_of[l] = (unsigned short)row[l];
+    return row_of;
+}
+
 // patch tables for the planar fused kernels: kPatch consecutive nodes per patch, every incident element listed once per
 // patch; each patch's tables are packed into one fixed-stride blob (layout: wcfe_patch.cuh) for a single TMA bulk copy
 int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
@@ -576,7 +636,8 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
     s.roff_halo = 16;
     s.roff_rptr = (int)(s.roff_halo + pad16(4 * (size_t)s.max_halo));
     s.roff_jk = (int)(s.roff_rptr + pad16((size_t)P));
-    s.ring_stride = (int)(s.roff_jk + pad16(4 * (size_t)max_val * P));
+    s.roff_row = (int)(s.roff_jk + pad16(4 * (size_t)max_val * P));
+    s.ring_stride = (int)(s.roff_row + pad16(2 * ((size_t)P + s.max_halo)));
     if (surface == WCFE_SUBS) {
         std::vector<unsigned char> rb((size_t)s.npatch * s.ring_stride, 0);
         for (int p = 0; p < s.npatch; p++) {
@@ -586,11 +647,13 @@ int build_patches(wcfe_ctx *c, int surface, const std::vector<int> &cand) {
             memcpy(b, hdr, 16);
             if (!t.halo.empty()) memcpy(b + s.roff_halo, t.halo.data(), 4 * t.halo.size());
             unsigned char *val = b + s.roff_rptr;
-            unsigned short *jkT = (unsigned short *)(b + s.roff_jk);
+            unsigned short *jkT = (unsigned short *)(b + s.roff_jk), *rowT = (unsigned short *)(b + s.roff_row);
+            const std::vector<unsigned short> row_of = ring_table_rows(t.jk, t.rptr, P, P + s.max_halo);
+            memcpy(rowT, row_of.data(), 2 * row_of.size());
             for (int l = 0; l < P; l++) {
                 const int r0 = t.rptr[l], r1 = t.rptr[l + 1];
                 val[l] = (unsigned char)(r1 - r0);
-                for (int r = r0; r < r1; r++) { jkT[2 * ((size_t)(r - r0) * P + l)] = t.jk[2 * r]; jkT[2 * ((size_t)(r - r0) * P + l) + 1] = t.jk[2 * r + 1]; }
+                for (int r = r0; r < r1; r++) { jkT[2 * ((size_t)(r - r0) * P + l)] = row_of[t.jk[2 * r]]; jkT[2 * ((size_t)(r - r0) * P + l) + 1] = row_of[t.jk[2 * r + 1]]; }
             }
         }
         CK(s.p_ring_blob.alloc(rb.size()));
@@ -614,7 +677,7 @@ PatchView pview(Surface &s) {
     PatchView v{};
     v.npatch = s.npatch; v.max_halo = s.max_halo; v.max_elem = s.max_elem;
     v.stride = s.stride; v.off_halo = s.off_halo; v.off_lv = s.off_lv; v.off_rptr = s.off_rptr; v.off_ring = s.off_ring;
-    v.ring_stride = s.ring_stride; v.roff_halo = s.roff_halo; v.roff_rptr = s.roff_rptr; v.roff_jk = s.roff_jk; v.ring_blob = s.p_ring_blob.p; v.ring_cyc = s.p_ring_cyc.p;
+    v.ring_stride = s.ring_stride; v.roff_halo = s.roff_halo; v.roff_rptr = s.roff_rptr; v.roff_jk = s.roff_jk; v.roff_row = s.roff_row; v.ring_blob = s.p_ring_blob.p; v.ring_cyc = s.p_ring_cyc.p;
     v.blob = s.p_blob.p; v.elem_ptr = s.p_elem_ptr.p; v.elem_gid = s.p_elem_gid.p; v.cand_l = s.p_cand_l.p;
     return v;
 }

@@ -55,7 +55,7 @@ struct PatchView {
     const int *elem_gid;             // global element id of every patch-local element (substrate: bucket lookup)
     const unsigned short *cand_l;    // parallel to BoundaryView::cand: local node ids (cell only)
     // node-centric substrate kernel (k_subs_ring): hdr | halo ids | ring_ptr | (j,k) local vertex pairs per ring entry
-    int ring_stride, roff_halo, roff_rptr, roff_jk;
+    int ring_stride, roff_halo, roff_rptr, roff_jk, roff_row;      // roff_row: table row of every local node (uint16; wcfe_api.cu ring_table_rows)
     const unsigned char *ring_blob;
     const int *ring_cyc;             // (element << 2 | slot) per ring entry in the blob's cyclic order (same offsets as SurfView::ring)
 };
@@ -187,7 +187,8 @@ __device__ __noinline__ void halo_wait(const unsigned long long *flags, const Ha
 }
 
 // ---- what one owned node does once its patch's node table is complete ----------------------------------------------------------
-// The table holds, per local node (owned first, halo after), (x, y), (e_xx, e_yy) and e_xy as stored in global memory.
+// The table holds, per local node, (x, y), (e_xx, e_yy) and e_xy as stored in global memory; a node's row is where the descriptor
+// says (row_of, chosen on the host against bank conflicts in the gathers below); (j, k) of a fan entry are rows.
 struct RingTable { const double2 *sxy, *se01; const double *se3; };
 
 template <bool DBG, bool HALO>
@@ -195,12 +196,12 @@ __device__ __forceinline__ void ring_node(const SurfView &s, const PatchView &pv
                                           double dt, double dt_real, double t_tot, double bx0, double bx1, double by0, double by1,
                                           const DebugView &dbg, const HaloView &hv, double dt_drv, const RingTable T,
                                           const unsigned char *valence, const ushort2 *rjk, int p, int tid, int i, int nrole, bool zero_list,
-                                          double V0, double V1, double A0v, double A1v) {
+                                          double V0, double V1, double A0v, double A1v, int myrow) {
     const int np = s.np;
     const double2 *sxy = T.sxy, *se01 = T.se01;
     const double *se3 = T.se3;
-    const double2 myxy = sxy[tid], mye01 = se01[tid];
-    const double ea0 = mye01.x, ea1 = mye01.y, ea3 = se3[tid];
+    const double2 myxy = sxy[myrow], mye01 = se01[myrow];
+    const double ea0 = mye01.x, ea1 = mye01.y, ea3 = se3[myrow];
     double rx = 0.0, ry = 0.0, q0 = 0.0, q1 = 0.0, q3 = 0.0, mm = 0.0;
     const int nring = valence[tid];
     // one incident element, with this node as local vertex 0 and (j, k) the other two in cyclic order.
@@ -398,27 +399,29 @@ __global__ void __launch_bounds__(kPatch, WCFE_RING_MINBLK) k_subs_ring(SurfView
     const int *halo_ids = (const int *)(sblob + pv.roff_halo);
     const unsigned char *valence = sblob + pv.roff_rptr;
     const ushort2 *rjk = (const ushort2 *)(sblob + pv.roff_jk);          // [step][node]: conflict-free across a warp
-    sxy[tid] = make_double2(stage[tid], stage[kPatch + tid]); se01[tid] = make_double2(stage[2 * kPatch + tid], stage[3 * kPatch + tid]); se3[tid] = stage[4 * kPatch + tid];
+    const unsigned short *row_of = (const unsigned short *)(sblob + pv.roff_row);
+    const int myrow = row_of[tid];
+    sxy[myrow] = make_double2(stage[tid], stage[kPatch + tid]); se01[myrow] = make_double2(stage[2 * kPatch + tid], stage[3 * kPatch + tid]); se3[myrow] = stage[4 * kPatch + tid];
     if (HALO && (prole & 1)) {
         // ghost rows were written by a peer GPU into L2 while this kernel was already running: read them past the (incoherent) L1
         for (int l = tid; l < nh; l += kPatch) {
-            const int g = halo_ids[l];
-            sxy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
-            se01[kPatch + l] = make_double2(__ldcg(s.ea_in + g), __ldcg(s.ea_in + np + g));
-            se3[kPatch + l] = __ldcg(s.ea_in + 3 * (size_t)np + g);
+            const int g = halo_ids[l], r = row_of[kPatch + l];
+            sxy[r] = make_double2(s.x[g], s.x[np + g]);
+            se01[r] = make_double2(__ldcg(s.ea_in + g), __ldcg(s.ea_in + np + g));
+            se3[r] = __ldcg(s.ea_in + 3 * (size_t)np + g);
         }
     } else {
         for (int l = tid; l < nh; l += kPatch) {
-            const int g = halo_ids[l];
-            sxy[kPatch + l] = make_double2(s.x[g], s.x[np + g]);
-            se01[kPatch + l] = make_double2(s.ea_in[g], s.ea_in[np + g]);
-            se3[kPatch + l] = s.ea_in[3 * (size_t)np + g];
+            const int g = halo_ids[l], r = row_of[kPatch + l];
+            sxy[r] = make_double2(s.x[g], s.x[np + g]);
+            se01[r] = make_double2(s.ea_in[g], s.ea_in[np + g]);
+            se3[r] = s.ea_in[3 * (size_t)np + g];
         }
     }
     __syncthreads();
     if (!own) return;
     ring_node<DBG, HALO>(s, pv, c, bk, k, dt, dt_real, t_tot, bx0, bx1, by0, by1, dbg, hv, dt_drv, RingTable{sxy, se01, se3}, valence, rjk, p, tid, i, nrole,
-                         blockIdx.x == 0 && tid == 0, V0, V1, A0v, A1v);
+                         blockIdx.x == 0 && tid == 0, V0, V1, A0v, A1v, myrow);
 }
 
 // ---- integrin force on the substrate, per triangle ---------------------------------------------------------------------------------
