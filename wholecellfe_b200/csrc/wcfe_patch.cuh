@@ -453,19 +453,33 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
             const int i0 = s.tri[e], i1 = s.tri[s.nep + e], i2 = s.tri[2 * s.nep + e];
             const double n1x = s.x[i0], n1y = s.x[s.np + i0], n2x = s.x[i1], n2y = s.x[s.np + i1], n3x = s.x[i2], n3y = s.x[s.np + i2];
             double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
-            int nlive = 0; bool dirty = false;
-            for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v < 0) dirty = true; else { nlive++; dirty |= (v & kItemVolatile) != 0; } }
-            int prev = -1;
-            for (int m = 0; m < nlive; m++) {        // ascending cell-node order: deterministic whatever the insertion order was
-                int ni = 0x7fffffff;
-                for (int q = 0; q < cnt; q++) { const int v = items[q]; const int id = v & kItemId; if (v >= 0 && id > prev && id < ni) ni = id; }
-                prev = ni;
+            int nlive = 0, last = -1; bool dirty = false, sorted = true;
+            for (int q = 0; q < cnt; q++) {
+                const int v = items[q];
+                if (v < 0) { dirty = true; continue; }
+                nlive++; dirty |= (v & kItemVolatile) != 0;
+                sorted &= (v & kItemId) > last; last = v & kItemId;
+            }
+            auto add_anchor = [&](int ni) {
                 const double2 ap = anc2[2 * (size_t)ni], ah = anc2[2 * (size_t)ni + 1];
                 double Ar[3], At;                                                        // UL:1303-1340; planar form, bit-identical
                 point_in_triangle_2d(n1x, n1y, n2x, n2y, n3x, n3y, ap.x, ap.y, Ar, At);
                 const Recip rt = recip_of(At);
                 const double w0 = quot(Ar[0], rt), w1 = quot(Ar[1], rt), w2 = quot(Ar[2], rt);
                 a0 += ah.x * w0; a1 += ah.y * w0; a2 += ah.x * w1; a3 += ah.y * w1; a4 += ah.x * w2; a5 += ah.y * w2;   // UL:1414-1422
+            };
+            // ascending cell-node order: deterministic whatever the insertion order was.  A persistent bucket is left in that order
+            // (below), so from the second step on the entries are simply walked; otherwise the next larger id is searched each time.
+            if (sorted) {
+                for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v >= 0) add_anchor(v & kItemId); }
+            } else {
+                int prev = -1;
+                for (int m = 0; m < nlive; m++) {
+                    int ni = 0x7fffffff;
+                    for (int q = 0; q < cnt; q++) { const int v = items[q]; const int id = v & kItemId; if (v >= 0 && id > prev && id < ni) ni = id; }
+                    prev = ni;
+                    add_anchor(ni);
+                }
             }
             // the triangle's three nodes have something to gather in this step
             bk.node_epoch[i0] = bk.epoch; bk.node_epoch[i1] = bk.epoch; bk.node_epoch[i2] = bk.epoch;
@@ -474,6 +488,8 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
                 o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3); o[2] = make_double2(a4, a5);
                 int w = cnt;
                 if (dirty) { w = 0; for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v >= 0 && !(v & kItemVolatile)) items[w++] = v; } }   // this thread alone owns the bucket now
+                if (!sorted)          // (membership changed, or the first step: once; insertion sort of a handful of ids)
+                    for (int a = 1; a < w; a++) { const int key = items[a]; int q = a - 1; while (q >= 0 && items[q] > key) { items[q + 1] = items[q]; q--; } items[q + 1] = key; }
                 bk.head[e] = ((unsigned long long)bk.epoch << 32) | kHeadListed | (unsigned int)w;
             } else {
                 double2 *o = reinterpret_cast<double2 *>(items);      // this thread alone reads and writes the bucket; its count starts the next step at zero
@@ -493,17 +509,23 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
         int *items = bk.items + (size_t)e * bk.cap;
         const int i0 = s.tri[e], i1 = s.tri[s.nep + e], i2 = s.tri[2 * s.nep + e];
         const double n1[3] = {s.x[i0], s.x[s.np + i0], 0.0}, n2[3] = {s.x[i1], s.x[s.np + i1], 0.0}, n3[3] = {s.x[i2], s.x[s.np + i2], 0.0};
-        int nlive = 0, dirty = 0;
-        for (int m = lane; m < cnt; m += 32) { const int v = items[m]; if (v < 0) dirty = 1; else { nlive++; dirty |= (v & kItemVolatile) != 0; } }
+        int nlive = 0, dirty = 0, ordered = 1;
+        for (int m = lane; m < cnt; m += 32) {
+            const int v = items[m];
+            if (v < 0) { dirty = 1; continue; }
+            nlive++; dirty |= (v & kItemVolatile) != 0;
+            if (m) { const int u = items[m - 1]; ordered &= (u >= 0 && (u & kItemId) < (v & kItemId)); }
+        }
         nlive = __reduce_add_sync(0xffffffffu, nlive); dirty = __any_sync(0xffffffffu, dirty);
+        const bool sorted = !dirty && __all_sync(0xffffffffu, ordered);      // a persistent bucket is left in ascending order (below): rank == position
         double acc = 0.0;                                   // lanes 0..5: (vertex, component) = (lane >> 1, lane & 1)
         for (int w0 = 0; w0 < nlive; w0 += kReduceWindow) {   // one window unless a bucket holds more than 128 anchors
             for (int m = lane; m < cnt; m += 32) {
                 const int vv = items[m];
                 if (vv < 0) continue;
                 const int v = vv & kItemId;
-                int rank = 0;
-                for (int q = 0; q < cnt; q++) { const int u = items[q]; rank += (u >= 0 && (u & kItemId) < v); }      // node ids inside a bucket are distinct
+                int rank = m;
+                if (!sorted) { rank = 0; for (int q = 0; q < cnt; q++) { const int u = items[q]; rank += (u >= 0 && (u & kItemId) < v); } }      // node ids inside a bucket are distinct
                 if (rank < w0 || rank >= w0 + kReduceWindow) continue;
                 const double2 ap = anc2[2 * (size_t)v], ah = anc2[2 * (size_t)v + 1];
                 double Ar[3], At;
@@ -523,10 +545,33 @@ __device__ __forceinline__ void bucket_reduce_body(int bid, int nblk, double (*t
         }
         if (bk.persist) {
             if (lane < 6) bk.sums[(size_t)6 * e + lane] = acc;
+            int w = cnt;
+            if (!sorted) {
+                // membership changed (or the first step): leave the survivors in ascending order -- every lane ranks its entries
+                // among them, the order is staged in this warp's shared scratch (all lanes are past its last use) and copied back
+                int npers = 0;
+                for (int m = lane; m < cnt; m += 32) { const int v = items[m]; npers += (v >= 0 && !(v & kItemVolatile)); }
+                npers = __reduce_add_sync(0xffffffffu, npers);
+                int *stg = reinterpret_cast<int *>(&tw[0][0]);
+                if (npers <= kReduceWindow * 6 * 2) {
+                    for (int m = lane; m < cnt; m += 32) {
+                        const int v = items[m];
+                        if (v < 0 || (v & kItemVolatile)) continue;
+                        int rank = 0;
+                        for (int q = 0; q < cnt; q++) { const int u = items[q]; rank += (u >= 0 && !(u & kItemVolatile) && u < v); }
+                        stg[rank] = v;
+                    }
+                    __syncwarp();
+                    for (int m = lane; m < npers; m += 32) items[m] = stg[m];
+                    __syncwarp();
+                    w = npers;
+                } else if (dirty) {      // (a bucket too large for the scratch: compacted by one lane, order left as it is)
+                    if (lane == 6) { w = 0; for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v >= 0 && !(v & kItemVolatile)) items[w++] = v; } }
+                    w = __shfl_sync(0xffffffffu, w, 6);
+                }
+            }
             if (lane == 6) {
                 bk.node_epoch[i0] = bk.epoch; bk.node_epoch[i1] = bk.epoch; bk.node_epoch[i2] = bk.epoch;
-                int w = cnt;
-                if (dirty) { w = 0; for (int q = 0; q < cnt; q++) { const int v = items[q]; if (v >= 0 && !(v & kItemVolatile)) items[w++] = v; } }   // every lane has finished reading the items (syncwarp above)
                 bk.head[e] = ((unsigned long long)bk.epoch << 32) | kHeadListed | (unsigned int)w;
             }
         } else {
