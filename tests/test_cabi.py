@@ -70,3 +70,18 @@ def test_product_does_not_import_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 for needle in ("ul_oracle.h", "libuloracle", "from oracle", "import oracle"):
                     assert needle not in txt, (f, needle)
+
+
+def test_environment_switches_are_documented():
+    """every WCFE_* variable the library, the adapter or the Python loader reads appears in INTEGRATION.md's table, and vice versa"""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    read = set()
+    for f in glob.glob(os.path.join(root, "wholecellfe_b200", "csrc", "*.cu")) + glob.glob(os.path.join(root, "wholecellfe_b200", "csrc", "*.cpp")):
+        read |= set(re.findall(r'getenv\("(WCFE_[A-Z0-9_]+)"', open(f).read()))
+    read |= set(re.findall(r'environ\.get\("(WCFE_[A-Z0-9_]+)"', open(os.path.join(root, "wholecellfe_b200", "_lib.py")).read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    table = doc[doc.index("Environment switches"):]
+    documented = set(re.findall(r"`(WCFE_[A-Z0-9_]+)", table))
+    assert read == documented, (sorted(read - documented), sorted(documented - read))
