@@ -48,3 +48,14 @@ extern "C" void hm_elem_eval_frozen(const double *X6, const double *e3, double m
     ElemOutFrozen o; elem_eval_frozen(X, e3, mu, thick, o);
     memcpy(r1, o.r1, 16); memcpy(r2, o.r2, 16); *A0 = o.A0;
 }
+
+// ---- host logic of the patch builder: row numbering of a substrate patch's node table (csrc/wcfe_rows.h)
+#include "../../wholecellfe_b200/csrc/wcfe_rows.h"
+extern "C" long long hm_ring_table_rows(const unsigned short *jk, int njk, const unsigned short *rptr, int P, int NL, unsigned short *row_of, long long *wavefronts_identity) {
+    std::vector<unsigned short> vjk(jk, jk + njk), vr(rptr, rptr + P + 1), id((size_t)NL);
+    for (int l = 0; l < NL; l++) id[l] = (unsigned short)l;
+    const std::vector<unsigned short> r = wcfe::ring_table_rows(vjk, vr, P, NL);
+    for (int l = 0; l < NL; l++) row_of[l] = r[l];
+    *wavefronts_identity = wcfe::ring_table_wavefronts(vjk, vr, P, NL, id);
+    return wcfe::ring_table_wavefronts(vjk, vr, P, NL, r);
+}

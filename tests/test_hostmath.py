@@ -169,3 +169,43 @@ def test_planar_element_matches_reference_vectors(hm, elements):
         worst = max(worst, np.abs(ref[:, [0, 1, 3]] - mine[:, [0, 1, 3]]).max() / (np.abs(eas).max() * A0.value))
         assert abs(e["MMe"][i][0] - A0.value / 3) <= 1e-14 * A0.value
     assert n >= 40 and worst < 1e-11, (n, worst)
+
+
+def test_node_table_rows_are_a_permutation_with_fewer_bank_conflicts(hm):
+    """Host logic of build_patches (csrc/wcfe_rows.h): the row numbering of a substrate patch's node table must be a permutation
+    of [0, NL) whatever the fans look like, and on the bench's own pattern -- a 16 x 8 block of a union-jack grid in Morton order,
+    valences 4 and 8, one ring of halo nodes -- it must cost fewer shared-memory wavefronts than numbering the rows like the nodes."""
+    def morton(x, y):
+        m = 0
+        for b in range(8):
+            m |= ((x >> b) & 1) << (2 * b) | ((y >> b) & 1) << (2 * b + 1)
+        return m
+    W_, H_ = 16, 8
+    own = sorted(((x, y) for x in range(1, W_ + 1) for y in range(1, H_ + 1)), key=lambda p: morton(p[0] - 1, p[1] - 1))
+    P = 128
+    assert len(own) == P
+    local = {p: i for i, p in enumerate(own)}
+    halo = sorted({(x + dx, y + dy) for (x, y) in own for dx in (-1, 0, 1) for dy in (-1, 0, 1)} - set(own))
+    for i, p in enumerate(halo):
+        local[p] = P + i
+    NL = P + (len(halo) + 3) // 4 * 4
+    ring8 = [(-1, -1), (0, -1), (1, -1), (1, 0), (1, 1), (0, 1), (-1, 1), (-1, 0)]
+    ring4 = [(0, -1), (1, 0), (0, 1), (-1, 0)]
+    jk, rptr = [], [0]
+    for (x, y) in own:
+        ring = ring8 if (x + y) % 2 == 0 else ring4
+        for q in range(len(ring)):
+            a, b = ring[q], ring[(q + 1) % len(ring)]
+            jk += [local[(x + a[0], y + a[1])], local[(x + b[0], y + b[1])]]
+        rptr.append(len(jk) // 2)
+    jk = np.asarray(jk, dtype=np.uint16); rptr = np.asarray(rptr, dtype=np.uint16)
+    row_of = np.zeros(NL, dtype=np.uint16); ident = C.c_longlong()
+    u16 = C.POINTER(C.c_ushort)
+    hm.hm_ring_table_rows.restype = C.c_longlong
+    got = hm.hm_ring_table_rows(jk.ctypes.data_as(u16), len(jk), rptr.ctypes.data_as(u16), P, NL, row_of.ctypes.data_as(u16), C.byref(ident))
+    assert sorted(row_of.tolist()) == list(range(NL))
+    assert got < ident.value, (got, ident.value)      # 236 against 263 here; on the GPU 27.2 M against 29.0 M wavefronts per launch (profiles/)
+    # degenerate input: no fans at all -> identity
+    z = np.zeros(P + 1, dtype=np.uint16); e = np.zeros(2, dtype=np.uint16)
+    hm.hm_ring_table_rows(e.ctypes.data_as(u16), 0, z.ctypes.data_as(u16), P, NL, row_of.ctypes.data_as(u16), C.byref(ident))
+    assert row_of.tolist() == list(range(NL))
