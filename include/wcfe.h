@@ -158,6 +158,20 @@ int wcfe_update_subs(wcfe_ctx *c, double dt_req, double dt_real, double t_curr);
 /* driverVelocities_Explicit (surface == WCFE_CELL, UL:103-124) / driverVelocities_Biaxial (WCFE_SUBS, UL:275-345) as a pure
  * function of host-owned arrays (AoS [3*nn]): V_hlf = V + dt/2 A, z = 0, substrate edge pins.  Computed on the device. */
 int wcfe_driver_velocities(wcfe_ctx *c, int surface, int nn, const double *X, const double *V, const double *A, double dt, double t_curr, double *Vh_out);
+/* Every driverVelocities_* of UL:103-345 by kind (main.cpp:69-76 declares them, :217-224 / :291-295 call the first two and keep the others
+ * commented out): V_hlf = V + dt/2 A with the driver's boundary conditions, computed on the device as a pure function of host-owned AoS
+ * arrays.  wcfe_driver_velocities(c, surface, ...) is kind == surface.  `surface` says whose V_hlf this is for the update that follows:
+ *  - WCFE_SUBS with any kind: the substrate's nodal update V = V_hlf + (dt_real - dt/2) A (UL:499, the only reader of V_hlf in that
+ *    overload) uses this driver's V_hlf (one context, one GPU, frozen substrate; WCFE_ERR_UNSUPPORTED otherwise);
+ *  - WCFE_CELL with a kind other than EXPLICIT: the function value is returned, but the cell's update refuses (WCFE_ERR_UNSUPPORTED):
+ *    its drag force reads V_hlf (UL:571-573) and the kernels form it as driverVelocities_Explicit does.
+ * The choice lasts for one update, as one driver call per step does in main.cpp. */
+#define WCFE_DRV_EXPLICIT 0     /* UL:103-124 */
+#define WCFE_DRV_BIAXIAL 1      /* UL:275-345 */
+#define WCFE_DRV_UNIAXIAL 2     /* UL:125-168 */
+#define WCFE_DRV_OFFBIAXIAL 3   /* UL:214-273 */
+#define WCFE_DRV_BULGETEST 4    /* UL:170-212 (keeps the normal component) */
+int wcfe_driver_velocities_kind(wcfe_ctx *c, int surface, int kind, int nn, const double *X, const double *V, const double *A, double dt, double t_curr, double *Vh_out);
 /* adapter mode: x (WCFE_F_X) and X_prev (WCFE_F_XPREV) were uploaded by the host integrator instead of predict/commit */
 int wcfe_mark_positions_committed(wcfe_ctx *c);
 

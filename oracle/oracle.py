@@ -64,6 +64,7 @@ def lib():
         L.ulo_default_params.argtypes = [C.POINTER(Params), C.c_int]
         L.ulo_srand.argtypes = [C.c_void_p, C.c_uint]
         L.ulo_rand.argtypes = [C.c_void_p]; L.ulo_rand.restype = C.c_int
+        L.ulo_driver_kind.argtypes = [C.POINTER(Params), C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
         L.ulo_mesh_build.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip]
         _lib = L
     return _lib
@@ -79,6 +80,19 @@ def glibc_rand_stream(seed, n):
     buf = C.create_string_buffer(4 * 31 + 8)
     L.ulo_srand(buf, seed)
     return np.array([L.ulo_rand(buf) for _ in range(n)], dtype=np.int64)
+
+
+DRIVERS = {"explicit": 0, "biaxial": 1, "uniaxial": 2, "offbiaxial": 3, "bulgetest": 4}
+
+
+def driver(variant, kind, X, V, A, dt, t_tot):
+    """The restatement of driverVelocities_<kind> (UL:103-345) on flat AoS arrays."""
+    L = lib()
+    p = Params(); L.ulo_default_params(C.byref(p), VARIANTS[variant])
+    X = np.ascontiguousarray(X, dtype=np.float64); V = np.ascontiguousarray(V, dtype=np.float64); A = np.ascontiguousarray(A, dtype=np.float64)
+    out = np.empty_like(X)
+    assert L.ulo_driver_kind(C.byref(p), DRIVERS[kind] if isinstance(kind, str) else kind, len(X), _d(X), _d(V), _d(A), dt, t_tot, _d(out)) == 0
+    return out
 
 
 class OracleSim:

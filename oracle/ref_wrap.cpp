@@ -32,6 +32,9 @@
 // ---- prototypes of the reference's free functions (cellBP/main.cpp:69-87; UL_growth_explicit.cpp:20-35)
 void driverVelocities_Explicit(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt);
 void driverVelocities_Biaxial(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot);
+void driverVelocities_Uniaxial(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot);
+void driverVelocities_OffBiaxial(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot);
+void driverVelocities_BulgeTest(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot);
 void updateFA(std::vector<double> &c_A, std::vector<double> &c_C, std::vector<Vec3d> &fa_u, double dt_real, const std::vector<Vec3d> &X_t_cell, const std::vector<Vec3d> &x_t_cell, const NonDestructiveTriMesh &mesh_cell, const std::vector<Vec3d> &X_t_subs, const std::vector<Vec3d> &x_t_subs, const NonDestructiveTriMesh &mesh_subs, double kint);
 void updateForces_Explicit(const std::vector<Vec3d> &X_t, const std::vector<Vec3d> &x_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, std::vector<Eigen::VectorXd> &ea_t,
                            std::vector<double> &c_A, std::vector<double> &c_B, std::vector<double> &c_C, std::vector<Vec3d> &fa_u, double dt, double dt_real, const NonDestructiveTriMesh &mesh, double t_tot);
@@ -186,6 +189,33 @@ void ulref_step(ulref *h, double dt, double t_curr, double kint, double subs_sca
     updateForces_Explicit(h->Xs_prev, s.x, s.V, h->Vh_s, s.A, s.ea, dt, dt, s.mesh, t_curr, c.fa_u, c.cC, c.x, c.mesh);   // :361
 }
 
+// The step of ulref_step (subs_scale 0) with the SUBSTRATE's driver swapped for one of the alternatives main.cpp keeps commented out
+// at that call site (main.cpp:291-295): kind 1 Biaxial (== ulref_step), 2 Uniaxial, 3 OffBiaxial, 4 BulgeTest.
+static void substrate_driver(int kind, Surface &s, std::vector<Vec3d> &Vh, double dt, double t_curr) {
+    switch (kind) {
+    case 2: driverVelocities_Uniaxial(s.x, s.V, Vh, s.A, dt, t_curr); break;
+    case 3: driverVelocities_OffBiaxial(s.x, s.V, Vh, s.A, dt, t_curr); break;
+    case 4: driverVelocities_BulgeTest(s.x, s.V, Vh, s.A, dt, t_curr); break;
+    default: driverVelocities_Biaxial(s.x, s.V, Vh, s.A, dt, t_curr); break;
+    }
+}
+void ulref_step_driver(ulref *h, double dt, double t_curr, double kint, int subs_kind) {
+    Quiet q;
+    Surface &c = h->cell, &s = h->subs;
+    const int nc = (int)c.x.size(), ns = (int)s.x.size();
+    h->Vh_c.assign(nc, Vec3d(0, 0, 0)); h->Vh_s.assign(ns, Vec3d(0, 0, 0));
+    driverVelocities_Explicit(c.x, c.V, h->Vh_c, c.A, dt);                       // main.cpp:224
+    std::vector<Vec3d> newp(nc);
+    for (int i = 0; i < nc; i++) newp[i] = c.x[i] + dt * h->Vh_c[i];           // main.cpp:227-231
+    h->Xc_prev = c.x;
+    c.x = newp;
+    substrate_driver(subs_kind, s, h->Vh_s, dt, t_curr);                         // main.cpp:291-295
+    h->Xs_prev = s.x;                                                            // main.cpp:299: x + 0*dt*V_hlf
+    updateFA(c.cA, c.cC, c.fa_u, dt, h->Xc_prev, c.x, c.mesh, h->Xs_prev, s.x, s.mesh, kint);   // main.cpp:354
+    updateForces_Explicit(h->Xc_prev, c.x, c.V, h->Vh_c, c.A, c.ea, c.cA, c.cB, c.cC, c.fa_u, dt, dt, c.mesh, t_curr);   // :360
+    updateForces_Explicit(h->Xs_prev, s.x, s.V, h->Vh_s, s.A, s.ea, dt, dt, s.mesh, t_curr, c.fa_u, c.cC, c.x, c.mesh);   // :361
+}
+
 // The same step when the host integrator accepts LESS than the requested dt (El Topo's integrate() with collision_safety on,
 // dynamicsurface.cpp:462-637, returns actual_dt <= dt and leaves the vertices part of the way): main.cpp:244-335 literally, with
 // integrate() modelled as "move the fraction frac of the way, actual_dt = frac * dt".  frac_subs < 1 also takes the redo branch
@@ -223,6 +253,25 @@ void ulref_step_short(ulref *h, double dt, double t_curr, double kint, double fr
     updateFA(c.cA, c.cC, c.fa_u, actual_dt, h->Xc_prev, c.x, c.mesh, h->Xs_prev, s.x, s.mesh, kint);   // main.cpp:354
     updateForces_Explicit(h->Xc_prev, c.x, c.V, h->Vh_c, c.A, c.ea, c.cA, c.cB, c.cC, c.fa_u, ori_dt, actual_dt, c.mesh, t_curr);   // :360
     updateForces_Explicit(h->Xs_prev, s.x, s.V, h->Vh_s, s.A, s.ea, ori_dt, actual_dt, s.mesh, t_curr, c.fa_u, c.cC, c.x, c.mesh);   // :361
+}
+
+// every driverVelocities_* the reference defines (UL:103-345; main.cpp:69-76 declares all five, :217-224 / :291-295 call two),
+// as pure functions of flat AoS arrays.  kind: 0 Explicit, 1 Biaxial, 2 Uniaxial, 3 OffBiaxial, 4 BulgeTest.  In the adapter build the
+// five symbols resolve to ul_adapter.cpp (the device).
+int ulref_driver(int kind, int nn, const double *X, const double *V, const double *A, double dt, double t_tot, double *Vh) {
+    Quiet q;
+    std::vector<Vec3d> x(nn), v(nn), a(nn), vh(nn, Vec3d(0, 0, 0));
+    get3(x, X); get3(v, V); get3(a, A);
+    switch (kind) {
+    case 0: driverVelocities_Explicit(x, v, vh, a, dt); break;
+    case 1: driverVelocities_Biaxial(x, v, vh, a, dt, t_tot); break;
+    case 2: driverVelocities_Uniaxial(x, v, vh, a, dt, t_tot); break;
+    case 3: driverVelocities_OffBiaxial(x, v, vh, a, dt, t_tot); break;
+    case 4: driverVelocities_BulgeTest(x, v, vh, a, dt, t_tot); break;
+    default: return -1;
+    }
+    put3(vh, Vh);
+    return 0;
 }
 
 #ifndef ULREF_ADAPTER_ONLY

@@ -37,6 +37,8 @@ def _load(variant, kind="ref"):
         lib.ulref_boundary_flags.argtypes = [C.c_void_p, C.c_int, _ip]
         lib.ulref_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
         lib.ulref_step_short.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+        lib.ulref_step_driver.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int]
+        lib.ulref_driver.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
         return lib
     lib.ulref_create.restype = C.c_void_p
     lib.ulref_create.argtypes = [C.c_int, _dp, C.c_int, _ip, C.c_int, _dp, C.c_int, _ip]
@@ -50,6 +52,8 @@ def _load(variant, kind="ref"):
     lib.ulref_boundary_flags.argtypes = [C.c_void_p, C.c_int, _ip]
     lib.ulref_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.ulref_step_short.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.ulref_step_driver.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int]
+    lib.ulref_driver.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
     lib.ulref_eval_element.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, C.c_double, _dp, _dp, _dp]
     lib.ulref_force_field.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp, _dp]
     lib.ulref_write_vtk_cell.argtypes = [C.c_void_p, C.c_double, C.c_char_p]
@@ -59,6 +63,19 @@ def _load(variant, kind="ref"):
 
 def _d(a):
     return a.ctypes.data_as(_dp)
+
+
+DRIVERS = {"explicit": 0, "biaxial": 1, "uniaxial": 2, "offbiaxial": 3, "bulgetest": 4}
+
+
+def driver(variant, kind, X, V, A, dt, t_tot, lib_kind="ref"):
+    """driverVelocities_<kind> of the reference (UL:103-345) on flat arrays; lib_kind "adapter": the drop-in's symbols (GPU)."""
+    lib = _load(variant, lib_kind)
+    X = np.ascontiguousarray(X, dtype=np.float64); V = np.ascontiguousarray(V, dtype=np.float64); A = np.ascontiguousarray(A, dtype=np.float64)
+    out = np.empty_like(X)
+    rc = lib.ulref_driver(DRIVERS[kind] if isinstance(kind, str) else kind, len(X), _d(X), _d(V), _d(A), dt, t_tot, _d(out))
+    assert rc == 0
+    return out
 
 
 class RefSim:
@@ -98,6 +115,10 @@ class RefSim:
     def step_short(self, dt, t_curr, frac_cell, frac_subs=1.0):
         """one step in which the host integrator accepts only a fraction of the requested dt (main.cpp:244-335)"""
         self.lib.ulref_step_short(self.h, dt, t_curr, self.kint, frac_cell, frac_subs)
+
+    def step_driver(self, dt, t_curr, subs_kind):
+        """one step with the substrate's driver swapped for an alternative of main.cpp:291-295 (2 Uniaxial, 3 OffBiaxial, 4 BulgeTest)"""
+        self.lib.ulref_step_driver(self.h, dt, t_curr, self.kint, subs_kind)
 
     def write_vtk(self, surface, time, path, fa_source=0):
         """the reference's own writer (cellBP/iomesh.cpp)"""

@@ -625,6 +625,38 @@ void ulo_driver_biaxial(const ulo_params *p, int nn, const double *X, const doub
     }
 }
 
+/* The drivers the reference defines and main.cpp leaves commented out (main.cpp:217-220, :291-295); identical in the three variants.
+ * kind: 2 driverVelocities_Uniaxial UL:125-168, 3 driverVelocities_OffBiaxial UL:214-273, 4 driverVelocities_BulgeTest UL:170-212;
+ * 0 / 1 dispatch to the two drivers main.cpp calls.  Thresholds are the reference's literals. */
+int ulo_driver_kind(const ulo_params *p, int kind, int nn, const double *X, const double *V, const double *A, double dt, double t_tot, double *Vh) {
+    int ni, k;
+    if (kind == 0) { ulo_driver_explicit(nn, V, A, dt, Vh); return 0; }
+    if (kind == 1) { ulo_driver_biaxial(p, nn, X, V, A, dt, t_tot, Vh); return 0; }
+    if (kind < 0 || kind > 4) return -1;
+    for (ni = 0; ni < nn; ni++) {
+        const double *Xi = X + 3 * ni;
+        double *v = Vh + 3 * ni;
+        for (k = 0; k < 3; k++) v[k] = V[3 * ni + k] + (dt / 2.0) * A[3 * ni + k];
+        if (kind == 2) {                                                        /* UL:141-164 */
+            v[2] = 0.0;
+            if (Xi[0] < -0.0499) { v[0] = 0.0; v[1] = 0.0; v[2] = 0.0; }
+            if (Xi[0] > 0.9499 + 0.1 * t_tot && t_tot <= 2.0) { v[0] = 0.1; v[1] = 0.0; v[2] = 0.0; }
+            if (Xi[0] > 0.9499 + 2.00 * 0.1 && t_tot >= 2.0) { v[0] = 0.0; v[1] = 0.0; v[2] = 0.0; }
+        } else if (kind == 3) {                                                 /* UL:230-269 */
+            v[2] = 0.0;
+            if (Xi[0] < -0.04) { v[0] = 0.0; v[1] = 0.0; v[2] = 0.0; }
+            if (Xi[0] > 0.94 + 0.1 * t_tot && t_tot < 1.0) { v[0] = 0.1; v[1] = 0.0; v[2] = 0.0; }
+            if (Xi[0] > 0.94 + 0.99 * 0.1 && t_tot >= 1.0) { v[0] = 0.0; v[1] = 0.0; v[2] = 0.0; }
+            if (Xi[1] > 0.99) { v[1] = 0.0; v[2] = 0.0; }
+            if (Xi[1] < 0.01) { v[1] = 0.0; v[2] = 0.0; }
+        } else {                                                                /* UL:184-209: the normal component is kept */
+            const int mid = Xi[2] < 0.001 && Xi[2] > -0.001;
+            if ((Xi[0] < 0.001 && mid) || (Xi[0] > 0.999 && mid) || (Xi[1] < 0.001 && mid) || (Xi[1] > 0.999 && mid)) { v[0] = 0.0; v[1] = 0.0; v[2] = 0.0; }
+        }
+    }
+    return 0;
+}
+
 /* nodal update shared by both updateForces_Explicit overloads: UL:601-628 / UL:478-503 */
 static void nodal_update(const ulo_params *p, int nn, const double *f, const double *MM, const double *Res_ea,
                          double *A, double *V, const double *Vh, double *ea, double dt, double dt_real) {

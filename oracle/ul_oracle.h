@@ -98,6 +98,8 @@ void ulo_force_area(const ulo_params *p, const ulo_mesh *m, const double *x, dou
 void ulo_update_FA(ulo_sim *s, double dt);
 void ulo_driver_explicit(int nn, const double *V, const double *A, double dt, double *Vh);
 void ulo_driver_biaxial(const ulo_params *p, int nn, const double *X, const double *V, const double *A, double dt, double t, double *Vh);
+/* every driverVelocities_* of UL:103-345 by kind: 0 Explicit, 1 Biaxial, 2 Uniaxial, 3 OffBiaxial, 4 BulgeTest; -1 on an unknown kind */
+int  ulo_driver_kind(const ulo_params *p, int kind, int nn, const double *X, const double *V, const double *A, double dt, double t, double *Vh);
 /* force field by id on the current state, same ids as ulref_force_field */
 int  ulo_force_field(ulo_sim *s, int which, double dt, double t_curr, double *out, double *mm, double *res_ea, double *aux4);
 /* the same fields as they were inside the last ulo_step() */

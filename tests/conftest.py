@@ -34,3 +34,15 @@ def rel_err(a, b, scale=None):
     a = np.asarray(a); b = np.asarray(b)
     s = max(np.abs(b).max(), 1e-300) if scale is None else scale
     return float(np.abs(a - b).max() / s)
+
+
+@pytest.fixture(scope="session")
+def drivers():
+    """tests/golden/drivers.npz (make_golden_drivers.py): inputs and, per driver and time, the reference's V_hlf as codes"""
+    d = np.load(os.path.join(GOLDEN, "drivers.npz"))
+    free = d["V"] + (float(d["dt"]) / 2.0) * d["A"]
+
+    def expect(name, it):
+        code = d["code_" + name][it]
+        return np.where(code == 0, free, np.where(code == 1, 0.0, 0.1))
+    return d, expect

@@ -73,3 +73,106 @@ def test_adapter_when_the_host_integrator_shortens_the_step(meshes, frac_cell, f
         for f in ["V", "A", "ea"]:
             ref = r.get(1, f)
             assert rel_err(a.get(1, f), ref, max(np.abs(ref).max(), SUBS_FLOOR[f])) < 1e-9, (k, f)
+
+
+DRIVER_NAMES = ["explicit", "biaxial", "uniaxial", "offbiaxial", "bulgetest"]
+
+
+@pytest.mark.parametrize("name", DRIVER_NAMES)
+def test_every_driver_on_the_device_against_reference_vectors(drivers, name):
+    """k_driver through wcfe_driver_velocities_kind, and through the adapter's own driverVelocities_* symbols, against the reference's
+    five drivers (UL:103-345; three of them commented out in main.cpp) on nodes on / one ulp off every threshold: bit for bit."""
+    import wholecellfe_b200 as W
+    from oracle.refrun import driver as rdriver
+    d, expect = drivers
+    g = W.ULSim("k1", device=0)
+    n0 = g.kernel_launches()
+    for it, t in enumerate(d["times"]):
+        for surface in (W.CELL, W.SUBS):
+            got = g.driver_velocities(surface, d["X"], d["V"], d["A"], float(d["dt"]), float(t), kind=name)
+            assert np.array_equal(got, expect(name, it)), (name, t, surface)
+        via_adapter = rdriver("k1", name, d["X"], d["V"], d["A"], float(d["dt"]), float(t), lib_kind="adapter")
+        assert np.array_equal(via_adapter, expect(name, it)), (name, t, "adapter")
+    assert g.kernel_launches() - n0 == 2 * len(d["times"])
+    with pytest.raises(W.WcfeError):
+        g.driver_velocities(W.SUBS, d["X"], d["V"], d["A"], 0.005, 0.0, kind=7)
+    g.close()
+
+
+@pytest.mark.parametrize("name,kind", [("uniaxial", 2), ("offbiaxial", 3), ("bulgetest", 4)])
+def test_substrate_step_with_a_dormant_driver_through_the_adapter(meshes, name, kind):
+    """A maintainer who swaps the substrate's driver at main.cpp:291-295 for one of the commented-out alternatives: the same call
+    sequence against the reference's own UL_growth_explicit.o and against the adapter + libwcfe.so, k1, 8 steps.  The substrate's
+    V = V_hlf + (dt_real - dt/2) A (UL:499) must come out with THAT driver's V_hlf (imposed 0.1 / pins), not _Biaxial's."""
+    from oracle.refrun import ref_available
+    if not ref_available("k1"):
+        pytest.skip("oracle/_ref/libulref_k1.so not built here")
+    xc, tc, xs, ts = meshes
+    a = RefSim("k1", xc, tc, xs, ts, kind="adapter"); a.srand(1)
+    r = RefSim("k1", xc, tc, xs, ts, kind="ref"); r.srand(1)
+    rng = np.random.default_rng(4)
+    v0 = 1e-2 * rng.normal(size=(len(xs), 3)); v0[:, 2] = 0.0        # a substrate at rest would hide the pins
+    for s in (a, r):
+        s.set(1, "V", v0)
+    t = 0.0
+    for k in range(8):
+        a.step_driver(0.005, t, kind); r.step_driver(0.005, t, kind); t += 0.005
+        for f in ["x", "V", "A", "ea", "cC", "fa_u"]:
+            ref = r.get(0, f)
+            assert rel_err(a.get(0, f), ref, max(np.abs(ref).max(), FLOOR[f])) < 1e-10, (name, k, f)
+        for f in ["V", "A", "ea"]:
+            ref = r.get(1, f)
+            assert rel_err(a.get(1, f), ref, max(np.abs(ref).max(), SUBS_FLOOR[f])) < 1e-9, (name, k, f)
+    assert np.array_equal(a.get(1, "x"), xs)
+    # the comparison is not vacuous: the shipped driver leaves another substrate velocity (run AFTER r: the reference draws from
+    # libc's one global rand() stream)
+    b = RefSim("k1", xc, tc, xs, ts, kind="ref"); b.srand(1)
+    b.set(1, "V", v0)
+    t = 0.0
+    for k in range(8):
+        b.step(0.005, t); t += 0.005
+    assert np.abs(r.get(1, "V") - b.get(1, "V")).max() > 1e-2, name
+    assert rel_err(r.get(0, "V"), b.get(0, "V")) < 1e-6       # ... and the same cell (the frozen substrate's velocity does not reach it)
+
+
+def test_dormant_driver_rules_at_the_c_abi(meshes):
+    """include/wcfe.h: a substrate driver other than _Biaxial is honoured by the next substrate update on the planar AND the general
+    kernels alike and lasts for one update; the cell's update refuses after a driver other than _Explicit (its drag force reads
+    V_hlf, UL:571-573) until the shipped driver is called again."""
+    import wholecellfe_b200 as W
+    xc, tc, xs, ts = meshes
+    rng = np.random.default_rng(8)
+    v0 = 1e-2 * rng.normal(size=(len(xs), 3)); v0[:, 2] = 0.0
+    out = {}
+    for general in (0, 1):
+        g = W.ULSim("k1", device=0)
+        g.upload_mesh(W.CELL, xc, tc); g.upload_mesh(W.SUBS, xs, ts); g.srand(1)
+        g.set_force_general(general)
+        g.set(W.SUBS, "V", v0)
+        assert bool(g.path_info()["planar"]) == (general == 0)
+        t = 0.0
+        for k in range(3):
+            g.predict(W.CELL, 0.005, t, download=False); g.commit(W.CELL)
+            vh = g.driver_velocities(W.SUBS, xs, g.get(W.SUBS, "V"), g.get(W.SUBS, "A"), 0.005, t, kind="uniaxial")
+            g.update_cell(0.005, 0.005, t); g.update_subs(0.005, 0.005, t); t += 0.005
+            A = g.get(W.SUBS, "A")
+            assert np.abs(g.get(W.SUBS, "V") - (vh + 0.0025 * A)).max() <= 1e-15 * max(1.0, np.abs(A).max())
+        out[general] = (g.get(W.SUBS, "V"), g.get(W.SUBS, "A"), g.get(W.CELL, "V"))
+        # the choice lasted for one update: a plain step afterwards is _Biaxial's again
+        vb = g.get(W.SUBS, "V"); ab = g.get(W.SUBS, "A")
+        g.step(0.005, t)
+        free = (np.abs(xs[:, 0]) <= 49.0) & (np.abs(xs[:, 1]) <= 49.0)
+        A2 = g.get(W.SUBS, "A")
+        assert np.abs(g.get(W.SUBS, "V")[free] - (vb + 0.0025 * ab + 0.0025 * A2)[free]).max() <= 1e-12 * max(1.0, np.abs(A2).max())
+        # the cell
+        g.predict(W.CELL, 0.005, t, download=False); g.commit(W.CELL)
+        g.driver_velocities(W.CELL, xc, g.get(W.CELL, "V"), g.get(W.CELL, "A"), 0.005, t, kind="offbiaxial")
+        with pytest.raises(W.WcfeError) as e:
+            g.update_cell(0.005, 0.005, t)
+        assert e.value.code == -3
+        g.driver_velocities(W.CELL, xc, g.get(W.CELL, "V"), g.get(W.CELL, "A"), 0.005, t)       # the shipped driver again
+        g.update_cell(0.005, 0.005, t); g.update_subs(0.005, 0.005, t)
+        g.close()
+    for q in range(3):
+        s = max(np.abs(out[1][q]).max(), 1e-3)
+        assert np.abs(out[0][q] - out[1][q]).max() / s < 1e-9, q

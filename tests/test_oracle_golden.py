@@ -71,3 +71,14 @@ def test_grid_point_location_equals_brute_force(meshes, traj):
     for w in ["loc_bond", "loc_force_cnt", "loc_force_first"]:
         assert np.array_equal(a.discrete(w), b.discrete(w))
     assert np.array_equal(a.get(1, "A"), b.get(1, "A"))
+
+
+@pytest.mark.parametrize("name", ["explicit", "biaxial", "uniaxial", "offbiaxial", "bulgetest"])
+def test_every_driver_against_reference_vectors(drivers, name):
+    """ulo_driver_kind against the reference's five driverVelocities_* (UL:103-345) on nodes lying on, and one ulp either side of,
+    every threshold, at times on and around every switch of the time windows: bit for bit."""
+    from oracle.oracle import driver
+    d, expect = drivers
+    for it, t in enumerate(d["times"]):
+        got = driver("k1", name, d["X"], d["V"], d["A"], float(d["dt"]), float(t))
+        assert np.array_equal(got, expect(name, it)), (name, t, int((got != expect(name, it)).sum()))

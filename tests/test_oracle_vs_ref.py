@@ -68,3 +68,20 @@ def test_random_elements_3d_and_planar():
         b = ref_eval_element("k1", mat, X.ravel(), x.ravel(), ea.ravel(), np.full(3, 100.0), np.zeros(3), 0.005, cen, 1.3)
         for u, v in zip(a, b):
             assert rel_err(u, v) < 1e-12
+
+
+@pytest.mark.parametrize("variant", ["k1", "k31", "kMD"])
+def test_every_driver_restatement_against_the_reference_functions(variant):
+    """The five driverVelocities_* of each variant's own translation unit (the three copies are identical, UL:103-345) against
+    ulo_driver_kind on fresh random nodes and times, bit for bit."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_drivers import inputs
+    from oracle.oracle import driver as odriver
+    from oracle.refrun import driver as rdriver, DRIVERS
+    X, V, A = inputs(seed={"k1": 5, "k31": 6, "kMD": 7}[variant], n=1500)
+    rng = np.random.default_rng(99)
+    for t in list(rng.uniform(0, 9, 6)) + [1.0, 2.0, 3.0, 8.0]:
+        dt = float(rng.uniform(1e-4, 1e-2))
+        for name in DRIVERS:
+            assert np.array_equal(odriver(variant, name, X, V, A, dt, float(t)), rdriver(variant, name, X, V, A, dt, float(t))), (variant, name, t)

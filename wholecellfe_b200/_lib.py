@@ -16,12 +16,13 @@ WIDTH = {"x": 3, "V": 3, "A": 3, "ea": 6, "cA": 1, "cB": 1, "cC": 1, "fa_u": 3, 
 DISCRETE = {"loc_bond": 0, "loc_force_cnt": 1, "loc_force_first": 2, "ap_fire": 3, "fa_reset": 4, "cc_clamp": 5}
 FORCE_FIELDS = {"Res_cell": 0, "F_FA": 1, "F_AP": 2, "F_bend": 3, "F_area": 4, "Res_subs": 5, "F_FA_subs": 6}
 RNG_GLIBC_REPLAY, RNG_PHILOX = 0, 1
+DRIVERS = {"explicit": 0, "biaxial": 1, "uniaxial": 2, "offbiaxial": 3, "bulgetest": 4}      # WCFE_DRV_*
 
 # every symbol include/wcfe.h declares
 SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_params", "wcfe_set_stream", "wcfe_last_error",
            "wcfe_upload_mesh", "wcfe_upload_state", "wcfe_download_state", "wcfe_upload_states", "wcfe_download_states", "wcfe_mesh_sizes", "wcfe_set_rng", "wcfe_set_debug",
            "wcfe_rng_skip", "wcfe_set_profile", "wcfe_get_kernel_ms", "wcfe_set_force_general", "wcfe_get_path_info",
-           "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities",
+           "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities", "wcfe_driver_velocities_kind",
            "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
            "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync", "wcfe_selftest_quotient", "wcfe_grid_refreshes",
            "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed", "wcfe_set_roundtrip_mode",
@@ -97,6 +98,7 @@ def load():
     L.wcfe_update_cell.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     L.wcfe_update_subs.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     L.wcfe_driver_velocities.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
+    L.wcfe_driver_velocities_kind.argtypes = [vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
     L.wcfe_mark_positions_committed.argtypes = [vp]
     L.wcfe_step_n.argtypes = [vp, C.c_int, C.c_double, _dp]
     L.wcfe_step_n_async.argtypes = [vp, C.c_int, C.c_double, _dp]

@@ -1,4 +1,5 @@
-// ul_adapter.cpp -- the reference's five UL entry points on top of the C ABI (include/wcfe.h).
+// ul_adapter.cpp -- the reference's UL entry points (the five main.cpp calls, and the three drivers it declares and leaves commented
+// out) on top of the C ABI (include/wcfe.h).
 //
 // Compile this translation unit against the REFERENCE's own headers (common/vec.h, eltopo3d/nondestructivetrimesh.h,
 // cellBP/Eigen) and link it, together with libwcfe.so, in place of cellBP/UL_growth_explicit.o: the unmodified
@@ -35,6 +36,7 @@ struct Adapter {
     std::vector<double> buf;          // AoS scratch
     double dt_real = 0;
     bool cell_pending = false;        // updateFA seen, device step not yet run
+    int ndrv = 0;                     // driver calls since the last substrate update (main.cpp: cell :224, substrate :293, cell again :329)
 } g;
 
 // WCFE_ADAPTER_PROFILE=1: wall time spent inside each of the five entry points, printed at exit (where the whole application's
@@ -122,6 +124,7 @@ void scatter_ea(std::vector<Eigen::VectorXd> &ea) {
 void driverVelocities_Explicit(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt) {
     ProfScope ps(0);
     ensure_context();
+    g.ndrv++;
     OK(wcfe_driver_velocities(g.ctx, WCFE_CELL, (int)X_t.size(), flat(X_t), flat(V_t), flat(A_t), dt, 0.0, flat(V_t_hlf)));
 }
 
@@ -129,7 +132,31 @@ void driverVelocities_Explicit(const std::vector<Vec3d> &X_t, std::vector<Vec3d>
 void driverVelocities_Biaxial(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot) {
     ProfScope ps(1);
     ensure_context();
+    g.ndrv++;
     OK(wcfe_driver_velocities(g.ctx, WCFE_SUBS, (int)X_t.size(), flat(X_t), flat(V_t), flat(A_t), dt, t_tot, flat(V_t_hlf)));
+}
+
+// The drivers main.cpp declares (:73, :74, :76) and keeps commented out at its two call sites (:217-220, :291-295).  Their signature
+// does not say which surface they serve; a maintainer who enables one puts it at one of the two call sites, so the position in
+// main.cpp's call order decides: the second driver call of a step is the substrate's (:293), the first and a third (:329) the cell's.
+// On the substrate the next update uses this V_hlf (UL:499); on the cell the update refuses (its drag force reads V_hlf, UL:571-573).
+namespace {
+void driver_of_kind(int kind, const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot) {
+    ensure_context();
+    const int surface = (g.ndrv == 1) ? WCFE_SUBS : WCFE_CELL;
+    ProfScope ps(surface);
+    g.ndrv++;
+    OK(wcfe_driver_velocities_kind(g.ctx, surface, kind, (int)X_t.size(), flat(X_t), flat(V_t), flat(A_t), dt, t_tot, flat(V_t_hlf)));
+}
+}   // namespace
+void driverVelocities_Uniaxial(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot) {
+    driver_of_kind(WCFE_DRV_UNIAXIAL, X_t, V_t, V_t_hlf, A_t, dt, t_tot);
+}
+void driverVelocities_OffBiaxial(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot) {
+    driver_of_kind(WCFE_DRV_OFFBIAXIAL, X_t, V_t, V_t_hlf, A_t, dt, t_tot);
+}
+void driverVelocities_BulgeTest(const std::vector<Vec3d> &X_t, std::vector<Vec3d> &V_t, std::vector<Vec3d> &V_t_hlf, std::vector<Vec3d> &A_t, double dt, double t_tot) {
+    driver_of_kind(WCFE_DRV_BULGETEST, X_t, V_t, V_t_hlf, A_t, dt, t_tot);
 }
 
 // main.cpp:354.  The device step needs V, A, ea too, which the reference only hands to updateForces_Explicit; main.cpp does
@@ -200,6 +227,7 @@ void updateForces_Explicit(const std::vector<Vec3d> &X_t, const std::vector<Vec3
         OK(wcfe_upload_states(g.ctx, WCFE_SUBS, 3, f, h));
     }
     OK(wcfe_update_subs(g.ctx, dt, dt_real, t_tot));
+    g.ndrv = 0;
     {
         const int f[3] = {WCFE_F_V, WCFE_F_A, WCFE_F_EA};
         double *h[3] = {flat(V_t), flat(A_t), g.buf.data()};

@@ -160,6 +160,9 @@ struct wcfe_ctx {
     double last_ms = 0, t_last = 0;
     bool have_predict[2] = {false, false};
     double drv_dt[2] = {-1.0, -1.0};      // dt of the last driver call per surface (wcfe_predict / wcfe_driver_velocities): V_hlf = V + drv_dt/2 A (UL:118, :295); < 0: the step's dt
+    int drv_kind[2] = {WCFE_DRV_EXPLICIT, WCFE_DRV_BIAXIAL};   // driver of the last driver call per surface (wcfe_driver_velocities_kind); back to these after every update
+    DevBuf<double> d_vh_subs;             // V_hlf (AoS) of a substrate driver other than _Biaxial, read by k_subs_vhalf after the next substrate update
+    size_t vh_subs_n = 0;
     bool tape_busy = false;               // an async step_n may still be reading the pinned RNG tape
     // partitioned substrate: fused peer-memory halo exchange (HaloView, wcfe_patch.cuh)
     struct {
@@ -802,6 +805,11 @@ int launch_update(wcfe_ctx *c, double dt, double dt_real, double t_tot, const un
     // El Topo may accept less than the requested step: the caller's V_hlf was formed by the LAST driver call, whose dt (curr_dt,
     // main.cpp:224/:293/:329) then differs from the dt updateForces_Explicit receives (ori_dt, main.cpp:360-361)
     const double dtd_c = (!fuse_predict && c->drv_dt[0] >= 0) ? c->drv_dt[0] : dt, dtd_s = (!fuse_predict && c->drv_dt[1] >= 0) ? c->drv_dt[1] : dt;
+    const bool custom_subs = !fuse_predict && (which & 2) && c->drv_kind[WCFE_SUBS] != WCFE_DRV_BIAXIAL;
+    if (!fuse_predict && (which & 1) && c->drv_kind[WCFE_CELL] != WCFE_DRV_EXPLICIT)
+        return fail(c, WCFE_ERR_UNSUPPORTED, "update(cell) after a driver other than driverVelocities_Explicit: the cell's drag force reads V_hlf (UL:571-573) and the kernels form it as _Explicit does");
+    if (custom_subs && (moving || c->nrep > 1 || c->halo.active || c->cpart.active || c->vh_subs_n != (size_t)ss.nn))
+        return fail(c, WCFE_ERR_UNSUPPORTED, "update(substrate) after a driver other than driverVelocities_Biaxial: one context on one GPU, frozen substrate, driver called on all its nodes");
     if (which & 1) c->epoch++;            // the cell half fills the triangle buckets of this epoch, the substrate half reads them
     if (which & 1) {
         // the two bucket-head protocols do not mix: zero the heads when the path changes (planar <-> general, k_subs_ring <-> k_subs_patch)
@@ -1008,6 +1016,10 @@ subs_half:
         else k_subs_node<false><<<gs, kBlock, 0, c->stream>>>(sv, cv, bk, c->k, dt, dt_real, t_tot, c->box[0], c->box[1], c->box[2], c->box[3], DebugView{}, dtd_s);
     }
     c->launches += 1;
+    if (custom_subs && dt_real > dt / 2.0) {       // UL:498-499 with the V_hlf the caller's driver formed
+        k_subs_vhalf<<<gs, kBlock, 0, c->stream>>>(ss.nn, ss.np, ss.V.p, ss.A.p, c->d_vh_subs.p, dt, dt_real);
+        c->launches += 1;
+    }
     if (reduce) c->big_clean = true;       // k_subs_ring zeroed the counter
     ss.ea_cur ^= 1;
     c->step++;
@@ -1237,7 +1249,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release(); c->b_node_epoch.release(); c->cell_done.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release(); c->d_loc_cache.release();
-    c->d_kb.release(); c->d_seeds.release(); c->big_count.release(); c->big_list.release(); c->b_sums.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_aos.release();
+    c->d_kb.release(); c->d_seeds.release(); c->big_count.release(); c->big_list.release(); c->b_sums.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_vh_subs.release(); c->d_aos.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
@@ -1598,7 +1610,7 @@ int wcfe_predict(wcfe_ctx *c, int surface, double dt, double t_curr, double *xyz
         CK(cudaGetLastError());
     }
     // substrate: x_new = x + 0*dt*V_hlf (main.cpp:299) == x; V_hlf itself is formed inside the update kernel
-    c->have_predict[surface] = true; c->drv_dt[surface] = dt;
+    c->have_predict[surface] = true; c->drv_dt[surface] = dt; c->drv_kind[surface] = surface;
     if (xyz_new_out) return get_field(c, s.x.p, xyz_new_out, s.nn, s.np, 3);
     return WCFE_OK;
 }
@@ -1630,16 +1642,17 @@ static int update_impl(wcfe_ctx *c, double dt_req, double dt_real, double t_curr
         if ((rc = stage_tape(c, 1))) return rc;
     }
     if ((rc = launch_update(c, dt_req, dt_real, t_curr, c->d_tape.p, false, which))) return rc;
-    if (which & 1) { c->have_predict[0] = false; c->drv_dt[0] = -1.0; }
-    if (which & 2) { c->have_predict[1] = false; c->drv_dt[1] = -1.0; c->t_last = t_curr + dt_real; }
+    if (which & 1) { c->have_predict[0] = false; c->drv_dt[0] = -1.0; c->drv_kind[0] = WCFE_DRV_EXPLICIT; }
+    if (which & 2) { c->have_predict[1] = false; c->drv_dt[1] = -1.0; c->drv_kind[1] = WCFE_DRV_BIAXIAL; c->t_last = t_curr + dt_real; }
     return check_device_errors(c);
 }
 int wcfe_update(wcfe_ctx *c, double dt_req, double dt_real, double t_curr) { return update_impl(c, dt_req, dt_real, t_curr, 3); }
 int wcfe_update_cell(wcfe_ctx *c, double dt_req, double dt_real, double t_curr) { return update_impl(c, dt_req, dt_real, t_curr, 1); }
 int wcfe_update_subs(wcfe_ctx *c, double dt_req, double dt_real, double t_curr) { return update_impl(c, dt_req, dt_real, t_curr, 2); }
 
-int wcfe_driver_velocities(wcfe_ctx *c, int surface, int nn, const double *X, const double *V, const double *A, double dt, double t_curr, double *Vh_out) {
+int wcfe_driver_velocities_kind(wcfe_ctx *c, int surface, int kind, int nn, const double *X, const double *V, const double *A, double dt, double t_curr, double *Vh_out) {
     if (!c || surface < 0 || surface > 1 || nn <= 0 || !X || !V || !A || !Vh_out) return fail(c, WCFE_ERR_ARG, "driver_velocities: bad arguments");
+    if (kind < WCFE_DRV_EXPLICIT || kind > WCFE_DRV_BULGETEST) return fail(c, WCFE_ERR_ARG, "driver_velocities: unknown driver kind");
     CK(cudaSetDevice(c->device));
     const size_t bytes = sizeof(double) * 3 * (size_t)nn;
     int rc = ensure_stage(c, 4 * bytes);
@@ -1649,14 +1662,23 @@ int wcfe_driver_velocities(wcfe_ctx *c, int surface, int nn, const double *X, co
     memcpy(h, X, bytes); memcpy(h + bytes, V, bytes); memcpy(h + 2 * bytes, A, bytes);
     CK(cudaMemcpyAsync(c->d_drv.p, h, 3 * bytes, cudaMemcpyHostToDevice, c->stream));
     double *d = c->d_drv.p;
-    k_driver<<<(nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(surface, nn, d, d + 3 * (size_t)nn, d + 6 * (size_t)nn, d + 9 * (size_t)nn, c->k, dt, t_curr);
+    k_driver<<<(nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(kind, nn, d, d + 3 * (size_t)nn, d + 6 * (size_t)nn, d + 9 * (size_t)nn, c->k, dt, t_curr);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h + 3 * bytes, d + 9 * (size_t)nn, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (surface == WCFE_SUBS && kind != WCFE_DRV_BIAXIAL) {      // kept for k_subs_vhalf: the scratch is overwritten by the next driver call
+        if (c->d_vh_subs.n < 3 * (size_t)nn) CK(c->d_vh_subs.alloc(3 * (size_t)nn));
+        CK(cudaMemcpyAsync(c->d_vh_subs.p, d + 9 * (size_t)nn, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        c->vh_subs_n = (size_t)nn;
+    }
     CK(cudaStreamSynchronize(c->stream));
     memcpy(Vh_out, h + 3 * bytes, bytes);
     c->drv_dt[surface] = dt;      // the update that follows forms the same V_hlf on the device
+    c->drv_kind[surface] = kind;
     return WCFE_OK;
+}
+int wcfe_driver_velocities(wcfe_ctx *c, int surface, int nn, const double *X, const double *V, const double *A, double dt, double t_curr, double *Vh_out) {
+    return wcfe_driver_velocities_kind(c, surface, surface, nn, X, V, A, dt, t_curr, Vh_out);
 }
 
 /* adapter mode: the host integrator owns the positions; declare that x and X_prev of the cell have been uploaded */

@@ -188,21 +188,48 @@ __global__ void __launch_bounds__(kBlock) k_soa_to_aos(int nn, int np, int w, co
     aos[idx] = soa[(size_t)q * np + i];
 }
 
-// ---- stand-alone drivers for the adapter: host-owned X, V, A in, V_hlf out (UL:103-124 cell, UL:275-345 substrate) -----------
-__global__ void __launch_bounds__(kBlock) k_driver(int surface, int nn, const double *__restrict__ X, const double *__restrict__ V,
+// ---- stand-alone drivers for the adapter: host-owned X, V, A in, V_hlf out.  kind 0 driverVelocities_Explicit UL:103-124,
+//      1 _Biaxial UL:275-345 (the two main.cpp calls), 2 _Uniaxial UL:125-168, 3 _OffBiaxial UL:214-273, 4 _BulgeTest UL:170-212
+//      (defined by the reference, commented out at main.cpp:217-220, :291-295).  Thresholds are the reference's literals; the
+//      moving thresholds are formed uncontracted like the reference's x86 code.
+__global__ void __launch_bounds__(kBlock) k_driver(int kind, int nn, const double *__restrict__ X, const double *__restrict__ V,
                                                    const double *__restrict__ A, double *__restrict__ Vh, Consts k, double dt, double t_tot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nn) return;
     double v[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) v[c] = WCFE_ADD(V[3 * i + c], WCFE_MUL(dt / 2.0, A[3 * i + c]));
-    v[2] = 0.0;
-    if (surface == 1 && (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f)) {
-        if (X[3 * i] < -k.pin_limit || X[3 * i] > k.pin_limit) v[0] = 0.0;
-        if (X[3 * i + 1] > k.pin_limit || X[3 * i + 1] < -k.pin_limit) v[1] = 0.0;
+    const double X0 = X[3 * i], X1 = X[3 * i + 1], X2 = X[3 * i + 2];
+    if (kind != 4) v[2] = 0.0;
+    if (kind == 1 && (t_tot < k.t_i || (t_tot > k.t_i && t_tot < k.t_f) || t_tot > k.t_f)) {
+        if (X0 < -k.pin_limit || X0 > k.pin_limit) v[0] = 0.0;
+        if (X1 > k.pin_limit || X1 < -k.pin_limit) v[1] = 0.0;
+    } else if (kind == 2) {
+        if (X0 < -0.0499) { v[0] = 0.0; v[1] = 0.0; }
+        if (X0 > WCFE_ADD(0.9499, WCFE_MUL(0.1, t_tot)) && t_tot <= 2.0) { v[0] = 0.1; v[1] = 0.0; }
+        if (X0 > 0.9499 + 2.00 * 0.1 && t_tot >= 2.0) { v[0] = 0.0; v[1] = 0.0; }
+    } else if (kind == 3) {
+        if (X0 < -0.04) { v[0] = 0.0; v[1] = 0.0; }
+        if (X0 > WCFE_ADD(0.94, WCFE_MUL(0.1, t_tot)) && t_tot < 1.0) { v[0] = 0.1; v[1] = 0.0; }
+        if (X0 > 0.94 + 0.99 * 0.1 && t_tot >= 1.0) { v[0] = 0.0; v[1] = 0.0; }
+        if (X1 > 0.99 || X1 < 0.01) v[1] = 0.0;
+    } else if (kind == 4) {
+        const bool mid = X2 < 0.001 && X2 > -0.001;
+        if (mid && (X0 < 0.001 || X0 > 0.999 || X1 < 0.001 || X1 > 0.999)) { v[0] = 0.0; v[1] = 0.0; v[2] = 0.0; }
     }
 #pragma unroll
     for (int c = 0; c < 3; c++) Vh[3 * i + c] = v[c];
+}
+
+// the substrate's nodal update after a driver other than _Biaxial: V = V_hlf + (dt_real - dt/2) A (UL:499) with the V_hlf that driver
+// returned (AoS, kept on the device) and the A the substrate kernel has just written; launched only when dt_real > dt/2 (UL:498)
+__global__ void __launch_bounds__(kBlock) k_subs_vhalf(int nn, int np, double *__restrict__ V, const double *__restrict__ A,
+                                                       const double *__restrict__ Vh, double dt, double dt_real) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn) return;
+    const double ddt = dt_real - dt / 2.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) V[c * np + i] = fma(ddt, A[c * np + i], Vh[3 * i + c]);
 }
 
 // ---- point location of one anchor in the substrate -------------------------------------------------------

@@ -144,6 +144,26 @@ class ULSim:
     def update(self, dt_req, dt_real, t_curr):
         self._ck(self.L.wcfe_update(self.h, dt_req, dt_real, t_curr))
 
+    def update_cell(self, dt_req, dt_real, t_curr):
+        """updateFA + updateForces_Explicit(cell) (main.cpp:354, :360)"""
+        self._ck(self.L.wcfe_update_cell(self.h, dt_req, dt_real, t_curr))
+
+    def update_subs(self, dt_req, dt_real, t_curr):
+        """updateForces_Explicit(substrate) (main.cpp:361); follows update_cell of the same step"""
+        self._ck(self.L.wcfe_update_subs(self.h, dt_req, dt_real, t_curr))
+
+    def mark_positions_committed(self):
+        self._ck(self.L.wcfe_mark_positions_committed(self.h))
+
+    def driver_velocities(self, surface, X, V, A, dt, t_curr, kind=None):
+        """driverVelocities_* (UL:103-345) on host-owned AoS arrays, computed on the device; kind: one of B.DRIVERS (default: the driver
+        main.cpp calls for that surface).  The next update of `surface` uses this V_hlf (see include/wcfe.h)."""
+        X = np.ascontiguousarray(X, dtype=np.float64); V = np.ascontiguousarray(V, dtype=np.float64); A = np.ascontiguousarray(A, dtype=np.float64)
+        out = np.empty_like(X)
+        k = surface if kind is None else (B.DRIVERS[kind] if isinstance(kind, str) else int(kind))
+        self._ck(self.L.wcfe_driver_velocities_kind(self.h, surface, k, len(X), _d(X), _d(V), _d(A), dt, t_curr, _d(out)))
+        return out
+
     def step(self, dt, t_curr):
         """One El-Topo-free step; same signature as the oracle's step()."""
         t = C.c_double(t_curr)
