@@ -205,6 +205,19 @@ double wcfe_last_step_ms(wcfe_ctx *c);
  * 0 Res(cell) 1 F_FA 2 F_AP 3 F_bending 4 F_area 5 Res(subs) 6 F_FA_subs; out[3*nn]; mm[nn] / res_ea[6*nn]
  * may be NULL.  Diagnostic entry point for the force-level parity gate (1e-10). */
 int wcfe_force_field(wcfe_ctx *c, int which, double dt, double t_curr, double *out, double *mm, double *res_ea);
+/* Dormant physics of the cell: fields the reference defines and whose calls / consumers are commented out, computed on the current
+ * device state (x, start-of-step X, c_A, c_C); diagnostic entry point outside the step, general (3-D) arithmetic.
+ *   WCFE_DORMANT_RES_ADIF / _RES_CDIF  diffusion residuals of free / bound integrins (evalElementRe UL:833-842, :915-925, assembled in
+ *                                      calculateRes UL:702-704; consumers commented out UL:617-618); out[nn]
+ *   WCFE_DORMANT_PRESSURE              calculatePressureForce UL:1765-1816 (bulge-test follower load, call commented out UL:577); out[3*nn]
+ *   WCFE_DORMANT_SPHERE                calculateConstraintForce UL:1178-1194 (call commented out UL:551); out[3*nn]
+ * Not built: calculateBendingRes UL:1818-1885, a one-sided finite difference (delta 1e-6) of an acos of unit normals -- on a flat
+ * sheet its value is the rounding noise of acos near 1, there is nothing to pin. */
+#define WCFE_DORMANT_RES_ADIF 0
+#define WCFE_DORMANT_RES_CDIF 1
+#define WCFE_DORMANT_PRESSURE 2
+#define WCFE_DORMANT_SPHERE 3
+int wcfe_dormant_field(wcfe_ctx *c, int which, double dt, double t_curr, double *out);
 /* raw device pointer of a state field (SoA: component q of node i at ptr[q*pitch + i]); x, V, A, ea are double-buffered, so
  * ask again after every step.  Zero-copy interop with torch.distributed for the halo exchange of partitioned meshes. */
 int wcfe_device_ptr(wcfe_ctx *c, int surface, int field, void **ptr, long long *pitch);

@@ -138,10 +138,13 @@ class OracleSim:
         self.L.ulo_step(self.h, dt, t_curr)
 
     def force_field(self, which, dt, t_curr):
-        names = {"Res_cell": 0, "F_FA": 1, "F_AP": 2, "F_bend": 3, "F_area": 4, "Res_subs": 5, "F_FA_subs": 6}
-        w = names[which]; surf = 1 if w >= 5 else 0; n = self.nn[surf]
+        names = {"Res_cell": 0, "F_FA": 1, "F_AP": 2, "F_bend": 3, "F_area": 4, "Res_subs": 5, "F_FA_subs": 6,
+                 "Res_Adif": 7, "Res_Cdif": 8, "F_pressure": 9, "F_sphere": 10}      # 7-10: dormant in the reference (calls commented out)
+        w = names[which]; surf = 1 if w in (5, 6) else 0; n = self.nn[surf]
         out = np.zeros((n, 3)); mm = np.zeros(n); rea = np.zeros((n, 6)); aux = np.zeros(4)
         assert self.L.ulo_force_field(self.h, w, dt, t_curr, _d(out), _d(mm), _d(rea), _d(aux)) == 0
+        if w in (7, 8):
+            return {"F": out.ravel()[:n].copy(), "area": aux}                       # one scalar per node
         return {"F": out, "MM": mm, "Res_ea": rea, "area": aux}
 
 

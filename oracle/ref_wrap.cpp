@@ -47,6 +47,8 @@ void calculateForce_FA(Eigen::VectorXd &F_constraint, const std::vector<Vec3d> &
 void calculateForce_FA_subs(Eigen::VectorXd &F_constraint, const std::vector<Vec3d> &X_t, const std::vector<Vec3d> &x_t, const NonDestructiveTriMesh &mesh, const std::vector<double> &c_C, const std::vector<Vec3d> &x_cell, std::vector<Vec3d> &fa_u, const NonDestructiveTriMesh &mesh_cell, double kint);
 void calculateForce_AP(Eigen::VectorXd &F_constraint, const std::vector<Vec3d> &X_t, const std::vector<Vec3d> &x_t, const std::vector<double> &c_A, const NonDestructiveTriMesh &mesh, double dt_real);
 void calculateBendingForce2D(Eigen::VectorXd &F_bending, const std::vector<Vec3d> &X_t, const std::vector<Vec3d> &x_t, const NonDestructiveTriMesh &mesh);
+void calculateConstraintForce(Eigen::VectorXd &F_constraint, const std::vector<Vec3d> &x_t);
+void calculatePressureForce(Eigen::VectorXd &F_constraint, const std::vector<Vec3d> &x_t, const Eigen::VectorXd &MM, const NonDestructiveTriMesh &mesh, double t_tot);
 Eigen::Vector4d calculateAreaTot(const std::vector<Vec3d> &x_t, const NonDestructiveTriMesh &mesh);
 void calculateAreaConstraintForce(Eigen::VectorXd &F_areaConstraint, const std::vector<Vec3d> &X_t, const std::vector<Vec3d> &x_t, const NonDestructiveTriMesh &mesh, double tot_area);
 
@@ -321,6 +323,23 @@ int ulref_force_field(ulref *h, int which, double dt, double t_curr, double kint
         for (int i = 0; i < nc * 3; i++) out[i] = Res(i);
         if (mm) for (int i = 0; i < nc; i++) mm[i] = MM(i);
         if (res_ea) for (int i = 0; i < nc * 6; i++) res_ea[i] = Rea(i);
+        return 0;
+    }
+    if (which >= 7 && which <= 9) {          // dormant: the diffusion residuals calculateRes(cell) returns and nobody reads (UL:617-618); pressure (UL:577)
+        Eigen::VectorXd Res(nc * 3), Rea(nc * 6), MM(nc), RA(nc), RC(nc);
+        Eigen::Vector3d cen; cen << area(1), area(2), area(3);
+        calculateRes(Xc, c.x, c.ea, c.cA, c.cC, c.mesh, dt, Res, Rea, MM, RA, RC, 1, cen, t_curr);
+        if (which == 9) {
+            Eigen::VectorXd Fp(nc * 3); Fp.setZero();
+            calculatePressureForce(Fp, c.x, MM, c.mesh, t_curr);
+            for (int i = 0; i < nc * 3; i++) out[i] = Fp(i);
+        } else for (int i = 0; i < nc; i++) out[i] = which == 7 ? RA(i) : RC(i);
+        return 0;
+    }
+    if (which == 10) {                       // dormant: sphere constraint (UL:551)
+        Eigen::VectorXd Fc(nc * 3); Fc.setZero();
+        calculateConstraintForce(Fc, c.x);
+        for (int i = 0; i < nc * 3; i++) out[i] = Fc(i);
         return 0;
     }
     if (which == 5) {

@@ -262,6 +262,83 @@ void ulo_calculate_res(const ulo_params *p, int mat, const ulo_mesh *m, const do
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* Dormant physics: functions the reference defines and whose calls are           */
+/* commented out -- restated so that the device versions (wcfe_dormant_field) have a checker.          */
+/* ------------------------------------------------------------------------------------------------ */
+/* Diffusion residuals of the two integrin species: element part evalElementRe UL:833-842, :915-925 (D_A = 1, D_C = 1e-10,
+ * shape-function gradients from the rows of [g1 g2 n]^-1 on the predicted coordinates), serial scatter-add in element order
+ * calculateRes UL:702-704.  Their consumers are commented out (UL:617-618). */
+void ulo_diffusion_res(const ulo_params *p, const ulo_mesh *m, const double *X, const double *x, const double *cA, const double *cC,
+                       double dt, double *Res_Adif, double *Res_Cdif) {
+    const double D_A = 1., D_C = 1e-10;                        /* UL:919-920 */
+    int e, i, k;
+    memset(Res_Adif, 0, sizeof(double) * (size_t)m->nn);
+    memset(Res_Cdif, 0, sizeof(double) * (size_t)m->nn);
+    for (e = 0; e < m->ne; e++) {
+        const int *t = m->tri + 3 * e;
+        double G1[3], G2[3], G1xG2[3], nG, g1[3], g2[3], gx[3], ng, n[3], g[9], ginv[9], g1inv[3], g2inv[3], gradA[3], gradC[3], c_A, c_C;
+        for (k = 0; k < 3; k++) {
+            G1[k] = -1.0 * X[3 * t[0] + k] + 1.0 * X[3 * t[1] + k]; G2[k] = -1.0 * X[3 * t[0] + k] + 1.0 * X[3 * t[2] + k];   /* UL:770-771 */
+            g1[k] = -1.0 * x[3 * t[0] + k] + 1.0 * x[3 * t[1] + k]; g2[k] = -1.0 * x[3 * t[0] + k] + 1.0 * x[3 * t[2] + k];   /* UL:805-806 */
+        }
+        cross3(G1, G2, G1xG2); nG = norm3(G1xG2);
+        cross3(g1, g2, gx); ng = norm3(gx);
+        for (k = 0; k < 3; k++) n[k] = gx[k] / ng;
+        for (k = 0; k < 3; k++) { M(g, k, 0) = g1[k]; M(g, k, 1) = g2[k]; M(g, k, 2) = n[k]; }                                /* UL:816-819 */
+        inv3(g, ginv);                                                                                                          /* UL:834 */
+        for (k = 0; k < 3; k++) { g1inv[k] = M(ginv, 0, k); g2inv[k] = M(ginv, 1, k); }
+        for (k = 0; k < 3; k++) {                                                                                               /* UL:839-840 */
+            gradA[k] = cA[t[0]] * g1inv[k] + cA[t[1]] * g2inv[k] + cA[t[2]] * (-g1inv[k] - g2inv[k]);
+            gradC[k] = cC[t[0]] * g1inv[k] + cC[t[1]] * g2inv[k] + cC[t[2]] * (-g1inv[k] - g2inv[k]);
+        }
+        c_A = (1. / 3.) * (cA[t[0]] + cA[t[1]] + cA[t[2]]);                                                                     /* UL:841-842 */
+        c_C = (1. / 3.) * (cC[t[0]] + cC[t[1]] + cC[t[2]]);
+        for (i = 0; i < 3; i++) {
+            double gN[3], dA = 0, dC = 0;
+            for (k = 0; k < 3; k++) gN[k] = (i == 0 ? 1.0 : 0.0) * g1inv[k] + (i == 1 ? 1.0 : 0.0) * g2inv[k] + (i == 2 ? 1.0 : 0.0) * (-g1inv[k] - g2inv[k]);   /* UL:917 */
+            for (k = 0; k < 3; k++) { dA += gradA[k] * gN[k]; dC += gradC[k] * gN[k]; }
+            Res_Adif[t[i]] += (c_A * (1. / 3.) - dt * D_A * dA) * nG / 2.0 * p->thick;                                          /* UL:924 */
+            Res_Cdif[t[i]] += (c_C * (1. / 3.) - dt * D_C * dC) * nG / 2.0 * p->thick;                                          /* UL:925 */
+        }
+    }
+}
+/* calculatePressureForce UL:1765-1816 (the bulge test's follower load; call commented out at UL:577): -pres (MM/thick) n with the
+ * area-weighted vertex normal on x, pres a trapezoid in time, thick the function's own literal 0.1 */
+void ulo_force_pressure(const ulo_mesh *m, const double *x, const double *MM, double t_tot, double *F) {
+    double pres = 2000.0, thick = 0.1;
+    int ni, r, k;
+    if (t_tot < 1) pres = 2000.0 * t_tot;
+    if (t_tot > 2) pres = 2000.0 * (3 - t_tot);
+    if (t_tot > 3) pres = 0.0;
+    for (ni = 0; ni < m->nn; ni++) {
+        double normal[3] = {0, 0, 0}, Asum = 0.0, nn_;
+        for (r = m->ring_ptr[ni]; r < m->ring_ptr[ni + 1]; r++) {
+            const int *t = m->tri + 3 * m->ring[r];
+            double E1[3], E2[3], nt[3], a, l;
+            for (k = 0; k < 3; k++) { E1[k] = x[3 * t[1] + k] - x[3 * t[0] + k]; E2[k] = x[3 * t[2] + k] - x[3 * t[0] + k]; }
+            cross3(E1, E2, nt);
+            l = norm3(nt); a = 0.5 * l;
+            for (k = 0; k < 3; k++) normal[k] += a * (nt[k] / l);
+            Asum += a;
+        }
+        for (k = 0; k < 3; k++) normal[k] = normal[k] / Asum;
+        nn_ = norm3(normal);
+        for (k = 0; k < 3; k++) normal[k] = normal[k] / nn_;
+        for (k = 0; k < 3; k++) F[3 * ni + k] = -pres * (MM[ni] / thick) * normal[k];
+    }
+}
+/* calculateConstraintForce UL:1178-1194 (penalty towards the sphere of radius 350 about the origin; call commented out at UL:551) */
+void ulo_force_sphere(int nn, const double *x, double *F) {
+    const double radius = 350.0, penalty_dist = 4000.0;
+    int ni, k;
+    for (ni = 0; ni < nn; ni++) {
+        const double *xi = x + 3 * ni;
+        double dist = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
+        for (k = 0; k < 3; k++) F[3 * ni + k] = penalty_dist * (radius - dist) * (xi[k] / dist);
+    }
+}
+
 /* calculateAreaTot UL:1641-1667 */
 void ulo_area_tot(const ulo_mesh *m, const double *x, double *out4) {
     double area_tot = 0, cen[3] = {0, 0, 0};
@@ -838,6 +915,21 @@ int ulo_force_field(ulo_sim *s, int which, double dt, double t_curr, double *out
         free(MM); free(Rea);
         return 0;
     }
+    if (which == 7 || which == 8) {                             /* Res_Adif / Res_Cdif: out[nn] */
+        double *RA = (double *)malloc(sizeof(double) * nc), *RC = (double *)malloc(sizeof(double) * nc);
+        ulo_diffusion_res(&s->p, &c->m, c->X, c->x, c->cA, c->cC, dt, RA, RC);
+        memcpy(out, which == 7 ? RA : RC, sizeof(double) * nc);
+        free(RA); free(RC);
+        return 0;
+    }
+    if (which == 9) {                                           /* pressure, with the lumped mass of calculateRes(cell) */
+        double *MM = (double *)malloc(sizeof(double) * nc), *Rea = (double *)malloc(sizeof(double) * 6 * nc), *Res = (double *)malloc(sizeof(double) * 3 * nc);
+        ulo_calculate_res(&s->p, 1, &c->m, c->X, c->x, c->ea, dt, area + 1, t_curr, Res, Rea, MM);
+        ulo_force_pressure(&c->m, c->x, MM, t_curr, out);
+        free(MM); free(Rea); free(Res);
+        return 0;
+    }
+    if (which == 10) { ulo_force_sphere(nc, c->x, out); return 0; }
     switch (which) {
     case 1: ulo_force_FA(&s->p, &c->m, c->x, c->cC, c->fa_u, out); return 0;
     case 2: ulo_force_AP(s, c->x, dt, out); return 0;

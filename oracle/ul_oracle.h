@@ -98,9 +98,15 @@ void ulo_force_area(const ulo_params *p, const ulo_mesh *m, const double *x, dou
 void ulo_update_FA(ulo_sim *s, double dt);
 void ulo_driver_explicit(int nn, const double *V, const double *A, double dt, double *Vh);
 void ulo_driver_biaxial(const ulo_params *p, int nn, const double *X, const double *V, const double *A, double dt, double t, double *Vh);
+/* dormant physics: defined by the reference, calls commented out (UL:617-618, :577, :551) */
+void ulo_diffusion_res(const ulo_params *p, const ulo_mesh *m, const double *X, const double *x, const double *cA, const double *cC,
+                       double dt, double *Res_Adif, double *Res_Cdif);
+void ulo_force_pressure(const ulo_mesh *m, const double *x, const double *MM, double t_tot, double *F);
+void ulo_force_sphere(int nn, const double *x, double *F);
 /* every driverVelocities_* of UL:103-345 by kind: 0 Explicit, 1 Biaxial, 2 Uniaxial, 3 OffBiaxial, 4 BulgeTest; -1 on an unknown kind */
 int  ulo_driver_kind(const ulo_params *p, int kind, int nn, const double *X, const double *V, const double *A, double dt, double t, double *Vh);
-/* force field by id on the current state, same ids as ulref_force_field */
+/* force field by id on the current state, same ids as ulref_force_field (7 Res_Adif, 8 Res_Cdif: out[nn]; 9 pressure, 10 sphere
+ * constraint: the dormant ones) */
 int  ulo_force_field(ulo_sim *s, int which, double dt, double t_curr, double *out, double *mm, double *res_ea, double *aux4);
 /* the same fields as they were inside the last ulo_step() */
 int  ulo_step_force_field(ulo_sim *s, int which, double *out, double *mm, double *res_ea);

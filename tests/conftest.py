@@ -46,3 +46,9 @@ def drivers():
         code = d["code_" + name][it]
         return np.where(code == 0, free, np.where(code == 1, 0.0, 0.1))
     return d, expect
+
+
+@pytest.fixture(scope="session")
+def dormant():
+    """tests/golden/dormant.npz (make_golden_dormant.py): a bent cell state and the reference's dormant fields on it"""
+    return np.load(os.path.join(GOLDEN, "dormant.npz"))

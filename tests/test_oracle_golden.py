@@ -82,3 +82,20 @@ def test_every_driver_against_reference_vectors(drivers, name):
     for it, t in enumerate(d["times"]):
         got = driver("k1", name, d["X"], d["V"], d["A"], float(d["dt"]), float(t))
         assert np.array_equal(got, expect(name, it)), (name, t, int((got != expect(name, it)).sum()))
+
+
+def test_dormant_fields_against_reference_vectors(meshes, dormant):
+    """The restatement of the reference's dormant physics -- diffusion residuals (UL:915-925), pressure load (UL:1765-1816), sphere
+    penalty (UL:1178-1194) -- against what the reference's own functions return on a bent, unevenly loaded cell."""
+    xc, tc, xs, ts = meshes
+    g = dormant
+    o = OracleSim("k1", xc, tc, xs, ts)
+    for f in ["x", "X_prev", "ea", "cA", "cC"]:                      # x before X_prev: setting x alone also resets X_prev
+        o.set(0, f, g["c_" + f])
+    for name in ["Res_Adif", "Res_Cdif"]:
+        for q, dt in enumerate(g["dts"]):
+            assert rel_err(o.force_field(name, float(dt), 0.7)["F"], g[name][q]) < 1e-13, (name, dt)
+    for q, t in enumerate(g["times"]):
+        assert rel_err(o.force_field("F_pressure", 0.005, float(t))["F"], g["F_pressure"][q], max(np.abs(g["F_pressure"][q]).max(), 1.0)) < 1e-13, t
+    assert np.abs(g["F_pressure"][-1]).max() == 0.0 and np.abs(g["F_pressure"][1]).max() > 1e4      # the schedule's branches are all there
+    assert rel_err(o.force_field("F_sphere", 0.005, 0.7)["F"], g["F_sphere"]) < 1e-14

@@ -85,3 +85,20 @@ def test_every_driver_restatement_against_the_reference_functions(variant):
         dt = float(rng.uniform(1e-4, 1e-2))
         for name in DRIVERS:
             assert np.array_equal(odriver(variant, name, X, V, A, dt, float(t)), rdriver(variant, name, X, V, A, dt, float(t))), (variant, name, t)
+
+
+@pytest.mark.parametrize("variant", ["k1", "kMD"])
+def test_dormant_fields_restatement_against_the_reference_functions(meshes, variant):
+    """Diffusion residuals, pressure load and sphere penalty (calls commented out in the reference, UL:617-618, :577, :551): the
+    restatement against the reference's own functions on a state bent out of plane by the same recipe on both sides."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_dormant import bent_state
+    xc, tc, xs, ts = meshes
+    r = RefSim(variant, xc, tc, xs, ts); bent_state(r, xc)
+    o = OracleSim(variant, xc, tc, xs, ts); bent_state(o, xc)
+    assert np.abs(r.get(0, "X_prev")[:, 2]).max() > 0.1
+    for name, dt, t in [("Res_Adif", 0.005, 0.7), ("Res_Adif", 0.5, 0.7), ("Res_Cdif", 0.5, 0.7), ("F_pressure", 0.005, 0.4), ("F_pressure", 0.005, 1.5),
+                        ("F_pressure", 0.005, 2.6), ("F_sphere", 0.005, 0.0)]:
+        a = o.force_field(name, dt, t)["F"]; b = r.force_field(name, dt, t)["F"]
+        assert rel_err(a, b) < 1e-12, (variant, name, dt, t)

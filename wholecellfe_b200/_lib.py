@@ -16,6 +16,7 @@ WIDTH = {"x": 3, "V": 3, "A": 3, "ea": 6, "cA": 1, "cB": 1, "cC": 1, "fa_u": 3, 
 DISCRETE = {"loc_bond": 0, "loc_force_cnt": 1, "loc_force_first": 2, "ap_fire": 3, "fa_reset": 4, "cc_clamp": 5}
 FORCE_FIELDS = {"Res_cell": 0, "F_FA": 1, "F_AP": 2, "F_bend": 3, "F_area": 4, "Res_subs": 5, "F_FA_subs": 6}
 RNG_GLIBC_REPLAY, RNG_PHILOX = 0, 1
+DORMANT = {"Res_Adif": 0, "Res_Cdif": 1, "F_pressure": 2, "F_sphere": 3}      # WCFE_DORMANT_*
 DRIVERS = {"explicit": 0, "biaxial": 1, "uniaxial": 2, "offbiaxial": 3, "bulgetest": 4}      # WCFE_DRV_*
 
 # every symbol include/wcfe.h declares
@@ -24,7 +25,7 @@ SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_param
            "wcfe_rng_skip", "wcfe_set_profile", "wcfe_get_kernel_ms", "wcfe_set_force_general", "wcfe_get_path_info",
            "wcfe_predict", "wcfe_commit", "wcfe_update", "wcfe_update_cell", "wcfe_update_subs", "wcfe_driver_velocities", "wcfe_driver_velocities_kind",
            "wcfe_mark_positions_committed", "wcfe_step_n", "wcfe_step_n_async", "wcfe_step_n_roundtrip", "wcfe_get_diagnostics",
-           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_device_ptr", "wcfe_sync", "wcfe_selftest_quotient", "wcfe_grid_refreshes",
+           "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_dormant_field", "wcfe_device_ptr", "wcfe_sync", "wcfe_selftest_quotient", "wcfe_grid_refreshes",
            "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed", "wcfe_set_roundtrip_mode",
            "wcfe_halo_info_get", "wcfe_halo_connect", "wcfe_halo_disconnect", "wcfe_cell_halo_info_get", "wcfe_cell_halo_connect", "wcfe_cell_halo_disconnect",
            "wcfe_strip_partition", "wcfe_strip_sizes", "wcfe_strip_mesh", "wcfe_strip_halo", "wcfe_strip_free"]
@@ -110,6 +111,7 @@ def load():
     L.wcfe_kernel_launches.argtypes = [vp]; L.wcfe_kernel_launches.restype = C.c_longlong
     L.wcfe_last_step_ms.argtypes = [vp]; L.wcfe_last_step_ms.restype = C.c_double
     L.wcfe_force_field.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp]
+    L.wcfe_dormant_field.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp]
     L.wcfe_device_ptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
     L.wcfe_sync.argtypes = [vp]
     L.wcfe_grid_refreshes.argtypes = [vp]; L.wcfe_grid_refreshes.restype = C.c_longlong

@@ -161,6 +161,7 @@ struct wcfe_ctx {
     bool have_predict[2] = {false, false};
     double drv_dt[2] = {-1.0, -1.0};      // dt of the last driver call per surface (wcfe_predict / wcfe_driver_velocities): V_hlf = V + drv_dt/2 A (UL:118, :295); < 0: the step's dt
     int drv_kind[2] = {WCFE_DRV_EXPLICIT, WCFE_DRV_BIAXIAL};   // driver of the last driver call per surface (wcfe_driver_velocities_kind); back to these after every update
+    DevBuf<double> d_dormant;             // output of k_dormant
     DevBuf<double> d_vh_subs;             // V_hlf (AoS) of a substrate driver other than _Biaxial, read by k_subs_vhalf after the next substrate update
     size_t vh_subs_n = 0;
     bool tape_busy = false;               // an async step_n may still be reading the pinned RNG tape
@@ -1249,7 +1250,7 @@ int wcfe_destroy(wcfe_ctx *c) {
     }
     c->g_ptr.release(); c->g_items.release(); c->b_head.release(); c->b_items.release(); c->b_node_epoch.release(); c->cell_done.release();
     c->d_flags.release(); c->d_loc_bond.release(); c->d_loc_cnt.release(); c->d_loc_first.release(); c->d_ap_fire.release(); c->d_err.release(); c->d_loc_cache.release();
-    c->d_kb.release(); c->d_seeds.release(); c->big_count.release(); c->big_list.release(); c->b_sums.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_vh_subs.release(); c->d_aos.release();
+    c->d_kb.release(); c->d_seeds.release(); c->big_count.release(); c->big_list.release(); c->b_sums.release(); c->d_partials.release(); c->d_diag.release(); c->d_tape.release(); c->d_drv.release(); c->d_vh_subs.release(); c->d_dormant.release(); c->d_aos.release();
     if (c->h_tape) cudaFreeHost(c->h_tape);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
@@ -1913,6 +1914,26 @@ int wcfe_force_field(wcfe_ctx *c, int which, double dt, double t_curr, double *o
     if (mm) { if ((rc = get_field(c, s.g_mm.p, mm, s.nn, s.np, 1))) return rc; }
     if (res_ea) { if ((rc = get_field(c, s.g_rea.p, res_ea, s.nn, s.np, 6))) return rc; }
     return WCFE_OK;
+}
+
+/* dormant physics of the cell on the current device state (include/wcfe.h); diagnostic, outside the step */
+int wcfe_dormant_field(wcfe_ctx *c, int which, double dt, double t_curr, double *out) {
+    int rc = ready(c);
+    if (rc) return rc;
+    if (!out || which < WCFE_DORMANT_RES_ADIF || which > WCFE_DORMANT_SPHERE) return fail(c, WCFE_ERR_ARG, "dormant_field: bad arguments");
+    NO_BATCH(c, "dormant_field");
+    CK(cudaSetDevice(c->device));
+    Surface &cs = c->s[WCFE_CELL];
+    const int w = which >= WCFE_DORMANT_PRESSURE ? 3 : 1;
+    if (c->d_dormant.n < 3 * (size_t)cs.np) CK(c->d_dormant.alloc(3 * (size_t)cs.np));
+    double pres = 2000.0;                                   // UL:1767-1778
+    if (t_curr < 1) pres = 2000.0 * t_curr;
+    if (t_curr > 2) pres = 2000.0 * (3 - t_curr);
+    if (t_curr > 3) pres = 0.0;
+    k_dormant<<<(cs.nn + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(view(cs), cs.cA.p, cs.cC.p, which, dt, pres, c->prm.thick, c->d_dormant.p);
+    c->launches++;
+    CK(cudaGetLastError());
+    return get_field(c, c->d_dormant.p, out, cs.nn, cs.np, w);
 }
 
 /* raw device pointer of a state field (SoA: component q of node i at ptr[q*pitch + i]); valid until the next step for the

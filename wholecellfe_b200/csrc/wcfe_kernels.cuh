@@ -232,6 +232,71 @@ __global__ void __launch_bounds__(kBlock) k_subs_vhalf(int nn, int np, double *_
     for (int c = 0; c < 3; c++) V[c * np + i] = fma(ddt, A[c * np + i], Vh[3 * i + c]);
 }
 
+// ---- dormant physics of the cell: fields the reference defines and whose calls / consumers are commented out.
+//      One thread per node, one-ring gather in ascending element order (the order the reference's serial scatter-add produces),
+//      on the CURRENT device state (x, X = start-of-step positions, c_A, c_C).  Diagnostic kernels, not part of the step.
+//      which 0 / 1: diffusion residuals Res_Adif / Res_Cdif (evalElementRe UL:833-842, :915-925; assembled calculateRes UL:702-704;
+//                   consumers commented out UL:617-618), out[np]
+//      which 2:     calculatePressureForce UL:1765-1816 (call commented out UL:577): -pres (MM / 0.1) n, MM the lumped mass of
+//                   calculateRes (one third of the one-ring reference areas times thick), out[3*np] SoA
+//      which 3:     calculateConstraintForce UL:1178-1194 (call commented out UL:551), out[3*np] SoA
+__global__ void __launch_bounds__(kBlock) k_dormant(SurfView s, const double *__restrict__ cA, const double *__restrict__ cC, int which,
+                                                    double dt, double pres, double thick, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.nn) return;
+    const int np = s.np;
+    if (which == 3) {
+        const double x0 = s.x[i], x1 = s.x[np + i], x2 = s.x[2 * np + i];
+        const double dist = sqrt(x0 * x0 + x1 * x1 + x2 * x2), f = 4000.0 * (350.0 - dist);
+        out[i] = f * (x0 / dist); out[np + i] = f * (x1 / dist); out[2 * np + i] = f * (x2 / dist);
+        return;
+    }
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, asum = 0.0, mm = 0.0;
+    const double *conc = which == 0 ? cA : cC;
+    const double D = which == 0 ? 1.0 : 1e-10;                                   // UL:919-920
+    for (int r = s.ring_ptr[i]; r < s.ring_ptr[i + 1]; r++) {
+        const int e = s.ring[r] >> 2, slot = s.ring[r] & 3;
+        const int n0 = s.tri[e], n1 = s.tri[s.nep + e], n2 = s.tri[2 * s.nep + e];
+        double G1[3], G2[3], g1[3], g2[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            G1[c] = s.X[c * np + n1] - s.X[c * np + n0]; G2[c] = s.X[c * np + n2] - s.X[c * np + n0];
+            g1[c] = s.x[c * np + n1] - s.x[c * np + n0]; g2[c] = s.x[c * np + n2] - s.x[c * np + n0];
+        }
+        const double Gx[3] = {G1[1] * G2[2] - G1[2] * G2[1], G1[2] * G2[0] - G1[0] * G2[2], G1[0] * G2[1] - G1[1] * G2[0]};
+        const double gx[3] = {g1[1] * g2[2] - g1[2] * g2[1], g1[2] * g2[0] - g1[0] * g2[2], g1[0] * g2[1] - g1[1] * g2[0]};
+        const double nG = sqrt(Gx[0] * Gx[0] + Gx[1] * Gx[1] + Gx[2] * Gx[2]), ng = sqrt(gx[0] * gx[0] + gx[1] * gx[1] + gx[2] * gx[2]);
+        if (which == 2) {
+            acc0 += 0.5 * gx[0]; acc1 += 0.5 * gx[1]; acc2 += 0.5 * gx[2];       // area_ti * unit normal_ti (UL:1799-1803)
+            asum += 0.5 * ng;
+            mm += (1. / 3.) * nG / 2.0 * thick;                                   // UL:913
+            continue;
+        }
+        // rows 0 and 1 of [g1 g2 n]^-1 (UL:834-836): the reciprocal basis g2 x n / det, n x g1 / det
+        const double n[3] = {gx[0] / ng, gx[1] / ng, gx[2] / ng};
+        const double c0[3] = {g2[1] * n[2] - g2[2] * n[1], g2[2] * n[0] - g2[0] * n[2], g2[0] * n[1] - g2[1] * n[0]};
+        const double c1[3] = {n[1] * g1[2] - n[2] * g1[1], n[2] * g1[0] - n[0] * g1[2], n[0] * g1[1] - n[1] * g1[0]};
+        const double det = g1[0] * c0[0] + g1[1] * c0[1] + g1[2] * c0[2];
+        const double a0 = conc[n0], a1 = conc[n1], a2 = conc[n2];
+        double dot = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double r0 = c0[c] / det, r1 = c1[c] / det;
+            const double grad = a0 * r0 + a1 * r1 + a2 * (-r0 - r1);              // UL:839-840
+            const double gN = slot == 0 ? r0 : (slot == 1 ? r1 : -r0 - r1);         // UL:917
+            dot += grad * gN;
+        }
+        const double mean = (1. / 3.) * (a0 + a1 + a2);                           // UL:841-842
+        acc0 += (mean * (1. / 3.) - dt * D * dot) * nG / 2.0 * thick;             // UL:924-925
+    }
+    if (which == 2) {
+        // the reference normalises the area-weighted sum twice (UL:1805-1806): the direction is that of the sum
+        const double l = sqrt(acc0 * acc0 + acc1 * acc1 + acc2 * acc2), f = -pres * (mm / 0.1);
+        (void)asum;
+        out[i] = f * (acc0 / l); out[np + i] = f * (acc1 / l); out[2 * np + i] = f * (acc2 / l);
+    } else out[i] = acc0;
+}
+
 // ---- point location of one anchor in the substrate -------------------------------------------------------
 // visits candidates in ascending triangle index; calls f(tri, A[3], A_tri) for every containing triangle
 template <class F>

@@ -215,6 +215,14 @@ class ULSim:
         self._ck(self.L.wcfe_force_field(self.h, w, 0.0, 0.0, _d(out), _d(mm), _d(rea)))
         return {"F": out, "MM": mm, "Res_ea": rea}
 
+    def dormant_field(self, which, dt, t_curr):
+        """Res_Adif / Res_Cdif ([nn]) or F_pressure / F_sphere ([nn, 3]) of the cell on the current device state: the reference's
+        dormant physics (include/wcfe.h wcfe_dormant_field)."""
+        w = B.DORMANT[which]
+        out = np.empty(self.nn[B.CELL] if w < 2 else (self.nn[B.CELL], 3))
+        self._ck(self.L.wcfe_dormant_field(self.h, w, dt, t_curr, _d(out)))
+        return out
+
     def device_ptr(self, surface, field):
         """(address, pitch) of a SoA state field on the device: component q of node i lives at address + 8*(q*pitch + i)."""
         ptr = C.c_void_p()
