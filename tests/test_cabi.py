@@ -85,3 +85,18 @@ def test_environment_switches_are_documented():
     table = doc[doc.index("Environment switches"):]
     documented = set(re.findall(r"`(WCFE_[A-Z0-9_]+)", table))
     assert read == documented, (sorted(read - documented), sorted(documented - read))
+
+
+def test_header_constants_match_the_python_tables():
+    """the enumerations of include/wcfe.h and the tables the ctypes binding / the oracle bindings use are the same numbers"""
+    from oracle import oracle as O, refrun as R
+    hdr = open(os.path.join(ROOT, "include", "wcfe.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(WCFE_[A-Z0-9_]+)\s+\(?(-?\d+)\)?", hdr)}
+    for name, v in B.DRIVERS.items():
+        assert defs["WCFE_DRV_" + name.upper()] == v == O.DRIVERS[name] == R.DRIVERS[name], name
+    for name, v in B.DORMANT.items():
+        assert defs["WCFE_DORMANT_" + name.upper().replace("F_", "")] == v, name
+    for name, v in B.FIELDS.items():
+        key = {"x": "X", "V": "V", "A": "A", "ea": "EA", "cA": "CA", "cB": "CB", "cC": "CC", "fa_u": "FAU", "X_prev": "XPREV"}[name]
+        assert defs["WCFE_F_" + key] == v, name
+    assert defs["WCFE_ERR_ARG"] == B.ERR_ARG and defs["WCFE_ERR_CUDA"] == B.ERR_CUDA and defs["WCFE_CELL"] == B.CELL and defs["WCFE_SUBS"] == B.SUBS
