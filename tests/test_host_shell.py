@@ -108,3 +108,61 @@ def test_vtk_frames_byte_identical_to_the_reference_writers(host, meshes, tmp_pa
     assert got_s == want_s
     assert got_c == want_c      # theta_e in Eigen's own operation order (3x3 inverse by cofactors, then its determinant): every digit
     assert host.cellbp_write_vtk_cell(b"/nonexistent/dir/c.vtk", C.c_double(t), len(x), d(x), len(tc32), tc32.ctypes.data_as(_ip), d(cA), d(cC), d(fa), d(ea), C.c_double(kint)) != 0
+
+
+REFAPP = os.path.join(ROOT, "oracle", "_ref", "cellBP_ref_k1")
+
+
+@pytest.mark.skipif(not os.path.exists(REFAPP), reason="oracle/_ref/cellBP_ref_k1 not built here (oracle/build_app.sh)")
+def test_shipped_example_with_eltopo_on_equals_the_eltopo_free_run_for_k1(host, meshes, tmp_path):
+    """What `cellbp_gpu --no-eltopo` rests on: the UNMODIFIED reference application run on the shipped example with the shipped
+    surftrack_parameters (perform_improvement 1, allow_topology_changes 1, collision_safety 1: El Topo fully on) writes, for k1, the
+    same frames byte for byte as the El-Topo-free step sequence -- El Topo never touches that mesh (296 / 542 for all 800
+    steps, actual_dt == dt).  20 frames = 160 steps here; all 100 frames were compared when the flag was added."""
+    from oracle.oracle import OracleSim
+    xc, tc, xs, ts = meshes
+    (tmp_path / "scripts").mkdir()
+    write_ecomsol(str(tmp_path / "scripts" / "disk.txt"), xc, tc); write_ecomsol(str(tmp_path / "scripts" / "subs.txt"), xs, ts)
+    tpl = open(os.path.join(GOLDEN, "reference_script_template.txt")).read()
+    (tmp_path / "cell.txt").write_text(tpl.format(end_t=0.8, max_edge=2, improve=1, topo=1, collide=1, mesh="scripts/disk.txt"))
+    (tmp_path / "subs.txt").write_text(tpl.format(end_t=0.8, max_edge=8, improve=1, topo=1, collide=1, mesh="scripts/subs.txt"))
+    (tmp_path / "out").mkdir()
+    r = subprocess.run([REFAPP, "cell.txt", "subs.txt", "out"], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    run = tmp_path / "out" / "cell_subs_example" / "run0001"
+    o = OracleSim("k1", xc, tc, xs, ts); o.srand(1)
+    tc32 = np.ascontiguousarray(tc, dtype=np.int32)
+    t = 0.0
+    for f in range(20):
+        cur = 0.0
+        while not (cur >= 0.04 - 1e-7):                         # framestepper.h:14-76
+            dt = 0.04 - cur if cur + 0.005 > 0.04 else 0.005
+            o.step(dt, t); t += dt; cur += dt
+        if f in (0, 7, 19):
+            x = o.get(0, "x"); cA = o.get(0, "cA"); cC = o.get(0, "cC"); fa = o.get(0, "fa_u"); ea = o.get(0, "ea")
+            mine = str(tmp_path / ("mine%d.vtk" % f))
+            assert host.cellbp_write_vtk_cell(mine.encode(), C.c_double(t), len(x), d(x), len(tc32), tc32.ctypes.data_as(_ip), d(cA), d(cC), d(fa), d(ea), C.c_double(1000.0)) == 0
+            assert open(mine, "rb").read() == open(run / ("cell_frame%04d.vtk" % f), "rb").read(), f
+
+
+def test_shell_accepts_eltopo_scripts_only_when_told_to(meshes, tmp_path):
+    """cellbp_gpu refuses a script that leaves El Topo's switches on unless --no-eltopo is given; then it says what it skips.  Without a
+    GPU (here) the accepted run must stop at wcfe_create with the no-CPU-fallback message, not compute anything."""
+    exe = os.path.join(HOST, "cellbp_gpu")
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    xc, tc, xs, ts = meshes
+    write_ecomsol(str(tmp_path / "disk.txt"), xc, tc); write_ecomsol(str(tmp_path / "subs.txt"), xs, ts)
+    tpl = open(os.path.join(GOLDEN, "reference_script_template.txt")).read()
+    (tmp_path / "cell.txt").write_text(tpl.format(end_t=0.04, max_edge=2, improve=1, topo=1, collide=1, mesh=str(tmp_path / "disk.txt")))
+    (tmp_path / "subs_script.txt").write_text(tpl.format(end_t=0.04, max_edge=8, improve=1, topo=1, collide=1, mesh=str(tmp_path / "subs.txt")))
+    (tmp_path / "out").mkdir()
+    args = [exe, str(tmp_path / "cell.txt"), str(tmp_path / "subs_script.txt"), str(tmp_path / "out"), "--quiet"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "does not link El Topo" in r.stderr and "--no-eltopo" in r.stderr
+    r = subprocess.run(args + ["--no-eltopo"], capture_output=True, text=True, timeout=300)
+    assert "does not link El Topo" not in r.stderr and r.stderr.count("SKIPPED") == 2
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "8 steps" in r.stdout
+    else:
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr

@@ -1,11 +1,15 @@
 // cellbp_gpu -- stand-alone host shell with the reference's command line, script format and .vtk frame output
 // (cellBP/main.cpp:636-740, :427-489; scriptinit.cpp; iomesh.cpp), driving the UL step on the GPU through the C ABI.
 //
-//   cellbp_gpu <scriptfile_cell> <scriptfile_subs> [outputbasedirectory] [--variant k1|k31|kMD] [--device N] [--quiet]
+//   cellbp_gpu <scriptfile_cell> <scriptfile_subs> [outputbasedirectory] [--variant k1|k31|kMD] [--device N] [--quiet] [--no-eltopo]
 //
 // El Topo is not linked: the scripts must switch remeshing and collision handling off (perform_improvement 0,
 // allow_topology_changes 0, collision_safety 0; scriptinit.cpp:57-65) -- with those flags the reference's step is exactly
 // the El-Topo-free path this shell runs.  Use the adapter to keep El Topo in the loop.
+// --no-eltopo accepts scripts that leave those switches on (the shipped scripts/cell_example.txt does) and runs them WITHOUT mesh
+// improvement and collision handling, saying so: the result is the reference's as long as El Topo would have left the mesh alone --
+// which it does for k1 on the shipped example, all 100 frames byte-identical (tests/test_host_shell.py) -- and is not otherwise
+// (k31 / kMD remesh from step ~300 on).
 #include "../../../include/wcfe.h"
 #include "cellbp_io.h"
 #include "cellbp_script.h"
@@ -62,12 +66,13 @@ void ck(wcfe_ctx *c, int rc, const char *what) {
 int main(int argc, char **argv) {
     std::cout << "\nCellBP (GPU UL step): cell biophysics on B200\n--------------------------------------------------\n\n";
     std::vector<std::string> pos;
-    int variant = WCFE_K1, device = 0; bool quiet = false;
+    int variant = WCFE_K1, device = 0; bool quiet = false, no_eltopo = false;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         if (a == "--variant" && i + 1 < argc) { const std::string v = argv[++i]; variant = v == "k31" ? WCFE_K31 : (v == "kMD" ? WCFE_KMD : WCFE_K1); }
         else if (a == "--device" && i + 1 < argc) device = std::atoi(argv[++i]);
         else if (a == "--quiet") quiet = true;
+        else if (a == "--no-eltopo") no_eltopo = true;
         else pos.push_back(a);
     }
     if (pos.size() < 2) {
@@ -78,9 +83,13 @@ int main(int argc, char **argv) {
     try {
         const cellbp::ScriptInfo sc = cellbp::read_script(pos[0]), ss = cellbp::read_script(pos[1]);
         for (const cellbp::ScriptInfo *s : {&sc, &ss})
-            if (s->perform_improvement || s->allow_topology_changes || s->collision_safety)
-                throw std::runtime_error("this shell does not link El Topo: set perform_improvement 0, allow_topology_changes 0, collision_safety 0 "
-                                         "in surftrack_parameters of both scripts (or use the adapter of INTEGRATION.md)");
+            if (s->perform_improvement || s->allow_topology_changes || s->collision_safety) {
+                if (!no_eltopo)
+                    throw std::runtime_error("this shell does not link El Topo: set perform_improvement 0, allow_topology_changes 0, collision_safety 0 "
+                                             "in surftrack_parameters of both scripts, pass --no-eltopo to run them without it, or use the adapter of INTEGRATION.md");
+                std::fprintf(stderr, "cellbp_gpu: --no-eltopo: %s asks for mesh improvement / topology changes / collision handling; El Topo is not linked, "
+                                     "they are SKIPPED (same frames as the reference only while El Topo would leave the mesh alone)\n", s == &sc ? pos[0].c_str() : pos[1].c_str());
+            }
         std::vector<double> xc, xs; std::vector<int> tc, ts;
         cellbp::read_ecomsol(sc.mesh_path, xc, tc);
         cellbp::read_ecomsol(ss.mesh_path, xs, ts);
