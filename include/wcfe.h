@@ -206,7 +206,9 @@ double wcfe_last_step_ms(wcfe_ctx *c);
  * may be NULL.  Diagnostic entry point for the force-level parity gate (1e-10). */
 int wcfe_force_field(wcfe_ctx *c, int which, double dt, double t_curr, double *out, double *mm, double *res_ea);
 /* Dormant physics of the cell: fields the reference defines and whose calls / consumers are commented out, computed on the current
- * device state (x, start-of-step X, c_A, c_C); diagnostic entry point outside the step, general (3-D) arithmetic.
+ * device state (x, start-of-step X, c_A, c_C); diagnostic entry point outside the step, general (3-D) arithmetic.  For a context that
+ * holds the whole cell (single GPU, or a partitioned substrate with the cell replicated); with a partitioned CELL a rank's rows outside
+ * its own patches are not current and neither are these fields there.  WCFE_ERR_UNSUPPORTED on a batched context.
  *   WCFE_DORMANT_RES_ADIF / _RES_CDIF  diffusion residuals of free / bound integrins (evalElementRe UL:833-842, :915-925, assembled in
  *                                      calculateRes UL:702-704; consumers commented out UL:617-618); out[nn]
  *   WCFE_DORMANT_PRESSURE              calculatePressureForce UL:1765-1816 (bulge-test follower load, call commented out UL:577); out[3*nn]
