@@ -1025,6 +1025,7 @@ subs_half:
     ss.ea_cur ^= 1;
     c->step++;
     if (!joined) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));      // join: later work on the main stream sees the finished boundary
+    c->drv_kind[WCFE_CELL] = WCFE_DRV_EXPLICIT; c->drv_kind[WCFE_SUBS] = WCFE_DRV_BIAXIAL;      // a driver choice lasts for one step, whichever entry point ran it
     CK(cudaGetLastError());
     return WCFE_OK;
 }
