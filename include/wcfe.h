@@ -6,7 +6,8 @@
  * advance_sim() (main.cpp:168-418).  This header is the flat C surface a binding would target (same
  * style as El Topo's own C API, eltopo3d/eltopo.h:150-268: flattened `const double* xyz[3N]`,
  * `const int* tri[3M]`, caller-owned buffers, int status codes, no exceptions).  The C++ adapter
- * wholecellfe_b200/csrc/ul_adapter.cpp defines the reference's five C++ symbols on top of it so that
+ * wholecellfe_b200/csrc/ul_adapter.cpp defines the reference's C++ symbols (the five main.cpp calls and the three drivers it keeps
+ * commented out) on top of it so that
  * the unmodified reference main.cpp links against libwcfe instead of UL_growth_explicit.o
  * (INTEGRATION.md).
  *
@@ -69,7 +70,7 @@ typedef struct wcfe_params {
     int law;             /* 0 linear integrin spring, 1 piecewise-linear MD table (kMD :1204-1214) */
     double kint_force;   /* kint inside updateForces_Explicit (:458,:559): 1000 / 31000 */
     double kint_bond;    /* kint main.cpp hands to updateFA (main.cpp:350-354): 1000 / 31000 / -1 */
-    double subs_scale;   /* the literal `0*` of main.cpp:299; only 0 is implemented on the GPU */
+    double subs_scale;   /* the literal `0*` of main.cpp:299 (0: frozen substrate, the planar fast path; != 0: moving substrate, general kernels, wcfe_step_n only) */
     double mu_cell, mu_subs;                  /* :724,:727 */
     double t_act_rate, t_act_max, t_act_t1;   /* :744-756  t<2 ? 200 t : 400 */
     double thick, kappa;                      /* :767,:871  (kappa must be 0.5 on the GPU: the a0 term vanishes) */
@@ -127,8 +128,9 @@ int wcfe_set_rng(wcfe_ctx *c, int mode, unsigned int seed);
 /* resume a glibc replay mid-run (checkpoint/restart): discard n_draws values (one per boundary vertex per step) */
 int wcfe_rng_skip(wcfe_ctx *c, long long n_draws);
 int wcfe_set_debug(wcfe_ctx *c, int on);   /* also record WCFE_D_LOC_BOND (extra point location per step) and force fields */
-/* per-kernel CUDA-event timing of wcfe_step_n (events on the launching stream); ids: 0 k_predict_cell 1 k_bond
- * 2 k_cell_node 3 k_boundary_finish 4 k_subs_node.  ms8 = accumulated ms, count8 = launches timed. */
+/* per-kernel CUDA-event timing of wcfe_step_n (events on the launching stream; switches the PDL chain off while on); slots: 0 predictor
+ * (k_predict_cell; fused into the cell kernel on the planar path) 1 k_bond 2 cell kernel (k_cell_patch / k_cell_node) 3 boundary finish
+ * 4 substrate kernel (k_subs_ring / k_subs_patch / k_subs_node) 5 k_bucket_reduce.  ms8 = accumulated ms, count8 = launches timed. */
 int wcfe_set_profile(wcfe_ctx *c, int on);
 /* test hook: run the general 3-D (node-centric) kernels even when the state is planar */
 int wcfe_set_force_general(wcfe_ctx *c, int on);
@@ -227,10 +229,10 @@ int wcfe_sync(wcfe_ctx *c);
 /* Device self test: n pseudo-random operand pairs (zero numerators, both signs, x / 3 included) through the division-free correctly
  * rounded quotients the kernels use (wcfe_math.cuh recip_of / quot) and through the compiler's IEEE `/`; *mismatch = results that
  * differ in any bit (the sign of a zero quotient excepted).  Must be 0. */
+int wcfe_selftest_quotient(int device, long long n, unsigned int seed, long long *mismatch);
 /* moving substrate (wcfe_params::subs_scale != 0): how often the point-location grid has been rebuilt because a substrate node had
  * drifted beyond half the grid's padding from where the grid was built (checked after every step of wcfe_step_n) */
 long long wcfe_grid_refreshes(wcfe_ctx *c);
-int wcfe_selftest_quotient(int device, long long n, unsigned int seed, long long *mismatch);
 
 /* ---- one mesh over several GPUs (BASELINE configs[3]: "element-partitioned over 2/4/8 B200 with ... halo exchange"; the reference
  * itself has no such mode).  Each rank's context holds ONE STRIP of the substrate -- its owned nodes plus a one-ring of
