@@ -315,6 +315,24 @@ int wcfe_strip_sizes(const wcfe_strip *s, int *n_local, int *n_elem, int *n_owne
 int wcfe_strip_mesh(const wcfe_strip *s, int *local_nodes, int *tri_local, int *elem_gid, int *owned_local, int *ghost_local);
 int wcfe_strip_halo(const wcfe_strip *s, int *peer_rank, int *my_slot_at_peer, int *rows_from_peer, int *export_node, int *export_peer, int *export_row);
 int wcfe_strip_free(wcfe_strip *s);
+/* owner[nn]: the rank that owns every node of the uncut mesh (the strips' node -> rank map) */
+int wcfe_strip_owner(const wcfe_strip *s, int *owner);
+
+/* Host-only as well: the arguments of wcfe_cell_halo_connect for `rank` -- which 128-node cell patches it computes (every patch that
+ * can drop an anchor, at most `margin` from its node, into one of the rank's substrate triangles), which of them it owns (the lowest
+ * rank owning substrate under the patch's centroid), the rows it pushes to and receives from the other ranks -- for ANY partition of
+ * the substrate given as subs_owner[nn_subs] (strips: wcfe_strip_owner).  world <= 32.  Same lists as wholecellfe_b200/partition.py
+ * cell_partition + cell_connect_plan.
+ *   sizes: n_peers (= world - 1), n_patches, n_export, n_import
+ *   lists: peer_rank, my_slot_at_peer [n_peers]; patch_list, patch_owned [n_patches]; export_node, export_peer [n_export];
+ *          import_node [n_import] */
+typedef struct wcfe_cell_plan wcfe_cell_plan;
+int wcfe_cell_partition(int world, int rank, int nn_subs, const double *subs_xyz, const int *subs_owner,
+                        int nn_cell, const double *cell_xyz, int ne_cell, const int *cell_tri, double margin, wcfe_cell_plan **out);
+int wcfe_cell_plan_sizes(const wcfe_cell_plan *p, int *n_peers, int *n_patches, int *n_export, int *n_import);
+int wcfe_cell_plan_lists(const wcfe_cell_plan *p, int *peer_rank, int *my_slot_at_peer, int *patch_list, int *patch_owned, int *export_node,
+                         int *export_peer, int *import_node);
+int wcfe_cell_plan_free(wcfe_cell_plan *p);
 
 #ifdef __cplusplus
 }

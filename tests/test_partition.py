@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 from wholecellfe_b200.meshgen import square_mesh, disk_mesh
 from wholecellfe_b200.partition import (strip_partition, sector_partition, make_partition, cell_partition, cell_connect_plan, exchange_rows,
-                                        connect_plan, neighbours, cell_weights, native_strip, PATCH)
+                                        connect_plan, neighbours, cell_weights, native_strip, native_cell_plan, PATCH)
 
 
 def _free_port():
@@ -158,6 +158,48 @@ def test_c_abi_strip_partition_equals_python(world, balanced):
             assert np.array_equal(nat["ghost_local"], gh)
             assert list(nat["peer_rank"]) == nb and list(nat["my_slot_at_peer"]) == slot and list(nat["rows_from_peer"]) == rows
             assert np.array_equal(nat["export_node"], en) and np.array_equal(nat["export_peer"], ep) and np.array_equal(nat["export_row"], er)
+
+
+@pytest.mark.parametrize("shape", ["strips", "sectors"])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_c_abi_cell_partition_equals_python(world, shape):
+    """wcfe_cell_partition (host-only C++ in libwcfe.so) returns, list for list, what partition.py cell_partition +
+    cell_connect_plan compute -- for strips (owner map from wcfe_strip_owner) and for sectors (owner map handed in), on a cell that
+    covers part of the substrate (ranks far from it get their nearest patch), with and without cost balancing."""
+    import ctypes as C
+    from wholecellfe_b200 import _lib as B
+    from wholecellfe_b200.build import build
+    build()
+    for (nc, ns, shift, margin, balance) in ((6000, 120, (0.0, 0.0), 0.15, True), (3001, 64, (17.3, -9.1), 0.4, False)):
+        xc, tc = disk_mesh(nc); xs, ts = square_mesh(ns)
+        xc = xc + np.array([shift[0], shift[1], 0.0])
+        parts = make_partition(xs, ts, world, xc, balance, "partitioned", shape)
+        owner = np.zeros(len(xs), dtype=np.int32)
+        for r, p in enumerate(parts):
+            owner[p.owned] = r
+        if shape == "strips" and not balance:          # the strips' own node -> rank map out of the C ABI
+            L = B.load()
+            x64 = np.ascontiguousarray(xs, dtype=np.float64); t32 = np.ascontiguousarray(ts, dtype=np.int32)
+            h = C.c_void_p()
+            assert L.wcfe_strip_partition(len(xs), x64.ctypes.data_as(B._dp), len(ts), t32.ctypes.data_as(B._ip), None, world, 0, C.byref(h)) == 0
+            nat_owner = np.zeros(len(xs), dtype=np.int32)
+            assert L.wcfe_strip_owner(h, nat_owner.ctypes.data_as(B._ip)) == 0 and L.wcfe_strip_free(h) == 0
+            assert np.array_equal(nat_owner, owner)
+        cps = cell_partition(parts, xc, tc, xs, margin)
+        for r in range(world):
+            peers, slot, pl, po, en, ep, imp = cell_connect_plan(cps, r)
+            nat = native_cell_plan(xs, owner, xc, tc, world, r, margin)
+            assert list(nat["peer_rank"]) == peers and list(nat["my_slot_at_peer"]) == slot, (world, shape, r)
+            assert np.array_equal(nat["patch_list"], pl) and np.array_equal(nat["patch_owned"], po), (world, shape, r)
+            assert np.array_equal(nat["export_node"], en) and np.array_equal(nat["export_peer"], ep), (world, shape, r)
+            assert np.array_equal(nat["import_node"], imp), (world, shape, r)
+    # argument checks
+    with pytest.raises(ValueError):
+        native_cell_plan(xs, owner, xc, tc, world, world, 0.15)                 # rank outside [0, world)
+    with pytest.raises(ValueError):
+        native_cell_plan(xs, owner + world, xc, tc, world, 0, 0.15)             # an owner outside [0, world)
+    with pytest.raises(ValueError):
+        native_cell_plan(xs, owner, xc, tc, 33, 0, 0.15)                        # rank sets are 32-bit masks
 
 
 def test_c_abi_strip_partition_rejects_bad_arguments():

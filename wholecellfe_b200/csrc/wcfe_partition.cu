@@ -12,6 +12,7 @@
 //     nodal sum is formed in the same order as on a single GPU and the owned rows of all ranks tile the single-GPU result bit for bit.
 #include "../../include/wcfe.h"
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -25,6 +26,11 @@ struct wcfe_strip {
     std::vector<int> ghost_local;      // local ids of the ghost nodes
     std::vector<int> peer_rank, my_slot_at_peer, rows_from_peer;
     std::vector<int> export_node, export_peer, export_row;
+    std::vector<int> owner;            // [nn global] rank that owns every node of the uncut mesh
+};
+
+struct wcfe_cell_plan {
+    std::vector<int> peer_rank, my_slot_at_peer, patch_list, patch_owned, export_node, export_peer, import_node;
 };
 
 namespace {
@@ -99,6 +105,7 @@ int wcfe_strip_partition(int nn, const double *xyz, int ne, const int *tri, cons
     const Part &me = parts[(size_t)rank];
     wcfe_strip *s = new wcfe_strip;
     s->rank = rank; s->world = world;
+    s->owner = owner;
     s->local_nodes = me.local_nodes;
     s->elem_gid = elems;                                 // ascending: elements were visited in order
     s->tri_local.resize(3 * elems.size());
@@ -151,6 +158,169 @@ int wcfe_strip_halo(const wcfe_strip *s, int *peer_rank, int *my_slot_at_peer, i
 int wcfe_strip_free(wcfe_strip *s) {
     if (!s) return WCFE_ERR_ARG;
     delete s;
+    return WCFE_OK;
+}
+
+int wcfe_strip_owner(const wcfe_strip *s, int *owner) {
+    if (!s || !owner) return WCFE_ERR_ARG;
+    put(s->owner, owner);
+    return WCFE_OK;
+}
+
+// ---- the CELL of a partitioned run: which 128-node patches a rank computes, owns, pushes and receives, for ANY partition of the
+// substrate given as a node -> rank map (strips: wcfe_strip_owner).  The lists wcfe_cell_halo_connect wants; the same rules, raster and
+// arithmetic as wholecellfe_b200/partition.py cell_partition + cell_connect_plan (tests/test_partition.py holds the two against each
+// other, list for list):
+//   * an anchor lies within `margin` of its cell node and a rank's local substrate triangles reach one edge length beyond its owned
+//     nodes, so a rank computes every patch with a node in a raster cell (size margin + 1.5 h, h the mean substrate spacing) that --
+//     after dilation by one cell -- holds a substrate node the rank owns; a patch on a cut is computed by every rank it touches;
+//   * a patch is OWNED by the lowest rank that owns substrate in the raster cell under the patch's centroid: that rank publishes the
+//     patch's area / centroid partial sums and pushes its rows to the ranks that read them as halo rows without computing them;
+//   * a rank with no patch at all takes the one nearest to its strip (every rank runs the step's kernels).
+namespace {
+// the summation order of numpy's float64 add (pairwise, blocks of 128 with eight accumulators): the centroids decide raster cells, and
+// the lists are meant to equal partition.py's bit for bit
+double pairwise_sum(const double *a, long long n) {
+    if (n < 8) { double r = 0.0; for (long long i = 0; i < n; i++) r += a[i]; return r; }
+    if (n <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; k++) r[k] = a[k];
+        long long i = 8;
+        for (; i < n - (n % 8); i += 8) for (int k = 0; k < 8; k++) r[k] += a[i + k];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    }
+    long long n2 = n / 2; n2 -= n2 % 8;
+    return pairwise_sum(a, n2) + pairwise_sum(a + n2, n - n2);
+}
+constexpr int kCellPatch = 128;      // owned nodes per cell patch (wcfe_patch.cuh kPatch)
+}   // namespace
+
+int wcfe_cell_partition(int world, int rank, int nn_subs, const double *subs_xyz, const int *subs_owner,
+                        int nn_cell, const double *cell_xyz, int ne_cell, const int *cell_tri, double margin, wcfe_cell_plan **out) {
+    if (!out) return WCFE_ERR_ARG;
+    *out = nullptr;
+    if (world < 1 || world > 32 || rank < 0 || rank >= world || nn_subs <= 0 || !subs_xyz || !subs_owner || nn_cell <= 0 || !cell_xyz ||
+        ne_cell <= 0 || !cell_tri || !(margin >= 0.0)) return WCFE_ERR_ARG;
+    for (int i = 0; i < nn_subs; i++) if (subs_owner[i] < 0 || subs_owner[i] >= world) return WCFE_ERR_ARG;
+    for (size_t q = 0; q < 3 * (size_t)ne_cell; q++) if (cell_tri[q] < 0 || cell_tri[q] >= nn_cell) return WCFE_ERR_ARG;
+    double xmin = subs_xyz[0], xmax = subs_xyz[0], ymin = subs_xyz[1], ymax = subs_xyz[1];
+    for (int i = 1; i < nn_subs; i++) {
+        xmin = std::min(xmin, subs_xyz[3 * (size_t)i]); xmax = std::max(xmax, subs_xyz[3 * (size_t)i]);
+        ymin = std::min(ymin, subs_xyz[3 * (size_t)i + 1]); ymax = std::max(ymax, subs_xyz[3 * (size_t)i + 1]);
+    }
+    const double h = std::sqrt((xmax - xmin) * (ymax - ymin) / (double)std::max(1, nn_subs));
+    const double g = margin + 1.5 * h;
+    if (!(g > 0.0)) return WCFE_ERR_ARG;
+    const long long nx = (long long)((xmax - xmin) / g) + 1, ny = (long long)((ymax - ymin) / g) + 1;
+    if (nx * ny > (1ll << 28)) return WCFE_ERR_ARG;
+    std::vector<unsigned int> mask((size_t)(nx * ny), 0u), dil;
+    for (int i = 0; i < nn_subs; i++) {
+        const long long ix = (long long)((subs_xyz[3 * (size_t)i] - xmin) / g), iy = (long long)((subs_xyz[3 * (size_t)i + 1] - ymin) / g);
+        mask[(size_t)(iy * nx + ix)] |= 1u << subs_owner[i];
+    }
+    dil = mask;
+    for (long long y = 0; y < ny; y++) for (long long x = 0; x < nx; x++) {
+        unsigned int m = 0;
+        for (long long dy = -1; dy <= 1; dy++) for (long long dx = -1; dx <= 1; dx++) {
+            const long long yy = y + dy, xx = x + dx;
+            if (yy >= 0 && yy < ny && xx >= 0 && xx < nx) m |= mask[(size_t)(yy * nx + xx)];
+        }
+        dil[(size_t)(y * nx + x)] = m;
+    }
+    auto cell_of = [&](double px, double py) {
+        long long ix = (long long)((px - xmin) / g), iy = (long long)((py - ymin) / g);
+        ix = std::min(std::max(ix, 0ll), nx - 1); iy = std::min(std::max(iy, 0ll), ny - 1);
+        return (size_t)(iy * nx + ix);
+    };
+    const int npatch = (nn_cell + kCellPatch - 1) / kCellPatch;
+    std::vector<unsigned int> pbits((size_t)npatch, 0u);
+    std::vector<double> cx((size_t)npatch), cy((size_t)npatch), col((size_t)kCellPatch);
+    std::vector<int> powner((size_t)npatch, 0);
+    for (int p = 0; p < npatch; p++) {
+        const int b = p * kCellPatch, e = std::min(nn_cell, b + kCellPatch), n = e - b;
+        for (int i = b; i < e; i++) pbits[(size_t)p] |= dil[cell_of(cell_xyz[3 * (size_t)i], cell_xyz[3 * (size_t)i + 1])];
+        for (int c = 0; c < 2; c++) {
+            for (int i = b; i < e; i++) col[(size_t)(i - b)] = cell_xyz[3 * (size_t)i + c];
+            const double sum = n > 1 ? col[0] + pairwise_sum(col.data() + 1, n - 1) : col[0];      // numpy add.reduceat: first element, then the rest
+            (c == 0 ? cx : cy)[(size_t)p] = sum / (double)n;
+        }
+        const size_t cc = cell_of(cx[(size_t)p], cy[(size_t)p]);
+        unsigned int cb = mask[cc];
+        if (!cb) cb = dil[cc];
+        if (!cb) cb = 1u;
+        int o = 0;
+        while (!((cb >> o) & 1u)) o++;
+        powner[(size_t)p] = o;
+    }
+    std::vector<std::vector<char>> listed((size_t)world, std::vector<char>((size_t)npatch, 0));
+    for (int r = 0; r < world; r++) {
+        bool any = false;
+        for (int p = 0; p < npatch; p++) {
+            listed[(size_t)r][(size_t)p] = (char)(((pbits[(size_t)p] >> r) & 1u) || powner[(size_t)p] == r);
+            any = any || listed[(size_t)r][(size_t)p];
+        }
+        if (!any) {
+            std::vector<double> ox, oy;
+            for (int i = 0; i < nn_subs; i++) if (subs_owner[i] == r) { ox.push_back(subs_xyz[3 * (size_t)i]); oy.push_back(subs_xyz[3 * (size_t)i + 1]); }
+            if (ox.empty()) return WCFE_ERR_ARG;          // a rank that owns no substrate at all
+            const double px = (0.0 + pairwise_sum(ox.data(), (long long)ox.size())) / (double)ox.size();
+            const double py = (0.0 + pairwise_sum(oy.data(), (long long)oy.size())) / (double)oy.size();
+            int best = 0; double bd = 0.0;
+            for (int p = 0; p < npatch; p++) {
+                const double dx = cx[(size_t)p] - px, dy = cy[(size_t)p] - py, d2 = dx * dx + dy * dy;
+                if (p == 0 || d2 < bd) { bd = d2; best = p; }
+            }
+            listed[(size_t)r][(size_t)best] = 1;
+        }
+    }
+    // halo rows a rank needs and does not compute: node b of an element edge (a, b) with a in a listed patch and b in one that is not
+    std::vector<std::vector<int>> imports((size_t)world);
+    for (int e = 0; e < ne_cell; e++) {
+        const int v[3] = {cell_tri[3 * (size_t)e], cell_tri[3 * (size_t)e + 1], cell_tri[3 * (size_t)e + 2]};
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+            if (i == j) continue;
+            const int pa = v[i] / kCellPatch, pb = v[j] / kCellPatch;
+            if (pa == pb) continue;
+            for (int r = 0; r < world; r++) if (listed[(size_t)r][(size_t)pa] && !listed[(size_t)r][(size_t)pb]) imports[(size_t)r].push_back(v[j]);
+        }
+    }
+    for (auto &v : imports) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    wcfe_cell_plan *pl = new wcfe_cell_plan;
+    for (int q = 0; q < world; q++) {
+        if (q == rank) continue;
+        const int slot = (int)pl->peer_rank.size();
+        pl->peer_rank.push_back(q);
+        pl->my_slot_at_peer.push_back(rank < q ? rank : rank - 1);
+        for (int node : imports[(size_t)q]) if (powner[(size_t)(node / kCellPatch)] == rank) { pl->export_node.push_back(node); pl->export_peer.push_back(slot); }
+    }
+    for (int p = 0; p < npatch; p++) if (listed[(size_t)rank][(size_t)p]) { pl->patch_list.push_back(p); pl->patch_owned.push_back(powner[(size_t)p] == rank ? 1 : 0); }
+    pl->import_node = imports[(size_t)rank];
+    *out = pl;
+    return WCFE_OK;
+}
+
+int wcfe_cell_plan_sizes(const wcfe_cell_plan *p, int *n_peers, int *n_patches, int *n_export, int *n_import) {
+    if (!p) return WCFE_ERR_ARG;
+    if (n_peers) *n_peers = (int)p->peer_rank.size();
+    if (n_patches) *n_patches = (int)p->patch_list.size();
+    if (n_export) *n_export = (int)p->export_node.size();
+    if (n_import) *n_import = (int)p->import_node.size();
+    return WCFE_OK;
+}
+
+int wcfe_cell_plan_lists(const wcfe_cell_plan *p, int *peer_rank, int *my_slot_at_peer, int *patch_list, int *patch_owned, int *export_node,
+                         int *export_peer, int *import_node) {
+    if (!p) return WCFE_ERR_ARG;
+    put(p->peer_rank, peer_rank); put(p->my_slot_at_peer, my_slot_at_peer); put(p->patch_list, patch_list); put(p->patch_owned, patch_owned);
+    put(p->export_node, export_node); put(p->export_peer, export_peer); put(p->import_node, import_node);
+    return WCFE_OK;
+}
+
+int wcfe_cell_plan_free(wcfe_cell_plan *p) {
+    if (!p) return WCFE_ERR_ARG;
+    delete p;
     return WCFE_OK;
 }
 

@@ -307,6 +307,30 @@ def native_strip(xyz, tri, world, rank, weights=None):
     return out
 
 
+def native_cell_plan(subs_xyz, subs_owner, cell_xyz, cell_tri, world, rank, margin=0.15):
+    """cell_partition + cell_connect_plan from the C ABI's host-side helper (wcfe_cell_partition, csrc/wcfe_partition.cu): what a C++ /
+    MPI host would call.  subs_owner: rank owning every substrate node.  Returns a dict of numpy arrays named like the C arguments."""
+    import ctypes as C
+    from . import _lib as B
+    L = B.load()
+    xs = np.ascontiguousarray(subs_xyz, dtype=np.float64); ow = np.ascontiguousarray(subs_owner, dtype=np.int32)
+    xc = np.ascontiguousarray(cell_xyz, dtype=np.float64); tc = np.ascontiguousarray(cell_tri, dtype=np.int32)
+    h = C.c_void_p()
+    ip = lambda a: a.ctypes.data_as(B._ip)
+    rc = L.wcfe_cell_partition(world, rank, len(xs), xs.ctypes.data_as(B._dp), ip(ow), len(xc), xc.ctypes.data_as(B._dp), len(tc), ip(tc), margin, C.byref(h))
+    if rc:
+        raise ValueError("wcfe_cell_partition failed (%d)" % rc)
+    n = [C.c_int() for _ in range(4)]
+    L.wcfe_cell_plan_sizes(h, *[C.byref(v) for v in n])
+    n_peers, n_patches, n_export, n_import = [v.value for v in n]
+    ia = lambda k: np.zeros(k, dtype=np.int32)
+    out = {"peer_rank": ia(n_peers), "my_slot_at_peer": ia(n_peers), "patch_list": ia(n_patches), "patch_owned": ia(n_patches),
+           "export_node": ia(n_export), "export_peer": ia(n_export), "import_node": ia(n_import)}
+    L.wcfe_cell_plan_lists(h, *[ip(out[k]) for k in ("peer_rank", "my_slot_at_peer", "patch_list", "patch_owned", "export_node", "export_peer", "import_node")])
+    L.wcfe_cell_plan_free(h)
+    return out
+
+
 def make_partition(xs, ts, world, cell_xyz, balance=True, cell="replicated", shape="strips", cell_cost=4.0):
     """The substrate partition of a run: pieces of equal COST -- nodes under the cell also gather integrin forces, and with the cell
     partitioned too they carry the cost of the cell nodes above them (balance=False: equal node counts) -- as vertical strips, or
