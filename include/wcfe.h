@@ -315,6 +315,10 @@ int wcfe_strip_sizes(const wcfe_strip *s, int *n_local, int *n_elem, int *n_owne
 int wcfe_strip_mesh(const wcfe_strip *s, int *local_nodes, int *tri_local, int *elem_gid, int *owned_local, int *ghost_local);
 int wcfe_strip_halo(const wcfe_strip *s, int *peer_rank, int *my_slot_at_peer, int *rows_from_peer, int *export_node, int *export_peer, int *export_row);
 int wcfe_strip_free(wcfe_strip *s);
+/* The same cut along any per-node key instead of x (ties by node id): key = atan2(y - cy, x - cx) about the cell's centroid gives the
+ * sectors of partition.py sector_partition -- every rank then holds a wedge of the substrate AND of the cell above it (world - 1 <=
+ * WCFE_HALO_MAX_PEERS: all sectors meet at the centre).  Same handle and accessors as wcfe_strip_partition. */
+int wcfe_key_partition(int nn, const double *key, int ne, const int *tri, const double *weights, int world, int rank, wcfe_strip **out);
 /* owner[nn]: the rank that owns every node of the uncut mesh (the strips' node -> rank map) */
 int wcfe_strip_owner(const wcfe_strip *s, int *owner);
 

@@ -160,6 +160,28 @@ def test_c_abi_strip_partition_equals_python(world, balanced):
             assert np.array_equal(nat["export_node"], en) and np.array_equal(nat["export_peer"], ep) and np.array_equal(nat["export_row"], er)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_c_abi_key_partition_gives_the_sectors_of_python(world):
+    """wcfe_key_partition cut along the angle about a centre = sector_partition + connect_plan of partition.py (every rank may have
+    every other as a neighbour); along x it is wcfe_strip_partition."""
+    from wholecellfe_b200.build import build
+    build()
+    xs, ts = square_mesh(41)
+    centre = (3.7, -2.2)
+    ang = np.arctan2(xs[:, 1] - centre[1], xs[:, 0] - centre[0])
+    w = cell_weights(xs, np.array([[-20.0, -5.0, 0.0], [0.0, 12.0, 0.0], [5.0, -8.0, 0.0]]))
+    parts = sector_partition(xs, ts, world, centre, w)
+    for r in range(world):
+        nat = native_strip(xs, ts, world, r, w, key=ang)
+        p = parts[r]
+        assert np.array_equal(nat["local_nodes"], p.local_nodes) and np.array_equal(nat["elem_gid"], p.elem_gid) and np.array_equal(nat["tri_local"], p.tri_local)
+        nb, slot, rows, en, ep, er, gh = connect_plan(parts, r)
+        assert np.array_equal(nat["ghost_local"], gh) and list(nat["peer_rank"]) == nb and list(nat["my_slot_at_peer"]) == slot and list(nat["rows_from_peer"]) == rows
+        assert np.array_equal(nat["export_node"], en) and np.array_equal(nat["export_peer"], ep) and np.array_equal(nat["export_row"], er)
+        a = native_strip(xs, ts, world, r, w); b = native_strip(xs, ts, world, r, w, key=xs[:, 0])
+        assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
 @pytest.mark.parametrize("shape", ["strips", "sectors"])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_c_abi_cell_partition_equals_python(world, shape):

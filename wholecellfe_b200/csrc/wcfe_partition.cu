@@ -76,15 +76,17 @@ void build_parts(int nn, int ne, const int *tri, const std::vector<int> &owner, 
 
 extern "C" {
 
-int wcfe_strip_partition(int nn, const double *xyz, int ne, const int *tri, const double *weights, int world, int rank, wcfe_strip **out) {
+// nodes sorted by key (ties by node id) and cut into `world` runs: key = x gives vertical strips, key = the angle about the cell's
+// centroid gives sectors (partition.py sector_partition: every rank then holds a wedge of the substrate and of the cell above it)
+int wcfe_key_partition(int nn, const double *key, int ne, const int *tri, const double *weights, int world, int rank, wcfe_strip **out) {
     if (!out) return WCFE_ERR_ARG;
     *out = nullptr;
-    if (nn <= 0 || ne <= 0 || !xyz || !tri || world < 1 || rank < 0 || rank >= world) return WCFE_ERR_ARG;
+    if (nn <= 0 || ne <= 0 || !key || !tri || world < 1 || rank < 0 || rank >= world) return WCFE_ERR_ARG;
     for (size_t q = 0; q < 3 * (size_t)ne; q++) if (tri[q] < 0 || tri[q] >= nn) return WCFE_ERR_ARG;
-    // owner of every node: position in the (x, id) order against the cut points
+    // owner of every node: position in the (key, id) order against the cut points
     std::vector<int> order((size_t)nn);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return xyz[3 * (size_t)a] < xyz[3 * (size_t)b]; });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[(size_t)a] < key[(size_t)b]; });
     std::vector<long long> bounds((size_t)world + 1, 0);
     bounds[(size_t)world] = nn;
     if (!weights) {
@@ -127,6 +129,15 @@ int wcfe_strip_partition(int nn, const double *xyz, int ne, const int *tri, cons
     }
     *out = s;
     return WCFE_OK;
+}
+
+int wcfe_strip_partition(int nn, const double *xyz, int ne, const int *tri, const double *weights, int world, int rank, wcfe_strip **out) {
+    if (!out) return WCFE_ERR_ARG;
+    *out = nullptr;
+    if (nn <= 0 || !xyz) return WCFE_ERR_ARG;
+    std::vector<double> key((size_t)nn);
+    for (int i = 0; i < nn; i++) key[(size_t)i] = xyz[3 * (size_t)i];
+    return wcfe_key_partition(nn, key.data(), ne, tri, weights, world, rank, out);
 }
 
 int wcfe_strip_sizes(const wcfe_strip *s, int *n_local, int *n_elem, int *n_owned, int *n_ghost, int *n_peers, int *n_export) {

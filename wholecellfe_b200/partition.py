@@ -279,17 +279,23 @@ def connect_plan(parts, rank):
     return nb, my_slot, rows_from, cat(en), cat(ep), cat(er), ghost_local
 
 
-def native_strip(xyz, tri, world, rank, weights=None):
+def native_strip(xyz, tri, world, rank, weights=None, key=None):
     """The same partition and connect plan from the C ABI's host-side helper (wcfe_strip_partition, csrc/wcfe_partition.cu):
-    what a C++ / MPI host would call.  Returns a dict of numpy arrays named like the C arguments."""
+    what a C++ / MPI host would call.  key: cut along this per-node key instead of x (wcfe_key_partition; the angle about the cell's
+    centroid gives sector_partition).  Returns a dict of numpy arrays named like the C arguments."""
     import ctypes as C
     from . import _lib as B
     L = B.load()
     xyz = np.ascontiguousarray(xyz, dtype=np.float64); tri = np.ascontiguousarray(tri, dtype=np.int32)
     w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
     h = C.c_void_p()
-    rc = L.wcfe_strip_partition(len(xyz), xyz.ctypes.data_as(B._dp), len(tri), tri.ctypes.data_as(B._ip),
-                                None if w is None else w.ctypes.data_as(B._dp), world, rank, C.byref(h))
+    if key is None:
+        rc = L.wcfe_strip_partition(len(xyz), xyz.ctypes.data_as(B._dp), len(tri), tri.ctypes.data_as(B._ip),
+                                    None if w is None else w.ctypes.data_as(B._dp), world, rank, C.byref(h))
+    else:
+        key = np.ascontiguousarray(key, dtype=np.float64)
+        rc = L.wcfe_key_partition(len(xyz), key.ctypes.data_as(B._dp), len(tri), tri.ctypes.data_as(B._ip),
+                                  None if w is None else w.ctypes.data_as(B._dp), world, rank, C.byref(h))
     if rc:
         raise ValueError("wcfe_strip_partition failed (%d)" % rc)
     n = [C.c_int() for _ in range(6)]
