@@ -319,6 +319,10 @@ int wcfe_strip_free(wcfe_strip *s);
  * sectors of partition.py sector_partition -- every rank then holds a wedge of the substrate AND of the cell above it (world - 1 <=
  * WCFE_HALO_MAX_PEERS: all sectors meet at the centre).  Same handle and accessors as wcfe_strip_partition. */
 int wcfe_key_partition(int nn, const double *key, int ne, const int *tri, const double *weights, int world, int rank, wcfe_strip **out);
+/* weights[nn_subs] for a cost-balanced cut: 1 + under_cell for a substrate node inside the cell's padded bounding box (measured ~3x a
+ * plain node: under_cell 2) + cell_cost per cell node above it when the cell is partitioned as well (measured ~4; 0 = replicated cell).
+ * partition.py cell_weights + cell_cost_weights. */
+int wcfe_partition_weights(int nn_subs, const double *subs_xyz, int nn_cell, const double *cell_xyz, double under_cell, double cell_cost, double *weights);
 /* owner[nn]: the rank that owns every node of the uncut mesh (the strips' node -> rank map) */
 int wcfe_strip_owner(const wcfe_strip *s, int *owner);
 

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 from wholecellfe_b200.meshgen import square_mesh, disk_mesh
 from wholecellfe_b200.partition import (strip_partition, sector_partition, make_partition, cell_partition, cell_connect_plan, exchange_rows,
-                                        connect_plan, neighbours, cell_weights, native_strip, native_cell_plan, PATCH)
+                                        connect_plan, neighbours, cell_weights, cell_cost_weights, native_strip, native_cell_plan, PATCH)
 
 
 def _free_port():
@@ -158,6 +158,25 @@ def test_c_abi_strip_partition_equals_python(world, balanced):
             assert np.array_equal(nat["ghost_local"], gh)
             assert list(nat["peer_rank"]) == nb and list(nat["my_slot_at_peer"]) == slot and list(nat["rows_from_peer"]) == rows
             assert np.array_equal(nat["export_node"], en) and np.array_equal(nat["export_peer"], ep) and np.array_equal(nat["export_row"], er)
+
+
+def test_c_abi_partition_weights_equal_python():
+    """wcfe_partition_weights = cell_weights (+ cell_cost_weights when the cell is partitioned too), value for value"""
+    import ctypes as C
+    from wholecellfe_b200 import _lib as B
+    from wholecellfe_b200.build import build
+    build()
+    L = B.load()
+    for (nc, ns, shift) in ((6000, 120, (0.0, 0.0)), (3001, 64, (17.3, -9.1)), (500, 33, (-60.0, 0.0))):       # the last cell hangs over the substrate's edge
+        xc, _ = disk_mesh(nc); xs, _ = square_mesh(ns)
+        xc = np.ascontiguousarray(xc + np.array([shift[0], shift[1], 0.0])); xs = np.ascontiguousarray(xs)
+        for cost in (0.0, 4.0):
+            w = np.zeros(len(xs))
+            assert L.wcfe_partition_weights(len(xs), xs.ctypes.data_as(B._dp), len(xc), xc.ctypes.data_as(B._dp), 2.0, cost, w.ctypes.data_as(B._dp)) == 0
+            want = cell_weights(xs, xc) + (cell_cost_weights(xs, xc, cost) if cost else 0.0)
+            assert np.array_equal(w, want), (nc, ns, cost)
+            assert w.min() >= 1.0 and (cost == 0.0 or w.sum() > len(xs) + 2.0 * 0)
+    assert L.wcfe_partition_weights(0, None, 1, None, 2.0, 0.0, None) == B.ERR_ARG
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])

@@ -172,6 +172,44 @@ int wcfe_strip_free(wcfe_strip *s) {
     return WCFE_OK;
 }
 
+// Cost weights per substrate node for a balanced cut (partition.py cell_weights + cell_cost_weights, measured on B200: DESIGN.md 6):
+// 1, plus under_cell for a node inside the cell's padded bounding box (it also reads its epoch stamp and walks anchor buckets), plus --
+// when the cell is partitioned too, cell_cost > 0 -- cell_cost for every cell node charged to one substrate node of the raster cell
+// (size 1.5 h) under it.
+int wcfe_partition_weights(int nn_subs, const double *subs_xyz, int nn_cell, const double *cell_xyz, double under_cell, double cell_cost, double *weights) {
+    if (nn_subs <= 0 || !subs_xyz || nn_cell <= 0 || !cell_xyz || !weights) return WCFE_ERR_ARG;
+    double lo[2] = {cell_xyz[0], cell_xyz[1]}, hi[2] = {cell_xyz[0], cell_xyz[1]};
+    for (int i = 1; i < nn_cell; i++) for (int c = 0; c < 2; c++) { lo[c] = std::min(lo[c], cell_xyz[3 * (size_t)i + c]); hi[c] = std::max(hi[c], cell_xyz[3 * (size_t)i + c]); }
+    const double pad = std::max(2.0, 0.25 * std::max(hi[0] - lo[0], hi[1] - lo[1]));
+    for (int i = 0; i < nn_subs; i++) {
+        const double x = subs_xyz[3 * (size_t)i], y = subs_xyz[3 * (size_t)i + 1];
+        const bool inside = x >= lo[0] - pad && x <= hi[0] + pad && y >= lo[1] - pad && y <= hi[1] + pad;
+        weights[i] = 1.0 + under_cell * (inside ? 1.0 : 0.0);
+    }
+    if (!(cell_cost > 0.0)) return WCFE_OK;
+    double xmin = subs_xyz[0], xmax = subs_xyz[0], ymin = subs_xyz[1], ymax = subs_xyz[1];
+    for (int i = 1; i < nn_subs; i++) {
+        xmin = std::min(xmin, subs_xyz[3 * (size_t)i]); xmax = std::max(xmax, subs_xyz[3 * (size_t)i]);
+        ymin = std::min(ymin, subs_xyz[3 * (size_t)i + 1]); ymax = std::max(ymax, subs_xyz[3 * (size_t)i + 1]);
+    }
+    const double h = std::sqrt((xmax - xmin) * (ymax - ymin) / (double)std::max(1, nn_subs)), g = 1.5 * h;
+    if (!(g > 0.0)) return WCFE_ERR_ARG;
+    const long long nx = (long long)((xmax - xmin) / g) + 1, ny = (long long)((ymax - ymin) / g) + 1;
+    if (nx * ny > (1ll << 28)) return WCFE_ERR_ARG;
+    std::vector<int> rep((size_t)(nx * ny), -1);
+    for (int i = 0; i < nn_subs; i++)          // the last node filed in a raster cell represents it
+        rep[(size_t)((long long)((subs_xyz[3 * (size_t)i + 1] - ymin) / g) * nx + (long long)((subs_xyz[3 * (size_t)i] - xmin) / g))] = i;
+    std::vector<double> extra((size_t)nn_subs, 0.0);
+    for (int i = 0; i < nn_cell; i++) {
+        long long ix = (long long)((cell_xyz[3 * (size_t)i] - xmin) / g), iy = (long long)((cell_xyz[3 * (size_t)i + 1] - ymin) / g);
+        ix = std::min(std::max(ix, 0ll), nx - 1); iy = std::min(std::max(iy, 0ll), ny - 1);
+        const int t = rep[(size_t)(iy * nx + ix)];
+        if (t >= 0) extra[(size_t)t] += cell_cost;
+    }
+    for (int i = 0; i < nn_subs; i++) weights[i] = weights[i] + extra[(size_t)i];
+    return WCFE_OK;
+}
+
 int wcfe_strip_owner(const wcfe_strip *s, int *owner) {
     if (!s || !owner) return WCFE_ERR_ARG;
     put(s->owner, owner);
