@@ -243,6 +243,36 @@ def test_c_abi_cell_partition_equals_python(world, shape):
         native_cell_plan(xs, owner, xc, tc, 33, 0, 0.15)                        # rank sets are 32-bit masks
 
 
+@pytest.mark.parametrize("shape", ["strips", "sectors"])
+def test_cpp_host_partition_plan_equals_python(shape, tmp_path):
+    """wholecellfe_b200/csrc/host/partition_plan: a C++ host driving the host-only partition entry points of the C ABI (weights, cut,
+    strip, cell plan) end to end, no GPU, no Python in the loop -- its per-rank sizes are those of partition.py make_partition +
+    cell_partition on the same meshes."""
+    import re
+    import subprocess
+    from wholecellfe_b200.meshio import write_ecomsol
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "wholecellfe_b200", "csrc", "host")
+    subprocess.check_call(["make", "-s", "-C", host])
+    xc, tc = disk_mesh(4000); xs, ts = square_mesh(90)
+    write_ecomsol(str(tmp_path / "cell.txt"), xc, tc); write_ecomsol(str(tmp_path / "subs.txt"), xs, ts)
+    world = 4
+    r = subprocess.run([os.path.join(host, "partition_plan"), str(tmp_path / "cell.txt"), str(tmp_path / "subs.txt"), str(world), shape, "0.15"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    rows = [[int(v) for v in re.findall(r"-?\d+", line)] for line in r.stdout.strip().split("\n")]
+    assert len(rows) == world
+    parts = make_partition(xs, ts, world, xc, True, "partitioned", shape)
+    cps = cell_partition(parts, xc, tc, xs, 0.15)
+    for q, (p, c) in enumerate(zip(parts, cps)):
+        _, _, rows_from, en, _, _, gh = connect_plan(parts, q)
+        want = [q, len(p.local_nodes), len(p.owned), len(gh), len(p.elem_gid), len(neighbours(p)), len(en),
+                len(c.patch_list), int(c.patch_owned.sum()), sum(len(v) for v in c.exports.values()), len(c.imports)]
+        assert rows[q] == want, (shape, q, rows[q], want)
+    bad = subprocess.run([os.path.join(host, "partition_plan"), str(tmp_path / "nope.txt"), str(tmp_path / "subs.txt"), "2"], capture_output=True, text=True)
+    assert bad.returncode != 0
+
+
 def test_c_abi_strip_partition_rejects_bad_arguments():
     import ctypes as C
     from wholecellfe_b200 import _lib as B
