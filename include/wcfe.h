@@ -106,6 +106,13 @@ int wcfe_replicas(wcfe_ctx *c);
 /* per-replica Philox key (WCFE_RNG_PHILOX only); wcfe_set_rng resets every replica to its common seed */
 int wcfe_set_replica_seed(wcfe_ctx *c, int replica, unsigned int seed);
 int wcfe_set_params(wcfe_ctx *c, const wcfe_params *p);
+/* Host-only: the parameter sweep of an ensemble (config 5: spring law x ligand density x seed) and its shard over ranks, deterministic
+ * from the cell id (every rank rebuilds its part without communication; same table as wholecellfe_b200/ensemble.py).  wcfe_sweep_cell:
+ * parameters (wcfe_default_params of the law with rho_i_max set) and RNG seed of cell `id` out of n_cells -- laws[n_laws] (WCFE_K1 ...) x
+ * round(sqrt(n_cells / n_laws)) log-spaced rho_i_max in [rho_min, rho_max], law-major, seed = 1 + number of completed passes through
+ * that grid.  wcfe_ensemble_shard: the contiguous balanced range [lo, hi) of cell ids of `rank`. */
+int wcfe_sweep_cell(int n_cells, int n_laws, const int *laws, double rho_min, double rho_max, int id, wcfe_params *params, unsigned int *seed);
+int wcfe_ensemble_shard(int n_cells, int world, int rank, int *lo, int *hi);
 /* run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own non-blocking stream;
  * pass cudaStreamLegacy ((cudaStream_t)0x1) to name the legacy default stream explicitly */
 int wcfe_set_stream(wcfe_ctx *c, void *cuda_stream);

@@ -70,3 +70,36 @@ def test_two_rank_ensemble_sharding_and_timing_reduction():
         spans = sorted((a, b) for a, b, _ in gathered)
         assert spans[0][0] == 0 and spans[-1][1] == n_cells and spans[0][1] == spans[1][0]
         assert sum(s for _, _, s in gathered) == sum(c["seed"] for c in cells)
+
+
+def test_c_abi_sweep_and_shard_equal_python():
+    """wcfe_sweep_cell / wcfe_ensemble_shard (host-only C++ in libwcfe.so: what a C++ / MPI host calls for config 5) against
+    ensemble.py sweep_grid / partition: law, seed and shard bounds exactly, the log-spaced ligand density to a few ulps (numpy's
+    geomspace and pow round differently), every other parameter the law's defaults."""
+    import ctypes as C
+    import wholecellfe_b200 as W
+    from wholecellfe_b200 import _lib as B
+    from wholecellfe_b200.build import build
+    build()
+    L = B.load()
+    laws = (C.c_int * 3)(B.VARIANTS["k1"], B.VARIANTS["k31"], B.VARIANTS["kMD"])
+    for n in (1, 7, 512, 4096, 4097):
+        cells = sweep_grid(n)
+        for c in cells[:: max(1, n // 97)] + cells[-3:]:
+            p = B.Params(); seed = C.c_uint()
+            assert L.wcfe_sweep_cell(n, 3, laws, 1.0, 100.0, c["id"], C.byref(p), C.byref(seed)) == 0
+            d = W.default_params(c["variant"])
+            assert seed.value == c["seed"] and p.law == d.law and p.kint_force == d.kint_force and p.kint_bond == d.kint_bond, (n, c)
+            assert abs(p.rho_i_max - c["rho_i_max"]) <= 1e-14 * c["rho_i_max"], (n, c, p.rho_i_max)
+            for f, _ in B.Params._fields_:
+                if f not in ("rho_i_max", "md_px", "md_py", "md_k"):
+                    assert getattr(p, f) == getattr(d, f), f
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                lo = C.c_int(); hi = C.c_int()
+                assert L.wcfe_ensemble_shard(n, world, r, C.byref(lo), C.byref(hi)) == 0
+                want = partition(n, world, r)
+                assert (lo.value, hi.value) == (want.start, want.stop)
+    p = B.Params()
+    assert L.wcfe_sweep_cell(10, 3, laws, 1.0, 100.0, 10, C.byref(p), None) == B.ERR_ARG
+    assert L.wcfe_ensemble_shard(10, 2, 2, C.byref(C.c_int()), C.byref(C.c_int())) == B.ERR_ARG

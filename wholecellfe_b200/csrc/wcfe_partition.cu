@@ -210,6 +210,32 @@ int wcfe_partition_weights(int nn_subs, const double *subs_xyz, int nn_cell, con
     return WCFE_OK;
 }
 
+// ---- ensembles (BASELINE configs[4]; the reference's mechanism is a job array of independent processes, s_sim_031021_1.sub): the
+// parameter sweep and its shard over ranks, deterministic from the cell id so that every rank rebuilds the table without communication
+// (ensemble.py sweep_grid / partition).  Cell `id` of n_cells: laws (WCFE_K1 / _K31 / _KMD ids) x n_rho log-spaced ligand densities
+// rho_i_max in [rho_min, rho_max] (UL:1231), n_rho = round(sqrt(n_cells / n_laws)), law-major; the seed counts how often the grid
+// has been passed through (from 1).
+int wcfe_sweep_cell(int n_cells, int n_laws, const int *laws, double rho_min, double rho_max, int id, wcfe_params *params, unsigned int *seed) {
+    if (n_cells <= 0 || n_laws <= 0 || !laws || id < 0 || id >= n_cells || !params || !(rho_min > 0.0) || !(rho_max >= rho_min)) return WCFE_ERR_ARG;
+    const int n_rho = std::max(1, (int)std::nearbyint(std::sqrt((double)n_cells / (double)n_laws)));
+    const int per_pass = n_laws * n_rho, k = id % per_pass, law = laws[k / n_rho], j = k % n_rho;
+    int rc = wcfe_default_params(params, law);
+    if (rc != WCFE_OK) return rc;
+    double rho = rho_min;
+    if (n_rho > 1) rho = j == 0 ? rho_min : (j == n_rho - 1 ? rho_max : rho_min * std::pow(rho_max / rho_min, (double)j / (double)(n_rho - 1)));
+    params->rho_i_max = rho;
+    if (seed) *seed = 1u + (unsigned int)(id / per_pass);
+    return WCFE_OK;
+}
+// contiguous, balanced shard [lo, hi) of the cell ids for `rank` (sizes differ by at most one)
+int wcfe_ensemble_shard(int n_cells, int world, int rank, int *lo, int *hi) {
+    if (n_cells < 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return WCFE_ERR_ARG;
+    const int base = n_cells / world, extra = n_cells % world;
+    *lo = rank * base + std::min(rank, extra);
+    *hi = *lo + base + (rank < extra ? 1 : 0);
+    return WCFE_OK;
+}
+
 int wcfe_strip_owner(const wcfe_strip *s, int *owner) {
     if (!s || !owner) return WCFE_ERR_ARG;
     put(s->owner, owner);
