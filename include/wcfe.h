@@ -326,6 +326,11 @@ int wcfe_strip_free(wcfe_strip *s);
  * sectors of partition.py sector_partition -- every rank then holds a wedge of the substrate AND of the cell above it (world - 1 <=
  * WCFE_HALO_MAX_PEERS: all sectors meet at the centre).  Same handle and accessors as wcfe_strip_partition. */
 int wcfe_key_partition(int nn, const double *key, int ne, const int *tri, const double *weights, int world, int rank, wcfe_strip **out);
+/* Host-only: renumber a mesh for the patch kernels (128 consecutive nodes per CTA, one-ring staged in shared memory: without locality
+ * in the numbering wcfe_upload_mesh falls back to the general kernels).  Nodes along a Morton (Z-order) curve over the 16-bit quantised
+ * (x, y), ties by old id; triangles by the key of their centroid, vertex order (orientation) kept.  perm[new] = old id; apply it to
+ * every nodal array before the upload and its inverse to what comes back.  What meshgen.py does for the synthetic configurations. */
+int wcfe_morton_order(int nn, const double *xyz, int ne, const int *tri, int *perm, int *tri_out);
 /* weights[nn_subs] for a cost-balanced cut: 1 + under_cell for a substrate node inside the cell's padded bounding box (measured ~3x a
  * plain node: under_cell 2) + cell_cost per cell node above it when the cell is partitioned as well (measured ~4; 0 = replicated cell).
  * partition.py cell_weights + cell_cost_weights. */

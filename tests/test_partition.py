@@ -518,3 +518,33 @@ def test_halo_connect_argument_checks_and_bounded_wait():
     assert e.value.code == B.ERR_PEER and "halo" in str(e.value)
     assert 5.0 < time.time() - t0 < 60.0                      # the bounded wait, once: later waits return at once
     g.close()
+
+
+def test_c_abi_morton_order_equals_meshgen_and_keeps_the_mesh():
+    """wcfe_morton_order (host-only C++ in libwcfe.so) numbers nodes and sorts triangles exactly as meshgen.py does for the synthetic
+    configurations; the renumbered mesh is the same mesh (coordinates of every triangle's vertices, orientation) and its patches of
+    128 consecutive nodes are compact."""
+    import ctypes as C
+    from wholecellfe_b200 import _lib as B
+    from wholecellfe_b200.build import build
+    from wholecellfe_b200.meshgen import _renumber
+    build()
+    L = B.load()
+    rng = np.random.default_rng(5)
+    for xyz, tri in (disk_mesh(5000, order=None), square_mesh(57, order=None, jitter=0.2)):
+        shuffle = rng.permutation(len(xyz))                      # a numbering without any locality
+        inv = np.empty_like(shuffle); inv[shuffle] = np.arange(len(xyz))
+        xyz = np.ascontiguousarray(xyz[shuffle]); tri = np.ascontiguousarray(inv[tri][rng.permutation(len(tri))], dtype=np.int32)
+        perm = np.zeros(len(xyz), dtype=np.int32); tout = np.zeros_like(tri)
+        assert L.wcfe_morton_order(len(xyz), xyz.ctypes.data_as(B._dp), len(tri), tri.ctypes.data_as(B._ip), perm.ctypes.data_as(B._ip), tout.ctypes.data_as(B._ip)) == 0
+        want_xyz, want_tri = _renumber(xyz, tri, "morton")
+        assert np.array_equal(xyz[perm], want_xyz) and np.array_equal(tout, want_tri)
+        assert sorted(perm.tolist()) == list(range(len(xyz)))
+        a = np.sort(xyz[perm][tout].reshape(len(tri), -1), axis=0); b = np.sort(xyz[tri].reshape(len(tri), -1), axis=0)
+        assert np.array_equal(a, b)                               # the same set of triangles, vertex order kept
+        x2 = xyz[perm]
+        ext = lambda pts: max(np.ptp(pts[:, 0]), np.ptp(pts[:, 1]))
+        before = np.median([ext(xyz[k:k + 128]) for k in range(0, len(xyz) - 128, 128)])
+        after = np.median([ext(x2[k:k + 128]) for k in range(0, len(xyz) - 128, 128)])
+        assert after < 0.5 * before, (before, after)
+    assert L.wcfe_morton_order(0, None, 0, None, None, None) == B.ERR_ARG

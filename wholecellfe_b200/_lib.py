@@ -28,7 +28,7 @@ SYMBOLS = ["wcfe_default_params", "wcfe_create", "wcfe_destroy", "wcfe_set_param
            "wcfe_get_discrete", "wcfe_get_boundary_flags", "wcfe_kernel_launches", "wcfe_last_step_ms", "wcfe_force_field", "wcfe_dormant_field", "wcfe_device_ptr", "wcfe_sync", "wcfe_selftest_quotient", "wcfe_grid_refreshes",
            "wcfe_create_batch", "wcfe_select_replica", "wcfe_replicas", "wcfe_set_replica_seed", "wcfe_set_roundtrip_mode",
            "wcfe_halo_info_get", "wcfe_halo_connect", "wcfe_halo_disconnect", "wcfe_cell_halo_info_get", "wcfe_cell_halo_connect", "wcfe_cell_halo_disconnect",
-           "wcfe_strip_partition", "wcfe_strip_sizes", "wcfe_strip_mesh", "wcfe_strip_halo", "wcfe_strip_free", "wcfe_strip_owner", "wcfe_key_partition", "wcfe_partition_weights", "wcfe_sweep_cell", "wcfe_ensemble_shard",
+           "wcfe_strip_partition", "wcfe_strip_sizes", "wcfe_strip_mesh", "wcfe_strip_halo", "wcfe_strip_free", "wcfe_strip_owner", "wcfe_key_partition", "wcfe_partition_weights", "wcfe_sweep_cell", "wcfe_ensemble_shard", "wcfe_morton_order",
            "wcfe_cell_partition", "wcfe_cell_plan_sizes", "wcfe_cell_plan_lists", "wcfe_cell_plan_free"]
 
 
@@ -129,6 +129,7 @@ def load():
     L.wcfe_strip_halo.argtypes = [vp] + [_ip] * 6
     L.wcfe_strip_free.argtypes = [vp]
     L.wcfe_strip_owner.argtypes = [vp, _ip]
+    L.wcfe_morton_order.argtypes = [C.c_int, _dp, C.c_int, _ip, _ip, _ip]
     L.wcfe_sweep_cell.argtypes = [C.c_int, C.c_int, _ip, C.c_double, C.c_double, C.c_int, C.POINTER(Params), C.POINTER(C.c_uint)]
     L.wcfe_ensemble_shard.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip]
     L.wcfe_partition_weights.argtypes = [C.c_int, _dp, C.c_int, _dp, C.c_double, C.c_double, _dp]

@@ -210,6 +210,49 @@ int wcfe_partition_weights(int nn_subs, const double *subs_xyz, int nn_cell, con
     return WCFE_OK;
 }
 
+// ---- node numbering.  The patch kernels own 128 consecutive nodes per CTA and stage their one-ring in shared memory: a mesh numbered
+// without locality (a mesh generator's advancing front, COMSOL's export order) has patches whose halo does not fit, and wcfe_upload_mesh
+// then selects the general kernels.  wcfe_morton_order renumbers nodes along a Morton (Z-order) curve over the 16-bit quantised (x, y)
+// and sorts the triangles by the key of their centroid -- what meshgen.py does for the synthetic configurations.
+namespace {
+unsigned long long spread16(unsigned long long v) {
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+}   // namespace
+// perm[new] = old node id; tri_out[3*ne]: the triangles in the new numbering and order (vertex order kept, hence orientation)
+int wcfe_morton_order(int nn, const double *xyz, int ne, const int *tri, int *perm, int *tri_out) {
+    if (nn <= 0 || !xyz || ne < 0 || (ne > 0 && !tri) || !perm || (ne > 0 && !tri_out)) return WCFE_ERR_ARG;
+    for (size_t q = 0; q < 3 * (size_t)ne; q++) if (tri[q] < 0 || tri[q] >= nn) return WCFE_ERR_ARG;
+    double lo[2] = {xyz[0], xyz[1]}, hi[2] = {xyz[0], xyz[1]};
+    for (int i = 1; i < nn; i++) for (int c = 0; c < 2; c++) { lo[c] = std::min(lo[c], xyz[3 * (size_t)i + c]); hi[c] = std::max(hi[c], xyz[3 * (size_t)i + c]); }
+    const double span[2] = {std::max(hi[0] - lo[0], 1e-300), std::max(hi[1] - lo[1], 1e-300)};
+    auto key_of = [&](double x, double y) {
+        const long long qx = std::min((long long)((x - lo[0]) / span[0] * 65535.0), 65535ll), qy = std::min((long long)((y - lo[1]) / span[1] * 65535.0), 65535ll);
+        return spread16((unsigned long long)qx) | (spread16((unsigned long long)qy) << 1);
+    };
+    std::vector<unsigned long long> key((size_t)nn);
+    for (int i = 0; i < nn; i++) key[(size_t)i] = key_of(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1]);
+    std::iota(perm, perm + nn, 0);
+    std::stable_sort(perm, perm + nn, [&](int a, int b) { return key[(size_t)a] < key[(size_t)b]; });
+    std::vector<int> inv((size_t)nn);
+    for (int n = 0; n < nn; n++) inv[(size_t)perm[n]] = n;
+    std::vector<unsigned long long> tkey((size_t)ne);
+    std::vector<int> torder((size_t)ne);
+    for (int e = 0; e < ne; e++) {
+        const double *a = xyz + 3 * (size_t)tri[3 * (size_t)e], *b = xyz + 3 * (size_t)tri[3 * (size_t)e + 1], *c = xyz + 3 * (size_t)tri[3 * (size_t)e + 2];
+        tkey[(size_t)e] = key_of(((a[0] + b[0]) + c[0]) / 3.0, ((a[1] + b[1]) + c[1]) / 3.0);
+    }
+    std::iota(torder.begin(), torder.end(), 0);
+    std::stable_sort(torder.begin(), torder.end(), [&](int a, int b) { return tkey[(size_t)a] < tkey[(size_t)b]; });
+    for (int n = 0; n < ne; n++) for (int j = 0; j < 3; j++) tri_out[3 * (size_t)n + j] = inv[(size_t)tri[3 * (size_t)torder[(size_t)n] + j]];
+    return WCFE_OK;
+}
+
 // ---- ensembles (BASELINE configs[4]; the reference's mechanism is a job array of independent processes, s_sim_031021_1.sub): the
 // parameter sweep and its shard over ranks, deterministic from the cell id so that every rank rebuilds the table without communication
 // (ensemble.py sweep_grid / partition).  Cell `id` of n_cells: laws (WCFE_K1 / _K31 / _KMD ids) x n_rho log-spaced ligand densities
