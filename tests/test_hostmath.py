@@ -209,3 +209,69 @@ def test_node_table_rows_are_a_permutation_with_fewer_bank_conflicts(hm):
     z = np.zeros(P + 1, dtype=np.uint16); e = np.zeros(2, dtype=np.uint16)
     hm.hm_ring_table_rows(e.ctypes.data_as(u16), 0, z.ctypes.data_as(u16), P, NL, row_of.ctypes.data_as(u16), C.byref(ident))
     assert row_of.tolist() == list(range(NL))
+
+
+def test_integrin_force_laws_match_the_reference_force_field(hm, meshes):
+    """integrin_force of wcfe_math.cuh (host build) -- the linear spring of k1 / k31 (UL:1259) and the piecewise-linear MD table of kMD
+    (kMD UL:1246-1265, incl. its jump at zero extension and the last segment's extrapolation) -- against the oracle's calculateForce_FA
+    (pinned to the reference) on the shipped cell mesh: F_i = -c_C f(fa_u_i) Asum_i rho, with Asum_i taken from the linear law."""
+    from oracle.oracle import OracleSim
+    import wholecellfe_b200 as W
+    xc, tc, xs, ts = meshes
+    rng = np.random.default_rng(12)
+    n = len(xc)
+    mag = 10.0 ** rng.uniform(-9, np.log10(0.03), size=n)                     # from far below the first knot to beyond the last (17e-3)
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]; u *= mag[:, None]
+    cC = rng.uniform(0.1, 1.0, size=n)
+    F = {}
+    for v in ("k1", "kMD"):
+        o = OracleSim(v, xc, tc, xs, ts)
+        o.set(0, "fa_u", u); o.set(0, "cC", cC)
+        F[v] = o.force_field("F_FA", 0.005, 0.0)["F"]
+    asum_rho = -F["k1"][:, 0] / (cC * 1000.0 * u[:, 0])                          # Asum_i * rho_i_max
+    p = W.default_params("kMD")                                                  # the table the kernels receive (kMD UL:1208-1214)
+    px = np.array(list(p.md_px)); py = np.array(list(p.md_py)); kk = np.array(list(p.md_k))
+    worst = 0.0
+    for i in range(n):
+        f = np.zeros(3)
+        hm.hm_integrin_force(1, C.c_double(-1.0), d(px), d(py), d(kk), d(np.ascontiguousarray(u[i])), d(f))
+        want = -F["kMD"][i] / (cC[i] * asum_rho[i])
+        worst = max(worst, np.abs(f - want).max() / np.abs(want).max())
+        g = np.zeros(3)
+        hm.hm_integrin_force(0, C.c_double(31000.0), d(px), d(py), d(kk), d(np.ascontiguousarray(u[i])), d(g))
+        assert np.array_equal(g, 31000.0 * u[i])
+    assert worst < 1e-11, worst
+    assert mag.min() < 1e-8 and mag.max() > 0.02
+
+
+@pytest.mark.parametrize("variant,law,kf,kb", [("k1", 0, 1000.0, 1000.0), ("k31", 0, 31000.0, 31000.0), ("kMD", 1, -1.0, -1.0)])
+def test_bond_update_matches_the_reference_step_node_by_node(hm, meshes, variant, law, kf, kb):
+    """bond_update of wcfe_math.cuh (host build): updateFA's anchor drift, Bell off-rate (2-D norm for k1 / k31, the MD force for kMD),
+    forward-Euler c_C, clamp and survivor-weighted anchor / reset branch (UL:2072-2111) -- fed, node by node, with what the oracle's
+    step saw (fa_u and c_C before, cell displacement x - X of the step) and compared with what the step left; the reset and clamp
+    masks must be the oracle's.  Steps 1-3 (bonds forming from rest) and 38-40 of the shipped example (ruptures under load)."""
+    from oracle.oracle import OracleSim
+    import wholecellfe_b200 as W
+    xc, tc, xs, ts = meshes
+    p = W.default_params(variant)
+    px = np.array(list(p.md_px)); py = np.array(list(p.md_py)); kk = np.array(list(p.md_k))
+    o = OracleSim(variant, xc, tc, xs, ts); o.srand(1)
+    t = 0.0; dt = 0.005
+    worst = 0.0; resets = 0
+    zero = np.zeros(3)
+    for k in range(40):
+        fa0 = o.get(0, "fa_u"); c0 = o.get(0, "cC")
+        o.step(dt, t); t += dt
+        if not (k < 3 or k >= 37):
+            continue
+        cell_u = o.get(0, "x") - o.get(0, "X_prev")
+        fa1 = o.get(0, "fa_u"); c1 = o.get(0, "cC")
+        reset = o.discrete("fa_reset"); clamp = o.discrete("cc_clamp")
+        for i in range(len(xc)):
+            fa = np.ascontiguousarray(fa0[i].copy()); cc = C.c_double(c0[i])
+            flags = hm.hm_bond_update(law, C.c_double(kf), C.c_double(kb), d(px), d(py), d(kk), C.c_double(dt), d(np.ascontiguousarray(cell_u[i])), d(zero), d(fa), C.byref(cc))
+            assert (flags & 1) == reset[i] and ((flags >> 1) & 1) == clamp[i], (variant, k, i)
+            worst = max(worst, abs(cc.value - c1[i]) / max(abs(c1[i]), 1e-3), np.abs(fa - fa1[i]).max() / max(np.abs(fa1).max(), 1e-6))
+        resets += int(reset.sum())
+    assert worst < 1e-12, (variant, worst)
+    assert resets > 0                         # step 1 from rest: every node takes the reset branch (c_C was 0)
