@@ -65,6 +65,7 @@ def lib():
         L.ulo_srand.argtypes = [C.c_void_p, C.c_uint]
         L.ulo_rand.argtypes = [C.c_void_p]; L.ulo_rand.restype = C.c_int
         L.ulo_driver_kind.argtypes = [C.POINTER(Params), C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
+        L.ulo_boundary_neighbours.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
         L.ulo_mesh_build.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip]
         _lib = L
     return _lib
@@ -125,6 +126,11 @@ class OracleSim:
     def set(self, surface, field, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float64); assert arr.size == self.nn[surface] * WIDTH[field]
         assert self.L.ulo_set(self.h, surface, FIELDS[field], _d(arr)) == 0
+
+    def boundary_neighbours(self, ni):
+        """(j1, j2): positions of the two boundary neighbours of cell vertex ni (UL:1479-1507), or None for an interior vertex"""
+        j1 = np.zeros(3); j2 = np.zeros(3)
+        return (j1, j2) if self.L.ulo_boundary_neighbours(self.h, int(ni), _d(j1), _d(j2)) else None
 
     def discrete(self, which):
         out = np.empty(self.nn[0], dtype=np.int32)

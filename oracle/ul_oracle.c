@@ -559,6 +559,15 @@ static void bnd_normal(const double *xi, const double *j1, const double *j2, dou
     *total_length = tl;
 }
 
+/* the two boundary neighbours of a boundary vertex of the cell as the force routines find them (UL:1479-1507), for the CPU tests of
+ * the device's boundary math; returns 0 for an interior vertex */
+int ulo_boundary_neighbours(ulo_sim *s, int ni, double *j1, double *j2) {
+    const ulo_mesh *m = &s->cell.m;
+    if (ni < 0 || ni >= m->nn || !m->is_bnd[ni]) return 0;
+    bnd_neighbours(m, s->cell.x, ni, j1, j2);
+    return 1;
+}
+
 /* calculateForce_AP UL:1456-1547; one rand() per boundary vertex in ascending vertex order */
 void ulo_force_AP(ulo_sim *s, const double *x, double dt, double *F) {
     const ulo_mesh *m = &s->cell.m;

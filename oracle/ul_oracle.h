@@ -103,6 +103,7 @@ void ulo_diffusion_res(const ulo_params *p, const ulo_mesh *m, const double *X, 
                        double dt, double *Res_Adif, double *Res_Cdif);
 void ulo_force_pressure(const ulo_mesh *m, const double *x, const double *MM, double t_tot, double *F);
 void ulo_force_sphere(int nn, const double *x, double *F);
+int  ulo_boundary_neighbours(ulo_sim *s, int ni, double *j1, double *j2);
 /* every driverVelocities_* of UL:103-345 by kind: 0 Explicit, 1 Biaxial, 2 Uniaxial, 3 OffBiaxial, 4 BulgeTest; -1 on an unknown kind */
 int  ulo_driver_kind(const ulo_params *p, int kind, int nn, const double *X, const double *V, const double *A, double dt, double t, double *Vh);
 /* force field by id on the current state, same ids as ulref_force_field (7 Res_Adif, 8 Res_Cdif: out[nn]; 9 pressure, 10 sphere

@@ -49,6 +49,13 @@ extern "C" void hm_elem_eval_frozen(const double *X6, const double *e3, double m
     memcpy(r1, o.r1, 16); memcpy(r2, o.r2, 16); *A0 = o.A0;
 }
 
+// boundary of the cell: outward normal, total edge length, bending curvature, actin loop trips (UL:1512-1520, :1604-1620, :1530)
+extern "C" void hm_boundary(const double *xi, const double *j1, const double *j2, double density, double *nrm, double *tl, double *kappa, double *trips) {
+    bnd_normal(xi, j1, j2, nrm, *tl);
+    *kappa = bnd_curvature(xi, j1, j2, *tl);
+    *trips = ap_trips(density, *tl);
+}
+
 // ---- host logic of the patch builder: row numbering of a substrate patch's node table (csrc/wcfe_rows.h)
 #include "../../wholecellfe_b200/csrc/wcfe_rows.h"
 extern "C" long long hm_ring_table_rows(const unsigned short *jk, int njk, const unsigned short *rptr, int P, int NL, unsigned short *row_of, long long *wavefronts_identity) {

@@ -275,3 +275,36 @@ def test_bond_update_matches_the_reference_step_node_by_node(hm, meshes, variant
         resets += int(reset.sum())
     assert worst < 1e-12, (variant, worst)
     assert resets > 0                         # step 1 from rest: every node takes the reset branch (c_C was 0)
+
+
+def test_boundary_math_matches_the_reference_force_fields(hm, meshes):
+    """bnd_normal / bnd_curvature / ap_trips of wcfe_math.cuh (host build) against the oracle's calculateBendingForce2D (UL:1550-1639),
+    calculateAreaConstraintForce (UL:1670-1763) and the trip count of calculateForce_AP's loop (UL:1530) on a developed state of the
+    shipped cell: F_bend = k_bend kappa n, F_area = -k_area (A - A0) / 2 L n at every boundary vertex."""
+    from oracle.oracle import OracleSim
+    xc, tc, xs, ts = meshes
+    o = OracleSim("k1", xc, tc, xs, ts); o.srand(1)
+    t = 0.0
+    for _ in range(60):
+        o.step(0.005, t); t += 0.005
+    x = o.get(0, "x")
+    fb = o.force_field("F_bend", 0.005, t); fa = o.force_field("F_area", 0.005, t)
+    area = fb["area"][0]
+    p = o.params
+    nb = 0; worst = 0.0
+    sb = np.abs(fb["F"]).max(); sa = np.abs(fa["F"]).max()
+    for i in range(len(xc)):
+        nbr = o.boundary_neighbours(i)
+        if nbr is None:
+            assert not fb["F"][i].any() and not fa["F"][i].any()
+            continue
+        nb += 1
+        nrm = np.zeros(3); tl = C.c_double(); kap = C.c_double(); trips = C.c_double()
+        hm.hm_boundary(d(np.ascontiguousarray(x[i])), d(nbr[0]), d(nbr[1]), C.c_double(p.ap_density), d(nrm), C.byref(tl), C.byref(kap), C.byref(trips))
+        worst = max(worst, np.abs(p.k_bend * kap.value * nrm - fb["F"][i]).max() / sb,
+                    np.abs(-p.k_area * (area - p.area_0) / 2 * tl.value * nrm - fa["F"][i]).max() / sa)
+        n_it = 0
+        while n_it < p.ap_density * tl.value / 2:           # UL:1530, literally
+            n_it += 1
+        assert trips.value == n_it
+    assert nb >= 40 and worst < 1e-12, (nb, worst)
