@@ -56,6 +56,17 @@ extern "C" void hm_boundary(const double *xi, const double *j1, const double *j2
     *trips = ap_trips(density, *tl);
 }
 
+// nodal update (UL:601-628): the three forms the kernels use -- correctly rounded quotient, reciprocal of M rho shared by a node's
+// components, reciprocal of M supplied
+extern "C" void hm_node_update(double f, double MM, double damp, double rho, double dt, double dt_real, double Vh, double V, double A, double *out6) {
+    double v = V, a = A;
+    node_update(f, MM, damp, rho, dt, dt_real, Vh, v, a); out6[0] = v; out6[1] = a;
+    v = V; a = A;
+    node_update_q(f, MM, recip_of(MM * rho), damp, rho, dt, dt_real, Vh, v, a); out6[2] = v; out6[3] = a;
+    v = V; a = A;
+    node_update_r(f, MM, 1.0 / MM, damp, rho, dt, dt_real, Vh, v, a); out6[4] = v; out6[5] = a;
+}
+
 // ---- host logic of the patch builder: row numbering of a substrate patch's node table (csrc/wcfe_rows.h)
 #include "../../wholecellfe_b200/csrc/wcfe_rows.h"
 extern "C" long long hm_ring_table_rows(const unsigned short *jk, int njk, const unsigned short *rptr, int P, int NL, unsigned short *row_of, long long *wavefronts_identity) {

@@ -308,3 +308,36 @@ def test_boundary_math_matches_the_reference_force_fields(hm, meshes):
             n_it += 1
         assert trips.value == n_it
     assert nb >= 40 and worst < 1e-12, (nb, worst)
+
+
+def test_nodal_update_matches_the_reference_step(hm, meshes):
+    """node_update / node_update_q / node_update_r of wcfe_math.cuh (host build) against the oracle's cell update (UL:592-628): the net
+    force assembled from the step's own force fields (drag on V_hlf, bending, actin, integrins, area constraint, minus the residual),
+    then A = (f - damp M rho V) / (M rho) and V = V_hlf + (dt_real - dt/2) A, for every node and component of steps 20-22 of k1.
+    The quotient form is bit-identical to an IEEE division; the reciprocal forms stay within 2 ulps."""
+    from oracle.oracle import OracleSim
+    xc, tc, xs, ts = meshes
+    o = OracleSim("k1", xc, tc, xs, ts); o.srand(1)
+    p = o.params
+    t = 0.0; dt = 0.005
+    worst = [0.0, 0.0, 0.0]
+    for k in range(23):
+        V0 = o.get(0, "V"); A0 = o.get(0, "A")
+        o.step(dt, t); t += dt
+        if k < 20:
+            continue
+        Vh = V0 + (dt / 2.0) * A0; Vh[:, 2] = 0.0                                   # UL:118-120
+        ff = {n: o.step_force_field(n) for n in ["Res_cell", "F_FA", "F_AP", "F_bend", "F_area"]}
+        f = -p.drag * Vh + ff["F_bend"]["F"] + ff["F_AP"]["F"] + ff["F_FA"]["F"] + ff["F_area"]["F"] - ff["Res_cell"]["F"]   # UL:568-592
+        MM = ff["Res_cell"]["MM"]
+        V1 = o.get(0, "V"); A1 = o.get(0, "A")
+        out = np.zeros(6)
+        for i in range(len(xc)):
+            for c in range(3):
+                hm.hm_node_update(C.c_double(f[i, c]), C.c_double(MM[i]), C.c_double(p.damp), C.c_double(p.rho), C.c_double(dt), C.c_double(dt),
+                                  C.c_double(Vh[i, c]), C.c_double(V0[i, c]), C.c_double(A0[i, c]), d(out))
+                assert out[0] == V1[i, c] and out[1] == A1[i, c], (k, i, c)          # the division-free quotient is an IEEE division
+                for q in (1, 2):
+                    sa = max(abs(A1[i, c]), 1e-300)
+                    worst[q] = max(worst[q], abs(out[2 * q + 1] - A1[i, c]) / sa)
+    assert worst[1] == 0.0 and worst[2] < 5e-16, worst
